@@ -1,0 +1,26 @@
+# Builds libseqkit_b200.so (sm_100a only) and the host `fasta` binary in-tree.
+NVCC ?= /usr/local/cuda/bin/nvcc
+ARCH := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -diag-suppress 186
+CSRC := seqkit_b200/csrc
+LIB := seqkit_b200/libseqkit_b200.so
+OBJ := $(CSRC)/sk_kernels.o $(CSRC)/sk_api.o $(CSRC)/sk_synth.o
+
+all: $(LIB) seqkit_b200/fasta oracle
+
+$(CSRC)/%.o: $(CSRC)/%.cu $(CSRC)/sk_internal.h include/seqkit_b200.h
+	$(NVCC) $(NVFLAGS) -c $< -o $@
+
+$(LIB): $(OBJ)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJ) -ldl
+
+seqkit_b200/fasta: seqkit_b200/host/fasta_main.cpp $(LIB) include/seqkit_b200.h
+	g++ -O2 -std=c++17 -Wall -Iinclude -o $@ $< -Lseqkit_b200 -lseqkit_b200 -Wl,-rpath,'$$ORIGIN' -lpthread
+
+oracle:
+	$(MAKE) -s -C oracle all
+
+clean:
+	rm -f $(OBJ) $(LIB) seqkit_b200/fasta
+	$(MAKE) -s -C oracle clean
+.PHONY: all oracle clean

@@ -1,0 +1,207 @@
+/*
+ * seqkit_b200.h -- C ABI of libseqkit_b200.so: the B200 (sm_100a) implementation of
+ * annalam/seqkit's per-read FASTQ batch path.
+ *
+ * The reference has no plugin/FFI interface: every operator is the body of a `main()` that
+ * calls `FileReader::read_line` four times per record and prints.  This header
+ * is the boundary a Rust `-sys` crate (or the C++ host binary in seqkit_b200/host/) binds: the
+ * host batcher fills pinned multi-MB buffers with raw FASTQ bytes, hands them to a *slot*, and
+ * gets back output bytes plus small tables.  Plain C types only; no exceptions cross it.
+ *
+ * Each entry point cites the reference code it replaces (paths relative to
+ * /root/reference/src/).  There is NO CPU fallback behind any of them: without a CUDA device
+ * sk_ctx_create fails with SK_E_CUDA.
+ */
+#ifndef SEQKIT_B200_H
+#define SEQKIT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SK_ABI_VERSION 1
+
+/* ---- API return codes (every function returning int) ------------------------------------- */
+#define SK_OK 0
+#define SK_E_INVALID (-1)     /* bad argument / call order */
+#define SK_E_CUDA (-2)        /* CUDA error or no device; text in sk_last_error */
+#define SK_E_NOMEM (-3)
+#define SK_E_TOO_LARGE (-4)   /* input larger than the slot capacity given to sk_ctx_create */
+#define SK_E_NO_SHEET (-5)    /* sk_demux before sk_set_sheet */
+#define SK_E_UNSUPPORTED (-6) /* e.g. sheet alphabet/length outside what the matcher packs */
+
+/* ---- data outcomes: sk_result.status -------------------------------------------------------
+ * Conditions the reference treats as fatal while streaming.  The kernels process every record
+ * with index < err_record exactly as the reference would have before stopping, so the host
+ * prints the reference's message AFTER flushing that output (same observable order). */
+#define SK_DATA_OK 0
+#define SK_DATA_BAD_HEADER 1      /* line 0 lacks '@'  (fasta_trim_by_quality.rs:20, fasta_mask_by_quality.rs:21, fasta_demultiplex.rs:118) */
+#define SK_DATA_LEN_MISMATCH 2    /* mask: seq/qual length differ (fasta_mask_by_quality.rs:35-37) */
+#define SK_DATA_SEQ_SHORT 3       /* trim: &seq[..k] out of range -> Rust panic, status 101 (fasta_trim_by_quality.rs:47) */
+#define SK_DATA_NO_BC 4           /* demux: no " BC:x" field (fasta_demultiplex.rs:141) */
+#define SK_DATA_BC_LEN 5          /* demux: barcode length != sheet (fasta_demultiplex.rs:148-150) */
+#define SK_DATA_INDEX_ASSERT 6    /* demux --index: '@' / '+' assertion -> panic 101 (fasta_demultiplex.rs:130,134) */
+#define SK_DATA_BAD_FASTX_LINE 7  /* add barcode: header is neither '@' nor '>' (fasta_add_barcode.rs:41-43) */
+/* Inputs this implementation refuses instead of guessing: */
+#define SK_DATA_NON_ASCII 32      /* a byte >= 0x80 in the batch */
+#define SK_DATA_RECORD_TOO_LONG 33
+#define SK_DATA_CHUNK_TOO_DENSE 34
+#define SK_DATA_MIXED_FORMAT 35   /* '@' and '>' records mixed in one add-barcode input */
+#define SK_DATA_OUT_OVERFLOW 36   /* output capacity of the slot exceeded */
+#define SK_DATA_TRUNCATED_FUSED 37 /* fused trim+demux on a header line without '\n' */
+
+/* sk_result.flags */
+#define SK_FLAG_MATE_COUNT 1u      /* mate/index streams hold fewer records than stream 0 */
+#define SK_FLAG_EVENTS_OVERFLOW 2u /* more ambiguity events than the slot can hold */
+
+/* stream indices inside a slot */
+#define SK_IN_R1 0    /* reads / mate 1            (<fastq_file>, <fastq_1>) */
+#define SK_IN_R2 1    /* mate 2                    (<fastq_2>) */
+#define SK_IN_AUX1 2  /* --index1 FASTQ, or the <barcode_file> of `add barcode` */
+#define SK_IN_AUX2 3  /* --index2 FASTQ */
+#define SK_N_INPUTS 4
+
+typedef struct sk_ctx sk_ctx;
+
+typedef struct sk_limits {
+    uint64_t max_stream_bytes; /* capacity of each input stream of a slot (< 4 GiB) */
+    uint64_t max_records;      /* records (pairs) per batch */
+    uint32_t n_slots;          /* independent stream slots for H2D / kernel / D2H overlap (>= 1) */
+    uint32_t max_samples;      /* largest sample sheet (0 = no demultiplexing) */
+    uint32_t aux_streams;      /* 0: allocate only R1/R2; 1: also AUX1/AUX2 (index reads, barcode file) */
+    uint32_t reserved;
+} sk_limits;
+
+typedef struct sk_result {
+    int32_t status;       /* SK_DATA_* of the first failing record, else SK_DATA_OK */
+    uint32_t flags;       /* SK_FLAG_* */
+    uint64_t err_record;  /* record index at which `status` was raised */
+    uint64_t n_records;   /* records processed (min of records present and rec_limit) */
+    uint64_t n_lines[SK_N_INPUTS];
+    uint64_t consumed[SK_N_INPUTS]; /* bytes of each input covered by the processed records */
+    uint64_t out_bytes[2];          /* payload bytes written per output stream */
+    uint64_t out_extent[2];         /* extent of the output buffer in use (demux chunks are 16 B aligned) */
+    uint64_t total_reads;           /* fasta_demultiplex.rs:108,169 */
+    uint64_t identified_reads;      /* fasta_demultiplex.rs:109,177 */
+    uint32_t n_chunks[2];           /* rows of the demux slice table per output stream */
+    uint32_t n_events;              /* ambiguity events (fasta_demultiplex.rs:184-188) */
+    uint32_t gpu_launches;          /* kernels this call enqueued */
+    uint32_t reserved;
+} sk_result;
+
+/* One "equally good match" occurrence; the host prints the WARNING (fasta_demultiplex.rs:184-188)
+ * in record order.  Header route: bc_off = byte offset of the observed barcode in SK_IN_R1 and
+ * bc_off2 = 0xFFFFFFFF.  --index route: bc_off / bc_off2 = byte offsets of the sequence lines of the
+ * first / second index read in their streams (0xFFFFFFFF when absent). */
+typedef struct sk_event {
+    uint32_t record;
+    uint32_t bc_off;
+    uint32_t bc_off2;
+    int16_t best_sample;
+    int16_t equally_fine_sample;
+    uint32_t mismatches;
+} sk_event;
+
+typedef struct sk_demux_opts {
+    int32_t fused_trim_min_baseq; /* -1: plain demultiplex; 0..255: trim by quality first (north-star config 5) */
+    uint32_t use_index;           /* bit0: AUX1 holds --index1, bit1: AUX2 holds --index2 */
+    uint64_t rec_limit;           /* process only records < rec_limit (0 = all; --dry-run=N / error replay) */
+    uint32_t no_output;           /* 1: count only (dry run, fasta_demultiplex.rs:77-78,179) */
+    uint32_t reserved;
+} sk_demux_opts;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int sk_abi_version(void);
+/* Allocates device buffers, streams and tables for `lim` on CUDA device `device`. */
+int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out);
+void sk_ctx_destroy(sk_ctx *ctx);
+const char *sk_last_error(const sk_ctx *ctx); /* ctx may be NULL: last create failure */
+/* cudaStream_t of a slot (so callers can record their own events on it). */
+void *sk_slot_stream(sk_ctx *ctx, uint32_t slot);
+
+/* ---- inputs ------------------------------------------------------------------------------- */
+/* Device address / capacity of an input stream buffer (for producers that write on the device). */
+void *sk_slot_in(sk_ctx *ctx, uint32_t slot, uint32_t which);
+uint64_t sk_slot_in_capacity(sk_ctx *ctx, uint32_t slot, uint32_t which);
+/* Async H2D of `n` raw FASTQ bytes (pin `host` for overlap); replaces FileReader (common.rs:88-112). */
+int sk_upload(sk_ctx *ctx, uint32_t slot, uint32_t which, const void *host, uint64_t n);
+/* Declare the length of an input already resident in the slot buffer (n = 0 clears the stream). */
+int sk_set_input_len(sk_ctx *ctx, uint32_t slot, uint32_t which, uint64_t n);
+
+/* ---- sample sheet ------------------------------------------------------------------------- */
+/* `barcodes` = S rows of L raw bytes in sheet order (Sample.barcode, fasta_demultiplex.rs:23-28,63-95).
+ * Packs them into bit-planes for the matcher that replaces barcode_diff (fasta_demultiplex.rs:269-277). */
+int sk_set_sheet(sk_ctx *ctx, const uint8_t *barcodes, uint32_t S, uint32_t L);
+
+/* ---- operators (async on the slot's stream; results via sk_wait) --------------------------- */
+/* fasta_trim_by_quality.rs:10-50 on SK_IN_R1 -> output stream 0. */
+int sk_trim_by_quality(sk_ctx *ctx, uint32_t slot, uint32_t min_baseq, uint64_t rec_limit);
+/* fasta_mask_by_quality.rs:11-47 on SK_IN_R1 -> output stream 0. */
+int sk_mask_by_quality(sk_ctx *ctx, uint32_t slot, uint32_t min_baseq, uint64_t rec_limit);
+/* fasta_add_barcode.rs:11-45: SK_IN_R1 = <fastq_file>, SK_IN_AUX1 = <barcode_file> -> output stream 0. */
+int sk_add_barcode(sk_ctx *ctx, uint32_t slot, uint64_t rec_limit);
+/* fasta_demultiplex.rs:117-249: SK_IN_R1 (+SK_IN_R2, +AUX index reads) -> output streams 0/1,
+ * slice tables, counters, events. */
+int sk_demultiplex(sk_ctx *ctx, uint32_t slot, const sk_demux_opts *opts);
+
+/* Blocks until the slot's stream is idle and returns the outcome of the last operator. */
+int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res);
+
+/* ---- outputs ------------------------------------------------------------------------------ */
+/* Device address of output stream `which` (0/1) of the last operator. */
+const void *sk_out_dev(sk_ctx *ctx, uint32_t slot, uint32_t which);
+/* D2H of the first `n` bytes of an output stream (call after sk_wait, or with n = capacity bound
+ * before it; the copy is ordered on the slot's stream). */
+int sk_download_out(sk_ctx *ctx, uint32_t slot, uint32_t which, void *host, uint64_t n);
+
+/* Demultiplex side tables (valid after sk_wait).  For output stream m, chunk c, sample s the
+ * slice is  [chunk_base[c] + sum_{t<s} lens[c*S+t],  + lens[c*S+s])  inside output stream m;
+ * concatenating a sample's slices over c = 0..n_chunks-1 gives that sample's file content in
+ * input order (fasta_demultiplex.rs:196-238). */
+int sk_download_demux_tables(sk_ctx *ctx, uint32_t slot, uint32_t which, uint64_t *chunk_base /*[n_chunks]*/,
+                             uint16_t *lens /*[n_chunks*S]*/);
+/* counts[0..S) = Sample.total_reads (:27,178), counts[S] = total_reads, counts[S+1] = identified_reads. */
+int sk_download_counts(sk_ctx *ctx, uint32_t slot, uint64_t *counts /*[S+2]*/);
+const void *sk_counts_dev(sk_ctx *ctx, uint32_t slot); /* device u64[S+2], for an in-place all-reduce */
+int sk_download_events(sk_ctx *ctx, uint32_t slot, sk_event *events, uint32_t cap); /* sorted by record */
+/* Per-record sample assignment of the last sk_demultiplex: >=0 sample, -1 no match, -2 ambiguous. */
+int sk_download_assign(sk_ctx *ctx, uint32_t slot, int16_t *assign, uint64_t n_records);
+
+/* Host helper: appends sample `s`'s slices (host copies of one output stream and its tables) to
+ * `dst`; returns the number of bytes written, or the required size when dst_cap is too small. */
+uint64_t sk_demux_gather(const uint8_t *out_host, const uint64_t *chunk_base, const uint16_t *lens, uint32_t n_chunks,
+                         uint32_t S, uint32_t s, uint8_t *dst, uint64_t dst_cap);
+
+/* ---- multi-GPU ---------------------------------------------------------------------------- */
+/* Sums the S+2 counters of this slot across ranks in place with one ncclAllReduce(sum, u64) on the
+ * slot's stream.  `nccl_comm` is an ncclComm_t created by the caller; the only collective on the
+ * path. */
+int sk_allreduce_counts(sk_ctx *ctx, uint32_t slot, void *nccl_comm);
+
+/* ---- synthetic workloads (bench / tests) ------------------------------------ */
+typedef struct sk_synth_spec {
+    uint64_t seed;
+    uint64_t first_pair;     /* global index of the first pair (shards regenerate any range) */
+    uint64_t n_pairs;
+    uint32_t read_len;       /* bases per read (150) */
+    uint32_t mate;           /* 1 or 2 */
+    uint32_t with_bc;        /* append " BC:<observed barcode>" to the header */
+    uint32_t qual_profile;   /* 0: 3'-decaying + 5% crash, 1: RTA3 4-bin variant */
+    uint32_t p_sub_ppm;      /* per-base substitution rate of the observed barcode */
+    uint32_t p_n_ppm;        /* per-base N rate of the observed barcode */
+    uint32_t p_random_ppm;   /* fraction of fully random barcodes */
+    uint32_t reserved;
+} sk_synth_spec;
+/* Writes FASTQ text for `spec` into input stream `which` of the slot (on the device) and sets its
+ * length; observed barcodes are drawn from the sheet given to sk_set_sheet.  Returns bytes via *n. */
+int sk_synth_fastq(sk_ctx *ctx, uint32_t slot, uint32_t which, const sk_synth_spec *spec, uint64_t *n);
+/* D2H copy of an input stream (to hand the same bytes to the CPU oracle). */
+int sk_download_in(sk_ctx *ctx, uint32_t slot, uint32_t which, void *host, uint64_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEQKIT_B200_H */

@@ -1,0 +1,231 @@
+"""Parity tests proper (-m gpu): every operator goes through the C ABI (libseqkit_b200.so) and is
+compared byte for byte with the CPU oracle on the same seeded inputs, with the committed golden
+fixtures, and -- at sizes the oracle cannot reach -- through size-independent properties."""
+import random
+
+import pytest
+
+import fuzzgen as G
+import golden_util as GU
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from seqkit_b200 import Engine
+    e = Engine(max_stream_bytes=48 << 20, max_records=1 << 18, max_samples=512)
+    yield e
+    e.close()
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import pyoracle
+    return pyoracle
+
+
+def fq(qual, seq=None, hdr=b"@r"):
+    seq = seq if seq is not None else b"A" * len(qual)
+    return hdr + b"\n" + seq + b"\n+\n" + qual + b"\n"
+
+
+def check3(a, b, ctx=None):
+    assert a[0] == b[0], ctx
+    assert a[1] == b[1], ctx
+    if a[0] != 101:
+        assert a[2] == b[2], ctx
+
+
+def test_native_library_is_the_path(eng):
+    import ctypes
+    from seqkit_b200 import LIB_PATH
+    assert LIB_PATH.endswith("libseqkit_b200.so")
+    assert isinstance(eng.lib, ctypes.CDLL)
+
+
+@pytest.mark.parametrize("qual,kept", [(b"IIIIIIIIII", 10), (b"IIIIIII###", 7), (b"##########", 0), (b"IIII#IIII#", 9),
+                                       (b"III#I#I#I#", 9), (b"IIIIII5555", 10), (b"IIIIIIII4", 8), (b"I", 1), (b"#", 0),
+                                       (b"", 0)])
+def test_trim_kats(eng, qual, kept):
+    seq = bytes(b"ACGT"[i % 4] for i in range(len(qual)))
+    code, out, err = eng.trim_by_quality(fq(qual, seq), 20)
+    assert code == 0 and err == b""
+    assert out == (b"@r\nN\n+\n!\n" if kept == 0 else b"@r\n" + seq[:kept] + b"\n+\n" + qual[:kept] + b"\n")
+
+
+def test_mask_kat_and_error_paths(eng, O):
+    assert eng.mask_by_quality(b"@h x\nACGTA\n+junk\nI#5 4\n", 20) == (0, b"@h x\nANGTN\n+\nI#5 4\n", b"")
+    for data in (fq(b"IIII") + b"\n", fq(b"IIII") + b"@x\nAC\n+\nIII\n", b"@p\nAC\n+\nIIIII\n", b"@t", b"@t\nACG", b"",
+                 b"\n", b"@a\n", b"@a\nAC\n+", fq(b"II") * 3 + b"X\n"):
+        for q in (20, 0, 255):
+            check3(eng.trim_by_quality(data, q), O.trim_by_quality(data, q), (data, q))
+            check3(eng.mask_by_quality(data, q), O.mask_by_quality(data, q), (data, q))
+
+
+def test_golden_stream_ops(eng):
+    n = 0
+    for c in GU.cases():
+        if c["op"] == "demux":
+            continue
+        if c["op"] == "trim":
+            got = eng.trim_by_quality(GU.blob(c["input"]), c["min_baseq"])
+        elif c["op"] == "mask":
+            got = eng.mask_by_quality(GU.blob(c["input"]), c["min_baseq"])
+        else:
+            got = eng.add_barcode(GU.blob(c["input"]), GU.blob(c["barcodes"]))
+        assert got[0] == c["exit_code"], c["tag"]
+        assert got[1] == GU.blob(c["stdout"]), c["tag"]
+        if got[0] != 101:
+            assert got[2] == GU.blob(c["stderr"]), c["tag"]
+        n += 1
+    assert n > 50
+
+
+def test_golden_demux(eng):
+    for c in GU.cases("demux"):
+        res = eng.demultiplex(GU.blob(c["sheet"]), GU.blob(c["r1"]), GU.blob(c["r2"]))
+        assert res["exit_code"] == c["exit_code"], c["tag"]
+        assert res["stderr"] == GU.blob(c["stderr"]), c["tag"]
+        assert res["counts"] == c["counts"] and res["total"] == c["total"] and res["identified"] == c["identified"]
+        assert set(res["files"]) == set(c["files"])
+        for k, v in c["files"].items():
+            assert res["files"][k] == GU.blob(v), (c["tag"], k)
+
+
+def test_fuzz_stream_ops_vs_oracle(eng, O):
+    rng = random.Random(2024)
+    for it in range(120):
+        n = rng.choice((0, 1, 2, 7, 40, 300))
+        data = G.nasty_fastq(rng.randrange(1 << 30), n) if it % 3 else G.clean_fastq(rng.randrange(1 << 30), n, qual_style="mix")
+        q = rng.choice((0, 2, 10, 20, 30, 41, 93, 200, 255))
+        check3(eng.trim_by_quality(data, q), O.trim_by_quality(data, q), ("trim", it, q))
+        check3(eng.mask_by_quality(data, q), O.mask_by_quality(data, q), ("mask", it, q))
+        bc = G.index_reads(rng.randrange(1 << 30), rng.choice((0, 1, n, n + 3, max(n - 2, 0))), [b"ACGT", b"GG+TT", b"ACGTACGTAC"])
+        check3(eng.add_barcode(data, bc), O.add_barcode(data, bc), ("addbc", it))
+
+
+def test_add_barcode_fasta_and_reuse(eng, O):
+    fa = b">s1 desc\nACGT\n>s2\nGGCC\n>s3\nTT\n"
+    for bc in (b">b\nAA\n>b\nCC\n", b">b\nAA\n", b"", b"@x\nACGT+TTAA\n+\nIIIIIIIII\n@y\nGGGG\n+\nIIII\n", b"junk\nlines\n"):
+        check3(eng.add_barcode(fa, bc), O.add_barcode(fa, bc), bc)
+    check3(eng.add_barcode(b">s\nACGT\nbad\n", b">b\nAA\n>b\nCC\n"), O.add_barcode(b">s\nACGT\nbad\n", b">b\nAA\n>b\nCC\n"))
+
+
+def _cmp_demux(a, b, ctx=None):
+    assert a["exit_code"] == b["exit_code"], ctx
+    if a["exit_code"] != 101:
+        assert a["stderr"] == b["stderr"], ctx
+    assert a["files"] == b["files"], ctx
+    if a["exit_code"] == 0:
+        assert a["counts"] == b["counts"] and a["total"] == b["total"] and a["identified"] == b["identified"], ctx
+
+
+def test_demux_kats(eng, O):
+    sheet = b"A\tACGTACGT\nB\tACGTACGA\n"
+    rec = lambda name, bc: b"@%s BC:%s\nAC\n+\nII\n" % (name, bc)
+    cases = [
+        (sheet, rec(b"r1", b"ACGTACGC") + rec(b"r2", b"ACGTACGT") + rec(b"r3", b"NCGTACGT"), None, {}),
+        (b"X\tACGTUUUU\n", rec(b"u1 1:N", b"ACGTTTGA"), b"@u1 2:N BC:ACGTTTGA\nGG\n+\nII\n", {}),
+        (b"P\tACGT\nQ\tACGT\n", rec(b"d", b"ACGT"), None, {}),
+        (sheet, b"@x\nA\n+\nI\n", None, {}),
+        (sheet, rec(b"ok", b"ACGTACGT") + rec(b"x", b"ACG"), None, {}),
+        (b"A\tAC\nA\tGG\n", b"", None, {}),
+        (b"S\tAC+GT\n", b"@r BC:zz\nAC\n+\nII\n", None, {"index1": b"@i\nAC\n+\nII\n", "index2": b"@i\nGT\n+\nII\n"}),
+        (sheet, rec(b"ok", b"ACGTACGT") + b"bad\nAC\n+\nII\n", None, {}),
+    ]
+    for sh, r1, r2, kw in cases:
+        _cmp_demux(eng.demultiplex(sh, r1, r2, **kw), O.demultiplex(sh, r1, r2, **kw), (sh, r1))
+
+
+def test_fuzz_demux_vs_oracle(eng, O):
+    rng = random.Random(99)
+    for it in range(60):
+        S = rng.choice((1, 2, 3, 8, 20, 96))
+        Lb = rng.choice((4, 6, 8, 12, 20))
+        umi = rng.choice((0, 0, 3, 8))
+        sheet, bcs = G.make_sheet(rng.randrange(1 << 30), S, Lb, umi=umi, dual=rng.random() < 0.3,
+                                  min_dist=rng.choice((0, 1, 2, 3)), wild_n=rng.choice((0, 0, 0.1)))
+        n = rng.choice((0, 1, 5, 60, 400))
+        if it % 2:
+            r1, r2 = G.nasty_headers_pairs(rng.randrange(1 << 30), n, bcs)
+        else:
+            r1, r2 = G.clean_pairs(rng.randrange(1 << 30), n, bcs, p_sub=0.1, p_n=0.05, p_random=0.1, p_lower=0.02,
+                                   bc_in_r2=rng.random() < 0.5)
+        for paired in (True, False):
+            _cmp_demux(eng.demultiplex(sheet, r1, r2 if paired else None), O.demultiplex(sheet, r1, r2 if paired else None),
+                       ("it", it, paired))
+
+
+def test_demux_index_route(eng, O):
+    rng = random.Random(5)
+    for it in range(8):
+        sheet, bcs = G.make_sheet(100 + it, 12, 16, umi=rng.choice((0, 4)), dual=True)
+        n = rng.choice((1, 30, 200))
+        r1, r2 = G.clean_pairs(200 + it, n, bcs, bc_in_r2=False)
+        lit = [b.rstrip(b"U") for b in bcs]
+        half1 = [b.split(b"+")[0] for b in lit]
+        half2 = [b.split(b"+")[1] for b in lit]
+        i1 = G.index_reads(300 + it, n, half1, p_sub=0.03)
+        i2 = G.index_reads(400 + it, n, half2, p_sub=0.03)
+        if rng.random() < 0.5 and bcs[0].endswith(b"U"):
+            # UMI bases ride at the end of the second index read
+            i2 = b"".join(b"@i\n" + rec.split(b"\n")[1] + b"ACGT"[:len(bcs[0]) - len(lit[0])] + b"\n+\nIIII\n"
+                          for rec in i2.split(b"@")[1:])
+        _cmp_demux(eng.demultiplex(sheet, r1, r2, index1=i1, index2=i2), O.demultiplex(sheet, r1, r2, index1=i1, index2=i2), it)
+
+
+def test_fused_trim_demux_equals_composition(eng, O):
+    """North-star config 5: fused trim+demux == demultiplex(trim(R1), trim(R2)) of the reference."""
+    for seed in range(4):
+        sheet, bcs = G.make_sheet(seed, 24, 20, umi=8, dual=True)
+        r1, r2 = G.clean_pairs(50 + seed, 300, bcs, qual_style="decay")
+        t1, t2 = O.trim_by_quality(r1, 20), O.trim_by_quality(r2, 20)
+        assert t1[0] == 0 and t2[0] == 0
+        want = O.demultiplex(sheet, t1[1], t2[1])
+        got = eng.demultiplex(sheet, r1, r2, fused_trim=20)
+        _cmp_demux(got, want, seed)
+
+
+def test_large_synthetic_multi_chunk(eng, O):
+    """~60 MB per stream: thousands of chunks, so the look-back chains and the demux slice tables
+    are exercised for real; the oracle still finishes in seconds."""
+    sheet, bcs = G.make_sheet(7, 96, 8)
+    eng.set_sheet(bcs)
+    n = 120_000
+    n1 = eng.synth(0, n, seed=11, mate=1, with_bc=True)
+    r1 = eng.download_in(0, n1)
+    n2 = eng.synth(1, n, seed=11, mate=2, with_bc=True)
+    r2 = eng.download_in(1, n2)
+    assert r1.count(b"\n") == 4 * n and r2.count(b"\n") == 4 * n
+    check3(eng.trim_by_quality(r1, 20), O.trim_by_quality(r1, 20), "trim-large")
+    check3(eng.mask_by_quality(r1, 20), O.mask_by_quality(r1, 20), "mask-large")
+    _cmp_demux(eng.demultiplex(sheet, r1, r2), O.demultiplex(sheet, r1, r2), "demux-large")
+    t1, t2 = O.trim_by_quality(r1, 20), O.trim_by_quality(r2, 20)
+    _cmp_demux(eng.demultiplex(sheet, r1, r2, fused_trim=20), O.demultiplex(sheet, t1[1], t2[1]), "fused-large")
+
+
+def test_dual_index_umi_384_samples(eng, O):
+    """Config-4 shape: 384 samples, i7(10)+i5(10)+UMI(8) = 29-character sheet barcodes."""
+    sheet, bcs = G.make_sheet(4, 384, 20, umi=8, dual=True)
+    eng.set_sheet(bcs)
+    n = 40_000
+    n1 = eng.synth(0, n, seed=4, mate=1, with_bc=True)
+    r1 = eng.download_in(0, n1)
+    n2 = eng.synth(1, n, seed=4, mate=2, with_bc=True)
+    r2 = eng.download_in(1, n2)
+    _cmp_demux(eng.demultiplex(sheet, r1, r2), O.demultiplex(sheet, r1, r2), "cfg4")
+
+
+def test_properties_at_scale(eng):
+    """Size-independent checks on a batch too big for a byte-for-byte oracle run in the test budget:
+    mask keeps every byte count, trim output re-trims to itself (idempotence), demux conserves reads."""
+    n = 200_000
+    n1 = eng.synth(0, n, seed=3, mate=1)
+    data = eng.download_in(0, n1)
+    code, masked, _ = eng.mask_by_quality(data, 20)
+    assert code == 0 and len(masked) == len(data) and masked.count(b"\n") == data.count(b"\n")
+    code, trimmed, _ = eng.trim_by_quality(data, 20)
+    assert code == 0 and trimmed.count(b"\n") == 4 * n
+    code2, again, _ = eng.trim_by_quality(trimmed, 20)
+    assert code2 == 0 and again.count(b"\n") == 4 * n and len(again) <= len(trimmed)
