@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the per-read FASTQ batch path on B200.
+
+Workload (BASELINE.json configs[4], the config the metric is quoted on): fused
+trim-by-quality (Q20) + demultiplex of paired-end 2x150 bp reads against a 384-sample dual-index
+sheet (10+10 bp, literal '+', 8 bp UMI -> 29-character barcodes), synthetic FASTQ generated on the
+device.  The 1 B-pair job does not fit any memory, so it is streamed: a "step" is one batch of
+`--pairs` read pairs per GPU (weak scaling: every rank processes its own contiguous pair range).
+
+  value     reads/s over all ranks with inputs resident in HBM (CUDA events on the kernels' stream)
+  e2e       the same metric through the C ABI with HOST buffers: pinned H2D upload, kernels, D2H of
+            outputs + tables, 3 slots in flight
+  roofline  algorithmic bytes (input once + output once) / average device time of the dominant
+            kernel, against MEASURED_PEAKS.json
+  cpu_baseline  the CPU oracle (port of the reference; the Rust reference cannot be built here)
+
+`--impl reference` times that oracle on all host cores instead (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import random
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+READ_LEN = 150
+MIN_BASEQ = 20
+N_SAMPLES = 384
+
+
+def make_sheet(n_samples=N_SAMPLES, seed=2024):
+    """i7(10)+i5(10)+UMI(8): 20 literal bases with pairwise Hamming distance >= 3."""
+    rng = random.Random(seed)
+    codes = []
+    while len(codes) < n_samples:
+        c = bytes(rng.choice(b"ACGT") for _ in range(20))
+        if all(sum(a != b for a, b in zip(c, d)) >= 3 for d in codes):
+            codes.append(c)
+    return [c[:10] + b"+" + c[10:] + b"U" * 8 for c in codes]
+
+
+def sheet_text(bcs):
+    return b"".join(b"S%03d\t%s\n" % (i, b) for i, b in enumerate(bcs))
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons of one GPU while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        try:
+            p = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                  "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+        except Exception:
+            return
+        self.proc = p
+        for line in p.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+            if self.stop_flag:
+                break
+        p.terminate()
+
+    def finish(self):
+        self.stop_flag = True
+        time.sleep(0.15)
+        if hasattr(self, "proc"):
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except Exception:
+                continue
+            for k, nm in enumerate(names):
+                if len(r) > 2 + k and r[2 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def _oracle_shard(args):
+    sheet, r1, r2 = args
+    from oracle import pyoracle as O
+    t1, t2 = O.trim_by_quality(r1, MIN_BASEQ), O.trim_by_quality(r2, MIN_BASEQ)
+    res = O.demultiplex(sheet, t1[1], t2[1])
+    return res["identified"]
+
+
+def cut_pairs(buf: bytes, n_pairs: int, parts: int):
+    """Splits a FASTQ buffer of n_pairs records into `parts` pieces at record boundaries."""
+    lines = buf.split(b"\n")
+    per = (n_pairs + parts - 1) // parts
+    out = []
+    for k in range(parts):
+        seg = lines[4 * k * per:4 * min((k + 1) * per, n_pairs)]
+        if seg:
+            out.append(b"\n".join(seg) + b"\n")
+    return out
+
+
+def time_oracle(sheet, r1, r2, n_pairs, procs, steps, warmup):
+    """Oracle = fasta demultiplex sheet <(fasta trim by quality R1 20) <(fasta trim by quality R2 20),
+    in memory, `procs` independent shards in parallel (the reference itself is single-threaded)."""
+    import multiprocessing as mp
+    from oracle import pyoracle as O
+    O.build()
+    s1, s2 = cut_pairs(r1, n_pairs, procs), cut_pairs(r2, n_pairs, procs)
+    jobs = [(sheet, a, b) for a, b in zip(s1, s2)]
+    times = []
+    if procs == 1:
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            _oracle_shard(jobs[0])
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            for it in range(warmup + steps):
+                t0 = time.perf_counter()
+                pool.map(_oracle_shard, jobs)
+                if it >= warmup:
+                    times.append(time.perf_counter() - t0)
+    dt = sum(times) / len(times)
+    return 2.0 * n_pairs / dt, dt
+
+
+def synth_pair(eng, n_pairs, first_pair, seed=5):
+    n1 = eng.synth(0, n_pairs, seed=seed, first_pair=first_pair, read_len=READ_LEN, mate=1, with_bc=True)
+    n2 = eng.synth(1, n_pairs, seed=seed, first_pair=first_pair, read_len=READ_LEN, mate=2, with_bc=True)
+    return n1, n2
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    from seqkit_b200 import Engine
+    bcs = make_sheet()
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 64))
+    n_pairs = args.ref_pairs_per_core * procs
+    with Engine(max_stream_bytes=n_pairs * 420 + (1 << 20), max_records=n_pairs, max_samples=N_SAMPLES,
+                aux_streams=False) as eng:  # input creation only: the timed path below is pure CPU
+        eng.set_sheet(bcs)
+        n1, n2 = synth_pair(eng, n_pairs, 0)
+        r1, r2 = eng.download_in(0, n1), eng.download_in(1, n2)
+    rps, dt = time_oracle(sheet_text(bcs), r1, r2, n_pairs, procs, args.steps, max(args.warmup, 1))
+    line = {
+        "impl": "reference", "metric": "reads_per_s", "value": rps, "unit": "reads/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "gbases_per_s": rps * READ_LEN / 1e9,
+        "config": workload_config(n_pairs, note="CPU arm: bounded sample of the same workload per step"),
+        "cpu_baseline": {"value": rps, "unit": "reads/s", "cores": procs, "kind": "port",
+                         "sample": "%d pairs per step, %d independent shards (oracle/fasta_oracle.c, in memory, no gzip)"
+                                   % (n_pairs, procs)},
+        "e2e": {"value": rps, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(pairs, note=None):
+    cfg = {"workload": "BASELINE configs[4]: fused trim-by-quality(Q%d)+demultiplex, paired-end 2x%d bp, %d samples, "
+                       "dual index 10+10 bp + 8 bp UMI (29-char barcodes incl. '+'), <=1 mismatch; 1B-pair job streamed "
+                       "in batches" % (MIN_BASEQ, READ_LEN, N_SAMPLES),
+           "pairs_per_gpu_per_step": pairs, "read_len": READ_LEN, "samples": N_SAMPLES, "min_baseq": MIN_BASEQ,
+           "l2": "inputs per step (>1 GB per stream) exceed the 126 MB L2; no flush needed"}
+    if note:
+        cfg["note"] = note
+    return cfg
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=8_000_000, help="read pairs per GPU per step (device-resident)")
+    ap.add_argument("--e2e-pairs", type=int, default=1_000_000, help="read pairs per host batch in the e2e leg")
+    ap.add_argument("--cpu-pairs", type=int, default=400_000, help="bounded sample for the 1-core CPU baseline")
+    ap.add_argument("--ref-pairs-per-core", type=int, default=100_000)
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from seqkit_b200 import Engine, _lib as L
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: seqkit_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    bcs = make_sheet()
+    P = args.pairs
+    steps, warm = args.steps, max(args.warmup, 3)
+    eng = Engine(device=local_rank, max_stream_bytes=P * 410 + (1 << 20), max_records=P, n_slots=1,
+                 max_samples=N_SAMPLES, aux_streams=False)
+    lib = eng.lib
+    eng.set_sheet(bcs)
+    n1, n2 = synth_pair(eng, P, rank * P)  # weak scaling: rank r owns pairs [r*P, (r+1)*P)
+    opts = L.DemuxOpts(MIN_BASEQ, 0, 0, 0, 0)
+    stream = torch.cuda.ExternalStream(lib.sk_slot_stream(eng.ctx, 0), device=local_rank)
+
+    def step():
+        rc = lib.sk_demultiplex(eng.ctx, 0, C.byref(opts))
+        if rc != 0:
+            raise RuntimeError("sk_demultiplex failed: %s" % lib.sk_last_error(eng.ctx).decode())
+
+    # the one collective of the path: per-sample counts merged over NVLink with a single NCCL all-reduce
+    comm = C.c_void_p()
+    if world > 1:
+        idbuf = torch.zeros(128, dtype=torch.uint8)
+        if rank == 0:
+            raw = C.create_string_buffer(128)
+            assert lib.sk_nccl_unique_id(eng.ctx, raw) == 0, lib.sk_last_error(eng.ctx)
+            idbuf = torch.frombuffer(bytearray(raw.raw), dtype=torch.uint8).clone()
+        idbuf = idbuf.cuda()
+        dist.broadcast(idbuf, 0)
+        raw = bytes(idbuf.cpu().numpy().tobytes())
+        assert lib.sk_nccl_comm_init(eng.ctx, raw, world, rank, C.byref(comm)) == 0, lib.sk_last_error(eng.ctx)
+
+    for _ in range(warm):
+        step()
+    res = eng.wait()
+    assert res.status == 0 and res.n_records == P, (res.status, res.n_records)
+    pairs_done = res.n_records
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(steps):
+        step()
+    if world > 1:
+        assert lib.sk_allreduce_counts(eng.ctx, 0, comm) == 0, lib.sk_last_error(eng.ctx)
+    ev1.record(stream)
+    barrier()
+    ms_total = ev0.elapsed_time(ev1)
+    res = eng.wait()
+    assert res.status == 0, res.status
+    launches = res.gpu_launches * steps
+    counts = (C.c_uint64 * (N_SAMPLES + 2))()
+    lib.sk_download_counts(eng.ctx, 0, counts)
+    if world > 1:
+        t = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        assert counts[N_SAMPLES] == P * world, "all-reduced total_reads must cover every rank"
+    clocks = sampler.finish()
+    ms_step = ms_total / steps
+    value = 2.0 * P * world / (ms_step * 1e-3)
+
+    # per-kernel device time (CUDA events around each launch, on the launching stream)
+    lib.sk_set_profiling(eng.ctx, 1)
+    pass_ms = [0.0, 0.0]
+    for _ in range(steps):
+        step()
+        r = eng.wait()
+        pass_ms[0] += r.pass_ms[0] / steps
+        pass_ms[1] += r.pass_ms[1] / steps
+    lib.sk_set_profiling(eng.ctx, 0)
+    bytes_pass = [n1 + res.out_bytes[0], n2 + res.out_bytes[1]]
+    dom = 0 if pass_ms[0] >= pass_ms[1] else 1
+    peak, peak_src = peaks()
+    achieved = bytes_pass[dom] / (pass_ms[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "sk_chunk_kernel<OP_DEMUX%d>" % (dom + 1), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": bytes_pass[dom], "ms_per_launch": pass_ms[dom],
+                "other_kernel": {"kernel": "sk_chunk_kernel<OP_DEMUX%d>" % (2 - dom), "ms_per_launch": pass_ms[1 - dom],
+                                 "achieved": bytes_pass[1 - dom] / (pass_ms[1 - dom] * 1e-3) / 1e9},
+                "step_bytes": sum(bytes_pass), "step_achieved": sum(bytes_pass) / (ms_step * 1e-3) / 1e9}
+    identified = counts[N_SAMPLES + 1]
+    out_bytes = [int(res.out_bytes[0]), int(res.out_bytes[1])]
+    eng.close()
+
+    # ---- e2e: host buffers through the C ABI, 3 slots in flight
+    e2e = None
+    if not args.skip_e2e:
+        e2e = run_e2e(args, torch, L, bcs, local_rank, rank, world, barrier)
+
+    # ---- CPU baseline (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        with Engine(device=local_rank, max_stream_bytes=args.cpu_pairs * 420 + (1 << 20), max_records=args.cpu_pairs,
+                    max_samples=N_SAMPLES, aux_streams=False) as e2:
+            e2.set_sheet(bcs)
+            m1, m2 = synth_pair(e2, args.cpu_pairs, 0)
+            r1, r2 = e2.download_in(0, m1), e2.download_in(1, m2)
+        rps, dt = time_oracle(sheet_text(bcs), r1, r2, args.cpu_pairs, 1, 1, 0)
+        cpu = {"value": rps, "unit": "reads/s", "cores": 1, "kind": "port",
+               "sample": "%d pairs (same generator), oracle/fasta_oracle.c trim x2 + demultiplex in memory, %.1f s"
+                         % (args.cpu_pairs, dt)}
+
+    if rank == 0:
+        line = {
+            "metric": "reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": steps, "warmup": warm,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "config": workload_config(P), "gbases_per_s": value * READ_LEN / 1e9,
+            "pairs_per_s": value / 2, "identified_fraction": identified / float(P * world),
+            "bytes_per_step_per_gpu": {"in": [n1, n2], "out": out_bytes},
+            "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, torch, L, bcs, local_rank, rank, world, barrier):
+    """Same metric through the reference-facing call with HOST buffers: every step uploads its
+    inputs from pinned memory, runs the kernels, and reads back outputs, slice tables and counters."""
+    from seqkit_b200 import Engine
+    Pe, nslots = args.e2e_pairs, 3
+    eng = Engine(device=local_rank, max_stream_bytes=Pe * 410 + (1 << 20), max_records=Pe, n_slots=nslots,
+                 max_samples=N_SAMPLES, aux_streams=False)
+    lib = eng.lib
+    eng.set_sheet(bcs)
+    n1, n2 = synth_pair(eng, Pe, rank * Pe, seed=9)
+    h_in = [torch.empty(n, dtype=torch.uint8).pin_memory() for n in (n1, n2)]
+    for w, t in enumerate(h_in):
+        assert lib.sk_download_in(eng.ctx, 0, w, t.data_ptr(), t.numel()) == 0
+    cap = max(n1, n2) + Pe * 16 + (1 << 20)
+    nchunks = (max(n1, n2) + 32767) // 32768 + 1
+    h_out = [[torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(2)] for _ in range(nslots)]
+    h_base = [[torch.empty(nchunks, dtype=torch.int64).pin_memory() for _ in range(2)] for _ in range(nslots)]
+    h_lens = [[torch.empty(nchunks * N_SAMPLES, dtype=torch.int16).pin_memory() for _ in range(2)] for _ in range(nslots)]
+    h_counts = [torch.empty(N_SAMPLES + 2, dtype=torch.int64).pin_memory() for _ in range(nslots)]
+    opts = L.DemuxOpts(MIN_BASEQ, 0, 0, 0, 0)
+    d2h = [0]
+
+    def submit(s):
+        assert lib.sk_upload(eng.ctx, s, 0, h_in[0].data_ptr(), n1) == 0
+        assert lib.sk_upload(eng.ctx, s, 1, h_in[1].data_ptr(), n2) == 0
+        assert lib.sk_demultiplex(eng.ctx, s, C.byref(opts)) == 0
+
+    def collect(s):
+        res = L.Result()
+        assert lib.sk_wait(eng.ctx, s, C.byref(res)) == 0 and res.status == 0
+        nb = 0
+        for m in range(2):
+            assert lib.sk_download_out(eng.ctx, s, m, h_out[s][m].data_ptr(), res.out_extent[m]) == 0
+            assert lib.sk_download_demux_tables(eng.ctx, s, m, h_base[s][m].data_ptr(), h_lens[s][m].data_ptr()) == 0
+            nb += res.out_extent[m] + res.n_chunks[m] * (8 + 2 * N_SAMPLES)
+        assert lib.sk_download_counts(eng.ctx, s, h_counts[s].data_ptr()) == 0  # syncs the slot
+        d2h[0] = nb + (N_SAMPLES + 2) * 8
+        return res
+
+    def run(k):
+        inflight = []
+        for i in range(k):
+            s = i % nslots
+            if len(inflight) == nslots:
+                collect(inflight.pop(0))
+            submit(s)
+            inflight.append(s)
+        for s in inflight:
+            collect(s)
+
+    run(3)
+    steps = max(args.steps, 6)
+    barrier()
+    t0 = time.perf_counter()
+    run(steps)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([dt], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    eng.close()
+    return {"value": 2.0 * Pe * world * steps / dt, "unit": "reads/s", "h2d_bytes_per_step": int(n1 + n2),
+            "d2h_bytes_per_step": int(d2h[0]), "pairs_per_step": Pe, "steps": steps, "slots": nslots,
+            "pcie_gbs": {"h2d": (n1 + n2) * steps / dt / 1e9, "d2h": d2h[0] * steps / dt / 1e9},
+            "note": "pinned host buffers -> sk_upload -> sk_demultiplex -> sk_download_out/tables/counts; gzip excluded"}
+
+
+if __name__ == "__main__":
+    main()

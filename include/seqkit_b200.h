@@ -90,6 +90,8 @@ typedef struct sk_result {
     uint32_t n_events;              /* ambiguity events (fasta_demultiplex.rs:184-188) */
     uint32_t gpu_launches;          /* kernels this call enqueued */
     uint32_t reserved;
+    float pass_ms[SK_N_INPUTS];     /* device time of the chunk-engine kernel over each input stream
+                                       (CUDA events on the slot's stream; only with sk_set_profiling) */
 } sk_result;
 
 /* One "equally good match" occurrence; the host prints the WARNING (fasta_demultiplex.rs:184-188)
@@ -121,6 +123,8 @@ void sk_ctx_destroy(sk_ctx *ctx);
 const char *sk_last_error(const sk_ctx *ctx); /* ctx may be NULL: last create failure */
 /* cudaStream_t of a slot (so callers can record their own events on it). */
 void *sk_slot_stream(sk_ctx *ctx, uint32_t slot);
+/* on != 0: bracket every kernel with CUDA events so that sk_wait can fill sk_result.pass_ms. */
+int sk_set_profiling(sk_ctx *ctx, int on);
 
 /* ---- inputs ------------------------------------------------------------------------------- */
 /* Device address / capacity of an input stream buffer (for producers that write on the device). */
@@ -180,6 +184,12 @@ uint64_t sk_demux_gather(const uint8_t *out_host, const uint64_t *chunk_base, co
  * slot's stream.  `nccl_comm` is an ncclComm_t created by the caller; the only collective on the
  * path. */
 int sk_allreduce_counts(sk_ctx *ctx, uint32_t slot, void *nccl_comm);
+/* Thin wrappers over ncclGetUniqueId / ncclCommInitRank / ncclCommDestroy (libnccl.so.2 is resolved at
+ * run time) so that a host without its own NCCL binding can build the communicator: rank 0 fills
+ * `id128` (128 bytes), every rank receives it out of band and calls sk_nccl_comm_init. */
+int sk_nccl_unique_id(sk_ctx *ctx, void *id128);
+int sk_nccl_comm_init(sk_ctx *ctx, const void *id128, int nranks, int rank, void **comm);
+int sk_nccl_comm_destroy(sk_ctx *ctx, void *comm);
 
 /* ---- synthetic workloads (bench / tests) ------------------------------------ */
 typedef struct sk_synth_spec {

@@ -32,7 +32,7 @@ class Result(C.Structure):
                 ("n_lines", C.c_uint64 * SK_N_INPUTS), ("consumed", C.c_uint64 * SK_N_INPUTS),
                 ("out_bytes", C.c_uint64 * 2), ("out_extent", C.c_uint64 * 2), ("total_reads", C.c_uint64),
                 ("identified_reads", C.c_uint64), ("n_chunks", C.c_uint32 * 2), ("n_events", C.c_uint32),
-                ("gpu_launches", C.c_uint32), ("reserved", C.c_uint32)]
+                ("gpu_launches", C.c_uint32), ("reserved", C.c_uint32), ("pass_ms", C.c_float * SK_N_INPUTS)]
 
 
 class Event(C.Structure):
@@ -59,6 +59,7 @@ SIGNATURES = {
     "sk_ctx_destroy": (None, [_P]),
     "sk_last_error": (C.c_char_p, [_P]),
     "sk_slot_stream": (_P, [_P, C.c_uint32]),
+    "sk_set_profiling": (C.c_int, [_P, C.c_int]),
     "sk_slot_in": (_P, [_P, C.c_uint32, C.c_uint32]),
     "sk_slot_in_capacity": (C.c_uint64, [_P, C.c_uint32, C.c_uint32]),
     "sk_upload": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.c_uint64]),
@@ -78,6 +79,9 @@ SIGNATURES = {
     "sk_download_assign": (C.c_int, [_P, C.c_uint32, _P, C.c_uint64]),
     "sk_demux_gather": (C.c_uint64, [_P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P, C.c_uint64]),
     "sk_allreduce_counts": (C.c_int, [_P, C.c_uint32, _P]),
+    "sk_nccl_unique_id": (C.c_int, [_P, _P]),
+    "sk_nccl_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "sk_nccl_comm_destroy": (C.c_int, [_P, _P]),
     "sk_synth_fastq": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(SynthSpec), C.POINTER(C.c_uint64)]),
     "sk_download_in": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.c_uint64]),
 }

@@ -51,6 +51,7 @@ struct Slot {
     uint32_t n_chunks[SK_N_INPUTS] = {0, 0, 0, 0};
     uint32_t launches = 0;
     bool pass_ran[SK_N_INPUTS] = {false, false, false, false};
+    cudaEvent_t ev[SK_N_INPUTS][2] = {};
 };
 
 struct sk_ctx {
@@ -60,6 +61,7 @@ struct sk_ctx {
     uint32_t max_chunks = 0;
     std::vector<Slot> slots;
     std::string err;
+    bool profiling = false;
     // sample sheet
     bool have_sheet = false;
     uint32_t S = 0, L = 0, Umax = 0, wide = 0;
@@ -102,6 +104,9 @@ static void free_slot(Slot &s) {
     cudaFree(s.counts);
     cudaFree(s.events);
     cudaFree(s.synth_tmp);
+    for (int i = 0; i < SK_N_INPUTS; i++)
+        for (int k = 0; k < 2; k++)
+            if (s.ev[i][k]) cudaEventDestroy(s.ev[i][k]);
     if (s.stream) cudaStreamDestroy(s.stream);
 }
 
@@ -164,6 +169,8 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
     ctx->slots.resize(lim->n_slots);
     for (auto &s : ctx->slots) {
         CKC(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        for (int i = 0; i < SK_N_INPUTS; i++)
+            for (int k = 0; k < 2; k++) CKC(cudaEventCreate(&s.ev[i][k]));
         const int nin = lim->aux_streams ? SK_N_INPUTS : 2;
         for (int i = 0; i < nin; i++) {
             CKC(cudaMalloc(&s.in[i], B + 64));
@@ -204,6 +211,11 @@ extern "C" void *sk_slot_stream(sk_ctx *ctx, uint32_t slot) {
     Slot *s = get_slot(ctx, slot);
     return s ? (void *)s->stream : nullptr;
 }
+extern "C" int sk_set_profiling(sk_ctx *ctx, int on) {
+    if (!ctx) return SK_E_INVALID;
+    ctx->profiling = on != 0;
+    return SK_OK;
+}
 extern "C" void *sk_slot_in(sk_ctx *ctx, uint32_t slot, uint32_t which) {
     Slot *s = get_slot(ctx, slot);
     return (s && which < SK_N_INPUTS) ? s->in[which] : nullptr;
@@ -241,7 +253,7 @@ extern "C" int sk_download_in(sk_ctx *ctx, uint32_t slot, uint32_t which, void *
 // sample sheet -> bit planes (replaces the byte loop of barcode_diff, fasta_demultiplex.rs:269-277)
 // ------------------------------------------------------------------------------------------------
 extern "C" int sk_set_sheet(sk_ctx *ctx, const uint8_t *barcodes, uint32_t S, uint32_t L) {
-    if (!ctx || (!barcodes && S * L)) return SK_E_INVALID;
+    if (!ctx || (!barcodes && S && L)) return SK_E_INVALID;
     cudaSetDevice(ctx->device);
     if (S > ctx->lim.max_samples || S > 32767) {
         ctx->err = "sample sheet larger than sk_limits.max_samples";
@@ -362,11 +374,13 @@ static int run_pass(sk_ctx *ctx, Slot *s, int which, int op, const KParams &p, b
     CK(cudaMemsetAsync(p.tile_lines, 0, (uint64_t)p.n_chunks * 8, s->stream));
     if (ordered_out) CK(cudaMemsetAsync(p.tile_out, 0, (uint64_t)p.n_chunks * 8, s->stream));
     const char *err = nullptr;
+    if (ctx->profiling) CK(cudaEventRecord(s->ev[which][0], s->stream));
     int rc = launch_chunk_kernel(op, p, ctx->sm_count, s->stream, &err);
     if (rc < 0) {
         ctx->err = std::string("kernel launch failed: ") + (err ? err : "?");
         return SK_E_CUDA;
     }
+    if (ctx->profiling) CK(cudaEventRecord(s->ev[which][1], s->stream));
     s->launches += (uint32_t)rc;
     s->pass_ran[which] = true;
     return SK_OK;
@@ -547,6 +561,9 @@ extern "C" int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res) {
     }
     res->n_records = h[SK_IN_R1].n_records;
     res->gpu_launches = s->launches;
+    if (ctx->profiling)
+        for (int i = 0; i < SK_N_INPUTS; i++)
+            if (s->pass_ran[i]) cudaEventElapsedTime(&res->pass_ms[i], s->ev[i][0], s->ev[i][1]);
     if (s->last_op == OP_DEMUX1) {
         res->out_bytes[0] = h[SK_IN_R1].out_bytes;
         res->out_extent[0] = h[SK_IN_R1].out_cursor;
@@ -652,19 +669,19 @@ extern "C" uint64_t sk_demux_gather(const uint8_t *out_host, const uint64_t *chu
 // multi-GPU: the one collective on the path.  NCCL is resolved at run time so the
 // library also loads where libnccl is absent.
 // ------------------------------------------------------------------------------------------------
+static void *nccl_sym(sk_ctx *ctx, const char *name) {
+    static void *h = nullptr;
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    void *f = h ? dlsym(h, name) : nullptr;
+    if (!f) ctx->err = std::string("libnccl.so.2 / ") + name + " not found";
+    return f;
+}
 extern "C" int sk_allreduce_counts(sk_ctx *ctx, uint32_t slot, void *nccl_comm) {
     Slot *s = get_slot(ctx, slot);
     if (!s || !s->counts || !nccl_comm) return SK_E_INVALID;
     typedef int (*allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
-    static allreduce_fn fn = nullptr;
-    if (!fn) {
-        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-        if (h) fn = (allreduce_fn)dlsym(h, "ncclAllReduce");
-        if (!fn) {
-            ctx->err = "libnccl.so.2 / ncclAllReduce not found";
-            return SK_E_UNSUPPORTED;
-        }
-    }
+    allreduce_fn fn = (allreduce_fn)nccl_sym(ctx, "ncclAllReduce");
+    if (!fn) return SK_E_UNSUPPORTED;
     // ncclUint64 = 5, ncclSum = 0
     int rc = fn(s->counts, s->counts, (size_t)ctx->S + 2, 5, 0, nccl_comm, s->stream);
     if (rc != 0) {
@@ -672,6 +689,35 @@ extern "C" int sk_allreduce_counts(sk_ctx *ctx, uint32_t slot, void *nccl_comm) 
         return SK_E_CUDA;
     }
     return SK_OK;
+}
+extern "C" int sk_nccl_unique_id(sk_ctx *ctx, void *id128) {
+    if (!ctx || !id128) return SK_E_INVALID;
+    typedef int (*fn_t)(void *);
+    fn_t fn = (fn_t)nccl_sym(ctx, "ncclGetUniqueId");
+    if (!fn) return SK_E_UNSUPPORTED;
+    return fn(id128) == 0 ? SK_OK : SK_E_CUDA;
+}
+extern "C" int sk_nccl_comm_init(sk_ctx *ctx, const void *id128, int nranks, int rank, void **comm) {
+    if (!ctx || !id128 || !comm) return SK_E_INVALID;
+    cudaSetDevice(ctx->device);
+    struct Id { char b[128]; } id;
+    memcpy(&id, id128, 128);
+    typedef int (*fn_t)(void **, int, Id, int);
+    fn_t fn = (fn_t)nccl_sym(ctx, "ncclCommInitRank");
+    if (!fn) return SK_E_UNSUPPORTED;
+    int rc = fn(comm, nranks, id, rank);
+    if (rc != 0) {
+        ctx->err = "ncclCommInitRank failed with code " + std::to_string(rc);
+        return SK_E_CUDA;
+    }
+    return SK_OK;
+}
+extern "C" int sk_nccl_comm_destroy(sk_ctx *ctx, void *comm) {
+    if (!ctx || !comm) return SK_E_INVALID;
+    typedef int (*fn_t)(void *);
+    fn_t fn = (fn_t)nccl_sym(ctx, "ncclCommDestroy");
+    if (!fn) return SK_E_UNSUPPORTED;
+    return fn(comm) == 0 ? SK_OK : SK_E_CUDA;
 }
 
 // ------------------------------------------------------------------------------------------------

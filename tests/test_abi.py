@@ -36,7 +36,7 @@ def test_struct_sizes_match_header():
     assert C.sizeof(L.Event) == 20
     assert C.sizeof(L.DemuxOpts) == 24
     assert C.sizeof(L.SynthSpec) == 56
-    assert C.sizeof(L.Result) == 4 + 4 + 8 + 8 + 32 + 32 + 16 + 16 + 8 + 8 + 8 + 4 + 4 + 4 + 4
+    assert C.sizeof(L.Result) == 4 + 4 + 8 + 8 + 32 + 32 + 16 + 16 + 8 + 8 + 8 + 4 + 4 + 4 + 4 + 16
 
 
 def test_no_cpu_fallback_without_device():

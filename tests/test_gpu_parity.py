@@ -220,7 +220,7 @@ def test_dual_index_umi_384_samples(eng, O):
 def test_properties_at_scale(eng):
     """Size-independent checks on a batch too big for a byte-for-byte oracle run in the test budget:
     mask keeps every byte count, trim output re-trims to itself (idempotence), demux conserves reads."""
-    n = 200_000
+    n = 130_000
     n1 = eng.synth(0, n, seed=3, mate=1)
     data = eng.download_in(0, n1)
     code, masked, _ = eng.mask_by_quality(data, 20)
