@@ -363,7 +363,7 @@ def run_e2e(args, torch, L, bcs, local_rank, rank, world, barrier):
     for w, t in enumerate(h_in):
         assert lib.sk_download_in(eng.ctx, 0, w, t.data_ptr(), t.numel()) == 0
     cap = max(n1, n2) + Pe * 16 + (1 << 20)
-    nchunks = (max(n1, n2) + 32767) // 32768 + 1
+    nchunks = lib.sk_max_chunks(eng.ctx)
     h_out = [[torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(2)] for _ in range(nslots)]
     h_base = [[torch.empty(nchunks, dtype=torch.int64).pin_memory() for _ in range(2)] for _ in range(nslots)]
     h_lens = [[torch.empty(nchunks * N_SAMPLES, dtype=torch.int16).pin_memory() for _ in range(2)] for _ in range(nslots)]

@@ -72,7 +72,7 @@ typedef struct sk_limits {
     uint32_t n_slots;          /* independent stream slots for H2D / kernel / D2H overlap (>= 1) */
     uint32_t max_samples;      /* largest sample sheet (0 = no demultiplexing) */
     uint32_t aux_streams;      /* 0: allocate only R1/R2; 1: also AUX1/AUX2 (index reads, barcode file) */
-    uint32_t reserved;
+    uint32_t reserved;         /* tuning: 0 default geometry, 1 = 16 KiB chunks, 2 = 32 KiB chunks */
 } sk_limits;
 
 typedef struct sk_result {
@@ -123,6 +123,11 @@ void sk_ctx_destroy(sk_ctx *ctx);
 const char *sk_last_error(const sk_ctx *ctx); /* ctx may be NULL: last create failure */
 /* cudaStream_t of a slot (so callers can record their own events on it). */
 void *sk_slot_stream(sk_ctx *ctx, uint32_t slot);
+/* Upper bound of sk_result.n_chunks for this context (rows of the demux slice tables). */
+uint32_t sk_max_chunks(sk_ctx *ctx);
+/* Diagnostic: per-phase SM cycles (summed over chunks, one timing thread per CTA) of the last kernel
+ * over input `which`; all zero unless the library was built with -DSK_PHASE_TIMING. */
+int sk_debug_phase_cycles(sk_ctx *ctx, uint32_t slot, uint32_t which, uint64_t out[16]);
 /* on != 0: bracket every kernel with CUDA events so that sk_wait can fill sk_result.pass_ms. */
 int sk_set_profiling(sk_ctx *ctx, int on);
 

@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libseqkit_b200.so")
+LIB_PATH = os.environ.get("SK_LIB") or os.path.join(HERE, "libseqkit_b200.so")
 
 SK_N_INPUTS = 4
 IN_R1, IN_R2, IN_AUX1, IN_AUX2 = 0, 1, 2, 3
@@ -59,6 +59,8 @@ SIGNATURES = {
     "sk_ctx_destroy": (None, [_P]),
     "sk_last_error": (C.c_char_p, [_P]),
     "sk_slot_stream": (_P, [_P, C.c_uint32]),
+    "sk_max_chunks": (C.c_uint32, [_P]),
+    "sk_debug_phase_cycles": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
     "sk_set_profiling": (C.c_int, [_P, C.c_int]),
     "sk_slot_in": (_P, [_P, C.c_uint32, C.c_uint32]),
     "sk_slot_in_capacity": (C.c_uint64, [_P, C.c_uint32, C.c_uint32]),

@@ -68,6 +68,11 @@ struct sk_ctx {
     std::vector<uint8_t> sheet_raw;
     uint32_t *d_planes = nullptr, *d_umask = nullptr;
     uint8_t *d_lut = nullptr, *d_sheet_raw = nullptr;
+    // exact-match index (FastIdx)
+    uint32_t f_classes = 0, f_nw = 0, f_tsize = 0;
+    uint32_t *d_fcls = nullptr, *d_skeys = nullptr;
+    unsigned long long *d_ftab = nullptr;
+    int cfg = 0;  // chunk-engine geometry: 0 = CfgBig (32 KiB chunks), 1 = CfgSmall (16 KiB chunks)
 };
 
 #define CK(call)                                                                         \
@@ -79,7 +84,10 @@ struct sk_ctx {
         }                                                                                \
     } while (0)
 
-static uint32_t chunks_of(uint64_t n) { return (uint32_t)((n + CfgStd::CHUNK - 1) / CfgStd::CHUNK); }
+static uint32_t chunks_of(const sk_ctx *ctx, uint64_t n) {
+    const uint64_t ch = (uint64_t)cfg_chunk_bytes(ctx->cfg);
+    return (uint32_t)((n + ch - 1) / ch);
+}
 
 extern "C" int sk_abi_version(void) { return SK_ABI_VERSION; }
 
@@ -118,6 +126,9 @@ extern "C" void sk_ctx_destroy(sk_ctx *ctx) {
     cudaFree(ctx->d_umask);
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_sheet_raw);
+    cudaFree(ctx->d_fcls);
+    cudaFree(ctx->d_skeys);
+    cudaFree(ctx->d_ftab);
     delete ctx;
 }
 
@@ -140,6 +151,8 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
     sk_ctx *ctx = new sk_ctx();
     ctx->device = device;
     ctx->lim = *lim;
+    ctx->cfg = lim->reserved == 1 ? 1 : lim->reserved == 2 ? 0 : 1;  // reserved: 0 default, 1 small, 2 big chunks
+    if (const char *e = getenv("SK_CFG")) ctx->cfg = atoi(e) ? 1 : 0;
     auto fail = [&](int code) {
         g_create_error = ctx->err;
         sk_ctx_destroy(ctx);
@@ -163,7 +176,7 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     const uint64_t B = (lim->max_stream_bytes + 15) & ~15ull;
     const uint64_t R = lim->max_records;
-    ctx->max_chunks = chunks_of(B) + 1;
+    ctx->max_chunks = chunks_of(ctx, B) + 1;
     const uint64_t out_cap = B + R * 72 + (uint64_t)ctx->max_chunks * 16 + 4096;
     const uint32_t Smax = lim->max_samples;
     ctx->slots.resize(lim->n_slots);
@@ -210,6 +223,14 @@ static Slot *get_slot(sk_ctx *ctx, uint32_t slot) {
 extern "C" void *sk_slot_stream(sk_ctx *ctx, uint32_t slot) {
     Slot *s = get_slot(ctx, slot);
     return s ? (void *)s->stream : nullptr;
+}
+extern "C" uint32_t sk_max_chunks(sk_ctx *ctx) { return ctx ? ctx->max_chunks : 0; }
+extern "C" int sk_debug_phase_cycles(sk_ctx *ctx, uint32_t slot, uint32_t which, uint64_t out[16]) {
+    Slot *s = get_slot(ctx, slot);
+    if (!s || which >= SK_N_INPUTS || !out) return SK_E_INVALID;
+    CK(cudaStreamSynchronize(s->stream));
+    for (int i = 0; i < 16; i++) out[i] = s->stats_h[which].phase_cycles[i];
+    return SK_OK;
 }
 extern "C" int sk_set_profiling(sk_ctx *ctx, int on) {
     if (!ctx) return SK_E_INVALID;
@@ -263,10 +284,7 @@ extern "C" int sk_set_sheet(sk_ctx *ctx, const uint8_t *barcodes, uint32_t S, ui
         ctx->err = "barcodes longer than 64 characters are not supported by the bit-plane matcher";
         return SK_E_UNSUPPORTED;
     }
-    if (chunk_kernel_smem_bytes(S, L > 32) > 227 * 1024) {
-        ctx->err = "sample sheet does not fit in shared memory";
-        return SK_E_UNSUPPORTED;
-    }
+    const uint32_t wide = L > 32 ? 1u : 0u;
     // literal alphabet of the sheet: every byte that is not a wildcard ('N'/'U', :273)
     uint8_t lut[256];
     memset(lut, 0, sizeof lut);
@@ -280,7 +298,7 @@ extern "C" int sk_set_sheet(sk_ctx *ctx, const uint8_t *barcodes, uint32_t S, ui
         }
         lut[b] = (uint8_t)(++ncode);
     }
-    const uint32_t wide = L > 32 ? 1u : 0u;
+    for (const char *c = "ACGTNacgtn+"; *c; c++) lut[(uint8_t)*c] |= 8u;  // regex class of fasta_demultiplex.rs:38
     const uint32_t wpe = wide ? 2u : 1u;  // u32 words per plane element
     std::vector<uint32_t> planes((size_t)S * 4 * wpe, 0u), umask((size_t)S * wpe, 0u);
     uint32_t Umax = 0;
@@ -290,7 +308,7 @@ extern "C" int sk_set_sheet(sk_ctx *ctx, const uint8_t *barcodes, uint32_t S, ui
             const uint8_t b = barcodes[(uint64_t)s * L + q];
             if (b == 'U') um |= 1ull << q;
             if (b == 'N' || b == 'U') continue;
-            const uint32_t code = lut[b];
+            const uint32_t code = lut[b] & 7u;
             for (int k = 0; k < 3; k++)
                 if ((code >> k) & 1u) pl[k] |= 1ull << q;
             pl[3] |= 1ull << q;  // care
@@ -303,27 +321,113 @@ extern "C" int sk_set_sheet(sk_ctx *ctx, const uint8_t *barcodes, uint32_t S, ui
         if (wide) umask[(size_t)s * wpe + 1] = (uint32_t)(um >> 32);
         Umax = std::max<uint32_t>(Umax, (uint32_t)__builtin_popcountll(um));
     }
+
+    // ---- exact-match index: classes of identical care mask, one open-addressing table per class
+    const uint32_t nw = (L + 3) / 4;
+    std::vector<std::vector<uint8_t>> cls_care;
+    std::vector<uint32_t> cls_of(S, 0);
+    for (uint32_t s = 0; s < S; s++) {
+        std::vector<uint8_t> care(L);
+        for (uint32_t q = 0; q < L; q++) {
+            const uint8_t b = barcodes[(uint64_t)s * L + q];
+            care[q] = (b != 'N' && b != 'U') ? 0xFF : 0x00;
+        }
+        uint32_t c = 0;
+        for (; c < cls_care.size(); c++)
+            if (cls_care[c] == care) break;
+        if (c == cls_care.size()) cls_care.push_back(care);
+        cls_of[s] = c;
+    }
+    uint32_t f_classes = (S && L && cls_care.size() <= 2) ? (uint32_t)cls_care.size() : 0;
+    uint32_t tsize = 16;
+    while (3 * tsize < 4 * S) tsize <<= 1;  // load factor <= 0.75
+    if (f_classes && chunk_kernel_smem_bytes(ctx->cfg, S, wide, f_classes, tsize) > 227 * 1024) f_classes = 0;
+    if (chunk_kernel_smem_bytes(ctx->cfg, S, wide, f_classes, tsize) > 227 * 1024) {
+        ctx->err = "sample sheet does not fit in shared memory";
+        return SK_E_UNSUPPORTED;
+    }
+    std::vector<uint32_t> skeys((size_t)S * std::max(nw, 1u), 0u), fcls((size_t)std::max(f_classes, 1u) * FAST_CLS_WORDS, 0u);
+    std::vector<unsigned long long> ftab((size_t)std::max(f_classes, 1u) * tsize, 0xFFFFull << 32);
+    for (uint32_t s = 0; s < S; s++)
+        for (uint32_t q = 0; q < L; q++) {
+            const uint8_t b = barcodes[(uint64_t)s * L + q] & cls_care[cls_of[s]][q];
+            skeys[(size_t)s * nw + q / 4] |= (uint32_t)b << (8 * (q % 4));
+        }
+    uint64_t rng = 0x9E3779B97F4A7C15ull ^ ((uint64_t)S << 32) ^ L;
+    auto next = [&]() {
+        rng ^= rng << 13;
+        rng ^= rng >> 7;
+        rng ^= rng << 17;
+        return (uint32_t)(rng >> 16);
+    };
+    for (uint32_t c = 0; c < f_classes; c++) {
+        uint32_t *cw = &fcls[(size_t)c * FAST_CLS_WORDS];
+        for (uint32_t q = 0; q < L; q++) cw[q / 4] |= (uint32_t)cls_care[c][q] << (8 * (q % 4));
+        for (uint32_t w = 0; w < (uint32_t)FAST_NWMAX; w++) {
+            cw[FAST_NWMAX + w] = next() | 1u;
+            cw[2 * FAST_NWMAX + w] = next() | 1u;
+        }
+        unsigned long long *tab = &ftab[(size_t)c * tsize];
+        for (uint32_t s = 0; s < S; s++) {
+            if (cls_of[s] != c) continue;
+            const uint32_t *key = &skeys[(size_t)s * nw];
+            uint32_t h1 = 0, h2 = 0;
+            for (uint32_t w = 0; w < nw; w++) {
+                h1 += key[w] * cw[FAST_NWMAX + w];
+                h2 += key[w] * cw[2 * FAST_NWMAX + w];
+            }
+            h1 ^= h1 >> 15;
+            uint32_t slot = h1 & (tsize - 1);
+            for (;;) {
+                const unsigned long long e = tab[slot];
+                const uint32_t f = (uint32_t)(e >> 32) & 0xFFFFu;
+                if (f == 0xFFFFu) {
+                    tab[slot] = (unsigned long long)h2 | ((unsigned long long)s << 32) | ((unsigned long long)s << 48);
+                    break;
+                }
+                if (memcmp(&skeys[(size_t)f * nw], key, (size_t)nw * 4) == 0) {  // duplicate barcode: widen [first,last]
+                    tab[slot] = (e & 0x0000FFFFFFFFFFFFull) | ((unsigned long long)s << 48);
+                    break;
+                }
+                slot = (slot + 1) & (tsize - 1);
+            }
+        }
+    }
+
     cudaFree(ctx->d_planes);
     cudaFree(ctx->d_umask);
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_sheet_raw);
-    ctx->d_planes = ctx->d_umask = nullptr;
+    cudaFree(ctx->d_fcls);
+    cudaFree(ctx->d_skeys);
+    cudaFree(ctx->d_ftab);
+    ctx->d_planes = ctx->d_umask = ctx->d_fcls = ctx->d_skeys = nullptr;
     ctx->d_lut = ctx->d_sheet_raw = nullptr;
+    ctx->d_ftab = nullptr;
     CK(cudaMalloc(&ctx->d_planes, std::max<size_t>(planes.size() * 4, 16)));
     CK(cudaMalloc(&ctx->d_umask, std::max<size_t>(umask.size() * 4, 16)));
     CK(cudaMalloc(&ctx->d_lut, 256));
     CK(cudaMalloc(&ctx->d_sheet_raw, std::max<size_t>((size_t)S * L, 16)));
+    CK(cudaMalloc(&ctx->d_fcls, fcls.size() * 4));
+    CK(cudaMalloc(&ctx->d_skeys, std::max<size_t>(skeys.size() * 4, 16)));
+    CK(cudaMalloc(&ctx->d_ftab, ftab.size() * 8));
     if (S) {
         CK(cudaMemcpy(ctx->d_planes, planes.data(), planes.size() * 4, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(ctx->d_umask, umask.data(), umask.size() * 4, cudaMemcpyHostToDevice));
         if (L) CK(cudaMemcpy(ctx->d_sheet_raw, barcodes, (size_t)S * L, cudaMemcpyHostToDevice));
+        if (L) CK(cudaMemcpy(ctx->d_skeys, skeys.data(), skeys.size() * 4, cudaMemcpyHostToDevice));
     }
     CK(cudaMemcpy(ctx->d_lut, lut, 256, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_fcls, fcls.data(), fcls.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_ftab, ftab.data(), ftab.size() * 8, cudaMemcpyHostToDevice));
     ctx->sheet_raw.assign(barcodes, barcodes + (size_t)S * L);
     ctx->S = S;
     ctx->L = L;
     ctx->Umax = Umax;
     ctx->wide = wide;
+    ctx->f_classes = f_classes;
+    ctx->f_nw = nw;
+    ctx->f_tsize = tsize;
     ctx->have_sheet = true;
     // the UMI side table depends on the sheet
     for (auto &s : ctx->slots) {
@@ -357,7 +461,7 @@ static void base_params(sk_ctx *ctx, Slot *s, int which, KParams &p) {
     memset(&p, 0, sizeof p);
     p.in = s->in[which];
     p.n = s->in_len[which];
-    p.n_chunks = chunks_of(p.n);
+    p.n_chunks = chunks_of(ctx, p.n);
     p.lpr = 4;
     p.rec_limit = ~0ull;
     p.final_batch = 1;
@@ -366,7 +470,6 @@ static void base_params(sk_ctx *ctx, Slot *s, int which, KParams &p) {
     p.tile_out = s->tile_out;
     p.stats = s->stats + which;
     s->n_chunks[which] = p.n_chunks;
-    (void)ctx;
 }
 
 static int run_pass(sk_ctx *ctx, Slot *s, int which, int op, const KParams &p, bool ordered_out) {
@@ -375,7 +478,7 @@ static int run_pass(sk_ctx *ctx, Slot *s, int which, int op, const KParams &p, b
     if (ordered_out) CK(cudaMemsetAsync(p.tile_out, 0, (uint64_t)p.n_chunks * 8, s->stream));
     const char *err = nullptr;
     if (ctx->profiling) CK(cudaEventRecord(s->ev[which][0], s->stream));
-    int rc = launch_chunk_kernel(op, p, ctx->sm_count, s->stream, &err);
+    int rc = launch_chunk_kernel(ctx->cfg, op, p, ctx->sm_count, s->stream, &err);
     if (rc < 0) {
         ctx->err = std::string("kernel launch failed: ") + (err ? err : "?");
         return SK_E_CUDA;
@@ -515,6 +618,12 @@ extern "C" int sk_demultiplex(sk_ctx *ctx, uint32_t slot, const sk_demux_opts *o
         p.sheet.L = ctx->L;
         p.sheet.Umax = ctx->Umax;
         p.sheet.wide = ctx->wide;
+        p.sheet.fast.n_classes = ctx->f_classes;
+        p.sheet.fast.nw = ctx->f_nw;
+        p.sheet.fast.tsize = ctx->f_tsize;
+        p.sheet.fast.cls = ctx->d_fcls;
+        p.sheet.fast.table = ctx->d_ftab;
+        p.sheet.fast.skeys = ctx->d_skeys;
         p.assign = s->assign;
         p.umi = s->umi;
         p.lens = s->lens[mate];

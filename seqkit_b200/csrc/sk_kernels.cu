@@ -6,6 +6,11 @@
 // once (16-byte vector stores from a shared staging image).  Record framing is by global line
 // index (decoupled look-back over per-chunk line counts), exactly like the reference's four
 // read_line calls per record (common.rs:106-112).
+//
+// The kernel is bound by issued instructions, not by DRAM (profiles/r1_v1_ncu_summary.txt), so every
+// phase is written for instruction count: SWAR scans on aligned words, one thread per record for the
+// sequential reference logic, 4 lanes per record copying whole words with funnel shifts, an
+// exact-match hash index in front of the brute-force barcode matcher.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -130,29 +135,28 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *scratc
     return r;
 }
 
-// 4-bit mask of the bytes of x equal to '\n' (exact SWAR zero-byte test, no cross-byte carries).
-__device__ __forceinline__ uint32_t nl4(uint32_t x) {
-    uint32_t t = x ^ 0x0A0A0A0Au;
-    uint32_t z = ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;
-    return (((z >> 7) * 0x00204081u) >> 21) & 0xFu;
+// 0x80 in every byte of x that equals the byte replicated in `pat` (exact SWAR test, no carries).
+__device__ __forceinline__ uint32_t eq_flags(uint32_t x, uint32_t pat) {
+    const uint32_t t = x ^ pat;
+    return ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;
 }
-// bits b of a 16-bit piece mask whose window position o+b lies in [lo, hi)
-__device__ __forceinline__ uint32_t range16(uint32_t o, uint32_t lo, uint32_t hi) {
-    uint32_t a = lo > o ? lo - o : 0u, b = hi > o ? hi - o : 0u;
-    if (a > 16u) a = 16u;
-    if (b > 16u) b = 16u;
-    return b > a ? (((1u << b) - 1u) & ~((1u << a) - 1u)) : 0u;
+// Newline map of a 16-byte piece: bit (8*b + w) is set when byte b of word w is '\n'
+// (window offset of that byte inside the piece = 4*w + b).
+__device__ __forceinline__ uint32_t nl_map(const uint4 v) {
+    const uint32_t zx = eq_flags(v.x, 0x0A0A0A0Au), zy = eq_flags(v.y, 0x0A0A0A0Au);
+    const uint32_t zz = eq_flags(v.z, 0x0A0A0A0Au), zw = eq_flags(v.w, 0x0A0A0A0Au);
+    return (zx >> 7) | (zy >> 6) | (zz >> 5) | (zw >> 4);
+}
+__device__ __forceinline__ uint32_t map_bit(uint32_t k) { return 8u * (k & 3u) + (k >> 2); }  // piece offset k -> map bit
+// the map restricted to piece offsets k with lo <= o + k < hi (rare path: pieces at a range boundary)
+__device__ __forceinline__ uint32_t map_clip(uint32_t y, uint32_t o, uint32_t lo, uint32_t hi) {
+    uint32_t keep = 0;
+    for (uint32_t k = 0; k < 16; k++)
+        if (o + k >= lo && o + k < hi) keep |= 1u << map_bit(k);
+    return y & keep;
 }
 
 __device__ __forceinline__ bool is_ws(uint8_t c) { return c == 32u || (c >= 9u && c <= 13u); }  // ASCII White_Space
-__device__ __forceinline__ bool is_bc_class(uint8_t c) {  // [ACGTNacgtn+], fasta_demultiplex.rs:38
-    switch (c) {
-        case 'A': case 'C': case 'G': case 'T': case 'N':
-        case 'a': case 'c': case 'g': case 't': case 'n': case '+':
-            return true;
-    }
-    return false;
-}
 
 __device__ __forceinline__ void report_err(DevStats *st, uint64_t rec, unsigned kind) {
     atomicMax(&st->err_key, ~((rec << 8) | (unsigned long long)kind));
@@ -160,7 +164,7 @@ __device__ __forceinline__ void report_err(DevStats *st, uint64_t rec, unsigned 
 
 // body modes of a planned record
 enum : uint8_t { B_VERBATIM = 0, B_TRIM = 1, B_GARBAGE = 2, B_MASK = 3, B_NONE = 4 };
-// tag kinds (r_taglen high bit unused; kind is implied by OP)
+enum : uint8_t { RF_SLOW = 1, RF_DEAD = 2 };
 
 struct Win {
     const uint8_t *b;
@@ -171,22 +175,38 @@ struct Win {
 __device__ __forceinline__ uint32_t lb(const Win &W, uint32_t x) { return x < W.nls ? (uint32_t)W.ls[x] : W.wlen; }
 
 // fasta_trim_by_quality.rs:28-48 on the quality line [L3,L4) / sequence line [L1,L2).
-// Returns false when &seq[..k] would panic.
-__device__ __forceinline__ bool plan_trim_body(const Win &W, uint32_t L1, uint32_t L2, uint32_t L3, uint32_t L4,
+// Quality bytes are fetched one aligned word at a time.  Returns false when &seq[..k] would panic.
+__device__ __forceinline__ bool plan_trim_body(const uint8_t *b, uint32_t L1, uint32_t L2, uint32_t L3, uint32_t L4,
                                                int minq, uint8_t &mode, uint32_t &kk, uint32_t &body_len) {
     uint32_t k = L4 - L3;
-    while (k > 0 && is_ws(W.b[L3 + k - 1])) k--;  // qual.trim_end().len()  (:31)
-    int total = -50, lowest = -50;                // :28-29
+    while (k > 0 && is_ws(b[L3 + k - 1])) k--;  // qual.trim_end().len()  (:31)
+    int total = -50, lowest = -50;              // :28-29
     uint32_t lowest_k = k;
-    while (k > 0) {  // :33-42
-        k--;
-        total += (int)(uint8_t)(W.b[L3 + k] - 33u) - minq;  // wrapping u8 subtraction (:35)
-        if (total > 0) break;
-        if (total < lowest) {
-            lowest = total;
-            lowest_k = k;
-        }
+    // Bytes are examined from the end, one aligned word per iteration; `pos` is one past the byte
+    // examined next.  STEP(j) handles byte j of the word when it lies inside [L3, pos).
+    uint32_t pos = L3 + k;
+    const int sub = 33 + minq;
+    bool stop = false;
+#define SK_TRIM_STEP(j)                                                            \
+    if (!stop && a + (j) < pos && a + (j) >= L3) {                                 \
+        const uint32_t q = (w >> (8 * (j))) & 0xFFu;                               \
+        total += q >= 33u ? (int)q - sub : (int)((q - 33u) & 0xFFu) - minq; /* wrapping u8 subtraction (:35) */ \
+        if (total > 0) stop = true;                                                \
+        else if (total < lowest) {                                                 \
+            lowest = total;                                                        \
+            lowest_k = a + (j) - L3;                                               \
+        }                                                                          \
     }
+    while (pos > L3 && !stop) {  // :33-42
+        const uint32_t a = (pos - 1) & ~3u;
+        const uint32_t w = *(const uint32_t *)(b + a);
+        SK_TRIM_STEP(3)
+        SK_TRIM_STEP(2)
+        SK_TRIM_STEP(1)
+        SK_TRIM_STEP(0)
+        pos = a;
+    }
+#undef SK_TRIM_STEP
     if (lowest_k == 0) {  // :44-45
         mode = B_GARBAGE;
         kk = 0;
@@ -199,18 +219,42 @@ __device__ __forceinline__ bool plan_trim_body(const Win &W, uint32_t L1, uint32
     return lowest_k <= L2 - L1;
 }
 
-// Leftmost match of " BC:[ACGTNacgtn+]+" in [h0,h1) (window offsets). Returns false if none.
-__device__ __forceinline__ bool bc_find(const uint8_t *b, uint32_t h0, uint32_t h1, uint32_t &st, uint32_t &en) {
-    for (uint32_t i = h0; i + 5 <= h1; i++) {
-        if (b[i] == ' ' && b[i + 1] == 'B' && b[i + 2] == 'C' && b[i + 3] == ':' && is_bc_class(b[i + 4])) {
-            uint32_t e = i + 5;
-            while (e < h1 && is_bc_class(b[e])) e++;
-            st = i;
-            en = e;
-            return true;
+// Leftmost match of " BC:[ACGTNacgtn+]" in [h0,h1): aligned words are tested for ' ' with SWAR and
+// only the candidates are looked at byte-wise.  `lut` bit 3 = regex class.  Returns the offset of ' '.
+__device__ __forceinline__ bool bc_find(const uint8_t *b, const uint8_t *lut, uint32_t h0, uint32_t h1, uint32_t &st) {
+    if (h1 < h0 + 5) return false;
+    const uint32_t last = h1 - 5;  // last admissible start
+    for (uint32_t a = h0 & ~3u; a <= last; a += 4) {
+        uint32_t z = eq_flags(*(const uint32_t *)(b + a), 0x20202020u);
+        while (z) {
+            const uint32_t i = a + ((__ffs(z) - 1) >> 3);
+            z &= z - 1;
+            if (i >= h0 && i <= last && b[i + 1] == 'B' && b[i + 2] == 'C' && b[i + 3] == ':' && (lut[b[i + 4]] & 8u)) {
+                st = i;
+                return true;
+            }
         }
     }
     return false;
+}
+// end of the greedy class run that starts at `from` (from < h1 is a class char already)
+__device__ __forceinline__ uint32_t bc_run_end(const uint8_t *b, const uint8_t *lut, uint32_t from, uint32_t h1) {
+    uint32_t e = from;
+    while (e < h1 && (e & 3u)) {  // up to the next aligned word
+        if (!(lut[b[e]] & 8u)) return e;
+        e++;
+    }
+    while (e + 4 <= h1) {
+        const uint32_t w = *(const uint32_t *)(b + e);
+        const uint32_t c0 = lut[w & 0xFFu], c1 = lut[(w >> 8) & 0xFFu], c2 = lut[(w >> 16) & 0xFFu], c3 = lut[w >> 24];
+        if (!(c0 & 8u)) return e;
+        if (!(c1 & 8u)) return e + 1;
+        if (!(c2 & 8u)) return e + 2;
+        if (!(c3 & 8u)) return e + 3;
+        e += 4;
+    }
+    while (e < h1 && (lut[b[e]] & 8u)) e++;
+    return e;
 }
 
 // header.drain(cut) then trim_end(): the kept pieces are [h0, h0+alen) and [c1, c1+blen).
@@ -235,29 +279,311 @@ template <>
 __device__ __forceinline__ uint32_t popcw<uint32_t>(uint32_t x) { return __popc(x); }
 template <>
 __device__ __forceinline__ uint32_t popcw<uint64_t>(uint64_t x) { return __popcll(x); }
-
-// Replaces the S x barcode_diff loop of fasta_demultiplex.rs:157-166.
 template <typename WT>
-__device__ __forceinline__ void match_sheet(const WT *sh, uint32_t S, WT o0, WT o1, WT o2, uint32_t &lowest,
+__device__ __forceinline__ uint32_t ffsw(WT x);  // index of the lowest set bit
+template <>
+__device__ __forceinline__ uint32_t ffsw<uint32_t>(uint32_t x) { return (uint32_t)__ffs((int)x) - 1u; }
+template <>
+__device__ __forceinline__ uint32_t ffsw<uint64_t>(uint64_t x) { return (uint32_t)__ffsll((long long)x) - 1u; }
+
+// Exact-match lookup (FastIdx): is the barcode at window offset bs byte-identical, on the cared
+// positions, to some sample?  On a hit best/last are the first/last such sample over all classes.
+template <int NWMAX>
+__device__ __forceinline__ bool fast_lookup(const uint8_t *b, uint32_t bs, uint32_t nw, uint32_t ncls, uint32_t tmask,
+                                            const uint32_t *cls, const unsigned long long *tab, const uint32_t *skeys,
                                             uint32_t &best, uint32_t &last) {
-    lowest = 0xFFFFFFFFu;
-    best = 0;
-    last = 0;
-    for (uint32_t s = 0; s < S; s++) {
-        const WT p0 = sh[4 * s], p1 = sh[4 * s + 1], p2 = sh[4 * s + 2], care = sh[4 * s + 3];
-        const uint32_t d = popcw<WT>(((o0 ^ p0) | (o1 ^ p1) | (o2 ^ p2)) & care);
-        if (d < lowest) {
-            lowest = d;
-            best = s;
-            last = s;
-        } else if (d == lowest) {
-            last = s;
+    const uint32_t a = bs & ~3u, sh = (bs & 3u) * 8u;
+    uint32_t raw[NWMAX];
+    uint32_t lo = *(const uint32_t *)(b + a);
+#pragma unroll
+    for (int w = 0; w < NWMAX; w++) {
+        raw[w] = 0;
+        if (w < (int)nw) {
+            const uint32_t hi = *(const uint32_t *)(b + a + 4 * w + 4);
+            raw[w] = __funnelshift_r(lo, hi, sh);
+            lo = hi;
         }
     }
+    bool hit = false;
+    best = 0xFFFFFFFFu;
+    last = 0;
+    for (uint32_t c = 0; c < ncls; c++) {
+        const uint32_t *cw = cls + c * FAST_CLS_WORDS;
+        uint32_t key[NWMAX], h1 = 0, h2 = 0;
+#pragma unroll
+        for (int w = 0; w < NWMAX; w++) {
+            key[w] = raw[w] & cw[w];  // care bytes are 0 beyond nw
+            h1 += key[w] * cw[FAST_NWMAX + w];
+            h2 += key[w] * cw[2 * FAST_NWMAX + w];
+        }
+        h1 ^= h1 >> 15;
+        uint32_t slot = h1 & tmask;
+        const unsigned long long *t = tab + (size_t)c * (tmask + 1);
+        for (;;) {
+            const unsigned long long e = t[slot];
+            const uint32_t f = (uint32_t)(e >> 32) & 0xFFFFu;
+            if (f == 0xFFFFu) break;  // empty slot: not in this class
+            if ((uint32_t)e == h2) {
+                bool same = true;
+#pragma unroll
+                for (int w = 0; w < NWMAX; w++)
+                    if (w < (int)nw) same &= (key[w] == skeys[f * nw + w]);
+                if (same) {
+                    hit = true;
+                    best = f < best ? f : best;
+                    const uint32_t l = (uint32_t)(e >> 48);
+                    last = l > last ? l : last;
+                    break;
+                }
+            }
+            slot = (slot + 1) & tmask;
+        }
+    }
+    return hit;
 }
 
-__device__ __forceinline__ void wcopy(uint8_t *dst, const uint8_t *src, uint32_t len, int lane) {
-    for (uint32_t i = lane; i < len; i += 32) dst[i] = src[i];
+// ------------------------------------------------------------------------------------------------
+// 4-lane groups: the per-record plan is latency bound when one thread walks a record alone
+// (profiles/r1_v2_phase_cycles.txt), so 4 consecutive lanes share each record.  Shuffles name only
+// the group's lanes, so groups of one warp may sit at different loop iterations.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t gmask4() { return 0xFu << ((threadIdx.x & 31u) & ~3u); }
+__device__ __forceinline__ uint32_t gmin4(uint32_t gm, uint32_t v) {
+    uint32_t o = __shfl_xor_sync(gm, v, 1);
+    v = o < v ? o : v;
+    o = __shfl_xor_sync(gm, v, 2);
+    return o < v ? o : v;
+}
+__device__ __forceinline__ uint32_t gmax4(uint32_t gm, uint32_t v) {
+    uint32_t o = __shfl_xor_sync(gm, v, 1);
+    v = o > v ? o : v;
+    o = __shfl_xor_sync(gm, v, 2);
+    return o > v ? o : v;
+}
+__device__ __forceinline__ uint32_t gsum4(uint32_t gm, uint32_t v) {
+    v += __shfl_xor_sync(gm, v, 1);
+    return v + __shfl_xor_sync(gm, v, 2);
+}
+
+// fasta_trim_by_quality.rs:28-48, four lanes per record: every step the group examines the next 16
+// bytes of the quality line from its end (one aligned word per lane, lane 0 the highest), forms the
+// running totals with a 4-lane prefix sum, finds the first total > 0 (the `break`, :37) and the
+// first strict minimum before it (:38-41).  All lanes return the same result.
+__device__ __forceinline__ bool plan_trim_body4(const uint8_t *b, uint32_t gm, uint32_t q4, uint32_t L1, uint32_t L2,
+                                                uint32_t L3, uint32_t L4, int minq, uint8_t &mode, uint32_t &kk,
+                                                uint32_t &body_len) {
+    uint32_t k = L4 - L3;
+    while (k > 0 && is_ws(b[L3 + k - 1])) k--;  // qual.trim_end().len()  (:31)
+    int total = -50, lowest = -50;              // :28-29
+    uint32_t lowest_k = k;
+    uint32_t pos = L3 + k;  // one past the byte examined next
+    const int sub = 33 + minq;
+    while (pos > L3) {
+        const uint32_t a_top = (pos - 1) & ~3u;
+        int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+        uint32_t vm = 0, a = 0;
+        if (a_top >= 4u * q4) {
+            a = a_top - 4u * q4;
+            if (a + 4 > L3) {
+                const uint32_t w = *(const uint32_t *)(b + a);
+#define SK_VAL(j, vj)                                                                                   \
+    if (a + (j) >= L3 && a + (j) < pos) {                                                               \
+        const uint32_t q = (w >> (8 * (j))) & 0xFFu;                                                    \
+        vj = q >= 33u ? (int)q - sub : (int)((q - 33u) & 0xFFu) - minq; /* wrapping u8 subtraction (:35) */ \
+        vm |= 1u << (j);                                                                                \
+    }
+                SK_VAL(0, v0) SK_VAL(1, v1) SK_VAL(2, v2) SK_VAL(3, v3)
+#undef SK_VAL
+            }
+        }
+        const int s3 = v3, s2 = s3 + v2, s1 = s2 + v1, s0 = s1 + v0;  // sums in scan order (descending address)
+        int inc = s0, t = __shfl_up_sync(gm, inc, 1, 4);
+        if (q4 >= 1) inc += t;
+        t = __shfl_up_sync(gm, inc, 2, 4);
+        if (q4 >= 2) inc += t;
+        const int pre = total + inc - s0;
+        const int T3 = pre + s3, T2 = pre + s2, T1 = pre + s1, T0 = pre + s0;
+        uint32_t brk = 0;  // address + 1 of the byte whose total first exceeds 0 (0 = none)
+        if ((vm & 1u) && T0 > 0) brk = a + 1;
+        if ((vm & 2u) && T1 > 0) brk = a + 2;
+        if ((vm & 4u) && T2 > 0) brk = a + 3;
+        if ((vm & 8u) && T3 > 0) brk = a + 4;
+        brk = gmax4(gm, brk);
+        int mT = 0x7FFFFFFF;
+        uint32_t mA = 0;
+        if ((vm & 8u) && a + 4 > brk && T3 < mT) { mT = T3; mA = a + 3; }
+        if ((vm & 4u) && a + 3 > brk && T2 < mT) { mT = T2; mA = a + 2; }
+        if ((vm & 2u) && a + 2 > brk && T1 < mT) { mT = T1; mA = a + 1; }
+        if ((vm & 1u) && a + 1 > brk && T0 < mT) { mT = T0; mA = a; }
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {  // lower total wins; on a tie the byte examined first (higher address)
+            const int oT = __shfl_xor_sync(gm, mT, o);
+            const uint32_t oA = __shfl_xor_sync(gm, mA, o);
+            if (oT < mT || (oT == mT && oA > mA)) { mT = oT; mA = oA; }
+        }
+        if (mT < lowest) {
+            lowest = mT;
+            lowest_k = mA - L3;
+        }
+        if (brk) break;
+        total += __shfl_sync(gm, inc, 3, 4);  // the group's 16 bytes
+        pos = a_top >= 12u ? a_top - 12u : 0u;
+    }
+    if (lowest_k == 0) {  // :44-45
+        mode = B_GARBAGE;
+        kk = 0;
+        body_len = 6;  // "N\n+\n!\n"
+        return true;
+    }
+    mode = B_TRIM;
+    kk = lowest_k;
+    body_len = 2 * lowest_k + 4;  // seq[..k] "\n+\n" qual[..k] "\n"  (:47)
+    return lowest_k <= L2 - L1;
+}
+
+// bc_find with the header's words dealt round-robin to the four lanes.
+__device__ __forceinline__ bool bc_find4(const uint8_t *b, const uint8_t *lut, uint32_t gm, uint32_t q4, uint32_t h0,
+                                         uint32_t h1, uint32_t &st) {
+    uint32_t best = 0xFFFFFFFFu;
+    if (h1 >= h0 + 5) {
+        const uint32_t last = h1 - 5;
+        for (uint32_t a = (h0 & ~3u) + 4u * q4; a <= last && best == 0xFFFFFFFFu; a += 16) {
+            uint32_t z = eq_flags(*(const uint32_t *)(b + a), 0x20202020u);
+            while (z) {
+                const uint32_t i = a + ((__ffs(z) - 1) >> 3);
+                z &= z - 1;
+                if (i >= h0 && i <= last && b[i + 1] == 'B' && b[i + 2] == 'C' && b[i + 3] == ':' && (lut[b[i + 4]] & 8u)) {
+                    best = i;
+                    break;
+                }
+            }
+        }
+    }
+    best = gmin4(gm, best);
+    st = best;
+    return best != 0xFFFFFFFFu;
+}
+// first offset in [from, h1) that is not a class byte (h1 if none), bytes dealt round-robin
+__device__ __forceinline__ uint32_t bc_run_end4(const uint8_t *b, const uint8_t *lut, uint32_t gm, uint32_t q4,
+                                                uint32_t from, uint32_t h1) {
+    uint32_t e = h1;
+    for (uint32_t i = from + q4; i < h1; i += 4)
+        if (!(lut[b[i]] & 8u)) {
+            e = i;
+            break;
+        }
+    return gmin4(gm, e);
+}
+
+// fast_lookup with the key words dealt round-robin to the four lanes (word w belongs to lane w & 3).
+template <int NWMAX>
+__device__ __forceinline__ bool fast_lookup4(const uint8_t *b, uint32_t gm, uint32_t q4, uint32_t bs, uint32_t nw,
+                                             uint32_t ncls, uint32_t tmask, const uint32_t *cls,
+                                             const unsigned long long *tab, const uint32_t *skeys, uint32_t &best,
+                                             uint32_t &last) {
+    constexpr int NT4 = NWMAX / 4;
+    const uint32_t a = bs & ~3u, sh = (bs & 3u) * 8u;
+    uint32_t raw[NT4];
+#pragma unroll
+    for (int t = 0; t < NT4; t++) {
+        const uint32_t w = q4 + 4u * t;
+        raw[t] = 0;
+        if (w < nw) raw[t] = __funnelshift_r(*(const uint32_t *)(b + a + 4 * w), *(const uint32_t *)(b + a + 4 * w + 4), sh);
+    }
+    bool hit = false;
+    best = 0xFFFFFFFFu;
+    last = 0;
+    for (uint32_t c = 0; c < ncls; c++) {
+        const uint32_t *cw = cls + c * FAST_CLS_WORDS;
+        uint32_t key[NT4], h1 = 0, h2 = 0;
+#pragma unroll
+        for (int t = 0; t < NT4; t++) {
+            const uint32_t w = q4 + 4u * t;
+            key[t] = raw[t] & cw[w];  // care bytes are 0 beyond nw
+            h1 += key[t] * cw[FAST_NWMAX + w];
+            h2 += key[t] * cw[2 * FAST_NWMAX + w];
+        }
+        h1 = gsum4(gm, h1);
+        h2 = gsum4(gm, h2);
+        h1 ^= h1 >> 15;
+        uint32_t slot = h1 & tmask;
+        const unsigned long long *t2 = tab + (size_t)c * (tmask + 1);
+        for (;;) {
+            const unsigned long long e = t2[slot];
+            const uint32_t f = (uint32_t)(e >> 32) & 0xFFFFu;
+            if (f == 0xFFFFu) break;  // empty slot: not in this class
+            if ((uint32_t)e == h2) {
+                uint32_t same = 1;
+#pragma unroll
+                for (int t = 0; t < NT4; t++) {
+                    const uint32_t w = q4 + 4u * t;
+                    if (w < nw && key[t] != skeys[f * nw + w]) same = 0;
+                }
+                if (gmin4(gm, same)) {
+                    hit = true;
+                    best = f < best ? f : best;
+                    const uint32_t l = (uint32_t)(e >> 48);
+                    last = l > last ? l : last;
+                    break;
+                }
+            }
+            slot = (slot + 1) & tmask;
+        }
+    }
+    return hit;
+}
+
+// Thread-serial copy of `len` bytes inside shared memory.  The destination is brought to 4- and then
+// 16-byte alignment, the body moves 16 bytes per iteration (4 LDS.32 + 4 funnel shifts + 1 STS.128);
+// the source is only ever read as aligned words.
+__device__ __forceinline__ void tcopy(uint8_t *dst, const uint8_t *src, uint32_t len) {
+    while (len && ((uint32_t)(uintptr_t)dst & 3u)) {
+        *dst++ = *src++;
+        len--;
+    }
+    if (len >= 4) {
+        const uint32_t sh = ((uint32_t)(uintptr_t)src & 3u) * 8u;
+        const uint32_t *sw = (const uint32_t *)((uintptr_t)src & ~(uintptr_t)3);
+        uint32_t *dw = (uint32_t *)dst;
+        uint32_t nwords = len >> 2;
+        uint32_t lo = *sw++;
+        while (nwords && ((uint32_t)(uintptr_t)dw & 15u)) {
+            const uint32_t hi = *sw++;
+            *dw++ = __funnelshift_r(lo, hi, sh);
+            lo = hi;
+            nwords--;
+        }
+        for (; nwords >= 4; nwords -= 4) {
+            const uint32_t w1 = sw[0], w2 = sw[1], w3 = sw[2], w4 = sw[3];
+            uint4 o;
+            o.x = __funnelshift_r(lo, w1, sh);
+            o.y = __funnelshift_r(w1, w2, sh);
+            o.z = __funnelshift_r(w2, w3, sh);
+            o.w = __funnelshift_r(w3, w4, sh);
+            *(uint4 *)dw = o;
+            lo = w4;
+            sw += 4;
+            dw += 4;
+        }
+        while (nwords) {
+            const uint32_t hi = *sw++;
+            *dw++ = __funnelshift_r(lo, hi, sh);
+            lo = hi;
+            nwords--;
+        }
+        const uint32_t done = len & ~3u;
+        dst += done;
+        src += done;
+        len &= 3u;
+    }
+    while (len) {
+        *dst++ = *src++;
+        len--;
+    }
+}
+// byte-wise variant for rare paths (global sources / unstaged global destination)
+__device__ __forceinline__ void bcopy(uint8_t *dst, const uint8_t *src, uint32_t len) {
+    for (uint32_t i = 0; i < len; i++) dst[i] = src[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -269,40 +595,62 @@ struct Misc {
     uint64_t out_base;  // where this chunk's output goes
     uint32_t chunk;
     uint32_t chunk_out;
-    uint32_t cta_total, cta_ident;
+    uint32_t cta_total, cta_ident, cta_slow;
+    uint32_t n_slow;
     uint32_t scratch[40];
 };
 
+#ifdef SK_PHASE_TIMING
+#define SK_T(i)                                              \
+    do {                                                     \
+        if (tid == 0) {                                      \
+            const long long t_now = clock64();               \
+            ph[i] += (unsigned long long)(t_now - t_prev);   \
+            t_prev = t_now;                                  \
+        }                                                    \
+    } while (0)
+#else
+#define SK_T(i) do { } while (0)
+#endif
+
 template <class Cfg, int OP, typename WT>
-__global__ void __launch_bounds__(Cfg::NT, 2) sk_chunk_kernel(const __grid_constant__ KParams p) {
+__global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const __grid_constant__ KParams p) {
     constexpr int NT = Cfg::NT, NW = NT / 32, MAXREC = Cfg::MAXREC, MAXLINES = Cfg::MAXLINES;
     constexpr bool WIDE = sizeof(WT) == 8;
+    constexpr int NWMAX = WIDE ? 16 : 8;
     constexpr bool IS_DEMUX = (OP == OP_DEMUX1 || OP == OP_DEMUX2);
     constexpr bool ORDERED = (OP == OP_TRIM || OP == OP_MASK || OP == OP_ADDBC);
     constexpr bool HAS_OUT = ORDERED || IS_DEMUX;
     static_assert(MAXREC <= NT, "one planning thread per record");
 
     const uint32_t S = IS_DEMUX ? p.sheet.S : 0u;
-    const SmemLayout SL = smem_layout<Cfg>(S, WIDE ? 1u : 0u);
+    const uint32_t FC = (OP == OP_DEMUX1) ? p.sheet.fast.n_classes : 0u;
+    const uint32_t FT = (OP == OP_DEMUX1) ? p.sheet.fast.tsize : 0u;
+    const SmemLayout SL = smem_layout<Cfg>(S, WIDE ? 1u : 0u, FC, FT);
     uint8_t *win = sk_smem + SL.win;
     uint8_t *stage = sk_smem + SL.stage;
     uint16_t *ls = (uint16_t *)(sk_smem + SL.ls);
     uint32_t *r_outoff = (uint32_t *)(sk_smem + SL.rec);
-    uint32_t *r_outlen = r_outoff + MAXREC;
-    uint32_t *r_ext = r_outlen + MAXREC;
-    uint16_t *r_alen = (uint16_t *)(r_ext + MAXREC);
-    uint16_t *r_cut1 = r_alen + MAXREC;
-    uint16_t *r_blen = r_cut1 + MAXREC;
+    uint32_t *r_aux = r_outoff + MAXREC;  // ADDBC: barcode offset; demux: sample << 16 | out_len
+    uint16_t *r_outlen = (uint16_t *)(r_aux + MAXREC);
+    uint16_t *r_cut0 = r_outlen + MAXREC;
+    uint16_t *r_cut1 = r_cut0 + MAXREC;
+    uint16_t *r_alen = r_cut1 + MAXREC;
+    uint16_t *r_blen = r_alen + MAXREC;
     uint16_t *r_k = r_blen + MAXREC;
     uint16_t *r_taglen = r_k + MAXREC;
     int16_t *r_sample = (int16_t *)(r_taglen + MAXREC);
     uint8_t *r_mode = (uint8_t *)(r_sample + MAXREC);
+    uint8_t *r_flags = r_mode + MAXREC;
     WT *sh_planes = (WT *)(sk_smem + SL.sheet);
     WT *sh_umask = (WT *)(sk_smem + SL.umask);
     uint8_t *sh_lut = sk_smem + SL.lut;
     uint32_t *hist = (uint32_t *)(sk_smem + SL.hist);
     uint32_t *sbase = (uint32_t *)(sk_smem + SL.sbase);
     uint32_t *ccount = (uint32_t *)(sk_smem + SL.ccount);
+    uint32_t *f_cls = (uint32_t *)(sk_smem + SL.fcls);
+    unsigned long long *f_tab = (unsigned long long *)(sk_smem + SL.ftab);
+    uint16_t *slow_list = (uint16_t *)(sk_smem + SL.slow);
     Misc *M = (Misc *)(sk_smem + SL.misc);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -313,6 +661,7 @@ __global__ void __launch_bounds__(Cfg::NT, 2) sk_chunk_kernel(const __grid_const
         mbar_init(&M->mbar, 1);
         M->cta_total = 0;
         M->cta_ident = 0;
+        M->cta_slow = 0;
     }
     if (IS_DEMUX) {
         const WT *gp = (const WT *)p.sheet.planes;
@@ -322,18 +671,28 @@ __global__ void __launch_bounds__(Cfg::NT, 2) sk_chunk_kernel(const __grid_const
             sh_umask[i] = gu[i];
             ccount[i] = 0;
         }
-        if (tid < 256) sh_lut[tid] = p.sheet.lut[tid];
+        for (uint32_t i = tid; i < 256; i += NT) sh_lut[i] = p.sheet.lut[i];
+        for (uint32_t i = tid; i < FC * FAST_CLS_WORDS; i += NT) f_cls[i] = p.sheet.fast.cls[i];
+        for (uint32_t i = tid; i < FC * FT; i += NT) f_tab[i] = p.sheet.fast.table[i];
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
+#ifdef SK_PHASE_TIMING
+    unsigned long long ph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long t_prev = clock64();
+#endif
     uint32_t parity = 0;
     for (;;) {
         // ---- P0 ticket
-        if (tid == 0) M->chunk = atomicAdd(&st->ticket, 1u);
+        if (tid == 0) {
+            M->chunk = atomicAdd(&st->ticket, 1u);
+            M->n_slow = 0;
+        }
         __syncthreads();
         const uint32_t c = M->chunk;
         if (c >= p.n_chunks) break;
+        SK_T(0);  // ticket
 
         const uint64_t c0 = (uint64_t)c * Cfg::CHUNK;
         const uint64_t w0 = c0 ? c0 - Cfg::PRE : 0;
@@ -347,7 +706,7 @@ __global__ void __launch_bounds__(Cfg::NT, 2) sk_chunk_kernel(const __grid_const
         // ---- P1 load the window: TMA bulk copy for the 16-byte multiple, plain loads for the tail
         const uint32_t bulk = wlen & ~15u;
         if (tid == 0 && bulk) {
-            fence_proxy_async();  // order earlier generic-proxy reads of `win` before the async write
+            fence_proxy_async();  // order earlier generic-proxy accesses to `win` before the async write
             mbar_expect_tx(&M->mbar, bulk);
             bulk_g2s(win, p.in + w0, bulk, &M->mbar);
         }
@@ -355,50 +714,74 @@ __global__ void __launch_bounds__(Cfg::NT, 2) sk_chunk_kernel(const __grid_const
             const uint32_t o = bulk + tid;
             if (o < (uint32_t)Cfg::WIN_MAX) win[o] = (o < wlen) ? p.in[w0 + o] : (uint8_t)0;
         }
-        if (bulk) mbar_wait(&M->mbar, parity);
-        if (bulk) parity ^= 1;
+        if (bulk) {
+            mbar_wait(&M->mbar, parity);
+            parity ^= 1;
+        }
         __syncthreads();
+        SK_T(1);  // window load
 
-        // ---- P2 newline scan: 80 contiguous bytes per thread
-        const uint32_t ls_lo = cs ? cs - 1 : 0;              // newline at q starts a line at q+1 >= cs
-        const uint32_t ls_hi = at_end ? (wlen ? wlen - 1 : 0) : wlen;  // a final '\n' starts no line in this buffer
-        uint32_t m16[Cfg::PPL];
+        // ---- P2 newline scan: 80 contiguous bytes per thread, kept as 5 piece maps
+        // A '\n' at window offset q starts a line at q+1.  Lines that start before the chunk belong to
+        // the previous chunk (q+1 >= cs); a '\n' that is the last byte of the buffer starts nothing.
+        const uint32_t ls_lo = cs ? cs - 1 : 0;
+        const uint32_t ls_hi = at_end ? (wlen ? wlen - 1 : 0) : wlen;
+        uint32_t ymap[Cfg::PPL];
         uint32_t cnt_all = 0, cnt_chunk = 0, hib = 0;
 #pragma unroll
         for (int q = 0; q < Cfg::PPL; q++) {
             const uint32_t o = (uint32_t)tid * (Cfg::PPL * 16) + q * 16;
-            uint32_t m = 0;
+            uint32_t y = 0;
             if (o < wlen) {
                 const uint4 v = *(const uint4 *)(win + o);
-                m = nl4(v.x) | (nl4(v.y) << 4) | (nl4(v.z) << 8) | (nl4(v.w) << 12);
-                m &= range16(o, ls_lo, ls_hi);
-                hib |= (v.x | v.y | v.z | v.w) & 0x80808080u;  // bytes past wlen in the last piece are zero
+                y = nl_map(v);
+                hib |= (v.x | v.y | v.z | v.w);  // bytes past wlen in the last piece are zero
+                if (o < ls_lo || o + 16 > ls_hi) y = map_clip(y, o, ls_lo, ls_hi);
+                const uint32_t n = __popc(y);
+                cnt_all += n;
+                if (o + 16 <= ce - 1) cnt_chunk += n;
+                else if (o < ce - 1) cnt_chunk += __popc(map_clip(y, o, 0, ce - 1));
             }
-            m16[q] = m;
-            cnt_all += __popc(m);
-            cnt_chunk += __popc(m & range16(o, 0, ce - 1));
+            ymap[q] = y;
         }
-        if (__any_sync(0xffffffffu, hib != 0) && lane == 0) atomicOr(&st->flags, F_NON_ASCII);
+        if (__any_sync(0xffffffffu, (hib & 0x80808080u) != 0) && lane == 0) atomicOr(&st->flags, F_NON_ASCII);
 
         uint32_t tot;
         const uint32_t pre = block_excl_scan<NT>((cnt_chunk << 16) | cnt_all, M->scratch, tot);
-        const uint32_t extra = (c0 == 0) ? 1u : 0u;  // the line that starts at byte 0
-        const uint32_t nls = (tot & 0xFFFFu) + extra;       // line starts in [cs, wlen)
-        const uint32_t nls_chunk = (tot >> 16) + extra;     // ... of which inside the chunk
+        const uint32_t extra = (c0 == 0) ? 1u : 0u;      // the line that starts at byte 0
+        const uint32_t nls = (tot & 0xFFFFu) + extra;    // line starts in [cs, wlen)
+        const uint32_t nls_chunk = (tot >> 16) + extra;  // ... of which inside the chunk
 
+        SK_T(2);  // scan + block scan
         // ---- P3 line-start table + look-back for the global line index
         {
             uint32_t idx = (pre & 0xFFFFu) + extra;
             if (tid == 0 && extra) ls[0] = 0;
 #pragma unroll
             for (int q = 0; q < Cfg::PPL; q++) {
-                uint32_t m = m16[q];
-                const uint32_t o = (uint32_t)tid * (Cfg::PPL * 16) + q * 16;
-                while (m) {
-                    const uint32_t b2 = __ffs(m) - 1;
-                    m &= m - 1;
-                    if (idx < (uint32_t)MAXLINES) ls[idx] = (uint16_t)(o + b2 + 1);
-                    idx++;
+                const uint32_t y = ymap[q];
+                if (y) {
+                    const uint32_t o = (uint32_t)tid * (Cfg::PPL * 16) + q * 16;
+                    const uint32_t y2 = y & (y - 1);
+                    const uint32_t i1 = __ffs(y) - 1;
+                    const uint32_t k1 = 4u * (i1 & 7u) + (i1 >> 3);  // piece offset of a map bit
+                    if (y2 == 0) {  // one newline in the piece
+                        if (idx < (uint32_t)MAXLINES) ls[idx] = (uint16_t)(o + k1 + 1u);
+                        idx++;
+                    } else if ((y2 & (y2 - 1)) == 0) {  // two ("\n+\n" puts two in one piece for most records)
+                        const uint32_t i2 = __ffs(y2) - 1;
+                        const uint32_t k2 = 4u * (i2 & 7u) + (i2 >> 3);
+                        const uint32_t ka = k1 < k2 ? k1 : k2, kb = k1 < k2 ? k2 : k1;
+                        if (idx < (uint32_t)MAXLINES) ls[idx] = (uint16_t)(o + ka + 1u);
+                        if (idx + 1 < (uint32_t)MAXLINES) ls[idx + 1] = (uint16_t)(o + kb + 1u);
+                        idx += 2;
+                    } else {
+                        for (uint32_t k = 0; k < 16; k++)
+                            if ((y >> map_bit(k)) & 1u) {
+                                if (idx < (uint32_t)MAXLINES) ls[idx] = (uint16_t)(o + k + 1u);
+                                idx++;
+                            }
+                    }
                 }
             }
         }
@@ -410,17 +793,18 @@ __global__ void __launch_bounds__(Cfg::NT, 2) sk_chunk_kernel(const __grid_const
             }
         }
         __syncthreads();
+        SK_T(3);  // line table + look-back (lines)
 
         // ---- P4 which records does this chunk own?
         const uint64_t g0 = M->g0;
         const uint32_t lpr = p.lpr;
-        const uint32_t j0 = (uint32_t)((lpr - (g0 % lpr)) % lpr);
+        const uint32_t j0 = (lpr - (uint32_t)(g0 & (lpr - 1))) & (lpr - 1);  // lpr is 2 or 4
         const uint64_t rec0 = (g0 + j0) / lpr;
         uint32_t nrec = j0 < nls_chunk ? (nls_chunk - 1 - j0) / lpr + 1 : 0;
         if (rec0 >= p.rec_limit) nrec = 0;
         else if ((uint64_t)nrec > p.rec_limit - rec0) nrec = (uint32_t)(p.rec_limit - rec0);
-        unsigned chunk_err = 0;
         if (nrec) {
+            unsigned chunk_err = 0;
             uint32_t jend = j0 + nrec * lpr;  // line index one past the last owned record
             const bool eof_ok = at_end && p.final_batch;
             if (jend >= nls && !eof_ok) {
@@ -446,43 +830,51 @@ __global__ void __launch_bounds__(Cfg::NT, 2) sk_chunk_kernel(const __grid_const
             atomicMax(&st->consumed, (unsigned long long)(w0 + lb(W, j0 + nrec * lpr)));
         }
 
-        // ---- P5 plan: one thread per record runs the reference's per-record logic
-        uint32_t my_outlen = 0;
-        if (tid < (int)nrec) {
-            const uint32_t r = tid;
+        // ---- P5a plan: the reference's per-record logic, four lanes per record.  Cheap straight-line
+        // parts run on the group's lane 0; the long scans (trim, " BC:" search, class run) are shared.
+        const uint32_t gm = gmask4();
+        const uint32_t q4 = (uint32_t)tid & 3u;
+        for (uint32_t rbase = 0; rbase < nrec; rbase += NT / 4) {
+            const uint32_t r = rbase + ((uint32_t)tid >> 2);
+            if (r >= nrec) continue;  // whole groups drop out together
             const uint32_t j = j0 + r * lpr;
             const uint64_t rec = rec0 + r;
             const uint32_t L0 = lb(W, j), L1 = lb(W, j + 1), L2 = lb(W, j + 2);
             const uint32_t L3 = lpr == 4 ? lb(W, j + 3) : L2, L4 = lpr == 4 ? lb(W, j + 4) : L2;
             const uint32_t Lend = lpr == 4 ? L4 : L2;
-            uint8_t mode = B_NONE;
-            uint32_t kk = 0, outlen = 0, alen = 0, cut1 = 0, blen = 0, taglen = 0, ext = 0;
+            uint8_t mode = B_NONE, flags = 0;
+            uint32_t kk = 0, outlen = 0, alen = 0, cut0 = 0, cut1 = 0, blen = 0, taglen = 0, ext = 0;
             int sample = -1;
 
             if (OP == OP_SCAN) {
-                // (seq_off, seq_len after trim_end, flags) of an index read / barcode record
-                uint32_t sl = L2 - L1;
-                while (sl > 0 && is_ws(win[L1 + sl - 1])) sl--;
-                uint16_t fl = 0;
-                if (L1 > L0 && win[L0] == '@') fl |= RR_L0_AT;
-                if (L1 > L0 && win[L0] == '>') fl |= RR_L0_GT;
-                if (lpr == 4 && L3 > L2 && win[L2] == '+') fl |= RR_L2_PLUS;
-                if (sl > 0xFFFFu) { fl |= RR_LONG; sl = 0xFFFFu; }
-                if (p.head_char && !(L1 > L0 && win[L0] == (uint8_t)p.head_char)) report_err(st, rec, K_MIXED);
-                if (rec < p.scan_cap) {
-                    RecRef rr;
-                    rr.seq_off = (uint32_t)(w0 + L1);
-                    rr.seq_len = (uint16_t)sl;
-                    rr.flags = fl;
-                    p.scan_out[rec] = rr;
+                if (q4 == 0) {
+                    // (seq_off, seq_len after trim_end, flags) of an index read / barcode record
+                    uint32_t sl = L2 - L1;
+                    while (sl > 0 && is_ws(win[L1 + sl - 1])) sl--;
+                    uint16_t fl = 0;
+                    if (L1 > L0 && win[L0] == '@') fl |= RR_L0_AT;
+                    if (L1 > L0 && win[L0] == '>') fl |= RR_L0_GT;
+                    if (lpr == 4 && L3 > L2 && win[L2] == '+') fl |= RR_L2_PLUS;
+                    if (sl > 0xFFFFu) {
+                        fl |= RR_LONG;
+                        sl = 0xFFFFu;
+                    }
+                    if (p.head_char && !(L1 > L0 && win[L0] == (uint8_t)p.head_char)) report_err(st, rec, K_MIXED);
+                    if (rec < p.scan_cap) {
+                        RecRef rr;
+                        rr.seq_off = (uint32_t)(w0 + L1);
+                        rr.seq_len = (uint16_t)sl;
+                        rr.flags = fl;
+                        p.scan_out[rec] = rr;
+                    }
                 }
             } else if (OP == OP_TRIM) {
                 if (win[L0] != '@') {  // fasta_trim_by_quality.rs:20-22
-                    report_err(st, rec, K_BAD_HEADER);
+                    if (q4 == 0) report_err(st, rec, K_BAD_HEADER);
                 } else {
                     uint32_t body;
-                    if (!plan_trim_body(W, L1, L2, L3, L4, (int)p.min_baseq, mode, kk, body)) {
-                        report_err(st, rec, K_SEQ_SHORT);
+                    if (!plan_trim_body4(win, gm, q4, L1, L2, L3, L4, (int)p.min_baseq, mode, kk, body)) {
+                        if (q4 == 0) report_err(st, rec, K_SEQ_SHORT);
                         mode = B_NONE;
                     } else {
                         outlen = (L1 - L0) + body;  // header verbatim (:23) + body
@@ -490,13 +882,13 @@ __global__ void __launch_bounds__(Cfg::NT, 2) sk_chunk_kernel(const __grid_const
                 }
             } else if (OP == OP_MASK) {
                 if (win[L0] != '@') {  // fasta_mask_by_quality.rs:21-23
-                    report_err(st, rec, K_BAD_HEADER);
+                    if (q4 == 0) report_err(st, rec, K_BAD_HEADER);
                 } else {
                     uint32_t sl = L2 - L1, ql = L4 - L3;
                     if (sl && win[L2 - 1] == '\n') sl--;  // :32
                     if (ql && win[L4 - 1] == '\n') ql--;  // :33
                     if (sl != ql) {                       // :35-37
-                        report_err(st, rec, K_LEN_MISMATCH);
+                        if (q4 == 0) report_err(st, rec, K_LEN_MISMATCH);
                     } else {
                         mode = B_MASK;
                         kk = sl;
@@ -521,131 +913,83 @@ __global__ void __launch_bounds__(Cfg::NT, 2) sk_chunk_kernel(const __grid_const
                 }
                 taglen = 4 + bl;  // " BC:" + barcode
                 ext = bo;
+                cut1 = alen;
                 if (h != (uint8_t)p.head_char) {
                     // the reference prints the BC'd header and then stops (:33 before :41-43); the host
                     // reproduces that line, the kernel only reports where.
-                    report_err(st, rec, (h == '@' || h == '>') ? K_MIXED : K_BAD_FASTX_LINE);
+                    if (q4 == 0) report_err(st, rec, (h == '@' || h == '>') ? K_MIXED : K_BAD_FASTX_LINE);
                     taglen = 0;
                 } else {
                     mode = B_VERBATIM;
                     outlen = alen + taglen + 1 + (Lend - L1);
                 }
             } else if (OP == OP_DEMUX1) {
-                bool ok = true;
-                if (win[L0] != '@') {  // fasta_demultiplex.rs:118-120
-                    report_err(st, rec, K_BAD_HEADER);
-                    ok = false;
-                }
-                uint32_t c0h = L1, c1h = L1;  // cut [c0h, c1h) (window offsets); empty on the index route
-                uint32_t bclen = 0;
-                RecRef ir[2];
-                uint32_t sep = 0;
-                if (ok && p.n_index) {  // :126-136
-                    for (uint32_t q = 0; q < p.n_index && ok; q++) {
-                        if (rec >= p.ext_stats[q]->n_records) { ok = false; break; }
-                        ir[q] = p.ext_tab[q][rec];
-                        if (!(ir[q].flags & RR_L0_AT) || !(ir[q].flags & RR_L2_PLUS)) ok = false;
-                    }
-                    if (!ok) report_err(st, rec, K_INDEX_ASSERT);
-                    else {
-                        bclen = ir[0].seq_len;
-                        if (p.n_index == 2) {
-                            sep = bclen ? 1u : 0u;  // '+' only if the barcode so far is non-empty (:128)
-                            bclen += sep + ir[1].seq_len;
-                        }
-                    }
-                } else if (ok) {  // :138-146
-                    if (!bc_find(win, L0, L1, c0h, c1h)) {
-                        report_err(st, rec, K_NO_BC);
-                        ok = false;
+                // fasta_demultiplex.rs:117-150: validate, locate the barcode, try the exact-match index.
+                // Anything the index cannot settle is queued for the warp-cooperative matcher (P5b).
+                flags = RF_DEAD;
+                if (win[L0] != '@') {  // :118-120
+                    if (q4 == 0) report_err(st, rec, K_BAD_HEADER);
+                } else if (p.fused_trim >= 0 && !(L1 > L0 && win[L1 - 1] == '\n')) {
+                    if (q4 == 0) report_err(st, rec, K_TRUNC_FUSED);
+                } else if (p.n_index) {
+                    flags = RF_SLOW;  // --index route: the barcode lives in other streams (:126-136)
+                } else {
+                    uint32_t stp;
+                    if (!bc_find4(win, sh_lut, gm, q4, L0, L1, stp)) {  // :138-141
+                        if (q4 == 0) report_err(st, rec, K_NO_BC);
                     } else {
-                        bclen = c1h - (c0h + 4);
-                    }
-                }
-                if (ok && bclen != p.sheet.L) {  // :148-150
-                    report_err(st, rec, K_BC_LEN);
-                    ok = false;
-                }
-                if (ok && p.fused_trim >= 0 && !(L1 > L0 && win[L1 - 1] == '\n')) {
-                    report_err(st, rec, K_TRUNC_FUSED);
-                    ok = false;
-                }
-                if (ok) {
-                    // observed barcode byte p
-                    auto obs = [&](uint32_t q) -> uint8_t {
-                        if (!p.n_index) return win[c0h + 4 + q];
-                        if (q < ir[0].seq_len) return p.ext_data[0][(uint64_t)ir[0].seq_off + q];
-                        if (q < ir[0].seq_len + sep) return (uint8_t)'+';
-                        return p.ext_data[1][(uint64_t)ir[1].seq_off + (q - ir[0].seq_len - sep)];
-                    };
-                    WT o0 = 0, o1 = 0, o2 = 0;
-                    for (uint32_t q = 0; q < bclen; q++) {
-                        const uint32_t code = sh_lut[obs(q)];
-                        o0 |= (WT)(code & 1u) << q;
-                        o1 |= (WT)((code >> 1) & 1u) << q;
-                        o2 |= (WT)((code >> 2) & 1u) << q;
-                    }
-                    uint32_t lowest, best, last;
-                    match_sheet<WT>(sh_planes, S, o0, o1, o2, lowest, best, last);  // :154-166
-                    atomicAdd(&M->cta_total, 1u);                                   // :169
-                    if (lowest <= 1u) {                                             // :172
-                        if (best == last) {
-                            sample = (int)best;
-                            atomicAdd(&M->cta_ident, 1u);  // :177
-                            atomicAdd(&ccount[best], 1u);  // :178
-                        } else {                           // :184-188
-                            sample = -2;
-                            const uint32_t ei = atomicAdd(&st->n_events, 1u);
-                            if (ei < p.events_cap) {
-                                Event ev;
-                                ev.record = (uint32_t)rec;
-                                ev.bc_off = p.n_index ? ir[0].seq_off : (uint32_t)(w0 + c0h + 4);
-                                ev.bc_off2 = p.n_index == 2 ? ir[1].seq_off : 0xFFFFFFFFu;
-                                ev.best = (int16_t)best;
-                                ev.last = (int16_t)last;
-                                ev.mismatches = lowest;
-                                p.events[ei] = ev;
-                            } else {
-                                atomicOr(&st->flags, F_EVENTS_OVERFLOW);
+                        flags = RF_SLOW;
+                        cut0 = stp - L0;
+                        const uint32_t bs = stp + 4, be = bs + p.sheet.L;
+                        // Fast path: the class run is exactly L long (next byte is outside the class or the
+                        // header ends) and the cared bytes equal some sample's barcode.
+                        if (FC && be <= L1 && (be == L1 || !(sh_lut[win[be]] & 8u))) {
+                            uint32_t best, last;
+                            if (fast_lookup4<NWMAX>(win, gm, q4, bs, p.sheet.fast.nw, FC, FT - 1, f_cls, f_tab,
+                                                    p.sheet.fast.skeys, best, last)) {
+                                // the run must not stop early: wildcard positions need class bytes too
+                                if (bc_run_end4(win, sh_lut, gm, q4, bs + 1, be) == be) {
+                                    flags = 0;
+                                    cut1 = be - L0;
+                                    sample = best == last ? (int)best : -2;
+                                    if (q4 == 0) {
+                                        atomicAdd(&M->cta_total, 1u);  // :169
+                                        if (best == last) {            // distance 0, unambiguous (:172-178)
+                                            atomicAdd(&M->cta_ident, 1u);
+                                            atomicAdd(&ccount[best], 1u);
+                                        } else {  // two samples at distance 0 (:184-188)
+                                            const uint32_t ei = atomicAdd(&st->n_events, 1u);
+                                            if (ei < p.events_cap) {
+                                                Event ev;
+                                                ev.record = (uint32_t)rec;
+                                                ev.bc_off = (uint32_t)(w0 + bs);
+                                                ev.bc_off2 = 0xFFFFFFFFu;
+                                                ev.best = (int16_t)best;
+                                                ev.last = (int16_t)last;
+                                                ev.mismatches = 0;
+                                                p.events[ei] = ev;
+                                            } else {
+                                                atomicOr(&st->flags, F_EVENTS_OVERFLOW);
+                                            }
+                                        }
+                                    }
+                                }
                             }
                         }
                     }
-                    if (sample >= 0) {
-                        // UMI = observed chars where the sheet barcode has 'U' (:200-203)
-                        uint32_t ul = 0;
-                        WT um = sh_umask[sample];
-                        while (um) {
-                            const uint32_t q = WIDE ? (uint32_t)(__ffsll((long long)um) - 1) : (uint32_t)(__ffs((int)um) - 1);
-                            um &= um - 1;
-                            p.umi[rec * p.sheet.Umax + ul] = obs(q);
-                            ul++;
-                        }
-                        taglen = ul ? 5 + ul : 0;  // " UMI:" + umi (:207)
-                        header_pieces(win, L0, L1, c0h, c1h, alen, blen);  // drain (:145) + trim_end (:206)
-                        cut1 = c1h - L0;
-                        uint32_t body = Lend - L1;  // three lines verbatim (:209-212)
-                        mode = B_VERBATIM;
-                        bool fine = true;
-                        if (p.fused_trim >= 0) fine = plan_trim_body(W, L1, L2, L3, L4, p.fused_trim, mode, kk, body);
-                        if (!fine) {
-                            report_err(st, rec, K_SEQ_SHORT);
-                            sample = -1;
-                            mode = B_NONE;
-                        } else if (!p.out) {
-                            mode = B_NONE;  // dry run: count only (:77-78,:179)
-                        } else {
-                            outlen = alen + blen + taglen + 1 + body;
-                        }
-                    }
                 }
+                if ((flags & RF_SLOW) && q4 == 0) slow_list[atomicAdd(&M->n_slow, 1u)] = (uint16_t)r;
             } else if (OP == OP_DEMUX2) {
                 // fasta_demultiplex.rs:215-237: mate 2 of an assigned pair
                 sample = rec < p.r1_stats->n_records ? (int)p.assign[rec] : -1;
                 if (sample >= 0 && p.out) {
                     uint32_t c0h = L1, c1h = L1;
                     if (!p.n_index) {  // :219-227
-                        uint32_t a, b;
-                        if (bc_find(win, L0, L1, a, b)) { c0h = a; c1h = b; }
+                        uint32_t a;
+                        if (bc_find4(win, sh_lut, gm, q4, L0, L1, a)) {
+                            c0h = a;
+                            c1h = bc_run_end4(win, sh_lut, gm, q4, a + 5, L1);
+                        }
                     }
                     header_pieces(win, L0, L1, c0h, c1h, alen, blen);  // :229
                     cut1 = c1h - L0;
@@ -656,10 +1000,10 @@ __global__ void __launch_bounds__(Cfg::NT, 2) sk_chunk_kernel(const __grid_const
                     bool fine = true;
                     if (p.fused_trim >= 0) {
                         if (!(L1 > L0 && win[L1 - 1] == '\n')) {
-                            report_err(st, rec, K_TRUNC_FUSED);
+                            if (q4 == 0) report_err(st, rec, K_TRUNC_FUSED);
                             fine = false;
-                        } else if (!plan_trim_body(W, L1, L2, L3, L4, p.fused_trim, mode, kk, body)) {
-                            report_err(st, rec, K_SEQ_SHORT);
+                        } else if (!plan_trim_body4(win, gm, q4, L1, L2, L3, L4, p.fused_trim, mode, kk, body)) {
+                            if (q4 == 0) report_err(st, rec, K_SEQ_SHORT);
                             fine = false;
                         }
                     }
@@ -667,51 +1011,279 @@ __global__ void __launch_bounds__(Cfg::NT, 2) sk_chunk_kernel(const __grid_const
                     else mode = B_NONE;
                 }
             }
-            r_outlen[r] = outlen;
-            r_ext[r] = ext;
-            r_alen[r] = (uint16_t)alen;
-            r_cut1[r] = (uint16_t)cut1;
-            r_blen[r] = (uint16_t)blen;
-            r_k[r] = (uint16_t)kk;
-            r_taglen[r] = (uint16_t)taglen;
-            r_sample[r] = (int16_t)sample;
-            r_mode[r] = mode;
-            my_outlen = outlen;
+            if (q4 == 0) {
+                r_outlen[r] = (uint16_t)(outlen > 0xFFFFu ? 0xFFFFu : outlen);
+                if (OP == OP_ADDBC) r_aux[r] = ext;
+                r_cut0[r] = (uint16_t)cut0;
+                r_cut1[r] = (uint16_t)cut1;
+                r_alen[r] = (uint16_t)alen;
+                r_blen[r] = (uint16_t)blen;
+                r_k[r] = (uint16_t)kk;
+                r_taglen[r] = (uint16_t)taglen;
+                r_sample[r] = (int16_t)sample;
+                r_mode[r] = mode;
+                r_flags[r] = flags;
+            }
+        }
+
+        if (OP != OP_DEMUX1) __syncthreads();  // plans are written by each group's lane 0, read by thread r
+        if (OP == OP_DEMUX1) {
+            __syncthreads();
+            SK_T(4);  // plan A
+            // ---- P5b brute-force matcher, one warp per queued record (fasta_demultiplex.rs:126-194):
+            // lanes encode the observed barcode into bit planes with ballots, then split the samples.
+            const uint32_t n_slow = M->n_slow;
+            for (uint32_t si = warp; si < n_slow; si += NW) {
+                const uint32_t r = slow_list[si];
+                const uint32_t j = j0 + r * lpr;
+                const uint64_t rec = rec0 + r;
+                const uint32_t L0 = lb(W, j), L1 = lb(W, j + 1);
+                const uint32_t Lb = p.sheet.L;
+                uint32_t bs = 0, bclen = 0, sep = 0, c1h = L1;
+                RecRef ir0{0, 0, 0}, ir1{0, 0, 0};
+                bool ok = true;
+                if (p.n_index) {
+                    for (uint32_t q = 0; q < p.n_index && ok; q++) {
+                        if (rec >= p.ext_stats[q]->n_records) {
+                            ok = false;
+                            break;
+                        }
+                        const RecRef t = p.ext_tab[q][rec];
+                        if (!(t.flags & RR_L0_AT) || !(t.flags & RR_L2_PLUS)) ok = false;  // :130,:134
+                        if (q == 0) ir0 = t;
+                        else ir1 = t;
+                    }
+                    if (!ok) {
+                        if (lane == 0) report_err(st, rec, K_INDEX_ASSERT);
+                    } else {
+                        bclen = ir0.seq_len;
+                        if (p.n_index == 2) {
+                            sep = bclen ? 1u : 0u;  // '+' only if the barcode so far is non-empty (:128)
+                            bclen += sep + ir1.seq_len;
+                        }
+                    }
+                } else {
+                    const uint32_t stp = L0 + r_cut0[r];
+                    bs = stp + 4;
+                    // greedy class run from bs+1 (bs itself is a class byte): first non-class offset
+                    uint32_t e = L1;
+                    for (uint32_t base = bs + 1; base < L1; base += 32) {
+                        const uint32_t q = base + lane;
+                        const bool stop = q < L1 && !(sh_lut[win[q]] & 8u);
+                        const uint32_t m = __ballot_sync(0xffffffffu, stop);
+                        if (m) {
+                            e = base + __ffs(m) - 1;
+                            break;
+                        }
+                    }
+                    c1h = e;
+                    bclen = e - bs;
+                }
+                if (ok && bclen != Lb) {  // :148-150
+                    if (lane == 0) report_err(st, rec, K_BC_LEN);
+                    ok = false;
+                }
+                int sample = -1;
+                if (ok) {
+                    auto obs = [&](uint32_t q) -> uint8_t {
+                        if (!p.n_index) return win[bs + q];
+                        if (q < ir0.seq_len) return p.ext_data[0][(uint64_t)ir0.seq_off + q];
+                        if (q < ir0.seq_len + sep) return (uint8_t)'+';
+                        return p.ext_data[1][(uint64_t)ir1.seq_off + (q - ir0.seq_len - sep)];
+                    };
+                    WT o0 = 0, o1 = 0, o2 = 0;
+                    for (uint32_t base = 0; base < Lb; base += 32) {
+                        const uint32_t q = base + lane;
+                        const uint32_t code = q < Lb ? (uint32_t)sh_lut[obs(q)] : 0u;
+                        o0 |= (WT)__ballot_sync(0xffffffffu, code & 1u) << base;
+                        o1 |= (WT)__ballot_sync(0xffffffffu, code & 2u) << base;
+                        o2 |= (WT)__ballot_sync(0xffffffffu, code & 4u) << base;
+                    }
+                    // each lane scans samples lane, lane+32, ...; then merge (lowest, first, last)
+                    uint32_t lowest = 0xFFFFFFFFu, best = 0xFFFFFFFFu, last = 0;
+                    for (uint32_t s2 = lane; s2 < S; s2 += 32) {
+                        const WT p0 = sh_planes[4 * s2], p1 = sh_planes[4 * s2 + 1], p2 = sh_planes[4 * s2 + 2],
+                                 care = sh_planes[4 * s2 + 3];
+                        const uint32_t d = popcw<WT>(((o0 ^ p0) | (o1 ^ p1) | (o2 ^ p2)) & care);
+                        if (d < lowest) {
+                            lowest = d;
+                            best = s2;
+                            last = s2;
+                        } else if (d == lowest) {
+                            last = s2;
+                        }
+                    }
+#pragma unroll
+                    for (int o = 16; o; o >>= 1) {
+                        const uint32_t l2 = __shfl_xor_sync(0xffffffffu, lowest, o);
+                        const uint32_t b2 = __shfl_xor_sync(0xffffffffu, best, o);
+                        const uint32_t a2 = __shfl_xor_sync(0xffffffffu, last, o);
+                        if (l2 < lowest) {
+                            lowest = l2;
+                            best = b2;
+                            last = a2;
+                        } else if (l2 == lowest) {
+                            best = b2 < best ? b2 : best;
+                            last = a2 > last ? a2 : last;
+                        }
+                    }
+                    if (lane == 0) {
+                        atomicAdd(&M->cta_total, 1u);  // :169
+                        atomicAdd(&M->cta_slow, 1u);
+                        if (lowest <= 1u) {            // :172
+                            if (best == last) {
+                                sample = (int)best;
+                                atomicAdd(&M->cta_ident, 1u);  // :177
+                                atomicAdd(&ccount[best], 1u);  // :178
+                            } else {                           // :184-188
+                                sample = -2;
+                                const uint32_t ei = atomicAdd(&st->n_events, 1u);
+                                if (ei < p.events_cap) {
+                                    Event ev;
+                                    ev.record = (uint32_t)rec;
+                                    ev.bc_off = p.n_index ? ir0.seq_off : (uint32_t)(w0 + bs);
+                                    ev.bc_off2 = p.n_index == 2 ? ir1.seq_off : 0xFFFFFFFFu;
+                                    ev.best = (int16_t)best;
+                                    ev.last = (int16_t)last;
+                                    ev.mismatches = lowest;
+                                    p.events[ei] = ev;
+                                } else {
+                                    atomicOr(&st->flags, F_EVENTS_OVERFLOW);
+                                }
+                            }
+                        }
+                    }
+                    sample = __shfl_sync(0xffffffffu, sample, 0);
+                    if (sample >= 0) {
+                        // UMI = observed chars where the sheet barcode has 'U' (:200-203), lanes in parallel
+                        const WT um = sh_umask[sample];
+                        for (uint32_t base = 0; base < Lb; base += 32) {
+                            const uint32_t q = base + lane;
+                            if (q < Lb && ((um >> q) & 1u)) {
+                                const uint32_t rank = popcw<WT>(um & (((WT)1 << q) - 1));
+                                p.umi[rec * p.sheet.Umax + rank] = obs(q);
+                            }
+                        }
+                    }
+                }
+                if (lane == 0) {
+                    r_sample[r] = (int16_t)sample;
+                    r_cut1[r] = (uint16_t)(c1h - L0);
+                    r_flags[r] = ok ? (uint8_t)RF_SLOW : (uint8_t)RF_DEAD;
+                }
+            }
+            __syncthreads();
+            SK_T(5);  // slow matcher
+            // ---- P5c finish the plan of assigned records (fasta_demultiplex.rs:196-212), 4 lanes each
+            for (uint32_t rbase = 0; rbase < nrec; rbase += NT / 4) {
+                const uint32_t r = rbase + ((uint32_t)tid >> 2);
+                if (r >= nrec) continue;
+                const int sample = r_sample[r];
+                uint32_t outlen = 0;
+                if (sample >= 0 && !(r_flags[r] & RF_DEAD)) {
+                    const uint32_t j = j0 + r * lpr;
+                    const uint64_t rec = rec0 + r;
+                    const uint32_t L0 = lb(W, j), L1 = lb(W, j + 1), L2 = lb(W, j + 2), L3 = lb(W, j + 3),
+                                   L4 = lb(W, j + 4);
+                    const uint32_t c0h = p.n_index ? L1 : L0 + r_cut0[r], c1h = p.n_index ? L1 : L0 + r_cut1[r];
+                    const WT um = sh_umask[sample];
+                    const uint32_t ul = popcw<WT>(um);
+                    if (ul && !(r_flags[r] & RF_SLOW) && q4 == 0) {  // queued records: the matcher warp wrote it
+                        WT m = um;
+                        uint32_t t = 0;
+                        while (m) {
+                            const uint32_t q = ffsw<WT>(m);
+                            m &= m - 1;
+                            p.umi[rec * p.sheet.Umax + t++] = win[c0h + 4 + q];
+                        }
+                    }
+                    uint32_t alen, blen;
+                    header_pieces(win, L0, L1, c0h, c1h, alen, blen);  // drain (:145) + trim_end (:206)
+                    const uint32_t taglen = ul ? 5 + ul : 0;           // " UMI:" + umi (:207)
+                    uint32_t body = L4 - L1, kk = 0;                   // three lines verbatim (:209-212)
+                    uint8_t mode = B_VERBATIM;
+                    bool fine = true;
+                    if (p.fused_trim >= 0)
+                        fine = plan_trim_body4(win, gm, q4, L1, L2, L3, L4, p.fused_trim, mode, kk, body);
+                    if (!fine) {
+                        if (q4 == 0) {
+                            report_err(st, rec, K_SEQ_SHORT);
+                            r_sample[r] = -1;
+                        }
+                        mode = B_NONE;
+                    } else if (!p.out) {
+                        mode = B_NONE;  // dry run: count only (:77-78,:179)
+                    } else {
+                        outlen = alen + blen + taglen + 1 + body;
+                    }
+                    if (q4 == 0) {
+                        r_alen[r] = (uint16_t)alen;
+                        r_blen[r] = (uint16_t)blen;
+                        r_cut1[r] = (uint16_t)(c1h - L0);
+                        r_taglen[r] = (uint16_t)taglen;
+                        r_k[r] = (uint16_t)kk;
+                        r_mode[r] = mode;
+                    }
+                }
+                if (q4 == 0) r_outlen[r] = (uint16_t)outlen;
+            }
         }
 
         if (HAS_OUT) {
             // ---- P6 layout of the chunk's output
             uint32_t chunk_out = 0;
+            SK_T(6);  // plan (A for non-demux1, C for demux1)
             if (ORDERED) {
-                const uint32_t off = block_excl_scan<NT>(my_outlen, M->scratch, chunk_out);
+                const uint32_t mine = tid < (int)nrec ? r_outlen[tid] : 0;
+                const uint32_t off = block_excl_scan<NT>(mine, M->scratch, chunk_out);
                 if (tid < (int)nrec) r_outoff[tid] = off;
             } else {
                 for (uint32_t s = tid; s < S; s += NT) hist[s] = 0;
                 __syncthreads();
-                if (tid < (int)nrec && r_sample[tid] >= 0 && my_outlen) atomicAdd(&hist[r_sample[tid]], my_outlen);
-                __syncthreads();
-                // sample-major bases: exclusive scan of hist over S (tiles of NT with a carry)
-                uint32_t carry = 0;
-                for (uint32_t s0 = 0; s0 < S; s0 += NT) {
-                    const uint32_t s = s0 + tid;
-                    const uint32_t v = s < S ? hist[s] : 0;
-                    uint32_t t2;
-                    const uint32_t e = block_excl_scan<NT>(v, M->scratch, t2);
-                    if (s < S) sbase[s] = carry + e;
-                    carry += t2;
-                }
-                chunk_out = carry;
-                __syncthreads();
-                // stable order inside a sample: bytes of earlier records of this chunk with the same sample
                 if (tid < (int)nrec) {
                     const int sm = r_sample[tid];
-                    uint32_t off = 0;
-                    if (sm >= 0 && my_outlen) {
-                        for (int i = 0; i < tid; i++)
-                            if (r_sample[i] == sm) off += r_outlen[i];
-                        off += sbase[sm];
+                    const uint32_t len = r_outlen[tid];
+                    const bool live = sm >= 0 && len;
+                    r_aux[tid] = live ? ((uint32_t)sm << 16) | len : 0xFFFF0000u;
+                    if (live) atomicAdd(&hist[sm], len);
+                }
+                __syncthreads();
+                // sample-major bases: exclusive scan of hist over S by one warp (contiguous runs per lane)
+                if (warp == 0) {
+                    const uint32_t per = (S + 31) / 32;
+                    const uint32_t s0 = lane * per < S ? lane * per : S, s1 = s0 + per < S ? s0 + per : S;
+                    uint32_t sum = 0;
+                    for (uint32_t s = s0; s < s1; s++) sum += hist[s];
+                    uint32_t inc = sum;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o) inc += y;
                     }
-                    r_outoff[tid] = off;
+                    uint32_t run = inc - sum;
+                    for (uint32_t s = s0; s < s1; s++) {
+                        sbase[s] = run;
+                        run += hist[s];
+                    }
+                    if (lane == 31) M->chunk_out = inc;
+                }
+                // stable order inside a sample: bytes of earlier records of this chunk with the same sample
+                uint32_t off = 0;
+                if (tid < (int)nrec) {
+                    const uint32_t mine = r_aux[tid];
+                    if (mine != 0xFFFF0000u) {
+                        const uint32_t key = mine >> 16;
+                        for (int i = 0; i < tid; i++) {
+                            const uint32_t x = r_aux[i];
+                            if ((x >> 16) == key) off += x & 0xFFFFu;
+                        }
+                    }
+                }
+                __syncthreads();
+                chunk_out = M->chunk_out;
+                if (tid < (int)nrec) {
+                    const uint32_t mine = r_aux[tid];
+                    r_outoff[tid] = mine != 0xFFFF0000u ? off + sbase[mine >> 16] : 0;
                 }
                 // slice table row (u16 lengths)
                 if (p.out) {
@@ -723,6 +1295,7 @@ __global__ void __launch_bounds__(Cfg::NT, 2) sk_chunk_kernel(const __grid_const
                 }
             }
 
+            SK_T(7);  // layout
             // ---- P7 reserve output space
             if (ORDERED) {
                 if (warp == 0) {
@@ -745,6 +1318,7 @@ __global__ void __launch_bounds__(Cfg::NT, 2) sk_chunk_kernel(const __grid_const
                 M->out_base = base;
             }
             __syncthreads();
+            SK_T(8);  // reserve (look-back on output bytes / atomic)
             const uint64_t out_base = M->out_base;
             bool writable = p.out != nullptr && chunk_out > 0;
             if (writable && out_base + chunk_out > p.out_cap) {
@@ -753,71 +1327,95 @@ __global__ void __launch_bounds__(Cfg::NT, 2) sk_chunk_kernel(const __grid_const
             }
 
             if (writable) {
-                // ---- P8 assemble: one warp per record.  Fast path builds the chunk's output image in
-                // shared memory (aligned like its global destination); oversized outputs go straight to
-                // global memory byte by byte.
+                // ---- P8 assemble.  Fast path: build the chunk's output image in shared memory, aligned
+                // like its global destination; 4 lanes per record, each copying whole pieces word-wise.
                 const uint32_t shift = (uint32_t)(out_base & 15u);
                 const bool staged = chunk_out <= (uint32_t)Cfg::STAGE;
-                uint8_t *dst0 = staged ? stage + shift : p.out + out_base;
-                for (uint32_t r = warp; r < nrec; r += NW) {
-                    const uint32_t outlen = r_outlen[r];
-                    if (!outlen) continue;
-                    const uint32_t j = j0 + r * lpr;
-                    const uint32_t L0 = lb(W, j), L1 = lb(W, j + 1), L2 = lb(W, j + 2);
-                    const uint32_t L3 = lpr == 4 ? lb(W, j + 3) : L2, L4 = lpr == 4 ? lb(W, j + 4) : L2;
-                    const uint32_t Lend = lpr == 4 ? L4 : L2;
-                    uint8_t *d = dst0 + r_outoff[r];
-                    const uint32_t kk = r_k[r];
-                    const uint8_t mode = r_mode[r];
-                    if (OP == OP_TRIM || OP == OP_MASK) {
-                        wcopy(d, win + L0, L1 - L0, lane);
-                        d += L1 - L0;
-                    } else {
-                        const uint32_t alen = r_alen[r], blen = r_blen[r], taglen = r_taglen[r];
-                        wcopy(d, win + L0, alen, lane);
-                        d += alen;
-                        wcopy(d, win + L0 + r_cut1[r], blen, lane);
-                        d += blen;
-                        if (taglen) {
-                            if (OP == OP_ADDBC) {
-                                if (lane < 4) d[lane] = (uint8_t)" BC:"[lane];
-                                wcopy(d + 4, p.ext_data[0] + r_ext[r], taglen - 4, lane);
-                            } else {
-                                if (lane < 5) d[lane] = (uint8_t)" UMI:"[lane];
-                                wcopy(d + 5, p.umi + (rec0 + r) * p.sheet.Umax, taglen - 5, lane);
-                            }
-                            d += taglen;
-                        }
-                        if (lane == 0) d[0] = '\n';
-                        d += 1;
-                    }
-                    if (mode == B_VERBATIM) {
-                        wcopy(d, win + L1, Lend - L1, lane);
-                    } else if (mode == B_TRIM) {
-                        wcopy(d, win + L1, kk, lane);
-                        d += kk;
-                        if (lane < 3) d[lane] = (lane == 1) ? '+' : '\n';
-                        d += 3;
-                        wcopy(d, win + L3, kk, lane);
-                        if (lane == 0) d[kk] = '\n';
-                    } else if (mode == B_GARBAGE) {
-                        if (lane < 6) d[lane] = (uint8_t)"N\n+\n!\n"[lane];
-                    } else if (mode == B_MASK) {
-                        const uint32_t minq = p.min_baseq;
-                        for (uint32_t i = lane; i < kk; i += 32) {
-                            const uint8_t q = (uint8_t)(win[L3 + i] - 33u);  // fasta_mask_by_quality.rs:42
-                            d[i] = q < minq ? (uint8_t)'N' : win[L1 + i];
-                        }
-                        d += kk;
-                        if (lane < 3) d[lane] = (lane == 1) ? '+' : '\n';
-                        d += 3;
-                        wcopy(d, win + L3, kk, lane);
-                        if (lane == 0) d[kk] = '\n';
-                    }
-                }
-                __syncthreads();
-                // ---- P9 store the staged image with 16-byte vectors (bytes at an unaligned head/tail)
                 if (staged) {
+                    uint8_t *sb = stage + shift;
+                    const uint32_t q4 = tid & 3;
+                    for (uint32_t r0 = 0; r0 < nrec; r0 += NT / 4) {
+                        const uint32_t r = r0 + (tid >> 2);
+                        // every lane ends up with at most one word-copy job; literals are written directly
+                        uint8_t *jd = nullptr;
+                        const uint8_t *js = nullptr;
+                        uint32_t jl = 0;
+                        const uint32_t outlen = r < nrec ? r_outlen[r] : 0;
+                        if (outlen) {
+                            const uint32_t j = j0 + r * lpr;
+                            const uint32_t L0 = lb(W, j), L1 = lb(W, j + 1);
+                            uint8_t *d0 = sb + r_outoff[r];
+                            const uint32_t kk = r_k[r];
+                            const uint8_t mode = r_mode[r];
+                            uint32_t hlen;  // bytes of the (rewritten) header line incl. '\n'
+                            if (OP == OP_TRIM || OP == OP_MASK) {
+                                hlen = L1 - L0;
+                                if (q4 == 0) { jd = d0; js = win + L0; jl = hlen; }
+                            } else {
+                                const uint32_t alen = r_alen[r], blen = r_blen[r], taglen = r_taglen[r];
+                                hlen = alen + blen + taglen + 1;
+                                if (q4 == 0) { jd = d0; js = win + L0; jl = alen; }
+                                if (q4 == 3) {  // the (usually empty) piece after the cut, the tag and the newline
+                                    uint8_t *d = d0 + alen;
+                                    const uint8_t *sB = win + L0 + r_cut1[r];
+                                    for (uint32_t i = 0; i < blen; i++) d[i] = sB[i];
+                                    d += blen;
+                                    if (taglen) {
+                                        if (OP == OP_ADDBC) {
+                                            d[0] = ' '; d[1] = 'B'; d[2] = 'C'; d[3] = ':';
+                                            bcopy(d + 4, p.ext_data[0] + r_aux[r], taglen - 4);
+                                        } else {
+                                            d[0] = ' '; d[1] = 'U'; d[2] = 'M'; d[3] = 'I'; d[4] = ':';
+                                            bcopy(d + 5, p.umi + (rec0 + r) * p.sheet.Umax, taglen - 5);
+                                        }
+                                        d += taglen;
+                                    }
+                                    d[0] = '\n';
+                                }
+                            }
+                            uint8_t *db = d0 + hlen;  // body destination
+                            if (mode == B_VERBATIM) {
+                                const uint32_t Lend = lb(W, j + lpr);
+                                const uint32_t blen2 = Lend - L1, half = (blen2 / 2 + 3) & ~3u;
+                                const uint32_t h1 = half < blen2 ? half : blen2;
+                                if (q4 == 1) { jd = db; js = win + L1; jl = h1; }
+                                if (q4 == 2) { jd = db + h1; js = win + L1 + h1; jl = blen2 - h1; }
+                            } else if (mode == B_TRIM) {
+                                const uint32_t L3 = lb(W, j + 3);
+                                if (q4 == 1) { jd = db; js = win + L1; jl = kk; }
+                                if (q4 == 2) { jd = db + kk + 3; js = win + L3; jl = kk; }
+                                if (q4 == 3) {
+                                    uint8_t *d = db + kk;
+                                    d[0] = '\n'; d[1] = '+'; d[2] = '\n';
+                                    d[3 + kk] = '\n';
+                                }
+                            } else if (mode == B_GARBAGE) {
+                                if (q4 == 3) {
+                                    uint8_t *d = db;
+                                    d[0] = 'N'; d[1] = '\n'; d[2] = '+'; d[3] = '\n'; d[4] = '!'; d[5] = '\n';
+                                }
+                            } else if (mode == B_MASK) {
+                                const uint32_t L3 = lb(W, j + 3);
+                                if (q4 == 1) {
+                                    const uint32_t minq = p.min_baseq;
+                                    for (uint32_t i = 0; i < kk; i++) {
+                                        const uint8_t q = (uint8_t)(win[L3 + i] - 33u);  // fasta_mask_by_quality.rs:42
+                                        db[i] = q < minq ? (uint8_t)'N' : win[L1 + i];
+                                    }
+                                }
+                                if (q4 == 2) { jd = db + kk + 3; js = win + L3; jl = kk; }
+                                if (q4 == 3) {
+                                    uint8_t *d = db + kk;
+                                    d[0] = '\n'; d[1] = '+'; d[2] = '\n';
+                                    d[3 + kk] = '\n';
+                                }
+                            }
+                        }
+                        tcopy(jd, js, jl);  // one call site: all lanes copy their piece together
+                    }
+                    __syncthreads();
+                    SK_T(9);  // assemble
+                    // ---- P9 store the staged image with 16-byte vectors (bytes at an unaligned head/tail)
                     const uint32_t span = shift + chunk_out;
                     uint8_t *g16 = p.out + (out_base - shift);
                     for (uint32_t v = tid; v * 16 < span; v += NT) {
@@ -829,6 +1427,54 @@ __global__ void __launch_bounds__(Cfg::NT, 2) sk_chunk_kernel(const __grid_const
                             for (uint32_t b2 = lo; b2 < hi; b2++) g16[b2] = stage[b2];
                         }
                     }
+                } else {
+                    // Oversized output (pathological growth): one thread per record, bytes straight to global.
+                    if (tid < (int)nrec && r_outlen[tid]) {
+                        const uint32_t r = tid, j = j0 + r * lpr;
+                        const uint32_t L0 = lb(W, j), L1 = lb(W, j + 1), L3 = lb(W, j + 3);
+                        const uint32_t kk = r_k[r];
+                        const uint8_t mode = r_mode[r];
+                        uint8_t *d = p.out + out_base + r_outoff[r];
+                        if (OP == OP_TRIM || OP == OP_MASK) {
+                            bcopy(d, win + L0, L1 - L0);
+                            d += L1 - L0;
+                        } else {
+                            const uint32_t alen = r_alen[r], blen = r_blen[r], taglen = r_taglen[r];
+                            bcopy(d, win + L0, alen);
+                            d += alen;
+                            bcopy(d, win + L0 + r_cut1[r], blen);
+                            d += blen;
+                            if (taglen) {
+                                if (OP == OP_ADDBC) {
+                                    bcopy(d, (const uint8_t *)" BC:", 4);
+                                    bcopy(d + 4, p.ext_data[0] + r_aux[r], taglen - 4);
+                                } else {
+                                    bcopy(d, (const uint8_t *)" UMI:", 5);
+                                    bcopy(d + 5, p.umi + (rec0 + r) * p.sheet.Umax, taglen - 5);
+                                }
+                                d += taglen;
+                            }
+                            *d++ = '\n';
+                        }
+                        if (mode == B_VERBATIM) {
+                            bcopy(d, win + L1, lb(W, j + lpr) - L1);
+                        } else if (mode == B_TRIM) {
+                            bcopy(d, win + L1, kk);
+                            bcopy(d + kk, (const uint8_t *)"\n+\n", 3);
+                            bcopy(d + kk + 3, win + L3, kk);
+                            d[2 * kk + 3] = '\n';
+                        } else if (mode == B_GARBAGE) {
+                            bcopy(d, (const uint8_t *)"N\n+\n!\n", 6);
+                        } else if (mode == B_MASK) {
+                            for (uint32_t i = 0; i < kk; i++) {
+                                const uint8_t q = (uint8_t)(win[L3 + i] - 33u);
+                                d[i] = q < p.min_baseq ? (uint8_t)'N' : win[L1 + i];
+                            }
+                            bcopy(d + kk, (const uint8_t *)"\n+\n", 3);
+                            bcopy(d + kk + 3, win + L3, kk);
+                            d[2 * kk + 3] = '\n';
+                        }
+                    }
                 }
             }
         }
@@ -836,7 +1482,13 @@ __global__ void __launch_bounds__(Cfg::NT, 2) sk_chunk_kernel(const __grid_const
         // ---- P10 per-record side tables
         if (OP == OP_DEMUX1 && tid < (int)nrec) p.assign[rec0 + tid] = r_sample[tid];
         __syncthreads();  // window, staging and record arrays are reused by the next chunk
+        SK_T(10);  // store + tables
     }
+#ifdef SK_PHASE_TIMING
+    if (tid == 0)
+        for (int i = 0; i < 16; i++)
+            if (ph[i]) atomicAdd(&st->phase_cycles[i], ph[i]);
+#endif
 
     // ---- flush per-CTA counters (fasta_demultiplex.rs:108-109,169,177-178)
     if (OP == OP_DEMUX1) {
@@ -846,6 +1498,7 @@ __global__ void __launch_bounds__(Cfg::NT, 2) sk_chunk_kernel(const __grid_const
         if (tid == 0) {
             if (M->cta_total) atomicAdd(&p.counts[S], (unsigned long long)M->cta_total);
             if (M->cta_ident) atomicAdd(&p.counts[S + 1], (unsigned long long)M->cta_ident);
+            if (M->cta_slow) atomicAdd(&st->n_slow, M->cta_slow);
         }
     }
 }
@@ -853,44 +1506,69 @@ __global__ void __launch_bounds__(Cfg::NT, 2) sk_chunk_kernel(const __grid_const
 // ------------------------------------------------------------------------------------------------
 // launcher
 // ------------------------------------------------------------------------------------------------
-int chunk_kernel_smem_bytes(uint32_t S, uint32_t wide) { return (int)smem_layout<CfgStd>(S, wide).total; }
+template <class Cfg>
+static uint32_t smem_for(int op, const KParams &p, bool wide) {
+    const bool demux = (op == OP_DEMUX1 || op == OP_DEMUX2);
+    const bool d1 = op == OP_DEMUX1;
+    return smem_layout<Cfg>(demux ? p.sheet.S : 0u, wide ? 1u : 0u, d1 ? p.sheet.fast.n_classes : 0u,
+                            d1 ? p.sheet.fast.tsize : 0u)
+        .total;
+}
+int chunk_kernel_smem_bytes(int cfg, uint32_t S, uint32_t wide, uint32_t n_classes, uint32_t tsize) {
+    return cfg == CfgSmall::ID ? (int)smem_layout<CfgSmall>(S, wide, n_classes, tsize).total
+                               : (int)smem_layout<CfgBig>(S, wide, n_classes, tsize).total;
+}
 
-template <int OP, typename WT>
+template <class Cfg, int OP, typename WT>
 static int launch_one(const KParams &p, int sm_count, cudaStream_t stream, const char **err) {
-    auto kfn = sk_chunk_kernel<CfgStd, OP, WT>;
-    const bool demux = (OP == OP_DEMUX1 || OP == OP_DEMUX2);
-    const int smem = (int)smem_layout<CfgStd>(demux ? p.sheet.S : 0u, sizeof(WT) == 8).total;
+    auto kfn = sk_chunk_kernel<Cfg, OP, WT>;
+    const int smem = (int)smem_for<Cfg>(OP, p, sizeof(WT) == 8);
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
+    if (e != cudaSuccess) {
+        *err = cudaGetErrorString(e);
+        return -1;
+    }
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, CfgStd::NT, smem);
-    if (e != cudaSuccess || per_sm < 1) { *err = e != cudaSuccess ? cudaGetErrorString(e) : "kernel does not fit on an SM"; return -1; }
-    long long grid = (long long)sm_count * per_sm;  // persistent: every CTA is resident (look-back needs it)
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, Cfg::NT, smem);
+    if (e != cudaSuccess || per_sm < 1) {
+        *err = e != cudaSuccess ? cudaGetErrorString(e) : "kernel does not fit on an SM";
+        return -1;
+    }
+    long long grid = (long long)sm_count * per_sm;  // persistent CTAs, chunks handed out by ticket
     if (grid > (long long)p.n_chunks) grid = p.n_chunks;
     if (grid < 1) return 0;
-    kfn<<<(unsigned)grid, CfgStd::NT, smem, stream>>>(p);
+    kfn<<<(unsigned)grid, Cfg::NT, smem, stream>>>(p);
     e = cudaGetLastError();
-    if (e != cudaSuccess) { *err = cudaGetErrorString(e); return -1; }
+    if (e != cudaSuccess) {
+        *err = cudaGetErrorString(e);
+        return -1;
+    }
     return 1;
 }
 
-int launch_chunk_kernel(int op, const KParams &p, int sm_count, void *stream_, const char **err) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+template <class Cfg>
+static int launch_cfg(int op, const KParams &p, int sm_count, cudaStream_t stream, const char **err) {
     const bool wide = p.sheet.wide != 0;
     switch (op) {
-        case OP_SCAN: return launch_one<OP_SCAN, uint32_t>(p, sm_count, stream, err);
-        case OP_TRIM: return launch_one<OP_TRIM, uint32_t>(p, sm_count, stream, err);
-        case OP_MASK: return launch_one<OP_MASK, uint32_t>(p, sm_count, stream, err);
-        case OP_ADDBC: return launch_one<OP_ADDBC, uint32_t>(p, sm_count, stream, err);
+        case OP_SCAN: return launch_one<Cfg, OP_SCAN, uint32_t>(p, sm_count, stream, err);
+        case OP_TRIM: return launch_one<Cfg, OP_TRIM, uint32_t>(p, sm_count, stream, err);
+        case OP_MASK: return launch_one<Cfg, OP_MASK, uint32_t>(p, sm_count, stream, err);
+        case OP_ADDBC: return launch_one<Cfg, OP_ADDBC, uint32_t>(p, sm_count, stream, err);
         case OP_DEMUX1:
-            return wide ? launch_one<OP_DEMUX1, uint64_t>(p, sm_count, stream, err)
-                        : launch_one<OP_DEMUX1, uint32_t>(p, sm_count, stream, err);
+            return wide ? launch_one<Cfg, OP_DEMUX1, uint64_t>(p, sm_count, stream, err)
+                        : launch_one<Cfg, OP_DEMUX1, uint32_t>(p, sm_count, stream, err);
         case OP_DEMUX2:
-            return wide ? launch_one<OP_DEMUX2, uint64_t>(p, sm_count, stream, err)
-                        : launch_one<OP_DEMUX2, uint32_t>(p, sm_count, stream, err);
+            return wide ? launch_one<Cfg, OP_DEMUX2, uint64_t>(p, sm_count, stream, err)
+                        : launch_one<Cfg, OP_DEMUX2, uint32_t>(p, sm_count, stream, err);
     }
     *err = "unknown operator";
     return -1;
+}
+
+int launch_chunk_kernel(int cfg, int op, const KParams &p, int sm_count, void *stream_, const char **err) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    return cfg == CfgSmall::ID ? launch_cfg<CfgSmall>(op, p, sm_count, stream, err)
+                               : launch_cfg<CfgBig>(op, p, sm_count, stream, err);
 }
 
 }  // namespace sk

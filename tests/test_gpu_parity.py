@@ -96,13 +96,24 @@ def test_golden_demux(eng):
 def test_fuzz_stream_ops_vs_oracle(eng, O):
     rng = random.Random(2024)
     for it in range(120):
-        n = rng.choice((0, 1, 2, 7, 40, 300))
+        n = rng.choice((0, 1, 2, 7, 40, 200))
         data = G.nasty_fastq(rng.randrange(1 << 30), n) if it % 3 else G.clean_fastq(rng.randrange(1 << 30), n, qual_style="mix")
         q = rng.choice((0, 2, 10, 20, 30, 41, 93, 200, 255))
         check3(eng.trim_by_quality(data, q), O.trim_by_quality(data, q), ("trim", it, q))
         check3(eng.mask_by_quality(data, q), O.mask_by_quality(data, q), ("mask", it, q))
         bc = G.index_reads(rng.randrange(1 << 30), rng.choice((0, 1, n, n + 3, max(n - 2, 0))), [b"ACGT", b"GG+TT", b"ACGTACGTAC"])
         check3(eng.add_barcode(data, bc), O.add_barcode(data, bc), ("addbc", it))
+
+
+def test_dense_or_long_records_are_refused_not_mangled(eng):
+    """Inputs outside the chunk geometry must surface as explicit statuses."""
+    from seqkit_b200.engine import Unsupported
+    tiny = b"@a\nAC\n+\nII\n" * 4000  # 11-byte records: > 512 per 32 KiB chunk
+    with pytest.raises(Unsupported):
+        eng.trim_by_quality(tiny, 20)
+    big = b"@long\n" + b"A" * 20000 + b"\n+\n" + b"I" * 20000 + b"\n"
+    with pytest.raises(Unsupported):
+        eng.mask_by_quality(big * 3, 20)
 
 
 def test_add_barcode_fasta_and_reuse(eng, O):
