@@ -106,7 +106,14 @@ struct SheetDev {
     FastIdx fast;
 };
 
+// Shared-memory carve-up (bytes), computed on the host and passed in KParams (the device code only
+// reads it: recomputing it in the kernel costs ~5 % of all instructions).
+struct SmemLayout {
+    uint32_t win, stage, ls, rec, sheet, umask, lut, hist, sbase, ccount, fcls, ftab, slow, misc, total;
+};
+
 struct KParams {
+    SmemLayout sl;
     // input stream
     const uint8_t *in;
     uint64_t n;
@@ -151,10 +158,6 @@ enum : unsigned {
 };
 enum : unsigned { F_MATE_COUNT = 1u, F_EVENTS_OVERFLOW = 2u, F_NON_ASCII = 0x100u };
 
-// Shared-memory carve-up (bytes), identical on host and device.
-struct SmemLayout {
-    uint32_t win, stage, ls, rec, sheet, umask, lut, hist, sbase, ccount, fcls, ftab, slow, misc, total;
-};
 constexpr int REC_BYTES = 26;  // per-record plan fields, see sk_kernels.cu
 template <class Cfg>
 inline __host__ __device__ SmemLayout smem_layout(uint32_t S, uint32_t wide, uint32_t n_classes, uint32_t tsize) {

@@ -626,7 +626,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
     const uint32_t S = IS_DEMUX ? p.sheet.S : 0u;
     const uint32_t FC = (OP == OP_DEMUX1) ? p.sheet.fast.n_classes : 0u;
     const uint32_t FT = (OP == OP_DEMUX1) ? p.sheet.fast.tsize : 0u;
-    const SmemLayout SL = smem_layout<Cfg>(S, WIDE ? 1u : 0u, FC, FT);
+    const SmemLayout &SL = p.sl;
     uint8_t *win = sk_smem + SL.win;
     uint8_t *stage = sk_smem + SL.stage;
     uint16_t *ls = (uint16_t *)(sk_smem + SL.ls);
@@ -683,13 +683,29 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
     long long t_prev = clock64();
 #endif
     uint32_t parity = 0;
-    for (;;) {
-        // ---- P0 ticket
-        if (tid == 0) {
-            M->chunk = atomicAdd(&st->ticket, 1u);
-            M->n_slow = 0;
+    if (tid == 0) {
+        M->chunk = atomicAdd(&st->ticket, 1u);
+        M->n_slow = 0;
+    }
+    __syncthreads();
+    // P9 of chunk k is deferred into the window load of chunk k+1: the staged image is stored with
+    // 16-byte vectors (bytes at an unaligned head/tail) while the TMA copy is in flight.
+    uint32_t pend_span = 0, pend_shift = 0;
+    uint8_t *pend_g16 = nullptr;
+    auto flush_stage = [&]() {
+        for (uint32_t v = tid; v * 16 < pend_span; v += NT) {
+            const uint32_t b0 = v * 16;
+            if (b0 >= pend_shift && b0 + 16 <= pend_span) {
+                *(uint4 *)(pend_g16 + b0) = *(const uint4 *)(stage + b0);
+            } else {
+                const uint32_t lo = b0 < pend_shift ? pend_shift : b0, hi = b0 + 16 < pend_span ? b0 + 16 : pend_span;
+                for (uint32_t b2 = lo; b2 < hi; b2++) pend_g16[b2] = stage[b2];
+            }
         }
-        __syncthreads();
+        pend_span = 0;
+    };
+    for (;;) {
+        // ---- P0 ticket (taken by thread 0 at the end of the previous chunk, published by its last barrier)
         const uint32_t c = M->chunk;
         if (c >= p.n_chunks) break;
         SK_T(0);  // ticket
@@ -714,12 +730,13 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
             const uint32_t o = bulk + tid;
             if (o < (uint32_t)Cfg::WIN_MAX) win[o] = (o < wlen) ? p.in[w0 + o] : (uint8_t)0;
         }
+        if (pend_span) flush_stage();  // previous chunk's output, overlapped with the copy above
         if (bulk) {
             mbar_wait(&M->mbar, parity);
             parity ^= 1;
         }
         __syncthreads();
-        SK_T(1);  // window load
+        SK_T(1);  // window load (+ deferred store of the previous chunk)
 
         // ---- P2 newline scan: 80 contiguous bytes per thread, kept as 5 piece maps
         // A '\n' at window offset q starts a line at q+1.  Lines that start before the chunk belong to
@@ -1238,16 +1255,42 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
                 const uint32_t off = block_excl_scan<NT>(mine, M->scratch, chunk_out);
                 if (tid < (int)nrec) r_outoff[tid] = off;
             } else {
-                for (uint32_t s = tid; s < S; s += NT) hist[s] = 0;
+                for (uint32_t s = tid; s < S; s += NT) hist[s] = 0;  // per-sample byte cursor, ends as the histogram
                 __syncthreads();
-                if (tid < (int)nrec) {
-                    const int sm = r_sample[tid];
-                    const uint32_t len = r_outlen[tid];
-                    const bool live = sm >= 0 && len;
-                    r_aux[tid] = live ? ((uint32_t)sm << 16) | len : 0xFFFF0000u;
-                    if (live) atomicAdd(&hist[sm], len);
+                // Stable order inside a sample: warps take their 32 records in turn; lanes holding the same
+                // sample (match.any) rank themselves by lane, the highest one advances the sample's cursor.
+                const uint32_t nwu = (nrec + 31) / 32;
+                for (uint32_t w = 0; w < nwu; w++) {
+                    if ((uint32_t)warp == w) {
+                        const uint32_t r = w * 32 + lane;
+                        int sm = -1;
+                        uint32_t len = 0;
+                        if (r < nrec) {
+                            sm = r_sample[r];
+                            len = r_outlen[r];
+                            if (sm < 0 || !len) sm = -1, len = 0;
+                        }
+                        const unsigned peers = __match_any_sync(0xffffffffu, sm);
+                        uint32_t pre = 0;
+                        if (sm >= 0) {
+                            unsigned lower = peers & ((1u << lane) - 1u);
+                            while (lower) {
+                                const int l = __ffs(lower) - 1;
+                                lower &= lower - 1;
+                                pre += r_outlen[w * 32 + l];
+                            }
+                        }
+                        const int hi = 31 - __clz(peers);
+                        uint32_t base = 0;
+                        if (lane == hi && sm >= 0) {
+                            base = hist[sm];
+                            hist[sm] = base + pre + len;
+                        }
+                        base = __shfl_sync(0xffffffffu, base, hi);
+                        if (r < nrec) r_outoff[r] = base + pre;
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
                 // sample-major bases: exclusive scan of hist over S by one warp (contiguous runs per lane)
                 if (warp == 0) {
                     const uint32_t per = (S + 31) / 32;
@@ -1267,23 +1310,11 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
                     }
                     if (lane == 31) M->chunk_out = inc;
                 }
-                // stable order inside a sample: bytes of earlier records of this chunk with the same sample
-                uint32_t off = 0;
-                if (tid < (int)nrec) {
-                    const uint32_t mine = r_aux[tid];
-                    if (mine != 0xFFFF0000u) {
-                        const uint32_t key = mine >> 16;
-                        for (int i = 0; i < tid; i++) {
-                            const uint32_t x = r_aux[i];
-                            if ((x >> 16) == key) off += x & 0xFFFFu;
-                        }
-                    }
-                }
                 __syncthreads();
                 chunk_out = M->chunk_out;
                 if (tid < (int)nrec) {
-                    const uint32_t mine = r_aux[tid];
-                    r_outoff[tid] = mine != 0xFFFF0000u ? off + sbase[mine >> 16] : 0;
+                    const int sm = r_sample[tid];
+                    if (sm >= 0 && r_outlen[tid]) r_outoff[tid] += sbase[sm];
                 }
                 // slice table row (u16 lengths)
                 if (p.out) {
@@ -1413,20 +1444,12 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
                         }
                         tcopy(jd, js, jl);  // one call site: all lanes copy their piece together
                     }
-                    __syncthreads();
                     SK_T(9);  // assemble
-                    // ---- P9 store the staged image with 16-byte vectors (bytes at an unaligned head/tail)
-                    const uint32_t span = shift + chunk_out;
-                    uint8_t *g16 = p.out + (out_base - shift);
-                    for (uint32_t v = tid; v * 16 < span; v += NT) {
-                        const uint32_t b0 = v * 16;
-                        if (b0 >= shift && b0 + 16 <= span) {
-                            *(uint4 *)(g16 + b0) = *(const uint4 *)(stage + b0);
-                        } else {
-                            const uint32_t lo = b0 < shift ? shift : b0, hi = b0 + 16 < span ? b0 + 16 : span;
-                            for (uint32_t b2 = lo; b2 < hi; b2++) g16[b2] = stage[b2];
-                        }
-                    }
+                    // ---- P9 is deferred (see flush_stage): the barrier that ends this chunk orders the
+                    // staging writes before the loads of the flush.
+                    pend_shift = shift;
+                    pend_span = shift + chunk_out;
+                    pend_g16 = p.out + (out_base - shift);
                 } else {
                     // Oversized output (pathological growth): one thread per record, bytes straight to global.
                     if (tid < (int)nrec && r_outlen[tid]) {
@@ -1481,9 +1504,16 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
 
         // ---- P10 per-record side tables
         if (OP == OP_DEMUX1 && tid < (int)nrec) p.assign[rec0 + tid] = r_sample[tid];
+        if (tid == 0) {
+            // Take the next ticket only now: a ticket held while another chunk is still being processed
+            // stalls the look-back of every later chunk (measured: +15 % step time).
+            M->chunk = atomicAdd(&st->ticket, 1u);
+            M->n_slow = 0;
+        }
         __syncthreads();  // window, staging and record arrays are reused by the next chunk
         SK_T(10);  // store + tables
     }
+    if (pend_span) flush_stage();
 #ifdef SK_PHASE_TIMING
     if (tid == 0)
         for (int i = 0; i < 16; i++)
@@ -1520,9 +1550,16 @@ int chunk_kernel_smem_bytes(int cfg, uint32_t S, uint32_t wide, uint32_t n_class
 }
 
 template <class Cfg, int OP, typename WT>
-static int launch_one(const KParams &p, int sm_count, cudaStream_t stream, const char **err) {
+static int launch_one(const KParams &p_in, int sm_count, cudaStream_t stream, const char **err) {
     auto kfn = sk_chunk_kernel<Cfg, OP, WT>;
-    const int smem = (int)smem_for<Cfg>(OP, p, sizeof(WT) == 8);
+    KParams p = p_in;
+    {
+        const bool demux = (OP == OP_DEMUX1 || OP == OP_DEMUX2);
+        const bool d1 = OP == OP_DEMUX1;
+        p.sl = smem_layout<Cfg>(demux ? p.sheet.S : 0u, sizeof(WT) == 8 ? 1u : 0u, d1 ? p.sheet.fast.n_classes : 0u,
+                                d1 ? p.sheet.fast.tsize : 0u);
+    }
+    const int smem = (int)p.sl.total;
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
         *err = cudaGetErrorString(e);
