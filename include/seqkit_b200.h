@@ -131,6 +131,13 @@ int sk_debug_phase_cycles(sk_ctx *ctx, uint32_t slot, uint32_t which, uint64_t o
 /* on != 0: bracket every kernel with CUDA events so that sk_wait can fill sk_result.pass_ms. */
 int sk_set_profiling(sk_ctx *ctx, int on);
 
+/* Pinned (page-locked) host memory for the batcher's multi-MB buffers, so that a host without its own
+ * CUDA binding (the Rust crate, the C++ `fasta` binary) gets asynchronous H2D/D2H copies. */
+void *sk_pinned_alloc(sk_ctx *ctx, uint64_t bytes);
+void sk_pinned_free(sk_ctx *ctx, void *p);
+/* Capacity in bytes of each output stream of a slot (upper bound of sk_result.out_extent). */
+uint64_t sk_out_capacity(sk_ctx *ctx);
+
 /* ---- inputs ------------------------------------------------------------------------------- */
 /* Device address / capacity of an input stream buffer (for producers that write on the device). */
 void *sk_slot_in(sk_ctx *ctx, uint32_t slot, uint32_t which);

@@ -62,6 +62,9 @@ SIGNATURES = {
     "sk_max_chunks": (C.c_uint32, [_P]),
     "sk_debug_phase_cycles": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
     "sk_set_profiling": (C.c_int, [_P, C.c_int]),
+    "sk_pinned_alloc": (_P, [_P, C.c_uint64]),
+    "sk_pinned_free": (None, [_P, _P]),
+    "sk_out_capacity": (C.c_uint64, [_P]),
     "sk_slot_in": (_P, [_P, C.c_uint32, C.c_uint32]),
     "sk_slot_in_capacity": (C.c_uint64, [_P, C.c_uint32, C.c_uint32]),
     "sk_upload": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.c_uint64]),

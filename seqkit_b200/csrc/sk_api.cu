@@ -237,6 +237,20 @@ extern "C" int sk_set_profiling(sk_ctx *ctx, int on) {
     ctx->profiling = on != 0;
     return SK_OK;
 }
+extern "C" void *sk_pinned_alloc(sk_ctx *ctx, uint64_t bytes) {
+    if (!ctx || !bytes) return nullptr;
+    cudaSetDevice(ctx->device);
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        ctx->err = "cudaMallocHost failed";
+        return nullptr;
+    }
+    return p;
+}
+extern "C" void sk_pinned_free(sk_ctx *ctx, void *p) {
+    if (ctx && p) cudaFreeHost(p);
+}
+extern "C" uint64_t sk_out_capacity(sk_ctx *ctx) { return (ctx && !ctx->slots.empty()) ? ctx->slots[0].out_cap : 0; }
 extern "C" void *sk_slot_in(sk_ctx *ctx, uint32_t slot, uint32_t which) {
     Slot *s = get_slot(ctx, slot);
     return (s && which < SK_N_INPUTS) ? s->in[which] : nullptr;

@@ -1,0 +1,1020 @@
+// fasta_main.cpp -- the drop-in `fasta` binary for the per-read FASTQ batch path, on top of the C ABI
+// of libseqkit_b200.so (include/seqkit_b200.h).
+//
+// Mirrors, for the four subcommands on the path, what the reference's dispatcher and modules do at
+// the process boundary (paths relative to /root/reference/src/):
+//   fasta_main.rs:42-82           word-prefix dispatch, top-level usage on stderr for anything else
+//   common.rs:11-22               error! -> "ERROR: <msg>\n" on stderr, exit status 255; docopt failure
+//   common.rs:88-104              FileReader::new: "-" = stdin, *.gz through a `gunzip -c` child
+//   common.rs:49-81               GzipWriter: File::create(path) as stdout of a `gzip -c` / `pigz -c` child
+//   fasta_trim_by_quality.rs, fasta_mask_by_quality.rs, fasta_add_barcode.rs, fasta_demultiplex.rs
+//
+// This file is the *batcher*: it reads bytes, cuts batches at record boundaries (a newline count; no
+// per-read arithmetic happens here), packs them into pinned multi-MB buffers, calls the CUDA path
+// through the ABI with two slots in flight, and streams the results to stdout / the gzip children in
+// batch order.  Every operator result comes from the GPU; there is no CPU fallback.
+#include <errno.h>
+#include <fcntl.h>
+#include <signal.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/types.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <thread>
+#include <unordered_map>
+#include <vector>
+
+#include "seqkit_b200.h"
+
+// ------------------------------------------------------------------------------------------------
+// process-level helpers
+// ------------------------------------------------------------------------------------------------
+static const char *TOP_USAGE =  // fasta_main.rs:20-40, restricted to nothing: printed verbatim like the reference
+    "\nUsage:\n"
+    "  fasta check <fasta/fastq>\n"
+    "  fasta to raw <fasta/fastq>\n"
+    "  fasta add base qualities <fasta> <baseq>\n"
+    "  fasta remove base qualities <fastq>\n"
+    "  fasta simplify read ids <fastq_file>\n"
+    "  fasta interleave <fastq_1> <fastq_2>\n"
+    "  fasta deinterleave <interleaved_fastq> <out_prefix>\n"
+    "  fasta split into anchors <fastq> <anchor_len>\n"
+    "  fasta trim <fastq_file>\n"
+    "  fasta trim by quality <fastq_file> <min_baseq>\n"
+    "  fasta mask by quality <fastq_file> <min_baseq>\n"
+    "  fasta gc content <genome.fa> <regions.bed>\n"
+    "  fasta add barcode <fastq_file> <barcode_file> <barcode_format>\n"
+    "  fasta extract dual umi <interleaved_fastq>\n"
+    "  fasta convert basespace <fastq_file>\n"
+    "  fasta demultiplex <sample_sheet> <fastq_1> <fastq_2>\n"
+    "  fasta demultiplex spe <sample_sheet> <fastq_1> <fastq_2>\n"
+    "  fasta statistics <fastq_file>\n";
+
+static const char *USAGE_TRIM = "\nUsage:\n  fasta trim by quality <fastq_file> <min_baseq>\n";
+static const char *USAGE_MASK = "\nUsage:\n  fasta mask by quality <fastq_file> <min_baseq>\n";
+static const char *USAGE_ADDBC = "\nUsage:\n  fasta add barcode <fastq_file> <barcode_file>\n";
+static const char *USAGE_DEMUX =
+    "\nUsage:\n"
+    "  fasta demultiplex [options] <sample_sheet> <fastq_1> [<fastq_2>]\n"
+    "\nOptions:\n"
+    "  --parallel      Use pigz (parallel gzip) for compression\n"
+    "  --index1=FASTQ  Path to FASTQ file containing the first index (optional)\n"
+    "  --index2=FASTQ  Path to FASTQ file containing the second index (optional)\n"
+    "  --dry-run=N     Analyze N reads and generate table of indexes found in the run\n"
+    "\nSplits a pooled FASTQ file into multiple individual FASTQ files, based on a\n"
+    "sample sheet. Each read in the pooled FASTQ file must carry a BC:xxxxxxxx\n"
+    "field in its header.\n";
+
+struct GzipSink;
+static std::vector<GzipSink *> g_sinks;  // closed (children reaped) before any exit
+static void close_all_sinks();
+
+[[noreturn]] static void finish(int code) {
+    fflush(stdout);
+    close_all_sinks();
+    fflush(stderr);
+    _exit(code);
+}
+// error! (common.rs:11-16)
+[[noreturn]] static void fatal(const char *fmt, ...) {
+    fflush(stdout);
+    va_list ap;
+    va_start(ap, fmt);
+    fputs("ERROR: ", stderr);
+    vfprintf(stderr, fmt, ap);
+    fputc('\n', stderr);
+    va_end(ap);
+    finish(255);
+}
+// Inputs this implementation refuses instead of guessing: not a reference message.
+[[noreturn]] static void refuse(const char *fmt, ...) {
+    fflush(stdout);
+    va_list ap;
+    va_start(ap, fmt);
+    fputs("seqkit_b200: unsupported input: ", stderr);
+    vfprintf(stderr, fmt, ap);
+    fputc('\n', stderr);
+    va_end(ap);
+    finish(2);
+}
+[[noreturn]] static void panic101(const char *what) {
+    fflush(stdout);
+    fprintf(stderr, "thread 'main' panicked: %s\n", what);
+    finish(101);
+}
+[[noreturn]] static void invalid_args(const char *usage) {  // parse_args (common.rs:18-22)
+    fprintf(stderr, "ERROR: Invalid arguments.\n%s\n", usage);
+    finish(255);
+}
+static void write_all(int fd, const uint8_t *p, size_t n) {
+    while (n) {
+        ssize_t k = write(fd, p, n);
+        if (k < 0) {
+            if (errno == EINTR) continue;
+            return;  // #![allow(unused_must_use)]: write errors are ignored (fasta_main.rs:2)
+        }
+        p += k;
+        n -= (size_t)k;
+    }
+}
+static bool is_ws(uint8_t c) { return c == 32 || (c >= 9 && c <= 13); }  // ASCII White_Space
+static size_t trim_end_len(const uint8_t *s, size_t n) {
+    while (n && is_ws(s[n - 1])) n--;
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FileReader::new (common.rs:88-104) as a byte source
+// ------------------------------------------------------------------------------------------------
+struct Input {
+    int fd = -1;
+    pid_t child = 0;
+    bool eof = false;
+    void open_path(const std::string &path) {
+        if (path == "-") {
+            fd = 0;
+            return;
+        }
+        int f = open(path.c_str(), O_RDONLY);
+        if (f < 0) fatal("Cannot open file %s for reading.", path.c_str());
+        if (path.size() >= 3 && path.compare(path.size() - 3, 3, ".gz") == 0) {
+            int pp[2];
+            if (pipe(pp) != 0) fatal("Cannot start gunzip process.");
+            pid_t pid = fork();
+            if (pid < 0) fatal("Cannot start gunzip process.");
+            if (pid == 0) {
+                dup2(f, 0);
+                dup2(pp[1], 1);
+                close(pp[0]);
+                close(pp[1]);
+                close(f);
+                execlp("gunzip", "gunzip", "-c", (char *)nullptr);
+                _exit(127);
+            }
+            close(pp[1]);
+            close(f);
+            fd = pp[0];
+            child = pid;
+            fcntl(fd, F_SETPIPE_SZ, 1 << 20);
+        } else {
+            fd = f;
+        }
+    }
+    size_t read_some(uint8_t *dst, size_t cap) {
+        size_t got = 0;
+        while (got < cap && !eof) {
+            ssize_t k = read(fd, dst + got, cap - got);
+            if (k < 0) {
+                if (errno == EINTR) continue;
+                fatal("I/O error while reading from file.");  // common.rs:110
+            }
+            if (k == 0) eof = true;
+            got += (size_t)k;
+        }
+        return got;
+    }
+};
+
+// One input stream of the batcher: bytes accumulate in one of two pinned buffers (the other one may
+// still be the source of an in-flight H2D copy); complete records are found by counting newlines.
+struct Stream {
+    Input in;
+    bool active = false;
+    uint8_t *buf[2] = {nullptr, nullptr};
+    size_t cap = 0;
+    int cur = 0;
+    size_t fill = 0, scanned = 0;
+    uint32_t lines_mod = 0;
+    uint32_t lpr = 4;
+    std::vector<uint32_t> rec_ends;  // end offset (exclusive) of every complete record in buf[cur]
+    uint64_t records_done = 0;
+
+    void top_up() {
+        if (!active) return;
+        if (!in.eof && fill < cap) fill += in.read_some(buf[cur] + fill, cap - fill);
+        const uint8_t *b = buf[cur];
+        while (scanned < fill) {
+            const uint8_t *nl = (const uint8_t *)memchr(b + scanned, '\n', fill - scanned);
+            if (!nl) {
+                scanned = fill;
+                break;
+            }
+            scanned = (size_t)(nl - b) + 1;
+            if (++lines_mod == lpr) {
+                lines_mod = 0;
+                rec_ends.push_back((uint32_t)scanned);
+            }
+        }
+    }
+    size_t last_end() const { return rec_ends.empty() ? 0 : rec_ends.back(); }
+    // records available now; at EOF the unterminated remainder is one more (truncated) record
+    size_t avail() const { return rec_ends.size() + ((in.eof && fill > last_end()) ? 1 : 0); }
+    bool drained() const { return in.eof && fill == 0; }
+    size_t bytes_for(size_t n) const { return n == 0 ? 0 : (n <= rec_ends.size() ? rec_ends[n - 1] : fill); }
+    // drops the first `bytes` (= n records) of the buffer; the tail moves to the other pinned buffer
+    void consume(size_t n, size_t bytes) {
+        const int nxt = cur ^ 1;
+        const size_t tail = fill - bytes;
+        if (tail) memcpy(buf[nxt], buf[cur] + bytes, tail);
+        const size_t nr = std::min(n, rec_ends.size());
+        rec_ends.erase(rec_ends.begin(), rec_ends.begin() + nr);
+        for (auto &e : rec_ends) e -= (uint32_t)bytes;
+        fill = tail;
+        scanned -= bytes;
+        cur = nxt;
+        records_done += n;
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// GzipWriter (common.rs:49-81)
+// ------------------------------------------------------------------------------------------------
+struct GzipSink {
+    int fd = -1;
+    pid_t child = 0;
+    void open_path(const std::string &path, bool pigz) {
+        int f = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+        if (f < 0) fatal("Cannot open file %s for writing.", path.c_str());
+        int pp[2];
+        if (pipe(pp) != 0) fatal("Cannot start %s process.", pigz ? "pigz" : "gzip");
+        pid_t pid = fork();
+        if (pid < 0) fatal("Cannot start %s process.", pigz ? "pigz" : "gzip");
+        if (pid == 0) {
+            dup2(pp[0], 0);
+            dup2(f, 1);
+            // the child must not hold the write ends of the other sinks' pipes open
+            for (int k = 3; k < 4096; k++) close(k);
+            execlp(pigz ? "pigz" : "gzip", pigz ? "pigz" : "gzip", "-c", (char *)nullptr);
+            _exit(127);
+        }
+        close(pp[0]);
+        close(f);
+        fd = pp[1];
+        child = pid;
+        fcntl(fd, F_SETPIPE_SZ, 1 << 20);
+        g_sinks.push_back(this);
+    }
+    void close_wait() {
+        if (fd >= 0) close(fd);
+        fd = -1;
+        if (child > 0) {
+            int st;
+            waitpid(child, &st, 0);
+        }
+        child = 0;
+    }
+};
+static void close_all_sinks() {
+    for (auto *s : g_sinks)
+        if (s->fd >= 0) {
+            close(s->fd);
+            s->fd = -1;
+        }
+    for (auto *s : g_sinks) s->close_wait();
+    g_sinks.clear();
+}
+
+// ------------------------------------------------------------------------------------------------
+// GPU context shared by the subcommands
+// ------------------------------------------------------------------------------------------------
+struct Gpu {
+    sk_ctx *ctx = nullptr;
+    uint64_t batch_bytes = 0, max_records = 0, out_cap = 0;
+    static const int NSLOT = 2;
+    uint8_t *out_h[NSLOT][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+
+    void create(uint32_t max_samples, bool aux, int n_out) {
+        uint64_t mb = 32;
+        if (const char *e = getenv("SK_BATCH_MB")) mb = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
+        batch_bytes = mb << 20;
+        max_records = std::max<uint64_t>(batch_bytes / 64, 1024);
+        int dev = 0;
+        if (const char *e = getenv("SK_DEVICE")) dev = atoi(e);
+        sk_limits lim;
+        memset(&lim, 0, sizeof lim);
+        lim.max_stream_bytes = batch_bytes;
+        lim.max_records = max_records;
+        lim.n_slots = NSLOT;
+        lim.max_samples = max_samples;
+        lim.aux_streams = aux ? 1 : 0;
+        int rc = sk_ctx_create(dev, &lim, &ctx);
+        if (rc != SK_OK) {
+            fprintf(stderr, "seqkit_b200: cannot initialise the GPU path: %s\n", sk_last_error(nullptr));
+            finish(3);
+        }
+        out_cap = sk_out_capacity(ctx);
+        for (int s = 0; s < NSLOT; s++)
+            for (int m = 0; m < n_out; m++) out_h[s][m] = (uint8_t *)pinned(out_cap);
+    }
+    void *pinned(uint64_t n) {
+        void *p = sk_pinned_alloc(ctx, n);
+        if (!p) {
+            fprintf(stderr, "seqkit_b200: cannot allocate %llu bytes of pinned memory\n", (unsigned long long)n);
+            finish(3);
+        }
+        return p;
+    }
+    void init_stream(Stream &st, const std::string &path) {
+        st.active = true;
+        st.cap = batch_bytes;
+        st.buf[0] = (uint8_t *)pinned(batch_bytes);
+        st.buf[1] = (uint8_t *)pinned(batch_bytes);
+        st.in.open_path(path);
+    }
+    void ck(int rc, const char *what) {
+        if (rc != SK_OK) {
+            fflush(stdout);
+            fprintf(stderr, "seqkit_b200: %s failed (%d): %s\n", what, rc, sk_last_error(ctx));
+            finish(3);
+        }
+    }
+};
+
+static void refuse_status(const sk_result &r, uint64_t base) {
+    const unsigned long long rec = (unsigned long long)(base + r.err_record);
+    switch (r.status) {
+        case SK_DATA_NON_ASCII: refuse("non-ASCII bytes in the input");
+        case SK_DATA_RECORD_TOO_LONG: refuse("record %llu is longer than the chunk overhang", rec);
+        case SK_DATA_CHUNK_TOO_DENSE: refuse("too many records in one chunk near record %llu", rec);
+        case SK_DATA_MIXED_FORMAT: refuse("mixed FASTA/FASTQ records (record %llu)", rec);
+        case SK_DATA_OUT_OVERFLOW: refuse("output capacity exceeded near record %llu", rec);
+        case SK_DATA_TRUNCATED_FUSED: refuse("fused trim+demultiplex on a truncated header (record %llu)", rec);
+        default: break;
+    }
+}
+
+// Rust's `u8::from_str` (fasta_trim_by_quality.rs:13): optional '+', decimal digits, <= 255.
+static bool parse_u8(const char *s, unsigned *v) {
+    if (*s == '+') s++;
+    if (!*s) return false;
+    unsigned long x = 0;
+    for (; *s; s++) {
+        if (*s < '0' || *s > '9') return false;
+        x = x * 10 + (unsigned long)(*s - '0');
+        if (x > 255) return false;
+    }
+    *v = (unsigned)x;
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------------
+// trim by quality / mask by quality / add barcode: one ordered output stream to stdout
+// ------------------------------------------------------------------------------------------------
+enum StreamOp { OP_TRIM, OP_MASK, OP_ADDBC };
+
+struct Batch {
+    bool live = false;
+    size_t n = 0;           // records
+    size_t bytes[SK_N_INPUTS] = {0, 0, 0, 0};
+    const uint8_t *src[SK_N_INPUTS] = {nullptr, nullptr, nullptr, nullptr};  // pinned copies (valid until the slot is reused)
+    uint64_t first_record = 0;
+};
+
+static int run_stream_op(StreamOp op, const std::string &fastq_path, const std::string &aux_path, unsigned min_baseq) {
+    Gpu g;
+    g.create(0, op == OP_ADDBC, 1);
+    Stream rd, bc;
+    g.init_stream(rd, fastq_path);
+    if (op == OP_ADDBC) g.init_stream(bc, aux_path);
+    std::vector<uint8_t> last_bc;  // last barcode record: reused once the barcode file is exhausted (fasta_add_barcode.rs:20-27)
+    bool first = true, bc_fastx = false;
+    Batch batches[Gpu::NSLOT];
+    uint64_t bi = 0;
+
+    auto launch = [&](int slot, uint64_t rec_limit) {
+        if (op == OP_TRIM) g.ck(sk_trim_by_quality(g.ctx, slot, min_baseq, rec_limit), "sk_trim_by_quality");
+        else if (op == OP_MASK) g.ck(sk_mask_by_quality(g.ctx, slot, min_baseq, rec_limit), "sk_mask_by_quality");
+        else g.ck(sk_add_barcode(g.ctx, slot, rec_limit), "sk_add_barcode");
+    };
+    auto submit = [&](int slot) -> bool {
+        Batch &B = batches[slot];
+        B = Batch();
+        rd.top_up();
+        if (first) {
+            first = false;
+            if (op == OP_ADDBC) {
+                auto reframe = [](Stream &x) {  // '>' = FASTA framing, 2 lines per record (fasta_add_barcode.rs:25-27,39-40)
+                    x.lpr = 2;
+                    x.rec_ends.clear();
+                    x.scanned = 0;
+                    x.lines_mod = 0;
+                    x.top_up();
+                };
+                if (rd.fill && rd.buf[rd.cur][0] == '>') reframe(rd);
+                bc.top_up();
+                bc_fastx = bc.fill && (bc.buf[bc.cur][0] == '@' || bc.buf[bc.cur][0] == '>');
+                if (bc.fill && bc.buf[bc.cur][0] == '>') reframe(bc);
+            }
+        }
+        size_t n = std::min<size_t>(rd.avail(), g.max_records);
+        if (n == 0) {
+            if (rd.drained()) return false;
+            refuse("a record does not fit in one batch (%llu bytes); raise SK_BATCH_MB", (unsigned long long)g.batch_bytes);
+        }
+        // Barcode records of this batch (fasta_add_barcode.rs:20-27).  A barcode file that does not start
+        // with '@' or '>' never yields a barcode; once the file is exhausted the last barcode is reused.
+        size_t nb = 0;
+        bool bc_reuse = false;
+        if (op == OP_ADDBC && bc_fastx) {
+            bc.top_up();
+            if (bc.avail() == 0 && bc.in.eof) {
+                bc_reuse = !last_bc.empty();
+            } else {
+                nb = std::min(n, bc.avail());
+                if (nb < n && !bc.in.eof) n = nb;  // the rest of the barcode records is still to be read
+                if (n == 0) refuse("a barcode record does not fit in one batch; raise SK_BATCH_MB");
+            }
+        }
+        B.live = true;
+        B.n = n;
+        B.first_record = rd.records_done;
+        B.bytes[SK_IN_R1] = rd.bytes_for(n);
+        B.src[SK_IN_R1] = rd.buf[rd.cur];
+        g.ck(sk_upload(g.ctx, slot, SK_IN_R1, B.src[SK_IN_R1], B.bytes[SK_IN_R1]), "sk_upload");
+        if (op == OP_ADDBC) {
+            B.src[SK_IN_AUX1] = bc.buf[bc.cur];
+            if (bc_reuse) {
+                memcpy(bc.buf[bc.cur], last_bc.data(), last_bc.size());
+                B.bytes[SK_IN_AUX1] = last_bc.size();
+                bc.cur ^= 1;  // the copy stays untouched until this slot is reused
+            } else if (nb) {
+                B.bytes[SK_IN_AUX1] = bc.bytes_for(nb);
+                const size_t s0 = nb >= 2 ? bc.bytes_for(nb - 1) : 0;
+                last_bc.assign(bc.buf[bc.cur] + s0, bc.buf[bc.cur] + B.bytes[SK_IN_AUX1]);
+            }
+            g.ck(sk_upload(g.ctx, slot, SK_IN_AUX1, B.src[SK_IN_AUX1], B.bytes[SK_IN_AUX1]), "sk_upload");
+            if (nb) bc.consume(nb, B.bytes[SK_IN_AUX1]);
+        }
+        launch(slot, 0);
+        rd.consume(n, B.bytes[SK_IN_R1]);
+        return true;
+    };
+    auto fetch_out = [&](int slot, uint64_t n) {
+        if (n > g.out_cap) refuse("output larger than the slot capacity");
+        if (n) g.ck(sk_download_out(g.ctx, slot, 0, g.out_h[slot][0], n), "sk_download_out");
+        g.ck(sk_wait(g.ctx, slot, nullptr), "sk_wait");
+        write_all(1, g.out_h[slot][0], n);
+    };
+    auto complete = [&](int slot) {
+        Batch &B = batches[slot];
+        sk_result r;
+        g.ck(sk_wait(g.ctx, slot, &r), "sk_wait");
+        refuse_status(r, B.first_record);
+        if (r.status == SK_DATA_OK) {
+            fetch_out(slot, r.out_bytes[0]);
+            B.live = false;
+            return;
+        }
+        // A record the reference stops at: everything before it has already been printed (replay).
+        uint64_t off = 0;
+        if (r.err_record) {
+            launch(slot, r.err_record);
+            sk_result rep;
+            g.ck(sk_wait(g.ctx, slot, &rep), "sk_wait");
+            fetch_out(slot, rep.out_bytes[0]);
+            off = rep.consumed[SK_IN_R1];
+        }
+        const uint8_t *d = B.src[SK_IN_R1];
+        const size_t nbytes = B.bytes[SK_IN_R1];
+        const uint8_t *nl = (const uint8_t *)memchr(d + off, '\n', nbytes - off);
+        const size_t hlen = nl ? (size_t)(nl - (d + off)) + 1 : nbytes - off;
+        switch (r.status) {
+            case SK_DATA_BAD_HEADER: fatal("Invalid FASTQ format encountered.");  // trim :20-22, mask :21-23
+            case SK_DATA_LEN_MISMATCH: fatal("Read sequence and base qualities are of different length.");  // mask :35-37
+            case SK_DATA_SEQ_SHORT:  // trim :47 slice panic; the header (:23) is already out
+                write_all(1, d + off, hlen);
+                panic101("byte index out of range of seq (fasta_trim_by_quality.rs:47)");
+            case SK_DATA_BAD_FASTX_LINE: {  // add barcode :33 then :41-43
+                write_all(1, d + off, trim_end_len(d + off, hlen));
+                write_all(1, (const uint8_t *)" BC:", 4);
+                // barcode of iteration err_record: sequence line of that barcode record (or the last one)
+                const uint8_t *b = B.src[SK_IN_AUX1];
+                const size_t bn = B.bytes[SK_IN_AUX1];
+                if (bn && (b[0] == '@' || b[0] == '>')) {
+                    const uint32_t lpr = b[0] == '>' ? 2 : 4;
+                    std::vector<size_t> ls{0};
+                    for (size_t i = 0; i < bn; i++)
+                        if (b[i] == '\n' && i + 1 < bn) ls.push_back(i + 1);
+                    const size_t nrec = (ls.size() + lpr - 1) / lpr;
+                    const size_t i = std::min<size_t>(r.err_record, nrec - 1);
+                    const size_t j = i * lpr + 1;
+                    if (j < ls.size()) {
+                        const size_t e = j + 1 < ls.size() ? ls[j + 1] : bn;
+                        write_all(1, b + ls[j], trim_end_len(b + ls[j], e - ls[j]));
+                    }
+                }
+                write_all(1, (const uint8_t *)"\n", 1);
+                std::string h((const char *)d + off, hlen);
+                fatal("Invalid FASTQ line:\n%s", h.c_str());
+            }
+            default:
+                fprintf(stderr, "seqkit_b200: unexpected data status %d\n", r.status);
+                finish(3);
+        }
+    };
+
+    bool more = submit(0);
+    while (more) {
+        const int slot = (int)(bi & 1), nxt = slot ^ 1;
+        more = submit(nxt);
+        complete(slot);
+        bi++;
+    }
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// demultiplex (fasta_demultiplex.rs:30-265)
+// ------------------------------------------------------------------------------------------------
+struct Sample {
+    std::string name, barcode;
+    GzipSink out[2];
+    uint64_t total_reads = 0;
+};
+
+static bool bc_class(uint8_t c) {
+    switch (c) {
+        case 'A': case 'C': case 'G': case 'T': case 'N': case 'a': case 'c': case 'g': case 't': case 'n': case '+':
+            return true;
+    }
+    return false;
+}
+// Regex::find(" BC:[ACGTNacgtn+]+") -- only used to quote the barcode in messages and the dry-run table.
+static bool bc_find(const uint8_t *s, size_t n, size_t *st, size_t *en) {
+    for (size_t i = 0; i + 5 <= n; i++)
+        if (s[i] == ' ' && s[i + 1] == 'B' && s[i + 2] == 'C' && s[i + 3] == ':' && bc_class(s[i + 4])) {
+            size_t e = i + 5;
+            while (e < n && bc_class(s[e])) e++;
+            *st = i;
+            *en = e;
+            return true;
+        }
+    return false;
+}
+
+static int run_demultiplex(int argc, char **argv) {
+    bool parallel = false;
+    std::string index1, index2, dry_s;
+    bool have_dry = false;
+    int fused_trim = -1;  // extension (off by default): --trim-by-quality=Q fuses `fasta trim by quality` into the pass
+    std::vector<std::string> pos;
+    for (int a = 2; a < argc; a++) {
+        std::string s = argv[a];
+        auto val = [&](const char *name, std::string &dst) -> bool {
+            const size_t k = strlen(name);
+            if (s.compare(0, k, name) != 0) return false;
+            if (s.size() > k && s[k] == '=') {
+                dst = s.substr(k + 1);
+                return true;
+            }
+            if (s.size() == k && a + 1 < argc) {
+                dst = argv[++a];
+                return true;
+            }
+            return false;
+        };
+        std::string tq;
+        if (s == "--parallel") parallel = true;
+        else if (val("--index1", index1) || val("--index2", index2)) {}
+        else if (val("--dry-run", dry_s)) have_dry = true;
+        else if (val("--trim-by-quality", tq)) {
+            unsigned q;
+            if (!parse_u8(tq.c_str(), &q)) invalid_args(USAGE_DEMUX);
+            fused_trim = (int)q;
+        } else if (s.size() > 1 && s[0] == '-' && s != "-") invalid_args(USAGE_DEMUX);
+        else pos.push_back(s);
+    }
+    if (pos.size() < 2 || pos.size() > 3) invalid_args(USAGE_DEMUX);
+    uint64_t dry_run = 0;  // :33-36
+    if (have_dry) {
+        char *e = nullptr;
+        errno = 0;
+        dry_run = dry_s.empty() || dry_s[0] == '-' ? 0 : strtoull(dry_s.c_str(), &e, 10);
+        if (errno || (e && *e)) dry_run = 0;
+        if (dry_run == 0 && !dry_s.empty()) fatal("In --dry-run=N, N must be 64-bit positive integer.");
+    }
+    const bool paired = pos.size() == 3 && !pos[2].empty();
+
+    // Readers are opened before the sheet is read (:41-55), so "Cannot open file" comes first.
+    Gpu g;
+    Stream st[SK_N_INPUTS];
+    Input sheet_in;
+    // (open order of the reference: fastq_1, fastq_2, index1, index2, then the sheet)
+    std::vector<std::pair<int, std::string>> to_open;
+    to_open.push_back({SK_IN_R1, pos[1]});
+    if (paired) to_open.push_back({SK_IN_R2, pos[2]});
+    if (!index1.empty()) to_open.push_back({SK_IN_AUX1, index1});
+    if (!index2.empty()) to_open.push_back({SK_IN_AUX2, index2});
+    for (auto &o : to_open) {  // check readability up front; the pinned buffers come with the context below
+        if (o.second == "-") continue;
+        int f = open(o.second.c_str(), O_RDONLY);
+        if (f < 0) fatal("Cannot open file %s for reading.", o.second.c_str());
+        close(f);
+    }
+
+    fputs("Reading sample sheet...\n", stderr);  // :58
+    sheet_in.open_path(pos[0]);
+    std::vector<uint8_t> sheet;
+    {
+        uint8_t tmp[1 << 16];
+        size_t k;
+        while ((k = sheet_in.read_some(tmp, sizeof tmp)) > 0) sheet.insert(sheet.end(), tmp, tmp + k);
+    }
+    for (uint8_t c : sheet)
+        if (c >= 0x80) refuse("non-ASCII bytes in the sample sheet");
+    std::vector<Sample *> samples;
+    size_t barcode_len = 0;
+    for (size_t p = 0; p < sheet.size();) {  // :63-95
+        const uint8_t *nl = (const uint8_t *)memchr(sheet.data() + p, '\n', sheet.size() - p);
+        const size_t end = nl ? (size_t)(nl - sheet.data()) + 1 : sheet.size();
+        const uint8_t *line = sheet.data() + p;
+        size_t n = end - p;
+        p = end;
+        if (n && line[0] == '#') continue;  // :64
+        size_t off = 0;
+        while (off < n && is_ws(line[off])) off++;  // line.trim() :65
+        const uint8_t *t = line + off;
+        const size_t tn = trim_end_len(t, n - off);
+        const uint8_t *tab = (const uint8_t *)memchr(t, '\t', tn);
+        if (!tab) continue;  // cols.len() < 2 :66
+        const size_t name_n = (size_t)(tab - t);
+        const uint8_t *c1 = tab + 1;
+        const size_t rest = tn - name_n - 1;
+        const uint8_t *tab2 = (const uint8_t *)memchr(c1, '\t', rest);
+        const size_t bc_n = tab2 ? (size_t)(tab2 - c1) : rest;
+        std::string name((const char *)t, name_n);
+        if (bc_n == 0) fatal("Sample %s has no barcode.", name.c_str());  // :68
+        if (barcode_len == 0) barcode_len = bc_n;                        // :69-73
+        else if (bc_n != barcode_len) fatal("Barcodes in sample sheet must all be of same length.");
+        Sample *s = new Sample();
+        s->name = name;
+        s->barcode.assign((const char *)c1, bc_n);
+        samples.push_back(s);
+        if (dry_run == 0) {  // outputs are created while the sheet is read (:77-87)
+            if (paired) {
+                s->out[0].open_path(name + "_1.fq.gz", parallel);
+                s->out[1].open_path(name + "_2.fq.gz", parallel);
+            } else {
+                s->out[0].open_path(name + ".fq.gz", parallel);
+            }
+        }
+    }
+    for (size_t a = 0; a < samples.size(); a++)  // :98-104
+        for (size_t b = a + 1; b < samples.size(); b++)
+            if (samples[a]->name == samples[b]->name)
+                fatal("Sample %s is listed multiple times in sample sheet.", samples[a]->name.c_str());
+    fprintf(stderr, "Starting demultiplexing in %s end mode...\n", paired ? "paired" : "single");  // :106-107
+
+    const uint32_t S = (uint32_t)samples.size();
+    if (S == 0) refuse("empty sample sheet");
+    const bool use_aux = !index1.empty() || !index2.empty();
+    g.create(S, use_aux, paired ? 2 : 1);
+    for (auto &o : to_open) g.init_stream(st[o.first], o.second);
+    {
+        std::string flat;
+        for (auto *s : samples) flat += s->barcode;
+        int rc = sk_set_sheet(g.ctx, (const uint8_t *)flat.data(), S, (uint32_t)barcode_len);
+        if (rc == SK_E_UNSUPPORTED) refuse("%s", sk_last_error(g.ctx));
+        g.ck(rc, "sk_set_sheet");
+    }
+    const uint32_t use_index = (index1.empty() ? 0u : 1u) | (index2.empty() ? 0u : 2u);
+    const uint32_t max_chunks = sk_max_chunks(g.ctx);
+    uint64_t *base_h[Gpu::NSLOT][2];
+    uint16_t *lens_h[Gpu::NSLOT][2];
+    for (int s = 0; s < Gpu::NSLOT; s++)
+        for (int m = 0; m < (paired ? 2 : 1); m++) {
+            base_h[s][m] = (uint64_t *)g.pinned((uint64_t)max_chunks * 8);
+            lens_h[s][m] = (uint16_t *)g.pinned((uint64_t)max_chunks * S * 2);
+        }
+    std::vector<uint64_t> counts_h(S + 2);
+    std::vector<sk_event> events;
+    std::vector<int16_t> assign_h;
+    std::unordered_map<std::string, uint64_t> extra;  // dry run: barcodes matching no sample (:190-194)
+    std::vector<std::string> extra_order;
+    uint64_t total_reads = 0, identified_reads = 0;
+    Batch batches[Gpu::NSLOT];
+    uint64_t bi = 0;
+    unsigned n_threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+
+    auto call = [&](int slot, uint64_t rec_limit) {
+        sk_demux_opts o;
+        memset(&o, 0, sizeof o);
+        o.fused_trim_min_baseq = fused_trim;
+        o.use_index = use_index;
+        o.rec_limit = rec_limit;
+        o.no_output = dry_run ? 1 : 0;
+        g.ck(sk_demultiplex(g.ctx, slot, &o), "sk_demultiplex");
+    };
+    auto submit = [&](int slot) -> bool {
+        Batch &B = batches[slot];
+        B = Batch();
+        if (dry_run && st[SK_IN_R1].records_done >= dry_run) return false;  // :248
+        for (auto &o : to_open) st[o.first].top_up();
+        size_t n = std::min<size_t>(st[SK_IN_R1].avail(), g.max_records);
+        if (n == 0) {
+            if (st[SK_IN_R1].drained()) return false;
+            refuse("a record does not fit in one batch (%llu bytes); raise SK_BATCH_MB", (unsigned long long)g.batch_bytes);
+        }
+        for (auto &o : to_open) {
+            if (o.first == SK_IN_R1) continue;
+            Stream &x = st[o.first];
+            if (x.avail() < n) {
+                if (x.in.eof) refuse("mate / index files hold fewer records than <fastq_1>");
+                n = x.avail();
+                if (n == 0) refuse("a record does not fit in one batch; raise SK_BATCH_MB");
+            }
+        }
+        if (dry_run) n = (size_t)std::min<uint64_t>(n, dry_run - st[SK_IN_R1].records_done);
+        B.live = true;
+        B.n = n;
+        B.first_record = st[SK_IN_R1].records_done;
+        for (auto &o : to_open) {
+            Stream &x = st[o.first];
+            B.bytes[o.first] = x.bytes_for(n);
+            B.src[o.first] = x.buf[x.cur];
+            g.ck(sk_upload(g.ctx, slot, o.first, B.src[o.first], B.bytes[o.first]), "sk_upload");
+        }
+        if (!paired) g.ck(sk_set_input_len(g.ctx, slot, SK_IN_R2, 0), "sk_set_input_len");
+        call(slot, 0);
+        for (auto &o : to_open) st[o.first].consume(n, B.bytes[o.first]);
+        return true;
+    };
+    // observed barcode of a record, for messages only
+    auto index_barcode = [&](const Batch &B, uint32_t off1, uint32_t off2) {
+        std::string bc;
+        const int which[2] = {index1.empty() ? SK_IN_AUX2 : SK_IN_AUX1, SK_IN_AUX2};
+        const uint32_t offs[2] = {off1, off2};
+        for (int q = 0; q < 2; q++) {
+            if (offs[q] == 0xFFFFFFFFu) continue;
+            const uint8_t *d = B.src[which[q]];
+            const size_t nb = B.bytes[which[q]];
+            if (offs[q] > nb) continue;
+            const uint8_t *nl = (const uint8_t *)memchr(d + offs[q], '\n', nb - offs[q]);
+            const size_t len = trim_end_len(d + offs[q], nl ? (size_t)(nl - (d + offs[q])) : nb - offs[q]);
+            if (q == 1 && !bc.empty()) bc += '+';
+            bc.append((const char *)d + offs[q], len);
+        }
+        return bc;
+    };
+    // processes the results of a batch that ran with `r` (possibly a replay limited to the records before an error)
+    auto drain = [&](int slot, const sk_result &r) {
+        Batch &B = batches[slot];
+        g.ck(sk_download_counts(g.ctx, slot, counts_h.data()), "sk_download_counts");
+        for (uint32_t s = 0; s < S; s++) samples[s]->total_reads += counts_h[s];
+        total_reads += counts_h[S];
+        identified_reads += counts_h[S + 1];
+        // WARNING lines in record order (:184-188)
+        if (r.flags & SK_FLAG_EVENTS_OVERFLOW) refuse("too many ambiguous reads in one batch");
+        events.resize(std::max<uint32_t>(r.n_events, 1));
+        const int ne = sk_download_events(g.ctx, slot, events.data(), r.n_events);
+        for (int k = 0; k < ne; k++) {
+            const sk_event &e = events[k];
+            std::string bc = use_index ? index_barcode(B, e.bc_off, e.bc_off2)
+                                       : std::string((const char *)B.src[SK_IN_R1] + e.bc_off, barcode_len);
+            const Sample *a = samples[e.best_sample], *b = samples[e.equally_fine_sample];
+            fprintf(stderr,
+                    "WARNING: Sequenced barcode %s was an equally good match (%u mismatches) for samples %s (%s) and %s "
+                    "(%s), and was therefore not assigned to any sample.\n",
+                    bc.c_str(), e.mismatches, a->name.c_str(), a->barcode.c_str(), b->name.c_str(), b->barcode.c_str());
+        }
+        if (dry_run) {
+            // tally the barcodes of reads whose best match is worse than one mismatch (:190-194)
+            assign_h.resize(std::max<uint64_t>(r.n_records, 1));
+            g.ck(sk_download_assign(g.ctx, slot, assign_h.data(), r.n_records), "sk_download_assign");
+            const uint8_t *d = B.src[SK_IN_R1];
+            size_t p = 0;
+            std::vector<size_t> ipos(2, 0);
+            for (uint64_t i = 0; i < r.n_records; i++) {
+                // record i of every stream starts where record i-1 ended: walk four lines
+                auto next_record = [](const uint8_t *b, size_t n, size_t &q, size_t &l1, size_t &l1e) {
+                    size_t line = 0;
+                    const size_t s0 = q;
+                    l1 = l1e = s0;
+                    while (line < 4 && q < n) {
+                        const uint8_t *nl = (const uint8_t *)memchr(b + q, '\n', n - q);
+                        const size_t e = nl ? (size_t)(nl - b) + 1 : n;
+                        if (line == 0) l1 = e;
+                        if (line == 1) l1e = e;
+                        q = e;
+                        line++;
+                    }
+                    if (line < 2) l1e = l1;
+                    return s0;
+                };
+                size_t l1, l1e;
+                const size_t h0 = next_record(d, B.bytes[SK_IN_R1], p, l1, l1e);
+                std::string bc;
+                if (use_index) {
+                    int k = 0;
+                    for (int w : {SK_IN_AUX1, SK_IN_AUX2}) {
+                        if (!st[w].active) continue;
+                        size_t a1, a1e;
+                        next_record(B.src[w], B.bytes[w], ipos[k], a1, a1e);
+                        if (!bc.empty()) bc += '+';
+                        bc.append((const char *)B.src[w] + a1, trim_end_len(B.src[w] + a1, a1e - a1));
+                        k++;
+                    }
+                } else {
+                    size_t a, b;
+                    if (bc_find(d + h0, l1 - h0, &a, &b)) bc.assign((const char *)d + h0 + a + 4, b - a - 4);
+                }
+                if (assign_h[i] == -1) {
+                    auto it = extra.find(bc);
+                    if (it == extra.end()) {
+                        extra.emplace(bc, 1);
+                        extra_order.push_back(bc);
+                    } else {
+                        it->second++;
+                    }
+                }
+            }
+            return;
+        }
+        // per-sample slices -> gzip children, in (batch, chunk) order; samples are spread over writer threads
+        const int nm = paired ? 2 : 1;
+        for (int m = 0; m < nm; m++) {
+            if (r.out_extent[m] > g.out_cap) refuse("output larger than the slot capacity");
+            if (r.out_extent[m]) g.ck(sk_download_out(g.ctx, slot, m, g.out_h[slot][m], r.out_extent[m]), "sk_download_out");
+            g.ck(sk_download_demux_tables(g.ctx, slot, m, base_h[slot][m], lens_h[slot][m]), "sk_download_demux_tables");
+        }
+        g.ck(sk_wait(g.ctx, slot, nullptr), "sk_wait");
+        // offs[c*S+s] = start of sample s's slice inside chunk c (exclusive prefix over the row)
+        std::vector<uint32_t> offs;
+        for (int m = 0; m < nm; m++) {
+            const uint32_t nc = r.n_chunks[m];
+            offs.assign((size_t)nc * S, 0);
+            const uint16_t *lens = lens_h[slot][m];
+            for (uint32_t c = 0; c < nc; c++) {
+                uint32_t run = 0;
+                const uint16_t *row = lens + (size_t)c * S;
+                uint32_t *o = offs.data() + (size_t)c * S;
+                for (uint32_t s = 0; s < S; s++) {
+                    o[s] = run;
+                    run += row[s];
+                }
+            }
+            std::atomic<uint32_t> next{0};
+            auto worker = [&]() {
+                std::vector<uint8_t> tmp;
+                for (;;) {
+                    const uint32_t s = next.fetch_add(1);
+                    if (s >= S) break;
+                    tmp.clear();
+                    for (uint32_t c = 0; c < nc; c++) {
+                        const uint32_t len = lens[(size_t)c * S + s];
+                        if (!len) continue;
+                        const uint8_t *src = g.out_h[slot][m] + base_h[slot][m][c] + offs[(size_t)c * S + s];
+                        tmp.insert(tmp.end(), src, src + len);
+                    }
+                    if (!tmp.empty()) write_all(samples[s]->out[m].fd, tmp.data(), tmp.size());
+                }
+            };
+            std::vector<std::thread> pool;
+            const unsigned nt = std::min<unsigned>(n_threads, S);
+            for (unsigned t = 1; t < nt; t++) pool.emplace_back(worker);
+            worker();
+            for (auto &t : pool) t.join();
+        }
+    };
+    auto complete = [&](int slot) {
+        Batch &B = batches[slot];
+        sk_result r;
+        g.ck(sk_wait(g.ctx, slot, &r), "sk_wait");
+        refuse_status(r, B.first_record);
+        if (r.flags & SK_FLAG_MATE_COUNT) refuse("mate / index files hold fewer records than <fastq_1>");
+        if (r.status == SK_DATA_OK) {
+            drain(slot, r);
+            B.live = false;
+            return;
+        }
+        sk_result rep;
+        memset(&rep, 0, sizeof rep);
+        if (r.err_record) {
+            call(slot, r.err_record);
+            g.ck(sk_wait(g.ctx, slot, &rep), "sk_wait");
+            drain(slot, rep);
+        }
+        const uint8_t *d = B.src[SK_IN_R1];
+        const size_t nbytes = B.bytes[SK_IN_R1];
+        const size_t off = r.err_record ? rep.consumed[SK_IN_R1] : 0;
+        const uint8_t *nl = (const uint8_t *)memchr(d + off, '\n', nbytes - off);
+        const size_t hlen = nl ? (size_t)(nl - (d + off)) + 1 : nbytes - off;
+        std::string hdr((const char *)d + off, hlen);
+        switch (r.status) {
+            case SK_DATA_BAD_HEADER: fatal("Invalid FASTQ header line:\n%s", hdr.c_str());  // :118-120
+            case SK_DATA_NO_BC: fatal("No BC:xxxx field found.");                           // :141
+            case SK_DATA_BC_LEN: {                                                          // :148-150
+                std::string bc;
+                if (use_index) {
+                    uint32_t offs2[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+                    int k = index1.empty() ? 1 : 0;
+                    for (int w : {SK_IN_AUX1, SK_IN_AUX2}) {
+                        if (!st[w].active) continue;
+                        const size_t o = r.err_record ? rep.consumed[w] : 0;
+                        const uint8_t *b = B.src[w];
+                        const uint8_t *e = (const uint8_t *)memchr(b + o, '\n', B.bytes[w] - o);
+                        offs2[k++] = e ? (uint32_t)(e - b) + 1 : (uint32_t)B.bytes[w];
+                    }
+                    bc = index_barcode(B, offs2[0], offs2[1]);
+                } else {
+                    size_t a, b;
+                    if (bc_find((const uint8_t *)hdr.data(), hdr.size(), &a, &b)) bc = hdr.substr(a + 4, b - a - 4);
+                }
+                fatal("Sequenced barcode %s is of different length (%zu nt) than barcodes in the sample sheet (%zu nt).",
+                      bc.c_str(), bc.size(), barcode_len);
+            }
+            case SK_DATA_INDEX_ASSERT: panic101("assertion failed (fasta_demultiplex.rs:130/134)");
+            case SK_DATA_SEQ_SHORT: refuse("fused trim: sequence shorter than the kept quality prefix");
+            default:
+                fprintf(stderr, "seqkit_b200: unexpected data status %d\n", r.status);
+                finish(3);
+        }
+    };
+
+    bool more = submit(0);
+    while (more) {
+        const int slot = (int)(bi & 1), nxt = slot ^ 1;
+        more = submit(nxt);
+        complete(slot);
+        bi++;
+    }
+
+    if (dry_run) {  // :251-261
+        fflush(stdout);
+        fprintf(stderr, "Dry run completed with %llu clusters. Barcodes found:\n", (unsigned long long)total_reads);
+        std::vector<std::pair<std::string, uint64_t>> entries;
+        for (auto *s : samples) entries.push_back({s->name, s->total_reads});
+        for (auto &k : extra_order) entries.push_back({k, extra[k]});  // the reference's HashMap order is arbitrary
+        std::stable_sort(entries.begin(), entries.end(),
+                         [](const std::pair<std::string, uint64_t> &a, const std::pair<std::string, uint64_t> &b) {
+                             return a.second < b.second;
+                         });
+        std::reverse(entries.begin(), entries.end());
+        if (entries.size() < 100) panic101("range end index 100 out of range for slice (fasta_demultiplex.rs:258)");
+        for (size_t q = 0; q < 100; q++) printf("- %s: %llu\n", entries[q].first.c_str(), (unsigned long long)entries[q].second);
+        fflush(stdout);
+    }
+    if (total_reads == 0)
+        fprintf(stderr, "%llu / %llu (NaN%%) clusters carried a barcode matching one of the provided samples.\n",
+                (unsigned long long)identified_reads, (unsigned long long)total_reads);
+    else
+        fprintf(stderr, "%llu / %llu (%.1f%%) clusters carried a barcode matching one of the provided samples.\n",
+                (unsigned long long)identified_reads, (unsigned long long)total_reads,
+                (double)identified_reads / (double)total_reads * 100.0);  // :263-264
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// dispatcher (fasta_main.rs:42-82)
+// ------------------------------------------------------------------------------------------------
+int main(int argc, char **argv) {
+    signal(SIGPIPE, SIG_IGN);
+    auto is = [&](int i, const char *w) { return i < argc && strcmp(argv[i], w) == 0; };
+    int rc = 0;
+    if (argc >= 4 && is(1, "trim") && is(2, "by") && is(3, "quality")) {
+        if (argc != 6 || argv[4][0] == '\0') invalid_args(USAGE_TRIM);
+        unsigned q;
+        Input probe;  // FileReader::new precedes the parse of <min_baseq> (fasta_trim_by_quality.rs:12-13)
+        if (strcmp(argv[4], "-") != 0) {
+            int f = open(argv[4], O_RDONLY);
+            if (f < 0) fatal("Cannot open file %s for reading.", argv[4]);
+            close(f);
+        }
+        if (!parse_u8(argv[5], &q)) panic101("min_baseq parse");
+        rc = run_stream_op(OP_TRIM, argv[4], "", q);
+    } else if (argc >= 4 && is(1, "mask") && is(2, "by") && is(3, "quality")) {
+        if (argc != 6) invalid_args(USAGE_MASK);
+        unsigned q;
+        if (strcmp(argv[4], "-") != 0) {
+            int f = open(argv[4], O_RDONLY);
+            if (f < 0) fatal("Cannot open file %s for reading.", argv[4]);
+            close(f);
+        }
+        if (!parse_u8(argv[5], &q)) panic101("min_baseq parse");
+        rc = run_stream_op(OP_MASK, argv[4], "", q);
+    } else if (argc >= 3 && is(1, "add") && is(2, "barcode")) {
+        if (argc != 5) invalid_args(USAGE_ADDBC);
+        for (int k = 3; k <= 4; k++)
+            if (strcmp(argv[k], "-") != 0) {
+                int f = open(argv[k], O_RDONLY);
+                if (f < 0) fatal("Cannot open file %s for reading.", argv[k]);
+                close(f);
+            }
+        rc = run_stream_op(OP_ADDBC, argv[3], argv[4], 0);
+    } else if (argc >= 2 && is(1, "demultiplex")) {
+        rc = run_demultiplex(argc, argv);
+    } else {
+        // Subcommands outside the per-read batch path are not part of this drop-in.
+        fprintf(stderr, "%s\n", TOP_USAGE);
+        rc = 0;
+    }
+    finish(rc);
+}
