@@ -365,8 +365,8 @@ def run_e2e(args, torch, L, bcs, local_rank, rank, world, barrier):
     cap = max(n1, n2) + Pe * 16 + (1 << 20)
     nchunks = lib.sk_max_chunks(eng.ctx)
     h_out = [[torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(2)] for _ in range(nslots)]
-    h_base = [[torch.empty(nchunks, dtype=torch.int64).pin_memory() for _ in range(2)] for _ in range(nslots)]
-    h_lens = [[torch.empty(nchunks * N_SAMPLES, dtype=torch.int16).pin_memory() for _ in range(2)] for _ in range(nslots)]
+    h_rows = [[torch.empty(nchunks * 2, dtype=torch.int64).pin_memory() for _ in range(2)] for _ in range(nslots)]
+    h_groups = [[torch.empty(Pe, dtype=torch.int32).pin_memory() for _ in range(2)] for _ in range(nslots)]
     h_counts = [torch.empty(N_SAMPLES + 2, dtype=torch.int64).pin_memory() for _ in range(nslots)]
     opts = L.DemuxOpts(MIN_BASEQ, 0, 0, 0, 0)
     d2h = [0]
@@ -382,8 +382,9 @@ def run_e2e(args, torch, L, bcs, local_rank, rank, world, barrier):
         nb = 0
         for m in range(2):
             assert lib.sk_download_out(eng.ctx, s, m, h_out[s][m].data_ptr(), res.out_extent[m]) == 0
-            assert lib.sk_download_demux_tables(eng.ctx, s, m, h_base[s][m].data_ptr(), h_lens[s][m].data_ptr()) == 0
-            nb += res.out_extent[m] + res.n_chunks[m] * (8 + 2 * N_SAMPLES)
+            assert lib.sk_download_demux_tables(eng.ctx, s, m, h_rows[s][m].data_ptr(), h_groups[s][m].data_ptr(),
+                                                res.n_records) == 0
+            nb += res.out_extent[m] + res.n_chunks[m] * 16 + res.n_records * 4
         assert lib.sk_download_counts(eng.ctx, s, h_counts[s].data_ptr()) == 0  # syncs the slot
         d2h[0] = nb + (N_SAMPLES + 2) * 8
         return res

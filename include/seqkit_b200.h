@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define SK_ABI_VERSION 1
+#define SK_ABI_VERSION 2
 
 /* ---- API return codes (every function returning int) ------------------------------------- */
 #define SK_OK 0
@@ -173,12 +173,23 @@ const void *sk_out_dev(sk_ctx *ctx, uint32_t slot, uint32_t which);
  * before it; the copy is ordered on the slot's stream). */
 int sk_download_out(sk_ctx *ctx, uint32_t slot, uint32_t which, void *host, uint64_t n);
 
-/* Demultiplex side tables (valid after sk_wait).  For output stream m, chunk c, sample s the
- * slice is  [chunk_base[c] + sum_{t<s} lens[c*S+t],  + lens[c*S+s])  inside output stream m;
- * concatenating a sample's slices over c = 0..n_chunks-1 gives that sample's file content in
- * input order (fasta_demultiplex.rs:196-238). */
-int sk_download_demux_tables(sk_ctx *ctx, uint32_t slot, uint32_t which, uint64_t *chunk_base /*[n_chunks]*/,
-                             uint16_t *lens /*[n_chunks*S]*/);
+/* Demultiplex side tables (valid after sk_wait).  The kernels write the records of a chunk grouped by
+ * sample, input order kept inside a sample ("stable per-sample compaction", chunk by chunk).  For
+ * output stream m, row c describes chunk c: its groups are groups[first_group .. first_group+n_groups),
+ * laid out back to back from byte `base` of output stream m.  Appending, for every sample, its groups
+ * over c = 0..n_chunks-1 gives that sample's file content in input order (fasta_demultiplex.rs:196-238). */
+typedef struct sk_group {
+    uint16_t sample;
+    uint16_t len; /* bytes */
+} sk_group;
+typedef struct sk_chunk_row {
+    uint64_t base;
+    uint32_t first_group;
+    uint32_t n_groups;
+} sk_chunk_row;
+/* rows[n_chunks], groups[n_records] (n_records = sk_result.n_records of the operator). */
+int sk_download_demux_tables(sk_ctx *ctx, uint32_t slot, uint32_t which, sk_chunk_row *rows, sk_group *groups,
+                             uint64_t n_records);
 /* counts[0..S) = Sample.total_reads (:27,178), counts[S] = total_reads, counts[S+1] = identified_reads. */
 int sk_download_counts(sk_ctx *ctx, uint32_t slot, uint64_t *counts /*[S+2]*/);
 const void *sk_counts_dev(sk_ctx *ctx, uint32_t slot); /* device u64[S+2], for an in-place all-reduce */
@@ -186,10 +197,10 @@ int sk_download_events(sk_ctx *ctx, uint32_t slot, sk_event *events, uint32_t ca
 /* Per-record sample assignment of the last sk_demultiplex: >=0 sample, -1 no match, -2 ambiguous. */
 int sk_download_assign(sk_ctx *ctx, uint32_t slot, int16_t *assign, uint64_t n_records);
 
-/* Host helper: appends sample `s`'s slices (host copies of one output stream and its tables) to
+/* Host helper: appends sample `s`'s groups (host copies of one output stream and its tables) to
  * `dst`; returns the number of bytes written, or the required size when dst_cap is too small. */
-uint64_t sk_demux_gather(const uint8_t *out_host, const uint64_t *chunk_base, const uint16_t *lens, uint32_t n_chunks,
-                         uint32_t S, uint32_t s, uint8_t *dst, uint64_t dst_cap);
+uint64_t sk_demux_gather(const uint8_t *out_host, const sk_chunk_row *rows, const sk_group *groups, uint32_t n_chunks,
+                         uint32_t s, uint8_t *dst, uint64_t dst_cap);
 
 /* ---- multi-GPU ---------------------------------------------------------------------------- */
 /* Sums the S+2 counters of this slot across ranks in place with one ncclAllReduce(sum, u64) on the

@@ -40,6 +40,14 @@ class Event(C.Structure):
                 ("equally_fine_sample", C.c_int16), ("mismatches", C.c_uint32)]
 
 
+class Group(C.Structure):
+    _fields_ = [("sample", C.c_uint16), ("len", C.c_uint16)]
+
+
+class ChunkRow(C.Structure):
+    _fields_ = [("base", C.c_uint64), ("first_group", C.c_uint32), ("n_groups", C.c_uint32)]
+
+
 class DemuxOpts(C.Structure):
     _fields_ = [("fused_trim_min_baseq", C.c_int32), ("use_index", C.c_uint32), ("rec_limit", C.c_uint64),
                 ("no_output", C.c_uint32), ("reserved", C.c_uint32)]
@@ -77,12 +85,12 @@ SIGNATURES = {
     "sk_wait": (C.c_int, [_P, C.c_uint32, C.POINTER(Result)]),
     "sk_out_dev": (_P, [_P, C.c_uint32, C.c_uint32]),
     "sk_download_out": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.c_uint64]),
-    "sk_download_demux_tables": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P]),
+    "sk_download_demux_tables": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, _P, C.c_uint64]),
     "sk_download_counts": (C.c_int, [_P, C.c_uint32, _P]),
     "sk_counts_dev": (_P, [_P, C.c_uint32]),
     "sk_download_events": (C.c_int, [_P, C.c_uint32, C.POINTER(Event), C.c_uint32]),
     "sk_download_assign": (C.c_int, [_P, C.c_uint32, _P, C.c_uint64]),
-    "sk_demux_gather": (C.c_uint64, [_P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P, C.c_uint64]),
+    "sk_demux_gather": (C.c_uint64, [_P, _P, _P, C.c_uint32, C.c_uint32, _P, C.c_uint64]),
     "sk_allreduce_counts": (C.c_int, [_P, C.c_uint32, _P]),
     "sk_nccl_unique_id": (C.c_int, [_P, _P]),
     "sk_nccl_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(_P)]),

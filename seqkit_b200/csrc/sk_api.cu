@@ -17,6 +17,7 @@
 using namespace sk;
 
 static_assert(sizeof(sk_event) == sizeof(Event), "sk_event layout");
+static_assert(sizeof(sk_group) == sizeof(Group) && sizeof(sk_chunk_row) == sizeof(ChunkRow), "demux table layout");
 
 namespace sk {
 int launch_synth(void *ctx_stream, uint8_t *dst, uint64_t cap, const sk_synth_spec &spec, const uint8_t *sheet_raw,
@@ -39,8 +40,8 @@ struct Slot {
     int16_t *assign = nullptr;
     uint8_t *umi = nullptr;
     uint64_t umi_cap = 0;
-    uint16_t *lens[2] = {nullptr, nullptr};
-    uint64_t *chunk_base[2] = {nullptr, nullptr};
+    Group *groups[2] = {nullptr, nullptr};
+    ChunkRow *rows[2] = {nullptr, nullptr};
     unsigned long long *counts = nullptr;
     Event *events = nullptr;
     RecRef *scan_tab[2] = {nullptr, nullptr};
@@ -68,11 +69,12 @@ struct sk_ctx {
     std::vector<uint8_t> sheet_raw;
     uint32_t *d_planes = nullptr, *d_umask = nullptr;
     uint8_t *d_lut = nullptr, *d_sheet_raw = nullptr;
-    // exact-match index (FastIdx)
-    uint32_t f_classes = 0, f_nw = 0, f_tsize = 0;
-    uint32_t *d_fcls = nullptr, *d_skeys = nullptr;
-    unsigned long long *d_ftab = nullptr;
-    int cfg = 0;  // chunk-engine geometry: 0 = CfgBig (32 KiB chunks), 1 = CfgSmall (16 KiB chunks)
+    // pigeonhole index (HalfIdx)
+    uint32_t h_classes = 0, h_nw = 0, h_nwp = 0, h_tsize = 0;
+    uint32_t *d_hcls = nullptr, *d_skeys = nullptr;
+    uint2 *d_htab = nullptr;
+    uint16_t *d_hcand = nullptr;
+    int cfg = 0;  // chunk-engine geometry: 0 = CfgA (16 KiB chunks, 4 warps), 1 = CfgB (32 KiB chunks, 8 warps)
 };
 
 #define CK(call)                                                                         \
@@ -100,8 +102,8 @@ static void free_slot(Slot &s) {
     }
     for (int i = 0; i < 2; i++) {
         cudaFree(s.out[i]);
-        cudaFree(s.lens[i]);
-        cudaFree(s.chunk_base[i]);
+        cudaFree(s.groups[i]);
+        cudaFree(s.rows[i]);
         cudaFree(s.scan_tab[i]);
     }
     cudaFree(s.tile_out);
@@ -126,9 +128,10 @@ extern "C" void sk_ctx_destroy(sk_ctx *ctx) {
     cudaFree(ctx->d_umask);
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_sheet_raw);
-    cudaFree(ctx->d_fcls);
+    cudaFree(ctx->d_hcls);
     cudaFree(ctx->d_skeys);
-    cudaFree(ctx->d_ftab);
+    cudaFree(ctx->d_htab);
+    cudaFree(ctx->d_hcand);
     delete ctx;
 }
 
@@ -151,7 +154,7 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
     sk_ctx *ctx = new sk_ctx();
     ctx->device = device;
     ctx->lim = *lim;
-    ctx->cfg = lim->reserved == 1 ? 1 : lim->reserved == 2 ? 0 : 1;  // reserved: 0 default, 1 small, 2 big chunks
+    ctx->cfg = lim->reserved == 2 ? 1 : 0;  // reserved: 0/1 = 16 KiB chunks (default), 2 = 32 KiB chunks
     if (const char *e = getenv("SK_CFG")) ctx->cfg = atoi(e) ? 1 : 0;
     auto fail = [&](int code) {
         g_create_error = ctx->err;
@@ -200,8 +203,8 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
         if (Smax) {
             CKC(cudaMalloc(&s.assign, R * 2));
             for (int i = 0; i < 2; i++) {
-                CKC(cudaMalloc(&s.lens[i], (uint64_t)ctx->max_chunks * Smax * 2));
-                CKC(cudaMalloc(&s.chunk_base[i], (uint64_t)ctx->max_chunks * 8));
+                CKC(cudaMalloc(&s.groups[i], R * sizeof(Group)));
+                CKC(cudaMalloc(&s.rows[i], (uint64_t)ctx->max_chunks * sizeof(ChunkRow)));
             }
             CKC(cudaMalloc(&s.counts, (uint64_t)(Smax + 2) * 8));
             CKC(cudaMalloc(&s.events, R * sizeof(Event)));
@@ -336,8 +339,9 @@ extern "C" int sk_set_sheet(sk_ctx *ctx, const uint8_t *barcodes, uint32_t S, ui
         Umax = std::max<uint32_t>(Umax, (uint32_t)__builtin_popcountll(um));
     }
 
-    // ---- exact-match index: classes of identical care mask, one open-addressing table per class
-    const uint32_t nw = (L + 3) / 4;
+    // ---- pigeonhole index (HalfIdx, sk_internal.h): classes of identical care mask; per class the cared
+    // positions are split into two halves and every sample is filed under the bytes of each half.
+    const uint32_t nw = (L + 3) / 4, nwp = std::max(4u, (nw + 3u) & ~3u);
     std::vector<std::vector<uint8_t>> cls_care;
     std::vector<uint32_t> cls_of(S, 0);
     for (uint32_t s = 0; s < S; s++) {
@@ -352,21 +356,35 @@ extern "C" int sk_set_sheet(sk_ctx *ctx, const uint8_t *barcodes, uint32_t S, ui
         if (c == cls_care.size()) cls_care.push_back(care);
         cls_of[s] = c;
     }
-    uint32_t f_classes = (S && L && cls_care.size() <= 2) ? (uint32_t)cls_care.size() : 0;
+    uint32_t h_classes = (S && L && cls_care.size() <= 4) ? (uint32_t)cls_care.size() : 0;
+    std::vector<std::vector<uint32_t>> halfpos[2];  // [half][class] -> positions
+    for (uint32_t c = 0; c < h_classes; c++) {
+        std::vector<uint32_t> pos;
+        for (uint32_t q = 0; q < L; q++)
+            if (cls_care[c][q]) pos.push_back(q);
+        if (pos.size() < 2) {  // one mismatch could hide anywhere: no half is guaranteed to match
+            h_classes = 0;
+            break;
+        }
+        const size_t na = (pos.size() + 1) / 2;
+        halfpos[0].push_back(std::vector<uint32_t>(pos.begin(), pos.begin() + na));
+        halfpos[1].push_back(std::vector<uint32_t>(pos.begin() + na, pos.end()));
+    }
     uint32_t tsize = 16;
-    while (3 * tsize < 4 * S) tsize <<= 1;  // load factor <= 0.75
-    if (f_classes && chunk_kernel_smem_bytes(ctx->cfg, S, wide, f_classes, tsize) > 227 * 1024) f_classes = 0;
-    if (chunk_kernel_smem_bytes(ctx->cfg, S, wide, f_classes, tsize) > 227 * 1024) {
+    while (2 * tsize < 3 * S) tsize <<= 1;  // load factor <= 2/3
+    if (chunk_kernel_smem_bytes(ctx->cfg, S, wide, h_classes, nwp) > 227 * 1024) {
         ctx->err = "sample sheet does not fit in shared memory";
         return SK_E_UNSUPPORTED;
     }
-    std::vector<uint32_t> skeys((size_t)S * std::max(nw, 1u), 0u), fcls((size_t)std::max(f_classes, 1u) * FAST_CLS_WORDS, 0u);
-    std::vector<unsigned long long> ftab((size_t)std::max(f_classes, 1u) * tsize, 0xFFFFull << 32);
+    std::vector<uint32_t> skeys((size_t)std::max(S, 1u) * nwp, 0u);
     for (uint32_t s = 0; s < S; s++)
         for (uint32_t q = 0; q < L; q++) {
             const uint8_t b = barcodes[(uint64_t)s * L + q] & cls_care[cls_of[s]][q];
-            skeys[(size_t)s * nw + q / 4] |= (uint32_t)b << (8 * (q % 4));
+            skeys[(size_t)s * nwp + q / 4] |= (uint32_t)b << (8 * (q % 4));
         }
+    std::vector<uint32_t> hcls((size_t)std::max(h_classes, 1u) * HIDX_CLS_ROWS * nwp, 0u);
+    std::vector<uint2> htab((size_t)std::max(h_classes, 1u) * 2 * tsize, make_uint2(0u, 0u));
+    std::vector<uint16_t> hcand;
     uint64_t rng = 0x9E3779B97F4A7C15ull ^ ((uint64_t)S << 32) ^ L;
     auto next = [&]() {
         rng ^= rng << 13;
@@ -374,74 +392,91 @@ extern "C" int sk_set_sheet(sk_ctx *ctx, const uint8_t *barcodes, uint32_t S, ui
         rng ^= rng << 17;
         return (uint32_t)(rng >> 16);
     };
-    for (uint32_t c = 0; c < f_classes; c++) {
-        uint32_t *cw = &fcls[(size_t)c * FAST_CLS_WORDS];
-        for (uint32_t q = 0; q < L; q++) cw[q / 4] |= (uint32_t)cls_care[c][q] << (8 * (q % 4));
-        for (uint32_t w = 0; w < (uint32_t)FAST_NWMAX; w++) {
-            cw[FAST_NWMAX + w] = next() | 1u;
-            cw[2 * FAST_NWMAX + w] = next() | 1u;
-        }
-        unsigned long long *tab = &ftab[(size_t)c * tsize];
-        for (uint32_t s = 0; s < S; s++) {
-            if (cls_of[s] != c) continue;
-            const uint32_t *key = &skeys[(size_t)s * nw];
-            uint32_t h1 = 0, h2 = 0;
-            for (uint32_t w = 0; w < nw; w++) {
-                h1 += key[w] * cw[FAST_NWMAX + w];
-                h2 += key[w] * cw[2 * FAST_NWMAX + w];
+    for (uint32_t c = 0; c < h_classes; c++) {
+        uint32_t *row = &hcls[(size_t)c * HIDX_CLS_ROWS * nwp];
+        for (uint32_t q = 0; q < L; q++) row[q / 4] |= (uint32_t)cls_care[c][q] << (8 * (q % 4));
+        for (uint32_t h = 0; h < 2; h++) {
+            uint32_t *hm = row + (1 + 3 * h) * nwp;
+            for (uint32_t q : halfpos[h][c]) hm[q / 4] |= 0xFFu << (8 * (q % 4));
+            for (uint32_t w = 0; w < nwp; w++) {
+                hm[nwp + w] = next() | 1u;
+                hm[2 * nwp + w] = next() | 1u;
             }
-            h1 ^= h1 >> 15;
-            uint32_t slot = h1 & (tsize - 1);
-            for (;;) {
-                const unsigned long long e = tab[slot];
-                const uint32_t f = (uint32_t)(e >> 32) & 0xFFFFu;
-                if (f == 0xFFFFu) {
-                    tab[slot] = (unsigned long long)h2 | ((unsigned long long)s << 32) | ((unsigned long long)s << 48);
-                    break;
+            // group the samples of the class by their bytes on this half
+            std::vector<uint32_t> members;
+            for (uint32_t s = 0; s < S; s++)
+                if (cls_of[s] == c) members.push_back(s);
+            auto halfkey = [&](uint32_t s, uint32_t w) { return skeys[(size_t)s * nwp + w] & hm[w]; };
+            std::vector<char> done(members.size(), 0);
+            uint2 *tab = &htab[(size_t)(c * 2 + h) * tsize];
+            for (size_t i = 0; i < members.size(); i++) {
+                if (done[i]) continue;
+                const uint32_t s0 = members[i];
+                const uint32_t start = (uint32_t)hcand.size();
+                for (size_t k = i; k < members.size(); k++) {
+                    if (done[k]) continue;
+                    bool same = true;
+                    for (uint32_t w = 0; w < nw && same; w++) same = halfkey(members[k], w) == halfkey(s0, w);
+                    if (same) {
+                        done[k] = 1;
+                        hcand.push_back((uint16_t)members[k]);
+                    }
                 }
-                if (memcmp(&skeys[(size_t)f * nw], key, (size_t)nw * 4) == 0) {  // duplicate barcode: widen [first,last]
-                    tab[slot] = (e & 0x0000FFFFFFFFFFFFull) | ((unsigned long long)s << 48);
-                    break;
+                const uint32_t count = (uint32_t)hcand.size() - start;
+                uint32_t h1 = 0, h2 = 0;
+                for (uint32_t w = 0; w < nw; w++) {
+                    h1 += halfkey(s0, w) * hm[nwp + w];
+                    h2 += halfkey(s0, w) * hm[2 * nwp + w];
                 }
-                slot = (slot + 1) & (tsize - 1);
+                h1 ^= h1 >> 15;
+                uint32_t slot = h1 & (tsize - 1);
+                while (tab[slot].y >> 16) slot = (slot + 1) & (tsize - 1);
+                tab[slot] = make_uint2(h2, start | (count << 16));
             }
         }
     }
+    if (hcand.size() > 0xFFFFu) h_classes = 0;  // list offsets are 16-bit
+    if (hcand.empty()) hcand.push_back(0);
 
     cudaFree(ctx->d_planes);
     cudaFree(ctx->d_umask);
     cudaFree(ctx->d_lut);
     cudaFree(ctx->d_sheet_raw);
-    cudaFree(ctx->d_fcls);
+    cudaFree(ctx->d_hcls);
     cudaFree(ctx->d_skeys);
-    cudaFree(ctx->d_ftab);
-    ctx->d_planes = ctx->d_umask = ctx->d_fcls = ctx->d_skeys = nullptr;
+    cudaFree(ctx->d_htab);
+    cudaFree(ctx->d_hcand);
+    ctx->d_planes = ctx->d_umask = ctx->d_hcls = ctx->d_skeys = nullptr;
     ctx->d_lut = ctx->d_sheet_raw = nullptr;
-    ctx->d_ftab = nullptr;
+    ctx->d_htab = nullptr;
+    ctx->d_hcand = nullptr;
     CK(cudaMalloc(&ctx->d_planes, std::max<size_t>(planes.size() * 4, 16)));
     CK(cudaMalloc(&ctx->d_umask, std::max<size_t>(umask.size() * 4, 16)));
     CK(cudaMalloc(&ctx->d_lut, 256));
     CK(cudaMalloc(&ctx->d_sheet_raw, std::max<size_t>((size_t)S * L, 16)));
-    CK(cudaMalloc(&ctx->d_fcls, fcls.size() * 4));
+    CK(cudaMalloc(&ctx->d_hcls, hcls.size() * 4));
     CK(cudaMalloc(&ctx->d_skeys, std::max<size_t>(skeys.size() * 4, 16)));
-    CK(cudaMalloc(&ctx->d_ftab, ftab.size() * 8));
+    CK(cudaMalloc(&ctx->d_htab, htab.size() * 8));
+    CK(cudaMalloc(&ctx->d_hcand, hcand.size() * 2));
     if (S) {
         CK(cudaMemcpy(ctx->d_planes, planes.data(), planes.size() * 4, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(ctx->d_umask, umask.data(), umask.size() * 4, cudaMemcpyHostToDevice));
         if (L) CK(cudaMemcpy(ctx->d_sheet_raw, barcodes, (size_t)S * L, cudaMemcpyHostToDevice));
-        if (L) CK(cudaMemcpy(ctx->d_skeys, skeys.data(), skeys.size() * 4, cudaMemcpyHostToDevice));
+        CK(cudaMemcpy(ctx->d_skeys, skeys.data(), skeys.size() * 4, cudaMemcpyHostToDevice));
     }
     CK(cudaMemcpy(ctx->d_lut, lut, 256, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_fcls, fcls.data(), fcls.size() * 4, cudaMemcpyHostToDevice));
-    CK(cudaMemcpy(ctx->d_ftab, ftab.data(), ftab.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_hcls, hcls.data(), hcls.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_htab, htab.data(), htab.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_hcand, hcand.data(), hcand.size() * 2, cudaMemcpyHostToDevice));
     ctx->sheet_raw.assign(barcodes, barcodes + (size_t)S * L);
     ctx->S = S;
     ctx->L = L;
     ctx->Umax = Umax;
     ctx->wide = wide;
-    ctx->f_classes = f_classes;
-    ctx->f_nw = nw;
-    ctx->f_tsize = tsize;
+    ctx->h_classes = h_classes;
+    ctx->h_nw = nw;
+    ctx->h_nwp = nwp;
+    ctx->h_tsize = tsize;
     ctx->have_sheet = true;
     // the UMI side table depends on the sheet
     for (auto &s : ctx->slots) {
@@ -632,16 +667,18 @@ extern "C" int sk_demultiplex(sk_ctx *ctx, uint32_t slot, const sk_demux_opts *o
         p.sheet.L = ctx->L;
         p.sheet.Umax = ctx->Umax;
         p.sheet.wide = ctx->wide;
-        p.sheet.fast.n_classes = ctx->f_classes;
-        p.sheet.fast.nw = ctx->f_nw;
-        p.sheet.fast.tsize = ctx->f_tsize;
-        p.sheet.fast.cls = ctx->d_fcls;
-        p.sheet.fast.table = ctx->d_ftab;
-        p.sheet.fast.skeys = ctx->d_skeys;
+        p.sheet.hidx.n_classes = getenv("SK_NO_HIDX") ? 0u : ctx->h_classes;
+        p.sheet.hidx.nw = ctx->h_nw;
+        p.sheet.hidx.nwp = ctx->h_nwp;
+        p.sheet.hidx.tsize = ctx->h_tsize;
+        p.sheet.hidx.cls = ctx->d_hcls;
+        p.sheet.hidx.table = ctx->d_htab;
+        p.sheet.hidx.cand = ctx->d_hcand;
+        p.sheet.hidx.skeys = ctx->d_skeys;
         p.assign = s->assign;
         p.umi = s->umi;
-        p.lens = s->lens[mate];
-        p.chunk_base = s->chunk_base[mate];
+        p.groups = s->groups[mate];
+        p.rows = s->rows[mate];
         p.counts = s->counts;
         p.events = s->events;
         p.events_cap = (uint32_t)std::min<uint64_t>(ctx->lim.max_records, 0xFFFFFFFFull);
@@ -732,16 +769,14 @@ extern "C" int sk_download_out(sk_ctx *ctx, uint32_t slot, uint32_t which, void 
     if (n) CK(cudaMemcpyAsync(host, s->out[which], n, cudaMemcpyDeviceToHost, s->stream));
     return SK_OK;
 }
-extern "C" int sk_download_demux_tables(sk_ctx *ctx, uint32_t slot, uint32_t which, uint64_t *chunk_base,
-                                        uint16_t *lens) {
+extern "C" int sk_download_demux_tables(sk_ctx *ctx, uint32_t slot, uint32_t which, sk_chunk_row *rows, sk_group *groups,
+                                        uint64_t n_records) {
     Slot *s = get_slot(ctx, slot);
-    if (!s || which >= 2 || !s->lens[which]) return SK_E_INVALID;
+    if (!s || which >= 2 || !s->groups[which] || n_records > ctx->lim.max_records) return SK_E_INVALID;
     const uint32_t nc = s->n_chunks[which == 0 ? SK_IN_R1 : SK_IN_R2];
-    if (nc) {
-        CK(cudaMemcpyAsync(chunk_base, s->chunk_base[which], (uint64_t)nc * 8, cudaMemcpyDeviceToHost, s->stream));
-        if (ctx->S)
-            CK(cudaMemcpyAsync(lens, s->lens[which], (uint64_t)nc * ctx->S * 2, cudaMemcpyDeviceToHost, s->stream));
-    }
+    if (nc) CK(cudaMemcpyAsync(rows, s->rows[which], (uint64_t)nc * sizeof(ChunkRow), cudaMemcpyDeviceToHost, s->stream));
+    if (n_records)
+        CK(cudaMemcpyAsync(groups, s->groups[which], n_records * sizeof(Group), cudaMemcpyDeviceToHost, s->stream));
     return SK_OK;
 }
 extern "C" int sk_download_counts(sk_ctx *ctx, uint32_t slot, uint64_t *counts) {
@@ -773,17 +808,19 @@ extern "C" int sk_download_assign(sk_ctx *ctx, uint32_t slot, int16_t *assign, u
     return SK_OK;
 }
 
-extern "C" uint64_t sk_demux_gather(const uint8_t *out_host, const uint64_t *chunk_base, const uint16_t *lens,
-                                    uint32_t n_chunks, uint32_t S, uint32_t smp, uint8_t *dst, uint64_t dst_cap) {
+extern "C" uint64_t sk_demux_gather(const uint8_t *out_host, const sk_chunk_row *rows, const sk_group *groups,
+                                    uint32_t n_chunks, uint32_t smp, uint8_t *dst, uint64_t dst_cap) {
     uint64_t total = 0;
     for (uint32_t c = 0; c < n_chunks; c++) {
-        const uint16_t *row = lens + (uint64_t)c * S;
-        const uint32_t len = row[smp];
-        if (!len) continue;
-        uint64_t off = chunk_base[c];
-        for (uint32_t t = 0; t < smp; t++) off += row[t];
-        if (dst && total + len <= dst_cap) memcpy(dst + total, out_host + off, len);
-        total += len;
+        uint64_t off = rows[c].base;
+        const sk_group *g = groups + rows[c].first_group;
+        for (uint32_t k = 0; k < rows[c].n_groups; k++) {
+            if (g[k].sample == smp) {
+                if (dst && total + g[k].len <= dst_cap) memcpy(dst + total, out_host + off, g[k].len);
+                total += g[k].len;
+            }
+            off += g[k].len;
+        }
     }
     return total;
 }

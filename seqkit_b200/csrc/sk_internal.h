@@ -16,34 +16,37 @@ enum Op : int {
 
 // Geometry of one chunk-engine configuration.  WIN_MAX = NT*PPL*16 bytes of window per CTA:
 // PRE bytes before the chunk (byte c0-1 decides whether a line starts at c0), the chunk itself and
-// the overhang a record may extend into.
-struct CfgBig {  // 2 CTAs/SM
+// the overhang a record may extend into.  PPL is odd so that the per-thread LDS.128 of the newline
+// scan are bank-conflict free (thread stride PPL*16 bytes).
+struct CfgA {  // 16 KiB chunks, 4 warps: every warp has work in every phase of a 150 bp workload
     static constexpr int ID = 0;
-    static constexpr int NT = 512;
-    static constexpr int PPL = 5;                       // 16-byte pieces scanned per thread (odd => LDS.128 conflict-free)
-    static constexpr int WIN_MAX = NT * PPL * 16;       // 40960
-    static constexpr int CHUNK = 32768;
-    static constexpr int PRE = 16;
-    static constexpr int OVERHANG = WIN_MAX - CHUNK - PRE;  // 8176
-    static constexpr int MAXLINES = 1792;
-    static constexpr int MAXREC = 512;
-    static constexpr int STAGE = 37888;                 // chunk outputs beyond this take the unstaged path
-    static constexpr int MIN_CTAS = 2;
-};
-struct CfgSmall {  // 3-4 CTAs/SM: more chunks in different phases per SM hide the serial plan phase
-    static constexpr int ID = 1;
-    static constexpr int NT = 256;
-    static constexpr int PPL = 5;
-    static constexpr int WIN_MAX = NT * PPL * 16;       // 20480
+    static constexpr int NT = 128;
+    static constexpr int PPL = 11;
+    static constexpr int WIN_MAX = NT * PPL * 16;       // 22528
     static constexpr int CHUNK = 16384;
     static constexpr int PRE = 16;
-    static constexpr int OVERHANG = WIN_MAX - CHUNK - PRE;  // 4080
-    static constexpr int MAXLINES = 1024;
+    static constexpr int OVERHANG = WIN_MAX - CHUNK - PRE;  // 6128
     static constexpr int MAXREC = 256;
-    static constexpr int STAGE = WIN_MAX;
+    static constexpr int MAXLINES = 4 * MAXREC + 16;
+    static constexpr int STAGE = 18432;                 // chunk outputs beyond this take the unstaged path
     static constexpr int MIN_CTAS = 3;
 };
-inline int cfg_chunk_bytes(int cfg) { return cfg == CfgSmall::ID ? CfgSmall::CHUNK : CfgBig::CHUNK; }
+struct CfgB {  // 32 KiB chunks, 8 warps
+    static constexpr int ID = 1;
+    static constexpr int NT = 256;
+    static constexpr int PPL = 9;
+    static constexpr int WIN_MAX = NT * PPL * 16;       // 36864
+    static constexpr int CHUNK = 32768;
+    static constexpr int PRE = 16;
+    static constexpr int OVERHANG = WIN_MAX - CHUNK - PRE;  // 4080
+    static constexpr int MAXREC = 512;
+    static constexpr int MAXLINES = 4 * MAXREC + 16;
+    static constexpr int STAGE = 35840;
+    static constexpr int MIN_CTAS = 2;
+};
+inline int cfg_chunk_bytes(int cfg) { return cfg == CfgB::ID ? CfgB::CHUNK : CfgA::CHUNK; }
+
+constexpr int LAYOUT_FAST_MAXREC = 128;  // the bit-mask layout handles chunks of up to this many records
 
 // Entry of an OP_SCAN table: where the sequence line of record i is.
 struct RecRef {
@@ -80,36 +83,49 @@ struct DevStats {
     unsigned long long phase_cycles[16];  // -DSK_PHASE_TIMING: per-phase SM cycles summed over chunks (thread 0)
 };
 
-// Exact-match index over the sample sheet (built on the host, sk_api.cu).  Samples are grouped in
-// classes of identical care mask; per class a hash table maps the cared bytes of a barcode to the
-// (first, last) sample holding exactly those bytes.  A read whose barcode is found here is at
-// distance 0 from those samples and from no others, which settles fasta_demultiplex.rs:157-173
-// without visiting the other samples; every other read takes the brute-force bit-plane path.
-constexpr int FAST_NWMAX = 16;                  // key words per barcode (L <= 64)
-constexpr int FAST_CLS_WORDS = 3 * FAST_NWMAX;  // care[16] | mulA[16] | mulB[16]
-struct FastIdx {
+// Pigeonhole index over the sample sheet (built on the host, sk_api.cu).  Samples are grouped in
+// classes of identical care mask.  The cared positions of a class are split into two halves; a read
+// within one mismatch of a sample equals that sample exactly on at least one half, so two hash
+// lookups per class yield every sample at distance <= 1 (plus harmless extras).  Each candidate's
+// true distance is then computed on the cared bytes, which makes the result identical to the loop
+// over all samples in fasta_demultiplex.rs:157-166 whenever the minimum is <= 1 -- and when it is
+// larger the read is unassigned either way (:172).
+constexpr int HIDX_NWMAX = 16;  // key words per barcode (L <= 64)
+struct HalfIdx {
     uint32_t n_classes;  // 0 = index unusable, every read takes the brute-force path
     uint32_t nw;         // words per key = ceil(L/4)
-    uint32_t tsize;      // slots per class table (power of two)
-    uint32_t pad;
-    const uint32_t *cls;                 // n_classes * FAST_CLS_WORDS
-    const unsigned long long *table;     // n_classes * tsize: tag(32) | first(16) | last(16); first == 0xFFFF: empty
-    const uint32_t *skeys;               // S * nw: cared bytes of every sample
+    uint32_t nwp;        // row stride of skeys / class rows, nw rounded up to 4
+    uint32_t tsize;      // slots per table (power of two)
+    const uint32_t *cls;     // per class 7 rows of nwp words: care | half0 {mask, mulA, mulB} | half1 {mask, mulA, mulB}
+    const uint2 *table;      // [n_classes][2][tsize]: {tag, start | count << 16}; count == 0: empty slot
+    const uint16_t *cand;    // candidate lists (sample indices, ascending)
+    const uint32_t *skeys;   // [S][nwp]: cared bytes of every sample, 0 elsewhere
 };
+constexpr int HIDX_CLS_ROWS = 7;
 
 // Sample sheet in device memory (packed by the host, sk_api.cu).
 struct SheetDev {
-    const uint32_t *planes;  // S entries of {p0,p1,p2,care} (u32 x4) or, when wide, {p0,p1,p2,care} (u64 x4)
+    const uint32_t *planes;  // brute-force fallback: S entries of {p0,p1,p2,care} (u32 x4, or u64 x4 when wide)
     const uint32_t *umask;   // S entries (u32) or 2*S (u64 as lo,hi): positions where the sheet has 'U'
     const uint8_t *lut;      // 256: bits 0-2 = 3-bit code (0 = matches no literal), bit 3 = [ACGTNacgtn+]
     uint32_t S, L, Umax, wide;
-    FastIdx fast;
+    HalfIdx hidx;
 };
 
-// Shared-memory carve-up (bytes), computed on the host and passed in KParams (the device code only
-// reads it: recomputing it in the kernel costs ~5 % of all instructions).
+// Shared-memory carve-up (bytes), computed on the host and passed in KParams.
 struct SmemLayout {
-    uint32_t win, stage, ls, rec, sheet, umask, lut, hist, sbase, ccount, fcls, ftab, slow, misc, total;
+    uint32_t win, stage, ls, rec, umask, lut, ccount, masks, gtot, hcls, slow, misc, total;
+};
+
+// One run of same-sample records inside a chunk's output (demux slice table, sparse form).
+struct Group {
+    uint16_t sample;
+    uint16_t len;  // bytes; a chunk's output is < 64 KiB
+};
+struct ChunkRow {
+    unsigned long long base;  // byte offset of the chunk's output in its output stream
+    uint32_t first_group;     // index of the chunk's first Group (== global index of its first record)
+    uint32_t n_groups;
 };
 
 struct KParams {
@@ -135,8 +151,8 @@ struct KParams {
     SheetDev sheet;
     int16_t *assign;        // [max_records]
     uint8_t *umi;           // [max_records * Umax]
-    uint16_t *lens;         // [n_chunks * S]
-    uint64_t *chunk_base;   // [n_chunks]
+    Group *groups;          // [max_records]
+    ChunkRow *rows;         // [n_chunks]
     unsigned long long *counts;  // [S + 2]
     Event *events;
     uint32_t events_cap;
@@ -160,22 +176,20 @@ enum : unsigned { F_MATE_COUNT = 1u, F_EVENTS_OVERFLOW = 2u, F_NON_ASCII = 0x100
 
 constexpr int REC_BYTES = 26;  // per-record plan fields, see sk_kernels.cu
 template <class Cfg>
-inline __host__ __device__ SmemLayout smem_layout(uint32_t S, uint32_t wide, uint32_t n_classes, uint32_t tsize) {
+inline __host__ __device__ SmemLayout smem_layout(uint32_t S, uint32_t wide, uint32_t n_classes, uint32_t nwp) {
     SmemLayout L;
     uint32_t o = 0;
     auto take = [&](uint32_t bytes) { uint32_t r = o; o += (bytes + 15u) & ~15u; return r; };
     L.win = take(Cfg::WIN_MAX);
-    L.stage = take(Cfg::STAGE + 16);
-    L.ls = take(Cfg::MAXLINES * 2);
+    L.stage = take(Cfg::STAGE + 32);
+    L.ls = take((Cfg::MAXLINES + 8) * 2);
     L.rec = take(Cfg::MAXREC * REC_BYTES);
-    L.sheet = take(S * (wide ? 32u : 16u));
     L.umask = take(S * (wide ? 8u : 4u));
     L.lut = take(S ? 256 : 0);
-    L.hist = take(S * 4);
-    L.sbase = take(S * 4);
     L.ccount = take(S * 4);
-    L.fcls = take(n_classes * FAST_CLS_WORDS * 4);
-    L.ftab = take(n_classes * tsize * 8);
+    L.masks = take(S * 16);
+    L.gtot = take(S ? LAYOUT_FAST_MAXREC * 4 : 0);
+    L.hcls = take(n_classes * HIDX_CLS_ROWS * nwp * 4);
     L.slow = take(S ? Cfg::MAXREC * 2 : 0);
     L.misc = take(512);
     L.total = o;
@@ -184,6 +198,6 @@ inline __host__ __device__ SmemLayout smem_layout(uint32_t S, uint32_t wide, uin
 
 // Launchers (sk_kernels.cu)
 int launch_chunk_kernel(int cfg, int op, const KParams &p, int sm_count, void *stream, const char **err);
-int chunk_kernel_smem_bytes(int cfg, uint32_t S, uint32_t wide, uint32_t n_classes, uint32_t tsize);
+int chunk_kernel_smem_bytes(int cfg, uint32_t S, uint32_t wide, uint32_t n_classes, uint32_t nwp);
 
 }  // namespace sk

@@ -3,14 +3,15 @@
 // One persistent kernel template implements every operator of the path:
 //   OP_SCAN / OP_TRIM / OP_MASK / OP_ADDBC / OP_DEMUX1 / OP_DEMUX2.
 // Input bytes are read from HBM once (TMA bulk copy into shared memory), output bytes are written
-// once (16-byte vector stores from a shared staging image).  Record framing is by global line
-// index (decoupled look-back over per-chunk line counts), exactly like the reference's four
-// read_line calls per record (common.rs:106-112).
+// once (TMA bulk store of a shared staging image).  Record framing is by global line index
+// (decoupled look-back over per-chunk line counts), exactly like the reference's four read_line
+// calls per record (common.rs:106-112).
 //
-// The kernel is bound by issued instructions, not by DRAM (profiles/r1_v1_ncu_summary.txt), so every
-// phase is written for instruction count: SWAR scans on aligned words, one thread per record for the
-// sequential reference logic, 4 lanes per record copying whole words with funnel shifts, an
-// exact-match hash index in front of the brute-force barcode matcher.
+// The kernel is bound by issued instructions and barrier stalls, not by DRAM (profiles/), so the
+// per-record logic runs one thread per record (no redundant lanes), independent sub-tasks of a
+// record (quality trim | header search + barcode match) run on different warps at the same time,
+// the barcode match is two hash probes plus a distance check of the few candidates, and the
+// per-sample grouping of a chunk's output is a bit-mask exchange instead of a serial walk.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -51,6 +52,13 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// TMA 1-D bulk copy shared -> global, tracked by the issuing thread's bulk async-group.
+__device__ __forceinline__ void bulk_s2g(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 // look-back words: 2-bit status | 62-bit value, one 8-byte relaxed gpu-scope access
@@ -87,9 +95,11 @@ __device__ uint64_t lookback(uint64_t *tiles, uint32_t c, uint64_t agg, int lane
         int64_t idx = base - lane;
         uint64_t w = TS_INC << 62;  // chunks before 0: inclusive prefix 0
         if (idx >= 0) {
-            do {
+            w = ts_load(&tiles[idx]);
+            while ((w >> 62) == TS_INVALID) {
+                __nanosleep(40);
                 w = ts_load(&tiles[idx]);
-            } while ((w >> 62) == TS_INVALID);
+            }
         }
         uint32_t inc = __ballot_sync(0xffffffffu, (w >> 62) == TS_INC);
         uint64_t v = w & TS_VMASK;
@@ -105,9 +115,10 @@ __device__ uint64_t lookback(uint64_t *tiles, uint32_t c, uint64_t agg, int lane
     return excl;
 }
 
-// Exclusive block scan of one u32 per thread; `scratch` holds NT/32+1 words.
+// Exclusive block scan of one u32 per thread; `scratch` holds 2*(NT/32) words (double buffered by
+// `flip`, so that one barrier per call suffices).
 template <int NT>
-__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *scratch, uint32_t &total) {
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *scratch, uint32_t &flip, uint32_t &total) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     constexpr int NW = NT / 32;
     uint32_t x = v;
@@ -116,29 +127,29 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *scratc
         uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
         if (lane >= o) x += y;
     }
-    if (lane == 31) scratch[w] = x;
+    uint32_t *s = scratch + flip * NW;
+    flip ^= 1u;
+    if (lane == 31) s[w] = x;
     __syncthreads();
-    if (w == 0) {
-        uint32_t t = lane < NW ? scratch[lane] : 0, s = t;
+    uint32_t before = 0, all = 0;
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
-            if (lane >= o) s += y;
-        }
-        if (lane < NW) scratch[lane] = s - t;
-        if (lane == NW - 1) scratch[NW] = s;
+    for (int k = 0; k < NW; k++) {
+        const uint32_t t = s[k];
+        if (k < w) before += t;
+        all += t;
     }
-    __syncthreads();
-    total = scratch[NW];
-    uint32_t r = scratch[w] + x - v;
-    __syncthreads();
-    return r;
+    total = all;
+    return before + x - v;
 }
 
 // 0x80 in every byte of x that equals the byte replicated in `pat` (exact SWAR test, no carries).
 __device__ __forceinline__ uint32_t eq_flags(uint32_t x, uint32_t pat) {
     const uint32_t t = x ^ pat;
     return ~(((t & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | t) & 0x80808080u;
+}
+// number of non-zero bytes of x
+__device__ __forceinline__ uint32_t nz_bytes(uint32_t x) {
+    return __popc((((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) & 0x80808080u);
 }
 // Newline map of a 16-byte piece: bit (8*b + w) is set when byte b of word w is '\n'
 // (window offset of that byte inside the piece = 4*w + b).
@@ -163,50 +174,73 @@ __device__ __forceinline__ void report_err(DevStats *st, uint64_t rec, unsigned 
 }
 
 // body modes of a planned record
-enum : uint8_t { B_VERBATIM = 0, B_TRIM = 1, B_GARBAGE = 2, B_MASK = 3, B_NONE = 4 };
+enum : uint8_t { B_VERBATIM = 0, B_TRIM = 1, B_GARBAGE = 2, B_MASK = 3, B_NONE = 4, B_FAIL = 5 };
 enum : uint8_t { RF_SLOW = 1, RF_DEAD = 2 };
 
-struct Win {
-    const uint8_t *b;
-    const uint16_t *ls;
-    uint32_t nls;   // line starts found in the window (may exceed MAXLINES; indices needed are checked)
-    uint32_t wlen;  // valid bytes in the window
-};
-__device__ __forceinline__ uint32_t lb(const Win &W, uint32_t x) { return x < W.nls ? (uint32_t)W.ls[x] : W.wlen; }
-
-// fasta_trim_by_quality.rs:28-48 on the quality line [L3,L4) / sequence line [L1,L2).
-// Quality bytes are fetched one aligned word at a time.  Returns false when &seq[..k] would panic.
+// fasta_trim_by_quality.rs:28-48 on the quality line [L3,L4) / sequence line [L1,L2), one thread.
+// Whole aligned words are examined with four dot products (the running totals after each of the
+// word's bytes); bytes below '!' (wrapping u8 subtraction, :35) and the word in which the loop
+// breaks (:37) fall back to the byte-wise form.  Returns false when &seq[..k] would panic (:47).
 __device__ __forceinline__ bool plan_trim_body(const uint8_t *b, uint32_t L1, uint32_t L2, uint32_t L3, uint32_t L4,
                                                int minq, uint8_t &mode, uint32_t &kk, uint32_t &body_len) {
     uint32_t k = L4 - L3;
     while (k > 0 && is_ws(b[L3 + k - 1])) k--;  // qual.trim_end().len()  (:31)
     int total = -50, lowest = -50;              // :28-29
     uint32_t lowest_k = k;
-    // Bytes are examined from the end, one aligned word per iteration; `pos` is one past the byte
-    // examined next.  STEP(j) handles byte j of the word when it lies inside [L3, pos).
-    uint32_t pos = L3 + k;
+    uint32_t pos = L3 + k;  // one past the byte examined next
     const int sub = 33 + minq;
-    bool stop = false;
-#define SK_TRIM_STEP(j)                                                            \
-    if (!stop && a + (j) < pos && a + (j) >= L3) {                                 \
-        const uint32_t q = (w >> (8 * (j))) & 0xFFu;                               \
-        total += q >= 33u ? (int)q - sub : (int)((q - 33u) & 0xFFu) - minq; /* wrapping u8 subtraction (:35) */ \
-        if (total > 0) stop = true;                                                \
-        else if (total < lowest) {                                                 \
-            lowest = total;                                                        \
-            lowest_k = a + (j) - L3;                                               \
-        }                                                                          \
+#define SK_TRIM_BYTE(addr)                                                                               \
+    {                                                                                                    \
+        const uint32_t q = b[addr];                                                                      \
+        total += q >= 33u ? (int)q - sub : (int)((q - 33u) & 0xFFu) - minq; /* wrapping u8 subtraction */ \
+        if (total > 0) goto trim_done;                                                                   \
+        if (total < lowest) {                                                                            \
+            lowest = total;                                                                              \
+            lowest_k = (addr) - L3;                                                                      \
+        }                                                                                                \
     }
-    while (pos > L3 && !stop) {  // :33-42
-        const uint32_t a = (pos - 1) & ~3u;
-        const uint32_t w = *(const uint32_t *)(b + a);
-        SK_TRIM_STEP(3)
-        SK_TRIM_STEP(2)
-        SK_TRIM_STEP(1)
-        SK_TRIM_STEP(0)
-        pos = a;
+    while (pos > L3 && (pos & 3u)) {  // down to a word boundary
+        pos--;
+        SK_TRIM_BYTE(pos)
     }
-#undef SK_TRIM_STEP
+    while (pos >= L3 + 4) {  // :33-42, four bytes per step
+        const uint32_t w = *(const uint32_t *)(b + pos - 4);
+        if ((((w | 0x80808080u) - 0x21212121u) & 0x80808080u) != 0x80808080u || (w & 0x80808080u)) {
+            // a byte below '!' (or non-ASCII): byte-wise
+            SK_TRIM_BYTE(pos - 1)
+            SK_TRIM_BYTE(pos - 2)
+            SK_TRIM_BYTE(pos - 3)
+            SK_TRIM_BYTE(pos - 4)
+            pos -= 4;
+            continue;
+        }
+        const int T3 = (int)__dp4a(w, 0x01000000u, (uint32_t)(total - sub));
+        const int T2 = (int)__dp4a(w, 0x01010000u, (uint32_t)(total - 2 * sub));
+        const int T1 = (int)__dp4a(w, 0x01010100u, (uint32_t)(total - 3 * sub));
+        const int T0 = (int)__dp4a(w, 0x01010101u, (uint32_t)(total - 4 * sub));
+        if (max(max(T3, T2), max(T1, T0)) > 0) {  // the break (:37) is inside this word
+            if (T3 > 0) goto trim_done;
+            if (T3 < lowest) { lowest = T3; lowest_k = pos - 1 - L3; }
+            if (T2 > 0) goto trim_done;
+            if (T2 < lowest) { lowest = T2; lowest_k = pos - 2 - L3; }
+            if (T1 > 0) goto trim_done;
+            if (T1 < lowest) { lowest = T1; lowest_k = pos - 3 - L3; }
+            goto trim_done;
+        }
+        const int mn = min(min(T3, T2), min(T1, T0));
+        if (mn < lowest) {  // strict '<' (:38): the byte examined first (highest address) wins a tie
+            lowest = mn;
+            lowest_k = (T3 == mn ? pos - 1 : T2 == mn ? pos - 2 : T1 == mn ? pos - 3 : pos - 4) - L3;
+        }
+        total = T0;
+        pos -= 4;
+    }
+    while (pos > L3) {
+        pos--;
+        SK_TRIM_BYTE(pos)
+    }
+#undef SK_TRIM_BYTE
+trim_done:
     if (lowest_k == 0) {  // :44-45
         mode = B_GARBAGE;
         kk = 0;
@@ -237,7 +271,7 @@ __device__ __forceinline__ bool bc_find(const uint8_t *b, const uint8_t *lut, ui
     }
     return false;
 }
-// end of the greedy class run that starts at `from` (from < h1 is a class char already)
+// end of the greedy class run that starts at `from` (from <= h1)
 __device__ __forceinline__ uint32_t bc_run_end(const uint8_t *b, const uint8_t *lut, uint32_t from, uint32_t h1) {
     uint32_t e = from;
     while (e < h1 && (e & 3u)) {  // up to the next aligned word
@@ -286,251 +320,80 @@ __device__ __forceinline__ uint32_t ffsw<uint32_t>(uint32_t x) { return (uint32_
 template <>
 __device__ __forceinline__ uint32_t ffsw<uint64_t>(uint64_t x) { return (uint32_t)__ffsll((long long)x) - 1u; }
 
-// Exact-match lookup (FastIdx): is the barcode at window offset bs byte-identical, on the cared
-// positions, to some sample?  On a hit best/last are the first/last such sample over all classes.
+// Pigeonhole barcode match (HalfIdx, sk_internal.h): (lowest distance, first and last sample at that
+// distance) over every sample within one mismatch of the barcode at window offset bs -- the outcome
+// of fasta_demultiplex.rs:157-166 whenever it matters (:172).  lowest stays 0xFFFFFFFF when no
+// sample is within one mismatch.
 template <int NWMAX>
-__device__ __forceinline__ bool fast_lookup(const uint8_t *b, uint32_t bs, uint32_t nw, uint32_t ncls, uint32_t tmask,
-                                            const uint32_t *cls, const unsigned long long *tab, const uint32_t *skeys,
-                                            uint32_t &best, uint32_t &last) {
+__device__ __forceinline__ void hidx_match(const uint8_t *b, uint32_t bs, const HalfIdx &H, const uint32_t *hcls,
+                                           uint32_t &lowest, uint32_t &best, uint32_t &last) {
     const uint32_t a = bs & ~3u, sh = (bs & 3u) * 8u;
+    const uint32_t nw = H.nw, nwp = H.nwp, tmask = H.tsize - 1u;
     uint32_t raw[NWMAX];
-    uint32_t lo = *(const uint32_t *)(b + a);
-#pragma unroll
-    for (int w = 0; w < NWMAX; w++) {
-        raw[w] = 0;
-        if (w < (int)nw) {
-            const uint32_t hi = *(const uint32_t *)(b + a + 4 * w + 4);
-            raw[w] = __funnelshift_r(lo, hi, sh);
-            lo = hi;
-        }
-    }
-    bool hit = false;
-    best = 0xFFFFFFFFu;
-    last = 0;
-    for (uint32_t c = 0; c < ncls; c++) {
-        const uint32_t *cw = cls + c * FAST_CLS_WORDS;
-        uint32_t key[NWMAX], h1 = 0, h2 = 0;
+    {
+        uint32_t lo = *(const uint32_t *)(b + a);
 #pragma unroll
         for (int w = 0; w < NWMAX; w++) {
-            key[w] = raw[w] & cw[w];  // care bytes are 0 beyond nw
-            h1 += key[w] * cw[FAST_NWMAX + w];
-            h2 += key[w] * cw[2 * FAST_NWMAX + w];
-        }
-        h1 ^= h1 >> 15;
-        uint32_t slot = h1 & tmask;
-        const unsigned long long *t = tab + (size_t)c * (tmask + 1);
-        for (;;) {
-            const unsigned long long e = t[slot];
-            const uint32_t f = (uint32_t)(e >> 32) & 0xFFFFu;
-            if (f == 0xFFFFu) break;  // empty slot: not in this class
-            if ((uint32_t)e == h2) {
-                bool same = true;
-#pragma unroll
-                for (int w = 0; w < NWMAX; w++)
-                    if (w < (int)nw) same &= (key[w] == skeys[f * nw + w]);
-                if (same) {
-                    hit = true;
-                    best = f < best ? f : best;
-                    const uint32_t l = (uint32_t)(e >> 48);
-                    last = l > last ? l : last;
-                    break;
-                }
-            }
-            slot = (slot + 1) & tmask;
-        }
-    }
-    return hit;
-}
-
-// ------------------------------------------------------------------------------------------------
-// 4-lane groups: the per-record plan is latency bound when one thread walks a record alone
-// (profiles/r1_v2_phase_cycles.txt), so 4 consecutive lanes share each record.  Shuffles name only
-// the group's lanes, so groups of one warp may sit at different loop iterations.
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t gmask4() { return 0xFu << ((threadIdx.x & 31u) & ~3u); }
-__device__ __forceinline__ uint32_t gmin4(uint32_t gm, uint32_t v) {
-    uint32_t o = __shfl_xor_sync(gm, v, 1);
-    v = o < v ? o : v;
-    o = __shfl_xor_sync(gm, v, 2);
-    return o < v ? o : v;
-}
-__device__ __forceinline__ uint32_t gmax4(uint32_t gm, uint32_t v) {
-    uint32_t o = __shfl_xor_sync(gm, v, 1);
-    v = o > v ? o : v;
-    o = __shfl_xor_sync(gm, v, 2);
-    return o > v ? o : v;
-}
-__device__ __forceinline__ uint32_t gsum4(uint32_t gm, uint32_t v) {
-    v += __shfl_xor_sync(gm, v, 1);
-    return v + __shfl_xor_sync(gm, v, 2);
-}
-
-// fasta_trim_by_quality.rs:28-48, four lanes per record: every step the group examines the next 16
-// bytes of the quality line from its end (one aligned word per lane, lane 0 the highest), forms the
-// running totals with a 4-lane prefix sum, finds the first total > 0 (the `break`, :37) and the
-// first strict minimum before it (:38-41).  All lanes return the same result.
-__device__ __forceinline__ bool plan_trim_body4(const uint8_t *b, uint32_t gm, uint32_t q4, uint32_t L1, uint32_t L2,
-                                                uint32_t L3, uint32_t L4, int minq, uint8_t &mode, uint32_t &kk,
-                                                uint32_t &body_len) {
-    uint32_t k = L4 - L3;
-    while (k > 0 && is_ws(b[L3 + k - 1])) k--;  // qual.trim_end().len()  (:31)
-    int total = -50, lowest = -50;              // :28-29
-    uint32_t lowest_k = k;
-    uint32_t pos = L3 + k;  // one past the byte examined next
-    const int sub = 33 + minq;
-    while (pos > L3) {
-        const uint32_t a_top = (pos - 1) & ~3u;
-        int v0 = 0, v1 = 0, v2 = 0, v3 = 0;
-        uint32_t vm = 0, a = 0;
-        if (a_top >= 4u * q4) {
-            a = a_top - 4u * q4;
-            if (a + 4 > L3) {
-                const uint32_t w = *(const uint32_t *)(b + a);
-#define SK_VAL(j, vj)                                                                                   \
-    if (a + (j) >= L3 && a + (j) < pos) {                                                               \
-        const uint32_t q = (w >> (8 * (j))) & 0xFFu;                                                    \
-        vj = q >= 33u ? (int)q - sub : (int)((q - 33u) & 0xFFu) - minq; /* wrapping u8 subtraction (:35) */ \
-        vm |= 1u << (j);                                                                                \
-    }
-                SK_VAL(0, v0) SK_VAL(1, v1) SK_VAL(2, v2) SK_VAL(3, v3)
-#undef SK_VAL
-            }
-        }
-        const int s3 = v3, s2 = s3 + v2, s1 = s2 + v1, s0 = s1 + v0;  // sums in scan order (descending address)
-        int inc = s0, t = __shfl_up_sync(gm, inc, 1, 4);
-        if (q4 >= 1) inc += t;
-        t = __shfl_up_sync(gm, inc, 2, 4);
-        if (q4 >= 2) inc += t;
-        const int pre = total + inc - s0;
-        const int T3 = pre + s3, T2 = pre + s2, T1 = pre + s1, T0 = pre + s0;
-        uint32_t brk = 0;  // address + 1 of the byte whose total first exceeds 0 (0 = none)
-        if ((vm & 1u) && T0 > 0) brk = a + 1;
-        if ((vm & 2u) && T1 > 0) brk = a + 2;
-        if ((vm & 4u) && T2 > 0) brk = a + 3;
-        if ((vm & 8u) && T3 > 0) brk = a + 4;
-        brk = gmax4(gm, brk);
-        int mT = 0x7FFFFFFF;
-        uint32_t mA = 0;
-        if ((vm & 8u) && a + 4 > brk && T3 < mT) { mT = T3; mA = a + 3; }
-        if ((vm & 4u) && a + 3 > brk && T2 < mT) { mT = T2; mA = a + 2; }
-        if ((vm & 2u) && a + 2 > brk && T1 < mT) { mT = T1; mA = a + 1; }
-        if ((vm & 1u) && a + 1 > brk && T0 < mT) { mT = T0; mA = a; }
-#pragma unroll
-        for (int o = 1; o <= 2; o <<= 1) {  // lower total wins; on a tie the byte examined first (higher address)
-            const int oT = __shfl_xor_sync(gm, mT, o);
-            const uint32_t oA = __shfl_xor_sync(gm, mA, o);
-            if (oT < mT || (oT == mT && oA > mA)) { mT = oT; mA = oA; }
-        }
-        if (mT < lowest) {
-            lowest = mT;
-            lowest_k = mA - L3;
-        }
-        if (brk) break;
-        total += __shfl_sync(gm, inc, 3, 4);  // the group's 16 bytes
-        pos = a_top >= 12u ? a_top - 12u : 0u;
-    }
-    if (lowest_k == 0) {  // :44-45
-        mode = B_GARBAGE;
-        kk = 0;
-        body_len = 6;  // "N\n+\n!\n"
-        return true;
-    }
-    mode = B_TRIM;
-    kk = lowest_k;
-    body_len = 2 * lowest_k + 4;  // seq[..k] "\n+\n" qual[..k] "\n"  (:47)
-    return lowest_k <= L2 - L1;
-}
-
-// bc_find with the header's words dealt round-robin to the four lanes.
-__device__ __forceinline__ bool bc_find4(const uint8_t *b, const uint8_t *lut, uint32_t gm, uint32_t q4, uint32_t h0,
-                                         uint32_t h1, uint32_t &st) {
-    uint32_t best = 0xFFFFFFFFu;
-    if (h1 >= h0 + 5) {
-        const uint32_t last = h1 - 5;
-        for (uint32_t a = (h0 & ~3u) + 4u * q4; a <= last && best == 0xFFFFFFFFu; a += 16) {
-            uint32_t z = eq_flags(*(const uint32_t *)(b + a), 0x20202020u);
-            while (z) {
-                const uint32_t i = a + ((__ffs(z) - 1) >> 3);
-                z &= z - 1;
-                if (i >= h0 && i <= last && b[i + 1] == 'B' && b[i + 2] == 'C' && b[i + 3] == ':' && (lut[b[i + 4]] & 8u)) {
-                    best = i;
-                    break;
-                }
+            raw[w] = 0;
+            if (w < (int)nw) {
+                const uint32_t hi = *(const uint32_t *)(b + a + 4 * w + 4);
+                raw[w] = __funnelshift_r(lo, hi, sh);
+                lo = hi;
             }
         }
     }
-    best = gmin4(gm, best);
-    st = best;
-    return best != 0xFFFFFFFFu;
-}
-// first offset in [from, h1) that is not a class byte (h1 if none), bytes dealt round-robin
-__device__ __forceinline__ uint32_t bc_run_end4(const uint8_t *b, const uint8_t *lut, uint32_t gm, uint32_t q4,
-                                                uint32_t from, uint32_t h1) {
-    uint32_t e = h1;
-    for (uint32_t i = from + q4; i < h1; i += 4)
-        if (!(lut[b[i]] & 8u)) {
-            e = i;
-            break;
-        }
-    return gmin4(gm, e);
-}
-
-// fast_lookup with the key words dealt round-robin to the four lanes (word w belongs to lane w & 3).
-template <int NWMAX>
-__device__ __forceinline__ bool fast_lookup4(const uint8_t *b, uint32_t gm, uint32_t q4, uint32_t bs, uint32_t nw,
-                                             uint32_t ncls, uint32_t tmask, const uint32_t *cls,
-                                             const unsigned long long *tab, const uint32_t *skeys, uint32_t &best,
-                                             uint32_t &last) {
-    constexpr int NT4 = NWMAX / 4;
-    const uint32_t a = bs & ~3u, sh = (bs & 3u) * 8u;
-    uint32_t raw[NT4];
-#pragma unroll
-    for (int t = 0; t < NT4; t++) {
-        const uint32_t w = q4 + 4u * t;
-        raw[t] = 0;
-        if (w < nw) raw[t] = __funnelshift_r(*(const uint32_t *)(b + a + 4 * w), *(const uint32_t *)(b + a + 4 * w + 4), sh);
-    }
-    bool hit = false;
+    lowest = 0xFFFFFFFFu;
     best = 0xFFFFFFFFu;
     last = 0;
-    for (uint32_t c = 0; c < ncls; c++) {
-        const uint32_t *cw = cls + c * FAST_CLS_WORDS;
-        uint32_t key[NT4], h1 = 0, h2 = 0;
+    for (uint32_t c = 0; c < H.n_classes; c++) {
+        const uint32_t *care = hcls + c * HIDX_CLS_ROWS * nwp;
+        for (uint32_t h = 0; h < 2; h++) {
+            const uint32_t *hm = care + (1 + 3 * h) * nwp;
+            uint32_t h1 = 0, h2 = 0;
 #pragma unroll
-        for (int t = 0; t < NT4; t++) {
-            const uint32_t w = q4 + 4u * t;
-            key[t] = raw[t] & cw[w];  // care bytes are 0 beyond nw
-            h1 += key[t] * cw[FAST_NWMAX + w];
-            h2 += key[t] * cw[2 * FAST_NWMAX + w];
-        }
-        h1 = gsum4(gm, h1);
-        h2 = gsum4(gm, h2);
-        h1 ^= h1 >> 15;
-        uint32_t slot = h1 & tmask;
-        const unsigned long long *t2 = tab + (size_t)c * (tmask + 1);
-        for (;;) {
-            const unsigned long long e = t2[slot];
-            const uint32_t f = (uint32_t)(e >> 32) & 0xFFFFu;
-            if (f == 0xFFFFu) break;  // empty slot: not in this class
-            if ((uint32_t)e == h2) {
-                uint32_t same = 1;
+            for (int w = 0; w < NWMAX; w++)
+                if (w < (int)nw) {
+                    const uint32_t k = raw[w] & hm[w];
+                    h1 += k * hm[nwp + w];
+                    h2 += k * hm[2 * nwp + w];
+                }
+            h1 ^= h1 >> 15;
+            uint32_t slot = h1 & tmask;
+            const uint2 *tab = H.table + (size_t)(c * 2 + h) * H.tsize;
+            for (;;) {
+                const uint2 e = __ldg(&tab[slot]);
+                const uint32_t cnt = e.y >> 16;
+                if (!cnt) break;  // empty slot: end of the probe chain
+                if (e.x == h2) {
+                    const uint32_t st = e.y & 0xFFFFu;
+                    for (uint32_t i = 0; i < cnt; i++) {
+                        const uint32_t s = __ldg(&H.cand[st + i]);
+                        const uint4 *sk = (const uint4 *)(H.skeys + (size_t)s * nwp);
+                        uint32_t d = 0;
 #pragma unroll
-                for (int t = 0; t < NT4; t++) {
-                    const uint32_t w = q4 + 4u * t;
-                    if (w < nw && key[t] != skeys[f * nw + w]) same = 0;
+                        for (int q = 0; q < NWMAX / 4; q++)
+                            if (4 * q < (int)nw) {
+                                const uint4 kq = __ldg(&sk[q]);
+                                d += nz_bytes((raw[4 * q] & care[4 * q]) ^ kq.x);
+                                d += nz_bytes((raw[4 * q + 1] & care[4 * q + 1]) ^ kq.y);
+                                d += nz_bytes((raw[4 * q + 2] & care[4 * q + 2]) ^ kq.z);
+                                d += nz_bytes((raw[4 * q + 3] & care[4 * q + 3]) ^ kq.w);
+                            }
+                        if (d < lowest) {
+                            lowest = d;
+                            best = s;
+                            last = s;
+                        } else if (d == lowest) {
+                            best = s < best ? s : best;
+                            last = s > last ? s : last;
+                        }
+                    }
                 }
-                if (gmin4(gm, same)) {
-                    hit = true;
-                    best = f < best ? f : best;
-                    const uint32_t l = (uint32_t)(e >> 48);
-                    last = l > last ? l : last;
-                    break;
-                }
+                slot = (slot + 1) & tmask;
             }
-            slot = (slot + 1) & tmask;
         }
     }
-    return hit;
+    if (lowest > 1u) lowest = 0xFFFFFFFFu;  // farther samples were not enumerated completely
 }
 
 // Thread-serial copy of `len` bytes inside shared memory.  The destination is brought to 4- and then
@@ -597,6 +460,7 @@ struct Misc {
     uint32_t chunk_out;
     uint32_t cta_total, cta_ident, cta_slow;
     uint32_t n_slow;
+    uint32_t n_groups;
     uint32_t scratch[40];
 };
 
@@ -615,46 +479,48 @@ struct Misc {
 
 template <class Cfg, int OP, typename WT>
 __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const __grid_constant__ KParams p) {
-    constexpr int NT = Cfg::NT, NW = NT / 32, MAXREC = Cfg::MAXREC, MAXLINES = Cfg::MAXLINES;
+    constexpr int NT = Cfg::NT, NW = NT / 32, MAXREC = Cfg::MAXREC;
     constexpr bool WIDE = sizeof(WT) == 8;
     constexpr int NWMAX = WIDE ? 16 : 8;
     constexpr bool IS_DEMUX = (OP == OP_DEMUX1 || OP == OP_DEMUX2);
     constexpr bool ORDERED = (OP == OP_TRIM || OP == OP_MASK || OP == OP_ADDBC);
     constexpr bool HAS_OUT = ORDERED || IS_DEMUX;
-    static_assert(MAXREC <= NT, "one planning thread per record");
+    // OP_SCAN keeps no per-record plan and no staging image: its line table takes the staging area, so
+    // that index reads and barcode files (very short records) do not hit the density limit.
+    constexpr int MAXLINES = (OP == OP_SCAN) ? (Cfg::STAGE / 2 - 8) : Cfg::MAXLINES;
+    constexpr int PIECE_BYTES = Cfg::PPL * 16;
 
     const uint32_t S = IS_DEMUX ? p.sheet.S : 0u;
-    const uint32_t FC = (OP == OP_DEMUX1) ? p.sheet.fast.n_classes : 0u;
-    const uint32_t FT = (OP == OP_DEMUX1) ? p.sheet.fast.tsize : 0u;
     const SmemLayout &SL = p.sl;
     uint8_t *win = sk_smem + SL.win;
     uint8_t *stage = sk_smem + SL.stage;
-    uint16_t *ls = (uint16_t *)(sk_smem + SL.ls);
-    uint32_t *r_outoff = (uint32_t *)(sk_smem + SL.rec);
-    uint32_t *r_aux = r_outoff + MAXREC;  // ADDBC: barcode offset; demux: sample << 16 | out_len
-    uint16_t *r_outlen = (uint16_t *)(r_aux + MAXREC);
+    uint16_t *ls = (uint16_t *)(sk_smem + (OP == OP_SCAN ? SL.stage : SL.ls));
+    uint32_t *r_aux = (uint32_t *)(sk_smem + SL.rec);  // ADDBC: barcode offset; demux slow layout: group totals
+    uint16_t *r_outoff = (uint16_t *)(r_aux + MAXREC);
+    uint16_t *r_outlen = r_outoff + MAXREC;
     uint16_t *r_cut0 = r_outlen + MAXREC;
     uint16_t *r_cut1 = r_cut0 + MAXREC;
     uint16_t *r_alen = r_cut1 + MAXREC;
     uint16_t *r_blen = r_alen + MAXREC;
     uint16_t *r_k = r_blen + MAXREC;
-    uint16_t *r_taglen = r_k + MAXREC;
+    uint16_t *r_body = r_k + MAXREC;
+    uint16_t *r_taglen = r_body + MAXREC;
     int16_t *r_sample = (int16_t *)(r_taglen + MAXREC);
     uint8_t *r_mode = (uint8_t *)(r_sample + MAXREC);
     uint8_t *r_flags = r_mode + MAXREC;
-    WT *sh_planes = (WT *)(sk_smem + SL.sheet);
+    static_assert(REC_BYTES >= 4 + 2 * 10 + 2, "per-record plan fields");
     WT *sh_umask = (WT *)(sk_smem + SL.umask);
     uint8_t *sh_lut = sk_smem + SL.lut;
-    uint32_t *hist = (uint32_t *)(sk_smem + SL.hist);
-    uint32_t *sbase = (uint32_t *)(sk_smem + SL.sbase);
     uint32_t *ccount = (uint32_t *)(sk_smem + SL.ccount);
-    uint32_t *f_cls = (uint32_t *)(sk_smem + SL.fcls);
-    unsigned long long *f_tab = (unsigned long long *)(sk_smem + SL.ftab);
+    uint32_t *masks = (uint32_t *)(sk_smem + SL.masks);  // per sample: 128 record bits of the current chunk
+    uint32_t *gbase_sm = (uint32_t *)(sk_smem + SL.gtot);
+    uint32_t *hcls = (uint32_t *)(sk_smem + SL.hcls);
     uint16_t *slow_list = (uint16_t *)(sk_smem + SL.slow);
     Misc *M = (Misc *)(sk_smem + SL.misc);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     DevStats *st = p.stats;
+    const bool use_hidx = (OP == OP_DEMUX1) && p.sheet.hidx.n_classes != 0 && p.n_index == 0;
 
     // ---- one-time per CTA: mbarrier, sheet -> shared memory
     if (tid == 0) {
@@ -664,16 +530,17 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
         M->cta_slow = 0;
     }
     if (IS_DEMUX) {
-        const WT *gp = (const WT *)p.sheet.planes;
-        for (uint32_t i = tid; i < 4 * S; i += NT) sh_planes[i] = gp[i];
         const WT *gu = (const WT *)p.sheet.umask;
         for (uint32_t i = tid; i < S; i += NT) {
             sh_umask[i] = gu[i];
             ccount[i] = 0;
         }
+        for (uint32_t i = tid; i < 4 * S; i += NT) masks[i] = 0;
         for (uint32_t i = tid; i < 256; i += NT) sh_lut[i] = p.sheet.lut[i];
-        for (uint32_t i = tid; i < FC * FAST_CLS_WORDS; i += NT) f_cls[i] = p.sheet.fast.cls[i];
-        for (uint32_t i = tid; i < FC * FT; i += NT) f_tab[i] = p.sheet.fast.table[i];
+        if (OP == OP_DEMUX1) {
+            const uint32_t nh = p.sheet.hidx.n_classes * HIDX_CLS_ROWS * p.sheet.hidx.nwp;
+            for (uint32_t i = tid; i < nh; i += NT) hcls[i] = p.sheet.hidx.cls[i];
+        }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -682,28 +549,13 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
     unsigned long long ph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long t_prev = clock64();
 #endif
-    uint32_t parity = 0;
+    uint32_t parity = 0, flip = 0;
+    bool store_pending = false;  // thread 0: a TMA store of the staging image may still be reading it
     if (tid == 0) {
         M->chunk = atomicAdd(&st->ticket, 1u);
         M->n_slow = 0;
     }
     __syncthreads();
-    // P9 of chunk k is deferred into the window load of chunk k+1: the staged image is stored with
-    // 16-byte vectors (bytes at an unaligned head/tail) while the TMA copy is in flight.
-    uint32_t pend_span = 0, pend_shift = 0;
-    uint8_t *pend_g16 = nullptr;
-    auto flush_stage = [&]() {
-        for (uint32_t v = tid; v * 16 < pend_span; v += NT) {
-            const uint32_t b0 = v * 16;
-            if (b0 >= pend_shift && b0 + 16 <= pend_span) {
-                *(uint4 *)(pend_g16 + b0) = *(const uint4 *)(stage + b0);
-            } else {
-                const uint32_t lo = b0 < pend_shift ? pend_shift : b0, hi = b0 + 16 < pend_span ? b0 + 16 : pend_span;
-                for (uint32_t b2 = lo; b2 < hi; b2++) pend_g16[b2] = stage[b2];
-            }
-        }
-        pend_span = 0;
-    };
     for (;;) {
         // ---- P0 ticket (taken by thread 0 at the end of the previous chunk, published by its last barrier)
         const uint32_t c = M->chunk;
@@ -726,51 +578,72 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
             mbar_expect_tx(&M->mbar, bulk);
             bulk_g2s(win, p.in + w0, bulk, &M->mbar);
         }
-        if (tid < 16) {  // tail bytes; zero padding so the last partial piece reads defined data
+        if (bulk != (uint32_t)Cfg::WIN_MAX && tid < 16) {  // tail bytes; zero padding so the last partial piece reads defined data
             const uint32_t o = bulk + tid;
             if (o < (uint32_t)Cfg::WIN_MAX) win[o] = (o < wlen) ? p.in[w0 + o] : (uint8_t)0;
         }
-        if (pend_span) flush_stage();  // previous chunk's output, overlapped with the copy above
         if (bulk) {
             mbar_wait(&M->mbar, parity);
             parity ^= 1;
         }
-        __syncthreads();
-        SK_T(1);  // window load (+ deferred store of the previous chunk)
+        if (bulk != (uint32_t)Cfg::WIN_MAX) __syncthreads();  // the tail bytes (last windows of the stream only)
+        SK_T(1);  // window load
 
-        // ---- P2 newline scan: 80 contiguous bytes per thread, kept as 5 piece maps
+        // ---- P2 newline scan: PPL*16 contiguous bytes per thread, kept as PPL piece maps
         // A '\n' at window offset q starts a line at q+1.  Lines that start before the chunk belong to
         // the previous chunk (q+1 >= cs); a '\n' that is the last byte of the buffer starts nothing.
         const uint32_t ls_lo = cs ? cs - 1 : 0;
         const uint32_t ls_hi = at_end ? (wlen ? wlen - 1 : 0) : wlen;
+        const uint32_t o0 = (uint32_t)tid * PIECE_BYTES;
         uint32_t ymap[Cfg::PPL];
         uint32_t cnt_all = 0, cnt_chunk = 0, hib = 0;
+        if (o0 >= ls_lo && o0 + PIECE_BYTES <= ls_hi && o0 + PIECE_BYTES <= wlen &&
+            (o0 + PIECE_BYTES <= ce - 1 || o0 >= ce - 1)) {
+            // interior thread: no range boundary inside its bytes
 #pragma unroll
-        for (int q = 0; q < Cfg::PPL; q++) {
-            const uint32_t o = (uint32_t)tid * (Cfg::PPL * 16) + q * 16;
-            uint32_t y = 0;
-            if (o < wlen) {
-                const uint4 v = *(const uint4 *)(win + o);
-                y = nl_map(v);
-                hib |= (v.x | v.y | v.z | v.w);  // bytes past wlen in the last piece are zero
-                if (o < ls_lo || o + 16 > ls_hi) y = map_clip(y, o, ls_lo, ls_hi);
-                const uint32_t n = __popc(y);
-                cnt_all += n;
-                if (o + 16 <= ce - 1) cnt_chunk += n;
-                else if (o < ce - 1) cnt_chunk += __popc(map_clip(y, o, 0, ce - 1));
+            for (int q = 0; q < Cfg::PPL; q++) {
+                const uint4 v = *(const uint4 *)(win + o0 + q * 16);
+                const uint32_t y = nl_map(v);
+                hib |= (v.x | v.y | v.z | v.w);
+                cnt_all += __popc(y);
+                ymap[q] = y;
             }
-            ymap[q] = y;
+            cnt_chunk = o0 >= ce - 1 ? 0u : cnt_all;
+        } else {
+#pragma unroll
+            for (int q = 0; q < Cfg::PPL; q++) {
+                const uint32_t o = o0 + q * 16;
+                uint32_t y = 0;
+                if (o < wlen) {
+                    const uint4 v = *(const uint4 *)(win + o);
+                    y = nl_map(v);
+                    hib |= (v.x | v.y | v.z | v.w);  // bytes past wlen in the last piece are zero
+                    if (o < ls_lo || o + 16 > ls_hi) y = map_clip(y, o, ls_lo, ls_hi);
+                    const uint32_t n = __popc(y);
+                    cnt_all += n;
+                    if (o + 16 <= ce - 1) cnt_chunk += n;
+                    else if (o < ce - 1) cnt_chunk += __popc(map_clip(y, o, 0, ce - 1));
+                }
+                ymap[q] = y;
+            }
         }
         if (__any_sync(0xffffffffu, (hib & 0x80808080u) != 0) && lane == 0) atomicOr(&st->flags, F_NON_ASCII);
 
         uint32_t tot;
-        const uint32_t pre = block_excl_scan<NT>((cnt_chunk << 16) | cnt_all, M->scratch, tot);
+        const uint32_t pre = block_excl_scan<NT>((cnt_chunk << 16) | cnt_all, M->scratch, flip, tot);
         const uint32_t extra = (c0 == 0) ? 1u : 0u;      // the line that starts at byte 0
         const uint32_t nls = (tot & 0xFFFFu) + extra;    // line starts in [cs, wlen)
         const uint32_t nls_chunk = (tot >> 16) + extra;  // ... of which inside the chunk
 
         SK_T(2);  // scan + block scan
-        // ---- P3 line-start table + look-back for the global line index
+        // ---- P3 look-back for the global line index (warp 0) + line-start table (everybody)
+        if (warp == 0) {
+            const uint64_t excl = lookback(p.tile_lines, c, nls_chunk, lane);
+            if (lane == 0) {
+                M->g0 = excl;
+                if (c == p.n_chunks - 1) st->n_lines = excl + nls_chunk;
+            }
+        }
         {
             uint32_t idx = (pre & 0xFFFFu) + extra;
             if (tid == 0 && extra) ls[0] = 0;
@@ -778,7 +651,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
             for (int q = 0; q < Cfg::PPL; q++) {
                 const uint32_t y = ymap[q];
                 if (y) {
-                    const uint32_t o = (uint32_t)tid * (Cfg::PPL * 16) + q * 16;
+                    const uint32_t o = o0 + q * 16;
                     const uint32_t y2 = y & (y - 1);
                     const uint32_t i1 = __ffs(y) - 1;
                     const uint32_t k1 = 4u * (i1 & 7u) + (i1 >> 3);  // piece offset of a map bit
@@ -801,16 +674,15 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
                     }
                 }
             }
-        }
-        if (warp == 0) {
-            const uint64_t excl = lookback(p.tile_lines, c, nls_chunk, lane);
-            if (lane == 0) {
-                M->g0 = excl;
-                if (c == p.n_chunks - 1) st->n_lines = excl + nls_chunk;
+            // sentinels: a line index past the last line start reads as "end of window" (EOF records)
+            if (tid >= NT - 8) {
+                const uint32_t k = nls + (uint32_t)(tid - (NT - 8));
+                if (k < (uint32_t)MAXLINES + 8u) ls[k] = (uint16_t)wlen;
             }
         }
         __syncthreads();
         SK_T(3);  // line table + look-back (lines)
+#define LB(x) ((uint32_t)ls[(x)])
 
         // ---- P4 which records does this chunk own?
         const uint64_t g0 = M->g0;
@@ -834,37 +706,54 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
             }
             if (!chunk_err && nrec) {
                 const uint32_t need = jend < nls ? jend : nls - 1;
-                if (need >= (uint32_t)MAXLINES || nrec > (uint32_t)MAXREC) chunk_err = K_TOO_DENSE;
+                if (need >= (uint32_t)MAXLINES || (OP != OP_SCAN && nrec > (uint32_t)MAXREC)) chunk_err = K_TOO_DENSE;
             }
             if (chunk_err) {
                 if (tid == 0) report_err(st, rec0, chunk_err);
                 nrec = 0;
             }
         }
-        const Win W{win, ls, nls, wlen};
         if (tid == 0 && nrec) {
             atomicAdd(&st->n_records, (unsigned long long)nrec);
-            atomicMax(&st->consumed, (unsigned long long)(w0 + lb(W, j0 + nrec * lpr)));
+            atomicMax(&st->consumed, (unsigned long long)(w0 + LB(j0 + nrec * lpr)));
         }
 
-        // ---- P5a plan: the reference's per-record logic, four lanes per record.  Cheap straight-line
-        // parts run on the group's lane 0; the long scans (trim, " BC:" search, class run) are shared.
-        const uint32_t gm = gmask4();
-        const uint32_t q4 = (uint32_t)tid & 3u;
-        for (uint32_t rbase = 0; rbase < nrec; rbase += NT / 4) {
-            const uint32_t r = rbase + ((uint32_t)tid >> 2);
-            if (r >= nrec) continue;  // whole groups drop out together
-            const uint32_t j = j0 + r * lpr;
-            const uint64_t rec = rec0 + r;
-            const uint32_t L0 = lb(W, j), L1 = lb(W, j + 1), L2 = lb(W, j + 2);
-            const uint32_t L3 = lpr == 4 ? lb(W, j + 3) : L2, L4 = lpr == 4 ? lb(W, j + 4) : L2;
-            const uint32_t Lend = lpr == 4 ? L4 : L2;
-            uint8_t mode = B_NONE, flags = 0;
-            uint32_t kk = 0, outlen = 0, alen = 0, cut0 = 0, cut1 = 0, blen = 0, taglen = 0, ext = 0;
-            int sample = -1;
+        // ---- P5 plan: the reference's per-record logic, one thread per record.  In the fused
+        // trim+demultiplex operators the two independent halves of a record's plan (quality trim |
+        // header search and barcode match) run on the two halves of the CTA at the same time.
+        const bool fused = IS_DEMUX && p.fused_trim >= 0;
+        const uint32_t tl = fused ? (uint32_t)tid % (NT / 2) : (uint32_t)tid;  // record slot of this thread
+        const uint32_t tstride = fused ? NT / 2 : NT;
+        const bool do_trim = fused && tid < NT / 2;
+        const bool do_main = !fused || tid >= NT / 2;
+        uint32_t my_total = 0, my_ident = 0;
 
-            if (OP == OP_SCAN) {
-                if (q4 == 0) {
+        if (do_trim) {
+            for (uint32_t r = tl; r < nrec; r += tstride) {
+                const uint32_t j = j0 + r * lpr;
+                const uint32_t L0 = LB(j), L1 = LB(j + 1), L2 = LB(j + 2), L3 = LB(j + 3), L4 = LB(j + 4);
+                uint8_t mode = B_FAIL;
+                uint32_t kk = 0, body = 0;
+                if (L1 > L0 && win[L1 - 1] == '\n') {
+                    if (!plan_trim_body(win, L1, L2, L3, L4, p.fused_trim, mode, kk, body)) mode = B_FAIL;
+                }
+                r_k[r] = (uint16_t)kk;
+                r_body[r] = (uint16_t)(body > 0xFFFFu ? 0xFFFFu : body);
+                r_mode[r] = mode;
+            }
+        }
+        if (do_main) {
+            for (uint32_t r = tl; r < nrec; r += tstride) {
+                const uint32_t j = j0 + r * lpr;
+                const uint64_t rec = rec0 + r;
+                const uint32_t L0 = LB(j), L1 = LB(j + 1), L2 = LB(j + 2);
+                const uint32_t L3 = lpr == 4 ? LB(j + 3) : L2, L4 = lpr == 4 ? LB(j + 4) : L2;
+                const uint32_t Lend = lpr == 4 ? L4 : L2;
+                uint8_t mode = B_NONE, flags = 0;
+                uint32_t kk = 0, outlen = 0, alen = 0, cut0 = 0, cut1 = 0, blen = 0, taglen = 0, ext = 0;
+                int sample = -1;
+
+                if (OP == OP_SCAN) {
                     // (seq_off, seq_len after trim_end, flags) of an index read / barcode record
                     uint32_t sl = L2 - L1;
                     while (sl > 0 && is_ws(win[L1 + sl - 1])) sl--;
@@ -884,179 +773,171 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
                         rr.flags = fl;
                         p.scan_out[rec] = rr;
                     }
-                }
-            } else if (OP == OP_TRIM) {
-                if (win[L0] != '@') {  // fasta_trim_by_quality.rs:20-22
-                    if (q4 == 0) report_err(st, rec, K_BAD_HEADER);
-                } else {
-                    uint32_t body;
-                    if (!plan_trim_body4(win, gm, q4, L1, L2, L3, L4, (int)p.min_baseq, mode, kk, body)) {
-                        if (q4 == 0) report_err(st, rec, K_SEQ_SHORT);
-                        mode = B_NONE;
+                    continue;
+                } else if (OP == OP_TRIM) {
+                    if (win[L0] != '@') {  // fasta_trim_by_quality.rs:20-22
+                        report_err(st, rec, K_BAD_HEADER);
                     } else {
-                        outlen = (L1 - L0) + body;  // header verbatim (:23) + body
+                        uint32_t body;
+                        if (!plan_trim_body(win, L1, L2, L3, L4, (int)p.min_baseq, mode, kk, body)) {
+                            report_err(st, rec, K_SEQ_SHORT);
+                            mode = B_NONE;
+                        } else {
+                            outlen = (L1 - L0) + body;  // header verbatim (:23) + body
+                        }
                     }
-                }
-            } else if (OP == OP_MASK) {
-                if (win[L0] != '@') {  // fasta_mask_by_quality.rs:21-23
-                    if (q4 == 0) report_err(st, rec, K_BAD_HEADER);
-                } else {
-                    uint32_t sl = L2 - L1, ql = L4 - L3;
-                    if (sl && win[L2 - 1] == '\n') sl--;  // :32
-                    if (ql && win[L4 - 1] == '\n') ql--;  // :33
-                    if (sl != ql) {                       // :35-37
-                        if (q4 == 0) report_err(st, rec, K_LEN_MISMATCH);
+                } else if (OP == OP_MASK) {
+                    if (win[L0] != '@') {  // fasta_mask_by_quality.rs:21-23
+                        report_err(st, rec, K_BAD_HEADER);
                     } else {
-                        mode = B_MASK;
-                        kk = sl;
-                        outlen = (L1 - L0) + 2 * sl + 4;  // header, masked, "\n+\n", qual, "\n"  (:26,:44)
+                        uint32_t sl = L2 - L1, ql = L4 - L3;
+                        if (sl && win[L2 - 1] == '\n') sl--;  // :32
+                        if (ql && win[L4 - 1] == '\n') ql--;  // :33
+                        if (sl != ql) {                       // :35-37
+                            report_err(st, rec, K_LEN_MISMATCH);
+                        } else {
+                            mode = B_MASK;
+                            kk = sl;
+                            outlen = (L1 - L0) + 2 * sl + 4;  // header, masked, "\n+\n", qual, "\n"  (:26,:44)
+                        }
                     }
-                }
-            } else if (OP == OP_ADDBC) {
-                // fasta_add_barcode.rs:29-43
-                const uint8_t h = win[L0];
-                uint32_t e = L1;
-                while (e > L0 && is_ws(win[e - 1])) e--;  // header.trim_end()
-                alen = e - L0;
-                // barcode of iteration i = sequence line of barcode record i; the last one is reused
-                // once the barcode file is exhausted (:20-27)
-                uint32_t bl = 0, bo = 0;
-                const uint64_t nb = p.ext_stats[0] ? p.ext_stats[0]->n_records : 0;
-                if (nb) {
-                    const uint64_t bi = rec < nb ? rec : nb - 1;
-                    const RecRef rr = p.ext_tab[0][bi];
-                    bl = rr.seq_len;
-                    bo = rr.seq_off;
-                }
-                taglen = 4 + bl;  // " BC:" + barcode
-                ext = bo;
-                cut1 = alen;
-                if (h != (uint8_t)p.head_char) {
-                    // the reference prints the BC'd header and then stops (:33 before :41-43); the host
-                    // reproduces that line, the kernel only reports where.
-                    if (q4 == 0) report_err(st, rec, (h == '@' || h == '>') ? K_MIXED : K_BAD_FASTX_LINE);
-                    taglen = 0;
-                } else {
-                    mode = B_VERBATIM;
-                    outlen = alen + taglen + 1 + (Lend - L1);
-                }
-            } else if (OP == OP_DEMUX1) {
-                // fasta_demultiplex.rs:117-150: validate, locate the barcode, try the exact-match index.
-                // Anything the index cannot settle is queued for the warp-cooperative matcher (P5b).
-                flags = RF_DEAD;
-                if (win[L0] != '@') {  // :118-120
-                    if (q4 == 0) report_err(st, rec, K_BAD_HEADER);
-                } else if (p.fused_trim >= 0 && !(L1 > L0 && win[L1 - 1] == '\n')) {
-                    if (q4 == 0) report_err(st, rec, K_TRUNC_FUSED);
-                } else if (p.n_index) {
-                    flags = RF_SLOW;  // --index route: the barcode lives in other streams (:126-136)
-                } else {
-                    uint32_t stp;
-                    if (!bc_find4(win, sh_lut, gm, q4, L0, L1, stp)) {  // :138-141
-                        if (q4 == 0) report_err(st, rec, K_NO_BC);
+                } else if (OP == OP_ADDBC) {
+                    // fasta_add_barcode.rs:29-43
+                    const uint8_t h = win[L0];
+                    uint32_t e = L1;
+                    while (e > L0 && is_ws(win[e - 1])) e--;  // header.trim_end()
+                    alen = e - L0;
+                    // barcode of iteration i = sequence line of barcode record i; the last one is reused
+                    // once the barcode file is exhausted (:20-27)
+                    uint32_t bl = 0, bo = 0;
+                    const uint64_t nb = p.ext_stats[0] ? p.ext_stats[0]->n_records : 0;
+                    if (nb) {
+                        const uint64_t bi = rec < nb ? rec : nb - 1;
+                        const RecRef rr = p.ext_tab[0][bi];
+                        bl = rr.seq_len;
+                        bo = rr.seq_off;
+                    }
+                    taglen = 4 + bl;  // " BC:" + barcode
+                    ext = bo;
+                    cut1 = alen;
+                    if (h != (uint8_t)p.head_char) {
+                        // the reference prints the BC'd header and then stops (:33 before :41-43); the host
+                        // reproduces that line, the kernel only reports where.
+                        report_err(st, rec, (h == '@' || h == '>') ? K_MIXED : K_BAD_FASTX_LINE);
+                        taglen = 0;
                     } else {
-                        flags = RF_SLOW;
-                        cut0 = stp - L0;
-                        const uint32_t bs = stp + 4, be = bs + p.sheet.L;
-                        // Fast path: the class run is exactly L long (next byte is outside the class or the
-                        // header ends) and the cared bytes equal some sample's barcode.
-                        if (FC && be <= L1 && (be == L1 || !(sh_lut[win[be]] & 8u))) {
-                            uint32_t best, last;
-                            if (fast_lookup4<NWMAX>(win, gm, q4, bs, p.sheet.fast.nw, FC, FT - 1, f_cls, f_tab,
-                                                    p.sheet.fast.skeys, best, last)) {
-                                // the run must not stop early: wildcard positions need class bytes too
-                                if (bc_run_end4(win, sh_lut, gm, q4, bs + 1, be) == be) {
-                                    flags = 0;
-                                    cut1 = be - L0;
-                                    sample = best == last ? (int)best : -2;
-                                    if (q4 == 0) {
-                                        atomicAdd(&M->cta_total, 1u);  // :169
-                                        if (best == last) {            // distance 0, unambiguous (:172-178)
-                                            atomicAdd(&M->cta_ident, 1u);
-                                            atomicAdd(&ccount[best], 1u);
-                                        } else {  // two samples at distance 0 (:184-188)
-                                            const uint32_t ei = atomicAdd(&st->n_events, 1u);
-                                            if (ei < p.events_cap) {
-                                                Event ev;
-                                                ev.record = (uint32_t)rec;
-                                                ev.bc_off = (uint32_t)(w0 + bs);
-                                                ev.bc_off2 = 0xFFFFFFFFu;
-                                                ev.best = (int16_t)best;
-                                                ev.last = (int16_t)last;
-                                                ev.mismatches = 0;
-                                                p.events[ei] = ev;
-                                            } else {
-                                                atomicOr(&st->flags, F_EVENTS_OVERFLOW);
-                                            }
+                        mode = B_VERBATIM;
+                        outlen = alen + taglen + 1 + (Lend - L1);
+                    }
+                } else if (OP == OP_DEMUX1) {
+                    // fasta_demultiplex.rs:117-194: validate, locate the barcode, match, decide.
+                    flags = RF_DEAD;
+                    if (win[L0] != '@') {  // :118-120
+                        report_err(st, rec, K_BAD_HEADER);
+                    } else if (fused && !(L1 > L0 && win[L1 - 1] == '\n')) {
+                        report_err(st, rec, K_TRUNC_FUSED);
+                    } else if (p.n_index) {
+                        flags = RF_SLOW;  // --index route: the barcode lives in other streams (:126-136)
+                    } else {
+                        uint32_t stp;
+                        if (!bc_find(win, sh_lut, L0, L1, stp)) {  // :138-141
+                            report_err(st, rec, K_NO_BC);
+                        } else {
+                            cut0 = stp - L0;
+                            const uint32_t bs = stp + 4;
+                            const uint32_t e = bc_run_end(win, sh_lut, bs + 1, L1);  // greedy class run (:38)
+                            cut1 = e - L0;
+                            if (e - bs != p.sheet.L) {  // :148-150
+                                report_err(st, rec, K_BC_LEN);
+                            } else if (!use_hidx) {
+                                flags = RF_SLOW;
+                            } else {
+                                flags = 0;
+                                uint32_t lowest, best, last;
+                                hidx_match<NWMAX>(win, bs, p.sheet.hidx, hcls, lowest, best, last);
+                                my_total++;                // :169
+                                if (lowest <= 1u) {        // :172
+                                    if (best == last) {    // :173-178
+                                        sample = (int)best;
+                                        my_ident++;
+                                        atomicAdd(&ccount[best], 1u);
+                                    } else {  // :184-188
+                                        sample = -2;
+                                        const uint32_t ei = atomicAdd(&st->n_events, 1u);
+                                        if (ei < p.events_cap) {
+                                            Event ev;
+                                            ev.record = (uint32_t)rec;
+                                            ev.bc_off = (uint32_t)(w0 + bs);
+                                            ev.bc_off2 = 0xFFFFFFFFu;
+                                            ev.best = (int16_t)best;
+                                            ev.last = (int16_t)last;
+                                            ev.mismatches = lowest;
+                                            p.events[ei] = ev;
+                                        } else {
+                                            atomicOr(&st->flags, F_EVENTS_OVERFLOW);
                                         }
                                     }
                                 }
                             }
                         }
                     }
-                }
-                if ((flags & RF_SLOW) && q4 == 0) slow_list[atomicAdd(&M->n_slow, 1u)] = (uint16_t)r;
-            } else if (OP == OP_DEMUX2) {
-                // fasta_demultiplex.rs:215-237: mate 2 of an assigned pair
-                sample = rec < p.r1_stats->n_records ? (int)p.assign[rec] : -1;
-                if (sample >= 0 && p.out) {
-                    uint32_t c0h = L1, c1h = L1;
-                    if (!p.n_index) {  // :219-227
-                        uint32_t a;
-                        if (bc_find4(win, sh_lut, gm, q4, L0, L1, a)) {
-                            c0h = a;
-                            c1h = bc_run_end4(win, sh_lut, gm, q4, a + 5, L1);
+                    if (flags & RF_SLOW) slow_list[atomicAdd(&M->n_slow, 1u)] = (uint16_t)r;
+                } else if (OP == OP_DEMUX2) {
+                    // fasta_demultiplex.rs:215-237: mate 2 of an assigned pair
+                    sample = rec < p.r1_stats->n_records ? (int)p.assign[rec] : -1;
+                    if (sample >= 0 && p.out) {
+                        uint32_t c0h = L1, c1h = L1;
+                        if (!p.n_index) {  // :219-227
+                            uint32_t a;
+                            if (bc_find(win, sh_lut, L0, L1, a)) {
+                                c0h = a;
+                                c1h = bc_run_end(win, sh_lut, a + 5, L1);
+                            }
                         }
-                    }
-                    header_pieces(win, L0, L1, c0h, c1h, alen, blen);  // :229
-                    cut1 = c1h - L0;
-                    const uint32_t ul = popcw<WT>(sh_umask[sample]);
-                    taglen = ul ? 5 + ul : 0;
-                    uint32_t body = Lend - L1;
-                    mode = B_VERBATIM;
-                    bool fine = true;
-                    if (p.fused_trim >= 0) {
-                        if (!(L1 > L0 && win[L1 - 1] == '\n')) {
-                            if (q4 == 0) report_err(st, rec, K_TRUNC_FUSED);
-                            fine = false;
-                        } else if (!plan_trim_body4(win, gm, q4, L1, L2, L3, L4, p.fused_trim, mode, kk, body)) {
-                            if (q4 == 0) report_err(st, rec, K_SEQ_SHORT);
-                            fine = false;
+                        header_pieces(win, L0, L1, c0h, c1h, alen, blen);  // :229
+                        cut1 = c1h - L0;
+                        const uint32_t ul = popcw<WT>(sh_umask[sample]);
+                        taglen = ul ? 5 + ul : 0;
+                        flags = 0;
+                        if (fused && !(L1 > L0 && win[L1 - 1] == '\n')) {
+                            report_err(st, rec, K_TRUNC_FUSED);
+                            flags = RF_DEAD;
                         }
+                    } else {
+                        flags = RF_DEAD;
                     }
-                    if (fine) outlen = alen + blen + taglen + 1 + body;
-                    else mode = B_NONE;
                 }
-            }
-            if (q4 == 0) {
                 r_outlen[r] = (uint16_t)(outlen > 0xFFFFu ? 0xFFFFu : outlen);
                 if (OP == OP_ADDBC) r_aux[r] = ext;
                 r_cut0[r] = (uint16_t)cut0;
                 r_cut1[r] = (uint16_t)cut1;
                 r_alen[r] = (uint16_t)alen;
                 r_blen[r] = (uint16_t)blen;
-                r_k[r] = (uint16_t)kk;
                 r_taglen[r] = (uint16_t)taglen;
                 r_sample[r] = (int16_t)sample;
-                r_mode[r] = mode;
                 r_flags[r] = flags;
+                if (!fused) {
+                    r_k[r] = (uint16_t)kk;
+                    r_mode[r] = mode;
+                }
             }
         }
+        __syncthreads();
+        SK_T(4);  // plan tasks
 
-        if (OP != OP_DEMUX1) __syncthreads();  // plans are written by each group's lane 0, read by thread r
-        if (OP == OP_DEMUX1) {
-            __syncthreads();
-            SK_T(4);  // plan A
-            // ---- P5b brute-force matcher, one warp per queued record (fasta_demultiplex.rs:126-194):
-            // lanes encode the observed barcode into bit planes with ballots, then split the samples.
+        if (OP == OP_DEMUX1 && M->n_slow) {
+            // ---- P5b brute-force matcher, one warp per queued record (fasta_demultiplex.rs:126-194): used
+            // for the --index route and for sheets the pigeonhole index cannot represent.  Lanes encode
+            // the observed barcode into bit planes with ballots, then split the samples.
+            const WT *planes = (const WT *)p.sheet.planes;
             const uint32_t n_slow = M->n_slow;
             for (uint32_t si = warp; si < n_slow; si += NW) {
                 const uint32_t r = slow_list[si];
                 const uint32_t j = j0 + r * lpr;
                 const uint64_t rec = rec0 + r;
-                const uint32_t L0 = lb(W, j), L1 = lb(W, j + 1);
+                const uint32_t L0 = LB(j);
                 const uint32_t Lb = p.sheet.L;
-                uint32_t bs = 0, bclen = 0, sep = 0, c1h = L1;
+                uint32_t bs = 0, bclen = 0, sep = 0;
                 RecRef ir0{0, 0, 0}, ir1{0, 0, 0};
                 bool ok = true;
                 if (p.n_index) {
@@ -1079,26 +960,12 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
                             bclen += sep + ir1.seq_len;
                         }
                     }
-                } else {
-                    const uint32_t stp = L0 + r_cut0[r];
-                    bs = stp + 4;
-                    // greedy class run from bs+1 (bs itself is a class byte): first non-class offset
-                    uint32_t e = L1;
-                    for (uint32_t base = bs + 1; base < L1; base += 32) {
-                        const uint32_t q = base + lane;
-                        const bool stop = q < L1 && !(sh_lut[win[q]] & 8u);
-                        const uint32_t m = __ballot_sync(0xffffffffu, stop);
-                        if (m) {
-                            e = base + __ffs(m) - 1;
-                            break;
-                        }
+                    if (ok && bclen != Lb) {  // :148-150
+                        if (lane == 0) report_err(st, rec, K_BC_LEN);
+                        ok = false;
                     }
-                    c1h = e;
-                    bclen = e - bs;
-                }
-                if (ok && bclen != Lb) {  // :148-150
-                    if (lane == 0) report_err(st, rec, K_BC_LEN);
-                    ok = false;
+                } else {
+                    bs = L0 + r_cut0[r] + 4;  // class run and length were checked by the planning thread
                 }
                 int sample = -1;
                 if (ok) {
@@ -1108,20 +975,20 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
                         if (q < ir0.seq_len + sep) return (uint8_t)'+';
                         return p.ext_data[1][(uint64_t)ir1.seq_off + (q - ir0.seq_len - sep)];
                     };
-                    WT o0 = 0, o1 = 0, o2 = 0;
+                    WT o0b = 0, o1b = 0, o2b = 0;
                     for (uint32_t base = 0; base < Lb; base += 32) {
                         const uint32_t q = base + lane;
                         const uint32_t code = q < Lb ? (uint32_t)sh_lut[obs(q)] : 0u;
-                        o0 |= (WT)__ballot_sync(0xffffffffu, code & 1u) << base;
-                        o1 |= (WT)__ballot_sync(0xffffffffu, code & 2u) << base;
-                        o2 |= (WT)__ballot_sync(0xffffffffu, code & 4u) << base;
+                        o0b |= (WT)__ballot_sync(0xffffffffu, code & 1u) << base;
+                        o1b |= (WT)__ballot_sync(0xffffffffu, code & 2u) << base;
+                        o2b |= (WT)__ballot_sync(0xffffffffu, code & 4u) << base;
                     }
                     // each lane scans samples lane, lane+32, ...; then merge (lowest, first, last)
                     uint32_t lowest = 0xFFFFFFFFu, best = 0xFFFFFFFFu, last = 0;
                     for (uint32_t s2 = lane; s2 < S; s2 += 32) {
-                        const WT p0 = sh_planes[4 * s2], p1 = sh_planes[4 * s2 + 1], p2 = sh_planes[4 * s2 + 2],
-                                 care = sh_planes[4 * s2 + 3];
-                        const uint32_t d = popcw<WT>(((o0 ^ p0) | (o1 ^ p1) | (o2 ^ p2)) & care);
+                        const WT p0 = planes[4 * s2], p1 = planes[4 * s2 + 1], p2 = planes[4 * s2 + 2],
+                                 care = planes[4 * s2 + 3];
+                        const uint32_t d = popcw<WT>(((o0b ^ p0) | (o1b ^ p1) | (o2b ^ p2)) & care);
                         if (d < lowest) {
                             lowest = d;
                             best = s2;
@@ -1171,8 +1038,9 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
                         }
                     }
                     sample = __shfl_sync(0xffffffffu, sample, 0);
-                    if (sample >= 0) {
-                        // UMI = observed chars where the sheet barcode has 'U' (:200-203), lanes in parallel
+                    if (sample >= 0 && p.n_index) {
+                        // --index route: the UMI bytes come from other streams; park them in the side table
+                        // (the header route gathers them from the window when the record is assembled)
                         const WT um = sh_umask[sample];
                         for (uint32_t base = 0; base < Lb; base += 32) {
                             const uint32_t q = base + lane;
@@ -1185,144 +1053,203 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
                 }
                 if (lane == 0) {
                     r_sample[r] = (int16_t)sample;
-                    r_cut1[r] = (uint16_t)(c1h - L0);
                     r_flags[r] = ok ? (uint8_t)RF_SLOW : (uint8_t)RF_DEAD;
                 }
             }
             __syncthreads();
-            SK_T(5);  // slow matcher
-            // ---- P5c finish the plan of assigned records (fasta_demultiplex.rs:196-212), 4 lanes each
-            for (uint32_t rbase = 0; rbase < nrec; rbase += NT / 4) {
-                const uint32_t r = rbase + ((uint32_t)tid >> 2);
-                if (r >= nrec) continue;
+        }
+        SK_T(5);  // slow matcher
+
+        // ---- P5c finish the plan (one thread per record): kept header pieces, tag, body, output length
+        if (IS_DEMUX) {
+            for (uint32_t r = tid; r < nrec; r += NT) {
                 const int sample = r_sample[r];
                 uint32_t outlen = 0;
                 if (sample >= 0 && !(r_flags[r] & RF_DEAD)) {
                     const uint32_t j = j0 + r * lpr;
                     const uint64_t rec = rec0 + r;
-                    const uint32_t L0 = lb(W, j), L1 = lb(W, j + 1), L2 = lb(W, j + 2), L3 = lb(W, j + 3),
-                                   L4 = lb(W, j + 4);
-                    const uint32_t c0h = p.n_index ? L1 : L0 + r_cut0[r], c1h = p.n_index ? L1 : L0 + r_cut1[r];
-                    const WT um = sh_umask[sample];
-                    const uint32_t ul = popcw<WT>(um);
-                    if (ul && !(r_flags[r] & RF_SLOW) && q4 == 0) {  // queued records: the matcher warp wrote it
-                        WT m = um;
-                        uint32_t t = 0;
-                        while (m) {
-                            const uint32_t q = ffsw<WT>(m);
-                            m &= m - 1;
-                            p.umi[rec * p.sheet.Umax + t++] = win[c0h + 4 + q];
-                        }
+                    const uint32_t L0 = LB(j), L1 = LB(j + 1), L4 = LB(j + 4);
+                    uint32_t alen = r_alen[r], blen = r_blen[r], taglen = r_taglen[r];
+                    if (OP == OP_DEMUX1) {
+                        const uint32_t c0h = p.n_index ? L1 : L0 + r_cut0[r], c1h = p.n_index ? L1 : L0 + r_cut1[r];
+                        header_pieces(win, L0, L1, c0h, c1h, alen, blen);  // drain (:145) + trim_end (:206)
+                        const uint32_t ul = popcw<WT>(sh_umask[sample]);
+                        taglen = ul ? 5 + ul : 0;  // " UMI:" + umi (:207)
+                        r_alen[r] = (uint16_t)alen;
+                        r_blen[r] = (uint16_t)blen;
+                        r_cut1[r] = (uint16_t)(c1h - L0);
+                        r_taglen[r] = (uint16_t)taglen;
                     }
-                    uint32_t alen, blen;
-                    header_pieces(win, L0, L1, c0h, c1h, alen, blen);  // drain (:145) + trim_end (:206)
-                    const uint32_t taglen = ul ? 5 + ul : 0;           // " UMI:" + umi (:207)
-                    uint32_t body = L4 - L1, kk = 0;                   // three lines verbatim (:209-212)
+                    uint32_t body = L4 - L1;  // three lines verbatim (:209-212)
                     uint8_t mode = B_VERBATIM;
                     bool fine = true;
-                    if (p.fused_trim >= 0)
-                        fine = plan_trim_body4(win, gm, q4, L1, L2, L3, L4, p.fused_trim, mode, kk, body);
+                    if (fused) {
+                        mode = r_mode[r];
+                        body = r_body[r];
+                        fine = mode != B_FAIL;
+                    } else {
+                        r_k[r] = 0;
+                    }
                     if (!fine) {
-                        if (q4 == 0) {
-                            report_err(st, rec, K_SEQ_SHORT);
-                            r_sample[r] = -1;
-                        }
+                        report_err(st, rec, K_SEQ_SHORT);
+                        if (OP == OP_DEMUX1) r_sample[r] = -1;
                         mode = B_NONE;
                     } else if (!p.out) {
                         mode = B_NONE;  // dry run: count only (:77-78,:179)
                     } else {
                         outlen = alen + blen + taglen + 1 + body;
                     }
-                    if (q4 == 0) {
-                        r_alen[r] = (uint16_t)alen;
-                        r_blen[r] = (uint16_t)blen;
-                        r_cut1[r] = (uint16_t)(c1h - L0);
-                        r_taglen[r] = (uint16_t)taglen;
-                        r_k[r] = (uint16_t)kk;
-                        r_mode[r] = mode;
-                    }
+                    r_mode[r] = mode;
                 }
-                if (q4 == 0) r_outlen[r] = (uint16_t)outlen;
+                r_outlen[r] = (uint16_t)(outlen > 0xFFFFu ? 0xFFFFu : outlen);
             }
+            if (OP == OP_DEMUX1) {
+                // counters of this thread's records (fasta_demultiplex.rs:169,177), one atomic per warp
+                const uint32_t wt = __reduce_add_sync(0xffffffffu, my_total), wi = __reduce_add_sync(0xffffffffu, my_ident);
+                if (lane == 0 && wt) atomicAdd(&M->cta_total, wt);
+                if (lane == 0 && wi) atomicAdd(&M->cta_ident, wi);
+            }
+            __syncthreads();  // plans of other threads' records are read below
         }
 
         if (HAS_OUT) {
             // ---- P6 layout of the chunk's output
             uint32_t chunk_out = 0;
-            SK_T(6);  // plan (A for non-demux1, C for demux1)
+            SK_T(6);  // plan C
+            if (tid == 0 && store_pending) {  // the previous chunk's TMA store must have read the staging image
+                bulk_wait_read0();
+                store_pending = false;
+            }
             if (ORDERED) {
-                const uint32_t mine = tid < (int)nrec ? r_outlen[tid] : 0;
-                const uint32_t off = block_excl_scan<NT>(mine, M->scratch, chunk_out);
-                if (tid < (int)nrec) r_outoff[tid] = off;
-            } else {
-                for (uint32_t s = tid; s < S; s += NT) hist[s] = 0;  // per-sample byte cursor, ends as the histogram
+                uint32_t run = 0;
+                for (uint32_t rb = 0; rb < nrec; rb += NT) {  // (one pass unless the chunk is very dense)
+                    const uint32_t r = rb + tid;
+                    const uint32_t mine = r < nrec ? r_outlen[r] : 0;
+                    uint32_t t2;
+                    const uint32_t off = block_excl_scan<NT>(mine, M->scratch, flip, t2);
+                    if (r < nrec) r_outoff[r] = (uint16_t)(run + off > 0xFFFFu ? 0xFFFFu : run + off);
+                    run += t2;
+                }
+                chunk_out = run;
+            } else if (nrec <= (uint32_t)LAYOUT_FAST_MAXREC && nrec <= (uint32_t)NT) {
+                // Sample-major inside the chunk, input order inside a sample.  Every record sets its bit
+                // in its sample's 128-bit mask; the lowest record of a sample (the leader) owns the
+                // group, members add up the lengths of the peers before them.
+                const uint32_t r = tid;
+                int sm = -1;
+                uint32_t len = 0;
+                if (r < nrec) {
+                    sm = r_sample[r];
+                    len = r_outlen[r];
+                    if (sm < 0 || !len) sm = -1, len = 0;
+                }
+                if (sm >= 0) atomicOr(&masks[4 * sm + (r >> 5)], 1u << (r & 31u));
                 __syncthreads();
-                // Stable order inside a sample: warps take their 32 records in turn; lanes holding the same
-                // sample (match.any) rank themselves by lane, the highest one advances the sample's cursor.
-                const uint32_t nwu = (nrec + 31) / 32;
-                for (uint32_t w = 0; w < nwu; w++) {
-                    if ((uint32_t)warp == w) {
-                        const uint32_t r = w * 32 + lane;
-                        int sm = -1;
-                        uint32_t len = 0;
-                        if (r < nrec) {
-                            sm = r_sample[r];
-                            len = r_outlen[r];
-                            if (sm < 0 || !len) sm = -1, len = 0;
-                        }
-                        const unsigned peers = __match_any_sync(0xffffffffu, sm);
-                        uint32_t pre = 0;
-                        if (sm >= 0) {
-                            unsigned lower = peers & ((1u << lane) - 1u);
-                            while (lower) {
-                                const int l = __ffs(lower) - 1;
-                                lower &= lower - 1;
-                                pre += r_outlen[w * 32 + l];
+                uint32_t within = 0, gt = 0, lead = r;
+                bool leader = false;
+                if (sm >= 0) {
+                    const uint4 mv = *(const uint4 *)&masks[4 * sm];
+                    const uint32_t wi = r >> 5, bit = 1u << (r & 31u);
+                    uint32_t lo[4], hi[4];
+                    const uint32_t mw[4] = {mv.x, mv.y, mv.z, mv.w};
+#pragma unroll
+                    for (int w = 0; w < 4; w++) {
+                        lo[w] = (uint32_t)w < wi ? mw[w] : ((uint32_t)w == wi ? mw[w] & (bit - 1u) : 0u);
+                        hi[w] = (uint32_t)w > wi ? mw[w] : ((uint32_t)w == wi ? mw[w] & ~(bit - 1u) & ~bit : 0u);
+                    }
+                    leader = (lo[0] | lo[1] | lo[2] | lo[3]) == 0u;
+                    if (!leader) {
+                        bool first = true;
+#pragma unroll
+                        for (int w = 0; w < 4; w++) {
+                            uint32_t x = lo[w];
+                            while (x) {
+                                const uint32_t q = 32u * w + (uint32_t)__ffs(x) - 1u;
+                                x &= x - 1;
+                                if (first) lead = q, first = false;
+                                within += r_outlen[q];
                             }
                         }
-                        const int hi = 31 - __clz(peers);
-                        uint32_t base = 0;
-                        if (lane == hi && sm >= 0) {
-                            base = hist[sm];
-                            hist[sm] = base + pre + len;
-                        }
-                        base = __shfl_sync(0xffffffffu, base, hi);
-                        if (r < nrec) r_outoff[r] = base + pre;
-                    }
-                    __syncthreads();
-                }
-                // sample-major bases: exclusive scan of hist over S by one warp (contiguous runs per lane)
-                if (warp == 0) {
-                    const uint32_t per = (S + 31) / 32;
-                    const uint32_t s0 = lane * per < S ? lane * per : S, s1 = s0 + per < S ? s0 + per : S;
-                    uint32_t sum = 0;
-                    for (uint32_t s = s0; s < s1; s++) sum += hist[s];
-                    uint32_t inc = sum;
+                    } else {
+                        gt = len;
 #pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o);
-                        if (lane >= o) inc += y;
+                        for (int w = 0; w < 4; w++) {
+                            uint32_t x = hi[w];
+                            while (x) {
+                                const uint32_t q = 32u * w + (uint32_t)__ffs(x) - 1u;
+                                x &= x - 1;
+                                gt += r_outlen[q];
+                            }
+                        }
                     }
-                    uint32_t run = inc - sum;
-                    for (uint32_t s = s0; s < s1; s++) {
-                        sbase[s] = run;
-                        run += hist[s];
+                }
+                // exclusive scan over the leaders (in record order) of group bytes and group count
+                uint32_t t2;
+                const uint32_t sc = block_excl_scan<NT>(gt | (leader ? 1u << 24 : 0u), M->scratch, flip, t2);
+                chunk_out = t2 & 0xFFFFFFu;
+                const uint32_t n_groups = t2 >> 24;
+                if (leader) {
+                    gbase_sm[r] = sc & 0xFFFFFFu;
+                    *(uint4 *)&masks[4 * sm] = make_uint4(0, 0, 0, 0);  // every member has read it (barrier in the scan)
+                    if (p.out) {
+                        Group g;
+                        g.sample = (uint16_t)sm;
+                        g.len = (uint16_t)gt;
+                        p.groups[rec0 + (sc >> 24)] = g;
                     }
-                    if (lane == 31) M->chunk_out = inc;
+                }
+                if (tid == 0) M->n_groups = n_groups;
+                __syncthreads();
+                if (sm >= 0) r_outoff[r] = (uint16_t)(gbase_sm[lead] + within);
+            } else {
+                // Very dense chunk: thread 0 walks the records (masks[4*s] = group id + 1, masks[4*s+1] =
+                // bytes of the group so far, r_aux[g] = group total, r_body[r] = group of record r).
+                if (tid == 0) {
+                    uint32_t ng = 0;
+                    for (uint32_t r = 0; r < nrec; r++) {
+                        const int sm = r_sample[r];
+                        const uint32_t len = r_outlen[r];
+                        if (sm < 0 || !len) continue;
+                        uint32_t g = masks[4 * sm];
+                        if (!g) {
+                            g = ++ng;
+                            masks[4 * sm] = g;
+                            masks[4 * sm + 1] = 0;
+                            r_aux[g - 1] = 0;
+                        }
+                        r_outoff[r] = (uint16_t)masks[4 * sm + 1];
+                        masks[4 * sm + 1] += len;
+                        r_aux[g - 1] += len;
+                        r_body[r] = (uint16_t)(g - 1);
+                    }
+                    // group bases in order of first appearance; reset the per-sample words
+                    uint32_t run = 0, gi = 0;
+                    for (uint32_t r = 0; r < nrec && gi < ng; r++) {
+                        const int sm = r_sample[r];
+                        if (sm < 0 || !r_outlen[r] || masks[4 * sm] != gi + 1) continue;
+                        const uint32_t tot2 = r_aux[gi];
+                        if (p.out) {
+                            Group g;
+                            g.sample = (uint16_t)sm;
+                            g.len = (uint16_t)tot2;
+                            p.groups[rec0 + gi] = g;
+                        }
+                        r_aux[gi] = run;
+                        run += tot2;
+                        gi++;
+                    }
+                    for (uint32_t r = 0; r < nrec; r++) {
+                        const int sm = r_sample[r];
+                        if (sm >= 0) masks[4 * sm] = 0, masks[4 * sm + 1] = 0;
+                    }
+                    M->chunk_out = run;
+                    M->n_groups = ng;
                 }
                 __syncthreads();
                 chunk_out = M->chunk_out;
-                if (tid < (int)nrec) {
-                    const int sm = r_sample[tid];
-                    if (sm >= 0 && r_outlen[tid]) r_outoff[tid] += sbase[sm];
-                }
-                // slice table row (u16 lengths)
-                if (p.out) {
-                    for (uint32_t s = tid; s < S; s += NT) {
-                        const uint32_t h = hist[s];
-                        if (h > 0xFFFFu) report_err(st, rec0, K_OUT_OVERFLOW);
-                        p.lens[(uint64_t)c * S + s] = (uint16_t)h;
-                    }
+                for (uint32_t r = tid; r < nrec; r += NT) {
+                    const int sm = r_sample[r];
+                    if (sm >= 0 && r_outlen[r]) r_outoff[r] = (uint16_t)(r_outoff[r] + r_aux[r_body[r]]);
                 }
             }
 
@@ -1343,7 +1270,11 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
                 unsigned long long base = 0;
                 if (p.out) {
                     base = atomicAdd(&st->out_cursor, (unsigned long long)((chunk_out + 15u) & ~15u));
-                    p.chunk_base[c] = base;
+                    ChunkRow row;
+                    row.base = base;
+                    row.first_group = (uint32_t)rec0;
+                    row.n_groups = M->n_groups;
+                    p.rows[c] = row;
                     if (chunk_out) atomicAdd(&st->out_bytes, (unsigned long long)chunk_out);
                 }
                 M->out_base = base;
@@ -1352,17 +1283,24 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
             SK_T(8);  // reserve (look-back on output bytes / atomic)
             const uint64_t out_base = M->out_base;
             bool writable = p.out != nullptr && chunk_out > 0;
-            if (writable && out_base + chunk_out > p.out_cap) {
+            if (writable && out_base + ((chunk_out + 15u) & ~15u) > p.out_cap) {
+                if (tid == 0) report_err(st, rec0, K_OUT_OVERFLOW);
+                writable = false;
+            }
+            if (chunk_out > 0xFFFFu) {  // offsets are 16-bit
                 if (tid == 0) report_err(st, rec0, K_OUT_OVERFLOW);
                 writable = false;
             }
 
+            bool staged_now = false;
+            uint32_t shift = 0;
             if (writable) {
                 // ---- P8 assemble.  Fast path: build the chunk's output image in shared memory, aligned
                 // like its global destination; 4 lanes per record, each copying whole pieces word-wise.
-                const uint32_t shift = (uint32_t)(out_base & 15u);
-                const bool staged = chunk_out <= (uint32_t)Cfg::STAGE;
+                shift = (uint32_t)(out_base & 15u);
+                const bool staged = shift + chunk_out <= (uint32_t)Cfg::STAGE;
                 if (staged) {
+                    staged_now = true;
                     uint8_t *sb = stage + shift;
                     const uint32_t q4 = tid & 3;
                     for (uint32_t r0 = 0; r0 < nrec; r0 += NT / 4) {
@@ -1374,7 +1312,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
                         const uint32_t outlen = r < nrec ? r_outlen[r] : 0;
                         if (outlen) {
                             const uint32_t j = j0 + r * lpr;
-                            const uint32_t L0 = lb(W, j), L1 = lb(W, j + 1);
+                            const uint32_t L0 = LB(j), L1 = LB(j + 1);
                             uint8_t *d0 = sb + r_outoff[r];
                             const uint32_t kk = r_k[r];
                             const uint8_t mode = r_mode[r];
@@ -1397,7 +1335,24 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
                                             bcopy(d + 4, p.ext_data[0] + r_aux[r], taglen - 4);
                                         } else {
                                             d[0] = ' '; d[1] = 'U'; d[2] = 'M'; d[3] = 'I'; d[4] = ':';
-                                            bcopy(d + 5, p.umi + (rec0 + r) * p.sheet.Umax, taglen - 5);
+                                            uint8_t *gu = p.umi + (rec0 + r) * p.sheet.Umax;
+                                            if (OP == OP_DEMUX1 && !p.n_index) {
+                                                // UMI = observed chars where the sheet barcode has 'U' (:200-203);
+                                                // also parked in the side table for mate 2
+                                                const uint8_t *ob = win + L0 + r_cut0[r] + 4;
+                                                WT m = sh_umask[r_sample[r]];
+                                                uint32_t t = 0;
+                                                while (m) {
+                                                    const uint32_t q = ffsw<WT>(m);
+                                                    m &= m - 1;
+                                                    const uint8_t ch = ob[q];
+                                                    d[5 + t] = ch;
+                                                    gu[t] = ch;
+                                                    t++;
+                                                }
+                                            } else {
+                                                bcopy(d + 5, gu, taglen - 5);
+                                            }
                                         }
                                         d += taglen;
                                     }
@@ -1406,13 +1361,13 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
                             }
                             uint8_t *db = d0 + hlen;  // body destination
                             if (mode == B_VERBATIM) {
-                                const uint32_t Lend = lb(W, j + lpr);
+                                const uint32_t Lend = LB(j + lpr);
                                 const uint32_t blen2 = Lend - L1, half = (blen2 / 2 + 3) & ~3u;
                                 const uint32_t h1 = half < blen2 ? half : blen2;
                                 if (q4 == 1) { jd = db; js = win + L1; jl = h1; }
                                 if (q4 == 2) { jd = db + h1; js = win + L1 + h1; jl = blen2 - h1; }
                             } else if (mode == B_TRIM) {
-                                const uint32_t L3 = lb(W, j + 3);
+                                const uint32_t L3 = LB(j + 3);
                                 if (q4 == 1) { jd = db; js = win + L1; jl = kk; }
                                 if (q4 == 2) { jd = db + kk + 3; js = win + L3; jl = kk; }
                                 if (q4 == 3) {
@@ -1426,7 +1381,7 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
                                     d[0] = 'N'; d[1] = '\n'; d[2] = '+'; d[3] = '\n'; d[4] = '!'; d[5] = '\n';
                                 }
                             } else if (mode == B_MASK) {
-                                const uint32_t L3 = lb(W, j + 3);
+                                const uint32_t L3 = LB(j + 3);
                                 if (q4 == 1) {
                                     const uint32_t minq = p.min_baseq;
                                     for (uint32_t i = 0; i < kk; i++) {
@@ -1444,17 +1399,14 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
                         }
                         tcopy(jd, js, jl);  // one call site: all lanes copy their piece together
                     }
+                    fence_proxy_async();  // staging writes -> visible to the TMA store issued after the barrier
                     SK_T(9);  // assemble
-                    // ---- P9 is deferred (see flush_stage): the barrier that ends this chunk orders the
-                    // staging writes before the loads of the flush.
-                    pend_shift = shift;
-                    pend_span = shift + chunk_out;
-                    pend_g16 = p.out + (out_base - shift);
                 } else {
                     // Oversized output (pathological growth): one thread per record, bytes straight to global.
-                    if (tid < (int)nrec && r_outlen[tid]) {
-                        const uint32_t r = tid, j = j0 + r * lpr;
-                        const uint32_t L0 = lb(W, j), L1 = lb(W, j + 1), L3 = lb(W, j + 3);
+                    for (uint32_t r = tid; r < nrec; r += NT) {
+                        if (!r_outlen[r]) continue;
+                        const uint32_t j = j0 + r * lpr;
+                        const uint32_t L0 = LB(j), L1 = LB(j + 1), L3 = LB(j + 3);
                         const uint32_t kk = r_k[r];
                         const uint8_t mode = r_mode[r];
                         uint8_t *d = p.out + out_base + r_outoff[r];
@@ -1473,14 +1425,25 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
                                     bcopy(d + 4, p.ext_data[0] + r_aux[r], taglen - 4);
                                 } else {
                                     bcopy(d, (const uint8_t *)" UMI:", 5);
-                                    bcopy(d + 5, p.umi + (rec0 + r) * p.sheet.Umax, taglen - 5);
+                                    uint8_t *gu = p.umi + (rec0 + r) * p.sheet.Umax;
+                                    if (OP == OP_DEMUX1 && !p.n_index) {
+                                        const uint8_t *ob = win + L0 + r_cut0[r] + 4;
+                                        WT m = sh_umask[r_sample[r]];
+                                        uint32_t t = 0;
+                                        while (m) {
+                                            const uint32_t q = ffsw<WT>(m);
+                                            m &= m - 1;
+                                            gu[t++] = ob[q];
+                                        }
+                                    }
+                                    bcopy(d + 5, gu, taglen - 5);
                                 }
                                 d += taglen;
                             }
                             *d++ = '\n';
                         }
                         if (mode == B_VERBATIM) {
-                            bcopy(d, win + L1, lb(W, j + lpr) - L1);
+                            bcopy(d, win + L1, LB(j + lpr) - L1);
                         } else if (mode == B_TRIM) {
                             bcopy(d, win + L1, kk);
                             bcopy(d + kk, (const uint8_t *)"\n+\n", 3);
@@ -1500,20 +1463,79 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
                     }
                 }
             }
-        }
+            // UMI side table for mate 2 of assigned records whose output was not assembled here
+            if (OP == OP_DEMUX1 && !p.n_index && !writable && p.sheet.Umax) {
+                for (uint32_t r = tid; r < nrec; r += NT) {
+                    const int sm = r_sample[r];
+                    if (sm < 0 || (r_flags[r] & RF_DEAD)) continue;
+                    const uint32_t L0 = LB(j0 + r * lpr);
+                    const uint8_t *ob = win + L0 + r_cut0[r] + 4;
+                    uint8_t *gu = p.umi + (rec0 + r) * p.sheet.Umax;
+                    WT m = sh_umask[sm];
+                    uint32_t t = 0;
+                    while (m) {
+                        const uint32_t q = ffsw<WT>(m);
+                        m &= m - 1;
+                        gu[t++] = ob[q];
+                    }
+                }
+            }
 
-        // ---- P10 per-record side tables
-        if (OP == OP_DEMUX1 && tid < (int)nrec) p.assign[rec0 + tid] = r_sample[tid];
-        if (tid == 0) {
-            // Take the next ticket only now: a ticket held while another chunk is still being processed
-            // stalls the look-back of every later chunk (measured: +15 % step time).
-            M->chunk = atomicAdd(&st->ticket, 1u);
-            M->n_slow = 0;
+            // ---- P10 per-record side tables, next ticket
+            if (OP == OP_DEMUX1)
+                for (uint32_t r = tid; r < nrec; r += NT) p.assign[rec0 + r] = r_sample[r];
+            if (tid == 0) {
+                // Take the next ticket only now: a ticket held while another chunk is still being processed
+                // stalls the look-back of every later chunk.
+                M->chunk = atomicAdd(&st->ticket, 1u);
+                M->n_slow = 0;
+            }
+            __syncthreads();  // window, staging and record arrays are reused by the next chunk
+
+            // ---- P9 store: one TMA bulk copy of the staged image (16-byte units); the ragged first and
+            // last bytes of an ordered chunk belong to 16-byte units shared with its neighbours.
+            if (staged_now) {
+                const uint32_t span = shift + chunk_out;  // image occupies stage[shift, span)
+                uint8_t *g16 = p.out + (out_base - shift);
+                if (ORDERED) {
+                    const uint32_t a = shift ? 16u : 0u;   // first whole unit
+                    const uint32_t b2 = span & ~15u;       // end of the last whole unit
+                    if (b2 > a) {
+                        if (tid == 0) {
+                            bulk_s2g(g16 + a, stage + a, b2 - a);
+                            bulk_commit();
+                            store_pending = true;
+                        }
+                        if (tid < 32) {
+                            const uint32_t t = (uint32_t)tid;
+                            if (t < 16u) {
+                                if (t >= shift && t < a && t < span) g16[t] = stage[t];
+                            } else {
+                                const uint32_t o = b2 + (t - 16u);
+                                if (o < span) g16[o] = stage[o];
+                            }
+                        }
+                        // the byte stores above read the staging image with generic loads; they finish
+                        // before the next chunk's assembly because of the barriers in between
+                    } else {
+                        for (uint32_t o = shift + tid; o < span; o += NT) g16[o] = stage[o];
+                    }
+                } else if (tid == 0) {
+                    bulk_s2g(g16, stage, (span + 15u) & ~15u);  // demux chunks own whole 16-byte units
+                    bulk_commit();
+                    store_pending = true;
+                }
+            }
+            SK_T(10);  // store + tables
+        } else {
+            if (tid == 0) {
+                M->chunk = atomicAdd(&st->ticket, 1u);
+                M->n_slow = 0;
+            }
+            __syncthreads();
         }
-        __syncthreads();  // window, staging and record arrays are reused by the next chunk
-        SK_T(10);  // store + tables
     }
-    if (pend_span) flush_stage();
+    if (tid == 0 && store_pending) bulk_wait_read0();  // shared memory must outlive the last TMA store
 #ifdef SK_PHASE_TIMING
     if (tid == 0)
         for (int i = 0; i < 16; i++)
@@ -1531,22 +1553,15 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
             if (M->cta_slow) atomicAdd(&st->n_slow, M->cta_slow);
         }
     }
+#undef LB
 }
 
 // ------------------------------------------------------------------------------------------------
 // launcher
 // ------------------------------------------------------------------------------------------------
-template <class Cfg>
-static uint32_t smem_for(int op, const KParams &p, bool wide) {
-    const bool demux = (op == OP_DEMUX1 || op == OP_DEMUX2);
-    const bool d1 = op == OP_DEMUX1;
-    return smem_layout<Cfg>(demux ? p.sheet.S : 0u, wide ? 1u : 0u, d1 ? p.sheet.fast.n_classes : 0u,
-                            d1 ? p.sheet.fast.tsize : 0u)
-        .total;
-}
-int chunk_kernel_smem_bytes(int cfg, uint32_t S, uint32_t wide, uint32_t n_classes, uint32_t tsize) {
-    return cfg == CfgSmall::ID ? (int)smem_layout<CfgSmall>(S, wide, n_classes, tsize).total
-                               : (int)smem_layout<CfgBig>(S, wide, n_classes, tsize).total;
+int chunk_kernel_smem_bytes(int cfg, uint32_t S, uint32_t wide, uint32_t n_classes, uint32_t nwp) {
+    return cfg == CfgB::ID ? (int)smem_layout<CfgB>(S, wide, n_classes, nwp).total
+                           : (int)smem_layout<CfgA>(S, wide, n_classes, nwp).total;
 }
 
 template <class Cfg, int OP, typename WT>
@@ -1556,8 +1571,8 @@ static int launch_one(const KParams &p_in, int sm_count, cudaStream_t stream, co
     {
         const bool demux = (OP == OP_DEMUX1 || OP == OP_DEMUX2);
         const bool d1 = OP == OP_DEMUX1;
-        p.sl = smem_layout<Cfg>(demux ? p.sheet.S : 0u, sizeof(WT) == 8 ? 1u : 0u, d1 ? p.sheet.fast.n_classes : 0u,
-                                d1 ? p.sheet.fast.tsize : 0u);
+        p.sl = smem_layout<Cfg>(demux ? p.sheet.S : 0u, sizeof(WT) == 8 ? 1u : 0u, d1 ? p.sheet.hidx.n_classes : 0u,
+                                d1 ? p.sheet.hidx.nwp : 0u);
     }
     const int smem = (int)p.sl.total;
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -1604,8 +1619,8 @@ static int launch_cfg(int op, const KParams &p, int sm_count, cudaStream_t strea
 
 int launch_chunk_kernel(int cfg, int op, const KParams &p, int sm_count, void *stream_, const char **err) {
     cudaStream_t stream = (cudaStream_t)stream_;
-    return cfg == CfgSmall::ID ? launch_cfg<CfgSmall>(op, p, sm_count, stream, err)
-                               : launch_cfg<CfgBig>(op, p, sm_count, stream, err);
+    return cfg == CfgB::ID ? launch_cfg<CfgB>(op, p, sm_count, stream, err)
+                           : launch_cfg<CfgA>(op, p, sm_count, stream, err);
 }
 
 }  // namespace sk

@@ -216,15 +216,15 @@ class Engine:
             n = res.out_extent[mate]
             out = self.fetch_out(mate, n)
             nc = res.n_chunks[mate]
-            base = (C.c_uint64 * max(nc, 1))()
-            lens = (C.c_uint16 * max(nc * S, 1))()
-            _check(self.ctx, self.lib.sk_download_demux_tables(self.ctx, 0, mate, base, lens), "tables")
+            rows = (L.ChunkRow * max(nc, 1))()
+            groups = (L.Group * max(res.n_records, 1))()
+            _check(self.ctx, self.lib.sk_download_demux_tables(self.ctx, 0, mate, rows, groups, res.n_records), "tables")
             self.wait()
             outbuf = C.create_string_buffer(out, max(len(out), 1))
             for s, name in enumerate(names):
-                need = self.lib.sk_demux_gather(outbuf, base, lens, nc, S, s, None, 0)
+                need = self.lib.sk_demux_gather(outbuf, rows, groups, nc, s, None, 0)
                 dst = C.create_string_buffer(max(need, 1))
-                self.lib.sk_demux_gather(outbuf, base, lens, nc, S, s, dst, need)
+                self.lib.sk_demux_gather(outbuf, rows, groups, nc, s, dst, need)
                 key = (name + (b"_%d.fq.gz" % (mate + 1) if paired else b".fq.gz")).decode()
                 files[key] = dst.raw[:need]
         return files

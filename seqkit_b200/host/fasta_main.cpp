@@ -687,12 +687,12 @@ static int run_demultiplex(int argc, char **argv) {
     }
     const uint32_t use_index = (index1.empty() ? 0u : 1u) | (index2.empty() ? 0u : 2u);
     const uint32_t max_chunks = sk_max_chunks(g.ctx);
-    uint64_t *base_h[Gpu::NSLOT][2];
-    uint16_t *lens_h[Gpu::NSLOT][2];
+    sk_chunk_row *rows_h[Gpu::NSLOT][2];
+    sk_group *groups_h[Gpu::NSLOT][2];
     for (int s = 0; s < Gpu::NSLOT; s++)
         for (int m = 0; m < (paired ? 2 : 1); m++) {
-            base_h[s][m] = (uint64_t *)g.pinned((uint64_t)max_chunks * 8);
-            lens_h[s][m] = (uint16_t *)g.pinned((uint64_t)max_chunks * S * 2);
+            rows_h[s][m] = (sk_chunk_row *)g.pinned((uint64_t)max_chunks * sizeof(sk_chunk_row));
+            groups_h[s][m] = (sk_group *)g.pinned(g.max_records * sizeof(sk_group));
         }
     std::vector<uint64_t> counts_h(S + 2);
     std::vector<sk_event> events;
@@ -843,22 +843,34 @@ static int run_demultiplex(int argc, char **argv) {
         for (int m = 0; m < nm; m++) {
             if (r.out_extent[m] > g.out_cap) refuse("output larger than the slot capacity");
             if (r.out_extent[m]) g.ck(sk_download_out(g.ctx, slot, m, g.out_h[slot][m], r.out_extent[m]), "sk_download_out");
-            g.ck(sk_download_demux_tables(g.ctx, slot, m, base_h[slot][m], lens_h[slot][m]), "sk_download_demux_tables");
+            g.ck(sk_download_demux_tables(g.ctx, slot, m, rows_h[slot][m], groups_h[slot][m], r.n_records),
+                 "sk_download_demux_tables");
         }
         g.ck(sk_wait(g.ctx, slot, nullptr), "sk_wait");
-        // offs[c*S+s] = start of sample s's slice inside chunk c (exclusive prefix over the row)
-        std::vector<uint32_t> offs;
+        // Bucket the groups by sample (one pass over the chunk rows), then let the writer threads append
+        // each sample's groups, in chunk order, to its gzip child.
+        struct Piece {
+            uint64_t off;
+            uint32_t len;
+        };
+        std::vector<uint32_t> cnt(S + 1);
+        std::vector<Piece> pieces;
         for (int m = 0; m < nm; m++) {
             const uint32_t nc = r.n_chunks[m];
-            offs.assign((size_t)nc * S, 0);
-            const uint16_t *lens = lens_h[slot][m];
+            const sk_chunk_row *rows = rows_h[slot][m];
+            const sk_group *groups = groups_h[slot][m];
+            std::fill(cnt.begin(), cnt.end(), 0u);
+            for (uint32_t c = 0; c < nc; c++)
+                for (uint32_t k = 0; k < rows[c].n_groups; k++) cnt[groups[rows[c].first_group + k].sample + 1]++;
+            for (uint32_t s = 0; s < S; s++) cnt[s + 1] += cnt[s];
+            pieces.resize(cnt[S]);
+            std::vector<uint32_t> cur(cnt.begin(), cnt.end() - 1);
             for (uint32_t c = 0; c < nc; c++) {
-                uint32_t run = 0;
-                const uint16_t *row = lens + (size_t)c * S;
-                uint32_t *o = offs.data() + (size_t)c * S;
-                for (uint32_t s = 0; s < S; s++) {
-                    o[s] = run;
-                    run += row[s];
+                uint64_t off = rows[c].base;
+                for (uint32_t k = 0; k < rows[c].n_groups; k++) {
+                    const sk_group &gr = groups[rows[c].first_group + k];
+                    pieces[cur[gr.sample]++] = Piece{off, gr.len};
+                    off += gr.len;
                 }
             }
             std::atomic<uint32_t> next{0};
@@ -868,11 +880,9 @@ static int run_demultiplex(int argc, char **argv) {
                     const uint32_t s = next.fetch_add(1);
                     if (s >= S) break;
                     tmp.clear();
-                    for (uint32_t c = 0; c < nc; c++) {
-                        const uint32_t len = lens[(size_t)c * S + s];
-                        if (!len) continue;
-                        const uint8_t *src = g.out_h[slot][m] + base_h[slot][m][c] + offs[(size_t)c * S + s];
-                        tmp.insert(tmp.end(), src, src + len);
+                    for (uint32_t k = cnt[s]; k < cnt[s + 1]; k++) {
+                        const uint8_t *src = g.out_h[slot][m] + pieces[k].off;
+                        tmp.insert(tmp.end(), src, src + pieces[k].len);
                     }
                     if (!tmp.empty()) write_all(samples[s]->out[m].fd, tmp.data(), tmp.size());
                 }

@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     lib = L.lib()
     for name in _declared_symbols():
         assert hasattr(lib, name), name
-    assert lib.sk_abi_version() == 1
+    assert lib.sk_abi_version() == 2
 
 
 def test_struct_sizes_match_header():

@@ -87,8 +87,8 @@ def test_stream_ops(oracle_bin, tmp_path, op):
 
 
 def test_stream_ops_multi_batch(oracle_bin, tmp_path):
-    data = G.clean_fastq(11, 12000, qual_style="mix")  # ~3.5 MB -> several 1 MiB batches, two slots in flight
-    assert len(data) > 3 << 20
+    data = G.clean_fastq(11, 12000, qual_style="mix")  # ~2.5 MB -> several 1 MiB batches, two slots in flight
+    assert len(data) > 2 << 20
     for op in ("trim", "mask"):
         both(oracle_bin, tmp_path, [op, "by", "quality", "in.fq", "20"], {"in.fq": data}, env={"SK_BATCH_MB": "1"}, ctx=op)
     bad = data + b"Xbroken\nACGT\n+\nIIII\n" + G.clean_fastq(12, 10)  # fatal in the last batch: earlier output stays
@@ -147,8 +147,8 @@ def test_demultiplex(oracle_bin, tmp_path):
 def test_demultiplex_multi_batch_gz_and_errors(oracle_bin, tmp_path):
     sheet, bcs = G.make_sheet(5, 48, 20, umi=8, dual=True)
     r1, r2 = G.clean_pairs(77, 9000, bcs, p_sub=0.03, p_random=0.05)
-    files = {"sheet.tsv": sheet, "r1.fq.gz": r1, "r2.fq.gz": r2}
-    ours, out_files = both(oracle_bin, tmp_path, ["demultiplex", "sheet.tsv", "r1.fq.gz", "r2.fq.gz"], files,
+    files = {"sheet.tsv": sheet, "r1.fastq.gz": r1, "r2.fastq.gz": r2}
+    ours, out_files = both(oracle_bin, tmp_path, ["demultiplex", "sheet.tsv", "r1.fastq.gz", "r2.fastq.gz"], files,
                            env={"SK_BATCH_MB": "1"}, ctx="multi-batch")
     assert len(out_files) == 96 and sum(len(v) for v in out_files.values()) > 1 << 20
     # a read without a BC field in a later batch: everything before it is written, then the reference's error
