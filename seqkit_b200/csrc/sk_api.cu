@@ -53,6 +53,12 @@ struct Slot {
     uint32_t launches = 0;
     bool pass_ran[SK_N_INPUTS] = {false, false, false, false};
     cudaEvent_t ev[SK_N_INPUTS][2] = {};
+    // the request behind last_op, so that sk_wait can re-run it on the general engine
+    bool used_fast = false;
+    bool reran_general = false;
+    uint32_t req_min_baseq = 0;
+    uint64_t req_rec_limit = 0;
+    sk_demux_opts req_opts{};
 };
 
 struct sk_ctx {
@@ -74,6 +80,10 @@ struct sk_ctx {
     uint32_t *d_hcls = nullptr, *d_skeys = nullptr;
     uint2 *d_htab = nullptr;
     uint16_t *d_hcand = nullptr;
+    uint2 *d_ftab = nullptr;      // FastIdx
+    uint16_t *d_fnext = nullptr;
+    bool fast_sheet = false;  // the sheet's FastIdx is usable
+    bool fast = true;   // lean engine (sk_fast.cu) for trim / mask / header-route demultiplex; SK_NO_FAST=1 disables
     int cfg = 0;  // chunk-engine geometry: 0 = CfgA (16 KiB chunks, 4 warps), 1 = CfgB (32 KiB chunks, 8 warps)
 };
 
@@ -86,8 +96,8 @@ struct sk_ctx {
         }                                                                                \
     } while (0)
 
-static uint32_t chunks_of(const sk_ctx *ctx, uint64_t n) {
-    const uint64_t ch = (uint64_t)cfg_chunk_bytes(ctx->cfg);
+static uint32_t chunks_of(const sk_ctx *ctx, uint64_t n, bool fast = false) {
+    const uint64_t ch = fast ? (uint64_t)fast_chunk_bytes() : (uint64_t)cfg_chunk_bytes(ctx->cfg);
     return (uint32_t)((n + ch - 1) / ch);
 }
 
@@ -132,6 +142,8 @@ extern "C" void sk_ctx_destroy(sk_ctx *ctx) {
     cudaFree(ctx->d_skeys);
     cudaFree(ctx->d_htab);
     cudaFree(ctx->d_hcand);
+    cudaFree(ctx->d_ftab);
+    cudaFree(ctx->d_fnext);
     delete ctx;
 }
 
@@ -156,6 +168,7 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
     ctx->lim = *lim;
     ctx->cfg = lim->reserved == 2 ? 1 : 0;  // reserved: 0/1 = 16 KiB chunks (default), 2 = 32 KiB chunks
     if (const char *e = getenv("SK_CFG")) ctx->cfg = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("SK_NO_FAST")) ctx->fast = atoi(e) == 0;
     auto fail = [&](int code) {
         g_create_error = ctx->err;
         sk_ctx_destroy(ctx);
@@ -179,7 +192,7 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     const uint64_t B = (lim->max_stream_bytes + 15) & ~15ull;
     const uint64_t R = lim->max_records;
-    ctx->max_chunks = chunks_of(ctx, B) + 1;
+    ctx->max_chunks = std::max(chunks_of(ctx, B, false), chunks_of(ctx, B, true)) + 1;
     const uint64_t out_cap = B + R * 72 + (uint64_t)ctx->max_chunks * 16 + 4096;
     const uint32_t Smax = lim->max_samples;
     ctx->slots.resize(lim->n_slots);
@@ -437,6 +450,32 @@ extern "C" int sk_set_sheet(sk_ctx *ctx, const uint8_t *barcodes, uint32_t S, ui
     }
     if (hcand.size() > 0xFFFFu) h_classes = 0;  // list offsets are 16-bit
     if (hcand.empty()) hcand.push_back(0);
+    // the same index for the lean engine (FastIdx): same slots, tag = the slot hash before mixing, first
+    // sample in the slot, the rest chained.  Tags must be unique inside a table so that a probe can stop
+    // at the first tag match; otherwise the lean engine is not used for this sheet.
+    std::vector<uint2> ftab(htab.size(), make_uint2(0u, 0u));
+    std::vector<uint16_t> fnext((size_t)std::max(h_classes, 1u) * 2 * std::max(S, 1u), (uint16_t)0xFFFFu);
+    bool fast_ok = h_classes != 0;
+    for (uint32_t c = 0; c < h_classes && fast_ok; c++)
+        for (uint32_t h = 0; h < 2 && fast_ok; h++) {
+            const uint32_t t = c * 2 + h;
+            const uint32_t *hm = &hcls[(size_t)c * HIDX_CLS_ROWS * nwp] + (1 + 3 * h) * nwp;
+            std::vector<uint32_t> tags;
+            for (uint32_t sl = 0; sl < tsize; sl++) {
+                const uint2 e = htab[(size_t)t * tsize + sl];
+                const uint32_t count = e.y >> 16, start = e.y & 0xFFFFu;
+                if (!count) continue;
+                const uint32_t s0 = hcand[start];
+                uint32_t h1 = 0;
+                for (uint32_t w = 0; w < nw; w++) h1 += (skeys[(size_t)s0 * nwp + w] & hm[w]) * hm[nwp + w];
+                tags.push_back(h1);
+                ftab[(size_t)t * tsize + sl] = make_uint2(h1, (s0 + 1u) | (count > 1 ? 1u << 16 : 0u));
+                for (uint32_t i = 0; i + 1 < count; i++) fnext[(size_t)t * S + hcand[start + i]] = hcand[start + i + 1];
+            }
+            std::sort(tags.begin(), tags.end());
+            if (std::adjacent_find(tags.begin(), tags.end()) != tags.end()) fast_ok = false;
+        }
+    ctx->fast_sheet = fast_ok;
 
     cudaFree(ctx->d_planes);
     cudaFree(ctx->d_umask);
@@ -446,6 +485,10 @@ extern "C" int sk_set_sheet(sk_ctx *ctx, const uint8_t *barcodes, uint32_t S, ui
     cudaFree(ctx->d_skeys);
     cudaFree(ctx->d_htab);
     cudaFree(ctx->d_hcand);
+    cudaFree(ctx->d_ftab);
+    cudaFree(ctx->d_fnext);
+    ctx->d_ftab = nullptr;
+    ctx->d_fnext = nullptr;
     ctx->d_planes = ctx->d_umask = ctx->d_hcls = ctx->d_skeys = nullptr;
     ctx->d_lut = ctx->d_sheet_raw = nullptr;
     ctx->d_htab = nullptr;
@@ -458,6 +501,10 @@ extern "C" int sk_set_sheet(sk_ctx *ctx, const uint8_t *barcodes, uint32_t S, ui
     CK(cudaMalloc(&ctx->d_skeys, std::max<size_t>(skeys.size() * 4, 16)));
     CK(cudaMalloc(&ctx->d_htab, htab.size() * 8));
     CK(cudaMalloc(&ctx->d_hcand, hcand.size() * 2));
+    CK(cudaMalloc(&ctx->d_ftab, ftab.size() * 8));
+    CK(cudaMalloc(&ctx->d_fnext, fnext.size() * 2));
+    CK(cudaMemcpy(ctx->d_ftab, ftab.data(), ftab.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->d_fnext, fnext.data(), fnext.size() * 2, cudaMemcpyHostToDevice));
     if (S) {
         CK(cudaMemcpy(ctx->d_planes, planes.data(), planes.size() * 4, cudaMemcpyHostToDevice));
         CK(cudaMemcpy(ctx->d_umask, umask.data(), umask.size() * 4, cudaMemcpyHostToDevice));
@@ -497,6 +544,7 @@ extern "C" int sk_set_sheet(sk_ctx *ctx, const uint8_t *barcodes, uint32_t S, ui
 // ------------------------------------------------------------------------------------------------
 static int begin_op(sk_ctx *ctx, Slot *s, int op) {
     s->last_op = op;
+    s->used_fast = false;
     s->launches = 0;
     for (int i = 0; i < SK_N_INPUTS; i++) {
         s->pass_ran[i] = false;
@@ -506,11 +554,11 @@ static int begin_op(sk_ctx *ctx, Slot *s, int op) {
     return SK_OK;
 }
 
-static void base_params(sk_ctx *ctx, Slot *s, int which, KParams &p) {
+static void base_params(sk_ctx *ctx, Slot *s, int which, KParams &p, bool fast = false) {
     memset(&p, 0, sizeof p);
     p.in = s->in[which];
     p.n = s->in_len[which];
-    p.n_chunks = chunks_of(ctx, p.n);
+    p.n_chunks = chunks_of(ctx, p.n, fast);
     p.lpr = 4;
     p.rec_limit = ~0ull;
     p.final_batch = 1;
@@ -521,13 +569,14 @@ static void base_params(sk_ctx *ctx, Slot *s, int which, KParams &p) {
     s->n_chunks[which] = p.n_chunks;
 }
 
-static int run_pass(sk_ctx *ctx, Slot *s, int which, int op, const KParams &p, bool ordered_out) {
+static int run_pass(sk_ctx *ctx, Slot *s, int which, int op, const KParams &p, bool ordered_out, bool fast = false) {
     if (p.n_chunks == 0) return SK_OK;
     CK(cudaMemsetAsync(p.tile_lines, 0, (uint64_t)p.n_chunks * 8, s->stream));
     if (ordered_out) CK(cudaMemsetAsync(p.tile_out, 0, (uint64_t)p.n_chunks * 8, s->stream));
     const char *err = nullptr;
     if (ctx->profiling) CK(cudaEventRecord(s->ev[which][0], s->stream));
-    int rc = launch_chunk_kernel(ctx->cfg, op, p, ctx->sm_count, s->stream, &err);
+    int rc = fast ? launch_fast_kernel(op, p, ctx->sm_count, s->stream, &err)
+                  : launch_chunk_kernel(ctx->cfg, op, p, ctx->sm_count, s->stream, &err);
     if (rc < 0) {
         ctx->err = std::string("kernel launch failed: ") + (err ? err : "?");
         return SK_E_CUDA;
@@ -543,20 +592,34 @@ static int end_op(sk_ctx *ctx, Slot *s) {
     return SK_OK;
 }
 
-static int stream_op(sk_ctx *ctx, uint32_t slot, int op, uint32_t min_baseq, uint64_t rec_limit) {
-    Slot *s = get_slot(ctx, slot);
-    if (!s || min_baseq > 255) return SK_E_INVALID;
+static int stream_op_enqueue(sk_ctx *ctx, Slot *s, int op, uint32_t min_baseq, uint64_t rec_limit, bool fast) {
     int rc = begin_op(ctx, s, op);
     if (rc) return rc;
     KParams p;
-    base_params(ctx, s, SK_IN_R1, p);
-    p.min_baseq = min_baseq;
-    p.rec_limit = rec_limit ? rec_limit : ~0ull;
-    p.out = s->out[0];
-    p.out_cap = s->out_cap;
-    rc = run_pass(ctx, s, SK_IN_R1, op, p, true);
+    auto fill = [&](bool f) {
+        base_params(ctx, s, SK_IN_R1, p, f);
+        p.min_baseq = min_baseq;
+        p.rec_limit = rec_limit ? rec_limit : ~0ull;
+        p.out = s->out[0];
+        p.out_cap = s->out_cap;
+    };
+    fill(fast);
+    if (fast && !fast_supported(op, p)) {
+        fast = false;
+        fill(false);
+    }
+    s->used_fast = fast;
+    s->req_min_baseq = min_baseq;
+    s->req_rec_limit = rec_limit;
+    rc = run_pass(ctx, s, SK_IN_R1, op, p, true, fast);
     if (rc) return rc;
     return end_op(ctx, s);
+}
+static int stream_op(sk_ctx *ctx, uint32_t slot, int op, uint32_t min_baseq, uint64_t rec_limit) {
+    Slot *s = get_slot(ctx, slot);
+    if (!s || min_baseq > 255) return SK_E_INVALID;
+    s->reran_general = false;
+    return stream_op_enqueue(ctx, s, op, min_baseq, rec_limit, ctx->fast);
 }
 
 extern "C" int sk_trim_by_quality(sk_ctx *ctx, uint32_t slot, uint32_t min_baseq, uint64_t rec_limit) {
@@ -621,9 +684,14 @@ extern "C" int sk_add_barcode(sk_ctx *ctx, uint32_t slot, uint64_t rec_limit) {
     return end_op(ctx, s);
 }
 
+static int demux_enqueue(sk_ctx *ctx, Slot *s, const sk_demux_opts *o, bool fast);
 extern "C" int sk_demultiplex(sk_ctx *ctx, uint32_t slot, const sk_demux_opts *o) {
     Slot *s = get_slot(ctx, slot);
     if (!s || !o) return SK_E_INVALID;
+    s->reran_general = false;
+    return demux_enqueue(ctx, s, o, ctx->fast);
+}
+static int demux_enqueue(sk_ctx *ctx, Slot *s, const sk_demux_opts *o, bool fast) {
     if (!ctx->have_sheet || !s->assign) {
         ctx->err = "sk_demultiplex: call sk_set_sheet first (and create the context with max_samples > 0)";
         return SK_E_NO_SHEET;
@@ -645,6 +713,13 @@ extern "C" int sk_demultiplex(sk_ctx *ctx, uint32_t slot, const sk_demux_opts *o
     uint32_t n_index = 0;
     if (o->use_index & 1u) idx_stream[n_index++] = SK_IN_AUX1;
     if (o->use_index & 2u) idx_stream[n_index++] = SK_IN_AUX2;
+    // the lean engine does the header route on sheets its index can represent
+    if (n_index || !ctx->h_classes || !ctx->fast_sheet || getenv("SK_NO_HIDX")) fast = false;
+    s->used_fast = fast;
+    {
+        const sk_demux_opts keep = *o;  // o may alias s->req_opts (re-run)
+        s->req_opts = keep;
+    }
     for (uint32_t q = 0; q < n_index; q++) {
         KParams k;
         base_params(ctx, s, idx_stream[q], k);
@@ -655,7 +730,9 @@ extern "C" int sk_demultiplex(sk_ctx *ctx, uint32_t slot, const sk_demux_opts *o
         if (rc) return rc;
     }
     auto demux_params = [&](int which, int mate, KParams &p) {
-        base_params(ctx, s, which, p);
+        base_params(ctx, s, which, p, fast);
+        p.sheet.fidx.table = ctx->d_ftab;
+        p.sheet.fidx.next = ctx->d_fnext;
         p.rec_limit = limit;
         p.fused_trim = o->fused_trim_min_baseq;
         p.out = o->no_output ? nullptr : s->out[mate];
@@ -692,12 +769,17 @@ extern "C" int sk_demultiplex(sk_ctx *ctx, uint32_t slot, const sk_demux_opts *o
     };
     KParams p1;
     demux_params(SK_IN_R1, 0, p1);
-    rc = run_pass(ctx, s, SK_IN_R1, OP_DEMUX1, p1, false);
+    if (fast && !fast_supported(OP_DEMUX1, p1)) {
+        fast = false;
+        s->used_fast = false;
+        demux_params(SK_IN_R1, 0, p1);
+    }
+    rc = run_pass(ctx, s, SK_IN_R1, OP_DEMUX1, p1, false, fast);
     if (rc) return rc;
     if (s->paired) {
         KParams p2;
         demux_params(SK_IN_R2, 1, p2);
-        rc = run_pass(ctx, s, SK_IN_R2, OP_DEMUX2, p2, false);
+        rc = run_pass(ctx, s, SK_IN_R2, OP_DEMUX2, p2, false, fast);
         if (rc) return rc;
     }
     return end_op(ctx, s);
@@ -707,6 +789,22 @@ extern "C" int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res) {
     Slot *s = get_slot(ctx, slot);
     if (!s) return SK_E_INVALID;
     CK(cudaStreamSynchronize(s->stream));
+    if (s->used_fast && s->last_op >= 0) {
+        // The lean engine met something outside its limits (long record, dense chunk, oversized chunk
+        // output): run the operator again on the general engine.
+        unsigned fl = 0;
+        for (int i = 0; i < SK_N_INPUTS; i++) fl |= s->stats_h[i].flags;
+        if (fl & F_NEED_GENERAL) {
+            const uint32_t fast_launches = s->launches;
+            const sk_demux_opts o = s->req_opts;
+            int rc = s->last_op == OP_DEMUX1 ? demux_enqueue(ctx, s, &o, false)
+                                             : stream_op_enqueue(ctx, s, s->last_op, s->req_min_baseq, s->req_rec_limit, false);
+            if (rc) return rc;
+            CK(cudaStreamSynchronize(s->stream));
+            s->launches += fast_launches;
+            s->reran_general = true;
+        }
+    }
     if (!res) return SK_OK;
     memset(res, 0, sizeof *res);
     if (s->last_op < 0) return SK_OK;
@@ -721,6 +819,7 @@ extern "C" int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res) {
     }
     res->n_records = h[SK_IN_R1].n_records;
     res->gpu_launches = s->launches;
+    res->reserved = (s->used_fast ? 1u : 0u) | (s->reran_general ? 2u : 0u);  // diagnostic: bit0 lean engine, bit1 re-run
     if (ctx->profiling)
         for (int i = 0; i < SK_N_INPUTS; i++)
             if (s->pass_ran[i]) cudaEventElapsedTime(&res->pass_ms[i], s->ev[i][0], s->ev[i][1]);

@@ -44,6 +44,20 @@ struct CfgB {  // 32 KiB chunks, 8 warps
     static constexpr int STAGE = 35840;
     static constexpr int MIN_CTAS = 2;
 };
+// Geometry of the lean engine (sk_fast.cu): the chunk is a whole number of scan threads (102 x 80 B),
+// the window holds no bytes before the chunk, 8 CTAs of 4 warps per SM.
+struct GeoS {
+    static constexpr int NT = 128;
+    static constexpr int PPL = 5;
+    static constexpr int WIN_MAX = NT * PPL * 16;       // 10240
+    static constexpr int CHUNK = 102 * PPL * 16;        // 8160
+    static constexpr int OVERHANG = WIN_MAX - CHUNK;    // 2080
+    static constexpr int MAXREC = NT;
+    static constexpr int MAXLINES = 4 * MAXREC + 16;
+    static constexpr int STAGE = WIN_MAX;
+    static constexpr int MIN_CTAS = 8;
+};
+constexpr int FAST_CCOUNT_MAX = 1024;  // per-sample counters live in shared memory up to this many samples
 inline int cfg_chunk_bytes(int cfg) { return cfg == CfgB::ID ? CfgB::CHUNK : CfgA::CHUNK; }
 
 constexpr int LAYOUT_FAST_MAXREC = 128;  // the bit-mask layout handles chunks of up to this many records
@@ -102,6 +116,12 @@ struct HalfIdx {
     const uint32_t *skeys;   // [S][nwp]: cared bytes of every sample, 0 elsewhere
 };
 constexpr int HIDX_CLS_ROWS = 7;
+// The same index in the form the lean engine probes: one 8-byte entry per slot that already names
+// the first sample of the key, further samples of a key chained through `next`.
+struct FastIdx {
+    const uint2 *table;     // [n_classes][2][tsize]: {tag, (first sample + 1) | more << 16}; y == 0: empty slot
+    const uint16_t *next;   // [n_classes][2][S]: next sample with the same half key, 0xFFFF = none
+};
 
 // Sample sheet in device memory (packed by the host, sk_api.cu).
 struct SheetDev {
@@ -110,6 +130,7 @@ struct SheetDev {
     const uint8_t *lut;      // 256: bits 0-2 = 3-bit code (0 = matches no literal), bit 3 = [ACGTNacgtn+]
     uint32_t S, L, Umax, wide;
     HalfIdx hidx;
+    FastIdx fidx;
 };
 
 // Shared-memory carve-up (bytes), computed on the host and passed in KParams.
@@ -172,7 +193,7 @@ enum : unsigned {
     K_BAD_FASTX_LINE = 7, K_NON_ASCII = 32, K_TOO_LONG = 33, K_TOO_DENSE = 34, K_MIXED = 35, K_OUT_OVERFLOW = 36,
     K_TRUNC_FUSED = 37,
 };
-enum : unsigned { F_MATE_COUNT = 1u, F_EVENTS_OVERFLOW = 2u, F_NON_ASCII = 0x100u };
+enum : unsigned { F_MATE_COUNT = 1u, F_EVENTS_OVERFLOW = 2u, F_NON_ASCII = 0x100u, F_NEED_GENERAL = 0x200u };
 
 constexpr int REC_BYTES = 26;  // per-record plan fields, see sk_kernels.cu
 template <class Cfg>
@@ -199,5 +220,9 @@ inline __host__ __device__ SmemLayout smem_layout(uint32_t S, uint32_t wide, uin
 // Launchers (sk_kernels.cu)
 int launch_chunk_kernel(int cfg, int op, const KParams &p, int sm_count, void *stream, const char **err);
 int chunk_kernel_smem_bytes(int cfg, uint32_t S, uint32_t wide, uint32_t n_classes, uint32_t nwp);
+// Lean engine (sk_fast.cu)
+int fast_chunk_bytes();
+bool fast_supported(int op, const KParams &p);
+int launch_fast_kernel(int op, const KParams &p, int sm_count, void *stream, const char **err);
 
 }  // namespace sk

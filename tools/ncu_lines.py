@@ -20,6 +20,7 @@ import tempfile
 rep = sys.argv[1]
 lib = sys.argv[2] if len(sys.argv) > 2 else "seqkit_b200/libseqkit_b200.so"
 topn = int(sys.argv[3]) if len(sys.argv) > 3 else 40
+sort_by = 1 if (len(sys.argv) > 4 and sys.argv[4] == "inst") else 0  # "inst": order by executed instructions
 
 tmp = tempfile.mkdtemp()
 subprocess.check_call(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, stdout=subprocess.DEVNULL)
@@ -61,6 +62,13 @@ for r in rows:
 
 def demangle_match(kname, funcs):
     # match by template arguments: Cfg name and OP number
+    m = re.search(r"sk_fast_kernel<sk::(\w+), \(int\)(\d+), \(int\)(\d+)>", kname)
+    if m:
+        geo, op, nw = m.group(1), m.group(2), m.group(3)
+        for f in funcs:
+            if "sk_fast_kernel" in f and ("%d%s" % (len(geo), geo)) in f and ("Li%sELi%sE" % (op, nw)) in f:
+                return f
+        return None
     m = re.search(r"sk_chunk_kernel<sk::(\w+), \(int\)(\d+), (unsigned int|unsigned long)", kname)
     if not m:
         return None
@@ -84,7 +92,11 @@ def src_line(f, n):
     return s[n - 1].strip() if 0 < n <= len(s) else ""
 
 
+seen = set()
 for K in kernels:
+    if K["name"] in seen:
+        continue
+    seen.add(K["name"])
     h = K["hdr"]
     f = demangle_match(K["name"], funcs)
     print("==", K["name"])
@@ -104,7 +116,7 @@ for K in kernels:
     tot = [sum(a[k] for a in agg.values()) or 1.0 for k in range(8)]
     print("   warp instructions %.0f, samples %.0f, barrier samples %.0f (%.0f%%), lane efficiency %.1f/32"
           % (tot[1], tot[0], tot[3], 100 * tot[3] / tot[0], tot[2] / tot[1]))
-    for ln, a in sorted(agg.items(), key=lambda kv: -kv[1][0])[:topn]:
+    for ln, a in sorted(agg.items(), key=lambda kv: -kv[1][sort_by])[:topn]:
         fn, n = ln if ln else ("?", 0)
         print("   %5.1f%% samp %5.1f%% inst  bar %5.1f%% ssb %4.1f%% wait %4.1f%% xsw %6.0fk  %s:%d  %s"
               % (100 * a[0] / tot[0], 100 * a[1] / tot[1], 100 * a[3] / tot[0], 100 * a[4] / tot[0], 100 * a[6] / tot[0],

@@ -9,7 +9,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from seqkit_b200 import Engine, _lib as L  # noqa: E402
 
-NAMES = ["ticket", "load", "scan", "lines+lookback", "planA(d1)", "slowmatch(d1)", "plan", "layout", "reserve", "assemble",
+FAST_NAMES = ["ticket", "load", "scan", "lines+lookback", "plan", "layout", "reserve", "assemble", "tables+store"]
+NAMES = FAST_NAMES if not os.environ.get("SK_NO_FAST") else ["ticket", "load", "scan", "lines+lookback", "planA(d1)", "slowmatch(d1)", "plan", "layout", "reserve", "assemble",
          "store+tables"]
 P = int(os.environ.get("PAIRS", "1000000"))
 bcs = bench.make_sheet()
