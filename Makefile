@@ -18,7 +18,7 @@ seqkit_b200/fasta: seqkit_b200/host/fasta_main.cpp $(LIB) include/seqkit_b200.h
 	g++ -O2 -std=c++17 -Wall -Iinclude -o $@ $< -Lseqkit_b200 -lseqkit_b200 -Wl,-rpath,'$$ORIGIN' -lpthread
 
 # diagnostic build with per-phase cycle counters (tools/phase_timing.py)
-seqkit_b200/libseqkit_b200_timing.so: $(CSRC)/sk_kernels.cu $(CSRC)/sk_api.cu $(CSRC)/sk_synth.cu $(CSRC)/sk_internal.h include/seqkit_b200.h
+seqkit_b200/libseqkit_b200_timing.so: $(CSRC)/sk_fast.cu $(CSRC)/sk_device.cuh $(CSRC)/sk_kernels.cu $(CSRC)/sk_api.cu $(CSRC)/sk_synth.cu $(CSRC)/sk_internal.h include/seqkit_b200.h
 	$(NVCC) $(NVFLAGS) -DSK_PHASE_TIMING -shared -o $@ $(CSRC)/sk_kernels.cu $(CSRC)/sk_fast.cu $(CSRC)/sk_api.cu $(CSRC)/sk_synth.cu -ldl
 
 oracle:

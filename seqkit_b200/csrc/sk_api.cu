@@ -83,6 +83,7 @@ struct sk_ctx {
     uint2 *d_ftab = nullptr;      // FastIdx
     uint16_t *d_fnext = nullptr;
     bool fast_sheet = false;  // the sheet's FastIdx is usable
+    int fast_geo = 0;   // lean-engine geometry: 0 = GeoS (8 KiB chunks), 1 = GeoM (16 KiB chunks); SK_FAST_GEO
     bool fast = true;   // lean engine (sk_fast.cu) for trim / mask / header-route demultiplex; SK_NO_FAST=1 disables
     int cfg = 0;  // chunk-engine geometry: 0 = CfgA (16 KiB chunks, 4 warps), 1 = CfgB (32 KiB chunks, 8 warps)
 };
@@ -97,7 +98,7 @@ struct sk_ctx {
     } while (0)
 
 static uint32_t chunks_of(const sk_ctx *ctx, uint64_t n, bool fast = false) {
-    const uint64_t ch = fast ? (uint64_t)fast_chunk_bytes() : (uint64_t)cfg_chunk_bytes(ctx->cfg);
+    const uint64_t ch = fast ? (uint64_t)fast_chunk_bytes(ctx->fast_geo) : (uint64_t)cfg_chunk_bytes(ctx->cfg);
     return (uint32_t)((n + ch - 1) / ch);
 }
 
@@ -169,6 +170,7 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
     ctx->cfg = lim->reserved == 2 ? 1 : 0;  // reserved: 0/1 = 16 KiB chunks (default), 2 = 32 KiB chunks
     if (const char *e = getenv("SK_CFG")) ctx->cfg = atoi(e) ? 1 : 0;
     if (const char *e = getenv("SK_NO_FAST")) ctx->fast = atoi(e) == 0;
+    if (const char *e = getenv("SK_FAST_GEO")) ctx->fast_geo = atoi(e) ? 1 : 0;
     auto fail = [&](int code) {
         g_create_error = ctx->err;
         sk_ctx_destroy(ctx);
@@ -192,7 +194,7 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     const uint64_t B = (lim->max_stream_bytes + 15) & ~15ull;
     const uint64_t R = lim->max_records;
-    ctx->max_chunks = std::max(chunks_of(ctx, B, false), chunks_of(ctx, B, true)) + 1;
+    ctx->max_chunks = std::max(chunks_of(ctx, B, false), (uint32_t)((B + GeoS::CHUNK - 1) / GeoS::CHUNK)) + 1;
     const uint64_t out_cap = B + R * 72 + (uint64_t)ctx->max_chunks * 16 + 4096;
     const uint32_t Smax = lim->max_samples;
     ctx->slots.resize(lim->n_slots);
@@ -575,7 +577,7 @@ static int run_pass(sk_ctx *ctx, Slot *s, int which, int op, const KParams &p, b
     if (ordered_out) CK(cudaMemsetAsync(p.tile_out, 0, (uint64_t)p.n_chunks * 8, s->stream));
     const char *err = nullptr;
     if (ctx->profiling) CK(cudaEventRecord(s->ev[which][0], s->stream));
-    int rc = fast ? launch_fast_kernel(op, p, ctx->sm_count, s->stream, &err)
+    int rc = fast ? launch_fast_kernel(ctx->fast_geo, op, p, ctx->sm_count, s->stream, &err)
                   : launch_chunk_kernel(ctx->cfg, op, p, ctx->sm_count, s->stream, &err);
     if (rc < 0) {
         ctx->err = std::string("kernel launch failed: ") + (err ? err : "?");
@@ -604,7 +606,7 @@ static int stream_op_enqueue(sk_ctx *ctx, Slot *s, int op, uint32_t min_baseq, u
         p.out_cap = s->out_cap;
     };
     fill(fast);
-    if (fast && !fast_supported(op, p)) {
+    if (fast && !fast_supported(ctx->fast_geo, op, p)) {
         fast = false;
         fill(false);
     }
@@ -769,7 +771,7 @@ static int demux_enqueue(sk_ctx *ctx, Slot *s, const sk_demux_opts *o, bool fast
     };
     KParams p1;
     demux_params(SK_IN_R1, 0, p1);
-    if (fast && !fast_supported(OP_DEMUX1, p1)) {
+    if (fast && !fast_supported(ctx->fast_geo, OP_DEMUX1, p1)) {
         fast = false;
         s->used_fast = false;
         demux_params(SK_IN_R1, 0, p1);

@@ -143,6 +143,147 @@ __device__ __forceinline__ bool class_run_is(const uint32_t (&raw)[NR], const ui
     return !(lut[term] & 8u);               // the byte after the barcode ends the run
 }
 
+// End of the greedy class run (fasta_demultiplex.rs:38) that starts at `from`, four bytes per step on
+// words aligned to `from` (lanes of a warp step together when their barcodes are equally long).
+__device__ __forceinline__ uint32_t class_run_end(const uint8_t *b, const uint8_t *lut, uint32_t from, uint32_t h1) {
+    const uint32_t a = from & ~3u, sh = (from & 3u) * 8u;
+    uint32_t lo = *(const uint32_t *)(b + a);
+    uint32_t e = from;
+    while (e < h1) {
+        const uint32_t hi = *(const uint32_t *)(b + a + 4 + (e - from));
+        const uint32_t x = __funnelshift_r(lo, hi, sh);
+        lo = hi;
+        const uint32_t c0 = lut[x & 0xFFu], c1 = lut[(x >> 8) & 0xFFu], c2 = lut[(x >> 16) & 0xFFu], c3 = lut[x >> 24];
+        if (c0 & c1 & c2 & c3 & 8u) {
+            e += 4;
+            continue;
+        }
+        e += (c0 & 8u) ? ((c1 & 8u) ? ((c2 & 8u) ? 3u : 2u) : 1u) : 0u;
+        break;
+    }
+    return e < h1 ? e : h1;
+}
+
+// Running totals of fasta_trim_by_quality.rs:33-36 over the aligned 8-byte block at window offset a,
+// in the order the reference examines the bytes: T[i] is the total after byte a+7-i, starting from
+// `total`.  Bytes outside the quality string [L3,E) contribute nothing (they are replaced by the
+// byte whose contribution is zero, sub = 33 + min_baseq <= 255).  A byte below '!' takes the wrapping
+// u8 subtraction (:35) on the byte-wise path.
+__device__ __forceinline__ void blk8_totals(const uint8_t *b, uint32_t a, uint32_t L3, uint32_t E, int sub, int minq,
+                                            int total, int (&T)[8]) {
+    uint2 v = *(const uint2 *)(b + a);
+    if (a < L3 || a + 8 > E) {
+        const uint32_t nlow = a < L3 ? L3 - a : 0u, nhigh = a + 8 > E ? a + 8 - E : 0u;
+        unsigned long long m = nlow >= 8u ? 0ull : (~0ull << (8u * nlow));
+        m = nhigh >= 8u ? 0ull : (m & (~0ull >> (8u * nhigh)));
+        const uint32_t mlo = (uint32_t)m, mhi = (uint32_t)(m >> 32), sub4 = (uint32_t)sub * 0x01010101u;
+        v.x = (v.x & mlo) | (sub4 & ~mlo);
+        v.y = (v.y & mhi) | (sub4 & ~mhi);
+    }
+    const uint32_t H = 0x80808080u, C = 0x21212121u;
+    const uint32_t bad = (~((v.x | H) - C) & ~v.x & H) | (~((v.y | H) - C) & ~v.y & H);  // bytes below '!'
+    if (!bad) {
+        T[0] = (int)__dp4a(v.y, 0x01000000u, (uint32_t)(total - sub));
+        T[1] = (int)__dp4a(v.y, 0x01010000u, (uint32_t)(total - 2 * sub));
+        T[2] = (int)__dp4a(v.y, 0x01010100u, (uint32_t)(total - 3 * sub));
+        T[3] = (int)__dp4a(v.y, 0x01010101u, (uint32_t)(total - 4 * sub));
+        T[4] = (int)__dp4a(v.x, 0x01000000u, (uint32_t)(T[3] - sub));
+        T[5] = (int)__dp4a(v.x, 0x01010000u, (uint32_t)(T[3] - 2 * sub));
+        T[6] = (int)__dp4a(v.x, 0x01010100u, (uint32_t)(T[3] - 3 * sub));
+        T[7] = (int)__dp4a(v.x, 0x01010101u, (uint32_t)(T[3] - 4 * sub));
+    } else {
+        int t = total;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t q = ((i < 4 ? v.y : v.x) >> (8 * (3 - (i & 3)))) & 0xFFu;
+            t += q >= 33u ? (int)q - sub : (int)((q - 33u) & 0xFFu) - minq;
+            T[i] = t;
+        }
+    }
+}
+
+// fasta_trim_by_quality.rs:28-48 for one record per lane, all lanes of the warp in step: every lane
+// walks its quality string down in aligned 8-byte blocks inside one warp-synchronous loop and only
+// notes (a) the block in which the running total first exceeds 0 (:37) and (b) the block holding the
+// minimum so far (:38); the positions inside those two blocks are resolved once after the loop.
+// Must be called by all 32 lanes (`has` = this lane carries a record).  min_baseq <= 222.
+__device__ __forceinline__ bool plan_trim_warp(const uint8_t *b, bool has, uint32_t L1, uint32_t L2, uint32_t L3, uint32_t L4,
+                                               int minq, uint8_t &mode, uint32_t &kk, uint32_t &body_len) {
+    const uint32_t NONE = 0xFFFFFFFFu;
+    uint32_t k = has ? L4 - L3 : 0u;
+    while (k > 0 && is_ws(b[L3 + k - 1])) k--;  // qual.trim_end().len()  (:31)
+    __syncwarp();
+    const uint32_t E = L3 + k;
+    const int sub = 33 + minq;
+    int total = -50, lowest = -50;  // :28-29
+    uint32_t low_a = NONE, brk_a = NONE;
+    int low_total = 0, brk_total = 0;
+    uint32_t a = k ? ((E - 1u) & ~7u) : 0u;
+    bool active = k > 0;
+    while (__any_sync(0xffffffffu, active)) {
+        if (active) {
+            int T[8];
+            blk8_totals(b, a, L3, E, sub, minq, total, T);
+            const int mx = max(max(max(T[0], T[1]), max(T[2], T[3])), max(max(T[4], T[5]), max(T[6], T[7])));
+            const int mn = min(min(min(T[0], T[1]), min(T[2], T[3])), min(min(T[4], T[5]), min(T[6], T[7])));
+            if (mx > 0) {  // the break is inside this block
+                brk_a = a;
+                brk_total = total;
+                active = false;
+            } else {
+                if (mn < lowest) {  // strict '<': an earlier block keeps a tie
+                    lowest = mn;
+                    low_a = a;
+                    low_total = total;
+                }
+                total = T[7];
+                if (a <= L3) active = false;
+                else a -= 8;
+            }
+        }
+    }
+    // resolve positions: first the break block (its totals before the break may lower the minimum),
+    // then the block that holds the minimum
+    uint32_t lowest_k = k;
+    bool placed = false;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        const uint32_t ra = pass == 0 ? brk_a : low_a;
+        const bool go = ra != NONE && !placed;
+        if (go) {
+            int T[8];
+            blk8_totals(b, ra, L3, E, sub, minq, pass == 0 ? brk_total : low_total, T);
+            bool ok = true;
+            int best = 0x7FFFFFFF;
+            uint32_t at = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                ok = ok && T[i] <= 0;           // totals after the break are never looked at
+                if (ok && T[i] < best) {        // first (highest address) of equal totals wins
+                    best = T[i];
+                    at = ra + 7u - (uint32_t)i;
+                }
+            }
+            if (pass == 0 ? best < lowest : best == lowest) {
+                lowest = best;
+                lowest_k = at - L3;
+                placed = true;
+            }
+        }
+        __syncwarp();
+    }
+    if (lowest_k == 0) {  // :44-45
+        mode = B_GARBAGE;
+        kk = 0;
+        body_len = 6;  // "N\n+\n!\n"
+        return true;
+    }
+    mode = B_TRIM;
+    kk = lowest_k;
+    body_len = 2 * lowest_k + 4;  // seq[..k] "\n+\n" qual[..k] "\n"  (:47)
+    return lowest_k <= L2 - L1;
+}
+
 // Pigeonhole barcode match on the compact tables (FastIdx): both half-key probes of a class are
 // issued before either is consumed; a probe stops at the first slot whose tag matches (tags are
 // unique per table, checked when the sheet is packed).  Same contract as hidx_match.
@@ -268,7 +409,7 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
     constexpr int TB = G::PPL * 16;              // bytes per thread in the scan
     constexpr int TCH = G::CHUNK / TB;           // threads whose bytes lie inside the chunk
     static_assert(G::CHUNK % TB == 0 && G::WIN_MAX == NT * TB && G::PPL == 5, "fast geometry");
-    static_assert(MAXREC == NT, "one thread per record");
+    static_assert(MAXREC == NT && NT % 64 == 0 && NT <= 256, "one thread per record");
     constexpr bool IS_DEMUX = (OP == OP_DEMUX1 || OP == OP_DEMUX2);
     constexpr bool ORDERED = !IS_DEMUX;
     using FL = FLayout<G>;
@@ -451,51 +592,70 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
             atomicMax(&st->consumed, (unsigned long long)(c0 + LB(j0 + nrec * 4u)));
         }
 
-        // ---- P5 plan, one thread per record.  Fused trim+demultiplex: the quality trim of a record
-        // runs on the lower half of the CTA while the upper half does the header work.
+        // ---- P5 plan, one lane per record, whole warps per task and every step warp-synchronous (lanes
+        // that took different branches meet again at the __syncwarp that closes the step).  Fused
+        // trim+demultiplex: the quality trim runs on the lower half of the CTA, the header work on
+        // the upper half.
         const uint32_t tl = fused ? (uint32_t)tid % (NT / 2) : (uint32_t)tid;
         const uint32_t tstride = fused ? NT / 2 : NT;
-        const bool do_trim = fused && tid < NT / 2;
-        const bool do_main = !fused || tid >= NT / 2;
+        const bool do_trim = (fused && tid < NT / 2) || OP == OP_TRIM;
+        const bool do_main = (!fused || tid >= NT / 2) && OP != OP_TRIM;
+        const int trim_q = OP == OP_TRIM ? (int)p.min_baseq : p.fused_trim;
 
         if (do_trim) {
-            for (uint32_t r = tl; r < nrec; r += tstride) {
-                const uint32_t j = j0 + r * 4u;
+            for (uint32_t r0 = 0; r0 < nrec; r0 += tstride) {
+                const uint32_t r = r0 + tl;
+                const bool has = r < nrec;
+                const uint32_t j = j0 + (has ? r : 0u) * 4u;
                 const uint32_t L0 = LB(j), L1 = LB(j + 1), L2 = LB(j + 2), L3 = LB(j + 3), L4 = LB(j + 4);
-                uint8_t mode = B_FAIL;
+                uint8_t mode = OP == OP_TRIM ? B_NONE : B_FAIL;
                 uint32_t kk = 0, body = 0;
-                if (L1 > L0 && win[L1 - 1] == '\n') {
-                    if (!plan_trim_body(win, L1, L2, L3, L4, p.fused_trim, mode, kk, body)) mode = B_FAIL;
-                }
-                r_k[r] = (uint16_t)kk;
-                r_body[r] = (uint16_t)(body > 0xFFFFu ? 0xFFFFu : body);
-                r_mode[r] = mode;
-            }
-        }
-        if (do_main) {
-            for (uint32_t r = tl; r < nrec; r += tstride) {
-                const uint32_t j = j0 + r * 4u;
-                const uint64_t rec = rec0 + r;
-                const uint32_t L0 = LB(j), L1 = LB(j + 1);
+                bool ok = has;
                 if (OP == OP_TRIM) {
-                    uint8_t mode = B_NONE;
-                    uint32_t kk = 0, outlen = 0;
-                    if (win[L0] != '@') {  // fasta_trim_by_quality.rs:20-22
-                        report_err(st, rec, K_BAD_HEADER);
-                    } else {
-                        const uint32_t L2 = LB(j + 2), L3 = LB(j + 3), L4 = LB(j + 4);
-                        uint32_t body;
-                        if (!plan_trim_body(win, L1, L2, L3, L4, (int)p.min_baseq, mode, kk, body)) {
-                            report_err(st, rec, K_SEQ_SHORT);
+                    if (has && win[L0] != '@') {  // fasta_trim_by_quality.rs:20-22
+                        report_err(st, rec0 + r, K_BAD_HEADER);
+                        ok = false;
+                    }
+                } else {
+                    ok = has && L1 > L0 && win[L1 - 1] == '\n';
+                }
+                bool fine;
+                if (trim_q <= 222) {
+                    fine = plan_trim_warp(win, ok, L1, L2, L3, L4, trim_q, mode, kk, body);
+                } else {
+                    fine = ok ? plan_trim_body(win, L1, L2, L3, L4, trim_q, mode, kk, body) : true;
+                    __syncwarp();
+                }
+                if (has) {
+                    if (OP == OP_TRIM) {
+                        uint32_t outlen = 0;
+                        if (!ok) {
+                            mode = B_NONE;
+                        } else if (!fine) {
+                            report_err(st, rec0 + r, K_SEQ_SHORT);
                             mode = B_NONE;
                         } else {
                             outlen = (L1 - L0) + body;  // header verbatim (:23) + body
                         }
+                        r_outlen[r] = (uint16_t)(outlen > 0x3FFFu ? 0x3FFFu : outlen);
+                    } else if (!ok || !fine) {
+                        mode = B_FAIL;
                     }
                     r_k[r] = (uint16_t)kk;
+                    r_body[r] = (uint16_t)(body > 0xFFFFu ? 0xFFFFu : body);
                     r_mode[r] = mode;
-                    r_outlen[r] = (uint16_t)(outlen > 0x3FFFu ? 0x3FFFu : outlen);
-                } else if (OP == OP_MASK) {
+                }
+            }
+        }
+        if (do_main) {
+            for (uint32_t r0 = 0; r0 < nrec; r0 += tstride) {
+                const uint32_t r = r0 + tl;
+                const bool has = r < nrec;
+                const uint32_t j = j0 + (has ? r : 0u) * 4u;
+                const uint64_t rec = rec0 + r;
+                const uint32_t L0 = LB(j), L1 = LB(j + 1);
+                if (OP == OP_MASK) {
+                    if (!has) continue;
                     uint8_t mode = B_NONE;
                     uint32_t kk = 0, outlen = 0;
                     if (win[L0] != '@') {  // fasta_mask_by_quality.rs:21-23
@@ -520,75 +680,95 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
                     // fasta_demultiplex.rs:117-194: validate, locate the barcode, match, decide
                     int sample = -1;
                     uint32_t alen = 0, blen = 0, cut0 = 0, cut1 = 0, taglen = 0;
-                    if (win[L0] != '@') {  // :118-120
-                        report_err(st, rec, K_BAD_HEADER);
-                    } else if (fused && !(L1 > L0 && win[L1 - 1] == '\n')) {
-                        report_err(st, rec, K_TRUNC_FUSED);
-                    } else {
-                        uint32_t stp;
-                        if (!bc_find16(win, sh_lut, L0, L1, stp)) {  // :138-141
+                    // step 1: header checks and the leftmost " BC:x" (:118-120, :138-141)
+                    bool live = has;
+                    uint32_t stp = 0;
+                    if (live) {
+                        if (win[L0] != '@') {
+                            report_err(st, rec, K_BAD_HEADER);
+                            live = false;
+                        } else if (fused && !(L1 > L0 && win[L1 - 1] == '\n')) {
+                            report_err(st, rec, K_TRUNC_FUSED);
+                            live = false;
+                        } else if (!bc_find16(win, sh_lut, L0, L1, stp)) {
                             report_err(st, rec, K_NO_BC);
-                        } else {
-                            cut0 = stp - L0;
-                            const uint32_t bs = stp + 4;
-                            const uint32_t Lb = p.sheet.L;
-                            uint32_t raw[NWMAX + 1];
-                            load_raw<NWMAX + 1>(win, bs, (Lb + 4u) >> 2, raw);
-                            cut1 = cut0 + 4 + Lb;  // end of the greedy class run (:38) when it is L long
-                            if (!class_run_is<NWMAX + 1>(raw, sh_lut, Lb, L1 - bs)) {  // :148-150
-                                report_err(st, rec, K_BC_LEN);
-                            } else {
-                                uint32_t lowest, best, last;
-                                fidx_match<NWMAX + 1>(raw, p.sheet.hidx, p.sheet.fidx, hcls, S, lowest, best, last);
-                                my_total++;                // :169
-                                if (lowest <= 1u) {        // :172
-                                    if (best == last) {    // :173-178
-                                        sample = (int)best;
-                                        my_ident++;
-                                        if (cc_smem) atomicAdd(&ccount[best], 1u);
-                                        else atomicAdd(&p.counts[best], 1ull);
-                                    } else {  // :184-188
-                                        sample = -2;
-                                        const uint32_t ei = atomicAdd(&st->n_events, 1u);
-                                        if (ei < p.events_cap) {
-                                            Event ev;
-                                            ev.record = (uint32_t)rec;
-                                            ev.bc_off = (uint32_t)(c0 + bs);
-                                            ev.bc_off2 = 0xFFFFFFFFu;
-                                            ev.best = (int16_t)best;
-                                            ev.last = (int16_t)last;
-                                            ev.mismatches = lowest;
-                                            p.events[ei] = ev;
-                                        } else {
-                                            atomicOr(&st->flags, F_EVENTS_OVERFLOW);
-                                        }
-                                    }
+                            live = false;
+                        }
+                    }
+                    __syncwarp();
+                    // step 2: the greedy class run must be exactly L long (:38, :148-150)
+                    const uint32_t Lb = p.sheet.L;
+                    uint32_t raw[NWMAX + 1];
+                    const uint32_t bs = stp + 4;
+                    if (live) {
+                        cut0 = stp - L0;
+                        cut1 = cut0 + 4 + Lb;
+                        load_raw<NWMAX + 1>(win, bs, (Lb + 4u) >> 2, raw);
+                        if (!class_run_is<NWMAX + 1>(raw, sh_lut, Lb, L1 - bs)) {
+                            report_err(st, rec, K_BC_LEN);
+                            live = false;
+                        }
+                    }
+                    __syncwarp();
+                    // step 3: match against the sheet and decide (:154-194)
+                    if (live) {
+                        uint32_t lowest, best, last;
+                        fidx_match<NWMAX + 1>(raw, p.sheet.hidx, p.sheet.fidx, hcls, S, lowest, best, last);
+                        my_total++;                // :169
+                        if (lowest <= 1u) {        // :172
+                            if (best == last) {    // :173-178
+                                sample = (int)best;
+                                my_ident++;
+                                if (cc_smem) atomicAdd(&ccount[best], 1u);
+                                else atomicAdd(&p.counts[best], 1ull);
+                            } else {  // :184-188
+                                sample = -2;
+                                const uint32_t ei = atomicAdd(&st->n_events, 1u);
+                                if (ei < p.events_cap) {
+                                    Event ev;
+                                    ev.record = (uint32_t)rec;
+                                    ev.bc_off = (uint32_t)(c0 + bs);
+                                    ev.bc_off2 = 0xFFFFFFFFu;
+                                    ev.best = (int16_t)best;
+                                    ev.last = (int16_t)last;
+                                    ev.mismatches = lowest;
+                                    p.events[ei] = ev;
+                                } else {
+                                    atomicOr(&st->flags, F_EVENTS_OVERFLOW);
                                 }
                             }
                         }
                     }
+                    __syncwarp();
                     if (sample >= 0) {
                         header_pieces(win, L0, L1, L0 + cut0, L0 + cut1, alen, blen);  // drain (:145) + trim_end (:206)
                         const uint32_t ul = p.sheet.wide ? (uint32_t)__popcll(((const unsigned long long *)p.sheet.umask)[sample])
                                                          : (uint32_t)__popc(p.sheet.umask[sample]);
                         taglen = ul ? 5 + ul : 0;  // " UMI:" + umi (:207)
                     }
-                    r_sample[r] = (int16_t)sample;
-                    r_alen[r] = (uint16_t)alen;
-                    r_blen[r] = (uint16_t)blen;
-                    r_cut0[r] = (uint16_t)cut0;
-                    r_cut1[r] = (uint16_t)cut1;
-                    r_taglen[r] = (uint8_t)taglen;
+                    __syncwarp();
+                    if (has) {
+                        r_sample[r] = (int16_t)sample;
+                        r_alen[r] = (uint16_t)alen;
+                        r_blen[r] = (uint16_t)blen;
+                        r_cut0[r] = (uint16_t)cut0;
+                        r_cut1[r] = (uint16_t)cut1;
+                        r_taglen[r] = (uint8_t)taglen;
+                    }
                 } else if (OP == OP_DEMUX2) {
                     // fasta_demultiplex.rs:215-237: mate 2 of an assigned pair
-                    int sample = rec < p.r1_stats->n_records ? (int)p.assign[rec] : -1;
+                    int sample = (has && rec < p.r1_stats->n_records) ? (int)p.assign[rec] : -1;
                     uint32_t alen = 0, blen = 0, cut1 = 0, taglen = 0;
-                    if (sample >= 0 && p.out) {
-                        uint32_t c0h = L1, c1h = L1, a;
-                        if (bc_find16(win, sh_lut, L0, L1, a)) {  // :219-227
-                            c0h = a;
-                            c1h = bc_run_end(win, sh_lut, a + 5, L1);
-                        }
+                    if (!p.out) sample = -1;
+                    uint32_t c0h = L1, c1h = L1, fa = 0;
+                    const bool found = sample >= 0 && bc_find16(win, sh_lut, L0, L1, fa);  // :219-227
+                    __syncwarp();
+                    if (found) {
+                        c0h = fa;
+                        c1h = class_run_end(win, sh_lut, fa + 4, L1);
+                    }
+                    __syncwarp();
+                    if (sample >= 0) {
                         header_pieces(win, L0, L1, c0h, c1h, alen, blen);  // :229
                         cut1 = c1h - L0;
                         const uint32_t ul = p.sheet.wide ? (uint32_t)__popcll(((const unsigned long long *)p.sheet.umask)[sample])
@@ -598,14 +778,15 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
                             report_err(st, rec, K_TRUNC_FUSED);
                             sample = -1;
                         }
-                    } else {
-                        sample = -1;
                     }
-                    r_sample[r] = (int16_t)sample;
-                    r_alen[r] = (uint16_t)alen;
-                    r_blen[r] = (uint16_t)blen;
-                    r_cut1[r] = (uint16_t)cut1;
-                    r_taglen[r] = (uint8_t)taglen;
+                    __syncwarp();
+                    if (has) {
+                        r_sample[r] = (int16_t)sample;
+                        r_alen[r] = (uint16_t)alen;
+                        r_blen[r] = (uint16_t)blen;
+                        r_cut1[r] = (uint16_t)cut1;
+                        r_taglen[r] = (uint8_t)taglen;
+                    }
                 }
             }
         }
@@ -654,8 +835,11 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
         const uint32_t my_off = sc & 0x3FFFFFu, my_rank = sc >> 22;
         FK_T(5);
 
-        // ---- P7 reserve output space: in-order operators chain a second look-back on output bytes,
-        // demultiplex chunks take 16-byte aligned space from a bump allocator (the slice table says where)
+        // ---- P7 reserve output space.  In-order operators chain a second look-back on output bytes (the
+        // staging image must be aligned like its destination).  Demultiplex chunks take 16-byte aligned
+        // space from a bump allocator: thread 0 issues the atomic here and needs its result only when it
+        // stores the image, so the round trip overlaps the assembly.
+        unsigned long long demux_base = 0;
         if (ORDERED) {
             if (warp == 0) {
                 const uint64_t excl = lookback(p.tile_out, c, chunk_out, lane);
@@ -667,18 +851,9 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
                     }
                 }
             }
-        } else if (tid == 0) {
-            unsigned long long base = 0;
-            if (p.out) {
-                base = atomicAdd(&st->out_cursor, (unsigned long long)((chunk_out + 15u) & ~15u));
-                ChunkRow row;
-                row.base = base;
-                row.first_group = (uint32_t)rec0;
-                row.n_groups = n_emit;
-                p.rows[c] = row;
-                if (chunk_out) atomicAdd(&st->out_bytes, (unsigned long long)chunk_out);
-            }
-            M->out_base = base;
+        } else if (tid == 0 && p.out) {
+            demux_base = atomicAdd(&st->out_cursor, (unsigned long long)((chunk_out + 15u) & ~15u));
+            if (chunk_out) atomicAdd(&st->out_bytes, (unsigned long long)chunk_out);
         }
         if (tid == 0 && store_pending) {  // the previous chunk's TMA store must have read the staging image
             bulk_wait_read0();
@@ -690,45 +865,81 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
         }
         __syncthreads();
         FK_T(6);
-        const uint64_t out_base = M->out_base;
+        const uint64_t out_base = ORDERED ? M->out_base : 0ull;
         const uint32_t shift = (uint32_t)(out_base & 15u);
         bool writable = p.out != nullptr && chunk_out > 0;
         if (writable && shift + chunk_out > (uint32_t)G::STAGE) {
             writable = false;
             bail = true;  // output does not fit the staging image
         }
-        if (writable && out_base + ((chunk_out + 15u) & ~15u) > p.out_cap) {
+        if (ORDERED && writable && out_base + ((chunk_out + 15u) & ~15u) > p.out_cap) {
             if (tid == 0) report_err(st, rec0, K_OUT_OVERFLOW);
             writable = false;
         }
         if (bail && tid == 0) atomicOr(&st->flags, F_NEED_GENERAL);
 
-        // ---- P8 assemble the chunk's output image in shared memory, aligned like its destination:
-        // four lanes per record, each copying one piece word-wise (header | sequence | qualities | literals)
+        // ---- P8 assemble the chunk's output image in shared memory, aligned like its destination.
+        // Six copy jobs per record (header | two halves of each of the two body pieces | tag and
+        // literals), numbered job-type major and dealt to all threads: a warp's lanes mostly share a job
+        // type, every job is a short word-wise copy, and the halves meet on a 16-byte boundary of the
+        // image.
         if (writable) {
             uint8_t *sb = stage + shift;
-            const uint32_t q4 = tid & 3;
-            for (uint32_t r0 = 0; r0 < nrec; r0 += NT / 4) {
-                const uint32_t r = r0 + (tid >> 2);
+            const uint32_t njobs = 6u * nrec;
+            for (uint32_t jb = (uint32_t)tid; jb < njobs; jb += NT) {
+                const uint32_t type = (jb >= nrec) + (jb >= 2u * nrec) + (jb >= 3u * nrec) + (jb >= 4u * nrec) + (jb >= 5u * nrec);
+                const uint32_t r = jb - type * nrec;
+                const uint32_t ol = r_outlen[r];
                 uint8_t *jd = nullptr;
-                const uint8_t *js = nullptr;
+                const uint8_t *js = nullptr, *jq = nullptr;  // jq: qualities of a masked copy
                 uint32_t jl = 0;
-                const uint32_t ol = r < nrec ? r_outlen[r] : 0;
                 if (ol) {
                     const uint32_t j = j0 + r * 4u;
                     const uint32_t L0 = LB(j), L1 = LB(j + 1);
                     uint8_t *d0 = sb + r_outoff[r];
                     const uint32_t kk = r_k[r];
                     const uint8_t mode = r_mode[r];
-                    uint32_t hlen;
+                    uint32_t hlen, alen = 0, blen = 0, taglen = 0;
                     if (ORDERED) {
                         hlen = L1 - L0;
-                        if (q4 == 0) { jd = d0; js = win + L0; jl = hlen; }
                     } else {
-                        const uint32_t alen = r_alen[r], blen = r_blen[r], taglen = r_taglen[r];
+                        alen = r_alen[r];
+                        blen = r_blen[r];
+                        taglen = r_taglen[r];
                         hlen = alen + blen + taglen + 1;
-                        if (q4 == 0) { jd = d0; js = win + L0; jl = alen; }
-                        if (q4 == 3) {  // the (usually empty) piece after the cut, the tag and the newline
+                    }
+                    uint8_t *db = d0 + hlen;
+                    if (type == 0) {
+                        jd = d0;
+                        js = win + L0;
+                        jl = ORDERED ? hlen : alen;
+                    } else if (type <= 4) {
+                        // body piece 0 / 1: verbatim -> the two halves of the three lines; trim and mask ->
+                        // sequence and qualities
+                        const uint32_t piece = (type - 1u) >> 1, hi = (type - 1u) & 1u;
+                        uint8_t *pd = nullptr;
+                        uint32_t ps = 0, pn = 0;
+                        if (mode == B_VERBATIM) {
+                            const uint32_t n = LB(j + 4) - L1;
+                            uint32_t m = (uint32_t)((((uintptr_t)db + n / 2 + 15u) & ~(uintptr_t)15) - (uintptr_t)db);
+                            if (m > n) m = n;
+                            pd = piece ? db + m : db;
+                            ps = piece ? L1 + m : L1;
+                            pn = piece ? n - m : m;
+                        } else if (mode == B_TRIM || mode == B_MASK) {
+                            pd = piece ? db + kk + 3 : db;
+                            ps = piece ? LB(j + 3) : L1;
+                            pn = kk;
+                            if (mode == B_MASK && !piece) jq = win + LB(j + 3);
+                        }
+                        uint32_t h = (uint32_t)((((uintptr_t)pd + pn / 2 + 15u) & ~(uintptr_t)15) - (uintptr_t)pd);
+                        if (h > pn) h = pn;
+                        jd = hi ? pd + h : pd;
+                        js = win + (hi ? ps + h : ps);
+                        jl = hi ? pn - h : h;
+                        if (jq) jq += hi ? h : 0u;
+                    } else {
+                        if (!ORDERED) {  // the (usually empty) piece after the cut, the tag and the newline
                             uint8_t *d = d0 + alen;
                             const uint8_t *sB = win + L0 + r_cut1[r];
                             for (uint32_t i = 0; i < blen; i++) d[i] = sB[i];
@@ -736,6 +947,7 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
                             if (taglen) {
                                 d[0] = ' '; d[1] = 'U'; d[2] = 'M'; d[3] = 'I'; d[4] = ':';
                                 uint8_t *gu = p.umi + (rec0 + r) * p.sheet.Umax;
+                                const uint32_t ul = taglen - 5;
                                 if (OP == OP_DEMUX1) {
                                     // UMI = observed chars where the sheet barcode has 'U' (:200-203); also
                                     // parked in the side table for mate 2
@@ -743,17 +955,25 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
                                     const int sm = r_sample[r];
                                     unsigned long long m = p.sheet.wide ? ((const unsigned long long *)p.sheet.umask)[sm]
                                                                         : (unsigned long long)p.sheet.umask[sm];
-                                    uint32_t t = 0;
-                                    while (m) {
-                                        const uint32_t q = (uint32_t)__ffsll((long long)m) - 1u;
-                                        m &= m - 1;
-                                        const uint8_t ch = ob[q];
-                                        d[5 + t] = ch;
-                                        gu[t] = ch;
-                                        t++;
+                                    const uint32_t u0 = (uint32_t)__ffsll((long long)m) - 1u;
+                                    if ((m >> u0) == ((1ull << ul) - 1ull)) {  // the U positions are one run (the usual sheet)
+                                        for (uint32_t t = 0; t < ul; t++) {
+                                            const uint8_t ch = ob[u0 + t];
+                                            d[5 + t] = ch;
+                                            gu[t] = ch;
+                                        }
+                                    } else {
+                                        uint32_t t = 0;
+                                        while (m) {
+                                            const uint32_t q = (uint32_t)__ffsll((long long)m) - 1u;
+                                            m &= m - 1;
+                                            const uint8_t ch = ob[q];
+                                            d[5 + t] = ch;
+                                            gu[t] = ch;
+                                            t++;
+                                        }
                                     }
                                 } else {
-                                    const uint32_t ul = taglen - 5;
                                     for (uint32_t i = 0; i < ul; i += 8) {
                                         uint8_t tmp[8];
 #pragma unroll
@@ -767,40 +987,17 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
                             }
                             d[0] = '\n';
                         }
-                    }
-                    uint8_t *db = d0 + hlen;
-                    if (mode == B_VERBATIM) {
-                        const uint32_t Lend = LB(j + 4);
-                        const uint32_t blen2 = Lend - L1, half = (blen2 / 2 + 3) & ~3u;
-                        const uint32_t h1 = half < blen2 ? half : blen2;
-                        if (q4 == 1) { jd = db; js = win + L1; jl = h1; }
-                        if (q4 == 2) { jd = db + h1; js = win + L1 + h1; jl = blen2 - h1; }
-                    } else if (mode == B_TRIM) {
-                        const uint32_t L3 = LB(j + 3);
-                        if (q4 == 1) { jd = db; js = win + L1; jl = kk; }
-                        if (q4 == 2) { jd = db + kk + 3; js = win + L3; jl = kk; }
-                        if (q4 == 3) {
+                        if (mode == B_TRIM || mode == B_MASK) {
                             uint8_t *d = db + kk;
                             d[0] = '\n'; d[1] = '+'; d[2] = '\n';
                             d[3 + kk] = '\n';
-                        }
-                    } else if (mode == B_GARBAGE) {
-                        if (q4 == 3) {
-                            uint8_t *d = db;
-                            d[0] = 'N'; d[1] = '\n'; d[2] = '+'; d[3] = '\n'; d[4] = '!'; d[5] = '\n';
-                        }
-                    } else if (mode == B_MASK) {
-                        const uint32_t L3 = LB(j + 3);
-                        if (q4 == 1) mask_copy(db, win + L1, win + L3, kk, p.min_baseq);
-                        if (q4 == 2) { jd = db + kk + 3; js = win + L3; jl = kk; }
-                        if (q4 == 3) {
-                            uint8_t *d = db + kk;
-                            d[0] = '\n'; d[1] = '+'; d[2] = '\n';
-                            d[3 + kk] = '\n';
+                        } else if (mode == B_GARBAGE) {
+                            db[0] = 'N'; db[1] = '\n'; db[2] = '+'; db[3] = '\n'; db[4] = '!'; db[5] = '\n';
                         }
                     }
                 }
-                tcopy(jd, js, jl);
+                if (jq) mask_copy(jd, js, jq, jl, p.min_baseq);
+                else tcopy(jd, js, jl);
             }
             fence_proxy_async();  // staging writes -> visible to the TMA store issued after the barrier
         } else if (OP == OP_DEMUX1 && p.sheet.Umax) {
@@ -834,10 +1031,10 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
         }
         if (tid == 0) M->chunk = atomicAdd(&st->ticket, 1u);
         __syncthreads();  // window, staging image and record arrays are reused by the next chunk
-        if (writable) {
-            const uint32_t span = shift + chunk_out;
-            uint8_t *g16 = p.out + (out_base - shift);
-            if (ORDERED) {
+        if (ORDERED) {
+            if (writable) {
+                const uint32_t span = shift + chunk_out;
+                uint8_t *g16 = p.out + (out_base - shift);
                 const uint32_t a = shift ? 16u : 0u;  // first whole 16-byte unit
                 const uint32_t b2 = span & ~15u;      // end of the last whole unit
                 if (b2 > a) {
@@ -858,11 +1055,21 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
                 } else {
                     for (uint32_t o = shift + tid; o < span; o += NT) g16[o] = stage[o];
                 }
-            } else if (tid == 0) {
-                bulk_s2g(g16, stage, (span + 15u) & ~15u);  // demux chunks own whole 16-byte units
+            }
+        } else if (tid == 0 && p.out) {
+            ChunkRow row;
+            row.base = demux_base;
+            row.first_group = (uint32_t)rec0;
+            row.n_groups = writable ? n_emit : 0u;
+            if (writable && demux_base + ((chunk_out + 15u) & ~15u) > p.out_cap) {
+                report_err(st, rec0, K_OUT_OVERFLOW);
+                row.n_groups = 0;
+            } else if (writable) {
+                bulk_s2g(p.out + demux_base, stage, (chunk_out + 15u) & ~15u);  // demux chunks own whole 16-byte units
                 bulk_commit();
                 store_pending = true;
             }
+            p.rows[c] = row;
         }
         FK_T(8);
     }
@@ -925,31 +1132,39 @@ static int launch_fast_one(const KParams &p, int sm_count, cudaStream_t stream, 
     return 1;
 }
 
-int fast_chunk_bytes() { return GeoS::CHUNK; }
+int fast_chunk_bytes(int geo) { return geo == GeoM::ID ? GeoM::CHUNK : GeoS::CHUNK; }
 
-bool fast_supported(int op, const KParams &p) {
+bool fast_supported(int geo, int op, const KParams &p) {
     if (op != OP_TRIM && op != OP_MASK && op != OP_DEMUX1 && op != OP_DEMUX2) return false;
     if (p.lpr != 4) return false;
     if (op == OP_DEMUX1 || op == OP_DEMUX2) {
         if (p.n_index || !p.sheet.hidx.n_classes || !p.sheet.fidx.table) return false;
-        if (fast_smem<GeoS>(p.sheet.S, p.sheet.hidx.n_classes, p.sheet.hidx.nwp, true) > 48u * 1024u) return false;
+        const uint32_t need = geo == GeoM::ID ? fast_smem<GeoM>(p.sheet.S, p.sheet.hidx.n_classes, p.sheet.hidx.nwp, true)
+                                              : fast_smem<GeoS>(p.sheet.S, p.sheet.hidx.n_classes, p.sheet.hidx.nwp, true);
+        if (need > 100u * 1024u) return false;
     }
     return true;
 }
 
-int launch_fast_kernel(int op, const KParams &p, int sm_count, void *stream_, const char **err) {
-    cudaStream_t stream = (cudaStream_t)stream_;
+template <class G>
+static int launch_fast_geo(int op, const KParams &p, int sm_count, cudaStream_t stream, const char **err) {
     const bool wide = p.sheet.wide != 0;
     switch (op) {
-        case OP_TRIM: return launch_fast_one<GeoS, OP_TRIM, 8>(p, sm_count, stream, err);
-        case OP_MASK: return launch_fast_one<GeoS, OP_MASK, 8>(p, sm_count, stream, err);
+        case OP_TRIM: return launch_fast_one<G, OP_TRIM, 8>(p, sm_count, stream, err);
+        case OP_MASK: return launch_fast_one<G, OP_MASK, 8>(p, sm_count, stream, err);
         case OP_DEMUX1:
-            return wide ? launch_fast_one<GeoS, OP_DEMUX1, 16>(p, sm_count, stream, err)
-                        : launch_fast_one<GeoS, OP_DEMUX1, 8>(p, sm_count, stream, err);
-        case OP_DEMUX2: return launch_fast_one<GeoS, OP_DEMUX2, 8>(p, sm_count, stream, err);
+            return wide ? launch_fast_one<G, OP_DEMUX1, 16>(p, sm_count, stream, err)
+                        : launch_fast_one<G, OP_DEMUX1, 8>(p, sm_count, stream, err);
+        case OP_DEMUX2: return launch_fast_one<G, OP_DEMUX2, 8>(p, sm_count, stream, err);
     }
-    *err = "operator not handled by the fast engine";
+    *err = "operator not handled by the lean engine";
     return -1;
+}
+
+int launch_fast_kernel(int geo, int op, const KParams &p, int sm_count, void *stream_, const char **err) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    return geo == GeoM::ID ? launch_fast_geo<GeoM>(op, p, sm_count, stream, err)
+                           : launch_fast_geo<GeoS>(op, p, sm_count, stream, err);
 }
 
 }  // namespace sk

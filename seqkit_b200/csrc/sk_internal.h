@@ -47,6 +47,7 @@ struct CfgB {  // 32 KiB chunks, 8 warps
 // Geometry of the lean engine (sk_fast.cu): the chunk is a whole number of scan threads (102 x 80 B),
 // the window holds no bytes before the chunk, 8 CTAs of 4 warps per SM.
 struct GeoS {
+    static constexpr int ID = 0;
     static constexpr int NT = 128;
     static constexpr int PPL = 5;
     static constexpr int WIN_MAX = NT * PPL * 16;       // 10240
@@ -56,6 +57,18 @@ struct GeoS {
     static constexpr int MAXLINES = 4 * MAXREC + 16;
     static constexpr int STAGE = WIN_MAX;
     static constexpr int MIN_CTAS = 8;
+};
+struct GeoM {  // 16 KiB chunks, 8 warps, 4 CTAs per SM: half the per-chunk fixed cost per record
+    static constexpr int ID = 1;
+    static constexpr int NT = 256;
+    static constexpr int PPL = 5;
+    static constexpr int WIN_MAX = NT * PPL * 16;       // 20480
+    static constexpr int CHUNK = 204 * PPL * 16;        // 16320
+    static constexpr int OVERHANG = WIN_MAX - CHUNK;    // 4160
+    static constexpr int MAXREC = NT;
+    static constexpr int MAXLINES = 4 * MAXREC + 16;
+    static constexpr int STAGE = WIN_MAX;
+    static constexpr int MIN_CTAS = 4;
 };
 constexpr int FAST_CCOUNT_MAX = 1024;  // per-sample counters live in shared memory up to this many samples
 inline int cfg_chunk_bytes(int cfg) { return cfg == CfgB::ID ? CfgB::CHUNK : CfgA::CHUNK; }
@@ -221,8 +234,8 @@ inline __host__ __device__ SmemLayout smem_layout(uint32_t S, uint32_t wide, uin
 int launch_chunk_kernel(int cfg, int op, const KParams &p, int sm_count, void *stream, const char **err);
 int chunk_kernel_smem_bytes(int cfg, uint32_t S, uint32_t wide, uint32_t n_classes, uint32_t nwp);
 // Lean engine (sk_fast.cu)
-int fast_chunk_bytes();
-bool fast_supported(int op, const KParams &p);
-int launch_fast_kernel(int op, const KParams &p, int sm_count, void *stream, const char **err);
+int fast_chunk_bytes(int geo);
+bool fast_supported(int geo, int op, const KParams &p);
+int launch_fast_kernel(int geo, int op, const KParams &p, int sm_count, void *stream, const char **err);
 
 }  // namespace sk
