@@ -265,6 +265,8 @@ def main():
         step()
     res = eng.wait()
     assert res.status == 0 and res.n_records == P, (res.status, res.n_records)
+    # sk_result.reserved: bit0 = the lean engine (sk_fast.cu) ran, bit1 = it was re-run on the general engine
+    assert res.reserved == 1, "bench workload must run on the lean engine without a re-run (got %d)" % res.reserved
     pairs_done = res.n_records
 
     sampler = ClockSampler(local_rank)
@@ -307,10 +309,21 @@ def main():
     dom = 0 if pass_ms[0] >= pass_ms[1] else 1
     peak, peak_src = peaks()
     achieved = bytes_pass[dom] / (pass_ms[dom] * 1e-3) / 1e9
+    geo = "GeoS" if os.environ.get("SK_FAST_GEO") == "0" else "GeoM"
+    kname = lambda k: "sk_fast_kernel<%s, OP_DEMUX%d>" % (geo, k + 1)
+    # DRAM traffic of the dominant kernel from the committed ncu capture (dram__bytes_read + write, 1 M pairs
+    # per launch), scaled to this launch's pairs; null when the summary is missing
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            tj = json.load(f)
+        traffic = tj["dram_bytes_per_launch"]["DEMUX%d" % (dom + 1)] * (P / float(tj["pairs_per_launch"]))
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "sk_chunk_kernel<OP_DEMUX%d>" % (dom + 1), "peak_source": peak_src,
+                "traffic": traffic, "kernel": kname(dom), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": bytes_pass[dom], "ms_per_launch": pass_ms[dom],
-                "other_kernel": {"kernel": "sk_chunk_kernel<OP_DEMUX%d>" % (2 - dom), "ms_per_launch": pass_ms[1 - dom],
+                "other_kernel": {"kernel": kname(1 - dom), "ms_per_launch": pass_ms[1 - dom],
                                  "achieved": bytes_pass[1 - dom] / (pass_ms[1 - dom] * 1e-3) / 1e9},
                 "step_bytes": sum(bytes_pass), "step_achieved": sum(bytes_pass) / (ms_step * 1e-3) / 1e9}
     identified = counts[N_SAMPLES + 1]

@@ -89,7 +89,8 @@ typedef struct sk_result {
     uint32_t n_chunks[2];           /* rows of the demux slice table per output stream */
     uint32_t n_events;              /* ambiguity events (fasta_demultiplex.rs:184-188) */
     uint32_t gpu_launches;          /* kernels this call enqueued */
-    uint32_t reserved;
+    uint32_t reserved;              /* diagnostic: bit0 = the lean engine (sk_fast.cu) ran, bit1 = the operator met
+                                       something outside its limits and was re-run on the general engine */
     float pass_ms[SK_N_INPUTS];     /* device time of the chunk-engine kernel over each input stream
                                        (CUDA events on the slot's stream; only with sk_set_profiling) */
 } sk_result;
@@ -173,11 +174,13 @@ const void *sk_out_dev(sk_ctx *ctx, uint32_t slot, uint32_t which);
  * before it; the copy is ordered on the slot's stream). */
 int sk_download_out(sk_ctx *ctx, uint32_t slot, uint32_t which, void *host, uint64_t n);
 
-/* Demultiplex side tables (valid after sk_wait).  The kernels write the records of a chunk grouped by
- * sample, input order kept inside a sample ("stable per-sample compaction", chunk by chunk).  For
- * output stream m, row c describes chunk c: its groups are groups[first_group .. first_group+n_groups),
- * laid out back to back from byte `base` of output stream m.  Appending, for every sample, its groups
- * over c = 0..n_chunks-1 gives that sample's file content in input order (fasta_demultiplex.rs:196-238). */
+/* Demultiplex side tables (valid after sk_wait).  The kernels write the emitted records of a chunk back
+ * to back as a sequence of *groups* -- runs of bytes that belong to one sample, in input order inside a
+ * sample (the lean engine emits one group per record in input order; the general engine groups a
+ * chunk's records by sample).  For output stream m, row c describes chunk c: its groups are
+ * groups[first_group .. first_group+n_groups), laid out back to back from byte `base` of output
+ * stream m.  Appending, for every sample, its groups over c = 0..n_chunks-1 gives that sample's file
+ * content in input order (fasta_demultiplex.rs:196-238). */
 typedef struct sk_group {
     uint16_t sample;
     uint16_t len; /* bytes */

@@ -83,7 +83,7 @@ struct sk_ctx {
     uint2 *d_ftab = nullptr;      // FastIdx
     uint16_t *d_fnext = nullptr;
     bool fast_sheet = false;  // the sheet's FastIdx is usable
-    int fast_geo = 0;   // lean-engine geometry: 0 = GeoS (8 KiB chunks), 1 = GeoM (16 KiB chunks); SK_FAST_GEO
+    int fast_geo = 1;   // lean-engine geometry: 0 = GeoS (8 KiB chunks), 1 = GeoM (16 KiB chunks, default); SK_FAST_GEO
     bool fast = true;   // lean engine (sk_fast.cu) for trim / mask / header-route demultiplex; SK_NO_FAST=1 disables
     int cfg = 0;  // chunk-engine geometry: 0 = CfgA (16 KiB chunks, 4 warps), 1 = CfgB (32 KiB chunks, 8 warps)
 };
@@ -206,11 +206,11 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
         for (int i = 0; i < nin; i++) {
             CKC(cudaMalloc(&s.in[i], B + 64));
             s.in_cap[i] = B;
-            CKC(cudaMalloc(&s.tile_lines[i], (uint64_t)ctx->max_chunks * 8));
+            CKC(cudaMalloc(&s.tile_lines[i], ((uint64_t)ctx->max_chunks + 8) * 8));  // look-back reads whole 4-entry blocks
         }
         for (int i = 0; i < 2; i++) CKC(cudaMalloc(&s.out[i], out_cap));
         s.out_cap = out_cap;
-        CKC(cudaMalloc(&s.tile_out, (uint64_t)ctx->max_chunks * 8));
+        CKC(cudaMalloc(&s.tile_out, ((uint64_t)ctx->max_chunks + 8) * 8));
         CKC(cudaMalloc(&s.stats, sizeof(DevStats) * SK_N_INPUTS));
         CKC(cudaMallocHost(&s.stats_h, sizeof(DevStats) * SK_N_INPUTS));
         memset(s.stats_h, 0, sizeof(DevStats) * SK_N_INPUTS);

@@ -103,6 +103,67 @@ static __device__ __noinline__ uint64_t lookback(uint64_t *tiles, uint32_t c, ui
     return excl;
 }
 
+// Decoupled look-back in two halves, with a 256-entry window per round (every lane reads eight
+// consecutive words with four 16-byte loads).  lookback_publish makes this chunk's aggregate visible as
+// early as possible; lookback_consume, called by one whole warp whenever the prefix is needed, returns
+// the exclusive prefix over all earlier chunks and publishes the inclusive one.  Chunks are handed out
+// by a ticket counter, so every predecessor is owned by a resident CTA that never waits on a later chunk.
+__device__ __forceinline__ void lookback_publish(uint64_t *tiles, uint32_t c, uint64_t agg) {
+    ts_store(&tiles[c], c == 0 ? TS_INC : TS_AGG, agg);
+}
+static __device__ __noinline__ uint64_t lookback_consume(uint64_t *tiles, uint32_t c, uint64_t agg, int lane) {
+    if (c == 0) return 0;
+    constexpr int E = 8;  // entries per lane and round (256-entry window)
+    uint64_t excl = 0;
+    int64_t hi = (int64_t)c - 1;  // nearest predecessor not yet accounted for
+    for (;;) {
+        // lane L takes the aligned block of E entries B = hi / E - L; entries above hi are skipped
+        const int64_t blk = (hi / E) - lane;
+        uint64_t lsum = 0;
+        bool lhas = false;
+        if (blk < 0) {
+            lhas = true;  // before chunk 0: inclusive prefix 0
+        } else {
+            const uint64_t *q = tiles + blk * E;
+            uint64_t w[E];
+            for (;;) {
+#pragma unroll
+                for (int k = 0; k < E; k += 2)
+                    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[k]), "=l"(w[k + 1]) : "l"(q + k) : "memory");
+                bool wait = false;
+#pragma unroll
+                for (int k = E - 1; k >= 0; k--) {
+                    if (blk * E + k > hi) continue;
+                    if ((w[k] >> 62) == TS_INVALID) wait = true;
+                    if ((w[k] >> 62) == TS_INC) break;  // entries below an inclusive one are not needed
+                }
+                if (!wait) break;
+                __nanosleep(40);
+            }
+#pragma unroll
+            for (int k = E - 1; k >= 0; k--) {
+                if (blk * E + k > hi || lhas) continue;
+                lsum += w[k] & TS_VMASK;
+                if ((w[k] >> 62) == TS_INC) lhas = true;
+            }
+        }
+        const uint32_t inc = __ballot_sync(0xffffffffu, lhas);
+        if (inc) {
+            const int first = __ffs(inc) - 1;
+            excl += warp_sum64(lane <= first ? lsum : 0);
+            break;
+        }
+        excl += warp_sum64(lsum);
+        hi = ((hi / E) - 32) * E + (E - 1);  // the block below the window, whole
+    }
+    if (lane == 0) ts_store(&tiles[c], TS_INC, excl + agg);
+    return excl;
+}
+static __device__ __forceinline__ uint64_t lookback_wide(uint64_t *tiles, uint32_t c, uint64_t agg, int lane) {
+    if (lane == 0) lookback_publish(tiles, c, agg);
+    return lookback_consume(tiles, c, agg, lane);
+}
+
 // Exclusive block scan of one u32 per thread; `scratch` holds 2*(NT/32) words (double buffered by
 // `flip`, so that one barrier per call suffices).
 template <int NT>

@@ -68,6 +68,50 @@ __device__ __forceinline__ uint32_t bits_below(int hi) {
     return hi <= 0 ? 0u : (hi >= 32 ? 0xFFFFFFFFu : (1u << hi) - 1u);
 }
 
+// Exclusive block scan of one u32 per thread (4 or 8 warps): warp scans by shuffle, then every thread
+// sums the warp totals out of two 16-byte shared-memory reads.  `scratch` holds 2*NW words (double
+// buffered by `flip`, one barrier per call).
+template <int NT>
+__device__ __forceinline__ uint32_t block_scan_fast(uint32_t v, uint32_t *scratch, uint32_t &flip, uint32_t &total) {
+    constexpr int NW = NT / 32;
+    static_assert(NW == 4 || NW == 8, "block_scan_fast: 4 or 8 warps");
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    uint32_t *s = scratch + flip * NW;
+    flip ^= 1u;
+    if (lane == 31) s[w] = x;
+    __syncthreads();
+    const uint4 a = *(const uint4 *)s;
+    uint32_t before = (w > 0 ? a.x : 0u) + (w > 1 ? a.y : 0u) + (w > 2 ? a.z : 0u) + (w > 3 ? a.w : 0u);
+    uint32_t all = a.x + a.y + a.z + a.w;
+    if (NW == 8) {
+        const uint4 b = *(const uint4 *)(s + 4);
+        before += (w > 4 ? b.x : 0u) + (w > 5 ? b.y : 0u) + (w > 6 ? b.z : 0u);
+        all += b.x + b.y + b.z + b.w;
+    }
+    total = all;
+    return before + x - v;
+}
+
+// mbarrier wait that parks the thread in hardware for up to the hinted time per attempt
+__device__ __forceinline__ void mbar_wait_parked(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+        "@P1 bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(0x989680u)
+        : "memory");
+}
 #ifdef SK_PHASE_TIMING
 #define FK_T(i)                                              \
     do {                                                     \
@@ -435,6 +479,8 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
     const uint32_t hcls_words = (OP == OP_DEMUX1) ? p.sheet.hidx.n_classes * HIDX_CLS_ROWS * p.sheet.hidx.nwp : 0u;
     uint32_t *ccount = hcls + ((hcls_words + 3u) & ~3u);
     const bool cc_smem = (OP == OP_DEMUX1) && S <= (uint32_t)FAST_CCOUNT_MAX;
+    uint8_t *sh_ulen = (uint8_t *)(ccount + (cc_smem ? ((S + 3u) & ~3u) : 0u));  // UMI length of every sample
+    constexpr int NW = NT / 32;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     DevStats *st = p.stats;
@@ -442,6 +488,8 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
     if (tid == 0) mbar_init(&M->mbar, 1);
     if (IS_DEMUX) {
         for (uint32_t i = tid; i < 256; i += NT) sh_lut[i] = p.sheet.lut[i];
+        for (uint32_t i = tid; i < S; i += NT)
+            sh_ulen[i] = (uint8_t)(p.sheet.wide ? __popcll(((const unsigned long long *)p.sheet.umask)[i]) : __popc(p.sheet.umask[i]));
         if (OP == OP_DEMUX1) {
             for (uint32_t i = tid; i < hcls_words; i += NT) hcls[i] = p.sheet.hidx.cls[i];
             if (cc_smem)
@@ -454,6 +502,7 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
 
 #ifdef SK_PHASE_TIMING
     unsigned long long ph[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long ph_x = 0;  // tid 0: trim warp's plan; tid NT/2: header warp's plan; last warp lane 0: look-back
     long long t_prev = clock64();
 #endif
     uint32_t parity = 0, flip = 0;
@@ -461,6 +510,8 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
     uint32_t my_total = 0, my_ident = 0;  // DEMUX1 counters of this thread's records (flushed at the end)
     const bool fused = IS_DEMUX && p.fused_trim >= 0;
 
+    // Chunks are handed out by a ticket counter (a static round-robin deal was measured slower: one
+    // lagging SM then holds up the look-back of every CTA behind it).
     for (;;) {
         const uint32_t c = M->chunk;
         if (c >= p.n_chunks) break;
@@ -483,7 +534,7 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
             if (o < (uint32_t)G::WIN_MAX) win[o] = (o < wlen) ? p.in[c0 + o] : (uint8_t)0;
         }
         if (bulk) {
-            mbar_wait(&M->mbar, parity);
+            mbar_wait_parked(&M->mbar, parity);
             parity ^= 1;
         }
         if (bulk != (uint32_t)G::WIN_MAX) __syncthreads();
@@ -524,20 +575,14 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
         const uint32_t cnt_all = __popc(m0) + __popc(m1) + __popc(m2);
         const uint32_t cnt_chunk = tid < TCH ? cnt_all : 0u;
         uint32_t tot;
-        const uint32_t pre = block_excl_scan<NT>((cnt_chunk << 16) | cnt_all, M->scratch, flip, tot);
+        const uint32_t pre = block_scan_fast<NT>((cnt_chunk << 16) | cnt_all, M->scratch, flip, tot);
         const uint32_t extra = (c == 0) ? 1u : 0u;
         const uint32_t nls = (tot & 0xFFFFu) + extra;
         const uint32_t nls_chunk = (tot >> 16) + extra;
         FK_T(2);
 
-        // ---- P3 look-back for the global line index (warp 0) while everybody writes the line table
-        if (warp == 0) {
-            const uint64_t excl = lookback(p.tile_lines, c, nls_chunk, lane);
-            if (lane == 0) {
-                M->g0 = excl;
-                if (c == p.n_chunks - 1) st->n_lines = excl + nls_chunk;
-            }
-        }
+        // ---- P3 publish this chunk's line count for the look-back; everybody writes the line table
+        if (tid == NT - 32) lookback_publish(p.tile_lines, c, nls_chunk);
         {
             uint32_t idx = (pre & 0xFFFFu) + extra;
             if (tid == 0 && extra) ls[0] = 0;
@@ -562,244 +607,326 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
         FK_T(3);
 #define LB(x) ((uint32_t)ls[(x)])
 
-        // ---- P4 records owned by this chunk (framing by line count: record i = lines 4i..4i+3)
-        const uint64_t g0 = M->g0;
-        const uint32_t j0 = (4u - (uint32_t)(g0 & 3u)) & 3u;
-        const uint64_t rec0 = (g0 + j0) >> 2;
-        uint32_t nrec = j0 < nls_chunk ? (nls_chunk - 1 - j0) / 4u + 1u : 0u;
-        if (rec0 >= p.rec_limit) nrec = 0;
-        else if ((uint64_t)nrec > p.rec_limit - rec0) nrec = (uint32_t)(p.rec_limit - rec0);
-        bool bail = false;
-        if (nrec) {
-            uint32_t jend = j0 + nrec * 4u;
-            const bool eof_ok = at_end && p.final_batch;
-            if (jend >= nls && !eof_ok) {
-                if (at_end) {  // non-final batch: the trailing incomplete record(s) stay for the next batch
-                    nrec = nls > j0 + 4u ? (nls - j0 - 5u) / 4u + 1u : 0u;
-                    jend = j0 + nrec * 4u;
-                } else {
-                    bail = true;  // a record runs past the overhang
-                }
-            }
-            if (!bail && nrec) {
-                const uint32_t need = jend < nls ? jend : nls - 1;
-                if (need >= (uint32_t)MAXLINES || nrec > (uint32_t)MAXREC) bail = true;
-            }
-            if (bail) nrec = 0;
+        // ---- P4 framing.  Record i is lines 4i..4i+3 of the stream (common.rs:106-112), so the chunk needs
+        // the global index g0 of its first line -- the look-back result, which every resident CTA would
+        // otherwise wait for at the same point of every chunk.  The framing is therefore guessed from the
+        // text (a line that starts with '@' whose second successor starts with '+'), the plan runs on the
+        // guess while the last warp collects the real prefix, and the guess is checked against it
+        // afterwards; a wrong guess (possible on malformed or adversarial text only) repeats the plan
+        // with the true framing.  The plan has no side effects outside the per-record arrays.
+        bool spec = false;
+        uint32_t j0 = 0;
+        if (c != 0 && p.rec_limit == ~0ull && nls >= 6u) {
+            const uint4 l8 = *(const uint4 *)ls;  // the first eight line starts
+            const uint32_t s0 = l8.x & 0xFFFFu, s1 = l8.x >> 16, s2 = l8.y & 0xFFFFu, s3 = l8.y >> 16;
+            const uint32_t s4 = l8.z & 0xFFFFu, s5 = l8.z >> 16;
+            const uint32_t b0 = win[s0], b1 = win[s1], b2 = win[s2], b3 = win[s3], b4 = win[s4], b5 = win[s5];
+            const bool k0 = b0 == '@' && b2 == '+', k1 = b1 == '@' && b3 == '+';
+            const bool k2 = b2 == '@' && b4 == '+', k3 = b3 == '@' && b5 == '+';
+            j0 = k0 ? 0u : k1 ? 1u : k2 ? 2u : 3u;
+            spec = (k0 || k1 || k2 || k3) && j0 < nls_chunk;
         }
-        if (tid == 0 && nrec) {
-            atomicAdd(&st->n_records, (unsigned long long)nrec);
-            atomicMax(&st->consumed, (unsigned long long)(c0 + LB(j0 + nrec * 4u)));
+        const bool speculated = spec;
+#ifdef SK_PHASE_TIMING
+        const long long t_plan0 = clock64();
+#endif
+        if (!spec) {
+            if (warp == NW - 1) {
+                const uint64_t excl = lookback_consume(p.tile_lines, c, nls_chunk, lane);
+                if (lane == 0) M->g0 = excl;
+            }
+            __syncthreads();
+            j0 = (4u - (uint32_t)(M->g0 & 3u)) & 3u;
         }
-
-        // ---- P5 plan, one lane per record, whole warps per task and every step warp-synchronous (lanes
-        // that took different branches meet again at the __syncwarp that closes the step).  Fused
-        // trim+demultiplex: the quality trim runs on the lower half of the CTA, the header work on
-        // the upper half.
         const uint32_t tl = fused ? (uint32_t)tid % (NT / 2) : (uint32_t)tid;
         const uint32_t tstride = fused ? NT / 2 : NT;
         const bool do_trim = (fused && tid < NT / 2) || OP == OP_TRIM;
         const bool do_main = (!fused || tid >= NT / 2) && OP != OP_TRIM;
         const int trim_q = OP == OP_TRIM ? (int)p.min_baseq : p.fused_trim;
+        uint32_t nrec = 0;
+        uint64_t g0 = 0;
+        bool bail = false;
+        for (;;) {
+            nrec = j0 < nls_chunk ? (nls_chunk - 1 - j0) / 4u + 1u : 0u;
+            if (!spec) {
+                g0 = M->g0;
+                const uint64_t first = (g0 + j0) >> 2;
+                if (first >= p.rec_limit) nrec = 0;
+                else if ((uint64_t)nrec > p.rec_limit - first) nrec = (uint32_t)(p.rec_limit - first);
+            }
+            bail = false;
+            if (nrec) {
+                uint32_t jend = j0 + nrec * 4u;
+                const bool eof_ok = at_end && p.final_batch;
+                if (jend >= nls && !eof_ok) {
+                    if (at_end) {  // non-final batch: the trailing incomplete record(s) stay for the next batch
+                        nrec = nls > j0 + 4u ? (nls - j0 - 5u) / 4u + 1u : 0u;
+                        jend = j0 + nrec * 4u;
+                    } else {
+                        bail = true;  // a record runs past the overhang
+                    }
+                }
+                if (!bail && nrec) {
+                    const uint32_t need = jend < nls ? jend : nls - 1;
+                    if (need >= (uint32_t)MAXLINES || nrec > (uint32_t)MAXREC) bail = true;
+                }
+                if (bail) nrec = 0;
+            }
 
-        if (do_trim) {
-            for (uint32_t r0 = 0; r0 < nrec; r0 += tstride) {
-                const uint32_t r = r0 + tl;
-                const bool has = r < nrec;
-                const uint32_t j = j0 + (has ? r : 0u) * 4u;
-                const uint32_t L0 = LB(j), L1 = LB(j + 1), L2 = LB(j + 2), L3 = LB(j + 3), L4 = LB(j + 4);
-                uint8_t mode = OP == OP_TRIM ? B_NONE : B_FAIL;
-                uint32_t kk = 0, body = 0;
-                bool ok = has;
-                if (OP == OP_TRIM) {
-                    if (has && win[L0] != '@') {  // fasta_trim_by_quality.rs:20-22
-                        report_err(st, rec0 + r, K_BAD_HEADER);
-                        ok = false;
-                    }
-                } else {
-                    ok = has && L1 > L0 && win[L1 - 1] == '\n';
-                }
-                bool fine;
-                if (trim_q <= 222) {
-                    fine = plan_trim_warp(win, ok, L1, L2, L3, L4, trim_q, mode, kk, body);
-                } else {
-                    fine = ok ? plan_trim_body(win, L1, L2, L3, L4, trim_q, mode, kk, body) : true;
-                    __syncwarp();
-                }
-                if (has) {
+            // The last warp collects the real prefix while the others plan (it carries records of its own
+            // only in very dense chunks), so the inclusive prefix is also published as early as possible.
+            const bool lb_early = (fused ? (uint32_t)(NT / 2 - 32) : (uint32_t)(NT - 32)) >= nrec;
+            if (spec && warp == NW - 1 && lb_early) {
+                const uint64_t excl = lookback_consume(p.tile_lines, c, nls_chunk, lane);
+                if (lane == 0) M->g0 = excl;
+#ifdef SK_PHASE_TIMING
+                if (lane == 0) ph_x += (unsigned long long)(clock64() - t_plan0);  // look-back done
+#endif
+            }
+
+            // ---- P5 plan, one lane per record, whole warps per task and every step warp-synchronous
+            // (lanes that took different branches meet again at the __syncwarp that closes the step).
+            // Fused trim+demultiplex: the quality trim runs on the lower half of the CTA, the header work
+            // on the upper half.  Failures are left in the record arrays and reported in P6.
+            if (do_trim) {
+                for (uint32_t r0 = 0; r0 < nrec; r0 += tstride) {
+                    const uint32_t r = r0 + tl;
+                    const bool has = r < nrec;
+                    const uint32_t j = j0 + (has ? r : 0u) * 4u;
+                    const uint32_t L0 = LB(j), L1 = LB(j + 1), L2 = LB(j + 2), L3 = LB(j + 3), L4 = LB(j + 4);
+                    uint8_t mode = OP == OP_TRIM ? B_NONE : B_FAIL;
+                    uint32_t kk = 0, body = 0, errk = 0;
+                    bool ok = has;
                     if (OP == OP_TRIM) {
-                        uint32_t outlen = 0;
-                        if (!ok) {
-                            mode = B_NONE;
-                        } else if (!fine) {
-                            report_err(st, rec0 + r, K_SEQ_SHORT);
-                            mode = B_NONE;
-                        } else {
-                            outlen = (L1 - L0) + body;  // header verbatim (:23) + body
+                        if (has && win[L0] != '@') {  // fasta_trim_by_quality.rs:20-22
+                            errk = K_BAD_HEADER;
+                            ok = false;
                         }
-                        r_outlen[r] = (uint16_t)(outlen > 0x3FFFu ? 0x3FFFu : outlen);
-                    } else if (!ok || !fine) {
-                        mode = B_FAIL;
+                    } else {
+                        ok = has && L1 > L0 && win[L1 - 1] == '\n';
                     }
-                    r_k[r] = (uint16_t)kk;
-                    r_body[r] = (uint16_t)(body > 0xFFFFu ? 0xFFFFu : body);
-                    r_mode[r] = mode;
+                    bool fine;
+                    if (trim_q <= 222) {
+                        fine = plan_trim_warp(win, ok, L1, L2, L3, L4, trim_q, mode, kk, body);
+                    } else {
+                        fine = ok ? plan_trim_body(win, L1, L2, L3, L4, trim_q, mode, kk, body) : true;
+                        __syncwarp();
+                    }
+                    if (has) {
+                        if (OP == OP_TRIM) {
+                            uint32_t outlen = 0;
+                            if (!ok) {
+                                mode = B_NONE;
+                            } else if (!fine) {
+                                errk = K_SEQ_SHORT;
+                                mode = B_NONE;
+                            } else {
+                                outlen = (L1 - L0) + body;  // header verbatim (:23) + body
+                            }
+                            if (mode == B_NONE) kk = errk;  // a failed record keeps its failure kind here
+                            r_outlen[r] = (uint16_t)(outlen > 0x3FFFu ? 0x3FFFu : outlen);
+                        } else if (!ok || !fine) {
+                            mode = B_FAIL;
+                        }
+                        r_k[r] = (uint16_t)kk;
+                        r_body[r] = (uint16_t)(body > 0xFFFFu ? 0xFFFFu : body);
+                        r_mode[r] = mode;
+                    }
                 }
             }
-        }
-        if (do_main) {
-            for (uint32_t r0 = 0; r0 < nrec; r0 += tstride) {
-                const uint32_t r = r0 + tl;
-                const bool has = r < nrec;
-                const uint32_t j = j0 + (has ? r : 0u) * 4u;
-                const uint64_t rec = rec0 + r;
-                const uint32_t L0 = LB(j), L1 = LB(j + 1);
-                if (OP == OP_MASK) {
-                    if (!has) continue;
-                    uint8_t mode = B_NONE;
-                    uint32_t kk = 0, outlen = 0;
-                    if (win[L0] != '@') {  // fasta_mask_by_quality.rs:21-23
-                        report_err(st, rec, K_BAD_HEADER);
-                    } else {
-                        const uint32_t L2 = LB(j + 2), L3 = LB(j + 3), L4 = LB(j + 4);
-                        uint32_t sl = L2 - L1, ql = L4 - L3;
-                        if (sl && win[L2 - 1] == '\n') sl--;  // :32
-                        if (ql && win[L4 - 1] == '\n') ql--;  // :33
-                        if (sl != ql) {                       // :35-37
-                            report_err(st, rec, K_LEN_MISMATCH);
+            if (do_main) {
+                for (uint32_t r0 = 0; r0 < nrec; r0 += tstride) {
+                    const uint32_t r = r0 + tl;
+                    const bool has = r < nrec;
+                    const uint32_t j = j0 + (has ? r : 0u) * 4u;
+                    const uint32_t L0 = LB(j), L1 = LB(j + 1);
+                    if (OP == OP_MASK) {
+                        if (!has) continue;
+                        uint8_t mode = B_NONE;
+                        uint32_t kk = 0, outlen = 0;
+                        if (win[L0] != '@') {  // fasta_mask_by_quality.rs:21-23
+                            kk = K_BAD_HEADER;
                         } else {
-                            mode = B_MASK;
-                            kk = sl;
-                            outlen = (L1 - L0) + 2 * sl + 4;  // header, masked, "\n+\n", qual, "\n"  (:26,:44)
+                            const uint32_t L2 = LB(j + 2), L3 = LB(j + 3), L4 = LB(j + 4);
+                            uint32_t sl = L2 - L1, ql = L4 - L3;
+                            if (sl && win[L2 - 1] == '\n') sl--;  // :32
+                            if (ql && win[L4 - 1] == '\n') ql--;  // :33
+                            if (sl != ql) {                       // :35-37
+                                kk = K_LEN_MISMATCH;
+                            } else {
+                                mode = B_MASK;
+                                kk = sl;
+                                outlen = (L1 - L0) + 2 * sl + 4;  // header, masked, "\n+\n", qual, "\n"  (:26,:44)
+                            }
                         }
-                    }
-                    r_k[r] = (uint16_t)kk;
-                    r_mode[r] = mode;
-                    r_outlen[r] = (uint16_t)(outlen > 0x3FFFu ? 0x3FFFu : outlen);
-                } else if (OP == OP_DEMUX1) {
-                    // fasta_demultiplex.rs:117-194: validate, locate the barcode, match, decide
-                    int sample = -1;
-                    uint32_t alen = 0, blen = 0, cut0 = 0, cut1 = 0, taglen = 0;
-                    // step 1: header checks and the leftmost " BC:x" (:118-120, :138-141)
-                    bool live = has;
-                    uint32_t stp = 0;
-                    if (live) {
-                        if (win[L0] != '@') {
-                            report_err(st, rec, K_BAD_HEADER);
-                            live = false;
-                        } else if (fused && !(L1 > L0 && win[L1 - 1] == '\n')) {
-                            report_err(st, rec, K_TRUNC_FUSED);
-                            live = false;
-                        } else if (!bc_find16(win, sh_lut, L0, L1, stp)) {
-                            report_err(st, rec, K_NO_BC);
-                            live = false;
+                        r_k[r] = (uint16_t)kk;  // a failed record (B_NONE) keeps its failure kind here
+                        r_mode[r] = mode;
+                        r_outlen[r] = (uint16_t)(outlen > 0x3FFFu ? 0x3FFFu : outlen);
+                    } else if (OP == OP_DEMUX1) {
+                        // fasta_demultiplex.rs:117-194: validate, locate the barcode, match, decide.
+                        // Outcome in the record arrays: sample >= 0 assigned; -2 ambiguous (best, last,
+                        // mismatches in alen, blen, taglen); -1 unassigned (taglen = failure kind, or 0xFF
+                        // for a record that never reached the match).
+                        int sample = -1;
+                        uint32_t alen = 0, blen = 0, cut0 = 0, cut1 = 0, taglen = 0xFFu;
+                        // step 1: header checks and the leftmost " BC:x" (:118-120, :138-141)
+                        bool live = has;
+                        uint32_t stp = 0;
+                        if (live) {
+                            if (win[L0] != '@') {
+                                taglen = K_BAD_HEADER;
+                                live = false;
+                            } else if (fused && !(L1 > L0 && win[L1 - 1] == '\n')) {
+                                taglen = K_TRUNC_FUSED;
+                                live = false;
+                            } else if (!bc_find16(win, sh_lut, L0, L1, stp)) {
+                                taglen = K_NO_BC;
+                                live = false;
+                            }
                         }
-                    }
-                    __syncwarp();
-                    // step 2: the greedy class run must be exactly L long (:38, :148-150)
-                    const uint32_t Lb = p.sheet.L;
-                    uint32_t raw[NWMAX + 1];
-                    const uint32_t bs = stp + 4;
-                    if (live) {
-                        cut0 = stp - L0;
-                        cut1 = cut0 + 4 + Lb;
-                        load_raw<NWMAX + 1>(win, bs, (Lb + 4u) >> 2, raw);
-                        if (!class_run_is<NWMAX + 1>(raw, sh_lut, Lb, L1 - bs)) {
-                            report_err(st, rec, K_BC_LEN);
-                            live = false;
+                        __syncwarp();
+                        // step 2: the greedy class run must be exactly L long (:38, :148-150)
+                        const uint32_t Lb = p.sheet.L;
+                        uint32_t raw[NWMAX + 1];
+                        const uint32_t bs = stp + 4;
+                        if (live) {
+                            cut0 = stp - L0;
+                            cut1 = cut0 + 4 + Lb;
+                            load_raw<NWMAX + 1>(win, bs, (Lb + 4u) >> 2, raw);
+                            if (!class_run_is<NWMAX + 1>(raw, sh_lut, Lb, L1 - bs)) {
+                                taglen = K_BC_LEN;
+                                live = false;
+                            }
                         }
-                    }
-                    __syncwarp();
-                    // step 3: match against the sheet and decide (:154-194)
-                    if (live) {
-                        uint32_t lowest, best, last;
-                        fidx_match<NWMAX + 1>(raw, p.sheet.hidx, p.sheet.fidx, hcls, S, lowest, best, last);
-                        my_total++;                // :169
-                        if (lowest <= 1u) {        // :172
-                            if (best == last) {    // :173-178
-                                sample = (int)best;
-                                my_ident++;
-                                if (cc_smem) atomicAdd(&ccount[best], 1u);
-                                else atomicAdd(&p.counts[best], 1ull);
-                            } else {  // :184-188
-                                sample = -2;
-                                const uint32_t ei = atomicAdd(&st->n_events, 1u);
-                                if (ei < p.events_cap) {
-                                    Event ev;
-                                    ev.record = (uint32_t)rec;
-                                    ev.bc_off = (uint32_t)(c0 + bs);
-                                    ev.bc_off2 = 0xFFFFFFFFu;
-                                    ev.best = (int16_t)best;
-                                    ev.last = (int16_t)last;
-                                    ev.mismatches = lowest;
-                                    p.events[ei] = ev;
-                                } else {
-                                    atomicOr(&st->flags, F_EVENTS_OVERFLOW);
+                        __syncwarp();
+                        // step 3: match against the sheet and decide (:154-194)
+                        if (live) {
+                            uint32_t lowest, best, last;
+                            fidx_match<NWMAX + 1>(raw, p.sheet.hidx, p.sheet.fidx, hcls, S, lowest, best, last);
+                            taglen = 0;
+                            if (lowest <= 1u) {        // :172
+                                if (best == last) {    // :173-178
+                                    sample = (int)best;
+                                } else {  // :184-188
+                                    sample = -2;
+                                    alen = best;
+                                    blen = last;
+                                    taglen = lowest;
                                 }
                             }
                         }
-                    }
-                    __syncwarp();
-                    if (sample >= 0) {
-                        header_pieces(win, L0, L1, L0 + cut0, L0 + cut1, alen, blen);  // drain (:145) + trim_end (:206)
-                        const uint32_t ul = p.sheet.wide ? (uint32_t)__popcll(((const unsigned long long *)p.sheet.umask)[sample])
-                                                         : (uint32_t)__popc(p.sheet.umask[sample]);
-                        taglen = ul ? 5 + ul : 0;  // " UMI:" + umi (:207)
-                    }
-                    __syncwarp();
-                    if (has) {
-                        r_sample[r] = (int16_t)sample;
-                        r_alen[r] = (uint16_t)alen;
-                        r_blen[r] = (uint16_t)blen;
-                        r_cut0[r] = (uint16_t)cut0;
-                        r_cut1[r] = (uint16_t)cut1;
-                        r_taglen[r] = (uint8_t)taglen;
-                    }
-                } else if (OP == OP_DEMUX2) {
-                    // fasta_demultiplex.rs:215-237: mate 2 of an assigned pair
-                    int sample = (has && rec < p.r1_stats->n_records) ? (int)p.assign[rec] : -1;
-                    uint32_t alen = 0, blen = 0, cut1 = 0, taglen = 0;
-                    if (!p.out) sample = -1;
-                    uint32_t c0h = L1, c1h = L1, fa = 0;
-                    const bool found = sample >= 0 && bc_find16(win, sh_lut, L0, L1, fa);  // :219-227
-                    __syncwarp();
-                    if (found) {
-                        c0h = fa;
-                        c1h = class_run_end(win, sh_lut, fa + 4, L1);
-                    }
-                    __syncwarp();
-                    if (sample >= 0) {
-                        header_pieces(win, L0, L1, c0h, c1h, alen, blen);  // :229
-                        cut1 = c1h - L0;
-                        const uint32_t ul = p.sheet.wide ? (uint32_t)__popcll(((const unsigned long long *)p.sheet.umask)[sample])
-                                                         : (uint32_t)__popc(p.sheet.umask[sample]);
-                        taglen = ul ? 5 + ul : 0;
-                        if (fused && !(L1 > L0 && win[L1 - 1] == '\n')) {
-                            report_err(st, rec, K_TRUNC_FUSED);
-                            sample = -1;
+                        __syncwarp();
+                        if (sample >= 0) {
+                            header_pieces(win, L0, L1, L0 + cut0, L0 + cut1, alen, blen);  // drain (:145) + trim_end (:206)
+                            const uint32_t ul = sh_ulen[sample];
+                            taglen = ul ? 5 + ul : 0;  // " UMI:" + umi (:207)
                         }
-                    }
-                    __syncwarp();
-                    if (has) {
-                        r_sample[r] = (int16_t)sample;
-                        r_alen[r] = (uint16_t)alen;
-                        r_blen[r] = (uint16_t)blen;
-                        r_cut1[r] = (uint16_t)cut1;
-                        r_taglen[r] = (uint8_t)taglen;
+                        __syncwarp();
+                        if (has) {
+                            r_sample[r] = (int16_t)sample;
+                            r_alen[r] = (uint16_t)alen;
+                            r_blen[r] = (uint16_t)blen;
+                            r_cut0[r] = (uint16_t)cut0;
+                            r_cut1[r] = (uint16_t)cut1;
+                            r_taglen[r] = (uint8_t)taglen;
+                        }
+                    } else if (OP == OP_DEMUX2) {
+                        // fasta_demultiplex.rs:215-229: the header of mate 2 without its " BC:" field; whether
+                        // the pair was assigned is looked up in P6, once the record index is known
+                        uint32_t alen = 0, blen = 0;
+                        uint32_t c0h = L1, c1h = L1, fa = 0;
+                        const bool found = has && p.out && bc_find16(win, sh_lut, L0, L1, fa);  // :219-227
+                        __syncwarp();
+                        if (found) {
+                            c0h = fa;
+                            c1h = class_run_end(win, sh_lut, fa + 4, L1);
+                        }
+                        __syncwarp();
+                        if (has && p.out) header_pieces(win, L0, L1, c0h, c1h, alen, blen);  // :229
+                        __syncwarp();
+                        if (has) {
+                            r_alen[r] = (uint16_t)alen;
+                            r_blen[r] = (uint16_t)blen;
+                            r_cut1[r] = (uint16_t)(c1h - L0);
+                        }
                     }
                 }
             }
+#ifdef SK_PHASE_TIMING
+            if (tid == 0 || tid == NT / 2) ph_x += (unsigned long long)(clock64() - t_plan0);  // this warp's plan done
+#endif
+            if (spec && warp == NW - 1 && !lb_early) {  // ... or after its own part of the plan
+                const uint64_t excl = lookback_consume(p.tile_lines, c, nls_chunk, lane);
+                if (lane == 0) M->g0 = excl;
+            }
+            if (IS_DEMUX || speculated) __syncthreads();  // the halves of a record's plan meet; g0 is known
+            if (!spec) break;
+            spec = false;
+            g0 = M->g0;
+            const uint32_t jt = (4u - (uint32_t)(g0 & 3u)) & 3u;
+            if (jt == j0) break;
+            j0 = jt;  // wrong guess: plan again on the true framing
+            __syncthreads();
         }
-        if (IS_DEMUX) __syncthreads();  // the two halves of a record's plan meet
+        const uint64_t rec0 = (g0 + j0) >> 2;
+        if (tid == 0) {
+            if (c == p.n_chunks - 1) st->n_lines = g0 + nls_chunk;
+            if (nrec) {
+                atomicAdd(&st->n_records, (unsigned long long)nrec);
+                atomicMax(&st->consumed, (unsigned long long)(c0 + LB(j0 + nrec * 4u)));
+            }
+        }
         FK_T(4);
 
-        // ---- P6 output length of every record and its place in the chunk's output (input order)
+        // ---- P6 outcome of every record (counters, deferred failures and ambiguity events), its output
+        // length and its place in the chunk's output (input order)
         uint32_t outlen = 0;
         {
             const uint32_t r = (uint32_t)tid;
             if (r < nrec) {
                 if (IS_DEMUX) {
-                    const int sample = r_sample[r];
+                    int sample;
+                    if (OP == OP_DEMUX1) {
+                        sample = r_sample[r];
+                        const uint32_t tg = r_taglen[r];
+                        if (sample == -1 && tg != 0xFFu && tg != 0u) report_err(st, rec0 + r, tg);
+                        if (sample != -1 || tg == 0u) my_total++;  // :169
+                        if (sample >= 0) {                          // :177-178
+                            my_ident++;
+                            if (cc_smem) atomicAdd(&ccount[sample], 1u);
+                            else atomicAdd(&p.counts[sample], 1ull);
+                        } else if (sample == -2) {  // :184-188
+                            const uint32_t ei = atomicAdd(&st->n_events, 1u);
+                            if (ei < p.events_cap) {
+                                Event ev;
+                                ev.record = (uint32_t)(rec0 + r);
+                                ev.bc_off = (uint32_t)(c0 + LB(j0 + r * 4u) + r_cut0[r] + 4u);
+                                ev.bc_off2 = 0xFFFFFFFFu;
+                                ev.best = (int16_t)r_alen[r];
+                                ev.last = (int16_t)r_blen[r];
+                                ev.mismatches = tg;
+                                p.events[ei] = ev;
+                            } else {
+                                atomicOr(&st->flags, F_EVENTS_OVERFLOW);
+                            }
+                        }
+                    } else {
+                        const uint64_t rec = rec0 + r;
+                        sample = (p.out && rec < p.r1_stats->n_records) ? (int)p.assign[rec] : -1;
+                        if (sample >= 0) {
+                            const uint32_t ul = sh_ulen[sample];
+                            r_taglen[r] = (uint8_t)(ul ? 5 + ul : 0);
+                            const uint32_t j = j0 + r * 4u;
+                            const uint32_t L0 = LB(j), L1 = LB(j + 1);
+                            if (fused && !(L1 > L0 && win[L1 - 1] == '\n')) {
+                                report_err(st, rec, K_TRUNC_FUSED);
+                                sample = -1;
+                            }
+                        } else {
+                            sample = -1;
+                        }
+                        r_sample[r] = (int16_t)sample;
+                    }
                     if (sample >= 0) {
                         const uint32_t j = j0 + r * 4u;
                         uint32_t body = LB(j + 4) - LB(j + 1);  // three lines verbatim (:209-212)
@@ -826,11 +953,12 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
                     }
                 } else {
                     outlen = r_outlen[r];
+                    if (r_mode[r] == B_NONE && r_k[r]) report_err(st, rec0 + r, r_k[r]);
                 }
             }
         }
         uint32_t t2;
-        const uint32_t sc = block_excl_scan<NT>(outlen | (outlen ? 1u << 22 : 0u), M->scratch, flip, t2);
+        const uint32_t sc = block_scan_fast<NT>(outlen | (outlen ? 1u << 22 : 0u), M->scratch, flip, t2);
         const uint32_t chunk_out = t2 & 0x3FFFFFu, n_emit = t2 >> 22;
         const uint32_t my_off = sc & 0x3FFFFFu, my_rank = sc >> 22;
         FK_T(5);
@@ -842,7 +970,7 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
         unsigned long long demux_base = 0;
         if (ORDERED) {
             if (warp == 0) {
-                const uint64_t excl = lookback(p.tile_out, c, chunk_out, lane);
+                const uint64_t excl = lookback_wide(p.tile_out, c, chunk_out, lane);
                 if (lane == 0) {
                     M->out_base = excl;
                     if (c == p.n_chunks - 1) {
@@ -879,15 +1007,15 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
         if (bail && tid == 0) atomicOr(&st->flags, F_NEED_GENERAL);
 
         // ---- P8 assemble the chunk's output image in shared memory, aligned like its destination.
-        // Six copy jobs per record (header | two halves of each of the two body pieces | tag and
-        // literals), numbered job-type major and dealt to all threads: a warp's lanes mostly share a job
-        // type, every job is a short word-wise copy, and the halves meet on a 16-byte boundary of the
-        // image.
+        // Five jobs per record (header, tag and literals | two halves of each of the two body pieces),
+        // numbered job-type major and dealt to all threads: a warp's lanes mostly share a job type,
+        // every job is a short word-wise copy, and the halves meet on a 16-byte boundary of the image.
+        // (Five, not six: 5 x 22 and 5 x 44 records fit one round of 128 / 256 threads.)
         if (writable) {
             uint8_t *sb = stage + shift;
-            const uint32_t njobs = 6u * nrec;
+            const uint32_t njobs = 5u * nrec;
             for (uint32_t jb = (uint32_t)tid; jb < njobs; jb += NT) {
-                const uint32_t type = (jb >= nrec) + (jb >= 2u * nrec) + (jb >= 3u * nrec) + (jb >= 4u * nrec) + (jb >= 5u * nrec);
+                const uint32_t type = (jb >= nrec) + (jb >= 2u * nrec) + (jb >= 3u * nrec) + (jb >= 4u * nrec);
                 const uint32_t r = jb - type * nrec;
                 const uint32_t ol = r_outlen[r];
                 uint8_t *jd = nullptr;
@@ -913,7 +1041,8 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
                         jd = d0;
                         js = win + L0;
                         jl = ORDERED ? hlen : alen;
-                    } else if (type <= 4) {
+                    }
+                    if (type != 0) {
                         // body piece 0 / 1: verbatim -> the two halves of the three lines; trim and mask ->
                         // sequence and qualities
                         const uint32_t piece = (type - 1u) >> 1, hi = (type - 1u) & 1u;
@@ -938,7 +1067,7 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
                         js = win + (hi ? ps + h : ps);
                         jl = hi ? pn - h : h;
                         if (jq) jq += hi ? h : 0u;
-                    } else {
+                    } else {  // type 0 also writes the record's literals
                         if (!ORDERED) {  // the (usually empty) piece after the cut, the tag and the newline
                             uint8_t *d = d0 + alen;
                             const uint8_t *sB = win + L0 + r_cut1[r];
@@ -1078,6 +1207,9 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
     if (tid == 0)
         for (int i = 0; i < 16; i++)
             if (ph[i]) atomicAdd(&st->phase_cycles[i], ph[i]);
+    if (tid == 0 && ph_x) atomicAdd(&st->phase_cycles[12], ph_x);
+    if (tid == NT / 2 && ph_x) atomicAdd(&st->phase_cycles[13], ph_x);
+    if (tid == NT - 32 && ph_x) atomicAdd(&st->phase_cycles[14], ph_x);
 #endif
     if (OP == OP_DEMUX1) {  // fasta_demultiplex.rs:108-109,169,177-178
         const uint32_t wt = __reduce_add_sync(0xffffffffu, my_total), wi = __reduce_add_sync(0xffffffffu, my_ident);
@@ -1102,6 +1234,7 @@ static uint32_t fast_smem(uint32_t S, uint32_t n_classes, uint32_t nwp, bool d1)
         o += ((n_classes * HIDX_CLS_ROWS * nwp + 3u) & ~3u) * 4u;
         if (S <= (uint32_t)FAST_CCOUNT_MAX) o += ((S + 3u) & ~3u) * 4u;
     }
+    o += (S + 15u) & ~15u;  // per-sample UMI lengths
     return o;
 }
 

@@ -240,3 +240,72 @@ def test_properties_at_scale(eng):
     assert code == 0 and trimmed.count(b"\n") == 4 * n
     code2, again, _ = eng.trim_by_quality(trimmed, 20)
     assert code2 == 0 and again.count(b"\n") == 4 * n and len(again) <= len(trimmed)
+
+
+def _bc_headers(data, bcs, seed):
+    """Appends ' BC:<barcode>' (a sheet barcode with its U positions filled) to every header line."""
+    rng = random.Random(seed)
+    out, lines = [], data.split(b"\n")
+    for i, ln in enumerate(lines):
+        if i % 4 == 0 and ln.startswith(b"@"):
+            bc = bytes(rng.choice(b"ACGT") if ch in b"UN" else ch for ch in rng.choice(bcs))
+            ln = ln + b" BC:" + bc
+        out.append(ln)
+    return b"\n".join(out)
+
+
+def test_lean_engine_is_the_default_and_reruns_beyond_its_limits(eng, O):
+    """Trim, mask and header-route demultiplex run on the lean engine (sk_fast.cu).  Records of ~5.5 KB
+    are longer than its overhang (4160 B) but inside the general engine's (6128 B): as soon as one of
+    them starts near the end of a lean chunk the operator is re-run on the general engine
+    (sk_result.reserved bit 1), and the bytes stay those of the oracle either way."""
+    sheet, bcs = G.make_sheet(3, 24, 8, umi=4)
+    data = G.clean_fastq(5, 3000, qual_style="decay")
+    rng = random.Random(17)
+    long_list = []
+    for i in range(60):
+        n = rng.randrange(2100, 2900)  # record of 4.2 .. 5.8 KB
+        long_list.append(b"@long read %d\n" % i + bytes(rng.choice(b"ACGT") for _ in range(n)) + b"\n+\n" +
+                         b"I" * (n // 2) + b"#" * (n - n // 2) + b"\n")
+    long_recs = b"".join(long_list)
+    # the construction must really leave the lean window (chunk 16320 B + 4160 B overhang) somewhere
+    pos, overruns = len(data), 0
+    for rec in long_list:
+        start_in_chunk = pos - ((pos - 1) // 16320) * 16320
+        overruns += start_in_chunk + len(rec) > 20480
+        pos += len(rec)
+    assert overruns > 0
+    for label, blob, rerun in (("normal", data, False), ("long", data + long_recs + data, True)):
+        check3(eng.trim_by_quality(blob, 20), O.trim_by_quality(blob, 20), ("trim", label))
+        assert eng.last_result.reserved == (2 if rerun else 1), ("trim", label, eng.last_result.reserved)
+        check3(eng.mask_by_quality(blob, 20), O.mask_by_quality(blob, 20), ("mask", label))
+        assert eng.last_result.reserved == (2 if rerun else 1), ("mask", label, eng.last_result.reserved)
+        r1 = _bc_headers(blob, bcs, 7)
+        for fused in (None, 20):
+            want_in = r1 if fused is None else O.trim_by_quality(r1, fused)[1]
+            _cmp_demux(eng.demultiplex(sheet, r1, None, fused_trim=fused), O.demultiplex(sheet, want_in, None), (label, fused))
+            assert eng.last_result.reserved == (2 if rerun else 1), ("demux", label, fused, eng.last_result.reserved)
+
+
+def test_framing_guess_is_verified_against_the_line_count(eng, O):
+    """The lean engine guesses a chunk's record framing from the text ('@' line whose second successor
+    starts with '+') and checks the guess against the global line count.  Here every sequence starts
+    with '+' and every quality string with '@', so the guess is wrong for chunks that begin inside a
+    record; the output must still be that of plain line counting (common.rs:106-112)."""
+    rng = random.Random(99)
+    sheet, bcs = G.make_sheet(5, 12, 8, umi=0)
+    recs = []
+    for i in range(6000):
+        n = rng.randrange(20, 260)
+        seq = b"+" + bytes(rng.choice(b"ACGT") for _ in range(n))
+        qual = b"@" + bytes(rng.choice(b"#+5?I@") for _ in range(n))
+        recs.append(b"@read%d %d:N:0\n%s\n+\n%s\n" % (i, i % 7, seq, qual))
+    data = b"".join(recs)
+    assert len(data) > 40 * 16320
+    check3(eng.trim_by_quality(data, 20), O.trim_by_quality(data, 20), "trim")
+    assert eng.last_result.reserved == 1
+    check3(eng.mask_by_quality(data, 20), O.mask_by_quality(data, 20), "mask")
+    r1 = _bc_headers(data, bcs, 11)
+    _cmp_demux(eng.demultiplex(sheet, r1, r1, fused_trim=20),
+               O.demultiplex(sheet, O.trim_by_quality(r1, 20)[1], O.trim_by_quality(r1, 20)[1]), "fused")
+    assert eng.last_result.reserved == 1

@@ -30,6 +30,11 @@ for which, name in ((0, "DEMUX1"), (1, "DEMUX2")):
     eng.lib.sk_debug_phase_cycles(eng.ctx, 0, which, out)
     tot = sum(out)
     print(name, "total cycles per timing thread-sum:", tot)
+    tot = sum(out[:12])
     for i, nm in enumerate(NAMES):
         if out[i]:
             print("   %-16s %5.1f%%" % (nm, 100.0 * out[i] / tot))
+    for i, nm in ((12, "within plan: first trim warp done"), (13, "within plan: first header warp done"),
+                  (14, "within plan: look-back collected")):
+        if out[i]:
+            print("   %-36s %5.1f%% of the chunk time" % (nm, 100.0 * out[i] / tot))
