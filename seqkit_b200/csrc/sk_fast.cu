@@ -328,6 +328,107 @@ __device__ __forceinline__ bool plan_trim_warp(const uint8_t *b, bool has, uint3
     return lowest_k <= L2 - L1;
 }
 
+// plan_trim_warp with two adjacent lanes per record (sub = 0 / 1): the pair walks the quality string
+// down sixteen bytes per step, lane 0 on the upper 8-byte block and lane 1 on the one below it; each
+// lane computes its block's totals relative to 0, one shuffle gives lane 1 the sum of lane 0's block
+// (its entering total), another tells the pair whether either block contains the break (:37).  Each
+// lane keeps the minimum over its own blocks; the pair's minimum is the lower of the two, the block
+// examined first winning a tie (:38).  The positions are resolved after the loop, the break block by
+// lane 0 and the minimum block by lane 1 at the same time.  Halves the length of the serial chain.
+// Must be called by all 32 lanes; both lanes of a pair pass the same arguments.  min_baseq <= 222.
+__device__ __forceinline__ bool plan_trim_pair(const uint8_t *b, bool has, uint32_t sub, uint32_t L1, uint32_t L2,
+                                               uint32_t L3, uint32_t L4, int minq, uint8_t &mode, uint32_t &kk,
+                                               uint32_t &body_len) {
+    const uint32_t FULL = 0xffffffffu;
+    const int NONE = -1;
+    uint32_t k = has ? L4 - L3 : 0u;
+    while (k > 0 && is_ws(b[L3 + k - 1])) k--;  // qual.trim_end().len()  (:31)
+    __syncwarp();
+    const uint32_t E = L3 + k;
+    const int sq = 33 + minq;
+    int tot = -50, lowest = -50;  // :28-29; tot = total entering lane 0's block of this step
+    int low_a = NONE, low_total = 0, brk_a = NONE, brk_total = 0;
+    int a = (k ? (int)((E - 1u) & ~7u) : 0) - 8 * (int)sub;
+    bool active = k > 0;
+    while (__any_sync(FULL, active)) {
+        const bool mine = active && a >= 0 && a + 8 > (int)L3;
+        int S = 0, mx = -0x40000000, mn = 0x40000000;
+        if (mine) {
+            int T[8];
+            blk8_totals(b, (uint32_t)a, L3, E, sq, minq, 0, T);
+            S = T[7];
+            mx = max(max(max(T[0], T[1]), max(T[2], T[3])), max(max(T[4], T[5]), max(T[6], T[7])));
+            mn = min(min(min(T[0], T[1]), min(T[2], T[3])), min(min(T[4], T[5]), min(T[6], T[7])));
+        }
+        const int S_o = __shfl_xor_sync(FULL, S, 1);
+        const int enter = tot + (sub ? S_o : 0);
+        const bool brk_me = mine && enter + mx > 0;
+        const bool brk_o = __shfl_xor_sync(FULL, (int)brk_me, 1) != 0;
+        const bool reached = mine && !(sub && brk_o);  // lane 0's block comes first
+        if (reached) {
+            if (brk_me) {
+                brk_a = a;
+                brk_total = enter;
+            } else if (enter + mn < lowest) {
+                lowest = enter + mn;
+                low_a = a;
+                low_total = enter;
+            }
+        }
+        tot += S + S_o;
+        const int a_first = a + 8 * (int)sub;  // lane 0's block of this step
+        active = active && !(brk_me || brk_o) && a_first - 8 > (int)L3;
+        a -= 16;
+    }
+    // the pair's break block (lane 0's if it broke, else lane 1's) and minimum block
+    {
+        const int ba_o = __shfl_xor_sync(FULL, brk_a, 1), bt_o = __shfl_xor_sync(FULL, brk_total, 1);
+        const int b0 = sub ? ba_o : brk_a, b1 = sub ? brk_a : ba_o;
+        const int t0 = sub ? bt_o : brk_total, t1 = sub ? brk_total : bt_o;
+        brk_a = b0 != NONE ? b0 : b1;
+        brk_total = b0 != NONE ? t0 : t1;
+        const int lo_o = __shfl_xor_sync(FULL, lowest, 1), la_o = __shfl_xor_sync(FULL, low_a, 1);
+        const int lt_o = __shfl_xor_sync(FULL, low_total, 1);
+        if (la_o != NONE && (lo_o < lowest || (lo_o == lowest && (low_a == NONE || la_o > low_a)))) {
+            lowest = lo_o;
+            low_a = la_o;
+            low_total = lt_o;
+        }
+    }
+    // resolve: lane 0 looks into the break block, lane 1 into the minimum block
+    const int ra = sub ? low_a : brk_a;
+    int best = 0x7FFFFFFF, at = 0;
+    if (ra != NONE) {
+        int T[8];
+        blk8_totals(b, (uint32_t)ra, L3, E, sq, minq, sub ? low_total : brk_total, T);
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            ok = ok && T[i] <= 0;     // totals after the break are never looked at
+            if (ok && T[i] < best) {  // first (highest address) of equal totals wins
+                best = T[i];
+                at = ra + 7 - i;
+            }
+        }
+    }
+    __syncwarp();
+    const int best0 = __shfl_sync(FULL, best, (threadIdx.x & 31) & ~1), at0 = __shfl_sync(FULL, at, (threadIdx.x & 31) & ~1);
+    const int at1 = __shfl_sync(FULL, at, (threadIdx.x & 31) | 1);
+    uint32_t lowest_k = k;
+    if (brk_a != NONE && best0 < lowest) lowest_k = (uint32_t)at0 - L3;  // a lower total just before the break
+    else if (low_a != NONE) lowest_k = (uint32_t)at1 - L3;
+    if (lowest_k == 0) {  // :44-45
+        mode = B_GARBAGE;
+        kk = 0;
+        body_len = 6;  // "N\n+\n!\n"
+        return true;
+    }
+    mode = B_TRIM;
+    kk = lowest_k;
+    body_len = 2 * lowest_k + 4;  // seq[..k] "\n+\n" qual[..k] "\n"  (:47)
+    return lowest_k <= L2 - L1;
+}
+
 // Pigeonhole barcode match on the compact tables (FastIdx): both half-key probes of a class are
 // issued before either is consumed; a probe stops at the first slot whose tag matches (tags are
 // unique per table, checked when the sheet is packed).  Same contract as hidx_match.
@@ -689,8 +790,8 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
             // Fused trim+demultiplex: the quality trim runs on the lower half of the CTA, the header work
             // on the upper half.  Failures are left in the record arrays and reported in P6.
             if (do_trim) {
-                for (uint32_t r0 = 0; r0 < nrec; r0 += tstride) {
-                    const uint32_t r = r0 + tl;
+                for (uint32_t r0 = 0; r0 < nrec; r0 += tstride / 2) {
+                    const uint32_t r = r0 + (tl >> 1), sub = tl & 1u;  // two adjacent lanes per record
                     const bool has = r < nrec;
                     const uint32_t j = j0 + (has ? r : 0u) * 4u;
                     const uint32_t L0 = LB(j), L1 = LB(j + 1), L2 = LB(j + 2), L3 = LB(j + 3), L4 = LB(j + 4);
@@ -707,12 +808,12 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
                     }
                     bool fine;
                     if (trim_q <= 222) {
-                        fine = plan_trim_warp(win, ok, L1, L2, L3, L4, trim_q, mode, kk, body);
+                        fine = plan_trim_pair(win, ok, sub, L1, L2, L3, L4, trim_q, mode, kk, body);
                     } else {
                         fine = ok ? plan_trim_body(win, L1, L2, L3, L4, trim_q, mode, kk, body) : true;
                         __syncwarp();
                     }
-                    if (has) {
+                    if (has && sub == 0) {
                         if (OP == OP_TRIM) {
                             uint32_t outlen = 0;
                             if (!ok) {
@@ -859,7 +960,7 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
                 const uint64_t excl = lookback_consume(p.tile_lines, c, nls_chunk, lane);
                 if (lane == 0) M->g0 = excl;
             }
-            if (IS_DEMUX || speculated) __syncthreads();  // the halves of a record's plan meet; g0 is known
+            __syncthreads();  // the parts of a record's plan meet; g0 is known
             if (!spec) break;
             spec = false;
             g0 = M->g0;
