@@ -84,6 +84,8 @@ struct sk_ctx {
     uint16_t *d_fnext = nullptr;
     bool fast_sheet = false;  // the sheet's FastIdx is usable
     int fast_geo = 1;   // lean-engine geometry: 0 = GeoS (8 KiB chunks), 1 = GeoM (16 KiB chunks, default); SK_FAST_GEO
+    bool warp = true;   // warp engine (sk_warp.cu) for header-route demultiplex; SK_NO_WARP=1 disables
+    uint32_t tile_lanes = GeoW::TILE_LANES;  // warp-engine tile = tile_lanes x 400 B; SK_TILE_LANES
     bool fast = true;   // lean engine (sk_fast.cu) for trim / mask / header-route demultiplex; SK_NO_FAST=1 disables
     int cfg = 0;  // chunk-engine geometry: 0 = CfgA (16 KiB chunks, 4 warps), 1 = CfgB (32 KiB chunks, 8 warps)
 };
@@ -97,8 +99,12 @@ struct sk_ctx {
         }                                                                                \
     } while (0)
 
-static uint32_t chunks_of(const sk_ctx *ctx, uint64_t n, bool fast = false) {
-    const uint64_t ch = fast ? (uint64_t)fast_chunk_bytes(ctx->fast_geo) : (uint64_t)cfg_chunk_bytes(ctx->cfg);
+// engine of a pass: 0 = general (sk_kernels.cu), 1 = lean (sk_fast.cu), 2 = warp (sk_warp.cu)
+enum { ENG_GENERAL = 0, ENG_LEAN = 1, ENG_WARP = 2 };
+static uint32_t chunks_of(const sk_ctx *ctx, uint64_t n, int eng = ENG_GENERAL) {
+    const uint64_t ch = eng == ENG_WARP   ? (uint64_t)ctx->tile_lanes * GeoW::LANE_BYTES
+                        : eng == ENG_LEAN ? (uint64_t)fast_chunk_bytes(ctx->fast_geo)
+                                          : (uint64_t)cfg_chunk_bytes(ctx->cfg);
     return (uint32_t)((n + ch - 1) / ch);
 }
 
@@ -171,6 +177,8 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
     if (const char *e = getenv("SK_CFG")) ctx->cfg = atoi(e) ? 1 : 0;
     if (const char *e = getenv("SK_NO_FAST")) ctx->fast = atoi(e) == 0;
     if (const char *e = getenv("SK_FAST_GEO")) ctx->fast_geo = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("SK_NO_WARP")) ctx->warp = atoi(e) == 0;
+    if (const char *e = getenv("SK_TILE_LANES")) ctx->tile_lanes = (uint32_t)std::min(30, std::max(8, atoi(e)));
     auto fail = [&](int code) {
         g_create_error = ctx->err;
         sk_ctx_destroy(ctx);
@@ -194,7 +202,9 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
     ctx->sm_count = prop.multiProcessorCount;
     const uint64_t B = (lim->max_stream_bytes + 15) & ~15ull;
     const uint64_t R = lim->max_records;
-    ctx->max_chunks = std::max(chunks_of(ctx, B, false), (uint32_t)((B + GeoS::CHUNK - 1) / GeoS::CHUNK)) + 1;
+    // slice-table rows: one per chunk, or GeoW::ROUNDS per tile of the warp engine (smallest tile: 8 lanes)
+    ctx->max_chunks = std::max(chunks_of(ctx, B, ENG_GENERAL), (uint32_t)((B + GeoS::CHUNK - 1) / GeoS::CHUNK)) + 1;
+    ctx->max_chunks = std::max(ctx->max_chunks, (uint32_t)(B / (8 * GeoW::LANE_BYTES) + 1) * GeoW::ROUNDS);
     const uint64_t out_cap = B + R * 72 + (uint64_t)ctx->max_chunks * 16 + 4096;
     const uint32_t Smax = lim->max_samples;
     ctx->slots.resize(lim->n_slots);
@@ -556,11 +566,12 @@ static int begin_op(sk_ctx *ctx, Slot *s, int op) {
     return SK_OK;
 }
 
-static void base_params(sk_ctx *ctx, Slot *s, int which, KParams &p, bool fast = false) {
+static void base_params(sk_ctx *ctx, Slot *s, int which, KParams &p, int eng = ENG_GENERAL) {
     memset(&p, 0, sizeof p);
     p.in = s->in[which];
     p.n = s->in_len[which];
-    p.n_chunks = chunks_of(ctx, p.n, fast);
+    p.n_chunks = chunks_of(ctx, p.n, eng);
+    p.tile_lanes = ctx->tile_lanes;
     p.lpr = 4;
     p.rec_limit = ~0ull;
     p.final_batch = 1;
@@ -568,17 +579,18 @@ static void base_params(sk_ctx *ctx, Slot *s, int which, KParams &p, bool fast =
     p.tile_lines = s->tile_lines[which];
     p.tile_out = s->tile_out;
     p.stats = s->stats + which;
-    s->n_chunks[which] = p.n_chunks;
+    s->n_chunks[which] = eng == ENG_WARP ? p.n_chunks * GeoW::ROUNDS : p.n_chunks;  // slice-table rows
 }
 
-static int run_pass(sk_ctx *ctx, Slot *s, int which, int op, const KParams &p, bool ordered_out, bool fast = false) {
+static int run_pass(sk_ctx *ctx, Slot *s, int which, int op, const KParams &p, bool ordered_out, int eng = ENG_GENERAL) {
     if (p.n_chunks == 0) return SK_OK;
     CK(cudaMemsetAsync(p.tile_lines, 0, (uint64_t)p.n_chunks * 8, s->stream));
     if (ordered_out) CK(cudaMemsetAsync(p.tile_out, 0, (uint64_t)p.n_chunks * 8, s->stream));
     const char *err = nullptr;
     if (ctx->profiling) CK(cudaEventRecord(s->ev[which][0], s->stream));
-    int rc = fast ? launch_fast_kernel(ctx->fast_geo, op, p, ctx->sm_count, s->stream, &err)
-                  : launch_chunk_kernel(ctx->cfg, op, p, ctx->sm_count, s->stream, &err);
+    int rc = eng == ENG_WARP   ? launch_warp_kernel(op, p, ctx->sm_count, s->stream, &err)
+             : eng == ENG_LEAN ? launch_fast_kernel(ctx->fast_geo, op, p, ctx->sm_count, s->stream, &err)
+                               : launch_chunk_kernel(ctx->cfg, op, p, ctx->sm_count, s->stream, &err);
     if (rc < 0) {
         ctx->err = std::string("kernel launch failed: ") + (err ? err : "?");
         return SK_E_CUDA;
@@ -599,7 +611,7 @@ static int stream_op_enqueue(sk_ctx *ctx, Slot *s, int op, uint32_t min_baseq, u
     if (rc) return rc;
     KParams p;
     auto fill = [&](bool f) {
-        base_params(ctx, s, SK_IN_R1, p, f);
+        base_params(ctx, s, SK_IN_R1, p, f ? ENG_LEAN : ENG_GENERAL);
         p.min_baseq = min_baseq;
         p.rec_limit = rec_limit ? rec_limit : ~0ull;
         p.out = s->out[0];
@@ -613,7 +625,7 @@ static int stream_op_enqueue(sk_ctx *ctx, Slot *s, int op, uint32_t min_baseq, u
     s->used_fast = fast;
     s->req_min_baseq = min_baseq;
     s->req_rec_limit = rec_limit;
-    rc = run_pass(ctx, s, SK_IN_R1, op, p, true, fast);
+    rc = run_pass(ctx, s, SK_IN_R1, op, p, true, fast ? ENG_LEAN : ENG_GENERAL);
     if (rc) return rc;
     return end_op(ctx, s);
 }
@@ -731,8 +743,9 @@ static int demux_enqueue(sk_ctx *ctx, Slot *s, const sk_demux_opts *o, bool fast
         rc = run_pass(ctx, s, idx_stream[q], OP_SCAN, k, false);
         if (rc) return rc;
     }
+    int eng = fast ? (ctx->warp ? ENG_WARP : ENG_LEAN) : ENG_GENERAL;
     auto demux_params = [&](int which, int mate, KParams &p) {
-        base_params(ctx, s, which, p, fast);
+        base_params(ctx, s, which, p, eng);
         p.sheet.fidx.table = ctx->d_ftab;
         p.sheet.fidx.next = ctx->d_fnext;
         p.rec_limit = limit;
@@ -771,17 +784,21 @@ static int demux_enqueue(sk_ctx *ctx, Slot *s, const sk_demux_opts *o, bool fast
     };
     KParams p1;
     demux_params(SK_IN_R1, 0, p1);
-    if (fast && !fast_supported(ctx->fast_geo, OP_DEMUX1, p1)) {
-        fast = false;
+    if (eng == ENG_WARP && !warp_supported(OP_DEMUX1, p1)) {
+        eng = ENG_LEAN;
+        demux_params(SK_IN_R1, 0, p1);
+    }
+    if (eng == ENG_LEAN && !fast_supported(ctx->fast_geo, OP_DEMUX1, p1)) {
+        eng = ENG_GENERAL;
         s->used_fast = false;
         demux_params(SK_IN_R1, 0, p1);
     }
-    rc = run_pass(ctx, s, SK_IN_R1, OP_DEMUX1, p1, false, fast);
+    rc = run_pass(ctx, s, SK_IN_R1, OP_DEMUX1, p1, false, eng);
     if (rc) return rc;
     if (s->paired) {
         KParams p2;
         demux_params(SK_IN_R2, 1, p2);
-        rc = run_pass(ctx, s, SK_IN_R2, OP_DEMUX2, p2, false, fast);
+        rc = run_pass(ctx, s, SK_IN_R2, OP_DEMUX2, p2, false, eng);
         if (rc) return rc;
     }
     return end_op(ctx, s);

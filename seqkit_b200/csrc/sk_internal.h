@@ -70,6 +70,22 @@ struct GeoM {  // 16 KiB chunks, 8 warps, 4 CTAs per SM: half the per-chunk fixe
     static constexpr int STAGE = WIN_MAX;
     static constexpr int MIN_CTAS = 4;
 };
+// Geometry of the warp engine (sk_warp.cu): a warp owns a tile, a lane owns a record.  Every lane scans
+// UPL 16-byte units (odd: conflict-free LDS.128); the tile is the first `tile_lanes` lanes' bytes
+// (KParams::tile_lanes, 29 unless the records are short), the remaining lanes' bytes are the overhang.
+struct GeoW {
+    static constexpr int ID = 2;
+    static constexpr int WARPS = 8;
+    static constexpr int NT = WARPS * 32;
+    static constexpr int UPL = 25;
+    static constexpr int LANE_BYTES = UPL * 16;           // 400
+    static constexpr int WIN = 32 * LANE_BYTES;           // 12800
+    static constexpr int TILE_LANES = 29;                 // default tile: 11600 B, overhang 1200 B
+    static constexpr int ROUNDS = 4;                      // rounds of 32 records; one slice-table row each
+    static constexpr int MAXREC = 32 * ROUNDS;
+    static constexpr int MAXLINES = 4 * MAXREC + 8;
+    static constexpr int MIN_CTAS = 2;
+};
 constexpr int FAST_CCOUNT_MAX = 1024;  // per-sample counters live in shared memory up to this many samples
 inline int cfg_chunk_bytes(int cfg) { return cfg == CfgB::ID ? CfgB::CHUNK : CfgA::CHUNK; }
 
@@ -174,6 +190,7 @@ struct KParams {
     uint32_t min_baseq;
     int32_t fused_trim;   // demux: >=0 -> trim by quality with this threshold
     uint32_t head_char;   // add barcode: '@' or '>' (uniform over the file)
+    uint32_t tile_lanes;  // warp engine: lanes whose bytes form the tile (GeoW)
     // look-back state (zeroed before launch)
     uint64_t *tile_lines;
     uint64_t *tile_out;
@@ -237,5 +254,8 @@ int chunk_kernel_smem_bytes(int cfg, uint32_t S, uint32_t wide, uint32_t n_class
 int fast_chunk_bytes(int geo);
 bool fast_supported(int geo, int op, const KParams &p);
 int launch_fast_kernel(int geo, int op, const KParams &p, int sm_count, void *stream, const char **err);
+// Warp engine (sk_warp.cu)
+bool warp_supported(int op, const KParams &p);
+int launch_warp_kernel(int op, const KParams &p, int sm_count, void *stream, const char **err);
 
 }  // namespace sk

@@ -1,0 +1,507 @@
+// sk_lean.cuh -- device helpers shared by the lean chunk engine (sk_fast.cu) and the warp engine
+// (sk_warp.cu): newline maps, " BC:" search, class-run checks, block-wise quality trim, pigeonhole
+// barcode match, masked copy.  Include after sk_device.cuh.
+#pragma once
+#include "sk_device.cuh"
+
+namespace sk {
+
+// 0x80 in every byte of x that is '\n'.  Exact for 7-bit input; a batch with a byte >= 0x80 is
+// refused as a whole (F_NON_ASCII), whatever this returns for it.
+__device__ __forceinline__ uint32_t nl_flags7(uint32_t x) {
+    const uint32_t t = x ^ 0x0A0A0A0Au;
+    return ~(t + 0x7F7F7F7Fu) & 0x80808080u;
+}
+// newline map of a 16-byte piece in natural order: bit k <=> byte k is '\n'
+__device__ __forceinline__ uint32_t nl_map_nat(const uint4 v) {
+    const uint32_t zx = nl_flags7(v.x), zy = nl_flags7(v.y), zz = nl_flags7(v.z), zw = nl_flags7(v.w);
+    const uint32_t lo = __dp4a(zx, 0x08040201u, __dp4a(zy, 0x80402010u, 0u));  // (bits 0-7) << 7
+    const uint32_t hi = __dp4a(zz, 0x08040201u, __dp4a(zw, 0x80402010u, 0u));  // (bits 8-15) << 7
+    return (lo >> 7) + hi * 2u;
+}
+// bits i with 0 <= i < hi (hi may be <= 0 or >= 32)
+__device__ __forceinline__ uint32_t bits_below(int hi) {
+    return hi <= 0 ? 0u : (hi >= 32 ? 0xFFFFFFFFu : (1u << hi) - 1u);
+}
+
+// Exclusive block scan of one u32 per thread (4 or 8 warps): warp scans by shuffle, then every thread
+// sums the warp totals out of two 16-byte shared-memory reads.  `scratch` holds 2*NW words (double
+// buffered by `flip`, one barrier per call).
+template <int NT>
+__device__ __forceinline__ uint32_t block_scan_fast(uint32_t v, uint32_t *scratch, uint32_t &flip, uint32_t &total) {
+    constexpr int NW = NT / 32;
+    static_assert(NW == 4 || NW == 8, "block_scan_fast: 4 or 8 warps");
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    uint32_t *s = scratch + flip * NW;
+    flip ^= 1u;
+    if (lane == 31) s[w] = x;
+    __syncthreads();
+    const uint4 a = *(const uint4 *)s;
+    uint32_t before = (w > 0 ? a.x : 0u) + (w > 1 ? a.y : 0u) + (w > 2 ? a.z : 0u) + (w > 3 ? a.w : 0u);
+    uint32_t all = a.x + a.y + a.z + a.w;
+    if (NW == 8) {
+        const uint4 b = *(const uint4 *)(s + 4);
+        before += (w > 4 ? b.x : 0u) + (w > 5 ? b.y : 0u) + (w > 6 ? b.z : 0u);
+        all += b.x + b.y + b.z + b.w;
+    }
+    total = all;
+    return before + x - v;
+}
+
+// mbarrier wait that parks the thread in hardware for up to the hinted time per attempt
+__device__ __forceinline__ void mbar_wait_parked(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+        "@P1 bra WAIT_DONE;\n"
+        "bra WAIT_LOOP;\n"
+        "WAIT_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(0x989680u)
+        : "memory");
+}
+#ifdef SK_PHASE_TIMING
+#define FK_T(i)                                              \
+    do {                                                     \
+        if (tid == 0) {                                      \
+            const long long t_now = clock64();               \
+            ph[i] += (unsigned long long)(t_now - t_prev);   \
+            t_prev = t_now;                                  \
+        }                                                    \
+    } while (0)
+#else
+#define FK_T(i) do { } while (0)
+#endif
+
+// Leftmost match of " BC:[class]" in [h0,h1), 16 bytes per step (see bc_find).
+__device__ __forceinline__ bool bc_find16(const uint8_t *b, const uint8_t *lut, uint32_t h0, uint32_t h1, uint32_t &st) {
+    if (h1 < h0 + 5) return false;
+    const uint32_t last = h1 - 5;
+    for (uint32_t a = h0 & ~15u; a <= last; a += 16) {
+        const uint4 v = *(const uint4 *)(b + a);
+        const uint32_t z0 = eq_flags(v.x, 0x20202020u), z1 = eq_flags(v.y, 0x20202020u);
+        const uint32_t z2 = eq_flags(v.z, 0x20202020u), z3 = eq_flags(v.w, 0x20202020u);
+        if (!(z0 | z1 | z2 | z3)) continue;
+        uint32_t m = __dp4a(z0, 0x08040201u, __dp4a(z1, 0x80402010u, 0u)) >> 7;
+        m |= (__dp4a(z2, 0x08040201u, __dp4a(z3, 0x80402010u, 0u)) >> 7) << 8;
+        while (m) {
+            const uint32_t i = a + (uint32_t)__ffs((int)m) - 1u;
+            m &= m - 1;
+            if (i >= h0 && i <= last && b[i + 1] == 'B' && b[i + 2] == 'C' && b[i + 3] == ':' && (lut[b[i + 4]] & 8u)) {
+                st = i;
+                return true;
+            }
+        }
+    }
+    return false;
+}
+
+// The observed barcode as words aligned to its first byte: raw[w] = bytes [bs+4w, bs+4w+4).
+template <int NR>
+__device__ __forceinline__ void load_raw(const uint8_t *b, uint32_t bs, uint32_t nwords, uint32_t (&raw)[NR]) {
+    const uint32_t a = bs & ~3u, sh = (bs & 3u) * 8u;
+    uint32_t lo = *(const uint32_t *)(b + a);
+#pragma unroll
+    for (int w = 0; w < NR; w++) {
+        raw[w] = 0;
+        if (w < (int)nwords) {
+            const uint32_t hi = *(const uint32_t *)(b + a + 4 * w + 4);
+            raw[w] = __funnelshift_r(lo, hi, sh);
+            lo = hi;
+        }
+    }
+}
+// Is the greedy class run (fasta_demultiplex.rs:38) that starts at the barcode's first byte exactly L
+// bytes long?  raw holds ceil((L+1)/4) words; `room` = header bytes from the barcode start to the end
+// of the header line.  Every lane runs the same number of steps.
+template <int NR>
+__device__ __forceinline__ bool class_run_is(const uint32_t (&raw)[NR], const uint8_t *lut, uint32_t L, uint32_t room) {
+    if (room < L) return false;
+    uint32_t acc = 8u, term = 0;
+#pragma unroll
+    for (int w = 0; w < NR; w++) {
+        const uint32_t x = raw[w];
+        if (4u * w + 4u <= L) {
+            acc &= lut[x & 0xFFu] & lut[(x >> 8) & 0xFFu] & lut[(x >> 16) & 0xFFu] & lut[x >> 24];
+        } else if (4u * w < L) {
+            acc &= lut[x & 0xFFu];
+            if (4u * w + 1u < L) acc &= lut[(x >> 8) & 0xFFu];
+            if (4u * w + 2u < L) acc &= lut[(x >> 16) & 0xFFu];
+        }
+        if ((uint32_t)w == (L >> 2)) term = (x >> (8u * (L & 3u))) & 0xFFu;
+    }
+    if (!(acc & 8u)) return false;          // the run ends early
+    if (room == L) return true;             // the header line ends with the barcode
+    return !(lut[term] & 8u);               // the byte after the barcode ends the run
+}
+
+// End of the greedy class run (fasta_demultiplex.rs:38) that starts at `from`, four bytes per step on
+// words aligned to `from` (lanes of a warp step together when their barcodes are equally long).
+__device__ __forceinline__ uint32_t class_run_end(const uint8_t *b, const uint8_t *lut, uint32_t from, uint32_t h1) {
+    const uint32_t a = from & ~3u, sh = (from & 3u) * 8u;
+    uint32_t lo = *(const uint32_t *)(b + a);
+    uint32_t e = from;
+    while (e < h1) {
+        const uint32_t hi = *(const uint32_t *)(b + a + 4 + (e - from));
+        const uint32_t x = __funnelshift_r(lo, hi, sh);
+        lo = hi;
+        const uint32_t c0 = lut[x & 0xFFu], c1 = lut[(x >> 8) & 0xFFu], c2 = lut[(x >> 16) & 0xFFu], c3 = lut[x >> 24];
+        if (c0 & c1 & c2 & c3 & 8u) {
+            e += 4;
+            continue;
+        }
+        e += (c0 & 8u) ? ((c1 & 8u) ? ((c2 & 8u) ? 3u : 2u) : 1u) : 0u;
+        break;
+    }
+    return e < h1 ? e : h1;
+}
+
+// Running totals of fasta_trim_by_quality.rs:33-36 over the aligned 8-byte block at window offset a,
+// in the order the reference examines the bytes: T[i] is the total after byte a+7-i, starting from
+// `total`.  Bytes outside the quality string [L3,E) contribute nothing (they are replaced by the
+// byte whose contribution is zero, sub = 33 + min_baseq <= 255).  A byte below '!' takes the wrapping
+// u8 subtraction (:35) on the byte-wise path.
+__device__ __forceinline__ void blk8_totals(const uint8_t *b, uint32_t a, uint32_t L3, uint32_t E, int sub, int minq,
+                                            int total, int (&T)[8]) {
+    uint2 v = *(const uint2 *)(b + a);
+    if (a < L3 || a + 8 > E) {
+        const uint32_t nlow = a < L3 ? L3 - a : 0u, nhigh = a + 8 > E ? a + 8 - E : 0u;
+        unsigned long long m = nlow >= 8u ? 0ull : (~0ull << (8u * nlow));
+        m = nhigh >= 8u ? 0ull : (m & (~0ull >> (8u * nhigh)));
+        const uint32_t mlo = (uint32_t)m, mhi = (uint32_t)(m >> 32), sub4 = (uint32_t)sub * 0x01010101u;
+        v.x = (v.x & mlo) | (sub4 & ~mlo);
+        v.y = (v.y & mhi) | (sub4 & ~mhi);
+    }
+    const uint32_t H = 0x80808080u, C = 0x21212121u;
+    const uint32_t bad = (~((v.x | H) - C) & ~v.x & H) | (~((v.y | H) - C) & ~v.y & H);  // bytes below '!'
+    if (!bad) {
+        T[0] = (int)__dp4a(v.y, 0x01000000u, (uint32_t)(total - sub));
+        T[1] = (int)__dp4a(v.y, 0x01010000u, (uint32_t)(total - 2 * sub));
+        T[2] = (int)__dp4a(v.y, 0x01010100u, (uint32_t)(total - 3 * sub));
+        T[3] = (int)__dp4a(v.y, 0x01010101u, (uint32_t)(total - 4 * sub));
+        T[4] = (int)__dp4a(v.x, 0x01000000u, (uint32_t)(T[3] - sub));
+        T[5] = (int)__dp4a(v.x, 0x01010000u, (uint32_t)(T[3] - 2 * sub));
+        T[6] = (int)__dp4a(v.x, 0x01010100u, (uint32_t)(T[3] - 3 * sub));
+        T[7] = (int)__dp4a(v.x, 0x01010101u, (uint32_t)(T[3] - 4 * sub));
+    } else {
+        int t = total;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t q = ((i < 4 ? v.y : v.x) >> (8 * (3 - (i & 3)))) & 0xFFu;
+            t += q >= 33u ? (int)q - sub : (int)((q - 33u) & 0xFFu) - minq;
+            T[i] = t;
+        }
+    }
+}
+
+// fasta_trim_by_quality.rs:28-48 for one record per lane, all lanes of the warp in step: every lane
+// walks its quality string down in aligned 8-byte blocks inside one warp-synchronous loop and only
+// notes (a) the block in which the running total first exceeds 0 (:37) and (b) the block holding the
+// minimum so far (:38); the positions inside those two blocks are resolved once after the loop.
+// Must be called by all 32 lanes (`has` = this lane carries a record).  min_baseq <= 222.
+__device__ __forceinline__ bool plan_trim_warp(const uint8_t *b, bool has, uint32_t L1, uint32_t L2, uint32_t L3, uint32_t L4,
+                                               int minq, uint8_t &mode, uint32_t &kk, uint32_t &body_len) {
+    const uint32_t NONE = 0xFFFFFFFFu;
+    uint32_t k = has ? L4 - L3 : 0u;
+    while (k > 0 && is_ws(b[L3 + k - 1])) k--;  // qual.trim_end().len()  (:31)
+    __syncwarp();
+    const uint32_t E = L3 + k;
+    const int sub = 33 + minq;
+    int total = -50, lowest = -50;  // :28-29
+    uint32_t low_a = NONE, brk_a = NONE;
+    int low_total = 0, brk_total = 0;
+    uint32_t a = k ? ((E - 1u) & ~7u) : 0u;
+    bool active = k > 0;
+    while (__any_sync(0xffffffffu, active)) {
+        if (active) {
+            int T[8];
+            blk8_totals(b, a, L3, E, sub, minq, total, T);
+            const int mx = max(max(max(T[0], T[1]), max(T[2], T[3])), max(max(T[4], T[5]), max(T[6], T[7])));
+            const int mn = min(min(min(T[0], T[1]), min(T[2], T[3])), min(min(T[4], T[5]), min(T[6], T[7])));
+            if (mx > 0) {  // the break is inside this block
+                brk_a = a;
+                brk_total = total;
+                active = false;
+            } else {
+                if (mn < lowest) {  // strict '<': an earlier block keeps a tie
+                    lowest = mn;
+                    low_a = a;
+                    low_total = total;
+                }
+                total = T[7];
+                if (a <= L3) active = false;
+                else a -= 8;
+            }
+        }
+    }
+    // resolve positions: first the break block (its totals before the break may lower the minimum),
+    // then the block that holds the minimum
+    uint32_t lowest_k = k;
+    bool placed = false;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        const uint32_t ra = pass == 0 ? brk_a : low_a;
+        const bool go = ra != NONE && !placed;
+        if (go) {
+            int T[8];
+            blk8_totals(b, ra, L3, E, sub, minq, pass == 0 ? brk_total : low_total, T);
+            bool ok = true;
+            int best = 0x7FFFFFFF;
+            uint32_t at = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                ok = ok && T[i] <= 0;           // totals after the break are never looked at
+                if (ok && T[i] < best) {        // first (highest address) of equal totals wins
+                    best = T[i];
+                    at = ra + 7u - (uint32_t)i;
+                }
+            }
+            if (pass == 0 ? best < lowest : best == lowest) {
+                lowest = best;
+                lowest_k = at - L3;
+                placed = true;
+            }
+        }
+        __syncwarp();
+    }
+    if (lowest_k == 0) {  // :44-45
+        mode = B_GARBAGE;
+        kk = 0;
+        body_len = 6;  // "N\n+\n!\n"
+        return true;
+    }
+    mode = B_TRIM;
+    kk = lowest_k;
+    body_len = 2 * lowest_k + 4;  // seq[..k] "\n+\n" qual[..k] "\n"  (:47)
+    return lowest_k <= L2 - L1;
+}
+
+// plan_trim_warp with two adjacent lanes per record (sub = 0 / 1): the pair walks the quality string
+// down sixteen bytes per step, lane 0 on the upper 8-byte block and lane 1 on the one below it; each
+// lane computes its block's totals relative to 0, one shuffle gives lane 1 the sum of lane 0's block
+// (its entering total), another tells the pair whether either block contains the break (:37).  Each
+// lane keeps the minimum over its own blocks; the pair's minimum is the lower of the two, the block
+// examined first winning a tie (:38).  The positions are resolved after the loop, the break block by
+// lane 0 and the minimum block by lane 1 at the same time.  Halves the length of the serial chain.
+// Must be called by all 32 lanes; both lanes of a pair pass the same arguments.  min_baseq <= 222.
+__device__ __forceinline__ bool plan_trim_pair(const uint8_t *b, bool has, uint32_t sub, uint32_t L1, uint32_t L2,
+                                               uint32_t L3, uint32_t L4, int minq, uint8_t &mode, uint32_t &kk,
+                                               uint32_t &body_len) {
+    const uint32_t FULL = 0xffffffffu;
+    const int NONE = -1;
+    uint32_t k = has ? L4 - L3 : 0u;
+    while (k > 0 && is_ws(b[L3 + k - 1])) k--;  // qual.trim_end().len()  (:31)
+    __syncwarp();
+    const uint32_t E = L3 + k;
+    const int sq = 33 + minq;
+    int tot = -50, lowest = -50;  // :28-29; tot = total entering lane 0's block of this step
+    int low_a = NONE, low_total = 0, brk_a = NONE, brk_total = 0;
+    int a = (k ? (int)((E - 1u) & ~7u) : 0) - 8 * (int)sub;
+    bool active = k > 0;
+    while (__any_sync(FULL, active)) {
+        const bool mine = active && a >= 0 && a + 8 > (int)L3;
+        int S = 0, mx = -0x40000000, mn = 0x40000000;
+        if (mine) {
+            int T[8];
+            blk8_totals(b, (uint32_t)a, L3, E, sq, minq, 0, T);
+            S = T[7];
+            mx = max(max(max(T[0], T[1]), max(T[2], T[3])), max(max(T[4], T[5]), max(T[6], T[7])));
+            mn = min(min(min(T[0], T[1]), min(T[2], T[3])), min(min(T[4], T[5]), min(T[6], T[7])));
+        }
+        const int S_o = __shfl_xor_sync(FULL, S, 1);
+        const int enter = tot + (sub ? S_o : 0);
+        const bool brk_me = mine && enter + mx > 0;
+        const bool brk_o = __shfl_xor_sync(FULL, (int)brk_me, 1) != 0;
+        const bool reached = mine && !(sub && brk_o);  // lane 0's block comes first
+        if (reached) {
+            if (brk_me) {
+                brk_a = a;
+                brk_total = enter;
+            } else if (enter + mn < lowest) {
+                lowest = enter + mn;
+                low_a = a;
+                low_total = enter;
+            }
+        }
+        tot += S + S_o;
+        const int a_first = a + 8 * (int)sub;  // lane 0's block of this step
+        active = active && !(brk_me || brk_o) && a_first - 8 > (int)L3;
+        a -= 16;
+    }
+    // the pair's break block (lane 0's if it broke, else lane 1's) and minimum block
+    {
+        const int ba_o = __shfl_xor_sync(FULL, brk_a, 1), bt_o = __shfl_xor_sync(FULL, brk_total, 1);
+        const int b0 = sub ? ba_o : brk_a, b1 = sub ? brk_a : ba_o;
+        const int t0 = sub ? bt_o : brk_total, t1 = sub ? brk_total : bt_o;
+        brk_a = b0 != NONE ? b0 : b1;
+        brk_total = b0 != NONE ? t0 : t1;
+        const int lo_o = __shfl_xor_sync(FULL, lowest, 1), la_o = __shfl_xor_sync(FULL, low_a, 1);
+        const int lt_o = __shfl_xor_sync(FULL, low_total, 1);
+        if (la_o != NONE && (lo_o < lowest || (lo_o == lowest && (low_a == NONE || la_o > low_a)))) {
+            lowest = lo_o;
+            low_a = la_o;
+            low_total = lt_o;
+        }
+    }
+    // resolve: lane 0 looks into the break block, lane 1 into the minimum block
+    const int ra = sub ? low_a : brk_a;
+    int best = 0x7FFFFFFF, at = 0;
+    if (ra != NONE) {
+        int T[8];
+        blk8_totals(b, (uint32_t)ra, L3, E, sq, minq, sub ? low_total : brk_total, T);
+        bool ok = true;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            ok = ok && T[i] <= 0;     // totals after the break are never looked at
+            if (ok && T[i] < best) {  // first (highest address) of equal totals wins
+                best = T[i];
+                at = ra + 7 - i;
+            }
+        }
+    }
+    __syncwarp();
+    const int best0 = __shfl_sync(FULL, best, (threadIdx.x & 31) & ~1), at0 = __shfl_sync(FULL, at, (threadIdx.x & 31) & ~1);
+    const int at1 = __shfl_sync(FULL, at, (threadIdx.x & 31) | 1);
+    uint32_t lowest_k = k;
+    if (brk_a != NONE && best0 < lowest) lowest_k = (uint32_t)at0 - L3;  // a lower total just before the break
+    else if (low_a != NONE) lowest_k = (uint32_t)at1 - L3;
+    if (lowest_k == 0) {  // :44-45
+        mode = B_GARBAGE;
+        kk = 0;
+        body_len = 6;  // "N\n+\n!\n"
+        return true;
+    }
+    mode = B_TRIM;
+    kk = lowest_k;
+    body_len = 2 * lowest_k + 4;  // seq[..k] "\n+\n" qual[..k] "\n"  (:47)
+    return lowest_k <= L2 - L1;
+}
+
+// Pigeonhole barcode match on the compact tables (FastIdx): both half-key probes of a class are
+// issued before either is consumed; a probe stops at the first slot whose tag matches (tags are
+// unique per table, checked when the sheet is packed).  Same contract as hidx_match.
+template <int NR>
+__device__ __forceinline__ void fidx_match(const uint32_t (&raw)[NR], const HalfIdx &H, const FastIdx &F,
+                                           const uint32_t *hcls, uint32_t S, uint32_t &lowest, uint32_t &best,
+                                           uint32_t &last) {
+    constexpr int NWMAX = NR - 1;
+    const uint32_t nw = H.nw, nwp = H.nwp, tmask = H.tsize - 1u;
+    lowest = 0xFFFFFFFFu;
+    best = 0xFFFFFFFFu;
+    last = 0;
+    for (uint32_t c = 0; c < H.n_classes; c++) {
+        const uint32_t *care = hcls + c * HIDX_CLS_ROWS * nwp;
+        uint32_t tag[2] = {0u, 0u};
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const uint32_t *hm = care + (1 + 3 * h) * nwp;
+#pragma unroll
+            for (int w = 0; w < NWMAX; w++)
+                if (w < (int)nw) tag[h] += (raw[w] & hm[w]) * hm[nwp + w];
+        }
+        const uint2 *tab0 = F.table + (size_t)(c * 2) * H.tsize, *tab1 = tab0 + H.tsize;
+        uint32_t sl0 = (tag[0] ^ (tag[0] >> 15)) & tmask, sl1 = (tag[1] ^ (tag[1] >> 15)) & tmask;
+        uint2 e0 = __ldg(&tab0[sl0]), e1 = __ldg(&tab1[sl1]);
+        while (e0.y && e0.x != tag[0]) {
+            sl0 = (sl0 + 1) & tmask;
+            e0 = __ldg(&tab0[sl0]);
+        }
+        while (e1.y && e1.x != tag[1]) {
+            sl1 = (sl1 + 1) & tmask;
+            e1 = __ldg(&tab1[sl1]);
+        }
+        // candidate chains of the two halves (usually one sample each, usually the same one)
+        uint32_t s = e0.y ? (e0.y & 0xFFFFu) - 1u : 0xFFFFFFFFu;
+        bool more = (e0.y >> 16) != 0;
+        uint32_t s_other = e1.y ? (e1.y & 0xFFFFu) - 1u : 0xFFFFFFFFu;
+        bool more_other = (e1.y >> 16) != 0;
+        if (s == s_other && !more && !more_other) s_other = 0xFFFFFFFFu;  // same single sample twice
+        int h = 0;
+        for (;;) {
+            if (s == 0xFFFFFFFFu) {
+                if (h) break;
+                h = 1;
+                s = s_other;
+                more = more_other;
+                if (s == 0xFFFFFFFFu) break;
+            }
+            const uint4 *sk = (const uint4 *)(H.skeys + (size_t)s * nwp);
+            uint32_t d = 0;
+#pragma unroll
+            for (int q = 0; q < NWMAX / 4; q++)
+                if (4 * q < (int)nw) {
+                    const uint4 kq = __ldg(&sk[q]);
+                    d += nz_bytes((raw[4 * q] & care[4 * q]) ^ kq.x);
+                    d += nz_bytes((raw[4 * q + 1] & care[4 * q + 1]) ^ kq.y);
+                    d += nz_bytes((raw[4 * q + 2] & care[4 * q + 2]) ^ kq.z);
+                    d += nz_bytes((raw[4 * q + 3] & care[4 * q + 3]) ^ kq.w);
+                }
+            if (d < lowest) {
+                lowest = d;
+                best = s;
+                last = s;
+            } else if (d == lowest) {
+                best = s < best ? s : best;
+                last = s > last ? s : last;
+            }
+            uint32_t n = 0xFFFFu;
+            if (more) n = __ldg(&F.next[(size_t)(c * 2 + h) * S + s]);
+            s = n == 0xFFFFu ? 0xFFFFFFFFu : n;
+        }
+    }
+    if (lowest > 1u) lowest = 0xFFFFFFFFu;  // farther samples were not enumerated completely
+}
+
+// dst[i] = ((u8)(qual[i] - 33) < minq) ? 'N' : seq[i]   (fasta_mask_by_quality.rs:40-43), thread-serial,
+// four bytes per step once dst is word aligned.  7-bit input (see nl_flags7); minq <= 223 on the word
+// path (bytes below '!' wrap to >= 223 and are then never masked).
+__device__ __forceinline__ void mask_copy(uint8_t *dst, const uint8_t *seq, const uint8_t *qual, uint32_t len,
+                                          uint32_t minq) {
+#define SK_MASK_BYTE()                                                      \
+    {                                                                       \
+        const uint8_t q = (uint8_t)(*qual++ - 33u);                         \
+        const uint8_t s = *seq++;                                           \
+        *dst++ = q < minq ? (uint8_t)'N' : s;                               \
+        len--;                                                              \
+    }
+    while (len && ((uint32_t)(uintptr_t)dst & 3u)) SK_MASK_BYTE()
+    if (len >= 4 && minq <= 223u) {
+        const uint32_t shs = ((uint32_t)(uintptr_t)seq & 3u) * 8u, shq = ((uint32_t)(uintptr_t)qual & 3u) * 8u;
+        const uint32_t *sw = (const uint32_t *)((uintptr_t)seq & ~(uintptr_t)3);
+        const uint32_t *qw = (const uint32_t *)((uintptr_t)qual & ~(uintptr_t)3);
+        uint32_t *dw = (uint32_t *)dst;
+        const uint32_t hi_c = 33u + minq;  // masked <=> 33 <= q < 33 + minq
+        const uint32_t k_hi = hi_c >= 128u ? 0u : (128u - hi_c) * 0x01010101u;
+        const bool no_hi = hi_c >= 128u;
+        uint32_t slo = *sw++, qlo = *qw++;
+        uint32_t nwords = len >> 2;
+        for (uint32_t i = 0; i < nwords; i++) {
+            const uint32_t shi = *sw++, qhi = *qw++;
+            const uint32_t s = __funnelshift_r(slo, shi, shs), q = __funnelshift_r(qlo, qhi, shq);
+            slo = shi;
+            qlo = qhi;
+            const uint32_t ge = (q + 0x5F5F5F5Fu);                       // bit 7 <=> q >= 33
+            const uint32_t lt = no_hi ? 0xFFFFFFFFu : ~(q + k_hi);        // bit 7 <=> q < 33 + minq
+            const uint32_t f = ge & lt & 0x80808080u;
+            const uint32_t m = (f >> 7) * 0xFFu;
+            *dw++ = (s & ~m) | (0x4E4E4E4Eu & m);
+        }
+        const uint32_t done = nwords * 4u;
+        dst += done;
+        seq += done;
+        qual += done;
+        len -= done;
+    }
+    while (len) SK_MASK_BYTE()
+#undef SK_MASK_BYTE
+}
+
+}  // namespace sk

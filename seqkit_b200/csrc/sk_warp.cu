@@ -1,0 +1,719 @@
+// sk_warp.cu -- the warp engine: header-route demultiplex (mate 1 / mate 2, with or without the fused
+// quality trim) with one warp per tile and one lane per record.
+//
+// The lean engine (sk_fast.cu) spends a third of its warp time at CTA barriers: its per-record phase
+// runs one lane per record on the few warps a 16 KiB chunk fills, while the other warps of the CTA
+// wait.  Here a warp owns a whole tile of the stream from load to store and never meets another warp:
+//   * tile = 29 lanes x 400 B of input (about 31 records of 2x150 bp FASTQ) + 3 lanes of overhang,
+//     loaded by one TMA bulk copy into the warp's private window; 16 such warps per SM sit in
+//     different phases, so nobody waits at a barrier and every per-record step has its 32 lanes busy;
+//   * newline scan: 25 conflict-free LDS.128 per lane, newline maps in registers, one shuffle scan,
+//     line starts written by plain ffs loops;
+//   * record framing by global line index (common.rs:106-112) through the decoupled look-back,
+//     speculated from the text and verified before anything is written (as in the lean engine);
+//   * per record, in registers: '@' check, leftmost " BC:x", class run, pigeonhole match, header
+//     surgery, quality trim (fasta_demultiplex.rs:117-212, fasta_trim_by_quality.rs:28-48);
+//   * output: a round (<= 32 records) takes its space with one atomicAdd, the record's edits are
+//     patched into the window in place (" UMI:x\n" over the deleted " BC:x", "\n+\n" and "\n" behind
+//     the kept bases and qualities), so that a record is two or three contiguous runs which the lane
+//     copies straight to global memory with 16-byte stores.  No staging image, no second pass.
+// Anything outside the engine's limits (a record longer than the overhang, more than 128 records in
+// a tile) raises F_NEED_GENERAL and sk_wait re-runs the operator on the general engine.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "sk_internal.h"
+
+namespace sk {
+extern __shared__ __align__(128) unsigned char sk_smem[];
+}
+#include "sk_device.cuh"
+#include "sk_lean.cuh"
+
+namespace sk {
+
+struct WLayout {
+    static constexpr uint32_t win = 0;
+    static constexpr uint32_t ls = GeoW::WIN + 32;                                   // patches may touch win[wlen]
+    static constexpr uint32_t misc = ls + (((GeoW::MAXLINES + 8) * 2 + 15) / 16) * 16;
+    static constexpr uint32_t per_warp = misc + 16;
+    static constexpr uint32_t lut = GeoW::WARPS * per_warp;
+    static constexpr uint32_t dyn = lut + 256;  // hcls rows, per-sample counters, UMI lengths
+};
+static_assert(WLayout::per_warp % 16 == 0, "warp areas are 16-byte aligned");
+
+// Lane-serial copy of `len` bytes from shared memory to global memory, any alignment on either side:
+// bytes up to a word of the destination, words up to a 16-byte unit, then 16 bytes per step
+// (4 LDS.32 + 4 funnel shifts + 1 STG.128); the source is only ever read as aligned words.
+__device__ __forceinline__ void gcopy(uint8_t *dst, const uint8_t *src, uint32_t len) {
+    while (len && ((uint32_t)(uintptr_t)dst & 3u)) {
+        *dst++ = *src++;
+        len--;
+    }
+    if (len >= 4) {
+        const uint32_t sh = ((uint32_t)(uintptr_t)src & 3u) * 8u;
+        const uint32_t *sw = (const uint32_t *)((uintptr_t)src & ~(uintptr_t)3);
+        uint32_t *dw = (uint32_t *)dst;
+        uint32_t nwords = len >> 2;
+        uint32_t lo = *sw++;
+        while (nwords && ((uint32_t)(uintptr_t)dw & 15u)) {
+            const uint32_t hi = *sw++;
+            *dw++ = __funnelshift_r(lo, hi, sh);
+            lo = hi;
+            nwords--;
+        }
+        for (; nwords >= 4; nwords -= 4) {
+            const uint32_t w1 = sw[0], w2 = sw[1], w3 = sw[2], w4 = sw[3];
+            uint4 o;
+            o.x = __funnelshift_r(lo, w1, sh);
+            o.y = __funnelshift_r(w1, w2, sh);
+            o.z = __funnelshift_r(w2, w3, sh);
+            o.w = __funnelshift_r(w3, w4, sh);
+            *(uint4 *)dw = o;
+            lo = w4;
+            sw += 4;
+            dw += 4;
+        }
+        while (nwords) {
+            const uint32_t hi = *sw++;
+            *dw++ = __funnelshift_r(lo, hi, sh);
+            lo = hi;
+            nwords--;
+        }
+        const uint32_t done = len & ~3u;
+        dst += done;
+        src += done;
+        len &= 3u;
+    }
+    while (len) {
+        *dst++ = *src++;
+        len--;
+    }
+}
+
+template <int OP, int NWMAX>
+__global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const __grid_constant__ KParams p) {
+    constexpr bool D1 = OP == OP_DEMUX1;
+    static_assert(OP == OP_DEMUX1 || OP == OP_DEMUX2, "warp engine: demultiplex passes");
+    constexpr int UPL = GeoW::UPL, LANE_BYTES = GeoW::LANE_BYTES, WIN = GeoW::WIN;
+    constexpr int MAXREC = GeoW::MAXREC, MAXLINES = GeoW::MAXLINES, NMW = (UPL + 1) / 2;
+    constexpr uint32_t FULL = 0xffffffffu;
+    using WL = WLayout;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint8_t *win = sk_smem + (uint32_t)warp * WL::per_warp;
+    uint16_t *ls = (uint16_t *)(win + WL::ls);
+    uint64_t *mbar = (uint64_t *)(win + WL::misc);
+    uint8_t *sh_lut = sk_smem + WL::lut;
+    uint32_t *hcls = (uint32_t *)(sk_smem + WL::dyn);
+    const uint32_t S = p.sheet.S;
+    const uint32_t hcls_words = D1 ? p.sheet.hidx.n_classes * HIDX_CLS_ROWS * p.sheet.hidx.nwp : 0u;
+    uint32_t *ccount = hcls + ((hcls_words + 3u) & ~3u);
+    const bool cc_smem = D1 && S <= (uint32_t)FAST_CCOUNT_MAX;
+    uint8_t *sh_ulen = (uint8_t *)(ccount + (cc_smem ? ((S + 3u) & ~3u) : 0u));  // UMI length of every sample
+    DevStats *st = p.stats;
+
+    if (lane == 0) mbar_init(mbar, 1);
+    for (uint32_t i = tid; i < 256; i += GeoW::NT) sh_lut[i] = p.sheet.lut[i];
+    for (uint32_t i = tid; i < S; i += GeoW::NT)
+        sh_ulen[i] = (uint8_t)(p.sheet.wide ? __popcll(((const unsigned long long *)p.sheet.umask)[i]) : __popc(p.sheet.umask[i]));
+    if (D1) {
+        for (uint32_t i = tid; i < hcls_words; i += GeoW::NT) hcls[i] = p.sheet.hidx.cls[i];
+        if (cc_smem)
+            for (uint32_t i = tid; i < S; i += GeoW::NT) ccount[i] = 0;
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+
+    const uint32_t tile_lanes = p.tile_lanes;
+    const uint32_t TILE = tile_lanes * (uint32_t)LANE_BYTES;
+    const bool fused = p.fused_trim >= 0;
+    const int trim_q = p.fused_trim;
+    const uint32_t Lb = p.sheet.L;
+    uint32_t parity = 0;
+    uint32_t my_total = 0, my_ident = 0;   // DEMUX1 counters of this lane's records
+    unsigned long long my_out = 0;         // lane 0: payload bytes of this warp's tiles
+#define LB(x) ((uint32_t)ls[(x)])
+
+    uint32_t c = 0;
+    if (lane == 0) c = atomicAdd(&st->ticket, 1u);
+    c = __shfl_sync(FULL, c, 0);
+    while (c < p.n_chunks) {
+        const uint64_t c0 = (uint64_t)c * TILE;
+        uint64_t wend = c0 + (uint64_t)WIN;
+        if (wend > p.n) wend = p.n;
+        const uint32_t wlen = (uint32_t)(wend - c0);
+        const bool at_end = (wend == p.n);
+
+        // ---- load the window (TMA bulk copy; plain loads for the ragged tail of the stream)
+        const uint32_t bulk = wlen & ~15u;
+        fence_proxy_async();  // this lane's patches of the previous window before the next TMA write
+        __syncwarp();         // every lane is done with the previous window
+        if (lane == 0 && bulk) {
+            fence_proxy_async();
+            mbar_expect_tx(mbar, bulk);
+            bulk_g2s(win, p.in + c0, bulk, mbar);
+        }
+        if (bulk != (uint32_t)WIN) {
+            const uint32_t o = bulk + (uint32_t)lane;
+            if (o < (uint32_t)WIN + 32u) win[o] = (o < wlen) ? p.in[c0 + o] : (uint8_t)0;
+        }
+        uint32_t c_next = 0;
+        if (lane == 0) c_next = atomicAdd(&st->ticket, 1u);  // consumed at the end of the tile
+        if (bulk) {
+            mbar_wait_parked(mbar, parity);
+            parity ^= 1;
+        }
+        __syncwarp();
+
+        // ---- newline scan.  A '\n' at window offset q starts a line at q+1; the tile owns the line
+        // starts of the newlines inside its TILE bytes (and the line at byte 0 of the stream).  A '\n'
+        // that is the last byte of the stream starts nothing.
+        const uint32_t ls_hi = at_end ? (wlen ? wlen - 1 : 0) : wlen;
+        const uint32_t o0 = (uint32_t)lane * LANE_BYTES;
+        uint32_t mw[NMW];
+        uint32_t hib = 0;
+#pragma unroll
+        for (int i = 0; i < NMW; i++) mw[i] = 0;
+        if (o0 + LANE_BYTES <= ls_hi) {
+#pragma unroll
+            for (int q = 0; q < UPL; q++) {
+                const uint4 v = *(const uint4 *)(win + o0 + q * 16);
+                hib |= v.x | v.y | v.z | v.w;
+                mw[q >> 1] |= nl_map_nat(v) << (16 * (q & 1));
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < UPL; q++) {
+                const uint32_t o = o0 + q * 16;
+                if (o < wlen) {
+                    const uint4 v = *(const uint4 *)(win + o);  // bytes past wlen in the last unit are zero
+                    hib |= v.x | v.y | v.z | v.w;
+                    mw[q >> 1] |= (nl_map_nat(v) & bits_below((int)ls_hi - (int)o)) << (16 * (q & 1));
+                }
+            }
+        }
+        if (__any_sync(FULL, (hib & 0x80808080u) != 0) && lane == 0) atomicOr(&st->flags, F_NON_ASCII);
+        uint32_t cnt_all = 0;
+#pragma unroll
+        for (int i = 0; i < NMW; i++) cnt_all += __popc(mw[i]);
+        const uint32_t cnt_own = (uint32_t)lane < tile_lanes ? cnt_all : 0u;
+        uint32_t incl = (cnt_own << 16) | cnt_all;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += y;
+        }
+        const uint32_t tot = __shfl_sync(FULL, incl, 31);
+        const uint32_t extra = (c == 0) ? 1u : 0u;
+        const uint32_t nls = (tot & 0xFFFFu) + extra;
+        const uint32_t nls_own = (tot >> 16) + extra;
+        if (lane == 0) lookback_publish(p.tile_lines, c, nls_own);
+        {
+            uint32_t idx = ((incl & 0xFFFFu) - cnt_all) + extra;
+            if (lane == 0 && extra) ls[0] = 0;
+            uint32_t base = o0 + 1u;
+#pragma unroll
+            for (int wi = 0; wi < NMW; wi++) {
+                uint32_t m = mw[wi];
+                while (m) {
+                    const uint32_t i = (uint32_t)__ffs((int)m) - 1u;
+                    m &= m - 1;
+                    if (idx < (uint32_t)MAXLINES) ls[idx] = (uint16_t)(base + i);
+                    idx++;
+                }
+                base += 32u;
+            }
+            if (lane < 8) {  // sentinels: lines past the last line start read as "end of window"
+                const uint32_t k = nls + (uint32_t)lane;
+                if (k < (uint32_t)MAXLINES + 8u) ls[k] = (uint16_t)wlen;
+            }
+        }
+        __syncwarp();
+
+        // ---- framing.  Record i is lines 4i..4i+3 of the stream (common.rs:106-112): the tile needs the
+        // global index g0 of its first line, the look-back result.  The framing is guessed from the text
+        // (a line that starts with '@' whose second successor starts with '+'), the plan runs on the guess
+        // and the guess is checked against the look-back before the round writes anything.
+        bool spec = false;
+        uint32_t j0 = 0;
+        uint64_t g0 = 0;
+        if (c != 0 && p.rec_limit == ~0ull && nls >= 6u) {
+            const uint32_t s0 = LB(0), s1 = LB(1), s2 = LB(2), s3 = LB(3), s4 = LB(4), s5 = LB(5);
+            const uint32_t b0 = win[s0], b1 = win[s1], b2 = win[s2], b3 = win[s3], b4 = win[s4], b5 = win[s5];
+            const bool k0 = b0 == '@' && b2 == '+', k1 = b1 == '@' && b3 == '+';
+            const bool k2 = b2 == '@' && b4 == '+', k3 = b3 == '@' && b5 == '+';
+            j0 = k0 ? 0u : k1 ? 1u : k2 ? 2u : 3u;
+            spec = (k0 || k1 || k2 || k3) && j0 < nls_own;
+        }
+        if (!spec) {
+            g0 = lookback_consume(p.tile_lines, c, nls_own, lane);
+            j0 = (4u - (uint32_t)(g0 & 3u)) & 3u;
+        }
+
+        uint32_t nrec = 0;
+        bool bail = false;
+        for (;;) {  // repeated only when the guess was wrong
+            nrec = j0 < nls_own ? (nls_own - 1 - j0) / 4u + 1u : 0u;
+            if (!spec) {
+                const uint64_t first = (g0 + j0) >> 2;
+                if (first >= p.rec_limit) nrec = 0;
+                else if ((uint64_t)nrec > p.rec_limit - first) nrec = (uint32_t)(p.rec_limit - first);
+            }
+            bail = false;
+            if (nrec) {
+                uint32_t jend = j0 + nrec * 4u;
+                const bool eof_ok = at_end && p.final_batch;
+                if (jend >= nls && !eof_ok) {
+                    if (at_end) {  // non-final batch: the trailing incomplete record(s) stay for the next batch
+                        nrec = nls > j0 + 4u ? (nls - j0 - 5u) / 4u + 1u : 0u;
+                        jend = j0 + nrec * 4u;
+                    } else {
+                        bail = true;  // a record runs past the overhang
+                    }
+                }
+                if (!bail && nrec) {
+                    const uint32_t need = jend < nls ? jend : nls - 1;
+                    if (need >= (uint32_t)MAXLINES || nrec > (uint32_t)MAXREC) bail = true;
+                }
+                if (bail) nrec = 0;
+            }
+
+            bool wrong = false;
+            uint64_t rec0 = 0;
+            for (uint32_t r0 = 0; r0 < nrec; r0 += 32u) {
+                // ---- plan: one lane per record, nothing is written
+                const uint32_t r = r0 + (uint32_t)lane;
+                const bool has = r < nrec;
+                const uint32_t j = j0 + (has ? r : 0u) * 4u;
+                const uint32_t L0 = LB(j), L1 = LB(j + 1), L2 = LB(j + 2), L3 = LB(j + 3), L4 = LB(j + 4);
+                uint8_t mode = B_VERBATIM;
+                uint32_t kk = 0, body = L4 - L1;  // three lines verbatim (:209-212)
+                if (fused) {
+                    const bool ok = has && L1 > L0 && win[L1 - 1] == '\n';
+                    bool fine;
+                    mode = B_FAIL;
+                    if (trim_q <= 222) {
+                        fine = plan_trim_warp(win, ok, L1, L2, L3, L4, trim_q, mode, kk, body);
+                    } else {
+                        fine = ok ? plan_trim_body(win, L1, L2, L3, L4, trim_q, mode, kk, body) : true;
+                        __syncwarp();
+                    }
+                    if (!ok || !fine) mode = B_FAIL;
+                }
+                int sample = -1;
+                uint32_t alen = 0, blen = 0, cut0 = 0, cut1 = 0, taglen = 0xFFu;
+                if (D1) {
+                    // fasta_demultiplex.rs:117-194: validate, locate the barcode, match, decide.  Outcome:
+                    // sample >= 0 assigned; -2 ambiguous (best, last, mismatches in alen, blen, taglen);
+                    // -1 unassigned (taglen = failure kind, or 0xFF for a record that never reached the match)
+                    bool live = has;
+                    uint32_t stp = 0;
+                    if (live) {
+                        if (win[L0] != '@') {
+                            taglen = K_BAD_HEADER;
+                            live = false;
+                        } else if (fused && !(L1 > L0 && win[L1 - 1] == '\n')) {
+                            taglen = K_TRUNC_FUSED;
+                            live = false;
+                        } else if (!bc_find16(win, sh_lut, L0, L1, stp)) {
+                            taglen = K_NO_BC;
+                            live = false;
+                        }
+                    }
+                    __syncwarp();
+                    uint32_t raw[NWMAX + 1];
+                    const uint32_t bs = stp + 4;
+                    if (live) {
+                        cut0 = stp - L0;
+                        cut1 = cut0 + 4 + Lb;
+                        load_raw<NWMAX + 1>(win, bs, (Lb + 4u) >> 2, raw);
+                        if (!class_run_is<NWMAX + 1>(raw, sh_lut, Lb, L1 - bs)) {  // :38, :148-150
+                            taglen = K_BC_LEN;
+                            live = false;
+                        }
+                    }
+                    __syncwarp();
+                    if (live) {  // :154-194
+                        uint32_t lowest, best, last;
+                        fidx_match<NWMAX + 1>(raw, p.sheet.hidx, p.sheet.fidx, hcls, S, lowest, best, last);
+                        taglen = 0;
+                        if (lowest <= 1u) {        // :172
+                            if (best == last) {    // :173-178
+                                sample = (int)best;
+                            } else {  // :184-188
+                                sample = -2;
+                                alen = best;
+                                blen = last;
+                                taglen = lowest;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (sample >= 0) {
+                        header_pieces(win, L0, L1, L0 + cut0, L0 + cut1, alen, blen);  // drain (:145) + trim_end (:206)
+                        const uint32_t ul = sh_ulen[sample];
+                        taglen = ul ? 5 + ul : 0;  // " UMI:" + umi (:207)
+                    }
+                    __syncwarp();
+                } else {
+                    // fasta_demultiplex.rs:215-229: the header of mate 2 without its " BC:" field
+                    uint32_t c0h = L1, c1h = L1, fa = 0;
+                    const bool found = has && p.out && bc_find16(win, sh_lut, L0, L1, fa);  // :219-227
+                    __syncwarp();
+                    if (found) {
+                        c0h = fa;
+                        c1h = class_run_end(win, sh_lut, fa + 4, L1);
+                    }
+                    __syncwarp();
+                    if (has && p.out) header_pieces(win, L0, L1, c0h, c1h, alen, blen);  // :229
+                    __syncwarp();
+                    cut0 = c0h - L0;
+                    cut1 = c1h - L0;
+                }
+
+                // ---- the guess is verified against the line count before the first round writes
+                if (spec) {
+                    g0 = lookback_consume(p.tile_lines, c, nls_own, lane);
+                    spec = false;
+                    const uint32_t jt = (4u - (uint32_t)(g0 & 3u)) & 3u;
+                    if (jt != j0) {
+                        j0 = jt;
+                        wrong = true;
+                        break;
+                    }
+                }
+                rec0 = (g0 + j0) >> 2;
+                const uint64_t rec = rec0 + r;
+
+                // ---- outcome of every record: counters, failures, ambiguity events (:169-194)
+                if (has) {
+                    if (D1) {
+                        if (sample == -1 && taglen != 0xFFu && taglen != 0u) report_err(st, rec, taglen);
+                        if (sample != -1 || taglen == 0u) my_total++;  // :169
+                        if (sample >= 0) {                              // :177-178
+                            my_ident++;
+                            if (cc_smem) atomicAdd(&ccount[sample], 1u);
+                            else atomicAdd(&p.counts[sample], 1ull);
+                        } else if (sample == -2) {  // :184-188
+                            const uint32_t ei = atomicAdd(&st->n_events, 1u);
+                            if (ei < p.events_cap) {
+                                Event ev;
+                                ev.record = (uint32_t)rec;
+                                ev.bc_off = (uint32_t)(c0 + L0 + cut0 + 4u);
+                                ev.bc_off2 = 0xFFFFFFFFu;
+                                ev.best = (int16_t)alen;
+                                ev.last = (int16_t)blen;
+                                ev.mismatches = taglen;
+                                p.events[ei] = ev;
+                            } else {
+                                atomicOr(&st->flags, F_EVENTS_OVERFLOW);
+                            }
+                        }
+                    } else {
+                        sample = (p.out && rec < p.r1_stats->n_records) ? (int)p.assign[rec] : -1;
+                        if (sample >= 0) {
+                            const uint32_t ul = sh_ulen[sample];
+                            taglen = ul ? 5 + ul : 0;
+                            if (fused && !(L1 > L0 && win[L1 - 1] == '\n')) {
+                                report_err(st, rec, K_TRUNC_FUSED);
+                                sample = -1;
+                            }
+                        } else {
+                            sample = -1;
+                        }
+                    }
+                }
+                uint32_t outlen = 0;
+                if (has && sample >= 0) {
+                    if (mode == B_FAIL) {  // &seq[..k] would panic (fasta_trim_by_quality.rs:47)
+                        report_err(st, rec, K_SEQ_SHORT);
+                        if (D1) sample = -1;
+                        mode = B_NONE;
+                    } else if (!p.out) {
+                        mode = B_NONE;  // dry run: count only (:77-78,:179)
+                    } else {
+                        outlen = alen + blen + taglen + 1u + body;
+                    }
+                }
+                if (D1 && has) p.assign[rec] = (int16_t)sample;
+
+                // ---- place of the record in the round's output (input order), space for the round
+                uint32_t oincl = outlen;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t y = __shfl_up_sync(FULL, oincl, o);
+                    if (lane >= o) oincl += y;
+                }
+                const uint32_t round_out = __shfl_sync(FULL, oincl, 31);
+                const uint32_t my_off = oincl - outlen;
+                const uint32_t emit_mask = __ballot_sync(FULL, outlen != 0);
+                const uint32_t my_rank = __popc(emit_mask & ((1u << lane) - 1u));
+                const uint32_t n_emit = __popc(emit_mask);
+                unsigned long long rbase = 0;
+                if (lane == 0 && p.out && round_out) {
+                    rbase = atomicAdd(&st->out_cursor, (unsigned long long)((round_out + 15u) & ~15u));
+                    my_out += round_out;
+                }
+                rbase = __shfl_sync(FULL, rbase, 0);
+                bool writable = p.out != nullptr && round_out > 0;
+                if (writable && rbase + ((round_out + 15u) & ~15u) > p.out_cap) {
+                    if (lane == 0) report_err(st, rec0 + r0, K_OUT_OVERFLOW);
+                    writable = false;
+                }
+
+                // ---- emit
+                uint8_t *gu = p.umi + rec * p.sheet.Umax;
+                if (writable) {
+                    uint8_t *gd = p.out + rbase + my_off;
+                    const bool emit = outlen != 0;
+                    const uint32_t ul = taglen ? taglen - 5u : 0u;
+                    // header: " UMI:x\n" goes over the deleted " BC:x" when the header ends with it
+                    const bool hpatch = emit && blen == 0 && alen + taglen + 1u <= L1 - L0;
+                    uint32_t hrun = 0;
+                    uint32_t ulo = 0, uhi = 0;  // the UMI in registers (up to eight characters)
+                    bool ureg = false;
+                    if (emit && ul) {
+                        if (D1) {
+                            // UMI = observed chars where the sheet barcode has 'U' (:200-203), also parked in
+                            // the side table for mate 2; read before the patch below overwrites the barcode
+                            const uint8_t *ob = win + L0 + cut0 + 4;
+                            unsigned long long m = p.sheet.wide ? ((const unsigned long long *)p.sheet.umask)[sample]
+                                                                : (unsigned long long)p.sheet.umask[sample];
+                            const uint32_t u0 = (uint32_t)__ffsll((long long)m) - 1u;
+                            if (ul <= 8u && (m >> u0) == ((1ull << ul) - 1ull)) {  // one run of U (the usual sheet)
+                                const uint8_t *us = ob + u0;
+                                const uint32_t sh = ((uint32_t)(uintptr_t)us & 3u) * 8u;
+                                const uint32_t *uw = (const uint32_t *)((uintptr_t)us & ~(uintptr_t)3);
+                                const uint32_t w0 = uw[0], w1 = uw[1], w2 = uw[2];
+                                ulo = __funnelshift_r(w0, w1, sh);
+                                uhi = __funnelshift_r(w1, w2, sh);
+                                ureg = true;
+                                if (p.sheet.Umax == 8u && ul == 8u) {
+                                    *(uint2 *)gu = make_uint2(ulo, uhi);
+                                } else {
+                                    for (uint32_t t = 0; t < ul; t++)
+                                        gu[t] = (uint8_t)(t < 4u ? ulo >> (8u * t) : uhi >> (8u * (t - 4u)));
+                                }
+                            } else {
+                                uint32_t t = 0;
+                                while (m) {
+                                    const uint32_t q = (uint32_t)__ffsll((long long)m) - 1u;
+                                    m &= m - 1;
+                                    gu[t++] = ob[q];
+                                }
+                            }
+                        } else if (p.sheet.Umax == 8u) {
+                            const uint2 v = *(const uint2 *)gu;
+                            ulo = v.x;
+                            uhi = v.y;
+                            ureg = true;
+                        }
+                    }
+                    __syncwarp();
+#define UMI_BYTE(t) (ureg ? (uint8_t)((t) < 4u ? ulo >> (8u * (t)) : uhi >> (8u * ((t) - 4u))) : gu[(t)])
+                    if (hpatch) {
+                        uint8_t *d = win + L0 + alen;
+                        if (taglen) {
+                            for (uint32_t t = 0; t < ul; t++) d[5 + t] = UMI_BYTE(t);
+                            d[0] = ' '; d[1] = 'U'; d[2] = 'M'; d[3] = 'I'; d[4] = ':';
+                        }
+                        d[taglen] = '\n';
+                        hrun = alen + taglen + 1u;
+                    }
+                    __syncwarp();
+                    gcopy(gd, win + L0, hrun);
+                    __syncwarp();
+                    if (emit && !hpatch) {  // rare: a header piece after the cut, or no room for the tag
+                        uint8_t *d = gd;
+                        for (uint32_t i = 0; i < alen; i++) *d++ = win[L0 + i];
+                        for (uint32_t i = 0; i < blen; i++) *d++ = win[L0 + cut1 + i];
+                        if (taglen) {
+                            d[0] = ' '; d[1] = 'U'; d[2] = 'M'; d[3] = 'I'; d[4] = ':';
+                            for (uint32_t t = 0; t < ul; t++) d[5 + t] = UMI_BYTE(t);
+                            d += taglen;
+                        }
+                        *d = '\n';
+                    }
+                    __syncwarp();
+                    gd += alen + blen + taglen + 1u;
+                    // body: "\n+\n" and "\n" are patched in behind the kept bases / qualities (:47)
+                    uint32_t run1 = 0, run2 = 0;
+                    bool bslow = false;
+                    if (emit) {
+                        if (mode == B_VERBATIM) {
+                            run1 = body;
+                        } else if (mode == B_TRIM) {
+                            if (L1 + kk + 3u <= L3) {
+                                uint8_t *d = win + L1 + kk;
+                                d[0] = '\n'; d[1] = '+'; d[2] = '\n';
+                                win[L3 + kk] = '\n';
+                                run1 = kk + 3u;
+                                run2 = kk + 1u;
+                            } else {
+                                bslow = true;
+                            }
+                        } else if (mode == B_GARBAGE) {  // :44-45
+                            if (L1 + 6u <= L4) {
+                                uint8_t *d = win + L1;
+                                d[0] = 'N'; d[1] = '\n'; d[2] = '+'; d[3] = '\n'; d[4] = '!'; d[5] = '\n';
+                                run1 = 6u;
+                            } else {
+                                bslow = true;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    gcopy(gd, win + L1, run1);
+                    __syncwarp();
+                    gcopy(gd + run1, win + L3, run2);
+                    __syncwarp();
+                    if (bslow) {  // rare: a '+' line too short to hold the patch
+                        uint8_t *d = gd;
+                        if (mode == B_TRIM) {
+                            for (uint32_t i = 0; i < kk; i++) *d++ = win[L1 + i];
+                            d[0] = '\n'; d[1] = '+'; d[2] = '\n';
+                            d += 3;
+                            for (uint32_t i = 0; i < kk; i++) *d++ = win[L3 + i];
+                            *d = '\n';
+                        } else {
+                            d[0] = 'N'; d[1] = '\n'; d[2] = '+'; d[3] = '\n'; d[4] = '!'; d[5] = '\n';
+                        }
+                    }
+                    if (emit) {
+                        Group g;
+                        g.sample = (uint16_t)sample;
+                        g.len = (uint16_t)outlen;
+                        p.groups[rec0 + r0 + my_rank] = g;
+                    }
+                } else if (D1 && p.sheet.Umax && has && sample >= 0) {
+                    // nothing is written here (dry run / overflow): mate 2 still needs the UMI side table
+                    const uint8_t *ob = win + L0 + cut0 + 4;
+                    unsigned long long m = p.sheet.wide ? ((const unsigned long long *)p.sheet.umask)[sample]
+                                                        : (unsigned long long)p.sheet.umask[sample];
+                    uint32_t t = 0;
+                    while (m) {
+                        const uint32_t q = (uint32_t)__ffsll((long long)m) - 1u;
+                        m &= m - 1;
+                        gu[t++] = ob[q];
+                    }
+                }
+                if (lane == 0 && p.out) {
+                    ChunkRow row;
+                    row.base = rbase;
+                    row.first_group = (uint32_t)(rec0 + r0);
+                    row.n_groups = writable ? n_emit : 0u;
+                    p.rows[(size_t)c * GeoW::ROUNDS + (r0 >> 5)] = row;
+                }
+                __syncwarp();
+            }
+            if (wrong) continue;
+            if (spec) {  // no round ran (the tile was given up): the prefix is still owed to the successors
+                g0 = lookback_consume(p.tile_lines, c, nls_own, lane);
+                spec = false;
+                const uint32_t jt = (4u - (uint32_t)(g0 & 3u)) & 3u;
+                if (jt != j0) {  // also re-evaluates a tile given up under the wrong framing
+                    j0 = jt;
+                    continue;
+                }
+            }
+            break;
+        }
+        if (bail && lane == 0) atomicOr(&st->flags, F_NEED_GENERAL);
+        if (p.out) {  // rows of the rounds that did not run
+            const uint32_t ran = (nrec + 31u) >> 5;
+            if ((uint32_t)lane < (uint32_t)GeoW::ROUNDS && (uint32_t)lane >= ran) {
+                ChunkRow row;
+                row.base = 0;
+                row.first_group = 0;
+                row.n_groups = 0;
+                p.rows[(size_t)c * GeoW::ROUNDS + lane] = row;
+            }
+        }
+        if (lane == 0) {
+            if (c == p.n_chunks - 1) st->n_lines = g0 + nls_own;
+            if (nrec) {
+                atomicAdd(&st->n_records, (unsigned long long)nrec);
+                atomicMax(&st->consumed, (unsigned long long)(c0 + LB(j0 + nrec * 4u)));
+            }
+        }
+        c = __shfl_sync(FULL, c_next, 0);
+    }
+#undef LB
+#undef UMI_BYTE
+    if (lane == 0 && my_out) atomicAdd(&st->out_bytes, my_out);
+    if (D1) {  // fasta_demultiplex.rs:108-109,169,177-178
+        const uint32_t wt = __reduce_add_sync(FULL, my_total), wi = __reduce_add_sync(FULL, my_ident);
+        if (lane == 0 && wt) atomicAdd(&p.counts[S], (unsigned long long)wt);
+        if (lane == 0 && wi) atomicAdd(&p.counts[S + 1], (unsigned long long)wi);
+        if (cc_smem) {
+            __syncthreads();
+            for (uint32_t s = tid; s < S; s += GeoW::NT)
+                if (ccount[s]) atomicAdd(&p.counts[s], (unsigned long long)ccount[s]);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launcher
+// ------------------------------------------------------------------------------------------------
+static uint32_t warp_smem(uint32_t S, uint32_t n_classes, uint32_t nwp, bool d1) {
+    uint32_t o = WLayout::dyn;
+    if (d1) {
+        o += ((n_classes * HIDX_CLS_ROWS * nwp + 3u) & ~3u) * 4u;
+        if (S <= (uint32_t)FAST_CCOUNT_MAX) o += ((S + 3u) & ~3u) * 4u;
+    }
+    o += (S + 15u) & ~15u;  // per-sample UMI lengths
+    return o;
+}
+
+bool warp_supported(int op, const KParams &p) {
+    if (op != OP_DEMUX1 && op != OP_DEMUX2) return false;
+    if (p.lpr != 4 || p.n_index || !p.sheet.hidx.n_classes || !p.sheet.fidx.table) return false;
+    if (p.tile_lanes < 8 || p.tile_lanes > 30) return false;
+    return warp_smem(p.sheet.S, p.sheet.hidx.n_classes, p.sheet.hidx.nwp, true) <= 115200u;
+}
+
+template <int OP, int NWMAX>
+static int launch_warp_one(const KParams &p, int sm_count, cudaStream_t stream, const char **err) {
+    auto kfn = sk_warp_kernel<OP, NWMAX>;
+    const int smem = (int)warp_smem(p.sheet.S, p.sheet.hidx.n_classes, p.sheet.hidx.nwp, OP == OP_DEMUX1);
+    cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) {
+        *err = cudaGetErrorString(e);
+        return -1;
+    }
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, GeoW::NT, smem);
+    if (e != cudaSuccess || per_sm < 1) {
+        *err = e != cudaSuccess ? cudaGetErrorString(e) : "kernel does not fit on an SM";
+        return -1;
+    }
+    const long long tiles_per_cta = GeoW::WARPS;
+    long long grid = (long long)sm_count * per_sm;
+    const long long want = ((long long)p.n_chunks + tiles_per_cta - 1) / tiles_per_cta;
+    if (grid > want) grid = want;
+    if (grid < 1) return 0;
+    kfn<<<(unsigned)grid, GeoW::NT, smem, stream>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        *err = cudaGetErrorString(e);
+        return -1;
+    }
+    return 1;
+}
+
+int launch_warp_kernel(int op, const KParams &p, int sm_count, void *stream_, const char **err) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const bool wide = p.sheet.wide != 0;
+    switch (op) {
+        case OP_DEMUX1:
+            return wide ? launch_warp_one<OP_DEMUX1, 16>(p, sm_count, stream, err)
+                        : launch_warp_one<OP_DEMUX1, 8>(p, sm_count, stream, err);
+        case OP_DEMUX2: return launch_warp_one<OP_DEMUX2, 8>(p, sm_count, stream, err);
+    }
+    *err = "operator not handled by the warp engine";
+    return -1;
+}
+
+}  // namespace sk
