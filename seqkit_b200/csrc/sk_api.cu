@@ -584,7 +584,8 @@ static void base_params(sk_ctx *ctx, Slot *s, int which, KParams &p, int eng = E
 
 static int run_pass(sk_ctx *ctx, Slot *s, int which, int op, const KParams &p, bool ordered_out, int eng = ENG_GENERAL) {
     if (p.n_chunks == 0) return SK_OK;
-    CK(cudaMemsetAsync(p.tile_lines, 0, (uint64_t)p.n_chunks * 8, s->stream));
+    // look-back words (the warp engine keeps 8 + 2 bytes per tile, sk_warp.cu:wlb_agg)
+    CK(cudaMemsetAsync(p.tile_lines, 0, eng == ENG_WARP ? (uint64_t)p.n_chunks * 10 + 64 : (uint64_t)p.n_chunks * 8, s->stream));
     if (ordered_out) CK(cudaMemsetAsync(p.tile_out, 0, (uint64_t)p.n_chunks * 8, s->stream));
     const char *err = nullptr;
     if (ctx->profiling) CK(cudaEventRecord(s->ev[which][0], s->stream));

@@ -9,8 +9,9 @@
 //     different phases, so nobody waits at a barrier and every per-record step has its 32 lanes busy;
 //   * newline scan: 25 conflict-free LDS.128 per lane, newline maps in registers, one shuffle scan,
 //     line starts written by plain ffs loops;
-//   * record framing by global line index (common.rs:106-112) through the decoupled look-back,
-//     speculated from the text and verified before anything is written (as in the lean engine);
+//   * record framing by global line index (common.rs:106-112): tiles publish their line counts as
+//     16-bit words, a tile sums the 256 counts before it with one 16-byte load per lane and adds the
+//     inclusive prefix of the tile before those (wlb_consume);
 //   * per record, in registers: '@' check, leftmost " BC:x", class run, pigeonhole match, header
 //     surgery, quality trim (fasta_demultiplex.rs:117-212, fasta_trim_by_quality.rs:28-48);
 //   * output: a round (<= 32 records) takes its space with one atomicAdd, the record's edits are
@@ -91,6 +92,79 @@ __device__ __forceinline__ void gcopy(uint8_t *dst, const uint8_t *src, uint32_t
     }
 }
 
+// Look-back of the warp engine over p.tile_lines: inc[c] (u64: bit 63 | lines through tile c) and, behind
+// those, agg[c] (u16: lines owned by tile c, plus one; 0 = not yet known).  A tile's exclusive prefix is
+// the inclusive prefix of tile 8(b-32)-1 plus the 256 + (c & 7) counts after it, b = c / 8: one aligned
+// 16-byte load per lane.  Tiles are handed out by a ticket counter, so every predecessor is owned by a
+// running warp that never waits on a later tile.
+__device__ __forceinline__ uint16_t *wlb_agg(uint64_t *tile_lines, uint32_t n_tiles) {
+    return (uint16_t *)(tile_lines + ((n_tiles + 1u) & ~1u));
+}
+__device__ __forceinline__ void wlb_publish(uint16_t *agg, uint32_t c, uint32_t count) {
+    const unsigned short v = (unsigned short)(count + 1u);
+    asm volatile("st.relaxed.gpu.global.u16 [%0], %1;" ::"l"(agg + c), "h"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t zero_half(uint32_t x) { return (x - 0x00010001u) & ~x & 0x80008000u; }
+static __device__ __noinline__ uint64_t wlb_consume(uint64_t *inc, const uint16_t *agg, uint32_t c, uint32_t own, int lane) {
+    constexpr uint32_t FULL = 0xffffffffu;
+    uint64_t excl = 0;
+    const uint32_t b = c >> 3;  // block of eight counts that holds c
+    if (b >= 32u) {
+        const uint16_t *blk = agg + 8u * (b - 32u + (uint32_t)lane);
+        const uint16_t *part = agg + 8u * b;
+        const uint32_t npart = c & 7u;
+        uint32_t sum;
+        for (;;) {
+            uint32_t x0, x1, x2, x3;
+            asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "l"(blk) : "memory");
+            bool ok = (zero_half(x0) | zero_half(x1) | zero_half(x2) | zero_half(x3)) == 0u;
+            sum = (x0 & 0xFFFFu) + (x0 >> 16) + (x1 & 0xFFFFu) + (x1 >> 16) + (x2 & 0xFFFFu) + (x2 >> 16) + (x3 & 0xFFFFu) + (x3 >> 16) - 8u;
+            if (lane == 0 && npart) {
+                uint32_t y[4];
+                asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(y[0]), "=r"(y[1]), "=r"(y[2]), "=r"(y[3]) : "l"(part) : "memory");
+#pragma unroll
+                for (int k = 0; k < 7; k++)
+                    if ((uint32_t)k < npart) {
+                        const uint32_t e = (y[k >> 1] >> (16 * (k & 1))) & 0xFFFFu;
+                        ok = ok && e != 0u;
+                        sum += e - 1u;
+                    }
+            }
+            if (__all_sync(FULL, ok)) break;
+            __nanosleep(40);
+        }
+        sum = __reduce_add_sync(FULL, sum);
+        const uint32_t t = 8u * (b - 32u);
+        uint64_t w = 1ull << 63;
+        if (t > 0u && lane == 0) {
+            w = ts_load(&inc[t - 1u]);
+            while (!(w >> 63)) {
+                __nanosleep(40);
+                w = ts_load(&inc[t - 1u]);
+            }
+        }
+        w = __shfl_sync(FULL, w, 0);
+        excl = (w & ~(1ull << 63)) + sum;
+    } else {
+        uint32_t sum = 0;
+        for (uint32_t i = (uint32_t)lane; i < c; i += 32u) {
+            unsigned short e;
+            for (;;) {
+                asm volatile("ld.relaxed.gpu.global.u16 %0, [%1];" : "=h"(e) : "l"(agg + i) : "memory");
+                if (e) break;
+                __nanosleep(40);
+            }
+            sum += (uint32_t)e - 1u;
+        }
+        excl = __reduce_add_sync(FULL, sum);
+    }
+    if (lane == 0) {
+        const uint64_t v = (1ull << 63) | (excl + own);
+        asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(inc + c), "l"(v) : "memory");
+    }
+    return excl;
+}
+
 template <int OP, int NWMAX>
 __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const __grid_constant__ KParams p) {
     constexpr bool D1 = OP == OP_DEMUX1;
@@ -130,6 +204,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
     const bool fused = p.fused_trim >= 0;
     const int trim_q = p.fused_trim;
     const uint32_t Lb = p.sheet.L;
+    uint16_t *agg16 = wlb_agg(p.tile_lines, p.n_chunks);
     uint32_t parity = 0;
     uint32_t my_total = 0, my_ident = 0;   // DEMUX1 counters of this lane's records
     unsigned long long my_out = 0;         // lane 0: payload bytes of this warp's tiles
@@ -154,12 +229,14 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
             mbar_expect_tx(mbar, bulk);
             bulk_g2s(win, p.in + c0, bulk, mbar);
         }
-        if (bulk != (uint32_t)WIN) {
-            const uint32_t o = bulk + (uint32_t)lane;
-            if (o < (uint32_t)WIN + 32u) win[o] = (o < wlen) ? p.in[c0 + o] : (uint8_t)0;
+        if (bulk != (uint32_t)WIN) {  // last window of the stream: ragged tail, zeros up to the end of the window
+            if (lane < 16) {
+                const uint32_t o = bulk + (uint32_t)lane;
+                win[o] = (o < wlen) ? p.in[c0 + o] : (uint8_t)0;
+            }
+            for (uint32_t o = bulk + 16u + 16u * (uint32_t)lane; o < (uint32_t)WIN + 32u; o += 512u)
+                *(uint4 *)(win + o) = make_uint4(0u, 0u, 0u, 0u);
         }
-        uint32_t c_next = 0;
-        if (lane == 0) c_next = atomicAdd(&st->ticket, 1u);  // consumed at the end of the tile
         if (bulk) {
             mbar_wait_parked(mbar, parity);
             parity ^= 1;
@@ -175,23 +252,15 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
         uint32_t hib = 0;
 #pragma unroll
         for (int i = 0; i < NMW; i++) mw[i] = 0;
-        if (o0 + LANE_BYTES <= ls_hi) {
 #pragma unroll
-            for (int q = 0; q < UPL; q++) {
-                const uint4 v = *(const uint4 *)(win + o0 + q * 16);
-                hib |= v.x | v.y | v.z | v.w;
-                mw[q >> 1] |= nl_map_nat(v) << (16 * (q & 1));
-            }
-        } else {
+        for (int q = 0; q < UPL; q++) {
+            const uint4 v = *(const uint4 *)(win + o0 + q * 16);
+            hib |= v.x | v.y | v.z | v.w;
+            mw[q >> 1] |= nl_map_nat(v) << (16 * (q & 1));
+        }
+        if (o0 + LANE_BYTES > ls_hi) {  // last window of the stream only
 #pragma unroll
-            for (int q = 0; q < UPL; q++) {
-                const uint32_t o = o0 + q * 16;
-                if (o < wlen) {
-                    const uint4 v = *(const uint4 *)(win + o);  // bytes past wlen in the last unit are zero
-                    hib |= v.x | v.y | v.z | v.w;
-                    mw[q >> 1] |= (nl_map_nat(v) & bits_below((int)ls_hi - (int)o)) << (16 * (q & 1));
-                }
-            }
+            for (int i = 0; i < NMW; i++) mw[i] &= bits_below((int)ls_hi - (int)(o0 + 32u * i));
         }
         if (__any_sync(FULL, (hib & 0x80808080u) != 0) && lane == 0) atomicOr(&st->flags, F_NON_ASCII);
         uint32_t cnt_all = 0;
@@ -208,7 +277,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
         const uint32_t extra = (c == 0) ? 1u : 0u;
         const uint32_t nls = (tot & 0xFFFFu) + extra;
         const uint32_t nls_own = (tot >> 16) + extra;
-        if (lane == 0) lookback_publish(p.tile_lines, c, nls_own);
+        if (lane == 0) wlb_publish(agg16, c, nls_own);
         {
             uint32_t idx = ((incl & 0xFFFFu) - cnt_all) + extra;
             if (lane == 0 && extra) ls[0] = 0;
@@ -232,30 +301,16 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
         __syncwarp();
 
         // ---- framing.  Record i is lines 4i..4i+3 of the stream (common.rs:106-112): the tile needs the
-        // global index g0 of its first line, the look-back result.  The framing is guessed from the text
-        // (a line that starts with '@' whose second successor starts with '+'), the plan runs on the guess
-        // and the guess is checked against the look-back before the round writes anything.
-        bool spec = false;
-        uint32_t j0 = 0;
-        uint64_t g0 = 0;
-        if (c != 0 && p.rec_limit == ~0ull && nls >= 6u) {
-            const uint32_t s0 = LB(0), s1 = LB(1), s2 = LB(2), s3 = LB(3), s4 = LB(4), s5 = LB(5);
-            const uint32_t b0 = win[s0], b1 = win[s1], b2 = win[s2], b3 = win[s3], b4 = win[s4], b5 = win[s5];
-            const bool k0 = b0 == '@' && b2 == '+', k1 = b1 == '@' && b3 == '+';
-            const bool k2 = b2 == '@' && b4 == '+', k3 = b3 == '@' && b5 == '+';
-            j0 = k0 ? 0u : k1 ? 1u : k2 ? 2u : 3u;
-            spec = (k0 || k1 || k2 || k3) && j0 < nls_own;
-        }
-        if (!spec) {
-            g0 = lookback_consume(p.tile_lines, c, nls_own, lane);
-            j0 = (4u - (uint32_t)(g0 & 3u)) & 3u;
-        }
+        // global index g0 of its first line.  The counts it sums were published right after their tiles'
+        // scans, so this rarely waits.
+        const uint64_t g0 = wlb_consume(p.tile_lines, agg16, c, nls_own, lane);
+        const uint32_t j0 = (4u - (uint32_t)(g0 & 3u)) & 3u;
 
         uint32_t nrec = 0;
         bool bail = false;
-        for (;;) {  // repeated only when the guess was wrong
+        {
             nrec = j0 < nls_own ? (nls_own - 1 - j0) / 4u + 1u : 0u;
-            if (!spec) {
+            {
                 const uint64_t first = (g0 + j0) >> 2;
                 if (first >= p.rec_limit) nrec = 0;
                 else if ((uint64_t)nrec > p.rec_limit - first) nrec = (uint32_t)(p.rec_limit - first);
@@ -279,8 +334,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 if (bail) nrec = 0;
             }
 
-            bool wrong = false;
-            uint64_t rec0 = 0;
+            const uint64_t rec0 = (g0 + j0) >> 2;
             for (uint32_t r0 = 0; r0 < nrec; r0 += 32u) {
                 // ---- plan: one lane per record, nothing is written
                 const uint32_t r = r0 + (uint32_t)lane;
@@ -372,18 +426,6 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                     cut1 = c1h - L0;
                 }
 
-                // ---- the guess is verified against the line count before the first round writes
-                if (spec) {
-                    g0 = lookback_consume(p.tile_lines, c, nls_own, lane);
-                    spec = false;
-                    const uint32_t jt = (4u - (uint32_t)(g0 & 3u)) & 3u;
-                    if (jt != j0) {
-                        j0 = jt;
-                        wrong = true;
-                        break;
-                    }
-                }
-                rec0 = (g0 + j0) >> 2;
                 const uint64_t rec = rec0 + r;
 
                 // ---- outcome of every record: counters, failures, ambiguity events (:169-194)
@@ -522,8 +564,6 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                         hrun = alen + taglen + 1u;
                     }
                     __syncwarp();
-                    gcopy(gd, win + L0, hrun);
-                    __syncwarp();
                     if (emit && !hpatch) {  // rare: a header piece after the cut, or no room for the tag
                         uint8_t *d = gd;
                         for (uint32_t i = 0; i < alen; i++) *d++ = win[L0 + i];
@@ -564,10 +604,15 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                         }
                     }
                     __syncwarp();
-                    gcopy(gd, win + L1, run1);
-                    __syncwarp();
-                    gcopy(gd + run1, win + L3, run2);
-                    __syncwarp();
+                    // the record's runs: header, bases (+ "\n+\n"), qualities (+ "\n")
+#pragma unroll 1
+                    for (int q = 0; q < 3; q++) {
+                        const uint32_t so = q == 0 ? L0 : q == 1 ? L1 : L3;
+                        const uint32_t ln = q == 0 ? hrun : q == 1 ? run1 : run2;
+                        uint8_t *dd = q == 0 ? gd - (alen + blen + taglen + 1u) : q == 1 ? gd : gd + run1;
+                        gcopy(dd, win + so, ln);
+                        __syncwarp();
+                    }
                     if (bslow) {  // rare: a '+' line too short to hold the patch
                         uint8_t *d = gd;
                         if (mode == B_TRIM) {
@@ -607,17 +652,6 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 }
                 __syncwarp();
             }
-            if (wrong) continue;
-            if (spec) {  // no round ran (the tile was given up): the prefix is still owed to the successors
-                g0 = lookback_consume(p.tile_lines, c, nls_own, lane);
-                spec = false;
-                const uint32_t jt = (4u - (uint32_t)(g0 & 3u)) & 3u;
-                if (jt != j0) {  // also re-evaluates a tile given up under the wrong framing
-                    j0 = jt;
-                    continue;
-                }
-            }
-            break;
         }
         if (bail && lane == 0) atomicOr(&st->flags, F_NEED_GENERAL);
         if (p.out) {  // rows of the rounds that did not run
@@ -637,7 +671,10 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 atomicMax(&st->consumed, (unsigned long long)(c0 + LB(j0 + nrec * 4u)));
             }
         }
-        c = __shfl_sync(FULL, c_next, 0);
+        // the next ticket is taken only now: a tile's count must appear soon after its ticket, its
+        // successors wait for it
+        if (lane == 0) c = atomicAdd(&st->ticket, 1u);
+        c = __shfl_sync(FULL, c, 0);
     }
 #undef LB
 #undef UMI_BYTE

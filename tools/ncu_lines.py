@@ -69,6 +69,12 @@ def demangle_match(kname, funcs):
             if "sk_fast_kernel" in f and ("%d%s" % (len(geo), geo)) in f and ("Li%sELi%sE" % (op, nw)) in f:
                 return f
         return None
+    m = re.search(r"sk_warp_kernel<\(int\)(\d+), \(int\)(\d+)>", kname)
+    if m:
+        for f in funcs:
+            if "sk_warp_kernel" in f and ("Li%sELi%sE" % (m.group(1), m.group(2))) in f:
+                return f
+        return None
     m = re.search(r"sk_chunk_kernel<sk::(\w+), \(int\)(\d+), (unsigned int|unsigned long)", kname)
     if not m:
         return None
