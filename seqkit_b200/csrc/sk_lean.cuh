@@ -284,6 +284,136 @@ __device__ __forceinline__ bool plan_trim_warp(const uint8_t *b, bool has, uint3
     return lowest_k <= L2 - L1;
 }
 
+// Running totals of fasta_trim_by_quality.rs:33-36 over the aligned 16-byte block at window offset a, in
+// the order the reference examines the bytes, as keys K[i] = 16 * T[i] + i, T[i] = the total after byte
+// a+15-i starting from `total`: the minimum key names the lowest total and, among equal totals, the byte
+// examined first (:38); a key above 15 is a total above 0 (:37).  Bytes outside the quality string
+// [L3,E) contribute nothing (they are replaced by the byte whose contribution is zero, sub = 33 +
+// min_baseq <= 255).  A byte below '!' takes the wrapping u8 subtraction (:35): its contribution is 256
+// more than q - sub, added through a second set of dot products over the flags of those bytes.
+__device__ __forceinline__ void blk16_keys(const uint8_t *b, uint32_t a, uint32_t L3, uint32_t E, int sub, int total,
+                                           int (&K)[16]) {
+    uint4 v = *(const uint4 *)(b + a);
+    if (a < L3 || a + 16u > E) {
+        const uint32_t lo = a < L3 ? L3 - a : 0u;                      // first kept byte of the block
+        const uint32_t hi = a + 16u > E ? (E > a ? E - a : 0u) : 16u;  // one past the last kept byte
+        const uint32_t sub4 = (uint32_t)sub * 0x01010101u;
+        auto keep = [&](uint32_t w, int q) {  // bytes [lo, hi) of the block keep their value, the others become `sub`
+            const int l = (int)lo - 4 * q, h = (int)hi - 4 * q;
+            const uint32_t ml = l <= 0 ? 0xFFFFFFFFu : (l >= 4 ? 0u : 0xFFFFFFFFu << (8 * l));
+            const uint32_t mh = h >= 4 ? 0xFFFFFFFFu : (h <= 0 ? 0u : 0xFFFFFFFFu >> (8 * (4 - h)));
+            const uint32_t m = ml & mh;
+            return (w & m) | (sub4 & ~m);
+        };
+        v.x = keep(v.x, 0);
+        v.y = keep(v.y, 1);
+        v.z = keep(v.z, 2);
+        v.w = keep(v.w, 3);
+    }
+    const uint32_t H = 0x80808080u, C = 0x21212121u;
+    const uint32_t gx = ((v.x | H) - C) | v.x, gy = ((v.y | H) - C) | v.y;  // bit 7 clear <=> byte below '!'
+    const uint32_t gz = ((v.z | H) - C) | v.z, gw = ((v.w | H) - C) | v.w;  // (a filler byte may be >= 0x80)
+    const int s16 = 16 * sub;
+    int base = 16 * total;
+#define SK_KEY4(w, q)                                                                       \
+    K[4 * q + 0] = (int)__dp4a(w, 0x10000000u, (uint32_t)(base - s16 + 4 * q));             \
+    K[4 * q + 1] = (int)__dp4a(w, 0x10100000u, (uint32_t)(base - 2 * s16 + 4 * q + 1));     \
+    K[4 * q + 2] = (int)__dp4a(w, 0x10101000u, (uint32_t)(base - 3 * s16 + 4 * q + 2));     \
+    K[4 * q + 3] = (int)__dp4a(w, 0x10101010u, (uint32_t)(base - 4 * s16 + 4 * q + 3));     \
+    base = K[4 * q + 3] - (4 * q + 3);
+    SK_KEY4(v.w, 0)
+    SK_KEY4(v.z, 1)
+    SK_KEY4(v.y, 2)
+    SK_KEY4(v.x, 3)
+#undef SK_KEY4
+    if ((~(gx & gy & gz & gw)) & H) {  // rare: add 256 per byte below '!' examined so far
+        const uint32_t fx = (~gx & H) >> 7, fy = (~gy & H) >> 7, fz = (~gz & H) >> 7, fw = (~gw & H) >> 7;
+        uint32_t n = 0;
+#define SK_BAD4(f, q)                                               \
+    K[4 * q + 0] += 4096 * (int)__dp4a(f, 0x01000000u, n);          \
+    K[4 * q + 1] += 4096 * (int)__dp4a(f, 0x01010000u, n);          \
+    K[4 * q + 2] += 4096 * (int)__dp4a(f, 0x01010100u, n);          \
+    n = __dp4a(f, 0x01010101u, n);                                  \
+    K[4 * q + 3] += 4096 * (int)n;
+        SK_BAD4(fw, 0)
+        SK_BAD4(fz, 1)
+        SK_BAD4(fy, 2)
+        SK_BAD4(fx, 3)
+#undef SK_BAD4
+    }
+}
+__device__ __forceinline__ int max3i(int a, int b, int c) { return max(max(a, b), c); }
+__device__ __forceinline__ int min3i(int a, int b, int c) { return min(min(a, b), c); }
+
+// fasta_trim_by_quality.rs:28-48 for one record per lane, sixteen quality bytes per step: every lane
+// walks its quality string down in aligned 16-byte blocks; the minimum key of a block gives the lowest
+// total and its position at once (:38), the block in which the running total first exceeds 0 (:37) is
+// looked into once after the loop (its totals before the break may still lower the minimum).  Must be
+// called by all 32 lanes (`has` = this lane carries a record).  min_baseq <= 222.
+__device__ __forceinline__ bool plan_trim_lane16(const uint8_t *b, bool has, uint32_t L1, uint32_t L2, uint32_t L3, uint32_t L4,
+                                                 int minq, uint8_t &mode, uint32_t &kk, uint32_t &body_len) {
+    const uint32_t NONE = 0xFFFFFFFFu;
+    uint32_t k = has ? L4 - L3 : 0u;
+#pragma unroll 1
+    while (k > 0 && is_ws(b[L3 + k - 1])) k--;  // qual.trim_end().len()  (:31)
+    __syncwarp();
+    const uint32_t E = L3 + k;
+    const int sub = 33 + minq;
+    int total = -50, lowest = -50;  // :28-29
+    uint32_t lowest_k = k, brk_a = NONE;
+    uint32_t a = k ? ((E - 1u) & ~15u) : 0u;
+    bool active = k > 0;
+#pragma unroll 1
+    while (__any_sync(0xffffffffu, active)) {
+        if (active) {
+            int K[16];
+            blk16_keys(b, a, L3, E, sub, total, K);
+            const int mx = max3i(max3i(max3i(K[0], K[1], K[2]), max3i(K[3], K[4], K[5]), max3i(K[6], K[7], K[8])),
+                                 max3i(K[9], K[10], K[11]), max3i(max3i(K[12], K[13], K[14]), K[15], K[15]));
+            if (mx > 15) {  // the break is inside this block; `total` stays the total before the block
+                brk_a = a;
+                active = false;
+            } else {
+                const int mn = min3i(min3i(min3i(K[0], K[1], K[2]), min3i(K[3], K[4], K[5]), min3i(K[6], K[7], K[8])),
+                                     min3i(K[9], K[10], K[11]), min3i(min3i(K[12], K[13], K[14]), K[15], K[15]));
+                if ((mn >> 4) < lowest) {  // strict '<': an earlier block keeps a tie
+                    lowest = mn >> 4;
+                    lowest_k = a + 15u - (uint32_t)(mn & 15) - L3;
+                }
+                total = K[15] >> 4;
+                if (a <= L3) active = false;
+                else a -= 16;
+            }
+        }
+    }
+    if (brk_a != NONE) {  // totals of the break block up to the break
+        int K[16];
+        blk16_keys(b, brk_a, L3, E, sub, total, K);
+        bool ok = true;
+        int best = 0x7FFFFFFF;
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            ok = ok && K[i] <= 15;  // totals after the break are never looked at
+            best = (ok && K[i] < best) ? K[i] : best;
+        }
+        if (best != 0x7FFFFFFF && (best >> 4) < lowest) {
+            lowest = best >> 4;
+            lowest_k = brk_a + 15u - (uint32_t)(best & 15) - L3;
+        }
+    }
+    __syncwarp();
+    if (lowest_k == 0) {  // :44-45
+        mode = B_GARBAGE;
+        kk = 0;
+        body_len = 6;  // "N\n+\n!\n"
+        return true;
+    }
+    mode = B_TRIM;
+    kk = lowest_k;
+    body_len = 2 * lowest_k + 4;  // seq[..k] "\n+\n" qual[..k] "\n"  (:47)
+    return lowest_k <= L2 - L1;
+}
+
 // plan_trim_warp with two adjacent lanes per record (sub = 0 / 1): the pair walks the quality string
 // down sixteen bytes per step, lane 0 on the upper 8-byte block and lane 1 on the one below it; each
 // lane computes its block's totals relative to 0, one shuffle gives lane 1 the sum of lane 0's block

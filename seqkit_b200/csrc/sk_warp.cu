@@ -47,6 +47,7 @@ static_assert(WLayout::per_warp % 16 == 0, "warp areas are 16-byte aligned");
 // bytes up to a word of the destination, words up to a 16-byte unit, then 16 bytes per step
 // (4 LDS.32 + 4 funnel shifts + 1 STG.128); the source is only ever read as aligned words.
 __device__ __forceinline__ void gcopy(uint8_t *dst, const uint8_t *src, uint32_t len) {
+#pragma unroll 1
     while (len && ((uint32_t)(uintptr_t)dst & 3u)) {
         *dst++ = *src++;
         len--;
@@ -57,12 +58,14 @@ __device__ __forceinline__ void gcopy(uint8_t *dst, const uint8_t *src, uint32_t
         uint32_t *dw = (uint32_t *)dst;
         uint32_t nwords = len >> 2;
         uint32_t lo = *sw++;
+#pragma unroll 1
         while (nwords && ((uint32_t)(uintptr_t)dw & 15u)) {
             const uint32_t hi = *sw++;
             *dw++ = __funnelshift_r(lo, hi, sh);
             lo = hi;
             nwords--;
         }
+#pragma unroll 1
         for (; nwords >= 4; nwords -= 4) {
             const uint32_t w1 = sw[0], w2 = sw[1], w3 = sw[2], w4 = sw[3];
             uint4 o;
@@ -75,6 +78,7 @@ __device__ __forceinline__ void gcopy(uint8_t *dst, const uint8_t *src, uint32_t
             sw += 4;
             dw += 4;
         }
+#pragma unroll 1
         while (nwords) {
             const uint32_t hi = *sw++;
             *dw++ = __funnelshift_r(lo, hi, sh);
@@ -86,10 +90,20 @@ __device__ __forceinline__ void gcopy(uint8_t *dst, const uint8_t *src, uint32_t
         src += done;
         len &= 3u;
     }
+#pragma unroll 1
     while (len) {
         *dst++ = *src++;
         len--;
     }
+}
+
+// min_baseq > 222 (never in practice): the byte-wise trim of sk_device.cuh, out of line.  Returns
+// kk | mode << 16 | fine << 24 (no reference parameters: they would pin the caller's variables to the stack).
+static __device__ __noinline__ uint32_t plan_trim_cold(const uint8_t *b, uint32_t L1, uint32_t L2, uint32_t L3, uint32_t L4, int minq) {
+    uint8_t mode = B_FAIL;
+    uint32_t kk = 0, body_len = 0;
+    const bool fine = plan_trim_body(b, L1, L2, L3, L4, minq, mode, kk, body_len);
+    return (kk & 0xFFFFu) | ((uint32_t)mode << 16) | (fine ? 1u << 24 : 0u);
 }
 
 // Look-back of the warp engine over p.tile_lines: inc[c] (u64: bit 63 | lines through tile c) and, behind
@@ -170,7 +184,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
     constexpr bool D1 = OP == OP_DEMUX1;
     static_assert(OP == OP_DEMUX1 || OP == OP_DEMUX2, "warp engine: demultiplex passes");
     constexpr int UPL = GeoW::UPL, LANE_BYTES = GeoW::LANE_BYTES, WIN = GeoW::WIN;
-    constexpr int MAXREC = GeoW::MAXREC, MAXLINES = GeoW::MAXLINES, NMW = (UPL + 1) / 2;
+    constexpr int MAXREC = GeoW::MAXREC, MAXLINES = GeoW::MAXLINES;
     constexpr uint32_t FULL = 0xffffffffu;
     using WL = WLayout;
 
@@ -248,6 +262,8 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
         // that is the last byte of the stream starts nothing.
         const uint32_t ls_hi = at_end ? (wlen ? wlen - 1 : 0) : wlen;
         const uint32_t o0 = (uint32_t)lane * LANE_BYTES;
+        // 25 conflict-free LDS.128 per lane; the newline maps stay in registers (13 words of 32 bytes each).
+        constexpr int NMW = (UPL + 1) / 2;
         uint32_t mw[NMW];
         uint32_t hib = 0;
 #pragma unroll
@@ -266,6 +282,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
         uint32_t cnt_all = 0;
 #pragma unroll
         for (int i = 0; i < NMW; i++) cnt_all += __popc(mw[i]);
+        const bool dense = false;
         const uint32_t cnt_own = (uint32_t)lane < tile_lanes ? cnt_all : 0u;
         uint32_t incl = (cnt_own << 16) | cnt_all;
 #pragma unroll
@@ -279,17 +296,29 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
         const uint32_t nls_own = (tot >> 16) + extra;
         if (lane == 0) wlb_publish(agg16, c, nls_own);
         {
+            // line starts: the first two newlines of every 32-byte word by predicated stores (a third one in
+            // 32 bytes is rare), no divergent loop in the common case
             uint32_t idx = ((incl & 0xFFFFu) - cnt_all) + extra;
             if (lane == 0 && extra) ls[0] = 0;
             uint32_t base = o0 + 1u;
 #pragma unroll
             for (int wi = 0; wi < NMW; wi++) {
                 uint32_t m = mw[wi];
-                while (m) {
-                    const uint32_t i = (uint32_t)__ffs((int)m) - 1u;
-                    m &= m - 1;
-                    if (idx < (uint32_t)MAXLINES) ls[idx] = (uint16_t)(base + i);
+                if (m) {
+                    if (idx < (uint32_t)MAXLINES) ls[idx] = (uint16_t)(base + (uint32_t)__ffs((int)m) - 1u);
                     idx++;
+                    m &= m - 1;
+                    if (m) {
+                        if (idx < (uint32_t)MAXLINES) ls[idx] = (uint16_t)(base + (uint32_t)__ffs((int)m) - 1u);
+                        idx++;
+                        m &= m - 1;
+#pragma unroll 1
+                        while (m) {
+                            if (idx < (uint32_t)MAXLINES) ls[idx] = (uint16_t)(base + (uint32_t)__ffs((int)m) - 1u);
+                            idx++;
+                            m &= m - 1;
+                        }
+                    }
                 }
                 base += 32u;
             }
@@ -301,21 +330,41 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
         __syncwarp();
 
         // ---- framing.  Record i is lines 4i..4i+3 of the stream (common.rs:106-112): the tile needs the
-        // global index g0 of its first line.  The counts it sums were published right after their tiles'
-        // scans, so this rarely waits.
-        const uint64_t g0 = wlb_consume(p.tile_lines, agg16, c, nls_own, lane);
-        const uint32_t j0 = (4u - (uint32_t)(g0 & 3u)) & 3u;
+        // global index g0 of its first line, i.e. the counts of every tile before it -- and the nearest of
+        // those are published only moments before this point is reached.  The framing is therefore guessed
+        // from the text (a line that starts with '@' whose second successor starts with '+'), the first
+        // round is planned on the guess, and the guess is checked against the look-back before the round
+        // writes anything; a wrong guess (malformed or adversarial text only) repeats the plan.
+        bool spec = false;
+        uint32_t j0 = 0;
+        uint64_t g0 = 0;
+        if (c != 0 && p.rec_limit == ~0ull && nls >= 6u && !dense) {
+            const uint32_t s0 = LB(0), s1 = LB(1), s2 = LB(2), s3 = LB(3), s4 = LB(4), s5 = LB(5);
+            const uint32_t b0 = win[s0], b1 = win[s1], b2 = win[s2], b3 = win[s3], b4 = win[s4], b5 = win[s5];
+            const bool k0 = b0 == '@' && b2 == '+', k1 = b1 == '@' && b3 == '+';
+            const bool k2 = b2 == '@' && b4 == '+', k3 = b3 == '@' && b5 == '+';
+            j0 = k0 ? 0u : k1 ? 1u : k2 ? 2u : 3u;
+            spec = (k0 || k1 || k2 || k3) && j0 < nls_own;
+        }
+        if (!spec) {
+            g0 = wlb_consume(p.tile_lines, agg16, c, nls_own, lane);
+            j0 = (4u - (uint32_t)(g0 & 3u)) & 3u;
+        }
 
         uint32_t nrec = 0;
         bool bail = false;
-        {
+        for (;;) {  // repeated only when the guess was wrong
             nrec = j0 < nls_own ? (nls_own - 1 - j0) / 4u + 1u : 0u;
-            {
+            if (!spec) {
                 const uint64_t first = (g0 + j0) >> 2;
                 if (first >= p.rec_limit) nrec = 0;
                 else if ((uint64_t)nrec > p.rec_limit - first) nrec = (uint32_t)(p.rec_limit - first);
             }
             bail = false;
+            if (dense) {
+                bail = true;
+                nrec = 0;
+            }
             if (nrec) {
                 uint32_t jend = j0 + nrec * 4u;
                 const bool eof_ok = at_end && p.final_batch;
@@ -334,7 +383,8 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 if (bail) nrec = 0;
             }
 
-            const uint64_t rec0 = (g0 + j0) >> 2;
+            bool wrong = false;
+            uint64_t rec0 = 0;
             for (uint32_t r0 = 0; r0 < nrec; r0 += 32u) {
                 // ---- plan: one lane per record, nothing is written
                 const uint32_t r = r0 + (uint32_t)lane;
@@ -348,9 +398,20 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                     bool fine;
                     mode = B_FAIL;
                     if (trim_q <= 222) {
+#ifdef SKW_TRIM8
                         fine = plan_trim_warp(win, ok, L1, L2, L3, L4, trim_q, mode, kk, body);
+#else
+                        fine = plan_trim_lane16(win, ok, L1, L2, L3, L4, trim_q, mode, kk, body);
+#endif
                     } else {
-                        fine = ok ? plan_trim_body(win, L1, L2, L3, L4, trim_q, mode, kk, body) : true;
+                        fine = true;
+                        if (ok) {
+                            const uint32_t pk = plan_trim_cold(win, L1, L2, L3, L4, trim_q);
+                            kk = pk & 0xFFFFu;
+                            mode = (uint8_t)(pk >> 16);
+                            fine = (pk >> 24) != 0u;
+                            body = mode == B_GARBAGE ? 6u : 2u * kk + 4u;
+                        }
                         __syncwarp();
                     }
                     if (!ok || !fine) mode = B_FAIL;
@@ -426,6 +487,18 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                     cut1 = c1h - L0;
                 }
 
+                // ---- the guess is verified against the line count before the first round writes
+                if (spec) {
+                    g0 = wlb_consume(p.tile_lines, agg16, c, nls_own, lane);
+                    spec = false;
+                    const uint32_t jt = (4u - (uint32_t)(g0 & 3u)) & 3u;
+                    if (jt != j0) {
+                        j0 = jt;
+                        wrong = true;
+                        break;
+                    }
+                }
+                rec0 = (g0 + j0) >> 2;
                 const uint64_t rec = rec0 + r;
 
                 // ---- outcome of every record: counters, failures, ambiguity events (:169-194)
@@ -652,6 +725,17 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 }
                 __syncwarp();
             }
+            if (wrong) continue;
+            if (spec) {  // no round ran (the tile was given up): the prefix is still owed to the successors
+                g0 = wlb_consume(p.tile_lines, agg16, c, nls_own, lane);
+                spec = false;
+                const uint32_t jt = (4u - (uint32_t)(g0 & 3u)) & 3u;
+                if (jt != j0) {  // also re-evaluates a tile given up under the wrong framing
+                    j0 = jt;
+                    continue;
+                }
+            }
+            break;
         }
         if (bail && lane == 0) atomicOr(&st->flags, F_NEED_GENERAL);
         if (p.out) {  // rows of the rounds that did not run
