@@ -347,12 +347,11 @@ __device__ __forceinline__ int min3i(int a, int b, int c) { return min(min(a, b)
 
 // fasta_trim_by_quality.rs:28-48 for one record per lane, sixteen quality bytes per step: every lane
 // walks its quality string down in aligned 16-byte blocks; the minimum key of a block gives the lowest
-// total and its position at once (:38), the block in which the running total first exceeds 0 (:37) is
-// looked into once after the loop (its totals before the break may still lower the minimum).  Must be
+// total and its position at once (:38); in the block in which the running total first exceeds 0 (:37)
+// only the totals before the break count.  Must be
 // called by all 32 lanes (`has` = this lane carries a record).  min_baseq <= 222.
 __device__ __forceinline__ bool plan_trim_lane16(const uint8_t *b, bool has, uint32_t L1, uint32_t L2, uint32_t L3, uint32_t L4,
                                                  int minq, uint8_t &mode, uint32_t &kk, uint32_t &body_len) {
-    const uint32_t NONE = 0xFFFFFFFFu;
     uint32_t k = has ? L4 - L3 : 0u;
 #pragma unroll 1
     while (k > 0 && is_ws(b[L3 + k - 1])) k--;  // qual.trim_end().len()  (:31)
@@ -360,7 +359,7 @@ __device__ __forceinline__ bool plan_trim_lane16(const uint8_t *b, bool has, uin
     const uint32_t E = L3 + k;
     const int sub = 33 + minq;
     int total = -50, lowest = -50;  // :28-29
-    uint32_t lowest_k = k, brk_a = NONE;
+    uint32_t lowest_k = k;
     uint32_t a = k ? ((E - 1u) & ~15u) : 0u;
     bool active = k > 0;
 #pragma unroll 1
@@ -370,8 +369,18 @@ __device__ __forceinline__ bool plan_trim_lane16(const uint8_t *b, bool has, uin
             blk16_keys(b, a, L3, E, sub, total, K);
             const int mx = max3i(max3i(max3i(K[0], K[1], K[2]), max3i(K[3], K[4], K[5]), max3i(K[6], K[7], K[8])),
                                  max3i(K[9], K[10], K[11]), max3i(max3i(K[12], K[13], K[14]), K[15], K[15]));
-            if (mx > 15) {  // the break is inside this block; `total` stays the total before the block
-                brk_a = a;
+            if (mx > 15) {  // the break (:37) is inside this block: its totals up to the break may still lower the minimum
+                bool ok = true;
+                int best = 0x7FFFFFFF;
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    ok = ok && K[i] <= 15;  // totals after the break are never looked at
+                    best = (ok && K[i] < best) ? K[i] : best;
+                }
+                if (best != 0x7FFFFFFF && (best >> 4) < lowest) {
+                    lowest = best >> 4;
+                    lowest_k = a + 15u - (uint32_t)(best & 15) - L3;
+                }
                 active = false;
             } else {
                 const int mn = min3i(min3i(min3i(K[0], K[1], K[2]), min3i(K[3], K[4], K[5]), min3i(K[6], K[7], K[8])),
@@ -384,21 +393,6 @@ __device__ __forceinline__ bool plan_trim_lane16(const uint8_t *b, bool has, uin
                 if (a <= L3) active = false;
                 else a -= 16;
             }
-        }
-    }
-    if (brk_a != NONE) {  // totals of the break block up to the break
-        int K[16];
-        blk16_keys(b, brk_a, L3, E, sub, total, K);
-        bool ok = true;
-        int best = 0x7FFFFFFF;
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-            ok = ok && K[i] <= 15;  // totals after the break are never looked at
-            best = (ok && K[i] < best) ? K[i] : best;
-        }
-        if (best != 0x7FFFFFFF && (best >> 4) < lowest) {
-            lowest = best >> 4;
-            lowest_k = brk_a + 15u - (uint32_t)(best & 15) - L3;
         }
     }
     __syncwarp();

@@ -31,6 +31,10 @@ extern __shared__ __align__(128) unsigned char sk_smem[];
 #include "sk_device.cuh"
 #include "sk_lean.cuh"
 
+#ifndef SKW_LOCKSTEP
+#define SKW_LOCKSTEP 1  // 0: every warp takes its own tickets
+#endif
+
 namespace sk {
 
 struct WLayout {
@@ -202,13 +206,18 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
     DevStats *st = p.stats;
 
     if (lane == 0) mbar_init(mbar, 1);
+#pragma unroll 1
     for (uint32_t i = tid; i < 256; i += GeoW::NT) sh_lut[i] = p.sheet.lut[i];
+#pragma unroll 1
     for (uint32_t i = tid; i < S; i += GeoW::NT)
         sh_ulen[i] = (uint8_t)(p.sheet.wide ? __popcll(((const unsigned long long *)p.sheet.umask)[i]) : __popc(p.sheet.umask[i]));
     if (D1) {
+#pragma unroll 1
         for (uint32_t i = tid; i < hcls_words; i += GeoW::NT) hcls[i] = p.sheet.hidx.cls[i];
-        if (cc_smem)
+        if (cc_smem) {
+#pragma unroll 1
             for (uint32_t i = tid; i < S; i += GeoW::NT) ccount[i] = 0;
+        }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -219,15 +228,39 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
     const int trim_q = p.fused_trim;
     const uint32_t Lb = p.sheet.L;
     uint16_t *agg16 = wlb_agg(p.tile_lines, p.n_chunks);
+    const unsigned long long r1_nrec = D1 ? 0ull : p.r1_stats->n_records;  // mate 2: records of the mate-1 pass
     uint32_t parity = 0;
     uint32_t my_total = 0, my_ident = 0;   // DEMUX1 counters of this lane's records
     unsigned long long my_out = 0;         // lane 0: payload bytes of this warp's tiles
 #define LB(x) ((uint32_t)ls[(x)])
 
     uint32_t c = 0;
+#if SKW_LOCKSTEP
+    // The warps of a CTA take eight consecutive tiles at a time and start them together: they then run
+    // the same code at about the same time, which the SM's instruction cache needs (the kernel is larger
+    // than that cache, and sixteen warps spread over it saturate the GPC-level instruction cache).
+    volatile uint32_t *cta_ticket = (volatile uint32_t *)(sk_smem + WL::misc + 8);  // two slots in warp 0's misc area
+    uint32_t cta_next = 0, flipk = 0;
+    bool cta_have = false;
+    for (;;) {
+        if (tid == 0) cta_ticket[flipk] = cta_have ? cta_next : atomicAdd(&st->ticket, (uint32_t)GeoW::WARPS);
+        cta_have = false;
+        __syncthreads();
+        const uint32_t cb = cta_ticket[flipk];
+        flipk ^= 1u;
+        if (cb >= p.n_chunks) break;
+        c = cb + (uint32_t)warp;
+        if (c >= p.n_chunks) {
+#if SKW_LOCKSTEP >= 2
+            __syncthreads();  // the mid-tile meeting point below
+#endif
+            continue;
+        }
+#else
     if (lane == 0) c = atomicAdd(&st->ticket, 1u);
     c = __shfl_sync(FULL, c, 0);
     while (c < p.n_chunks) {
+#endif
         const uint64_t c0 = (uint64_t)c * TILE;
         uint64_t wend = c0 + (uint64_t)WIN;
         if (wend > p.n) wend = p.n;
@@ -327,7 +360,11 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 if (k < (uint32_t)MAXLINES + 8u) ls[k] = (uint16_t)wlen;
             }
         }
+#if SKW_LOCKSTEP >= 2
+        __syncthreads();  // second meeting point of the CTA's warps (plain __syncwarp otherwise)
+#else
         __syncwarp();
+#endif
 
         // ---- framing.  Record i is lines 4i..4i+3 of the stream (common.rs:106-112): the tile needs the
         // global index g0 of its first line, i.e. the counts of every tile before it -- and the nearest of
@@ -351,8 +388,8 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
             j0 = (4u - (uint32_t)(g0 & 3u)) & 3u;
         }
 
-        uint32_t nrec = 0;
-        bool bail = false;
+        uint32_t nrec = 0, c_next = 0;
+        bool bail = false, have_next = false;
         for (;;) {  // repeated only when the guess was wrong
             nrec = j0 < nls_own ? (nls_own - 1 - j0) / 4u + 1u : 0u;
             if (!spec) {
@@ -417,6 +454,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                     if (!ok || !fine) mode = B_FAIL;
                 }
                 int sample = -1;
+                unsigned long long um = 0;  // positions where the sample's sheet barcode has 'U'
                 uint32_t alen = 0, blen = 0, cut0 = 0, cut1 = 0, taglen = 0xFFu;
                 if (D1) {
                     // fasta_demultiplex.rs:117-194: validate, locate the barcode, match, decide.  Outcome:
@@ -466,6 +504,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                     }
                     __syncwarp();
                     if (sample >= 0) {
+                        um = p.sheet.wide ? ((const unsigned long long *)p.sheet.umask)[sample] : (unsigned long long)p.sheet.umask[sample];
                         header_pieces(win, L0, L1, L0 + cut0, L0 + cut1, alen, blen);  // drain (:145) + trim_end (:206)
                         const uint32_t ul = sh_ulen[sample];
                         taglen = ul ? 5 + ul : 0;  // " UMI:" + umi (:207)
@@ -501,6 +540,55 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 rec0 = (g0 + j0) >> 2;
                 const uint64_t rec = rec0 + r;
 
+                // ---- loads whose results are needed further down go out first: mate 2 reads the pair's
+                // sample and UMI from mate 1's tables; the last round takes the warp's next ticket
+                uint8_t *gu = p.umi + rec * p.sheet.Umax;
+                int a16 = -1;
+                uint2 guv = make_uint2(0u, 0u);
+                if (!D1 && has && p.out && rec < r1_nrec) {
+                    a16 = (int)p.assign[rec];
+                    if (p.sheet.Umax == 8u) guv = *(const uint2 *)gu;
+                }
+                if (r0 + 32u >= nrec && lane == 0) {
+#if SKW_LOCKSTEP
+                    if (warp == 0) {
+                        cta_next = atomicAdd(&st->ticket, (uint32_t)GeoW::WARPS);
+                        cta_have = true;
+                    }
+#else
+                    c_next = atomicAdd(&st->ticket, 1u);
+                    have_next = true;
+#endif
+                }
+
+                // ---- body: "\n+\n" and "\n" are patched in behind the kept bases / qualities (:47), whether or
+                // not the record is written in the end (the window is private to the tile)
+                uint32_t run1 = 0, run2 = 0;
+                bool bslow = false;
+                if (has && p.out) {
+                    if (mode == B_VERBATIM) {
+                        run1 = body;
+                    } else if (mode == B_TRIM) {
+                        if (L1 + kk + 3u <= L3) {
+                            uint8_t *d = win + L1 + kk;
+                            d[0] = '\n'; d[1] = '+'; d[2] = '\n';
+                            win[L3 + kk] = '\n';
+                            run1 = kk + 3u;
+                            run2 = kk + 1u;
+                        } else {
+                            bslow = true;
+                        }
+                    } else if (mode == B_GARBAGE) {  // :44-45
+                        if (L1 + 6u <= L4) {
+                            uint8_t *d = win + L1;
+                            d[0] = 'N'; d[1] = '\n'; d[2] = '+'; d[3] = '\n'; d[4] = '!'; d[5] = '\n';
+                            run1 = 6u;
+                        } else {
+                            bslow = true;
+                        }
+                    }
+                }
+
                 // ---- outcome of every record: counters, failures, ambiguity events (:169-194)
                 if (has) {
                     if (D1) {
@@ -526,7 +614,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                             }
                         }
                     } else {
-                        sample = (p.out && rec < p.r1_stats->n_records) ? (int)p.assign[rec] : -1;
+                        sample = a16;
                         if (sample >= 0) {
                             const uint32_t ul = sh_ulen[sample];
                             taglen = ul ? 5 + ul : 0;
@@ -566,132 +654,112 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 const uint32_t my_rank = __popc(emit_mask & ((1u << lane) - 1u));
                 const uint32_t n_emit = __popc(emit_mask);
                 unsigned long long rbase = 0;
-                if (lane == 0 && p.out && round_out) {
+                if (lane == 0 && p.out && round_out) {  // the reply is awaited after the header patches
                     rbase = atomicAdd(&st->out_cursor, (unsigned long long)((round_out + 15u) & ~15u));
                     my_out += round_out;
                 }
+                const bool emit = outlen != 0;
+                const uint32_t ul = taglen ? taglen - 5u : 0u;
+
+                // ---- header: " UMI:x\n" goes over the deleted " BC:x" when the header ends with it
+                const bool hpatch = emit && blen == 0 && alen + taglen + 1u <= L1 - L0;
+                uint32_t hrun = 0;
+                uint32_t ulo = 0, uhi = 0;  // the UMI in registers (up to eight characters)
+                bool ureg = false;
+                if (D1) {
+                    if (has && sample >= 0 && p.sheet.Umax) {
+                        // UMI = observed chars where the sheet barcode has 'U' (:200-203), parked in the side
+                        // table for mate 2 (also on a dry run); read before the patch overwrites the barcode
+                        const uint8_t *ob = win + L0 + cut0 + 4;
+                        unsigned long long m = um;
+                        const uint32_t ulen = sh_ulen[sample];
+                        const uint32_t u0 = (uint32_t)__ffsll((long long)m) - 1u;
+                        if (ulen && ulen <= 8u && (m >> u0) == ((1ull << ulen) - 1ull)) {  // one run of U (the usual sheet)
+                            const uint8_t *us = ob + u0;
+                            const uint32_t sh = ((uint32_t)(uintptr_t)us & 3u) * 8u;
+                            const uint32_t *uw = (const uint32_t *)((uintptr_t)us & ~(uintptr_t)3);
+                            const uint32_t w0 = uw[0], w1 = uw[1], w2 = uw[2];
+                            ulo = __funnelshift_r(w0, w1, sh);
+                            uhi = __funnelshift_r(w1, w2, sh);
+                            ureg = true;
+                            if (p.sheet.Umax == 8u && ulen == 8u) {
+                                *(uint2 *)gu = make_uint2(ulo, uhi);
+                            } else {
+#pragma unroll 1
+                                for (uint32_t t = 0; t < ulen; t++)
+                                    gu[t] = (uint8_t)(t < 4u ? ulo >> (8u * t) : uhi >> (8u * (t - 4u)));
+                            }
+                        } else {
+                            uint32_t t = 0;
+#pragma unroll 1
+                            while (m) {
+                                const uint32_t q = (uint32_t)__ffsll((long long)m) - 1u;
+                                m &= m - 1;
+                                gu[t++] = ob[q];
+                            }
+                        }
+                    }
+                } else if (p.sheet.Umax == 8u) {
+                    ulo = guv.x;
+                    uhi = guv.y;
+                    ureg = true;
+                }
+                __syncwarp();
+#define UMI_BYTE(t) (ureg ? (uint8_t)((t) < 4u ? ulo >> (8u * (t)) : uhi >> (8u * ((t) - 4u))) : gu[(t)])
+                if (hpatch) {
+                    uint8_t *d = win + L0 + alen;
+                    if (taglen) {
+#pragma unroll 1
+                        for (uint32_t t = 0; t < ul; t++) d[5 + t] = UMI_BYTE(t);
+                        d[0] = ' '; d[1] = 'U'; d[2] = 'M'; d[3] = 'I'; d[4] = ':';
+                    }
+                    d[taglen] = '\n';
+                    hrun = alen + taglen + 1u;
+                }
+                __syncwarp();
+
+                // ---- emit
                 rbase = __shfl_sync(FULL, rbase, 0);
                 bool writable = p.out != nullptr && round_out > 0;
                 if (writable && rbase + ((round_out + 15u) & ~15u) > p.out_cap) {
                     if (lane == 0) report_err(st, rec0 + r0, K_OUT_OVERFLOW);
                     writable = false;
                 }
-
-                // ---- emit
-                uint8_t *gu = p.umi + rec * p.sheet.Umax;
                 if (writable) {
                     uint8_t *gd = p.out + rbase + my_off;
-                    const bool emit = outlen != 0;
-                    const uint32_t ul = taglen ? taglen - 5u : 0u;
-                    // header: " UMI:x\n" goes over the deleted " BC:x" when the header ends with it
-                    const bool hpatch = emit && blen == 0 && alen + taglen + 1u <= L1 - L0;
-                    uint32_t hrun = 0;
-                    uint32_t ulo = 0, uhi = 0;  // the UMI in registers (up to eight characters)
-                    bool ureg = false;
-                    if (emit && ul) {
-                        if (D1) {
-                            // UMI = observed chars where the sheet barcode has 'U' (:200-203), also parked in
-                            // the side table for mate 2; read before the patch below overwrites the barcode
-                            const uint8_t *ob = win + L0 + cut0 + 4;
-                            unsigned long long m = p.sheet.wide ? ((const unsigned long long *)p.sheet.umask)[sample]
-                                                                : (unsigned long long)p.sheet.umask[sample];
-                            const uint32_t u0 = (uint32_t)__ffsll((long long)m) - 1u;
-                            if (ul <= 8u && (m >> u0) == ((1ull << ul) - 1ull)) {  // one run of U (the usual sheet)
-                                const uint8_t *us = ob + u0;
-                                const uint32_t sh = ((uint32_t)(uintptr_t)us & 3u) * 8u;
-                                const uint32_t *uw = (const uint32_t *)((uintptr_t)us & ~(uintptr_t)3);
-                                const uint32_t w0 = uw[0], w1 = uw[1], w2 = uw[2];
-                                ulo = __funnelshift_r(w0, w1, sh);
-                                uhi = __funnelshift_r(w1, w2, sh);
-                                ureg = true;
-                                if (p.sheet.Umax == 8u && ul == 8u) {
-                                    *(uint2 *)gu = make_uint2(ulo, uhi);
-                                } else {
-                                    for (uint32_t t = 0; t < ul; t++)
-                                        gu[t] = (uint8_t)(t < 4u ? ulo >> (8u * t) : uhi >> (8u * (t - 4u)));
-                                }
-                            } else {
-                                uint32_t t = 0;
-                                while (m) {
-                                    const uint32_t q = (uint32_t)__ffsll((long long)m) - 1u;
-                                    m &= m - 1;
-                                    gu[t++] = ob[q];
-                                }
-                            }
-                        } else if (p.sheet.Umax == 8u) {
-                            const uint2 v = *(const uint2 *)gu;
-                            ulo = v.x;
-                            uhi = v.y;
-                            ureg = true;
-                        }
-                    }
-                    __syncwarp();
-#define UMI_BYTE(t) (ureg ? (uint8_t)((t) < 4u ? ulo >> (8u * (t)) : uhi >> (8u * ((t) - 4u))) : gu[(t)])
-                    if (hpatch) {
-                        uint8_t *d = win + L0 + alen;
-                        if (taglen) {
-                            for (uint32_t t = 0; t < ul; t++) d[5 + t] = UMI_BYTE(t);
-                            d[0] = ' '; d[1] = 'U'; d[2] = 'M'; d[3] = 'I'; d[4] = ':';
-                        }
-                        d[taglen] = '\n';
-                        hrun = alen + taglen + 1u;
-                    }
-                    __syncwarp();
                     if (emit && !hpatch) {  // rare: a header piece after the cut, or no room for the tag
                         uint8_t *d = gd;
+#pragma unroll 1
                         for (uint32_t i = 0; i < alen; i++) *d++ = win[L0 + i];
+#pragma unroll 1
                         for (uint32_t i = 0; i < blen; i++) *d++ = win[L0 + cut1 + i];
                         if (taglen) {
                             d[0] = ' '; d[1] = 'U'; d[2] = 'M'; d[3] = 'I'; d[4] = ':';
+#pragma unroll 1
                             for (uint32_t t = 0; t < ul; t++) d[5 + t] = UMI_BYTE(t);
                             d += taglen;
                         }
                         *d = '\n';
                     }
                     __syncwarp();
-                    gd += alen + blen + taglen + 1u;
-                    // body: "\n+\n" and "\n" are patched in behind the kept bases / qualities (:47)
-                    uint32_t run1 = 0, run2 = 0;
-                    bool bslow = false;
-                    if (emit) {
-                        if (mode == B_VERBATIM) {
-                            run1 = body;
-                        } else if (mode == B_TRIM) {
-                            if (L1 + kk + 3u <= L3) {
-                                uint8_t *d = win + L1 + kk;
-                                d[0] = '\n'; d[1] = '+'; d[2] = '\n';
-                                win[L3 + kk] = '\n';
-                                run1 = kk + 3u;
-                                run2 = kk + 1u;
-                            } else {
-                                bslow = true;
-                            }
-                        } else if (mode == B_GARBAGE) {  // :44-45
-                            if (L1 + 6u <= L4) {
-                                uint8_t *d = win + L1;
-                                d[0] = 'N'; d[1] = '\n'; d[2] = '+'; d[3] = '\n'; d[4] = '!'; d[5] = '\n';
-                                run1 = 6u;
-                            } else {
-                                bslow = true;
-                            }
-                        }
-                    }
-                    __syncwarp();
+                    const uint32_t hlen = alen + blen + taglen + 1u;
                     // the record's runs: header, bases (+ "\n+\n"), qualities (+ "\n")
 #pragma unroll 1
                     for (int q = 0; q < 3; q++) {
                         const uint32_t so = q == 0 ? L0 : q == 1 ? L1 : L3;
-                        const uint32_t ln = q == 0 ? hrun : q == 1 ? run1 : run2;
-                        uint8_t *dd = q == 0 ? gd - (alen + blen + taglen + 1u) : q == 1 ? gd : gd + run1;
+                        const uint32_t ln = !emit ? 0u : q == 0 ? hrun : q == 1 ? run1 : run2;
+                        uint8_t *dd = q == 0 ? gd : q == 1 ? gd + hlen : gd + hlen + run1;
                         gcopy(dd, win + so, ln);
                         __syncwarp();
                     }
-                    if (bslow) {  // rare: a '+' line too short to hold the patch
-                        uint8_t *d = gd;
+                    if (emit && bslow) {  // rare: a '+' line too short to hold the patch
+                        uint8_t *d = gd + hlen;
                         if (mode == B_TRIM) {
+#pragma unroll 1
                             for (uint32_t i = 0; i < kk; i++) *d++ = win[L1 + i];
                             d[0] = '\n'; d[1] = '+'; d[2] = '\n';
                             d += 3;
+#pragma unroll 1
                             for (uint32_t i = 0; i < kk; i++) *d++ = win[L3 + i];
                             *d = '\n';
                         } else {
@@ -703,17 +771,6 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                         g.sample = (uint16_t)sample;
                         g.len = (uint16_t)outlen;
                         p.groups[rec0 + r0 + my_rank] = g;
-                    }
-                } else if (D1 && p.sheet.Umax && has && sample >= 0) {
-                    // nothing is written here (dry run / overflow): mate 2 still needs the UMI side table
-                    const uint8_t *ob = win + L0 + cut0 + 4;
-                    unsigned long long m = p.sheet.wide ? ((const unsigned long long *)p.sheet.umask)[sample]
-                                                        : (unsigned long long)p.sheet.umask[sample];
-                    uint32_t t = 0;
-                    while (m) {
-                        const uint32_t q = (uint32_t)__ffsll((long long)m) - 1u;
-                        m &= m - 1;
-                        gu[t++] = ob[q];
                     }
                 }
                 if (lane == 0 && p.out) {
@@ -755,10 +812,15 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 atomicMax(&st->consumed, (unsigned long long)(c0 + LB(j0 + nrec * 4u)));
             }
         }
-        // the next ticket is taken only now: a tile's count must appear soon after its ticket, its
-        // successors wait for it
-        if (lane == 0) c = atomicAdd(&st->ticket, 1u);
-        c = __shfl_sync(FULL, c, 0);
+        // The next ticket is taken during the last round (or now): a tile's count must appear soon after
+        // its ticket, its successors wait for it.
+#if !SKW_LOCKSTEP
+        if (lane == 0 && !have_next) c_next = atomicAdd(&st->ticket, 1u);
+        c = __shfl_sync(FULL, c_next, 0);
+#else
+        (void)c_next;
+        (void)have_next;
+#endif
     }
 #undef LB
 #undef UMI_BYTE
@@ -769,6 +831,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
         if (lane == 0 && wi) atomicAdd(&p.counts[S + 1], (unsigned long long)wi);
         if (cc_smem) {
             __syncthreads();
+#pragma unroll 1
             for (uint32_t s = tid; s < S; s += GeoW::NT)
                 if (ccount[s]) atomicAdd(&p.counts[s], (unsigned long long)ccount[s]);
         }
