@@ -47,58 +47,88 @@ struct WLayout {
 };
 static_assert(WLayout::per_warp % 16 == 0, "warp areas are 16-byte aligned");
 
-// Lane-serial copy of `len` bytes from shared memory to global memory, any alignment on either side:
-// bytes up to a word of the destination, words up to a 16-byte unit, then 16 bytes per step
-// (4 LDS.32 + 4 funnel shifts + 1 STG.128); the source is only ever read as aligned words.
+// Up to eight bytes of shared memory from any byte offset, as aligned words and funnel shifts.
+__device__ __forceinline__ uint32_t lds_un32(const uint8_t *src) {
+    const uint32_t *w = (const uint32_t *)((uintptr_t)src & ~(uintptr_t)3);
+    return __funnelshift_r(w[0], w[1], ((uint32_t)(uintptr_t)src & 3u) * 8u);
+}
+__device__ __forceinline__ uint2 lds_un64(const uint8_t *src) {
+    const uint32_t *w = (const uint32_t *)((uintptr_t)src & ~(uintptr_t)3);
+    const uint32_t sh = ((uint32_t)(uintptr_t)src & 3u) * 8u;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+}
+// Lane-serial copy of `len` bytes from shared memory to global memory, any alignment on either side.
+// The destination is brought to a 16-byte boundary by at most one store of each size 1, 2, 4, 8 (no
+// loops: the lanes of a warp copy runs of different alignment), then 16 bytes per step (4 LDS.32 + 4
+// funnel shifts + 1 STG.128), then at most one store of each size 8, 4, 2, 1.  The source is only ever
+// read as aligned words (up to seven bytes past its end).
 __device__ __forceinline__ void gcopy(uint8_t *dst, const uint8_t *src, uint32_t len) {
-#pragma unroll 1
-    while (len && ((uint32_t)(uintptr_t)dst & 3u)) {
-        *dst++ = *src++;
-        len--;
+    const uint32_t a = (uint32_t)(uintptr_t)dst;
+    if ((a & 1u) && len >= 1u) {
+        *dst = *src;
+        dst += 1, src += 1, len -= 1;
     }
-    if (len >= 4) {
+    if (((uint32_t)(uintptr_t)dst & 2u) && len >= 2u) {
+        *(uint16_t *)dst = (uint16_t)lds_un32(src);
+        dst += 2, src += 2, len -= 2;
+    }
+    if (((uint32_t)(uintptr_t)dst & 4u) && len >= 4u) {
+        *(uint32_t *)dst = lds_un32(src);
+        dst += 4, src += 4, len -= 4;
+    }
+    if (((uint32_t)(uintptr_t)dst & 8u) && len >= 8u) {
+        *(uint2 *)dst = lds_un64(src);
+        dst += 8, src += 8, len -= 8;
+    }
+    if (len >= 16u) {  // dst is 16-byte aligned here
         const uint32_t sh = ((uint32_t)(uintptr_t)src & 3u) * 8u;
         const uint32_t *sw = (const uint32_t *)((uintptr_t)src & ~(uintptr_t)3);
-        uint32_t *dw = (uint32_t *)dst;
-        uint32_t nwords = len >> 2;
-        uint32_t lo = *sw++;
+        uint4 *dq = (uint4 *)dst;
+        uint32_t lo = *sw;
+        const uint32_t n16 = len >> 4;
 #pragma unroll 1
-        while (nwords && ((uint32_t)(uintptr_t)dw & 15u)) {
-            const uint32_t hi = *sw++;
-            *dw++ = __funnelshift_r(lo, hi, sh);
-            lo = hi;
-            nwords--;
-        }
-#pragma unroll 1
-        for (; nwords >= 4; nwords -= 4) {
-            const uint32_t w1 = sw[0], w2 = sw[1], w3 = sw[2], w4 = sw[3];
+        for (uint32_t i = 0; i < n16; i++) {
+            const uint32_t w1 = sw[1], w2 = sw[2], w3 = sw[3], w4 = sw[4];
             uint4 o;
             o.x = __funnelshift_r(lo, w1, sh);
             o.y = __funnelshift_r(w1, w2, sh);
             o.z = __funnelshift_r(w2, w3, sh);
             o.w = __funnelshift_r(w3, w4, sh);
-            *(uint4 *)dw = o;
+            *dq++ = o;
             lo = w4;
             sw += 4;
-            dw += 4;
         }
+        dst += n16 * 16u, src += n16 * 16u, len &= 15u;
+    }
+    if (len & 8u) {
+        if (((uint32_t)(uintptr_t)dst & 7u) == 0u) {
+            *(uint2 *)dst = lds_un64(src);
+        } else {  // (a run shorter than its head alignment)
 #pragma unroll 1
-        while (nwords) {
-            const uint32_t hi = *sw++;
-            *dw++ = __funnelshift_r(lo, hi, sh);
-            lo = hi;
-            nwords--;
+            for (int i = 0; i < 8; i++) dst[i] = src[i];
         }
-        const uint32_t done = len & ~3u;
-        dst += done;
-        src += done;
-        len &= 3u;
+        dst += 8, src += 8;
     }
+    if (len & 4u) {
+        if (((uint32_t)(uintptr_t)dst & 3u) == 0u) {
+            *(uint32_t *)dst = lds_un32(src);
+        } else {
 #pragma unroll 1
-    while (len) {
-        *dst++ = *src++;
-        len--;
+            for (int i = 0; i < 4; i++) dst[i] = src[i];
+        }
+        dst += 4, src += 4;
     }
+    if (len & 2u) {
+        if (((uint32_t)(uintptr_t)dst & 1u) == 0u) {
+            *(uint16_t *)dst = (uint16_t)lds_un32(src);
+        } else {
+            dst[0] = src[0];
+            dst[1] = src[1];
+        }
+        dst += 2, src += 2;
+    }
+    if (len & 1u) *dst = *src;
 }
 
 // min_baseq > 222 (never in practice): the byte-wise trim of sk_device.cuh, out of line.  Returns
