@@ -265,8 +265,8 @@ def main():
         step()
     res = eng.wait()
     assert res.status == 0 and res.n_records == P, (res.status, res.n_records)
-    # sk_result.reserved: bit0 = the lean engine (sk_fast.cu) ran, bit1 = it was re-run on the general engine
-    assert res.reserved == 1, "bench workload must run on the lean engine without a re-run (got %d)" % res.reserved
+    # sk_result.reserved: bit0 = the warp / lean engine ran, bit1 = it was re-run on the general engine
+    assert res.reserved == 1, "bench workload must run on the warp engine without a re-run (got %d)" % res.reserved
     pairs_done = res.n_records
 
     sampler = ClockSampler(local_rank)
@@ -309,8 +309,11 @@ def main():
     dom = 0 if pass_ms[0] >= pass_ms[1] else 1
     peak, peak_src = peaks()
     achieved = bytes_pass[dom] / (pass_ms[dom] * 1e-3) / 1e9
-    geo = "GeoS" if os.environ.get("SK_FAST_GEO") == "0" else "GeoM"
-    kname = lambda k: "sk_fast_kernel<%s, OP_DEMUX%d>" % (geo, k + 1)
+    if os.environ.get("SK_NO_WARP", "0") not in ("", "0"):  # the lean engine instead of the warp engine
+        geo = "GeoS" if os.environ.get("SK_FAST_GEO") == "0" else "GeoM"
+        kname = lambda k: "sk_fast_kernel<%s, OP_DEMUX%d>" % (geo, k + 1)
+    else:
+        kname = lambda k: "sk_warp_kernel<OP_DEMUX%d>" % (k + 1)
     # DRAM traffic of the dominant kernel from the committed ncu capture (dram__bytes_read + write, 1 M pairs
     # per launch), scaled to this launch's pairs; null when the summary is missing
     traffic = None

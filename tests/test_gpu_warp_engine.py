@@ -1,0 +1,153 @@
+"""Parity tests for the warp engine (seqkit_b200/csrc/sk_warp.cu, the default path of header-route
+demultiplex): every branch the engine takes for unusual records -- header pieces after the cut, no room
+for the UMI tag, '+' lines too short for the in-place patch, tiles of several rounds, tiles it gives up --
+must produce the oracle's bytes (fasta_demultiplex.rs:117-249, fasta_trim_by_quality.rs:28-48)."""
+import os
+import random
+
+import pytest
+
+import fuzzgen as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import pyoracle
+    return pyoracle
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from seqkit_b200 import Engine
+    e = Engine(max_stream_bytes=48 << 20, max_records=1 << 18, max_samples=512)
+    yield e
+    e.close()
+
+
+def _cmp(a, b, ctx=None):
+    assert a["exit_code"] == b["exit_code"], ctx
+    if a["exit_code"] != 101:
+        assert a["stderr"] == b["stderr"], ctx
+    assert a["files"] == b["files"], ctx
+    if a["exit_code"] == 0:
+        assert a["counts"] == b["counts"] and a["total"] == b["total"] and a["identified"] == b["identified"], ctx
+
+
+def _both(eng, O, sheet, r1, r2, ctx, want_engine=1):
+    """plain and fused-trim demultiplex of (r1, r2) against the oracle; want_engine = sk_result.reserved"""
+    _cmp(eng.demultiplex(sheet, r1, r2), O.demultiplex(sheet, r1, r2), (ctx, "plain"))
+    if want_engine is not None:
+        assert eng.last_result.reserved == want_engine, (ctx, eng.last_result.reserved)
+    t1 = O.trim_by_quality(r1, 20)
+    t2 = O.trim_by_quality(r2, 20) if r2 is not None else None
+    if t1[0] == 0 and (t2 is None or t2[0] == 0):
+        _cmp(eng.demultiplex(sheet, r1, r2, fused_trim=20), O.demultiplex(sheet, t1[1], None if t2 is None else t2[1]),
+             (ctx, "fused"))
+        if want_engine is not None:
+            assert eng.last_result.reserved == want_engine, (ctx, eng.last_result.reserved)
+
+
+def _reads(seed, n, bcs, read_len=(100, 160), header_tail=(b"",), plus=(b"+",), qual_style="decay", umi_fill=b"ACGT"):
+    """n records whose headers carry ' BC:<sheet barcode with U filled>' followed by one of header_tail"""
+    rng = random.Random(seed)
+    r1, r2 = [], []
+    for i in range(n):
+        L = rng.randrange(read_len[0], read_len[1] + 1)
+        bc = bytes(rng.choice(umi_fill) if ch in b"UN" else ch for ch in rng.choice(bcs))
+        if rng.random() < 0.05:
+            bc = bytes(rng.choice(b"ACGT") for _ in bc)
+        tail = rng.choice(header_tail)
+        for mate, dst in ((1, r1), (2, r2)):
+            hdr = b"@SIM:%d:%d %d:N:0 BC:%s%s" % (seed, i, mate, bc, tail)
+            dst.append(hdr + b"\n" + G.rand_seq(rng, L) + b"\n" + rng.choice(plus) + b"\n" + G.rand_qual(rng, L, qual_style) + b"\n")
+    return b"".join(r1), b"".join(r2)
+
+
+def test_regular_tiles_stay_on_the_warp_engine(eng, O):
+    sheet, bcs = G.make_sheet(21, 48, 8, umi=6)
+    r1, r2 = _reads(1, 9000, bcs)
+    _both(eng, O, sheet, r1, r2, "regular")
+    _both(eng, O, sheet, r1, None, "single-end")
+
+
+def test_header_piece_after_the_barcode(eng, O):
+    """' BC:x' in the middle of the header: the kept header is two pieces (fasta_demultiplex.rs:145), which
+    the in-place patch cannot express -- the record takes the byte-wise header path."""
+    sheet, bcs = G.make_sheet(22, 24, 8, umi=4)
+    r1, r2 = _reads(2, 6000, bcs, header_tail=(b"", b" extra", b" x y z", b"\t", b"  "))
+    _both(eng, O, sheet, r1, r2, "mid-header")
+
+
+def test_umi_shapes(eng, O):
+    """A sheet of wildcards only (' UMI:' + L characters is one byte longer than the deleted ' BC:' + L; the
+    pigeonhole index cannot represent it, so this one runs on the general engine), a UMI longer than two
+    registers, and U positions that are not one run."""
+    sheet = b"all\tUUUUUUUU\n"
+    r1, r2 = _reads(3, 5000, [b"UUUUUUUU"])
+    _both(eng, O, sheet, r1, r2, "all-U", want_engine=None)
+    sheet2 = b"a\tACUUUUUUUUUU\nb\tTGUUUUUUUUUU\n"  # ten U: the UMI does not fit two registers
+    r1, r2 = _reads(4, 5000, [b"ACUUUUUUUUUU", b"TGUUUUUUUUUU"])
+    _both(eng, O, sheet2, r1, r2, "ten-U")
+    sheet3 = b"a\tAUCUGUTU\nb\tTUGUCUAU\n"  # U positions that are not one run
+    r1, r2 = _reads(5, 5000, [b"AUCUGUTU", b"TUGUCUAU"])
+    _both(eng, O, sheet3, r1, r2, "scattered-U")
+
+
+def test_plus_lines_and_tiny_records(eng, O):
+    """'+' lines of every shape (bare, with text, empty) and records too short for the patched literals."""
+    sheet, bcs = G.make_sheet(23, 16, 6, umi=3)
+    r1, r2 = _reads(6, 7000, bcs, read_len=(40, 120), plus=(b"+", b"+SIM", b"", b"+ "), qual_style="mix")
+    _both(eng, O, sheet, r1, r2, "plus-shapes")
+    # mostly ordinary records with tiny ones in between (a tile of tiny records only is too dense, below)
+    rng = random.Random(70)
+    a1, a2 = _reads(7, 3000, bcs, read_len=(0, 6), plus=(b"+", b""), qual_style="bad")
+    b1, b2 = _reads(71, 3000, bcs, read_len=(120, 150), plus=(b"+", b""), qual_style="mix")
+    split = lambda d: [b"\n".join(x) + b"\n" for x in zip(*[iter(d.split(b"\n")[:-1])] * 4)]
+    mix = [(x, y) for x, y in zip(split(a1), split(a2))] + [(x, y) for x, y in zip(split(b1), split(b2))] * 3
+    rng.shuffle(mix)
+    _both(eng, O, sheet, b"".join(x for x, _ in mix), b"".join(y for _, y in mix), "tiny-in-between")
+
+
+def test_tiles_of_several_rounds_and_dense_tiles(eng, O):
+    """~150-byte records: three rounds of 32 per tile; ~60-byte records: more than 128 per tile, the engine
+    gives the tile up and the operator is re-run on the general engine (sk_result.reserved == 2)."""
+    sheet, bcs = G.make_sheet(24, 32, 8, umi=0)
+    r1, r2 = _reads(8, 20000, bcs, read_len=(40, 60))
+    _both(eng, O, sheet, r1, r2, "multi-round")
+    rng = random.Random(9)
+    recs = [b"@r BC:%s\n%s\n+\n%s\n" % (rng.choice(bcs), G.rand_seq(rng, 30), b"I" * 30) for _ in range(30000)]
+    data = b"".join(recs)
+    _both(eng, O, sheet, data, data, "dense", want_engine=2)
+
+
+def test_ragged_ends(eng, O):
+    sheet, bcs = G.make_sheet(25, 16, 8, umi=4)
+    r1, r2 = _reads(10, 3000, bcs)
+    for cut in (1, 2, 7, 160, 171, 330):
+        _both(eng, O, sheet, r1[:-cut], r2, ("cut", cut), want_engine=None)
+        _both(eng, O, sheet, r1[:-cut], None, ("cut-single", cut), want_engine=None)
+    _both(eng, O, sheet, r1 + b"\n", r2, "blank-line", want_engine=None)
+    _both(eng, O, sheet, r1[: len(r1) // 2], r2, "short-mate-1", want_engine=None)
+
+
+@pytest.mark.parametrize("lanes", [8, 20, 27, 30])
+def test_other_tile_sizes(O, lanes, monkeypatch):
+    """SK_TILE_LANES: the tile may be anything from 8 to 30 lanes of 400 bytes (the rest is overhang)."""
+    from seqkit_b200 import Engine
+    monkeypatch.setenv("SK_TILE_LANES", str(lanes))
+    sheet, bcs = G.make_sheet(26, 24, 8, umi=4)
+    r1, r2 = _reads(11, 8000, bcs, read_len=(60, 200) if lanes < 30 else (100, 150))
+    with Engine(max_stream_bytes=16 << 20, max_records=1 << 16, max_samples=64) as e:
+        _both(e, O, sheet, r1, r2, ("lanes", lanes))
+
+
+def test_lean_engine_still_available(O, monkeypatch):
+    """SK_NO_WARP=1 routes demultiplex through the lean engine (sk_fast.cu): same bytes."""
+    from seqkit_b200 import Engine
+    monkeypatch.setenv("SK_NO_WARP", "1")
+    sheet, bcs = G.make_sheet(27, 24, 8, umi=4)
+    r1, r2 = _reads(12, 6000, bcs)
+    with Engine(max_stream_bytes=16 << 20, max_records=1 << 16, max_samples=64) as e:
+        _both(e, O, sheet, r1, r2, "lean")
