@@ -512,10 +512,40 @@ __device__ __forceinline__ bool plan_trim_pair(const uint8_t *b, bool has, uint3
 // Pigeonhole barcode match on the compact tables (FastIdx): both half-key probes of a class are
 // issued before either is consumed; a probe stops at the first slot whose tag matches (tags are
 // unique per table, checked when the sheet is packed).  Same contract as hidx_match.
+// The two table probes of one class, issued (fidx_issue) as soon as the barcode bytes are in registers so
+// that their latency is covered by whatever the caller does before it needs the match.
+struct FProbe {
+    uint32_t tag0, tag1, sl0, sl1;
+    uint2 e0, e1;
+};
+template <int NR>
+__device__ __forceinline__ FProbe fidx_issue(const uint32_t (&raw)[NR], const HalfIdx &H, const FastIdx &F, const uint32_t *hcls,
+                                             uint32_t c) {
+    constexpr int NWMAX = NR - 1;
+    const uint32_t nw = H.nw, nwp = H.nwp, tmask = H.tsize - 1u;
+    const uint32_t *care = hcls + c * HIDX_CLS_ROWS * nwp;
+    uint32_t tag[2] = {0u, 0u};
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const uint32_t *hm = care + (1 + 3 * h) * nwp;
+#pragma unroll
+        for (int w = 0; w < NWMAX; w++)
+            if (w < (int)nw) tag[h] += (raw[w] & hm[w]) * hm[nwp + w];
+    }
+    const uint2 *tab0 = F.table + (size_t)(c * 2) * H.tsize, *tab1 = tab0 + H.tsize;
+    FProbe pr;
+    pr.tag0 = tag[0];
+    pr.tag1 = tag[1];
+    pr.sl0 = (tag[0] ^ (tag[0] >> 15)) & tmask;
+    pr.sl1 = (tag[1] ^ (tag[1] >> 15)) & tmask;
+    pr.e0 = __ldg(&tab0[pr.sl0]);
+    pr.e1 = __ldg(&tab1[pr.sl1]);
+    return pr;
+}
 template <int NR>
 __device__ __forceinline__ void fidx_match(const uint32_t (&raw)[NR], const HalfIdx &H, const FastIdx &F,
                                            const uint32_t *hcls, uint32_t S, uint32_t &lowest, uint32_t &best,
-                                           uint32_t &last) {
+                                           uint32_t &last, const FProbe *first = nullptr) {
     constexpr int NWMAX = NR - 1;
     const uint32_t nw = H.nw, nwp = H.nwp, tmask = H.tsize - 1u;
     lowest = 0xFFFFFFFFu;
@@ -523,17 +553,11 @@ __device__ __forceinline__ void fidx_match(const uint32_t (&raw)[NR], const Half
     last = 0;
     for (uint32_t c = 0; c < H.n_classes; c++) {
         const uint32_t *care = hcls + c * HIDX_CLS_ROWS * nwp;
-        uint32_t tag[2] = {0u, 0u};
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-            const uint32_t *hm = care + (1 + 3 * h) * nwp;
-#pragma unroll
-            for (int w = 0; w < NWMAX; w++)
-                if (w < (int)nw) tag[h] += (raw[w] & hm[w]) * hm[nwp + w];
-        }
+        const FProbe pr = (c == 0 && first) ? *first : fidx_issue<NR>(raw, H, F, hcls, c);  // class 0 may come pre-issued
+        const uint32_t tag[2] = {pr.tag0, pr.tag1};
         const uint2 *tab0 = F.table + (size_t)(c * 2) * H.tsize, *tab1 = tab0 + H.tsize;
-        uint32_t sl0 = (tag[0] ^ (tag[0] >> 15)) & tmask, sl1 = (tag[1] ^ (tag[1] >> 15)) & tmask;
-        uint2 e0 = __ldg(&tab0[sl0]), e1 = __ldg(&tab1[sl1]);
+        uint32_t sl0 = pr.sl0, sl1 = pr.sl1;
+        uint2 e0 = pr.e0, e1 = pr.e1;
         while (e0.y && e0.x != tag[0]) {
             sl0 = (sl0 + 1) & tmask;
             e0 = __ldg(&tab0[sl0]);

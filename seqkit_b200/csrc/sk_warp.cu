@@ -360,27 +360,29 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
         if (lane == 0) wlb_publish(agg16, c, nls_own);
         {
             // line starts: the first two newlines of every 32-byte word by predicated stores (a third one in
-            // 32 bytes is rare), no divergent loop in the common case
+            // 32 bytes is rare), no branch in the common case
             uint32_t idx = ((incl & 0xFFFFu) - cnt_all) + extra;
             if (lane == 0 && extra) ls[0] = 0;
-            uint32_t base = o0 + 1u;
+            uint32_t base = o0;
 #pragma unroll
             for (int wi = 0; wi < NMW; wi++) {
                 uint32_t m = mw[wi];
-                if (m) {
-                    if (idx < (uint32_t)MAXLINES) ls[idx] = (uint16_t)(base + (uint32_t)__ffs((int)m) - 1u);
-                    idx++;
-                    m &= m - 1;
-                    if (m) {
-                        if (idx < (uint32_t)MAXLINES) ls[idx] = (uint16_t)(base + (uint32_t)__ffs((int)m) - 1u);
+                const bool h1 = m != 0u;
+                const uint32_t p1 = base + (uint32_t)__ffs((int)m);
+                if (h1 && idx < (uint32_t)MAXLINES) ls[idx] = (uint16_t)p1;
+                idx += h1 ? 1u : 0u;
+                m &= m - 1;
+                const bool h2 = m != 0u;
+                const uint32_t p2 = base + (uint32_t)__ffs((int)m);
+                if (h2 && idx < (uint32_t)MAXLINES) ls[idx] = (uint16_t)p2;
+                idx += h2 ? 1u : 0u;
+                m &= m - 1;
+                if (__any_sync(FULL, m != 0u)) {
+#pragma unroll 1
+                    while (m) {
+                        if (idx < (uint32_t)MAXLINES) ls[idx] = (uint16_t)(base + (uint32_t)__ffs((int)m));
                         idx++;
                         m &= m - 1;
-#pragma unroll 1
-                        while (m) {
-                            if (idx < (uint32_t)MAXLINES) ls[idx] = (uint16_t)(base + (uint32_t)__ffs((int)m) - 1u);
-                            idx++;
-                            m &= m - 1;
-                        }
                     }
                 }
                 base += 32u;
@@ -506,11 +508,13 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                     }
                     __syncwarp();
                     uint32_t raw[NWMAX + 1];
+                    FProbe probe;
                     const uint32_t bs = stp + 4;
                     if (live) {
                         cut0 = stp - L0;
                         cut1 = cut0 + 4 + Lb;
                         load_raw<NWMAX + 1>(win, bs, (Lb + 4u) >> 2, raw);
+                        probe = fidx_issue<NWMAX + 1>(raw, p.sheet.hidx, p.sheet.fidx, hcls, 0u);  // consumed after the class check
                         if (!class_run_is<NWMAX + 1>(raw, sh_lut, Lb, L1 - bs)) {  // :38, :148-150
                             taglen = K_BC_LEN;
                             live = false;
@@ -519,7 +523,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                     __syncwarp();
                     if (live) {  // :154-194
                         uint32_t lowest, best, last;
-                        fidx_match<NWMAX + 1>(raw, p.sheet.hidx, p.sheet.fidx, hcls, S, lowest, best, last);
+                        fidx_match<NWMAX + 1>(raw, p.sheet.hidx, p.sheet.fidx, hcls, S, lowest, best, last, &probe);
                         taglen = 0;
                         if (lowest <= 1u) {        // :172
                             if (best == last) {    // :173-178
