@@ -47,43 +47,44 @@ struct WLayout {
 };
 static_assert(WLayout::per_warp % 16 == 0, "warp areas are 16-byte aligned");
 
-// Up to eight bytes of shared memory from any byte offset, as aligned words and funnel shifts.
-__device__ __forceinline__ uint32_t lds_un32(const uint8_t *src) {
-    const uint32_t *w = (const uint32_t *)((uintptr_t)src & ~(uintptr_t)3);
-    return __funnelshift_r(w[0], w[1], ((uint32_t)(uintptr_t)src & 3u) * 8u);
+// Up to eight bytes of the window from any byte offset, as aligned words and funnel shifts.  The window
+// is addressed as base + offset throughout, so that the compiler keeps the accesses in the shared space
+// (a pointer rebuilt from an integer turns them into generic loads).
+__device__ __forceinline__ uint32_t lds_un32(const uint8_t *win, uint32_t off) {
+    const uint32_t *w = (const uint32_t *)(win + (off & ~3u));
+    return __funnelshift_r(w[0], w[1], (off & 3u) * 8u);
 }
-__device__ __forceinline__ uint2 lds_un64(const uint8_t *src) {
-    const uint32_t *w = (const uint32_t *)((uintptr_t)src & ~(uintptr_t)3);
-    const uint32_t sh = ((uint32_t)(uintptr_t)src & 3u) * 8u;
+__device__ __forceinline__ uint2 lds_un64(const uint8_t *win, uint32_t off) {
+    const uint32_t *w = (const uint32_t *)(win + (off & ~3u));
+    const uint32_t sh = (off & 3u) * 8u;
     const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
     return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
 }
-// Lane-serial copy of `len` bytes from shared memory to global memory, any alignment on either side.
+// Lane-serial copy of `len` window bytes from offset `so` to global memory, any alignment on either side.
 // The destination is brought to a 16-byte boundary by at most one store of each size 1, 2, 4, 8 (no
 // loops: the lanes of a warp copy runs of different alignment), then 16 bytes per step (4 LDS.32 + 4
-// funnel shifts + 1 STG.128), then at most one store of each size 8, 4, 2, 1.  The source is only ever
-// read as aligned words (up to seven bytes past its end).
-__device__ __forceinline__ void gcopy(uint8_t *dst, const uint8_t *src, uint32_t len) {
-    const uint32_t a = (uint32_t)(uintptr_t)dst;
-    if ((a & 1u) && len >= 1u) {
-        *dst = *src;
-        dst += 1, src += 1, len -= 1;
+// funnel shifts + 1 STG.128), then at most one store of each size 8, 4, 2, 1.  The window is only ever
+// read as aligned words (up to seven bytes past the run).
+__device__ __forceinline__ void gcopy(uint8_t *dst, const uint8_t *win, uint32_t so, uint32_t len) {
+    if (((uint32_t)(uintptr_t)dst & 1u) && len >= 1u) {
+        *dst = win[so];
+        dst += 1, so += 1, len -= 1;
     }
     if (((uint32_t)(uintptr_t)dst & 2u) && len >= 2u) {
-        *(uint16_t *)dst = (uint16_t)lds_un32(src);
-        dst += 2, src += 2, len -= 2;
+        *(uint16_t *)dst = (uint16_t)lds_un32(win, so);
+        dst += 2, so += 2, len -= 2;
     }
     if (((uint32_t)(uintptr_t)dst & 4u) && len >= 4u) {
-        *(uint32_t *)dst = lds_un32(src);
-        dst += 4, src += 4, len -= 4;
+        *(uint32_t *)dst = lds_un32(win, so);
+        dst += 4, so += 4, len -= 4;
     }
     if (((uint32_t)(uintptr_t)dst & 8u) && len >= 8u) {
-        *(uint2 *)dst = lds_un64(src);
-        dst += 8, src += 8, len -= 8;
+        *(uint2 *)dst = lds_un64(win, so);
+        dst += 8, so += 8, len -= 8;
     }
     if (len >= 16u) {  // dst is 16-byte aligned here
-        const uint32_t sh = ((uint32_t)(uintptr_t)src & 3u) * 8u;
-        const uint32_t *sw = (const uint32_t *)((uintptr_t)src & ~(uintptr_t)3);
+        const uint32_t sh = (so & 3u) * 8u;
+        const uint32_t *sw = (const uint32_t *)(win + (so & ~3u));
         uint4 *dq = (uint4 *)dst;
         uint32_t lo = *sw;
         const uint32_t n16 = len >> 4;
@@ -99,36 +100,36 @@ __device__ __forceinline__ void gcopy(uint8_t *dst, const uint8_t *src, uint32_t
             lo = w4;
             sw += 4;
         }
-        dst += n16 * 16u, src += n16 * 16u, len &= 15u;
+        dst += n16 * 16u, so += n16 * 16u, len &= 15u;
     }
     if (len & 8u) {
         if (((uint32_t)(uintptr_t)dst & 7u) == 0u) {
-            *(uint2 *)dst = lds_un64(src);
+            *(uint2 *)dst = lds_un64(win, so);
         } else {  // (a run shorter than its head alignment)
 #pragma unroll 1
-            for (int i = 0; i < 8; i++) dst[i] = src[i];
+            for (uint32_t i = 0; i < 8u; i++) dst[i] = win[so + i];
         }
-        dst += 8, src += 8;
+        dst += 8, so += 8;
     }
     if (len & 4u) {
         if (((uint32_t)(uintptr_t)dst & 3u) == 0u) {
-            *(uint32_t *)dst = lds_un32(src);
+            *(uint32_t *)dst = lds_un32(win, so);
         } else {
 #pragma unroll 1
-            for (int i = 0; i < 4; i++) dst[i] = src[i];
+            for (uint32_t i = 0; i < 4u; i++) dst[i] = win[so + i];
         }
-        dst += 4, src += 4;
+        dst += 4, so += 4;
     }
     if (len & 2u) {
         if (((uint32_t)(uintptr_t)dst & 1u) == 0u) {
-            *(uint16_t *)dst = (uint16_t)lds_un32(src);
+            *(uint16_t *)dst = (uint16_t)lds_un32(win, so);
         } else {
-            dst[0] = src[0];
-            dst[1] = src[1];
+            dst[0] = win[so];
+            dst[1] = win[so + 1];
         }
-        dst += 2, src += 2;
+        dst += 2, so += 2;
     }
-    if (len & 1u) *dst = *src;
+    if (len & 1u) *dst = win[so];
 }
 
 // min_baseq > 222 (never in practice): the byte-wise trim of sk_device.cuh, out of line.  Returns
@@ -142,8 +143,10 @@ static __device__ __noinline__ uint32_t plan_trim_cold(const uint8_t *b, uint32_
 
 // Look-back of the warp engine over p.tile_lines: inc[c] (u64: bit 63 | lines through tile c) and, behind
 // those, agg[c] (u16: lines owned by tile c, plus one; 0 = not yet known).  A tile's exclusive prefix is
-// the inclusive prefix of tile 8(b-32)-1 plus the 256 + (c & 7) counts after it, b = c / 8: one aligned
-// 16-byte load per lane.  Tiles are handed out by a ticket counter, so every predecessor is owned by a
+// the inclusive prefix of tile 8(b-128)-1 plus the 1024 + (c & 7) counts after it, b = c / 8: four aligned
+// 16-byte loads per lane.  The window is that wide because the inclusive prefixes form a chain (tile c
+// needs the one of tile c-1024 or so): with n tiles the chain has n/1024 links of a few microseconds of
+// memory latency each, which must stay far below the kernel's run time.  Tiles are handed out by a ticket counter, so every predecessor is owned by a
 // running warp that never waits on a later tile.
 __device__ __forceinline__ uint16_t *wlb_agg(uint64_t *tile_lines, uint32_t n_tiles) {
     return (uint16_t *)(tile_lines + ((n_tiles + 1u) & ~1u));
@@ -155,18 +158,32 @@ __device__ __forceinline__ void wlb_publish(uint16_t *agg, uint32_t c, uint32_t 
 __device__ __forceinline__ uint32_t zero_half(uint32_t x) { return (x - 0x00010001u) & ~x & 0x80008000u; }
 static __device__ __noinline__ uint64_t wlb_consume(uint64_t *inc, const uint16_t *agg, uint32_t c, uint32_t own, int lane) {
     constexpr uint32_t FULL = 0xffffffffu;
+    constexpr uint32_t BPL = 4;           // blocks of eight counts per lane: a window of 1024 tiles
+    constexpr uint32_t NB = 32 * BPL;
     uint64_t excl = 0;
     const uint32_t b = c >> 3;  // block of eight counts that holds c
-    if (b >= 32u) {
-        const uint16_t *blk = agg + 8u * (b - 32u + (uint32_t)lane);
+    if (b >= NB) {
+        const uint16_t *blk = agg + 8u * (b - NB + BPL * (uint32_t)lane);
         const uint16_t *part = agg + 8u * b;
         const uint32_t npart = c & 7u;
         uint32_t sum;
         for (;;) {
-            uint32_t x0, x1, x2, x3;
-            asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(x0), "=r"(x1), "=r"(x2), "=r"(x3) : "l"(blk) : "memory");
-            bool ok = (zero_half(x0) | zero_half(x1) | zero_half(x2) | zero_half(x3)) == 0u;
-            sum = (x0 & 0xFFFFu) + (x0 >> 16) + (x1 & 0xFFFFu) + (x1 >> 16) + (x2 & 0xFFFFu) + (x2 >> 16) + (x3 & 0xFFFFu) + (x3 >> 16) - 8u;
+            uint32_t x[4 * BPL];
+#pragma unroll
+            for (uint32_t q = 0; q < BPL; q++)
+                asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(x[4 * q]), "=r"(x[4 * q + 1]), "=r"(x[4 * q + 2]), "=r"(x[4 * q + 3])
+                             : "l"(blk + 8u * q)
+                             : "memory");
+            uint32_t z = 0;
+            sum = 0;
+#pragma unroll
+            for (uint32_t q = 0; q < 4 * BPL; q++) {
+                z |= zero_half(x[q]);
+                sum += (x[q] & 0xFFFFu) + (x[q] >> 16);
+            }
+            sum -= 8u * BPL;
+            bool ok = z == 0u;
             if (lane == 0 && npart) {
                 uint32_t y[4];
                 asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(y[0]), "=r"(y[1]), "=r"(y[2]), "=r"(y[3]) : "l"(part) : "memory");
@@ -182,7 +199,7 @@ static __device__ __noinline__ uint64_t wlb_consume(uint64_t *inc, const uint16_
             __nanosleep(40);
         }
         sum = __reduce_add_sync(FULL, sum);
-        const uint32_t t = 8u * (b - 32u);
+        const uint32_t t = 8u * (b - NB);
         uint64_t w = 1ull << 63;
         if (t > 0u && lane == 0) {
             w = ts_load(&inc[t - 1u]);
@@ -195,6 +212,7 @@ static __device__ __noinline__ uint64_t wlb_consume(uint64_t *inc, const uint16_
         excl = (w & ~(1ull << 63)) + sum;
     } else {
         uint32_t sum = 0;
+#pragma unroll 1
         for (uint32_t i = (uint32_t)lane; i < c; i += 32u) {
             unsigned short e;
             for (;;) {
@@ -709,12 +727,9 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                         const uint32_t ulen = sh_ulen[sample];
                         const uint32_t u0 = (uint32_t)__ffsll((long long)m) - 1u;
                         if (ulen && ulen <= 8u && (m >> u0) == ((1ull << ulen) - 1ull)) {  // one run of U (the usual sheet)
-                            const uint8_t *us = ob + u0;
-                            const uint32_t sh = ((uint32_t)(uintptr_t)us & 3u) * 8u;
-                            const uint32_t *uw = (const uint32_t *)((uintptr_t)us & ~(uintptr_t)3);
-                            const uint32_t w0 = uw[0], w1 = uw[1], w2 = uw[2];
-                            ulo = __funnelshift_r(w0, w1, sh);
-                            uhi = __funnelshift_r(w1, w2, sh);
+                            const uint2 uv = lds_un64(win, L0 + cut0 + 4u + u0);
+                            ulo = uv.x;
+                            uhi = uv.y;
                             ureg = true;
                             if (p.sheet.Umax == 8u && ulen == 8u) {
                                 *(uint2 *)gu = make_uint2(ulo, uhi);
@@ -783,7 +798,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                         const uint32_t so = q == 0 ? L0 : q == 1 ? L1 : L3;
                         const uint32_t ln = !emit ? 0u : q == 0 ? hrun : q == 1 ? run1 : run2;
                         uint8_t *dd = q == 0 ? gd : q == 1 ? gd + hlen : gd + hlen + run1;
-                        gcopy(dd, win + so, ln);
+                        gcopy(dd, win, so, ln);
                         __syncwarp();
                     }
                     if (emit && bslow) {  // rare: a '+' line too short to hold the patch
