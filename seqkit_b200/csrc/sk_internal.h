@@ -118,12 +118,17 @@ struct DevStats {
     unsigned long long out_extent;    // bytes of the out buffer in use
     unsigned long long err_key;       // max over failing records of ~(record << 8 | kind); 0 = none
     unsigned long long consumed;      // byte offset just past the last processed record
-    unsigned long long out_cursor;    // demux: bump allocator
     unsigned int flags;
     unsigned int n_events;
-    unsigned int ticket;              // dynamic chunk counter
     unsigned int n_slow;              // records that took the brute-force match (diagnostic)
+    unsigned int pad0;
     unsigned long long phase_cycles[16];  // -DSK_PHASE_TIMING: per-phase SM cycles summed over chunks (thread 0)
+    // the two words every chunk hits with an atomic, each on a 128-byte line of its own
+    unsigned long long pad1[8];
+    unsigned long long out_cursor;    // demux: bump allocator
+    unsigned long long pad2[15];
+    unsigned int ticket;              // dynamic chunk counter
+    unsigned int pad3[31];
 };
 
 // Pigeonhole index over the sample sheet (built on the host, sk_api.cu).  Samples are grouped in

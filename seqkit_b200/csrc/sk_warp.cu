@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
     uint32_t parity = 0;
     uint32_t my_total = 0, my_ident = 0;   // DEMUX1 counters of this lane's records
     unsigned long long my_out = 0;         // lane 0: payload bytes of this warp's tiles
+    unsigned long long my_nrec = 0, my_upto = 0;  // lane 0: records of this warp's tiles, end of the last one
 #define LB(x) ((uint32_t)ls[(x)])
 
     uint32_t c = 0;
@@ -856,9 +857,10 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
         }
         if (lane == 0) {
             if (c == p.n_chunks - 1) st->n_lines = g0 + nls_own;
-            if (nrec) {
-                atomicAdd(&st->n_records, (unsigned long long)nrec);
-                atomicMax(&st->consumed, (unsigned long long)(c0 + LB(j0 + nrec * 4u)));
+            if (nrec) {  // flushed once, after the last tile
+                my_nrec += nrec;
+                const unsigned long long upto = c0 + LB(j0 + nrec * 4u);
+                my_upto = upto > my_upto ? upto : my_upto;
             }
         }
         // The next ticket is taken during the last round (or now): a tile's count must appear soon after
@@ -874,6 +876,10 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
 #undef LB
 #undef UMI_BYTE
     if (lane == 0 && my_out) atomicAdd(&st->out_bytes, my_out);
+    if (lane == 0 && my_nrec) {
+        atomicAdd(&st->n_records, my_nrec);
+        atomicMax(&st->consumed, my_upto);
+    }
     if (D1) {  // fasta_demultiplex.rs:108-109,169,177-178
         const uint32_t wt = __reduce_add_sync(FULL, my_total), wi = __reduce_add_sync(FULL, my_ident);
         if (lane == 0 && wt) atomicAdd(&p.counts[S], (unsigned long long)wt);
