@@ -1,17 +1,19 @@
 // sk_warp.cu -- the warp engine: header-route demultiplex (mate 1 / mate 2, with or without the fused
-// quality trim) with one warp per tile and one lane per record (DESIGN.md section 3.1).
+// quality trim) with one warp per tile and one lane per record (DESIGN.md section 3.0).
 //
 // The lean engine (sk_fast.cu) spends a third of its warp time at CTA barriers: its per-record phase
 // runs one lane per record on the few warps a 16 KiB chunk fills, while the other warps of the CTA
-// wait.  Here a warp owns a whole tile of the stream from load to store and never meets another warp:
+// wait.  Here a warp owns a whole tile of the stream from load to store (the warps of a CTA only start
+// their tiles together, for the instruction cache):
 //   * tile = 29 lanes x 400 B of input (about 31 records of 2x150 bp FASTQ) + 3 lanes of overhang,
 //     loaded by one TMA bulk copy into the warp's private window; 16 such warps per SM sit in
 //     different phases, so nobody waits at a barrier and every per-record step has its 32 lanes busy;
 //   * newline scan: 25 conflict-free LDS.128 per lane, newline maps in registers, one shuffle scan,
-//     line starts written by plain ffs loops;
+//     line starts written by predicated stores;
 //   * record framing by global line index (common.rs:106-112): tiles publish their line counts as
-//     16-bit words, a tile sums the 256 counts before it with one 16-byte load per lane and adds the
-//     inclusive prefix of the tile before those (wlb_consume);
+//     16-bit words, a tile sums the 1024 counts before it with four 16-byte loads per lane and adds
+//     the inclusive prefix of the tile before those (wlb_consume); the framing is guessed from the
+//     text first and the guess verified before anything is written;
 //   * per record, in registers: '@' check, leftmost " BC:x", class run, pigeonhole match, header
 //     surgery, quality trim (fasta_demultiplex.rs:117-212, fasta_trim_by_quality.rs:28-48);
 //   * output: a round (<= 32 records) takes its space with one atomicAdd, the record's edits are
