@@ -62,11 +62,25 @@ __device__ __forceinline__ uint2 lds_un64(const uint8_t *win, uint32_t off) {
     const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
     return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
 }
+// Sixteen bytes of the window from any byte offset.
+__device__ __forceinline__ uint4 lds_unaligned16(const uint8_t *win, uint32_t off) {
+    const uint32_t *w = (const uint32_t *)(win + (off & ~3u));
+    const uint32_t sh = (off & 3u) * 8u;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+    return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+}
+// One 256-bit store to a 32-byte aligned global address (sm_100: STG.256).
+__device__ __forceinline__ void stg256(void *dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                       uint32_t g, uint32_t h) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e),
+                 "r"(f), "r"(g), "r"(h)
+                 : "memory");
+}
 // Lane-serial copy of `len` window bytes from offset `so` to global memory, any alignment on either side.
 // The destination is brought to a 16-byte boundary by at most one store of each size 1, 2, 4, 8 (no
-// loops: the lanes of a warp copy runs of different alignment), then 16 bytes per step (4 LDS.32 + 4
-// funnel shifts + 1 STG.128), then at most one store of each size 8, 4, 2, 1.  The window is only ever
-// read as aligned words (up to seven bytes past the run).
+// loops: the lanes of a warp copy runs of different alignment), one of 16 to reach a 32-byte sector
+// boundary, then 32 bytes per step (8 LDS.32 + 8 funnel shifts + 1 STG.256), then at most one store of
+// each size 16, 8, 4, 2, 1.  The window is only ever read as aligned words (up to seven bytes past the run).
 __device__ __forceinline__ void gcopy(uint8_t *dst, const uint8_t *win, uint32_t so, uint32_t len) {
     if (((uint32_t)(uintptr_t)dst & 1u) && len >= 1u) {
         *dst = win[so];
@@ -84,25 +98,32 @@ __device__ __forceinline__ void gcopy(uint8_t *dst, const uint8_t *win, uint32_t
         *(uint2 *)dst = lds_un64(win, so);
         dst += 8, so += 8, len -= 8;
     }
-    if (len >= 16u) {  // dst is 16-byte aligned here
+    // dst is 16-byte aligned here; one 16-byte step brings it to a 32-byte sector boundary, then whole
+    // sectors go out with 256-bit stores (STG.256: half as many requests, none of them a partial sector)
+    if ((((uint32_t)(uintptr_t)dst & 16u) && len >= 16u)) {
+        *(uint4 *)dst = lds_unaligned16(win, so);
+        dst += 16, so += 16, len -= 16;
+    }
+    if (len >= 32u) {
         const uint32_t sh = (so & 3u) * 8u;
         const uint32_t *sw = (const uint32_t *)(win + (so & ~3u));
-        uint4 *dq = (uint4 *)dst;
         uint32_t lo = *sw;
-        const uint32_t n16 = len >> 4;
+        const uint32_t n32 = len >> 5;
 #pragma unroll 1
-        for (uint32_t i = 0; i < n16; i++) {
-            const uint32_t w1 = sw[1], w2 = sw[2], w3 = sw[3], w4 = sw[4];
-            uint4 o;
-            o.x = __funnelshift_r(lo, w1, sh);
-            o.y = __funnelshift_r(w1, w2, sh);
-            o.z = __funnelshift_r(w2, w3, sh);
-            o.w = __funnelshift_r(w3, w4, sh);
-            *dq++ = o;
-            lo = w4;
-            sw += 4;
+        for (uint32_t i = 0; i < n32; i++) {
+            const uint32_t w1 = sw[1], w2 = sw[2], w3 = sw[3], w4 = sw[4], w5 = sw[5], w6 = sw[6], w7 = sw[7], w8 = sw[8];
+            stg256(dst, __funnelshift_r(lo, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                   __funnelshift_r(w3, w4, sh), __funnelshift_r(w4, w5, sh), __funnelshift_r(w5, w6, sh),
+                   __funnelshift_r(w6, w7, sh), __funnelshift_r(w7, w8, sh));
+            lo = w8;
+            sw += 8;
+            dst += 32;
         }
-        dst += n16 * 16u, so += n16 * 16u, len &= 15u;
+        so += n32 * 32u, len &= 31u;
+    }
+    if (len & 16u) {
+        *(uint4 *)dst = lds_unaligned16(win, so);
+        dst += 16, so += 16;
     }
     if (len & 8u) {
         if (((uint32_t)(uintptr_t)dst & 7u) == 0u) {
