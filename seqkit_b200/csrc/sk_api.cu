@@ -205,7 +205,7 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
     // slice-table rows: one per chunk, or GeoW::ROUNDS per tile of the warp engine (smallest tile: 8 lanes)
     ctx->max_chunks = std::max(chunks_of(ctx, B, ENG_GENERAL), (uint32_t)((B + GeoS::CHUNK - 1) / GeoS::CHUNK)) + 1;
     ctx->max_chunks = std::max(ctx->max_chunks, (uint32_t)(B / (8 * GeoW::LANE_BYTES) + 1) * GeoW::ROUNDS);
-    const uint64_t out_cap = B + R * 72 + (uint64_t)ctx->max_chunks * 16 + 4096;
+    const uint64_t out_cap = B + R * 72 + (uint64_t)ctx->max_chunks * 32 + 4096;  // every chunk / round owns whole 32-byte sectors
     const uint32_t Smax = lim->max_samples;
     ctx->slots.resize(lim->n_slots);
     for (auto &s : ctx->slots) {

@@ -40,8 +40,8 @@ extern __shared__ __align__(128) unsigned char sk_smem[];
 namespace sk {
 
 struct WLayout {
-    static constexpr uint32_t win = 0;
-    static constexpr uint32_t ls = GeoW::WIN + 32;                                   // patches may touch win[wlen]
+    static constexpr uint32_t win = 32;                                              // the sector emit reads up to 31 bytes below a run
+    static constexpr uint32_t ls = win + GeoW::WIN + 32;                             // patches may touch win[wlen]
     static constexpr uint32_t misc = ls + (((GeoW::MAXLINES + 8) * 2 + 15) / 16) * 16;
     static constexpr uint32_t per_warp = misc + 16;
     static constexpr uint32_t lut = GeoW::WARPS * per_warp;
@@ -68,6 +68,34 @@ __device__ __forceinline__ uint4 lds_unaligned16(const uint8_t *win, uint32_t of
     const uint32_t sh = (off & 3u) * 8u;
     const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
     return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+}
+// Thirty-two bytes of the window from any byte offset >= -32.
+struct U256 {
+    uint32_t w[8];
+};
+__device__ __forceinline__ U256 lds_unaligned32(const uint8_t *win, int off) {
+    const uint32_t *p = (const uint32_t *)(win + (off & ~3));
+    const uint32_t sh = ((uint32_t)off & 3u) * 8u;
+    U256 r;
+    uint32_t lo = p[0];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t hi = p[k + 1];
+        r.w[k] = __funnelshift_r(lo, hi, sh);
+        lo = hi;
+    }
+    return r;
+}
+// bytes [0, f) of a, the others of b (0 < f < 32)
+__device__ __forceinline__ U256 merge_low32(const U256 &a, const U256 &b, uint32_t f) {
+    U256 r;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int n = (int)f - 4 * k;
+        const uint32_t m = n <= 0 ? 0u : (n >= 4 ? 0xFFFFFFFFu : (1u << (8 * n)) - 1u);
+        r.w[k] = (a.w[k] & m) | (b.w[k] & ~m);
+    }
+    return r;
 }
 // One 256-bit store to a 32-byte aligned global address (sm_100: STG.256).
 __device__ __forceinline__ void stg256(void *dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
@@ -264,9 +292,10 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
     using WL = WLayout;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint8_t *win = sk_smem + (uint32_t)warp * WL::per_warp;
-    uint16_t *ls = (uint16_t *)(win + WL::ls);
-    uint64_t *mbar = (uint64_t *)(win + WL::misc);
+    uint8_t *warea = sk_smem + (uint32_t)warp * WL::per_warp;
+    uint8_t *win = warea + WL::win;
+    uint16_t *ls = (uint16_t *)(warea + WL::ls);
+    uint64_t *mbar = (uint64_t *)(warea + WL::misc);
     uint8_t *sh_lut = sk_smem + WL::lut;
     uint32_t *hcls = (uint32_t *)(sk_smem + WL::dyn);
     const uint32_t S = p.sheet.S;
@@ -731,7 +760,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 const uint32_t n_emit = __popc(emit_mask);
                 unsigned long long rbase = 0;
                 if (lane == 0 && p.out && round_out) {  // the reply is awaited after the header patches
-                    rbase = atomicAdd(&st->out_cursor, (unsigned long long)((round_out + 15u) & ~15u));
+                    rbase = atomicAdd(&st->out_cursor, (unsigned long long)((round_out + 31u) & ~31u));  // whole sectors
                     my_out += round_out;
                 }
                 const bool emit = outlen != 0;
@@ -794,11 +823,64 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 // ---- emit
                 rbase = __shfl_sync(FULL, rbase, 0);
                 bool writable = p.out != nullptr && round_out > 0;
-                if (writable && rbase + ((round_out + 15u) & ~15u) > p.out_cap) {
+                if (writable && rbase + ((round_out + 31u) & ~31u) > p.out_cap) {
                     if (lane == 0) report_err(st, rec0 + r0, K_OUT_OVERFLOW);
                     writable = false;
                 }
-                if (writable) {
+                // Sector emit (the usual round: every record patched in place, one round in the tile).  The
+                // round's output is the concatenation of three runs per record (run table behind the line
+                // table).  A lane writes the 32-byte sectors that start inside its record, each with one
+                // STG.256: a sector inside one run is one unaligned 32-byte read of the window; at a seam the
+                // lane walks on through the table -- into the next records' runs if need be -- reading each
+                // piece at the offset that puts its bytes in place.  No partial-sector store, a third of the
+                // store requests of the run copies below.
+                const bool sect = writable && nrec <= 32u && !__any_sync(FULL, emit && (!hpatch || bslow));
+                if (sect) {
+                    uint32_t *rt = (uint32_t *)(ls + 144);
+                    const uint32_t ro1 = my_off + (emit ? hrun : 0u), ro2 = ro1 + (emit ? run1 : 0u);
+                    rt[3 * lane] = my_off | (L0 << 16);
+                    rt[3 * lane + 1] = ro1 | (L1 << 16);
+                    rt[3 * lane + 2] = ro2 | (L3 << 16);
+                    if (lane == 0) rt[96] = round_out;
+                    __syncwarp();
+                    uint8_t *gbase = p.out + rbase;
+                    if (emit) {
+                        uint32_t i = 3u * (uint32_t)lane;
+                        uint32_t e = rt[i], en = rt[i + 1];
+                        const uint32_t oend = my_off + outlen;
+#pragma unroll 1
+                        for (uint32_t o = (my_off + 31u) & ~31u; o < oend; o += 32u) {
+#pragma unroll 1
+                            while ((en & 0xFFFFu) <= o) {  // ends: rt[96] = round_out > o
+                                i++;
+                                e = en;
+                                en = rt[i + 1];
+                            }
+                            U256 v = lds_unaligned32(win, (int)(e >> 16) + (int)o - (int)(e & 0xFFFFu));
+                            uint32_t filled = (en & 0xFFFFu) - o;
+                            if (filled < 32u) {  // a seam: the runs after this one fill the sector
+                                uint32_t j = i + 1u, ej = en;
+#pragma unroll 1
+                                while (filled < 32u && j < 96u) {
+                                    const uint32_t ejn = rt[j + 1];
+                                    if ((ejn & 0xFFFFu) > o + filled) {
+                                        const U256 v2 = lds_unaligned32(win, (int)(ej >> 16) + (int)o - (int)(ej & 0xFFFFu));
+                                        v = merge_low32(v, v2, filled);
+                                        filled = (ejn & 0xFFFFu) - o;
+                                    }
+                                    j++;
+                                    ej = ejn;
+                                }
+                            }
+                            stg256(gbase + o, v.w[0], v.w[1], v.w[2], v.w[3], v.w[4], v.w[5], v.w[6], v.w[7]);
+                        }
+                        Group g;
+                        g.sample = (uint16_t)sample;
+                        g.len = (uint16_t)outlen;
+                        p.groups[rec0 + r0 + my_rank] = g;
+                    }
+                    __syncwarp();
+                } else if (writable) {
                     uint8_t *gd = p.out + rbase + my_off;
                     if (emit && !hpatch) {  // rare: a header piece after the cut, or no room for the tag
                         uint8_t *d = gd;
