@@ -319,6 +319,10 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
             for (uint32_t i = tid; i < S; i += GeoW::NT) ccount[i] = 0;
         }
     }
+    if (tid == 0) {  // CTA ticket slots (below): 0 is never newer than a ticket
+        ((volatile uint32_t *)(sk_smem + WL::misc + 8))[0] = 0u;
+        ((volatile uint32_t *)(sk_smem + WL::misc + 8))[1] = 0u;
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
 
@@ -334,6 +338,34 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
     unsigned long long my_out = 0;         // lane 0: payload bytes of this warp's tiles
     unsigned long long my_nrec = 0, my_upto = 0;  // lane 0: records of this warp's tiles, end of the last one
 #define LB(x) ((uint32_t)ls[(x)])
+
+    // Starts the load of tile cc into the warp's window (TMA bulk copy; plain loads for the ragged tail of
+    // the stream).  The window must be dead: called at the top of a tile or, when the CTA's next ticket is
+    // already known, right after the previous tile's emit -- the copy then runs while the warp waits for
+    // its CTA at the meeting point.
+    auto issue_load = [&](uint32_t cc) {
+        const uint64_t b0 = (uint64_t)cc * TILE;
+        uint64_t bend = b0 + (uint64_t)WIN;
+        if (bend > p.n) bend = p.n;
+        const uint32_t blen = (uint32_t)(bend - b0);
+        const uint32_t bbulk = blen & ~15u;
+        fence_proxy_async();  // this lane's patches of the previous window before the next TMA write
+        __syncwarp();         // every lane is done with the previous window
+        if (lane == 0 && bbulk) {
+            fence_proxy_async();
+            mbar_expect_tx(mbar, bbulk);
+            bulk_g2s(win, p.in + b0, bbulk, mbar);
+        }
+        if (bbulk != (uint32_t)WIN) {  // last window of the stream: ragged tail, zeros up to the end of the window
+            if (lane < 16) {
+                const uint32_t o = bbulk + (uint32_t)lane;
+                win[o] = (o < blen) ? p.in[b0 + o] : (uint8_t)0;
+            }
+            for (uint32_t o = bbulk + 16u + 16u * (uint32_t)lane; o < (uint32_t)WIN + 32u; o += 512u)
+                *(uint4 *)(win + o) = make_uint4(0u, 0u, 0u, 0u);
+        }
+    };
+    bool early = false;  // the load of this tile was started at the end of the previous one
 
     uint32_t c = 0;
 #if SKW_LOCKSTEP
@@ -368,23 +400,10 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
         const uint32_t wlen = (uint32_t)(wend - c0);
         const bool at_end = (wend == p.n);
 
-        // ---- load the window (TMA bulk copy; plain loads for the ragged tail of the stream)
+        // ---- load the window
         const uint32_t bulk = wlen & ~15u;
-        fence_proxy_async();  // this lane's patches of the previous window before the next TMA write
-        __syncwarp();         // every lane is done with the previous window
-        if (lane == 0 && bulk) {
-            fence_proxy_async();
-            mbar_expect_tx(mbar, bulk);
-            bulk_g2s(win, p.in + c0, bulk, mbar);
-        }
-        if (bulk != (uint32_t)WIN) {  // last window of the stream: ragged tail, zeros up to the end of the window
-            if (lane < 16) {
-                const uint32_t o = bulk + (uint32_t)lane;
-                win[o] = (o < wlen) ? p.in[c0 + o] : (uint8_t)0;
-            }
-            for (uint32_t o = bulk + 16u + 16u * (uint32_t)lane; o < (uint32_t)WIN + 32u; o += 512u)
-                *(uint4 *)(win + o) = make_uint4(0u, 0u, 0u, 0u);
-        }
+        if (!early) issue_load(c);
+        early = false;
         if (bulk) {
             mbar_wait_parked(mbar, parity);
             parity ^= 1;
@@ -822,6 +841,9 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
 
                 // ---- emit
                 rbase = __shfl_sync(FULL, rbase, 0);
+#if SKW_LOCKSTEP
+                if (tid == 0 && cta_have) cta_ticket[flipk] = cta_next;  // the CTA's next ticket, for early loads
+#endif
                 bool writable = p.out != nullptr && round_out > 0;
                 if (writable && rbase + ((round_out + 31u) & ~31u) > p.out_cap) {
                     if (lane == 0) report_err(st, rec0 + r0, K_OUT_OVERFLOW);
@@ -976,6 +998,13 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
 #else
         (void)c_next;
         (void)have_next;
+        {  // the CTA's next ticket may be known already (tickets only grow): start the next load now
+            const uint32_t v = cta_ticket[flipk];
+            if (v > cb && v + (uint32_t)warp < p.n_chunks) {
+                issue_load(v + (uint32_t)warp);
+                early = true;
+            }
+        }
 #endif
     }
 #undef LB
