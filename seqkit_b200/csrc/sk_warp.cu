@@ -86,7 +86,7 @@ __device__ __forceinline__ U256 lds_unaligned32(const uint8_t *win, int off) {
     }
     return r;
 }
-// bytes [0, f) of a, the others of b (0 < f < 32)
+// bytes [0, f) of a, the others of b (0 <= f < 32)
 __device__ __forceinline__ U256 merge_low32(const U256 &a, const U256 &b, uint32_t f) {
     U256 r;
 #pragma unroll
@@ -866,36 +866,43 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                     if (lane == 0) rt[96] = round_out;
                     __syncwarp();
                     uint8_t *gbase = p.out + rbase;
-                    if (emit) {
+                    // One step = one piece: read 32 bytes of the current run at the offset that puts them in
+                    // place, merge them behind the bytes the sector already has, then either store the sector
+                    // (full, or the round's last) or move on to the next run.  Every lane takes the same path
+                    // through a step, whatever its seams.
+                    {
                         uint32_t i = 3u * (uint32_t)lane;
                         uint32_t e = rt[i], en = rt[i + 1];
                         const uint32_t oend = my_off + outlen;
+                        uint32_t o = (my_off + 31u) & ~31u, filled = 0;
+                        bool act = emit && o < oend;
+                        U256 v;
+#pragma unroll
+                        for (int k = 0; k < 8; k++) v.w[k] = 0u;
 #pragma unroll 1
-                        for (uint32_t o = (my_off + 31u) & ~31u; o < oend; o += 32u) {
+                        while (__any_sync(FULL, act)) {
+                            if (act) {
 #pragma unroll 1
-                            while ((en & 0xFFFFu) <= o) {  // ends: rt[96] = round_out > o
-                                i++;
-                                e = en;
-                                en = rt[i + 1];
-                            }
-                            U256 v = lds_unaligned32(win, (int)(e >> 16) + (int)o - (int)(e & 0xFFFFu));
-                            uint32_t filled = (en & 0xFFFFu) - o;
-                            if (filled < 32u) {  // a seam: the runs after this one fill the sector
-                                uint32_t j = i + 1u, ej = en;
-#pragma unroll 1
-                                while (filled < 32u && j < 96u) {
-                                    const uint32_t ejn = rt[j + 1];
-                                    if ((ejn & 0xFFFFu) > o + filled) {
-                                        const U256 v2 = lds_unaligned32(win, (int)(ej >> 16) + (int)o - (int)(ej & 0xFFFFu));
-                                        v = merge_low32(v, v2, filled);
-                                        filled = (ejn & 0xFFFFu) - o;
-                                    }
-                                    j++;
-                                    ej = ejn;
+                                while ((en & 0xFFFFu) <= o + filled && i < 95u) {  // runs that end before the next byte
+                                    i++;
+                                    e = en;
+                                    en = rt[i + 1];
+                                }
+                                const U256 ld = lds_unaligned32(win, (int)(e >> 16) + (int)o - (int)(e & 0xFFFFu));
+                                v = merge_low32(v, ld, filled);
+                                const uint32_t upto = (en & 0xFFFFu) - o;  // bytes of the sector known after this run
+                                if (upto >= 32u || (en & 0xFFFFu) >= round_out) {
+                                    stg256(gbase + o, v.w[0], v.w[1], v.w[2], v.w[3], v.w[4], v.w[5], v.w[6], v.w[7]);
+                                    o += 32u;
+                                    filled = 0;
+                                    act = o < oend;
+                                } else {
+                                    filled = upto;
                                 }
                             }
-                            stg256(gbase + o, v.w[0], v.w[1], v.w[2], v.w[3], v.w[4], v.w[5], v.w[6], v.w[7]);
                         }
+                    }
+                    if (emit) {
                         Group g;
                         g.sample = (uint16_t)sample;
                         g.len = (uint16_t)outlen;
