@@ -2,6 +2,7 @@
 // packing, operator launch sequences, result collection.  No CPU implementation of any operator
 // lives here: every operator enqueues the chunk-engine kernels of sk_kernels.cu.
 #include <cuda_runtime.h>
+#include <cmath>
 #include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -86,6 +87,8 @@ struct sk_ctx {
     int fast_geo = 1;   // lean-engine geometry: 0 = GeoS (8 KiB chunks), 1 = GeoM (16 KiB chunks, default); SK_FAST_GEO
     bool warp = true;   // warp engine (sk_warp.cu) for header-route demultiplex; SK_NO_WARP=1 disables
     uint32_t tile_lanes = GeoW::TILE_LANES;  // warp-engine tile = tile_lanes x 400 B; SK_TILE_LANES
+    bool tile_auto = true;   // tile_lanes follows the record size of the data (no SK_TILE_LANES override)
+    double rec_est = 0.0;    // bytes per record: peeked from the first batch, then measured by every operator
     bool fast = true;   // lean engine (sk_fast.cu) for trim / mask / header-route demultiplex; SK_NO_FAST=1 disables
     int cfg = 0;  // chunk-engine geometry: 0 = CfgA (16 KiB chunks, 4 warps), 1 = CfgB (32 KiB chunks, 8 warps)
 };
@@ -178,7 +181,10 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
     if (const char *e = getenv("SK_NO_FAST")) ctx->fast = atoi(e) == 0;
     if (const char *e = getenv("SK_FAST_GEO")) ctx->fast_geo = atoi(e) ? 1 : 0;
     if (const char *e = getenv("SK_NO_WARP")) ctx->warp = atoi(e) == 0;
-    if (const char *e = getenv("SK_TILE_LANES")) ctx->tile_lanes = (uint32_t)std::min(30, std::max(8, atoi(e)));
+    if (const char *e = getenv("SK_TILE_LANES")) {
+        ctx->tile_lanes = (uint32_t)std::min(30, std::max(8, atoi(e)));
+        ctx->tile_auto = false;
+    }
     auto fail = [&](int code) {
         g_create_error = ctx->err;
         sk_ctx_destroy(ctx);
@@ -706,6 +712,32 @@ extern "C" int sk_demultiplex(sk_ctx *ctx, uint32_t slot, const sk_demux_opts *o
     s->reran_general = false;
     return demux_enqueue(ctx, s, o, ctx->fast);
 }
+// The warp engine wants about 31 records in a tile (32 lanes, one round): tile = the largest whole number
+// of 400-byte lanes that holds at most 31.1 records of the size the data has, 29 lanes (11 600 B, 2x150 bp
+// reads) at most -- three lanes stay the overhang.  The size comes from the previous operator's outcome
+// (consumed bytes / records); before the first one, from the newlines of the first 64 KiB of mate 1.
+static int choose_tile_lanes(sk_ctx *ctx, Slot *s) {
+    if (!ctx->tile_auto) return SK_OK;
+    if (ctx->rec_est <= 0.0 && s->in_len[SK_IN_R1]) {
+        const size_t n = (size_t)std::min<uint64_t>(s->in_len[SK_IN_R1], 64u << 10);
+        std::vector<uint8_t> head(n);
+        CK(cudaMemcpyAsync(head.data(), s->in[SK_IN_R1], n, cudaMemcpyDeviceToHost, s->stream));
+        CK(cudaStreamSynchronize(s->stream));
+        size_t lines = 0, last = 0;
+        for (size_t i = 0; i < n; i++)
+            if (head[i] == '\n') {
+                lines++;
+                if (lines % 4 == 0) last = i + 1;
+            }
+        if (lines >= 8) ctx->rec_est = (double)last / (double)(lines / 4);
+    }
+    if (ctx->rec_est > 0.0) {
+        const double lanes = 31.1 * ctx->rec_est / (double)GeoW::LANE_BYTES;
+        ctx->tile_lanes = (uint32_t)std::min<double>((double)GeoW::TILE_LANES, std::max(8.0, std::floor(lanes)));
+    }
+    return SK_OK;
+}
+
 static int demux_enqueue(sk_ctx *ctx, Slot *s, const sk_demux_opts *o, bool fast) {
     if (!ctx->have_sheet || !s->assign) {
         ctx->err = "sk_demultiplex: call sk_set_sheet first (and create the context with max_samples > 0)";
@@ -716,7 +748,9 @@ static int demux_enqueue(sk_ctx *ctx, Slot *s, const sk_demux_opts *o, bool fast
         return SK_E_INVALID;
     }
     if (o->fused_trim_min_baseq > 255) return SK_E_INVALID;
-    int rc = begin_op(ctx, s, OP_DEMUX1);
+    int rc = choose_tile_lanes(ctx, s);
+    if (rc) return rc;
+    rc = begin_op(ctx, s, OP_DEMUX1);
     if (rc) return rc;
     const uint32_t S = ctx->S;
     s->paired = s->in_len[SK_IN_R2] > 0;
@@ -838,6 +872,8 @@ extern "C" int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res) {
         flags |= h[i].flags;
     }
     res->n_records = h[SK_IN_R1].n_records;
+    if (h[SK_IN_R1].n_records >= 64 && h[SK_IN_R1].consumed)  // record size of this data, for the next tile choice
+        ctx->rec_est = (double)h[SK_IN_R1].consumed / (double)h[SK_IN_R1].n_records;
     res->gpu_launches = s->launches;
     res->reserved = (s->used_fast ? 1u : 0u) | (s->reran_general ? 2u : 0u);  // diagnostic: bit0 lean engine, bit1 re-run
     if (ctx->profiling)

@@ -36,6 +36,9 @@ extern __shared__ __align__(128) unsigned char sk_smem[];
 #ifndef SKW_LOCKSTEP
 #define SKW_LOCKSTEP 1  // 0: every warp takes its own tickets
 #endif
+#ifndef SKW_GROUP_WARPS
+#define SKW_GROUP_WARPS 8  // warps that take consecutive tiles and start them together (8 = the CTA, or 4)
+#endif
 
 namespace sk {
 
@@ -319,9 +322,13 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
             for (uint32_t i = tid; i < S; i += GeoW::NT) ccount[i] = 0;
         }
     }
-    if (tid == 0) {  // CTA ticket slots (below): 0 is never newer than a ticket
-        ((volatile uint32_t *)(sk_smem + WL::misc + 8))[0] = 0u;
-        ((volatile uint32_t *)(sk_smem + WL::misc + 8))[1] = 0u;
+    constexpr int GW = SKW_GROUP_WARPS;  // warps of a group; its first warp is the group's leader
+    static_assert(GW == 8 || GW == 4, "groups of 8 or 4 warps");
+    const bool g_lead = (tid % (GW * 32)) == 0;
+    const int wg = warp % GW;
+    if (g_lead) {  // the group's ticket slots (below): 0 is never newer than a ticket
+        ((volatile uint32_t *)(warea + WL::misc + 8))[0] = 0u;
+        ((volatile uint32_t *)(warea + WL::misc + 8))[1] = 0u;
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
@@ -372,17 +379,19 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
     // The warps of a CTA take eight consecutive tiles at a time and start them together: they then run
     // the same code at about the same time, which the SM's instruction cache needs (the kernel is larger
     // than that cache, and sixteen warps spread over it saturate the GPC-level instruction cache).
-    volatile uint32_t *cta_ticket = (volatile uint32_t *)(sk_smem + WL::misc + 8);  // two slots in warp 0's misc area
+    volatile uint32_t *cta_ticket =
+        (volatile uint32_t *)(sk_smem + (uint32_t)(warp - wg) * WL::per_warp + WL::misc + 8);  // two slots in the leader's misc area
     uint32_t cta_next = 0, flipk = 0;
     bool cta_have = false;
     for (;;) {
-        if (tid == 0) cta_ticket[flipk] = cta_have ? cta_next : atomicAdd(&st->ticket, (uint32_t)GeoW::WARPS);
+        if (g_lead) cta_ticket[flipk] = cta_have ? cta_next : atomicAdd(&st->ticket, (uint32_t)GW);
         cta_have = false;
-        __syncthreads();
+        if (GW == 8) __syncthreads();
+        else asm volatile("bar.sync %0, %1;" ::"r"(1 + warp / GW), "r"(GW * 32) : "memory");
         const uint32_t cb = cta_ticket[flipk];
         flipk ^= 1u;
         if (cb >= p.n_chunks) break;
-        c = cb + (uint32_t)warp;
+        c = cb + (uint32_t)wg;
         if (c >= p.n_chunks) {
 #if SKW_LOCKSTEP >= 2
             __syncthreads();  // the mid-tile meeting point below
@@ -675,8 +684,8 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 }
                 if (r0 + 32u >= nrec && lane == 0) {
 #if SKW_LOCKSTEP
-                    if (warp == 0) {
-                        cta_next = atomicAdd(&st->ticket, (uint32_t)GeoW::WARPS);
+                    if (wg == 0) {
+                        cta_next = atomicAdd(&st->ticket, (uint32_t)GW);
                         cta_have = true;
                     }
 #else
@@ -842,7 +851,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 // ---- emit
                 rbase = __shfl_sync(FULL, rbase, 0);
 #if SKW_LOCKSTEP
-                if (tid == 0 && cta_have) cta_ticket[flipk] = cta_next;  // the CTA's next ticket, for early loads
+                if (g_lead && cta_have) cta_ticket[flipk] = cta_next;  // the group's next ticket, for early loads
 #endif
                 bool writable = p.out != nullptr && round_out > 0;
                 if (writable && rbase + ((round_out + 31u) & ~31u) > p.out_cap) {
@@ -1007,8 +1016,8 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
         (void)have_next;
         {  // the CTA's next ticket may be known already (tickets only grow): start the next load now
             const uint32_t v = cta_ticket[flipk];
-            if (v > cb && v + (uint32_t)warp < p.n_chunks) {
-                issue_load(v + (uint32_t)warp);
+            if (v > cb && v + (uint32_t)wg < p.n_chunks) {
+                issue_load(v + (uint32_t)wg);
                 early = true;
             }
         }

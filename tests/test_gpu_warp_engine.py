@@ -110,16 +110,39 @@ def test_plus_lines_and_tiny_records(eng, O):
     _both(eng, O, sheet, b"".join(x for x, _ in mix), b"".join(y for _, y in mix), "tiny-in-between")
 
 
-def test_tiles_of_several_rounds_and_dense_tiles(eng, O):
-    """~150-byte records: three rounds of 32 per tile; ~60-byte records: more than 128 per tile, the engine
-    gives the tile up and the operator is re-run on the general engine (sk_result.reserved == 2)."""
+def test_tiles_of_several_rounds_and_dense_tiles(O, monkeypatch):
+    """With the tile pinned at 29 lanes: ~150-byte records make three rounds of 32 per tile; ~80-byte records
+    are more than 128 per tile, the engine gives the tile up and the operator is re-run on the general
+    engine (sk_result.reserved == 2)."""
+    from seqkit_b200 import Engine
+    monkeypatch.setenv("SK_TILE_LANES", "29")
     sheet, bcs = G.make_sheet(24, 32, 8, umi=0)
-    r1, r2 = _reads(8, 20000, bcs, read_len=(40, 60))
-    _both(eng, O, sheet, r1, r2, "multi-round")
-    rng = random.Random(9)
-    recs = [b"@r BC:%s\n%s\n+\n%s\n" % (rng.choice(bcs), G.rand_seq(rng, 30), b"I" * 30) for _ in range(30000)]
-    data = b"".join(recs)
-    _both(eng, O, sheet, data, data, "dense", want_engine=2)
+    with Engine(max_stream_bytes=16 << 20, max_records=1 << 17, max_samples=64) as e:
+        r1, r2 = _reads(8, 20000, bcs, read_len=(40, 60))
+        _both(e, O, sheet, r1, r2, "multi-round")
+        rng = random.Random(9)
+        recs = [b"@r BC:%s\n%s\n+\n%s\n" % (rng.choice(bcs), G.rand_seq(rng, 30), b"I" * 30) for _ in range(30000)]
+        data = b"".join(recs)
+        _both(e, O, sheet, data, data, "dense", want_engine=2)
+
+
+def test_tile_size_follows_the_record_size(O):
+    """Without SK_TILE_LANES the tile is sized for about 31 records of the data at hand (sk_api.cu:
+    choose_tile_lanes): 60 bp reads get a smaller tile than 150 bp reads, both stay on the warp engine in
+    one round per tile, and a change of record size between calls is picked up."""
+    from seqkit_b200 import Engine
+    assert "SK_TILE_LANES" not in os.environ
+    sheet, bcs = G.make_sheet(28, 24, 8, umi=4)
+    with Engine(max_stream_bytes=16 << 20, max_records=1 << 16, max_samples=64) as e:
+        tiles = {}
+        for label, rl in (("short", (60, 60)), ("long", (150, 150)), ("short-again", (60, 60))):
+            r1, r2 = _reads(13, 8000, bcs, read_len=rl)
+            for _ in range(2):  # the second call has the first one's measured record size
+                _both(e, O, sheet, r1, r2, label)
+            tile = len(r1) / (e.last_result.n_chunks[0] / 4.0)  # bytes per tile (4 slice-table rows each)
+            tiles[label] = tile / (len(r1) / 8000.0)              # records per tile
+        # a whole number of 400-byte lanes that holds at most 31.1 records, never more than 29 lanes
+        assert all(28.0 < v <= 31.2 for v in tiles.values()), tiles
 
 
 def test_ragged_ends(eng, O):
@@ -151,3 +174,19 @@ def test_lean_engine_still_available(O, monkeypatch):
     r1, r2 = _reads(12, 6000, bcs)
     with Engine(max_stream_bytes=16 << 20, max_records=1 << 16, max_samples=64) as e:
         _both(e, O, sheet, r1, r2, "lean")
+
+
+def test_shards_concatenate_to_the_single_stream_output(eng, O):
+    """SURVEY 8e on one GPU: the job cut into contiguous record ranges (seqkit_b200/shard.py), each range
+    demultiplexed on its own, files appended in range order and counters summed = the whole job at once."""
+    from seqkit_b200 import shard
+    sheet, bcs = G.make_sheet(29, 24, 8, umi=4)
+    r1, r2 = _reads(14, 9000, bcs)
+    whole = eng.demultiplex(sheet, r1, r2, fused_trim=20)
+    parts = [eng.demultiplex(sheet, a, b, fused_trim=20) for a, b in zip(shard.split_records(r1, 3), shard.split_records(r2, 3))]
+    assert all(p["exit_code"] == 0 for p in parts) and whole["exit_code"] == 0
+    assert shard.merge_files([p["files"] for p in parts]) == whole["files"]
+    assert [sum(c) for c in zip(*[p["counts"] for p in parts])] == whole["counts"]
+    assert sum(p["total"] for p in parts) == whole["total"] and sum(p["identified"] for p in parts) == whole["identified"]
+    want = O.demultiplex(sheet, O.trim_by_quality(r1, 20)[1], O.trim_by_quality(r2, 20)[1])
+    assert whole["files"] == want["files"] and whole["counts"] == want["counts"]
