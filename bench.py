@@ -352,6 +352,26 @@ def main():
                 "step_bytes": sum(bytes_pass), "step_achieved": sum(bytes_pass) / (ms_step * 1e-3) / 1e9}
     identified = counts[N_SAMPLES + 1]
     out_bytes = [int(res.out_bytes[0]), int(res.out_bytes[1])]
+    # the path's other two operators on the same resident mate-1 stream (BASELINE configs[0] / [1] shapes):
+    # device time per launch and algorithmic bytes (input once + output once), for the record
+    if rank == 0:
+        lib.sk_set_profiling(eng.ctx, 1)
+        other = {}
+        for name, fn in (("trim_by_quality", lib.sk_trim_by_quality), ("mask_by_quality", lib.sk_mask_by_quality)):
+            ms, ob = 0.0, 0
+            reps = 5
+            for i in range(reps + 1):
+                assert fn(eng.ctx, 0, MIN_BASEQ, 0) == 0, lib.sk_last_error(eng.ctx)
+                r = eng.wait()
+                assert r.status == 0 and r.n_records == P, (name, r.status, r.n_records)
+                if i:
+                    ms += r.pass_ms[0] / reps
+                    ob = int(r.out_bytes[0])
+            other[name] = {"kernel": "sk_fast_kernel<GeoM, OP_%s>" % ("TRIM" if name.startswith("trim") else "MASK"),
+                           "reads_per_launch": P, "ms_per_launch": ms, "algorithmic_bytes_per_launch": n1 + ob,
+                           "achieved": (n1 + ob) / (ms * 1e-3) / 1e9, "frac": (n1 + ob) / (ms * 1e-3) / 1e9 / peak}
+        lib.sk_set_profiling(eng.ctx, 0)
+        roofline["other_ops"] = other
     eng.close()
 
     # ---- e2e: host buffers through the C ABI, 3 slots in flight
