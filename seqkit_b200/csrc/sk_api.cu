@@ -86,6 +86,8 @@ struct sk_ctx {
     bool fast_sheet = false;  // the sheet's FastIdx is usable
     int fast_geo = 1;   // lean-engine geometry: 0 = GeoS (8 KiB chunks), 1 = GeoM (16 KiB chunks, default); SK_FAST_GEO
     bool warp = true;   // warp engine (sk_warp.cu) for header-route demultiplex; SK_NO_WARP=1 disables
+    bool warp_stream = false;  // warp engine for trim / mask as well (SK_WARP_STREAM=1): correct, but its second
+                               // look-back (output bytes, known only after the plan) makes it slower than the lean engine
     uint32_t tile_lanes = GeoW::TILE_LANES;  // warp-engine tile = tile_lanes x 400 B; SK_TILE_LANES
     bool tile_auto = true;   // tile_lanes follows the record size of the data (no SK_TILE_LANES override)
     double rec_est = 0.0;    // bytes per record: peeked from the first batch, then measured by every operator
@@ -181,6 +183,7 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
     if (const char *e = getenv("SK_NO_FAST")) ctx->fast = atoi(e) == 0;
     if (const char *e = getenv("SK_FAST_GEO")) ctx->fast_geo = atoi(e) ? 1 : 0;
     if (const char *e = getenv("SK_NO_WARP")) ctx->warp = atoi(e) == 0;
+    if (const char *e = getenv("SK_WARP_STREAM")) ctx->warp_stream = atoi(e) != 0;
     if (const char *e = getenv("SK_TILE_LANES")) {
         ctx->tile_lanes = (uint32_t)std::min(30, std::max(8, atoi(e)));
         ctx->tile_auto = false;
@@ -592,7 +595,8 @@ static int run_pass(sk_ctx *ctx, Slot *s, int which, int op, const KParams &p, b
     if (p.n_chunks == 0) return SK_OK;
     // look-back words (the warp engine keeps 8 + 2 bytes per tile, sk_warp.cu:wlb_agg)
     CK(cudaMemsetAsync(p.tile_lines, 0, eng == ENG_WARP ? (uint64_t)p.n_chunks * 10 + 64 : (uint64_t)p.n_chunks * 8, s->stream));
-    if (ordered_out) CK(cudaMemsetAsync(p.tile_out, 0, (uint64_t)p.n_chunks * 8, s->stream));
+    if (ordered_out)
+        CK(cudaMemsetAsync(p.tile_out, 0, eng == ENG_WARP ? (uint64_t)p.n_chunks * 10 + 64 : (uint64_t)p.n_chunks * 8, s->stream));
     const char *err = nullptr;
     if (ctx->profiling) CK(cudaEventRecord(s->ev[which][0], s->stream));
     int rc = eng == ENG_WARP   ? launch_warp_kernel(op, p, ctx->sm_count, s->stream, &err)
@@ -613,26 +617,35 @@ static int end_op(sk_ctx *ctx, Slot *s) {
     return SK_OK;
 }
 
+static int choose_tile_lanes(sk_ctx *ctx, Slot *s);
 static int stream_op_enqueue(sk_ctx *ctx, Slot *s, int op, uint32_t min_baseq, uint64_t rec_limit, bool fast) {
-    int rc = begin_op(ctx, s, op);
+    int rc = (op == OP_TRIM || op == OP_MASK) ? choose_tile_lanes(ctx, s) : SK_OK;
+    if (rc) return rc;
+    rc = begin_op(ctx, s, op);
     if (rc) return rc;
     KParams p;
-    auto fill = [&](bool f) {
-        base_params(ctx, s, SK_IN_R1, p, f ? ENG_LEAN : ENG_GENERAL);
+    int eng = fast ? ((ctx->warp && ctx->warp_stream) ? ENG_WARP : ENG_LEAN) : ENG_GENERAL;
+    auto fill = [&](int e) {
+        base_params(ctx, s, SK_IN_R1, p, e);
         p.min_baseq = min_baseq;
         p.rec_limit = rec_limit ? rec_limit : ~0ull;
         p.out = s->out[0];
         p.out_cap = s->out_cap;
     };
-    fill(fast);
-    if (fast && !fast_supported(ctx->fast_geo, op, p)) {
-        fast = false;
-        fill(false);
+    fill(eng);
+    if (eng == ENG_WARP && !warp_supported(op, p)) {
+        eng = ENG_LEAN;
+        fill(eng);
     }
+    if (eng == ENG_LEAN && !fast_supported(ctx->fast_geo, op, p)) {
+        eng = ENG_GENERAL;
+        fill(eng);
+    }
+    fast = eng != ENG_GENERAL;
     s->used_fast = fast;
     s->req_min_baseq = min_baseq;
     s->req_rec_limit = rec_limit;
-    rc = run_pass(ctx, s, SK_IN_R1, op, p, true, fast ? ENG_LEAN : ENG_GENERAL);
+    rc = run_pass(ctx, s, SK_IN_R1, op, p, true, eng);
     if (rc) return rc;
     return end_op(ctx, s);
 }

@@ -1,5 +1,6 @@
 // sk_warp.cu -- the warp engine: header-route demultiplex (mate 1 / mate 2, with or without the fused
-// quality trim) with one warp per tile and one lane per record.
+// quality trim), trim by quality and mask by quality, with one warp per tile and one lane per record
+// (DESIGN.md section 3.0).
 //
 // The lean engine (sk_fast.cu) spends a third of its warp time at CTA barriers: its per-record phase
 // runs one lane per record on the few warps a 16 KiB chunk fills, while the other warps of the CTA
@@ -288,7 +289,8 @@ static __device__ __noinline__ uint64_t wlb_consume(uint64_t *inc, const uint16_
 template <int OP, int NWMAX>
 __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const __grid_constant__ KParams p) {
     constexpr bool D1 = OP == OP_DEMUX1;
-    static_assert(OP == OP_DEMUX1 || OP == OP_DEMUX2, "warp engine: demultiplex passes");
+    constexpr bool IS_DEMUX = OP == OP_DEMUX1 || OP == OP_DEMUX2;  // else OP_TRIM / OP_MASK: one output stream, input order
+    static_assert(IS_DEMUX || OP == OP_TRIM || OP == OP_MASK, "warp engine: demultiplex passes, trim, mask");
     constexpr int UPL = GeoW::UPL, LANE_BYTES = GeoW::LANE_BYTES, WIN = GeoW::WIN;
     constexpr int MAXREC = GeoW::MAXREC, MAXLINES = GeoW::MAXLINES;
     constexpr uint32_t FULL = 0xffffffffu;
@@ -309,11 +311,13 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
     DevStats *st = p.stats;
 
     if (lane == 0) mbar_init(mbar, 1);
+    if (IS_DEMUX) {
 #pragma unroll 1
-    for (uint32_t i = tid; i < 256; i += GeoW::NT) sh_lut[i] = p.sheet.lut[i];
+        for (uint32_t i = tid; i < 256; i += GeoW::NT) sh_lut[i] = p.sheet.lut[i];
 #pragma unroll 1
-    for (uint32_t i = tid; i < S; i += GeoW::NT)
-        sh_ulen[i] = (uint8_t)(p.sheet.wide ? __popcll(((const unsigned long long *)p.sheet.umask)[i]) : __popc(p.sheet.umask[i]));
+        for (uint32_t i = tid; i < S; i += GeoW::NT)
+            sh_ulen[i] = (uint8_t)(p.sheet.wide ? __popcll(((const unsigned long long *)p.sheet.umask)[i]) : __popc(p.sheet.umask[i]));
+    }
     if (D1) {
 #pragma unroll 1
         for (uint32_t i = tid; i < hcls_words; i += GeoW::NT) hcls[i] = p.sheet.hidx.cls[i];
@@ -335,11 +339,12 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
 
     const uint32_t tile_lanes = p.tile_lanes;
     const uint32_t TILE = tile_lanes * (uint32_t)LANE_BYTES;
-    const bool fused = p.fused_trim >= 0;
-    const int trim_q = p.fused_trim;
+    const bool fused = IS_DEMUX && p.fused_trim >= 0;
+    const int trim_q = IS_DEMUX ? p.fused_trim : (int)p.min_baseq;
+    uint16_t *oagg16 = wlb_agg(p.tile_out, p.n_chunks);  // trim / mask: second look-back, on output bytes
     const uint32_t Lb = p.sheet.L;
     uint16_t *agg16 = wlb_agg(p.tile_lines, p.n_chunks);
-    const unsigned long long r1_nrec = D1 ? 0ull : p.r1_stats->n_records;  // mate 2: records of the mate-1 pass
+    const unsigned long long r1_nrec = (D1 || !IS_DEMUX) ? 0ull : p.r1_stats->n_records;  // mate 2: records of the mate-1 pass
     uint32_t parity = 0;
     uint32_t my_total = 0, my_ident = 0;   // DEMUX1 counters of this lane's records
     unsigned long long my_out = 0;         // lane 0: payload bytes of this warp's tiles
@@ -521,6 +526,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
 
         uint32_t nrec = 0, c_next = 0;
         bool bail = false, have_next = false;
+        bool out_done = false;  // trim / mask: this tile's output bytes are in the second look-back
         for (;;) {  // repeated only when the guess was wrong
             nrec = j0 < nls_own ? (nls_own - 1 - j0) / 4u + 1u : 0u;
             if (!spec) {
@@ -551,6 +557,63 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 if (bail) nrec = 0;
             }
 
+            // trim / mask by quality for one record per lane (fasta_trim_by_quality.rs:19-48,
+            // fasta_mask_by_quality.rs:20-45): returns the record's output length, failure kind in errk
+            auto stream_plan = [&](bool has, uint32_t L0, uint32_t L1, uint32_t L2, uint32_t L3, uint32_t L4, uint8_t &mode,
+                                   uint32_t &kk, uint32_t &errk) -> uint32_t {
+                uint32_t slen = 0;
+                errk = 0;
+                mode = B_NONE;
+                if (OP == OP_TRIM) {
+                    bool ok = has;
+                    if (has && win[L0] != '@') {  // :20-22
+                        errk = K_BAD_HEADER;
+                        ok = false;
+                    }
+                    bool fine = true;
+                    uint32_t body = 0;
+                    if (trim_q <= 222) {
+                        fine = plan_trim_lane16(win, ok, L1, L2, L3, L4, trim_q, mode, kk, body);
+                    } else {
+                        if (ok) {
+                            const uint32_t pk = plan_trim_cold(win, L1, L2, L3, L4, trim_q);
+                            kk = pk & 0xFFFFu;
+                            mode = (uint8_t)(pk >> 16);
+                            fine = (pk >> 24) != 0u;
+                            body = mode == B_GARBAGE ? 6u : 2u * kk + 4u;
+                        }
+                        __syncwarp();
+                    }
+                    if (!ok) {
+                        mode = B_NONE;
+                    } else if (!fine) {  // &seq[..k] would panic (:47)
+                        errk = K_SEQ_SHORT;
+                        mode = B_NONE;
+                    } else {
+                        slen = (L1 - L0) + body;  // header verbatim (:23) + body
+                    }
+                }
+                if (OP == OP_MASK && has) {
+                    if (win[L0] != '@') {  // fasta_mask_by_quality.rs:21-23
+                        errk = K_BAD_HEADER;
+                    } else {
+                        uint32_t sl = L2 - L1, ql = L4 - L3;
+                        if (sl && win[L2 - 1] == '\n') sl--;  // :32
+                        if (ql && win[L4 - 1] == '\n') ql--;  // :33
+                        if (sl != ql) {                       // :35-37
+                            errk = K_LEN_MISMATCH;
+                        } else {
+                            mode = B_MASK;
+                            kk = sl;
+                            slen = (L1 - L0) + 2u * sl + 4u;  // header, masked, "\n+\n", qual, "\n"  (:26,:44)
+                        }
+                    }
+                }
+                return slen;
+            };
+            uint64_t s_obase = 0;   // trim / mask: the tile's place in the output stream ...
+            uint32_t s_done = 0;    // ... and the bytes its earlier rounds have written
+            bool s_writable = false;
             bool wrong = false;
             uint64_t rec0 = 0;
             for (uint32_t r0 = 0; r0 < nrec; r0 += 32u) {
@@ -584,10 +647,14 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                     }
                     if (!ok || !fine) mode = B_FAIL;
                 }
+                // trim / mask by quality: failure kind in errk, output length in slen
+                uint32_t errk = 0, slen = 0;
+                if (!IS_DEMUX) slen = stream_plan(has, L0, L1, L2, L3, L4, mode, kk, errk);
                 int sample = -1;
                 unsigned long long um = 0;  // positions where the sample's sheet barcode has 'U'
                 uint32_t alen = 0, blen = 0, cut0 = 0, cut1 = 0, taglen = 0xFFu;
-                if (D1) {
+                if (!IS_DEMUX) {
+                } else if (D1) {
                     // fasta_demultiplex.rs:117-194: validate, locate the barcode, match, decide.  Outcome:
                     // sample >= 0 assigned; -2 ambiguous (best, last, mismatches in alen, blen, taglen);
                     // -1 unassigned (taglen = failure kind, or 0xFF for a record that never reached the match)
@@ -672,6 +739,128 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 }
                 rec0 = (g0 + j0) >> 2;
                 const uint64_t rec = rec0 + r;
+                if (!IS_DEMUX) {
+                    // ---- trim / mask: one output stream in input order.  The tile's output bytes go through a
+                    // second look-back (p.tile_out) to its place in the stream; a record is patched in place
+                    // into two runs of the window -- header + bases + "\n+\n", qualities + "\n" -- and copied.
+                    if (r0 + 32u >= nrec && lane == 0) {
+#if SKW_LOCKSTEP
+                        if (wg == 0) {
+                            cta_next = atomicAdd(&st->ticket, (uint32_t)GW);
+                            cta_have = true;
+                        }
+#else
+                        c_next = atomicAdd(&st->ticket, 1u);
+                        have_next = true;
+#endif
+                    }
+                    if (has && errk) report_err(st, rec, errk);
+                    uint32_t oincl = slen;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const uint32_t y = __shfl_up_sync(FULL, oincl, o);
+                        if (lane >= o) oincl += y;
+                    }
+                    const uint32_t round_outb = __shfl_sync(FULL, oincl, 31);
+                    const uint32_t my_off = s_done + oincl - slen;
+                    uint32_t tile_outb = round_outb;
+                    if (r0 == 0) {
+                        // the look-back wants the whole tile's output: a tile of several rounds (short or uneven
+                        // records) plans its later rounds twice, once here for their lengths only
+#pragma unroll 1
+                        for (uint32_t rr = 32u; rr < nrec; rr += 32u) {
+                            const bool has2 = rr + (uint32_t)lane < nrec;
+                            const uint32_t j2 = j0 + (has2 ? rr + (uint32_t)lane : 0u) * 4u;
+                            uint8_t m2;
+                            uint32_t k2 = 0, e2 = 0;
+                            const uint32_t l2 = stream_plan(has2, LB(j2), LB(j2 + 1), LB(j2 + 2), LB(j2 + 3), LB(j2 + 4), m2, k2, e2);
+                            tile_outb += __reduce_add_sync(FULL, l2);
+                        }
+                        if (lane == 0) wlb_publish(oagg16, c, tile_outb);
+                    }
+                    // patches (and the mask itself, in place) while the predecessors' counts arrive
+                    uint32_t run1 = 0, run2 = 0;
+                    bool slow = false;
+                    if (slen && p.out) {
+                        if (mode == B_MASK) {
+                            if (L1 + kk + 3u <= L3) {
+                                mask_copy(win + L1, win + L1, win + L3, kk, p.min_baseq);  // :40-43, in place
+                                uint8_t *d = win + L1 + kk;
+                                d[0] = '\n'; d[1] = '+'; d[2] = '\n';
+                                win[L3 + kk] = '\n';
+                                run1 = (L1 - L0) + kk + 3u;
+                                run2 = kk + 1u;
+                            } else {
+                                slow = true;
+                            }
+                        } else if (mode == B_TRIM) {
+                            if (L1 + kk + 3u <= L3) {
+                                uint8_t *d = win + L1 + kk;
+                                d[0] = '\n'; d[1] = '+'; d[2] = '\n';
+                                win[L3 + kk] = '\n';
+                                run1 = (L1 - L0) + kk + 3u;
+                                run2 = kk + 1u;
+                            } else {
+                                slow = true;
+                            }
+                        } else {  // B_GARBAGE (:44-45)
+                            if (L1 + 6u <= L4) {
+                                uint8_t *d = win + L1;
+                                d[0] = 'N'; d[1] = '\n'; d[2] = '+'; d[3] = '\n'; d[4] = '!'; d[5] = '\n';
+                                run1 = (L1 - L0) + 6u;
+                            } else {
+                                slow = true;
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    if (r0 == 0) {
+                        s_obase = wlb_consume(p.tile_out, oagg16, c, tile_outb, lane);
+                        out_done = true;
+                        if (lane == 0 && c == p.n_chunks - 1) {
+                            st->out_bytes = s_obase + tile_outb;
+                            st->out_extent = s_obase + tile_outb;
+                        }
+                        s_writable = p.out != nullptr && tile_outb > 0;
+                        if (s_writable && s_obase + tile_outb > p.out_cap) {
+                            if (lane == 0) report_err(st, rec0, K_OUT_OVERFLOW);
+                            s_writable = false;
+                        }
+                    }
+#if SKW_LOCKSTEP
+                    if (g_lead && cta_have) cta_ticket[flipk] = cta_next;  // the group's next ticket, for early loads
+#endif
+                    s_done += round_outb;
+                    if (s_writable) {
+                        uint8_t *gd = p.out + s_obase + my_off;
+#pragma unroll 1
+                        for (int q = 0; q < 2; q++) {
+                            gcopy(q == 0 ? gd : gd + run1, win, q == 0 ? L0 : L3, q == 0 ? run1 : run2);
+                            __syncwarp();
+                        }
+                        if (slow) {  // rare: a '+' line too short to hold the patch, a record cut off by the end of the stream
+                            uint8_t *d = gd;
+#pragma unroll 1
+                            for (uint32_t i = L0; i < L1; i++) *d++ = win[i];
+                            if (mode == B_GARBAGE) {
+                                d[0] = 'N'; d[1] = '\n'; d[2] = '+'; d[3] = '\n'; d[4] = '!'; d[5] = '\n';
+                            } else {
+#pragma unroll 1
+                                for (uint32_t i = 0; i < kk; i++) {
+                                    const uint8_t sq = win[L1 + i];
+                                    *d++ = (mode == B_MASK && (uint8_t)(win[L3 + i] - 33u) < p.min_baseq) ? (uint8_t)'N' : sq;
+                                }
+                                d[0] = '\n'; d[1] = '+'; d[2] = '\n';
+                                d += 3;
+#pragma unroll 1
+                                for (uint32_t i = 0; i < kk; i++) *d++ = win[L3 + i];
+                                *d = '\n';
+                            }
+                        }
+                    }
+                    __syncwarp();
+                    continue;
+                }
 
                 // ---- loads whose results are needed further down go out first: mate 2 reads the pair's
                 // sample and UMI from mate 1's tables; the last round takes the warp's next ticket
@@ -988,7 +1177,15 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
             break;
         }
         if (bail && lane == 0) atomicOr(&st->flags, F_NEED_GENERAL);
-        if (p.out) {  // rows of the rounds that did not run
+        if (!IS_DEMUX && !out_done) {  // a tile without a round still owes its (empty) output to the look-back
+            if (lane == 0) wlb_publish(oagg16, c, 0u);
+            const uint64_t obase = wlb_consume(p.tile_out, oagg16, c, 0u, lane);
+            if (lane == 0 && c == p.n_chunks - 1) {
+                st->out_bytes = obase;
+                st->out_extent = obase;
+            }
+        }
+        if (IS_DEMUX && p.out) {  // rows of the rounds that did not run
             const uint32_t ran = (nrec + 31u) >> 5;
             if ((uint32_t)lane < (uint32_t)GeoW::ROUNDS && (uint32_t)lane >= ran) {
                 ChunkRow row;
@@ -1057,8 +1254,10 @@ static uint32_t warp_smem(uint32_t S, uint32_t n_classes, uint32_t nwp, bool d1)
 }
 
 bool warp_supported(int op, const KParams &p) {
+    if (p.lpr != 4 || p.tile_lanes < 8 || p.tile_lanes > 30) return false;
+    if (op == OP_TRIM || op == OP_MASK) return true;
     if (op != OP_DEMUX1 && op != OP_DEMUX2) return false;
-    if (p.lpr != 4 || p.n_index || !p.sheet.hidx.n_classes || !p.sheet.fidx.table) return false;
+    if (p.n_index || !p.sheet.hidx.n_classes || !p.sheet.fidx.table) return false;
     if (p.tile_lanes < 8 || p.tile_lanes > 30) return false;
     return warp_smem(p.sheet.S, p.sheet.hidx.n_classes, p.sheet.hidx.nwp, true) <= 115200u;
 }
@@ -1066,7 +1265,8 @@ bool warp_supported(int op, const KParams &p) {
 template <int OP, int NWMAX>
 static int launch_warp_one(const KParams &p, int sm_count, cudaStream_t stream, const char **err) {
     auto kfn = sk_warp_kernel<OP, NWMAX>;
-    const int smem = (int)warp_smem(p.sheet.S, p.sheet.hidx.n_classes, p.sheet.hidx.nwp, OP == OP_DEMUX1);
+    const bool stream_op = OP == OP_TRIM || OP == OP_MASK;  // no sheet tables
+    const int smem = (int)warp_smem(stream_op ? 0u : p.sheet.S, stream_op ? 0u : p.sheet.hidx.n_classes, p.sheet.hidx.nwp, OP == OP_DEMUX1);
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
         *err = cudaGetErrorString(e);
@@ -1100,6 +1300,8 @@ int launch_warp_kernel(int op, const KParams &p, int sm_count, void *stream_, co
             return wide ? launch_warp_one<OP_DEMUX1, 16>(p, sm_count, stream, err)
                         : launch_warp_one<OP_DEMUX1, 8>(p, sm_count, stream, err);
         case OP_DEMUX2: return launch_warp_one<OP_DEMUX2, 8>(p, sm_count, stream, err);
+        case OP_TRIM: return launch_warp_one<OP_TRIM, 8>(p, sm_count, stream, err);
+        case OP_MASK: return launch_warp_one<OP_MASK, 8>(p, sm_count, stream, err);
     }
     *err = "operator not handled by the warp engine";
     return -1;

@@ -190,3 +190,28 @@ def test_shards_concatenate_to_the_single_stream_output(eng, O):
     assert sum(p["total"] for p in parts) == whole["total"] and sum(p["identified"] for p in parts) == whole["identified"]
     want = O.demultiplex(sheet, O.trim_by_quality(r1, 20)[1], O.trim_by_quality(r2, 20)[1])
     assert whole["files"] == want["files"] and whole["counts"] == want["counts"]
+
+
+def test_trim_and_mask_on_the_warp_engine(O, monkeypatch):
+    """SK_WARP_STREAM=1: trim / mask by quality through the warp engine (second look-back on output bytes,
+    in-place mask, two runs per record).  Off by default -- the lean engine is faster for these two -- but
+    the bytes must be the oracle's: regular data, uneven record sizes (tiles of several rounds), every
+    nasty record shape, failing records (the host replays the records before them)."""
+    from seqkit_b200 import Engine
+    monkeypatch.setenv("SK_WARP_STREAM", "1")
+    with Engine(max_stream_bytes=16 << 20, max_records=1 << 17, max_samples=64) as e:
+        blobs = [("decay", G.clean_fastq(41, 9000, read_len=(150, 150))), ("uneven", G.clean_fastq(42, 12000, read_len=(20, 160), qual_style="mix")),
+                 ("short", G.clean_fastq(43, 20000, read_len=(30, 40), qual_style="bad"))]
+        blobs += [("nasty%d" % k, G.nasty_fastq(50 + k, 1500)) for k in range(6)]
+        blobs += [("ragged", G.clean_fastq(44, 500)[:-9]), ("empty", b""), ("one", b"@r\nACGT\n+\nII#I\n"), ("blank", G.clean_fastq(45, 300) + b"\n")]
+        for label, blob in blobs:
+            for q in (20, 0, 2, 41, 255):
+                got, want = e.trim_by_quality(blob, q), O.trim_by_quality(blob, q)
+                assert got[0] == want[0] and got[1] == want[1], ("trim", label, q)
+                if got[0] != 101:
+                    assert got[2] == want[2], ("trim", label, q)
+                got, want = e.mask_by_quality(blob, q), O.mask_by_quality(blob, q)
+                assert got[0] == want[0] and got[1] == want[1], ("mask", label, q)
+                if got[0] != 101:
+                    assert got[2] == want[2], ("mask", label, q)
+        assert e.last_result.reserved in (1, 2)
