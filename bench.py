@@ -367,7 +367,11 @@ def main():
                 if i:
                     ms += r.pass_ms[0] / reps
                     ob = int(r.out_bytes[0])
-            other[name] = {"kernel": "sk_fast_kernel<GeoM, OP_%s>" % ("TRIM" if name.startswith("trim") else "MASK"),
+                    eng_bits = int(r.reserved)  # 1: lean (or warp) engine, 2: re-run on the general engine
+            opn = "TRIM" if name.startswith("trim") else "MASK"
+            ws = os.environ.get("SK_WARP_STREAM")  # default: mask on the warp engine, trim on the lean engine
+            on_warp = os.environ.get("SK_NO_WARP", "0") in ("", "0") and ((ws is None and opn == "MASK") or (ws not in (None, "", "0")))
+            other[name] = {"kernel": ("sk_warp_kernel<OP_%s>" if on_warp else "sk_fast_kernel<GeoM, OP_%s>") % opn, "engine_bits": eng_bits,
                            "reads_per_launch": P, "ms_per_launch": ms, "algorithmic_bytes_per_launch": n1 + ob,
                            "achieved": (n1 + ob) / (ms * 1e-3) / 1e9, "frac": (n1 + ob) / (ms * 1e-3) / 1e9 / peak}
         lib.sk_set_profiling(eng.ctx, 0)

@@ -743,17 +743,8 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                     // ---- trim / mask: one output stream in input order.  The tile's output bytes go through a
                     // second look-back (p.tile_out) to its place in the stream; a record is patched in place
                     // into two runs of the window -- header + bases + "\n+\n", qualities + "\n" -- and copied.
-                    if (r0 + 32u >= nrec && lane == 0) {
-#if SKW_LOCKSTEP
-                        if (wg == 0) {
-                            cta_next = atomicAdd(&st->ticket, (uint32_t)GW);
-                            cta_have = true;
-                        }
-#else
-                        c_next = atomicAdd(&st->ticket, 1u);
-                        have_next = true;
-#endif
-                    }
+                    // (no early ticket here: a tile's output bytes are published only after its plan and every
+                    // later tile waits for them before it writes, so tickets must be taken when tiles start)
                     if (has && errk) report_err(st, rec, errk);
                     uint32_t oincl = slen;
 #pragma unroll

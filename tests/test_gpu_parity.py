@@ -254,11 +254,19 @@ def _bc_headers(data, bcs, seed):
     return b"\n".join(out)
 
 
-def test_lean_engine_is_the_default_and_reruns_beyond_its_limits(eng, O):
-    """Trim, mask and header-route demultiplex run on the lean engine (sk_fast.cu).  Records of ~5.5 KB
-    are longer than its overhang (4160 B) but inside the general engine's (6128 B): as soon as one of
-    them starts near the end of a lean chunk the operator is re-run on the general engine
-    (sk_result.reserved bit 1), and the bytes stay those of the oracle either way."""
+def test_lean_engine_is_the_default_and_reruns_beyond_its_limits(O, monkeypatch):
+    """Trim, mask and header-route demultiplex run on the lean / warp engines (sk_fast.cu, sk_warp.cu).
+    Records of ~5.5 KB are longer than their overhangs (4160 B; 1200 B with the warp engine's tile pinned
+    at 29 lanes) but inside the general engine's (6128 B): as soon as one of them starts near the end of a
+    chunk the operator is re-run on the general engine (sk_result.reserved bit 1), and the bytes stay
+    those of the oracle either way."""
+    from seqkit_b200 import Engine
+    monkeypatch.setenv("SK_TILE_LANES", "29")
+    with Engine(max_stream_bytes=48 << 20, max_records=1 << 18, max_samples=512) as eng:
+        _rerun_body(eng, O)
+
+
+def _rerun_body(eng, O):
     sheet, bcs = G.make_sheet(3, 24, 8, umi=4)
     data = G.clean_fastq(5, 3000, qual_style="decay")
     rng = random.Random(17)

@@ -193,10 +193,10 @@ def test_shards_concatenate_to_the_single_stream_output(eng, O):
 
 
 def test_trim_and_mask_on_the_warp_engine(O, monkeypatch):
-    """SK_WARP_STREAM=1: trim / mask by quality through the warp engine (second look-back on output bytes,
-    in-place mask, two runs per record).  Off by default -- the lean engine is faster for these two -- but
-    the bytes must be the oracle's: regular data, uneven record sizes (tiles of several rounds), every
-    nasty record shape, failing records (the host replays the records before them)."""
+    """SK_WARP_STREAM=1: trim and mask by quality through the warp engine (second look-back on output bytes,
+    in-place mask, two runs per record; by default only mask takes it).  The bytes must be the oracle's:
+    regular data, uneven record sizes (tiles of several rounds), every nasty record shape, failing records
+    (the host replays the records before them)."""
     from seqkit_b200 import Engine
     monkeypatch.setenv("SK_WARP_STREAM", "1")
     with Engine(max_stream_bytes=16 << 20, max_records=1 << 17, max_samples=64) as e:
