@@ -89,8 +89,8 @@ typedef struct sk_result {
     uint32_t n_chunks[2];           /* rows of the demux slice table per output stream */
     uint32_t n_events;              /* ambiguity events (fasta_demultiplex.rs:184-188) */
     uint32_t gpu_launches;          /* kernels this call enqueued */
-    uint32_t reserved;              /* diagnostic: bit0 = the lean engine (sk_fast.cu) ran, bit1 = the operator met
-                                       something outside its limits and was re-run on the general engine */
+    uint32_t reserved;              /* diagnostic: bit0 = the warp or lean engine (sk_warp.cu, sk_fast.cu) ran, bit1 = the
+                                       operator met something outside its limits and was re-run on the general engine */
     float pass_ms[SK_N_INPUTS];     /* device time of the chunk-engine kernel over each input stream
                                        (CUDA events on the slot's stream; only with sk_set_profiling) */
 } sk_result;
@@ -176,8 +176,9 @@ int sk_download_out(sk_ctx *ctx, uint32_t slot, uint32_t which, void *host, uint
 
 /* Demultiplex side tables (valid after sk_wait).  The kernels write the emitted records of a chunk back
  * to back as a sequence of *groups* -- runs of bytes that belong to one sample, in input order inside a
- * sample (the lean engine emits one group per record in input order; the general engine groups a
- * chunk's records by sample).  For output stream m, row c describes chunk c: its groups are
+ * sample (the warp and lean engines emit one group per record in input order -- the warp engine one row
+ * per round of 32 records, four rows per tile, unused ones empty; the general engine groups a chunk's
+ * records by sample).  For output stream m, row c describes chunk (or round) c: its groups are
  * groups[first_group .. first_group+n_groups), laid out back to back from byte `base` of output
  * stream m.  Appending, for every sample, its groups over c = 0..n_chunks-1 gives that sample's file
  * content in input order (fasta_demultiplex.rs:196-238). */
