@@ -380,34 +380,35 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
     bool early = false;  // the load of this tile was started at the end of the previous one
 
     uint32_t c = 0;
-#if SKW_LOCKSTEP
-    // The warps of a CTA take eight consecutive tiles at a time and start them together: they then run
-    // the same code at about the same time, which the SM's instruction cache needs (the kernel is larger
-    // than that cache, and sixteen warps spread over it saturate the GPC-level instruction cache).
+    // Demultiplex and trim: the warps of a CTA take eight consecutive tiles at a time and start them
+    // together: they then run the same code at about the same time, which the SM's instruction cache needs
+    // (the kernels are larger than that cache, and sixteen warps spread over them saturate the GPC-level
+    // instruction cache).  Mask (a small kernel whose tiles wait on each other's output sizes) runs faster
+    // with every warp on its own ticket, taken when the tile starts.
+    constexpr bool LS = SKW_LOCKSTEP && OP != OP_MASK;
     volatile uint32_t *cta_ticket =
         (volatile uint32_t *)(sk_smem + (uint32_t)(warp - wg) * WL::per_warp + WL::misc + 8);  // two slots in the leader's misc area
     uint32_t cta_next = 0, flipk = 0;
     bool cta_have = false;
+    if (!LS) {
+        if (lane == 0) c = atomicAdd(&st->ticket, 1u);
+        c = __shfl_sync(FULL, c, 0);
+    }
     for (;;) {
-        if (g_lead) cta_ticket[flipk] = cta_have ? cta_next : atomicAdd(&st->ticket, (uint32_t)GW);
-        cta_have = false;
-        if (GW == 8) __syncthreads();
-        else asm volatile("bar.sync %0, %1;" ::"r"(1 + warp / GW), "r"(GW * 32) : "memory");
-        const uint32_t cb = cta_ticket[flipk];
-        flipk ^= 1u;
-        if (cb >= p.n_chunks) break;
-        c = cb + (uint32_t)wg;
-        if (c >= p.n_chunks) {
-#if SKW_LOCKSTEP >= 2
-            __syncthreads();  // the mid-tile meeting point below
-#endif
-            continue;
+        uint32_t cb = 0;
+        if (LS) {
+            if (g_lead) cta_ticket[flipk] = cta_have ? cta_next : atomicAdd(&st->ticket, (uint32_t)GW);
+            cta_have = false;
+            if (GW == 8) __syncthreads();
+            else asm volatile("bar.sync %0, %1;" ::"r"(1 + warp / GW), "r"(GW * 32) : "memory");
+            cb = cta_ticket[flipk];
+            flipk ^= 1u;
+            if (cb >= p.n_chunks) break;
+            c = cb + (uint32_t)wg;
+            if (c >= p.n_chunks) continue;
+        } else if (c >= p.n_chunks) {
+            break;
         }
-#else
-    if (lane == 0) c = atomicAdd(&st->ticket, 1u);
-    c = __shfl_sync(FULL, c, 0);
-    while (c < p.n_chunks) {
-#endif
         const uint64_t c0 = (uint64_t)c * TILE;
         uint64_t wend = c0 + (uint64_t)WIN;
         if (wend > p.n) wend = p.n;
@@ -496,11 +497,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 if (k < (uint32_t)MAXLINES + 8u) ls[k] = (uint16_t)wlen;
             }
         }
-#if SKW_LOCKSTEP >= 2
-        __syncthreads();  // second meeting point of the CTA's warps (plain __syncwarp otherwise)
-#else
         __syncwarp();
-#endif
 
         // ---- framing.  Record i is lines 4i..4i+3 of the stream (common.rs:106-112): the tile needs the
         // global index g0 of its first line, i.e. the counts of every tile before it -- and the nearest of
@@ -818,9 +815,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                             s_writable = false;
                         }
                     }
-#if SKW_LOCKSTEP
-                    if (g_lead && cta_have) cta_ticket[flipk] = cta_next;  // the group's next ticket, for early loads
-#endif
+                    if (LS && g_lead && cta_have) cta_ticket[flipk] = cta_next;  // the group's next ticket, for early loads
                     s_done += round_outb;
                     if (s_writable) {
                         uint8_t *gd = p.out + s_obase + my_off;
@@ -863,15 +858,15 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                     if (p.sheet.Umax == 8u) guv = *(const uint2 *)gu;
                 }
                 if (r0 + 32u >= nrec && lane == 0) {
-#if SKW_LOCKSTEP
-                    if (wg == 0) {
-                        cta_next = atomicAdd(&st->ticket, (uint32_t)GW);
-                        cta_have = true;
+                    if (LS) {
+                        if (wg == 0) {
+                            cta_next = atomicAdd(&st->ticket, (uint32_t)GW);
+                            cta_have = true;
+                        }
+                    } else {
+                        c_next = atomicAdd(&st->ticket, 1u);
+                        have_next = true;
                     }
-#else
-                    c_next = atomicAdd(&st->ticket, 1u);
-                    have_next = true;
-#endif
                 }
 
                 // ---- body: "\n+\n" and "\n" are patched in behind the kept bases / qualities (:47), whether or
@@ -1030,9 +1025,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
 
                 // ---- emit
                 rbase = __shfl_sync(FULL, rbase, 0);
-#if SKW_LOCKSTEP
-                if (g_lead && cta_have) cta_ticket[flipk] = cta_next;  // the group's next ticket, for early loads
-#endif
+                if (LS && g_lead && cta_have) cta_ticket[flipk] = cta_next;  // the group's next ticket, for early loads
                 bool writable = p.out != nullptr && round_out > 0;
                 if (writable && rbase + ((round_out + 31u) & ~31u) > p.out_cap) {
                     if (lane == 0) report_err(st, rec0 + r0, K_OUT_OVERFLOW);
@@ -1196,20 +1189,16 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
         }
         // The next ticket is taken during the last round (or now): a tile's count must appear soon after
         // its ticket, its successors wait for it.
-#if !SKW_LOCKSTEP
-        if (lane == 0 && !have_next) c_next = atomicAdd(&st->ticket, 1u);
-        c = __shfl_sync(FULL, c_next, 0);
-#else
-        (void)c_next;
-        (void)have_next;
-        {  // the CTA's next ticket may be known already (tickets only grow): start the next load now
+        if (!LS) {
+            if (lane == 0 && !have_next) c_next = atomicAdd(&st->ticket, 1u);
+            c = __shfl_sync(FULL, c_next, 0);
+        } else {  // the CTA's next ticket may be known already (tickets only grow): start the next load now
             const uint32_t v = cta_ticket[flipk];
             if (v > cb && v + (uint32_t)wg < p.n_chunks) {
                 issue_load(v + (uint32_t)wg);
                 early = true;
             }
         }
-#endif
     }
 #undef LB
 #undef UMI_BYTE
