@@ -369,9 +369,12 @@ def main():
                     ob = int(r.out_bytes[0])
                     eng_bits = int(r.reserved)  # 1: lean (or warp) engine, 2: re-run on the general engine
             opn = "TRIM" if name.startswith("trim") else "MASK"
-            ws = os.environ.get("SK_WARP_STREAM")  # default: mask on the warp engine, trim on the lean engine
-            on_warp = os.environ.get("SK_NO_WARP", "0") in ("", "0") and ((ws is None and opn == "MASK") or (ws not in (None, "", "0")))
-            other[name] = {"kernel": ("sk_warp_kernel<OP_%s>" if on_warp else "sk_fast_kernel<GeoM, OP_%s>") % opn, "engine_bits": eng_bits,
+            ws = os.environ.get("SK_WARP_STREAM")  # default: both on the warp engine (trim: + scan + gather kernels)
+            on_warp = os.environ.get("SK_NO_WARP", "0") in ("", "0") and ws not in ("", "0")
+            kn = ("sk_warp_kernel<OP_%s>" if on_warp else "sk_fast_kernel<GeoM, OP_%s>") % opn
+            if on_warp and opn == "TRIM" and os.environ.get("SK_TRIM_GATHER") not in ("", "0"):
+                kn += " + sk_tile_scan_kernel + sk_tile_gather_kernel"
+            other[name] = {"kernel": kn, "engine_bits": eng_bits,
                            "reads_per_launch": P, "ms_per_launch": ms, "algorithmic_bytes_per_launch": n1 + ob,
                            "achieved": (n1 + ob) / (ms * 1e-3) / 1e9, "frac": (n1 + ob) / (ms * 1e-3) / 1e9 / peak}
         lib.sk_set_profiling(eng.ctx, 0)

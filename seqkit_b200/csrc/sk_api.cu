@@ -86,11 +86,16 @@ struct sk_ctx {
     bool fast_sheet = false;  // the sheet's FastIdx is usable
     int fast_geo = 1;   // lean-engine geometry: 0 = GeoS (8 KiB chunks), 1 = GeoM (16 KiB chunks, default); SK_FAST_GEO
     bool warp = true;   // warp engine (sk_warp.cu) for header-route demultiplex; SK_NO_WARP=1 disables
-    // Warp engine for the two ordered operators as well: bit 0 = trim, bit 1 = mask.  Their tiles write in input
-    // order, so a tile waits for the output sizes of all tiles before it (second look-back); measured on 8 M reads
-    // of 150 bp: mask 4.03 ms (lean engine 5.44), trim 5.46 ms (lean 5.33).  Default: mask only.  SK_WARP_STREAM=0/1:
-    // neither / both.
-    uint32_t warp_stream = 2;
+    // Warp engine for the two ordered operators as well: bit 0 = trim, bit 1 = mask (SK_WARP_STREAM=0: the lean
+    // engine for both).  Their tiles write in input order, so a tile needs the output sizes of all tiles before
+    // it.  Mask knows its sizes right after the line table: second look-back on output bytes, 2.9 ms per 8 M
+    // reads of 150 bp (lean engine 5.4 ms).  Trim knows them only after its plan, and waiting for the slowest
+    // plan among a thousand predecessors costs more than a second pass (5.5 ms): with trim_gather (default,
+    // SK_TRIM_GATHER=0 switches it off) the tiles write wherever the output cursor puts them (the spare output
+    // buffer), a one-block scan turns their lengths into destinations and a gather kernel writes the stream in
+    // input order: 3.2 ms (lean engine 5.3 ms).
+    uint32_t warp_stream = 3;
+    bool trim_gather = true;
     uint32_t tile_lanes = GeoW::TILE_LANES;  // warp-engine tile = tile_lanes x 400 B; SK_TILE_LANES
     bool tile_auto = true;   // tile_lanes follows the record size of the data (no SK_TILE_LANES override)
     double rec_est = 0.0;    // bytes per record: peeked from the first batch, then measured by every operator
@@ -187,6 +192,7 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
     if (const char *e = getenv("SK_FAST_GEO")) ctx->fast_geo = atoi(e) ? 1 : 0;
     if (const char *e = getenv("SK_NO_WARP")) ctx->warp = atoi(e) == 0;
     if (const char *e = getenv("SK_WARP_STREAM")) ctx->warp_stream = atoi(e) ? 3u : 0u;
+    if (const char *e = getenv("SK_TRIM_GATHER")) ctx->trim_gather = atoi(e) != 0;
     if (const char *e = getenv("SK_TILE_LANES")) {
         ctx->tile_lanes = (uint32_t)std::min(30, std::max(8, atoi(e)));
         ctx->tile_auto = false;
@@ -598,8 +604,8 @@ static int run_pass(sk_ctx *ctx, Slot *s, int which, int op, const KParams &p, b
     if (p.n_chunks == 0) return SK_OK;
     // look-back words (the warp engine keeps 8 + 2 bytes per tile, sk_warp.cu:wlb_agg)
     CK(cudaMemsetAsync(p.tile_lines, 0, eng == ENG_WARP ? (uint64_t)p.n_chunks * 10 + 64 : (uint64_t)p.n_chunks * 8, s->stream));
-    if (ordered_out)
-        CK(cudaMemsetAsync(p.tile_out, 0, eng == ENG_WARP ? (uint64_t)p.n_chunks * 10 + 64 : (uint64_t)p.n_chunks * 8, s->stream));
+    if (ordered_out)  // (an unordered trim keeps 20 bytes per tile there: base, length, destination)
+        CK(cudaMemsetAsync(p.tile_out, 0, eng == ENG_WARP ? (uint64_t)p.n_chunks * (p.unordered ? 20 : 10) + 64 : (uint64_t)p.n_chunks * 8, s->stream));
     const char *err = nullptr;
     if (ctx->profiling) CK(cudaEventRecord(s->ev[which][0], s->stream));
     int rc = eng == ENG_WARP   ? launch_warp_kernel(op, p, ctx->sm_count, s->stream, &err)
@@ -608,6 +614,14 @@ static int run_pass(sk_ctx *ctx, Slot *s, int which, int op, const KParams &p, b
     if (rc < 0) {
         ctx->err = std::string("kernel launch failed: ") + (err ? err : "?");
         return SK_E_CUDA;
+    }
+    if (rc > 0 && eng == ENG_WARP && p.unordered) {  // trim: scan of the tiles' lengths, gather into input order
+        const int rc2 = launch_tile_gather(p, ctx->sm_count, s->stream, &err);
+        if (rc2 < 0) {
+            ctx->err = std::string("kernel launch failed: ") + (err ? err : "?");
+            return SK_E_CUDA;
+        }
+        rc += rc2;
     }
     if (ctx->profiling) CK(cudaEventRecord(s->ev[which][1], s->stream));
     s->launches += (uint32_t)rc;
@@ -644,6 +658,11 @@ static int stream_op_enqueue(sk_ctx *ctx, Slot *s, int op, uint32_t min_baseq, u
     if (eng == ENG_LEAN && !fast_supported(ctx->fast_geo, op, p)) {
         eng = ENG_GENERAL;
         fill(eng);
+    }
+    if (eng == ENG_WARP && op == OP_TRIM && ctx->trim_gather) {  // unordered tiles into the spare output buffer, then gather
+        p.unordered = 1;
+        p.final_out = s->out[0];
+        p.out = s->out[1];
     }
     fast = eng != ENG_GENERAL;
     s->used_fast = fast;

@@ -196,6 +196,9 @@ struct KParams {
     int32_t fused_trim;   // demux: >=0 -> trim by quality with this threshold
     uint32_t head_char;   // add barcode: '@' or '>' (uniform over the file)
     uint32_t tile_lanes;  // warp engine: lanes whose bytes form the tile (GeoW)
+    uint32_t unordered;   // warp engine, trim: tiles take output space from the cursor (in `out`, a scratch buffer) and
+                          // note (base, length) in tile_out; a scan and a gather pass then write `final_out` in input order
+    uint8_t *final_out;
     // look-back state (zeroed before launch)
     uint64_t *tile_lines;
     uint64_t *tile_out;
@@ -261,6 +264,7 @@ bool fast_supported(int geo, int op, const KParams &p);
 int launch_fast_kernel(int geo, int op, const KParams &p, int sm_count, void *stream, const char **err);
 // Warp engine (sk_warp.cu)
 bool warp_supported(int op, const KParams &p);
+int launch_tile_gather(const KParams &p, int sm_count, void *stream, const char **err);  // after an `unordered` launch
 int launch_warp_kernel(int op, const KParams &p, int sm_count, void *stream, const char **err);
 
 }  // namespace sk

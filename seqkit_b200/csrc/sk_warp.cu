@@ -26,6 +26,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <algorithm>
+
 #include "sk_internal.h"
 
 namespace sk {
@@ -740,8 +742,12 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                     // ---- trim / mask: one output stream in input order.  The tile's output bytes go through a
                     // second look-back (p.tile_out) to its place in the stream; a record is patched in place
                     // into two runs of the window -- header + bases + "\n+\n", qualities + "\n" -- and copied.
-                    // (no early ticket here: a tile's output bytes are published only after its plan and every
-                    // later tile waits for them before it writes, so tickets must be taken when tiles start)
+                    // (no early ticket for ordered output: a tile's output bytes are published only after its plan
+                    // and every later tile waits for them before it writes, so tickets must be taken when tiles start)
+                    if (p.unordered && LS && r0 + 32u >= nrec && tid % (GW * 32) == 0) {
+                        cta_next = atomicAdd(&st->ticket, (uint32_t)GW);
+                        cta_have = true;
+                    }
                     if (has && errk) report_err(st, rec, errk);
                     uint32_t oincl = slen;
 #pragma unroll
@@ -764,7 +770,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                             const uint32_t l2 = stream_plan(has2, LB(j2), LB(j2 + 1), LB(j2 + 2), LB(j2 + 3), LB(j2 + 4), m2, k2, e2);
                             tile_outb += __reduce_add_sync(FULL, l2);
                         }
-                        if (lane == 0) wlb_publish(oagg16, c, tile_outb);
+                        if (lane == 0 && !p.unordered) wlb_publish(oagg16, c, tile_outb);
                     }
                     // patches (and the mask itself, in place) while the predecessors' counts arrive
                     uint32_t run1 = 0, run2 = 0;
@@ -802,7 +808,22 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                         }
                     }
                     __syncwarp();
-                    if (r0 == 0) {
+                    if (r0 == 0 && p.unordered) {
+                        // space from the cursor; (base, length) noted for the scan and gather passes
+                        unsigned long long b = 0;
+                        if (lane == 0 && tile_outb) b = atomicAdd(&st->out_cursor, (unsigned long long)((tile_outb + 31u) & ~31u));
+                        s_obase = __shfl_sync(FULL, b, 0);
+                        out_done = true;
+                        s_writable = p.out != nullptr && tile_outb > 0;
+                        if (s_writable && s_obase + ((tile_outb + 31u) & ~31u) > p.out_cap) {
+                            if (lane == 0) report_err(st, rec0, K_OUT_OVERFLOW);
+                            s_writable = false;
+                        }
+                        if (lane == 0) {
+                            p.tile_out[c] = s_obase;
+                            ((uint32_t *)(p.tile_out + p.n_chunks))[c] = s_writable ? tile_outb : 0u;
+                        }
+                    } else if (r0 == 0) {
                         s_obase = wlb_consume(p.tile_out, oagg16, c, tile_outb, lane);
                         out_done = true;
                         if (lane == 0 && c == p.n_chunks - 1) {
@@ -1161,7 +1182,12 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
             break;
         }
         if (bail && lane == 0) atomicOr(&st->flags, F_NEED_GENERAL);
-        if (!IS_DEMUX && !out_done) {  // a tile without a round still owes its (empty) output to the look-back
+        if (!IS_DEMUX && !out_done && p.unordered) {
+            if (lane == 0) {
+                p.tile_out[c] = 0;
+                ((uint32_t *)(p.tile_out + p.n_chunks))[c] = 0u;
+            }
+        } else if (!IS_DEMUX && !out_done) {  // a tile without a round still owes its (empty) output to the look-back
             if (lane == 0) wlb_publish(oagg16, c, 0u);
             const uint64_t obase = wlb_consume(p.tile_out, oagg16, c, 0u, lane);
             if (lane == 0 && c == p.n_chunks - 1) {
@@ -1218,6 +1244,94 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 if (ccount[s]) atomicAdd(&p.counts[s], (unsigned long long)ccount[s]);
         }
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// unordered trim: scan of the tiles' output lengths, gather into input order
+// ------------------------------------------------------------------------------------------------
+// One block: dst[c] = sum of len[0..c), the total into the outcome block.
+__global__ void __launch_bounds__(1024) sk_tile_scan_kernel(const uint32_t *len, uint64_t *dst, uint32_t n, DevStats *st) {
+    __shared__ unsigned long long part[1024];
+    const uint32_t t = threadIdx.x, per = (n + 1023u) / 1024u;
+    const uint32_t lo = t * per, hi = lo + per < n ? lo + per : n;
+    unsigned long long sum = 0;
+    for (uint32_t i = lo; i < hi; i++) sum += len[i];
+    part[t] = sum;
+    __syncthreads();
+    for (uint32_t o = 1; o < 1024u; o <<= 1) {  // inclusive scan of the slices' sums
+        const unsigned long long y = t >= o ? part[t - o] : 0ull;
+        __syncthreads();
+        part[t] += y;
+        __syncthreads();
+    }
+    unsigned long long run = part[t] - sum;
+    for (uint32_t i = lo; i < hi; i++) {
+        dst[i] = run;
+        run += len[i];
+    }
+    if (t == 1023u) {
+        st->out_bytes = part[1023];
+        st->out_extent = part[1023];
+    }
+}
+
+// One warp per tile: len[c] bytes from the 32-byte aligned scratch + base[c] to out + dst[c] (any alignment),
+// 16 destination-aligned bytes per lane and step, read as two aligned 16-byte loads and shifted into place.
+__global__ void __launch_bounds__(256) sk_tile_gather_kernel(const uint8_t *scratch, uint8_t *out, const uint64_t *base,
+                                                             const uint32_t *len, const uint64_t *dst, uint32_t n) {
+    const uint32_t lane = threadIdx.x & 31u, wpb = blockDim.x >> 5;
+    for (uint32_t c = blockIdx.x * wpb + (threadIdx.x >> 5); c < n; c += gridDim.x * wpb) {
+        const uint32_t L = len[c];
+        if (!L) continue;
+        const uint8_t *src = scratch + base[c];
+        uint8_t *d = out + dst[c];
+        const uint32_t a = (uint32_t)(uintptr_t)d & 15u;  // d - a is 16-byte aligned
+        const uint32_t r = (16u - a) & 15u, wo = r >> 2, bs = (r & 3u) * 8u;
+        const uint32_t units = (a + L + 15u) >> 4;
+        for (uint32_t u = lane; u < units; u += 32u) {
+            const int s0 = (int)(16u * u) - (int)a;  // source offset of the unit's first byte
+            const int k = s0 >> 4;                   // aligned 16-byte chunk that holds it
+            uint4 A = make_uint4(0u, 0u, 0u, 0u), B = make_uint4(0u, 0u, 0u, 0u);
+            if (k >= 0) A = *(const uint4 *)(src + 16 * k);
+            if (r && 16u * (uint32_t)(k + 1) < ((L + 31u) & ~31u)) B = *(const uint4 *)(src + 16 * (k + 1));  // inside the tile's sectors
+            const uint32_t W[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
+            uint4 o;
+            switch (wo) {  // uniform over the tile
+                case 0: o = make_uint4(__funnelshift_r(W[0], W[1], bs), __funnelshift_r(W[1], W[2], bs), __funnelshift_r(W[2], W[3], bs), __funnelshift_r(W[3], W[4], bs)); break;
+                case 1: o = make_uint4(__funnelshift_r(W[1], W[2], bs), __funnelshift_r(W[2], W[3], bs), __funnelshift_r(W[3], W[4], bs), __funnelshift_r(W[4], W[5], bs)); break;
+                case 2: o = make_uint4(__funnelshift_r(W[2], W[3], bs), __funnelshift_r(W[3], W[4], bs), __funnelshift_r(W[4], W[5], bs), __funnelshift_r(W[5], W[6], bs)); break;
+                default: o = make_uint4(__funnelshift_r(W[3], W[4], bs), __funnelshift_r(W[4], W[5], bs), __funnelshift_r(W[5], W[6], bs), __funnelshift_r(W[6], W[7], bs)); break;
+            }
+            uint8_t *du = d - a + 16u * u;
+            const uint32_t first = u == 0 ? a : 0u;                                     // valid bytes of the unit: [first, last)
+            const uint32_t last = 16u * u + 16u > a + L ? a + L - 16u * u : 16u;
+            if (first == 0u && last == 16u) {
+                *(uint4 *)du = o;
+            } else {  // the tile's first and last unit are shared with its neighbours
+                const uint32_t ow[4] = {o.x, o.y, o.z, o.w};
+                for (uint32_t i = first; i < last; i++) du[i] = (uint8_t)(ow[i >> 2] >> (8u * (i & 3u)));
+            }
+        }
+    }
+}
+
+// (base, length, destination) of every tile in p.tile_out: u64 base[n], u32 len[n], u64 dst[n]
+static inline uint64_t *tt_base(const KParams &p) { return p.tile_out; }
+static inline uint32_t *tt_len(const KParams &p) { return (uint32_t *)(p.tile_out + p.n_chunks); }
+static inline uint64_t *tt_dst(const KParams &p) { return p.tile_out + p.n_chunks + (p.n_chunks + 1u) / 2u; }
+
+int launch_tile_gather(const KParams &p, int sm_count, void *stream_, const char **err) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!p.n_chunks) return 0;
+    sk_tile_scan_kernel<<<1, 1024, 0, stream>>>(tt_len(p), tt_dst(p), p.n_chunks, p.stats);
+    const unsigned grid = (unsigned)std::min<long long>((long long)sm_count * 8, ((long long)p.n_chunks + 7) / 8);
+    sk_tile_gather_kernel<<<grid ? grid : 1u, 256, 0, stream>>>(p.out, p.final_out, tt_base(p), tt_len(p), tt_dst(p), p.n_chunks);
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        *err = cudaGetErrorString(e);
+        return -1;
+    }
+    return 2;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -192,13 +192,16 @@ def test_shards_concatenate_to_the_single_stream_output(eng, O):
     assert whole["files"] == want["files"] and whole["counts"] == want["counts"]
 
 
-def test_trim_and_mask_on_the_warp_engine(O, monkeypatch):
+@pytest.mark.parametrize("gather", [False, True])
+def test_trim_and_mask_on_the_warp_engine(O, monkeypatch, gather):
     """SK_WARP_STREAM=1: trim and mask by quality through the warp engine (second look-back on output bytes,
     in-place mask, two runs per record; by default only mask takes it).  The bytes must be the oracle's:
     regular data, uneven record sizes (tiles of several rounds), every nasty record shape, failing records
     (the host replays the records before them)."""
     from seqkit_b200 import Engine
     monkeypatch.setenv("SK_WARP_STREAM", "1")
+    # trim: unordered tiles + scan + gather (the default), or the in-order look-back on output bytes
+    monkeypatch.setenv("SK_TRIM_GATHER", "1" if gather else "0")
     with Engine(max_stream_bytes=16 << 20, max_records=1 << 17, max_samples=64) as e:
         blobs = [("decay", G.clean_fastq(41, 9000, read_len=(150, 150))), ("uneven", G.clean_fastq(42, 12000, read_len=(20, 160), qual_style="mix")),
                  ("short", G.clean_fastq(43, 20000, read_len=(30, 40), qual_style="bad"))]
