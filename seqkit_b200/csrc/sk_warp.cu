@@ -21,6 +21,10 @@
 //     patched into the window in place (" UMI:x\n" over the deleted " BC:x", "\n+\n" and "\n" behind
 //     the kept bases and qualities), so that a record is two or three contiguous runs which the lane
 //     copies straight to global memory with 16-byte stores.  No staging image, no second pass.
+// Trim and mask by quality write one stream in input order: mask through a second look-back (on output
+// bytes, known right after the line table); trim, whose sizes are known only after the plan, lets its
+// tiles write wherever the output cursor puts them and restores the order with a scan and a gather
+// kernel (bottom of this file).
 // Anything outside the engine's limits (a record longer than the overhang, more than 128 records in
 // a tile) raises F_NEED_GENERAL and sk_wait re-runs the operator on the general engine.
 #include <cuda_runtime.h>
