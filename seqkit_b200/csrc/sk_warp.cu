@@ -1253,29 +1253,61 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
 // ------------------------------------------------------------------------------------------------
 // unordered trim: scan of the tiles' output lengths, gather into input order
 // ------------------------------------------------------------------------------------------------
-// One block: dst[c] = sum of len[0..c), the total into the outcome block.
-__global__ void __launch_bounds__(1024) sk_tile_scan_kernel(const uint32_t *len, uint64_t *dst, uint32_t n, DevStats *st) {
-    __shared__ unsigned long long part[1024];
-    const uint32_t t = threadIdx.x, per = (n + 1023u) / 1024u;
-    const uint32_t lo = t * per, hi = lo + per < n ? lo + per : n;
-    unsigned long long sum = 0;
-    for (uint32_t i = lo; i < hi; i++) sum += len[i];
-    part[t] = sum;
+// dst[c] = sum of len[0..c) in two small launches: sums of blocks of 1024 tiles, then every block adds the
+// sums before it to the scan of its own 1024 lengths; the total goes into the outcome block.
+__global__ void __launch_bounds__(1024) sk_tile_sum_kernel(const uint32_t *len, unsigned long long *bsum, uint32_t n) {
+    __shared__ unsigned long long ws[32];
+    const uint32_t i = blockIdx.x * 1024u + threadIdx.x, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    unsigned long long v = i < n ? len[i] : 0u;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) ws[w] = v;
     __syncthreads();
-    for (uint32_t o = 1; o < 1024u; o <<= 1) {  // inclusive scan of the slices' sums
-        const unsigned long long y = t >= o ? part[t - o] : 0ull;
-        __syncthreads();
-        part[t] += y;
-        __syncthreads();
+    if (w == 0) {
+        v = ws[lane];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) bsum[blockIdx.x] = v;
     }
-    unsigned long long run = part[t] - sum;
-    for (uint32_t i = lo; i < hi; i++) {
-        dst[i] = run;
-        run += len[i];
+}
+__global__ void __launch_bounds__(1024) sk_tile_scan_kernel(const uint32_t *len, const unsigned long long *bsum, uint64_t *dst,
+                                                             uint32_t n, DevStats *st) {
+    __shared__ unsigned long long ws[32];
+    __shared__ unsigned long long s_before;
+    const uint32_t i = blockIdx.x * 1024u + threadIdx.x, lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    // sums of the blocks before this one (a few hundred values at most)
+    unsigned long long b = 0;
+    for (uint32_t j = threadIdx.x; j < blockIdx.x; j += 1024u) b += bsum[j];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+    if (lane == 0) ws[w] = b;
+    __syncthreads();
+    if (w == 0) {
+        b = ws[lane];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) b += __shfl_xor_sync(0xffffffffu, b, o);
+        if (lane == 0) s_before = b;
     }
-    if (t == 1023u) {
-        st->out_bytes = part[1023];
-        st->out_extent = part[1023];
+    __syncthreads();
+    const unsigned long long before = s_before;
+    // inclusive scan of this block's lengths
+    const unsigned long long own = i < n ? len[i] : 0u;
+    unsigned long long x = own;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+        if ((int)lane >= o) x += y;
+    }
+    __syncthreads();  // ws is reused
+    if (lane == 31) ws[w] = x;
+    __syncthreads();
+    unsigned long long wb = 0;
+    for (uint32_t k = 0; k < w; k++) wb += ws[k];
+    const unsigned long long incl = before + wb + x;
+    if (i < n) dst[i] = incl - own;
+    if (i == n - 1) {
+        st->out_bytes = incl;
+        st->out_extent = incl;
     }
 }
 
@@ -1319,7 +1351,7 @@ __global__ void __launch_bounds__(256) sk_tile_gather_kernel(const uint8_t *scra
     }
 }
 
-// (base, length, destination) of every tile in p.tile_out: u64 base[n], u32 len[n], u64 dst[n]
+// (base, length, destination) of every tile in p.tile_out: u64 base[n], u32 len[n], u64 dst[n], then the block sums
 static inline uint64_t *tt_base(const KParams &p) { return p.tile_out; }
 static inline uint32_t *tt_len(const KParams &p) { return (uint32_t *)(p.tile_out + p.n_chunks); }
 static inline uint64_t *tt_dst(const KParams &p) { return p.tile_out + p.n_chunks + (p.n_chunks + 1u) / 2u; }
@@ -1327,7 +1359,10 @@ static inline uint64_t *tt_dst(const KParams &p) { return p.tile_out + p.n_chunk
 int launch_tile_gather(const KParams &p, int sm_count, void *stream_, const char **err) {
     cudaStream_t stream = (cudaStream_t)stream_;
     if (!p.n_chunks) return 0;
-    sk_tile_scan_kernel<<<1, 1024, 0, stream>>>(tt_len(p), tt_dst(p), p.n_chunks, p.stats);
+    const unsigned nb = (p.n_chunks + 1023u) / 1024u;
+    unsigned long long *bsum = (unsigned long long *)(tt_dst(p) + p.n_chunks);  // behind the three per-tile arrays
+    sk_tile_sum_kernel<<<nb, 1024, 0, stream>>>(tt_len(p), bsum, p.n_chunks);
+    sk_tile_scan_kernel<<<nb, 1024, 0, stream>>>(tt_len(p), bsum, tt_dst(p), p.n_chunks, p.stats);
     const unsigned grid = (unsigned)std::min<long long>((long long)sm_count * 8, ((long long)p.n_chunks + 7) / 8);
     sk_tile_gather_kernel<<<grid ? grid : 1u, 256, 0, stream>>>(p.out, p.final_out, tt_base(p), tt_len(p), tt_dst(p), p.n_chunks);
     const cudaError_t e = cudaGetLastError();
@@ -1335,7 +1370,7 @@ int launch_tile_gather(const KParams &p, int sm_count, void *stream_, const char
         *err = cudaGetErrorString(e);
         return -1;
     }
-    return 2;
+    return 3;
 }
 
 // ------------------------------------------------------------------------------------------------
