@@ -373,7 +373,7 @@ def main():
             on_warp = os.environ.get("SK_NO_WARP", "0") in ("", "0") and ws not in ("", "0")
             kn = ("sk_warp_kernel<OP_%s>" if on_warp else "sk_fast_kernel<GeoM, OP_%s>") % opn
             if on_warp and opn == "TRIM" and os.environ.get("SK_TRIM_GATHER") not in ("", "0"):
-                kn += " + sk_tile_scan_kernel + sk_tile_gather_kernel"
+                kn += " + sk_tile_sum_kernel + sk_tile_scan_kernel + sk_tile_gather_kernel"
             other[name] = {"kernel": kn, "engine_bits": eng_bits,
                            "reads_per_launch": P, "ms_per_launch": ms, "algorithmic_bytes_per_launch": n1 + ob,
                            "achieved": (n1 + ob) / (ms * 1e-3) / 1e9, "frac": (n1 + ob) / (ms * 1e-3) / 1e9 / peak}
