@@ -234,7 +234,6 @@ __global__ void __launch_bounds__(G::NT, G::MIN_CTAS) sk_fast_kernel(const __gri
             j0 = k0 ? 0u : k1 ? 1u : k2 ? 2u : 3u;
             spec = (k0 || k1 || k2 || k3) && j0 < nls_chunk;
         }
-        const bool speculated = spec;
 #ifdef SK_PHASE_TIMING
         const long long t_plan0 = clock64();
 #endif

@@ -456,7 +456,6 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
         uint32_t cnt_all = 0;
 #pragma unroll
         for (int i = 0; i < NMW; i++) cnt_all += __popc(mw[i]);
-        const bool dense = false;
         const uint32_t cnt_own = (uint32_t)lane < tile_lanes ? cnt_all : 0u;
         uint32_t incl = (cnt_own << 16) | cnt_all;
 #pragma unroll
@@ -514,7 +513,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
         bool spec = false;
         uint32_t j0 = 0;
         uint64_t g0 = 0;
-        if (c != 0 && p.rec_limit == ~0ull && nls >= 6u && !dense) {
+        if (c != 0 && p.rec_limit == ~0ull && nls >= 6u) {
             const uint32_t s0 = LB(0), s1 = LB(1), s2 = LB(2), s3 = LB(3), s4 = LB(4), s5 = LB(5);
             const uint32_t b0 = win[s0], b1 = win[s1], b2 = win[s2], b3 = win[s3], b4 = win[s4], b5 = win[s5];
             const bool k0 = b0 == '@' && b2 == '+', k1 = b1 == '@' && b3 == '+';
@@ -538,10 +537,6 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 else if ((uint64_t)nrec > p.rec_limit - first) nrec = (uint32_t)(p.rec_limit - first);
             }
             bail = false;
-            if (dense) {
-                bail = true;
-                nrec = 0;
-            }
             if (nrec) {
                 uint32_t jend = j0 + nrec * 4u;
                 const bool eof_ok = at_end && p.final_batch;
@@ -632,11 +627,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                     bool fine;
                     mode = B_FAIL;
                     if (trim_q <= 222) {
-#ifdef SKW_TRIM8
-                        fine = plan_trim_warp(win, ok, L1, L2, L3, L4, trim_q, mode, kk, body);
-#else
                         fine = plan_trim_lane16(win, ok, L1, L2, L3, L4, trim_q, mode, kk, body);
-#endif
                     } else {
                         fine = true;
                         if (ok) {
