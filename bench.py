@@ -225,6 +225,8 @@ def main():
     ap.add_argument("--cpu-pairs", type=int, default=400_000, help="bounded sample for the 1-core CPU baseline")
     ap.add_argument("--ref-pairs-per-core", type=int, default=100_000)
     ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--cli-pairs", type=int, default=200_000,
+                    help="bounded sample for the files+gzip end-to-end leg (the `fasta` binary; 0 = skip)")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
 
@@ -399,6 +401,14 @@ def main():
                "sample": "%d pairs (same generator), oracle/fasta_oracle.c trim x2 + demultiplex in memory, %.1f s"
                          % (args.cpu_pairs, dt)}
 
+    # ---- files + gzip end to end (rank 0, N=1 only): the `fasta` binary beside the oracle's CLI
+    e2e_files = None
+    if rank == 0 and world == 1 and args.cli_pairs > 0:
+        try:
+            e2e_files = run_cli_leg(args, bcs, local_rank, with_cpu=not args.skip_cpu)
+        except Exception as ex:  # a reported extra: never costs the contract line
+            e2e_files = {"error": "%s: %s" % (type(ex).__name__, ex)}
+
     if rank == 0:
         line = {
             "metric": "reads_per_s", "value": value, "unit": "reads/s", "n_gpus": world, "steps": steps, "warmup": warm,
@@ -407,10 +417,105 @@ def main():
             "pairs_per_s": value / 2, "identified_fraction": identified / float(P * world),
             "bytes_per_step_per_gpu": {"in": [n1, n2], "out": out_bytes},
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
+            "e2e_files_gzip": e2e_files,
         }
         emit_line(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_cli_leg(args, bcs, local_rank, with_cpu=True):
+    """Third number of SURVEY 8(d): end to end WITH files and gzip.  The drop-in `fasta` binary
+    (`demultiplex --trim-by-quality=Q`, its one-pass form of the benchmark's pipeline) reads two plain FASTQ
+    files and feeds one `gzip -c` child per output file (common.rs:49-81); beside it the oracle's CLI runs the
+    reference's own three commands (trim R1, trim R2, demultiplex) on the same files.  Wall clock of the
+    processes, CUDA context creation and the gzip children included; a bounded sample."""
+    import shutil
+    import tempfile
+    from seqkit_b200 import Engine
+    from oracle import pyoracle as O
+    n = args.cli_pairs
+    fasta = os.path.join(ROOT, "seqkit_b200", "fasta")
+    if not os.path.exists(fasta):
+        subprocess.check_call(["make", "-s", "-C", ROOT, "seqkit_b200/fasta"])
+    O.build()
+    oracle_cli = os.path.join(ROOT, "oracle", "_build", "fasta_oracle")
+    with Engine(device=local_rank, max_stream_bytes=n * 420 + (1 << 20), max_records=n, max_samples=N_SAMPLES,
+                aux_streams=False) as e3:
+        e3.set_sheet(bcs)
+        m1, m2 = synth_pair(e3, n, 0, seed=11)
+        r1, r2 = e3.download_in(0, m1), e3.download_in(1, m2)
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    top = tempfile.mkdtemp(prefix="skbench_", dir=base)
+    try:
+        for name, data in (("sheet.tsv", sheet_text(bcs)), ("r1.fq", r1), ("r2.fq", r2)):
+            with open(os.path.join(top, name), "wb") as f:
+                f.write(data)
+        env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local_rank)))
+
+        def outputs(d):
+            tot = 0
+            for f in os.listdir(d):
+                if f.endswith(".fq.gz"):
+                    tot += os.path.getsize(os.path.join(d, f))
+            return tot
+
+        def settle(d):  # the reference does not wait for its gzip children (common.rs:49-81): wait for the files
+            last, t_end = -1, time.time() + 60
+            while time.time() < t_end:
+                cur = outputs(d)
+                if cur == last:
+                    return cur
+                last = cur
+                time.sleep(0.2)
+            return last
+
+        d_ours = os.path.join(top, "ours")
+        os.mkdir(d_ours)
+        t0 = time.perf_counter()
+        p = subprocess.run([fasta, "demultiplex", "--trim-by-quality=%d" % MIN_BASEQ, "../sheet.tsv", "../r1.fq", "../r2.fq"],
+                           cwd=d_ours, env=env, capture_output=True, timeout=600)
+        dt_ours = time.perf_counter() - t0
+        if p.returncode != 0:
+            raise RuntimeError("fasta demultiplex: exit %d: %s" % (p.returncode, p.stderr[-300:].decode("replace")))
+        gz_ours = settle(d_ours)
+        res = {"value": 2.0 * n / dt_ours, "unit": "reads/s", "seconds": dt_ours, "pairs": n,
+               "gz_bytes_out": gz_ours, "summary": p.stderr.decode("replace").strip().splitlines()[-1][:200],
+               "note": "fasta demultiplex --trim-by-quality=%d sheet r1.fq r2.fq: process start, CUDA context, file "
+                       "reads, kernels, %d gzip -c children; wall clock" % (MIN_BASEQ, 2 * N_SAMPLES)}
+        if with_cpu:
+            d_cpu = os.path.join(top, "cpu")
+            os.mkdir(d_cpu)
+            t0 = time.perf_counter()
+            for m in ("1", "2"):
+                with open(os.path.join(d_cpu, "t%s.fq" % m), "wb") as f:
+                    subprocess.run([oracle_cli, "trim", "by", "quality", "../r%s.fq" % m, str(MIN_BASEQ)], cwd=d_cpu,
+                                   stdout=f, check=True, timeout=900)
+            q = subprocess.run([oracle_cli, "demultiplex", "../sheet.tsv", "t1.fq", "t2.fq"], cwd=d_cpu,
+                               capture_output=True, timeout=900)
+            dt_cpu = time.perf_counter() - t0
+            gz_cpu = settle(d_cpu)
+            same = None
+            if q.returncode == 0:  # decompressed bytes of every output file, ours against the oracle's
+                import gzip as _gz
+                same = True
+                for f in sorted(os.listdir(d_cpu)):
+                    if f.endswith(".fq.gz"):
+                        a = _gz.decompress(open(os.path.join(d_cpu, f), "rb").read())
+                        try:
+                            b = _gz.decompress(open(os.path.join(d_ours, f), "rb").read())
+                        except Exception:
+                            b = None
+                        if a != b:
+                            same = False
+                            break
+            res["cpu"] = {"value": 2.0 * n / dt_cpu, "unit": "reads/s", "seconds": dt_cpu, "cores": 1, "kind": "port",
+                          "exit": q.returncode, "gz_bytes_out": gz_cpu, "outputs_identical": same,
+                          "note": "oracle CLI, single-threaded: trim by quality R1, R2 to files, then demultiplex; it compresses its "
+                                  "output files one after another (the reference runs its gzip -c children concurrently)"}
+        return res
+    finally:
+        shutil.rmtree(top, ignore_errors=True)
 
 
 def run_e2e(args, torch, L, bcs, local_rank, rank, world, barrier):
