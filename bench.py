@@ -477,10 +477,10 @@ def run_cli_leg(args, bcs, local_rank, with_cpu=True):
                            cwd=d_ours, env=env, capture_output=True, timeout=600)
         dt_ours = time.perf_counter() - t0
         if p.returncode != 0:
-            raise RuntimeError("fasta demultiplex: exit %d: %s" % (p.returncode, p.stderr[-300:].decode("replace")))
+            raise RuntimeError("fasta demultiplex: exit %d: %s" % (p.returncode, p.stderr[-300:].decode("utf-8", "replace")))
         gz_ours = settle(d_ours)
         res = {"value": 2.0 * n / dt_ours, "unit": "reads/s", "seconds": dt_ours, "pairs": n,
-               "gz_bytes_out": gz_ours, "summary": p.stderr.decode("replace").strip().splitlines()[-1][:200],
+               "gz_bytes_out": gz_ours, "summary": p.stderr.decode("utf-8", "replace").strip().splitlines()[-1][:200],
                "note": "fasta demultiplex --trim-by-quality=%d sheet r1.fq r2.fq: process start, CUDA context, file "
                        "reads, kernels, %d gzip -c children; wall clock" % (MIN_BASEQ, 2 * N_SAMPLES)}
         if with_cpu:

@@ -98,12 +98,16 @@ __device__ __forceinline__ U256 lds_unaligned32(const uint8_t *win, int off) {
 }
 // bytes [0, f) of a, the others of b (0 <= f < 32)
 __device__ __forceinline__ U256 merge_low32(const U256 &a, const U256 &b, uint32_t f) {
+    // Three instructions a word: the bit position of byte f in word k, clamped below at 0 by the fused
+    // add-max and above at 32 by shl (PTX clamps the shift amount), is where b takes over from a.
     U256 r;
+    const int t = 8 * (int)f;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
-        const int n = (int)f - 4 * k;
-        const uint32_t m = n <= 0 ? 0u : (n >= 4 ? 0xFFFFFFFFu : (1u << (8 * n)) - 1u);
-        r.w[k] = (a.w[k] & m) | (b.w[k] & ~m);
+        const int s = __viaddmax_s32(t, -32 * k, 0);
+        uint32_t mb;
+        asm("shl.b32 %0, %1, %2;" : "=r"(mb) : "r"(0xFFFFFFFFu), "r"(s));
+        r.w[k] = (a.w[k] & ~mb) | (b.w[k] & mb);
     }
     return r;
 }
