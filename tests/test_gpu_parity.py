@@ -317,3 +317,60 @@ def test_framing_guess_is_verified_against_the_line_count(eng, O):
     _cmp_demux(eng.demultiplex(sheet, r1, r1, fused_trim=20),
                O.demultiplex(sheet, O.trim_by_quality(r1, 20)[1], O.trim_by_quality(r1, 20)[1]), "fused")
     assert eng.last_result.reserved == 1
+
+
+def test_properties_at_bench_batch_size():
+    """BASELINE configs[4] shape at a size no CPU oracle run fits into the test budget (2 M pairs, 384 samples,
+    device-resident inputs, straight through the C ABI).  Size-independent properties: read conservation
+    (fasta_demultiplex.rs:169,177-178), the fused quality trim changes bytes but never an assignment, every
+    emitted record has one slice-table group, the trimmed output is never longer than the untrimmed one, and
+    shard linearity -- the counters of two half ranges add up to those of the whole range, which is what the
+    multi-GPU all-reduce relies on."""
+    import ctypes as C
+    import numpy as np
+    import bench
+    from seqkit_b200 import Engine, _lib as L
+
+    n, S = 2_000_000, 384
+    bcs = bench.make_sheet(S)
+    with Engine(max_stream_bytes=n * 410 + (1 << 20), max_records=n, max_samples=S, aux_streams=False) as eng:
+        lib = eng.lib
+        eng.set_sheet(bcs)
+
+        def run(first, cnt, fused):
+            bench.synth_pair(eng, cnt, first)
+            opts = L.DemuxOpts(20 if fused else -1, 0, 0, 0, 0)
+            assert lib.sk_demultiplex(eng.ctx, 0, C.byref(opts)) == 0, lib.sk_last_error(eng.ctx)
+            res = eng.wait()
+            assert res.status == 0 and res.n_records == cnt and res.reserved == 1, (res.status, res.n_records, res.reserved)
+            counts = np.zeros(S + 2, dtype=np.uint64)
+            assert lib.sk_download_counts(eng.ctx, 0, counts.ctypes.data) == 0
+            assign = np.zeros(cnt, dtype=np.int16)
+            assert lib.sk_download_assign(eng.ctx, 0, assign.ctypes.data, cnt) == 0
+            eng.wait()
+            ngroups = []
+            for m in range(2):
+                nc = res.n_chunks[m]
+                rows = np.zeros(max(nc, 1) * 2, dtype=np.uint64)
+                groups = np.zeros(cnt, dtype=np.uint32)
+                assert lib.sk_download_demux_tables(eng.ctx, 0, m, rows.ctypes.data, groups.ctypes.data, cnt) == 0
+                eng.wait()
+                ng = (rows[1::2][:nc] >> np.uint64(32)).astype(np.int64)  # {u64 base, u32 first_group, u32 n_groups}
+                ngroups.append(int(ng.sum()))
+            return counts, assign, [int(res.out_extent[0]), int(res.out_extent[1])], ngroups
+
+        c_plain, a_plain, ext_plain, g_plain = run(0, n, False)
+        c_fused, a_fused, ext_fused, g_fused = run(0, n, True)
+        for c, a, g in ((c_plain, a_plain, g_plain), (c_fused, a_fused, g_fused)):
+            assert int(c[S]) == n and int(c[:S].sum()) == int(c[S + 1]) <= n
+            assert int((a >= 0).sum()) == int(c[S + 1]) and a.min() >= -2 and a.max() < S
+            assert np.array_equal(np.bincount(a[a >= 0], minlength=S).astype(np.uint64), c[:S])
+            assert g == [int(c[S + 1])] * 2  # one group per emitted record and mate
+        assert np.array_equal(a_plain, a_fused) and np.array_equal(c_plain, c_fused)
+        assert 0.9 * n < int(c_plain[S + 1]) < n  # the generator leaves 2 % random barcodes and some double errors
+        assert all(0 < f <= p for f, p in zip(ext_fused, ext_plain))
+        half = n // 2
+        c_lo, a_lo, _, _ = run(0, half, True)
+        c_hi, a_hi, _, _ = run(half, n - half, True)
+        assert np.array_equal(c_lo + c_hi, c_fused)
+        assert np.array_equal(np.concatenate([a_lo, a_hi]), a_fused)
