@@ -837,7 +837,34 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                     }
                     if (LS && g_lead && cta_have) cta_ticket[flipk] = cta_next;  // the group's next ticket, for early loads
                     s_done += round_outb;
-                    if (s_writable) {
+                    // Mask by quality of a regular file (bare "+" lines, final newline) changes bytes, not lengths:
+                    // every record's two runs are the record's own bytes in the window and the round's output is
+                    // one piece of the window, first header to last newline.  The warp then copies that piece as
+                    // a whole, 16 destination-aligned bytes per lane and step (512 contiguous bytes per store
+                    // instruction), instead of two runs per lane.
+                    bool whole = false;
+                    if (OP == OP_MASK && s_writable) {
+                        const bool idl = !slen || (!slow && L0 + run1 == L3 && L3 + run2 == L4);
+                        const uint32_t src0 = __shfl_sync(FULL, L0, 0);
+                        const uint32_t srce = __reduce_max_sync(FULL, slen ? L4 : 0u);
+                        whole = __all_sync(FULL, idl) && srce == src0 + round_outb;
+                        if (whole) {
+                            uint8_t *g0 = p.out + s_obase + (s_done - round_outb);
+                            uint32_t so = src0, len = round_outb;
+                            const uint32_t head = min((16u - ((uint32_t)(uintptr_t)g0 & 15u)) & 15u, len);
+                            if ((uint32_t)lane < head) g0[lane] = win[so + (uint32_t)lane];
+                            g0 += head, so += head, len -= head;
+                            const uint32_t nv = len >> 4;
+#pragma unroll 2
+                            for (uint32_t u = (uint32_t)lane; u < nv; u += 32u) {
+                                const uint4 v = lds_unaligned16(win, so + 16u * u);
+                                *(uint4 *)(g0 + 16u * u) = v;
+                            }
+                            const uint32_t tl = len & 15u;
+                            if ((uint32_t)lane < tl) g0[16u * nv + (uint32_t)lane] = win[so + 16u * nv + (uint32_t)lane];
+                        }
+                    }
+                    if (s_writable && !whole) {
                         uint8_t *gd = p.out + s_obase + my_off;
 #pragma unroll 1
                         for (int q = 0; q < 2; q++) {
