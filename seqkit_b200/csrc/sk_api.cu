@@ -57,6 +57,7 @@ struct Slot {
     // the request behind last_op, so that sk_wait can re-run it on the general engine
     bool used_fast = false;
     bool reran_general = false;
+    bool no_inplace = false;  // mask: the in-place layout was refused by the data (F_NEED_ORDERED), ordered form from now on
     uint32_t req_min_baseq = 0;
     uint64_t req_rec_limit = 0;
     sk_demux_opts req_opts{};
@@ -96,6 +97,9 @@ struct sk_ctx {
     // input order: 3.0 ms (lean engine 5.3 ms).
     uint32_t warp_stream = 3;
     bool trim_gather = true;
+    // mask by quality of a regular file keeps every record's length: tiles write at their input offsets, no second
+    // look-back (SK_MASK_INPLACE=0 switches it off); data of any other shape raises F_NEED_ORDERED and runs again
+    bool mask_inplace = true;
     uint32_t tile_lanes = GeoW::TILE_LANES;  // warp-engine tile = tile_lanes x 400 B; SK_TILE_LANES
     bool tile_auto = true;   // tile_lanes follows the record size of the data (no SK_TILE_LANES override)
     double rec_est = 0.0;    // bytes per record: peeked from the first batch, then measured by every operator
@@ -193,6 +197,7 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
     if (const char *e = getenv("SK_NO_WARP")) ctx->warp = atoi(e) == 0;
     if (const char *e = getenv("SK_WARP_STREAM")) ctx->warp_stream = atoi(e) ? 3u : 0u;
     if (const char *e = getenv("SK_TRIM_GATHER")) ctx->trim_gather = atoi(e) != 0;
+    if (const char *e = getenv("SK_MASK_INPLACE")) ctx->mask_inplace = atoi(e) != 0;
     if (const char *e = getenv("SK_TILE_LANES")) {
         ctx->tile_lanes = (uint32_t)std::min(30, std::max(8, atoi(e)));
         ctx->tile_auto = false;
@@ -664,6 +669,7 @@ static int stream_op_enqueue(sk_ctx *ctx, Slot *s, int op, uint32_t min_baseq, u
         p.final_out = s->out[0];
         p.out = s->out[1];
     }
+    if (eng == ENG_WARP && op == OP_MASK && ctx->mask_inplace && !s->no_inplace && p.rec_limit == ~0ull) p.inplace = 1;
     fast = eng != ENG_GENERAL;
     s->used_fast = fast;
     s->req_min_baseq = min_baseq;
@@ -676,6 +682,7 @@ static int stream_op(sk_ctx *ctx, uint32_t slot, int op, uint32_t min_baseq, uin
     Slot *s = get_slot(ctx, slot);
     if (!s || min_baseq > 255) return SK_E_INVALID;
     s->reran_general = false;
+    s->no_inplace = false;
     return stream_op_enqueue(ctx, s, op, min_baseq, rec_limit, ctx->fast);
 }
 
@@ -884,6 +891,17 @@ extern "C" int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res) {
         // output): run the operator again on the general engine.
         unsigned fl = 0;
         for (int i = 0; i < SK_N_INPUTS; i++) fl |= s->stats_h[i].flags;
+        if (!(fl & F_NEED_GENERAL) && (fl & F_NEED_ORDERED) && s->last_op == OP_MASK && !s->no_inplace) {
+            // mask met a record that changes its length (or fails): same engine, ordered output
+            const uint32_t first_launches = s->launches;
+            s->no_inplace = true;
+            int rc = stream_op_enqueue(ctx, s, s->last_op, s->req_min_baseq, s->req_rec_limit, ctx->fast);
+            if (rc) return rc;
+            CK(cudaStreamSynchronize(s->stream));
+            s->launches += first_launches;
+            fl = 0;
+            for (int i = 0; i < SK_N_INPUTS; i++) fl |= s->stats_h[i].flags;
+        }
         if (fl & F_NEED_GENERAL) {
             const uint32_t fast_launches = s->launches;
             const sk_demux_opts o = s->req_opts;

@@ -199,6 +199,8 @@ struct KParams {
     uint32_t unordered;   // warp engine, trim: tiles take output space from the cursor (in `out`, a scratch buffer) and
                           // note (base, length) in tile_out; a scan and a gather pass then write `final_out` in input order
     uint8_t *final_out;
+    uint32_t inplace;     // warp engine, mask: a tile writes its records at their input offsets (a regular file keeps every
+                          // length), no look-back on output bytes; any other record shape raises F_NEED_ORDERED
     // look-back state (zeroed before launch)
     uint64_t *tile_lines;
     uint64_t *tile_out;
@@ -231,7 +233,7 @@ enum : unsigned {
     K_BAD_FASTX_LINE = 7, K_NON_ASCII = 32, K_TOO_LONG = 33, K_TOO_DENSE = 34, K_MIXED = 35, K_OUT_OVERFLOW = 36,
     K_TRUNC_FUSED = 37,
 };
-enum : unsigned { F_MATE_COUNT = 1u, F_EVENTS_OVERFLOW = 2u, F_NON_ASCII = 0x100u, F_NEED_GENERAL = 0x200u };
+enum : unsigned { F_MATE_COUNT = 1u, F_EVENTS_OVERFLOW = 2u, F_NON_ASCII = 0x100u, F_NEED_GENERAL = 0x200u, F_NEED_ORDERED = 0x400u };
 
 constexpr int REC_BYTES = 26;  // per-record plan fields, see sk_kernels.cu
 template <class Cfg>

@@ -769,7 +769,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                             const uint32_t l2 = stream_plan(has2, LB(j2), LB(j2 + 1), LB(j2 + 2), LB(j2 + 3), LB(j2 + 4), m2, k2, e2);
                             tile_outb += __reduce_add_sync(FULL, l2);
                         }
-                        if (lane == 0 && !p.unordered) wlb_publish(oagg16, c, tile_outb);
+                        if (lane == 0 && !p.unordered && !p.inplace) wlb_publish(oagg16, c, tile_outb);
                     }
                     // patches (and the mask itself, in place) while the predecessors' counts arrive
                     uint32_t run1 = 0, run2 = 0;
@@ -822,6 +822,15 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                             p.tile_out[c] = s_obase;
                             ((uint32_t *)(p.tile_out + p.n_chunks))[c] = s_writable ? tile_outb : 0u;
                         }
+                    } else if (r0 == 0 && OP == OP_MASK && p.inplace) {
+                        // mask of a regular file: the tile's records go where they came from (verified per round below)
+                        s_obase = c0 + __shfl_sync(FULL, L0, 0);
+                        out_done = true;
+                        s_writable = p.out != nullptr && tile_outb > 0;
+                        if (s_writable && s_obase + tile_outb > p.out_cap) {
+                            if (lane == 0) report_err(st, rec0, K_OUT_OVERFLOW);
+                            s_writable = false;
+                        }
                     } else if (r0 == 0) {
                         s_obase = wlb_consume(p.tile_out, oagg16, c, tile_outb, lane);
                         out_done = true;
@@ -843,12 +852,17 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                     // a whole, 16 destination-aligned bytes per lane and step (512 contiguous bytes per store
                     // instruction), instead of two runs per lane.
                     bool whole = false;
-                    if (OP == OP_MASK && s_writable) {
+                    if (OP == OP_MASK && (s_writable || p.inplace)) {
                         const bool idl = !slen || (!slow && L0 + run1 == L3 && L3 + run2 == L4);
                         const uint32_t src0 = __shfl_sync(FULL, L0, 0);
                         const uint32_t srce = __reduce_max_sync(FULL, slen ? L4 : 0u);
                         whole = __all_sync(FULL, idl) && srce == src0 + round_outb;
-                        if (whole) {
+                        if (p.inplace && (!whole || !s_writable || __any_sync(FULL, has && !slen))) {
+                            // a record that changes its length, fails or cannot be written: the input offsets are
+                            // not the output offsets; nothing is written and sk_wait runs the ordered form
+                            if (lane == 0) atomicOr(&st->flags, F_NEED_ORDERED);
+                            whole = true;
+                        } else if (whole) {
                             uint8_t *g0 = p.out + s_obase + (s_done - round_outb);
                             uint32_t so = src0, len = round_outb;
                             const uint32_t head = min((16u - ((uint32_t)(uintptr_t)g0 & 15u)) & 15u, len);
@@ -1213,7 +1227,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 p.tile_out[c] = 0;
                 ((uint32_t *)(p.tile_out + p.n_chunks))[c] = 0u;
             }
-        } else if (!IS_DEMUX && !out_done) {  // a tile without a round still owes its (empty) output to the look-back
+        } else if (!IS_DEMUX && !out_done && !p.inplace) {  // a tile without a round still owes its (empty) output to the look-back
             if (lane == 0) wlb_publish(oagg16, c, 0u);
             const uint64_t obase = wlb_consume(p.tile_out, oagg16, c, 0u, lane);
             if (lane == 0 && c == p.n_chunks - 1) {
@@ -1258,6 +1272,10 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
     if (lane == 0 && my_nrec) {
         atomicAdd(&st->n_records, my_nrec);
         atomicMax(&st->consumed, my_upto);
+        if (OP == OP_MASK && p.inplace) {  // output == input bytes of the complete records
+            atomicMax(&st->out_bytes, my_upto);
+            atomicMax(&st->out_extent, my_upto);
+        }
     }
     if (D1) {  // fasta_demultiplex.rs:108-109,169,177-178
         const uint32_t wt = __reduce_add_sync(FULL, my_total), wi = __reduce_add_sync(FULL, my_ident);
