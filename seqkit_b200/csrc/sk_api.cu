@@ -929,7 +929,7 @@ extern "C" int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res) {
     if (h[SK_IN_R1].n_records >= 64 && h[SK_IN_R1].consumed)  // record size of this data, for the next tile choice
         ctx->rec_est = (double)h[SK_IN_R1].consumed / (double)h[SK_IN_R1].n_records;
     res->gpu_launches = s->launches;
-    res->reserved = (s->used_fast ? 1u : 0u) | (s->reran_general ? 2u : 0u);  // diagnostic: bit0 lean engine, bit1 re-run
+    res->reserved = (s->used_fast ? 1u : 0u) | (s->reran_general ? 2u : 0u) | (s->no_inplace ? 4u : 0u);  // diagnostic: bit0 warp / lean engine, bit1 re-run on the general engine, bit2 mask re-run in its ordered form
     if (ctx->profiling)
         for (int i = 0; i < SK_N_INPUTS; i++)
             if (s->pass_ran[i]) cudaEventElapsedTime(&res->pass_ms[i], s->ev[i][0], s->ev[i][1]);

@@ -217,4 +217,31 @@ def test_trim_and_mask_on_the_warp_engine(O, monkeypatch, gather):
                 assert got[0] == want[0] and got[1] == want[1], ("mask", label, q)
                 if got[0] != 101:
                     assert got[2] == want[2], ("mask", label, q)
-        assert e.last_result.reserved in (1, 2)
+        assert (e.last_result.reserved & 3) in (1, 2)
+
+
+def test_mask_in_place_and_its_ordered_form(O, monkeypatch):
+    """Mask by quality of a regular file (bare '+' lines, final newline) keeps every record's length: the warp
+    engine writes each tile at its input offsets without a look-back on output bytes (sk_result.reserved == 1).
+    A single record that changes its length -- a named '+' line, a missing final newline, CRLF is fine (same
+    length) -- or fails (fasta_mask_by_quality.rs:21-23,35-37) makes sk_wait run the ordered form (bit 2); the
+    bytes are the oracle's either way, and with the in-place form switched off."""
+    from seqkit_b200 import Engine
+    reg = G.clean_fastq(61, 6000, read_len=(150, 150))
+    recs = reg.split(b"\n")
+    named = list(recs)
+    named[4 * 3000 + 2] = b"+named line"
+    cases = [("regular", reg, 1), ("named plus", b"\n".join(named), 5), ("no final newline", reg[:-1], 5),
+             # failing records: the ordered form reports them, then the host replays the records before them with a
+             # record limit (ordered from the start: bits of the replay)
+             ("bad header", reg + b"oops\nACGT\n+\nIIII\n" + reg, 1),
+             ("length mismatch", reg + b"@x\nACGT\n+\nIII\n", 1), ("empty", b"", None)]
+    for switch in ("1", "0"):
+        monkeypatch.setenv("SK_MASK_INPLACE", switch)
+        with Engine(max_stream_bytes=16 << 20, max_records=1 << 17, max_samples=64) as e:
+            for label, blob, bits in cases:
+                for q in (20, 41):
+                    got, want = e.mask_by_quality(blob, q), O.mask_by_quality(blob, q)
+                    assert got[0] == want[0] and got[1] == want[1] and got[2] == want[2], (label, q, switch)
+                    if bits is not None:
+                        assert e.last_result.reserved == (bits if switch == "1" else 1), (label, q, switch, e.last_result.reserved)
