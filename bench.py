@@ -351,7 +351,9 @@ def main():
                 "algorithmic_bytes_per_launch": bytes_pass[dom], "ms_per_launch": pass_ms[dom],
                 "other_kernel": {"kernel": kname(1 - dom), "ms_per_launch": pass_ms[1 - dom],
                                  "achieved": bytes_pass[1 - dom] / (pass_ms[1 - dom] * 1e-3) / 1e9},
-                "step_bytes": sum(bytes_pass), "step_achieved": sum(bytes_pass) / (ms_step * 1e-3) / 1e9}
+                "step_bytes": sum(bytes_pass), "step_achieved": sum(bytes_pass) / (ms_step * 1e-3) / 1e9,
+                # against the nominal figure of the north star as well (~8 TB/s)
+                "frac_of_nominal_8000_gbs": achieved / 8000.0}
     identified = counts[N_SAMPLES + 1]
     out_bytes = [int(res.out_bytes[0]), int(res.out_bytes[1])]
     # the path's other two operators on the same resident mate-1 stream (BASELINE configs[0] / [1] shapes):
