@@ -133,8 +133,15 @@ int sk_debug_phase_cycles(sk_ctx *ctx, uint32_t slot, uint32_t which, uint64_t o
 /* on != 0: bracket every kernel with CUDA events so that sk_wait can fill sk_result.pass_ms. */
 int sk_set_profiling(sk_ctx *ctx, int on);
 
-/* Pinned (page-locked) host memory for the batcher's multi-MB buffers, so that a host without its own
- * CUDA binding (the Rust crate, the C++ `fasta` binary) gets asynchronous H2D/D2H copies. */
+/* Number of CUDA devices this process sees (0 when there is none). */
+int sk_device_count(void);
+/* Restricts the calling thread to the CPUs of the NUMA node `device` hangs off (sysfs); returns the node, or
+ * -1 when the topology is not exposed.  Host threads that feed a GPU (and the pinned buffers they touch first)
+ * belong next to that GPU's PCIe root: on a two-socket 8-GPU box the cross-socket hop halves H2D/D2H. */
+int sk_bind_thread_to_device(int device);
+/* Pinned (page-locked, portable) host memory for the batcher's multi-MB buffers, so that a host without its own
+ * CUDA binding (the Rust crate, the C++ `fasta` binary) gets asynchronous H2D/D2H copies; allocated on the
+ * NUMA node of the context's device. */
 void *sk_pinned_alloc(sk_ctx *ctx, uint64_t bytes);
 void sk_pinned_free(sk_ctx *ctx, void *p);
 /* Capacity in bytes of each output stream of a slot (upper bound of sk_result.out_extent). */
@@ -207,6 +214,22 @@ int sk_download_assign(sk_ctx *ctx, uint32_t slot, int16_t *assign, uint64_t n_r
 uint64_t sk_demux_gather(const uint8_t *out_host, const sk_chunk_row *rows, const sk_group *groups, uint32_t n_chunks,
                          uint32_t s, uint8_t *dst, uint64_t dst_cap);
 
+/* Device-side stable per-sample compaction (fasta_demultiplex.rs:196-238: a sample's file is the sample's records
+ * in input order).  Enqueued after sk_demultiplex on the same slot, it regroups the emitted records of both
+ * mates so that every sample's records are one contiguous run of bytes in input order; the host then appends S
+ * slices per batch and mate instead of one piece per record.  After sk_wait, sk_result.out_extent[m] is the
+ * extent of the compacted buffer of mate m, sk_result.reserved has bit 3 set, and slices[s] = {offset, len} of
+ * sample s inside it (every run starts on a 128-byte line); slices[S] = {extent, payload bytes}.
+ * Returns SK_E_UNSUPPORTED for sheets of more than 4096 samples (use the slice tables above). */
+typedef struct sk_slice {
+    uint64_t offset;
+    uint64_t len;
+} sk_slice;
+int sk_demux_compact(sk_ctx *ctx, uint32_t slot);
+const void *sk_compact_dev(sk_ctx *ctx, uint32_t slot, uint32_t which);
+int sk_download_compact(sk_ctx *ctx, uint32_t slot, uint32_t which, void *host, uint64_t n);
+int sk_download_slices(sk_ctx *ctx, uint32_t slot, uint32_t which, sk_slice *slices /*[S+1]*/);
+
 /* ---- multi-GPU ---------------------------------------------------------------------------- */
 /* Sums the S+2 counters of this slot across ranks in place with one ncclAllReduce(sum, u64) on the
  * slot's stream.  `nccl_comm` is an ncclComm_t created by the caller; the only collective on the
@@ -215,6 +238,15 @@ int sk_allreduce_counts(sk_ctx *ctx, uint32_t slot, void *nccl_comm);
 /* Thin wrappers over ncclGetUniqueId / ncclCommInitRank / ncclCommDestroy (libnccl.so.2 is resolved at
  * run time) so that a host without its own NCCL binding can build the communicator: rank 0 fills
  * `id128` (128 bytes), every rank receives it out of band and calls sk_nccl_comm_init. */
+/* One process driving several GPUs (the `fasta` binary: one context per device, batches dealt round-robin):
+ * sk_counts_accumulate adds the counters of a finished batch (call it after sk_wait, once the batch's outcome
+ * is final) to the context's device-side run totals; sk_allreduce_totals merges the totals of `n` contexts with
+ * one grouped ncclAllReduce(sum, u64, S+2) over NVLink (ncclCommInitAll; n == 1: nothing to merge), after which
+ * every context holds the run's counters (fasta_demultiplex.rs:108-109,177-178,263-264). */
+int sk_counts_accumulate(sk_ctx *ctx, uint32_t slot);
+int sk_totals_reset(sk_ctx *ctx);
+int sk_allreduce_totals(sk_ctx **ctxs, int n);
+int sk_download_totals(sk_ctx *ctx, uint64_t *totals /*[S+2]*/);
 int sk_nccl_unique_id(sk_ctx *ctx, void *id128);
 int sk_nccl_comm_init(sk_ctx *ctx, const void *id128, int nranks, int rank, void **comm);
 int sk_nccl_comm_destroy(sk_ctx *ctx, void *comm);

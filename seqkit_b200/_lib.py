@@ -48,6 +48,10 @@ class ChunkRow(C.Structure):
     _fields_ = [("base", C.c_uint64), ("first_group", C.c_uint32), ("n_groups", C.c_uint32)]
 
 
+class Slice(C.Structure):
+    _fields_ = [("offset", C.c_uint64), ("len", C.c_uint64)]
+
+
 class DemuxOpts(C.Structure):
     _fields_ = [("fused_trim_min_baseq", C.c_int32), ("use_index", C.c_uint32), ("rec_limit", C.c_uint64),
                 ("no_output", C.c_uint32), ("reserved", C.c_uint32)]
@@ -70,6 +74,8 @@ SIGNATURES = {
     "sk_max_chunks": (C.c_uint32, [_P]),
     "sk_debug_phase_cycles": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint64)]),
     "sk_set_profiling": (C.c_int, [_P, C.c_int]),
+    "sk_device_count": (C.c_int, []),
+    "sk_bind_thread_to_device": (C.c_int, [C.c_int]),
     "sk_pinned_alloc": (_P, [_P, C.c_uint64]),
     "sk_pinned_free": (None, [_P, _P]),
     "sk_out_capacity": (C.c_uint64, [_P]),
@@ -91,7 +97,15 @@ SIGNATURES = {
     "sk_download_events": (C.c_int, [_P, C.c_uint32, C.POINTER(Event), C.c_uint32]),
     "sk_download_assign": (C.c_int, [_P, C.c_uint32, _P, C.c_uint64]),
     "sk_demux_gather": (C.c_uint64, [_P, _P, _P, C.c_uint32, C.c_uint32, _P, C.c_uint64]),
+    "sk_demux_compact": (C.c_int, [_P, C.c_uint32]),
+    "sk_compact_dev": (_P, [_P, C.c_uint32, C.c_uint32]),
+    "sk_download_compact": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.c_uint64]),
+    "sk_download_slices": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.POINTER(Slice)]),
     "sk_allreduce_counts": (C.c_int, [_P, C.c_uint32, _P]),
+    "sk_counts_accumulate": (C.c_int, [_P, C.c_uint32]),
+    "sk_totals_reset": (C.c_int, [_P]),
+    "sk_allreduce_totals": (C.c_int, [C.POINTER(_P), C.c_int]),
+    "sk_download_totals": (C.c_int, [_P, _P]),
     "sk_nccl_unique_id": (C.c_int, [_P, _P]),
     "sk_nccl_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int, C.POINTER(_P)]),
     "sk_nccl_comm_destroy": (C.c_int, [_P, _P]),

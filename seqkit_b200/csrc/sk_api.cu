@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <cmath>
 #include <dlfcn.h>
+#include <sched.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -47,6 +48,12 @@ struct Slot {
     Event *events = nullptr;
     RecRef *scan_tab[2] = {nullptr, nullptr};
     uint64_t *synth_tmp = nullptr;
+    // per-sample compaction (sk_compact.cu): mate 1 -> cbuf, mate 2 -> out[0] (free once mate 1 is compacted)
+    uint8_t *cbuf = nullptr;
+    void *cwork = nullptr;
+    unsigned long long *slices = nullptr;     // [2][(Smax + 1) * 2]
+    unsigned long long *piece_dst = nullptr;  // [max_records]
+    bool want_compact = false, compacted = false;
     // description of the last operator, for sk_wait
     int last_op = -1;
     bool paired = false;
@@ -74,9 +81,12 @@ struct sk_ctx {
     // sample sheet
     bool have_sheet = false;
     uint32_t S = 0, L = 0, Umax = 0, wide = 0;
+    bool u_uniform = false;            // every sample has its 'U' at the same positions
+    unsigned long long u_mask = 0;
     std::vector<uint8_t> sheet_raw;
     uint32_t *d_planes = nullptr, *d_umask = nullptr;
     uint8_t *d_lut = nullptr, *d_sheet_raw = nullptr;
+    unsigned long long *d_totals = nullptr;  // [Smax + 2] counters summed over the batches of a run (sk_counts_accumulate)
     // pigeonhole index (HalfIdx)
     uint32_t h_classes = 0, h_nw = 0, h_nwp = 0, h_tsize = 0;
     uint32_t *d_hcls = nullptr, *d_skeys = nullptr;
@@ -148,6 +158,10 @@ static void free_slot(Slot &s) {
     cudaFree(s.counts);
     cudaFree(s.events);
     cudaFree(s.synth_tmp);
+    cudaFree(s.cbuf);
+    cudaFree(s.cwork);
+    cudaFree(s.slices);
+    cudaFree(s.piece_dst);
     for (int i = 0; i < SK_N_INPUTS; i++)
         for (int k = 0; k < 2; k++)
             if (s.ev[i][k]) cudaEventDestroy(s.ev[i][k]);
@@ -158,6 +172,7 @@ extern "C" void sk_ctx_destroy(sk_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     for (auto &s : ctx->slots) free_slot(s);
+    cudaFree(ctx->d_totals);
     cudaFree(ctx->d_planes);
     cudaFree(ctx->d_umask);
     cudaFree(ctx->d_lut);
@@ -190,7 +205,7 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
     sk_ctx *ctx = new sk_ctx();
     ctx->device = device;
     ctx->lim = *lim;
-    ctx->cfg = lim->reserved == 2 ? 1 : 0;  // reserved: 0/1 = 16 KiB chunks (default), 2 = 32 KiB chunks
+    ctx->cfg = (lim->reserved & 0xFFu) == 2 ? 1 : 0;  // reserved: 0/1 = 16 KiB chunks (default), 2 = 32 KiB chunks
     if (const char *e = getenv("SK_CFG")) ctx->cfg = atoi(e) ? 1 : 0;
     if (const char *e = getenv("SK_NO_FAST")) ctx->fast = atoi(e) == 0;
     if (const char *e = getenv("SK_FAST_GEO")) ctx->fast_geo = atoi(e) ? 1 : 0;
@@ -228,8 +243,13 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
     // slice-table rows: one per chunk, or GeoW::ROUNDS per tile of the warp engine (smallest tile: 8 lanes)
     ctx->max_chunks = std::max(chunks_of(ctx, B, ENG_GENERAL), (uint32_t)((B + GeoS::CHUNK - 1) / GeoS::CHUNK)) + 1;
     ctx->max_chunks = std::max(ctx->max_chunks, (uint32_t)(B / (8 * GeoW::LANE_BYTES) + 1) * GeoW::ROUNDS);
-    const uint64_t out_cap = B + R * 72 + (uint64_t)ctx->max_chunks * 32 + 4096;  // every chunk / round owns whole 32-byte sectors
     const uint32_t Smax = lim->max_samples;
+    // every chunk / round owns whole 32-byte sectors; a compacted buffer starts every sample on a 128-byte line
+    const uint64_t out_cap = B + R * 72 + (uint64_t)ctx->max_chunks * 32 + 4096 + (uint64_t)Smax * 128;
+    if (Smax) {
+        CKC(cudaMalloc(&ctx->d_totals, (uint64_t)(Smax + 2) * 8));
+        CKC(cudaMemset(ctx->d_totals, 0, (uint64_t)(Smax + 2) * 8));
+    }
     ctx->slots.resize(lim->n_slots);
     for (auto &s : ctx->slots) {
         CKC(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
@@ -241,7 +261,7 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
             s.in_cap[i] = B;
             CKC(cudaMalloc(&s.tile_lines[i], ((uint64_t)ctx->max_chunks + 8) * 8));  // look-back reads whole 4-entry blocks
         }
-        for (int i = 0; i < 2; i++) CKC(cudaMalloc(&s.out[i], out_cap));
+        for (int i = 0; i < 2; i++) CKC(cudaMalloc(&s.out[i], out_cap + 64));
         s.out_cap = out_cap;
         CKC(cudaMalloc(&s.tile_out, ((uint64_t)ctx->max_chunks + 8) * 8));
         CKC(cudaMalloc(&s.stats, sizeof(DevStats) * SK_N_INPUTS));
@@ -256,6 +276,12 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
             }
             CKC(cudaMalloc(&s.counts, (uint64_t)(Smax + 2) * 8));
             CKC(cudaMalloc(&s.events, R * sizeof(Event)));
+            if (Smax <= 4096 && !(lim->reserved & 0x100u)) {  // (reserved bit 8: no compaction buffers)
+                CKC(cudaMalloc(&s.cbuf, out_cap + 64));
+                CKC(cudaMalloc(&s.cwork, compact_work_bytes(ctx->max_chunks, Smax)));
+                CKC(cudaMalloc(&s.slices, (uint64_t)(Smax + 1) * 16 * 2));
+                CKC(cudaMalloc(&s.piece_dst, R * 8));
+            }
         }
         if (lim->aux_streams)
             for (int i = 0; i < 2; i++) CKC(cudaMalloc(&s.scan_tab[i], R * sizeof(RecRef)));
@@ -288,12 +314,79 @@ extern "C" int sk_set_profiling(sk_ctx *ctx, int on) {
     ctx->profiling = on != 0;
     return SK_OK;
 }
+// CPUs of the NUMA node a device hangs off (sysfs: the PCI device's numa_node, the node's cpulist).
+static bool device_node_cpus(int device, cpu_set_t *set, int *node_out) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) return false;
+    for (char *c = bus; *c; c++) *c = (char)tolower(*c);
+    char path[256];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE *f = fopen(path, "r");
+    if (!f) return false;
+    int node = -1;
+    const int got = fscanf(f, "%d", &node);
+    fclose(f);
+    if (got != 1 || node < 0) return false;
+    snprintf(path, sizeof path, "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return false;
+    char list[4096] = {0};
+    const bool ok = fgets(list, sizeof list, f) != nullptr;
+    fclose(f);
+    if (!ok) return false;
+    CPU_ZERO(set);
+    int n = 0;
+    for (char *q = list; *q;) {  // "0-31,64-95"
+        char *e;
+        const long a = strtol(q, &e, 10);
+        if (e == q) break;
+        long b = a;
+        if (*e == '-') b = strtol(e + 1, &e, 10);
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++) {
+            CPU_SET((int)c, set);
+            n++;
+        }
+        q = (*e == ',') ? e + 1 : e;
+        if (*e != ',') break;
+    }
+    if (node_out) *node_out = node;
+    return n > 0;
+}
+extern "C" int sk_device_count(void) {
+    int n = 0;
+    return cudaGetDeviceCount(&n) == cudaSuccess ? n : 0;
+}
+extern "C" int sk_bind_thread_to_device(int device) {
+    cpu_set_t set;
+    int node = -1;
+    if (!device_node_cpus(device, &set, &node)) return -1;
+    // keep to the CPUs this process may use at all (containers hand out subsets)
+    cpu_set_t cur, both;
+    if (sched_getaffinity(0, sizeof cur, &cur) == 0) {
+        CPU_AND(&both, &cur, &set);
+        if (CPU_COUNT(&both) == 0) return -1;
+        set = both;
+    }
+    return sched_setaffinity(0, sizeof set, &set) == 0 ? node : -1;
+}
+// Pinned, portable (usable from every device's streams) and allocated while the calling thread sits on the
+// NUMA node of the context's device, so that first touch puts the pages next to the GPU's PCIe root.
 extern "C" void *sk_pinned_alloc(sk_ctx *ctx, uint64_t bytes) {
     if (!ctx || !bytes) return nullptr;
     cudaSetDevice(ctx->device);
+    cpu_set_t old, node;
+    const bool have_old = sched_getaffinity(0, sizeof old, &old) == 0;
+    bool moved = false;
+    if (have_old && !getenv("SK_NO_NUMA") && device_node_cpus(ctx->device, &node, nullptr)) {
+        cpu_set_t both;
+        CPU_AND(&both, &old, &node);
+        if (CPU_COUNT(&both) > 0) moved = sched_setaffinity(0, sizeof both, &both) == 0;
+    }
     void *p = nullptr;
-    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
-        ctx->err = "cudaMallocHost failed";
+    const cudaError_t e = cudaHostAlloc(&p, bytes, cudaHostAllocPortable);
+    if (moved) sched_setaffinity(0, sizeof old, &old);
+    if (e != cudaSuccess) {
+        ctx->err = std::string("cudaHostAlloc failed: ") + cudaGetErrorString(e);
         return nullptr;
     }
     return p;
@@ -367,6 +460,8 @@ extern "C" int sk_set_sheet(sk_ctx *ctx, const uint8_t *barcodes, uint32_t S, ui
     const uint32_t wpe = wide ? 2u : 1u;  // u32 words per plane element
     std::vector<uint32_t> planes((size_t)S * 4 * wpe, 0u), umask((size_t)S * wpe, 0u);
     uint32_t Umax = 0;
+    unsigned long long u_first = 0;
+    bool u_same = true;
     for (uint32_t s = 0; s < S; s++) {
         uint64_t pl[4] = {0, 0, 0, 0}, um = 0;
         for (uint32_t q = 0; q < L; q++) {
@@ -385,6 +480,8 @@ extern "C" int sk_set_sheet(sk_ctx *ctx, const uint8_t *barcodes, uint32_t S, ui
         umask[(size_t)s * wpe] = (uint32_t)um;
         if (wide) umask[(size_t)s * wpe + 1] = (uint32_t)(um >> 32);
         Umax = std::max<uint32_t>(Umax, (uint32_t)__builtin_popcountll(um));
+        if (s == 0) u_first = um;
+        else if (um != u_first) u_same = false;
     }
 
     // ---- pigeonhole index (HalfIdx, sk_internal.h): classes of identical care mask; per class the cared
@@ -554,6 +651,8 @@ extern "C" int sk_set_sheet(sk_ctx *ctx, const uint8_t *barcodes, uint32_t S, ui
     ctx->S = S;
     ctx->L = L;
     ctx->Umax = Umax;
+    ctx->u_uniform = u_same;
+    ctx->u_mask = u_first;
     ctx->wide = wide;
     ctx->h_classes = h_classes;
     ctx->h_nw = nw;
@@ -581,6 +680,7 @@ static int begin_op(sk_ctx *ctx, Slot *s, int op) {
     s->last_op = op;
     s->used_fast = false;
     s->launches = 0;
+    s->want_compact = s->compacted = false;
     for (int i = 0; i < SK_N_INPUTS; i++) {
         s->pass_ran[i] = false;
         s->n_chunks[i] = 0;
@@ -836,6 +936,8 @@ static int demux_enqueue(sk_ctx *ctx, Slot *s, const sk_demux_opts *o, bool fast
         p.sheet.S = S;
         p.sheet.L = ctx->L;
         p.sheet.Umax = ctx->Umax;
+        p.sheet.u_uniform = ctx->u_uniform ? 1u : 0u;
+        p.sheet.u_mask = ctx->u_mask;
         p.sheet.wide = ctx->wide;
         p.sheet.hidx.n_classes = getenv("SK_NO_HIDX") ? 0u : ctx->h_classes;
         p.sheet.hidx.nw = ctx->h_nw;
@@ -882,6 +984,54 @@ static int demux_enqueue(sk_ctx *ctx, Slot *s, const sk_demux_opts *o, bool fast
     return end_op(ctx, s);
 }
 
+// Per-sample compaction of the last demultiplex of the slot (sk_compact.cu), both mates, on the slot's stream.
+static int compact_enqueue(sk_ctx *ctx, Slot *s) {
+    const uint32_t S = ctx->S;
+    const int nm = s->paired ? 2 : 1;
+    for (int m = 0; m < nm; m++) {
+        const int which = m == 0 ? SK_IN_R1 : SK_IN_R2;
+        const char *err = nullptr;
+        const int rc = launch_compact(s->rows[m], s->groups[m], s->n_chunks[which], S, s->out[m], m == 0 ? s->cbuf : s->out[0],
+                                      s->out_cap, s->cwork, s->slices + (size_t)m * (ctx->lim.max_samples + 1) * 2, s->piece_dst,
+                                      s->stats + which, ctx->sm_count, s->stream, &err);
+        if (rc < 0) {
+            ctx->err = std::string("per-sample compaction: ") + (err ? err : "?");
+            return SK_E_UNSUPPORTED;
+        }
+        s->launches += (uint32_t)rc;
+    }
+    s->compacted = true;
+    return end_op(ctx, s);
+}
+extern "C" int sk_demux_compact(sk_ctx *ctx, uint32_t slot) {
+    Slot *s = get_slot(ctx, slot);
+    if (!s || s->last_op != OP_DEMUX1) return SK_E_INVALID;
+    if (!s->cbuf) {
+        ctx->err = "sk_demux_compact: the context holds no compaction buffers (more than 4096 samples, or switched off)";
+        return SK_E_UNSUPPORTED;
+    }
+    if (s->req_opts.no_output) return SK_OK;  // dry run: nothing was written
+    s->want_compact = true;
+    return compact_enqueue(ctx, s);
+}
+extern "C" const void *sk_compact_dev(sk_ctx *ctx, uint32_t slot, uint32_t which) {
+    Slot *s = get_slot(ctx, slot);
+    return (s && which < 2 && s->cbuf) ? (which == 0 ? s->cbuf : s->out[0]) : nullptr;
+}
+extern "C" int sk_download_compact(sk_ctx *ctx, uint32_t slot, uint32_t which, void *host, uint64_t n) {
+    Slot *s = get_slot(ctx, slot);
+    if (!s || which >= 2 || !s->cbuf || n > s->out_cap) return SK_E_INVALID;
+    if (n) CK(cudaMemcpyAsync(host, which == 0 ? s->cbuf : s->out[0], n, cudaMemcpyDeviceToHost, s->stream));
+    return SK_OK;
+}
+extern "C" int sk_download_slices(sk_ctx *ctx, uint32_t slot, uint32_t which, sk_slice *slices) {
+    Slot *s = get_slot(ctx, slot);
+    if (!s || which >= 2 || !s->slices || !slices) return SK_E_INVALID;
+    CK(cudaMemcpyAsync(slices, s->slices + (size_t)which * (ctx->lim.max_samples + 1) * 2, (uint64_t)(ctx->S + 1) * 16,
+                       cudaMemcpyDeviceToHost, s->stream));
+    return SK_OK;
+}
+
 extern "C" int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res) {
     Slot *s = get_slot(ctx, slot);
     if (!s) return SK_E_INVALID;
@@ -905,9 +1055,15 @@ extern "C" int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res) {
         if (fl & F_NEED_GENERAL) {
             const uint32_t fast_launches = s->launches;
             const sk_demux_opts o = s->req_opts;
+            const bool again = s->want_compact;  // (begin_op clears it)
             int rc = s->last_op == OP_DEMUX1 ? demux_enqueue(ctx, s, &o, false)
                                              : stream_op_enqueue(ctx, s, s->last_op, s->req_min_baseq, s->req_rec_limit, false);
             if (rc) return rc;
+            if (again) {
+                s->want_compact = true;
+                rc = compact_enqueue(ctx, s);
+                if (rc) return rc;
+            }
             CK(cudaStreamSynchronize(s->stream));
             s->launches += fast_launches;
             s->reran_general = true;
@@ -929,7 +1085,7 @@ extern "C" int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res) {
     if (h[SK_IN_R1].n_records >= 64 && h[SK_IN_R1].consumed)  // record size of this data, for the next tile choice
         ctx->rec_est = (double)h[SK_IN_R1].consumed / (double)h[SK_IN_R1].n_records;
     res->gpu_launches = s->launches;
-    res->reserved = (s->used_fast ? 1u : 0u) | (s->reran_general ? 2u : 0u) | (s->no_inplace ? 4u : 0u);  // diagnostic: bit0 warp / lean engine, bit1 re-run on the general engine, bit2 mask re-run in its ordered form
+    res->reserved = (s->used_fast ? 1u : 0u) | (s->reran_general ? 2u : 0u) | (s->no_inplace ? 4u : 0u) | (s->compacted ? 8u : 0u);  // diagnostic: bit0 warp / lean engine, bit1 re-run on the general engine, bit2 mask re-run in its ordered form
     if (ctx->profiling)
         for (int i = 0; i < SK_N_INPUTS; i++)
             if (s->pass_ran[i]) cudaEventElapsedTime(&res->pass_ms[i], s->ev[i][0], s->ev[i][1]);
@@ -938,6 +1094,10 @@ extern "C" int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res) {
         res->out_extent[0] = h[SK_IN_R1].out_cursor;
         res->out_bytes[1] = h[SK_IN_R2].out_bytes;
         res->out_extent[1] = h[SK_IN_R2].out_cursor;
+        if (s->compacted) {  // extent of the compacted buffers (sk_download_compact)
+            res->out_extent[0] = h[SK_IN_R1].compact_extent;
+            res->out_extent[1] = s->paired ? h[SK_IN_R2].compact_extent : 0;
+        }
         res->n_chunks[0] = s->n_chunks[SK_IN_R1];
         res->n_chunks[1] = s->n_chunks[SK_IN_R2];
         res->n_events = std::min<uint32_t>(h[SK_IN_R1].n_events, (uint32_t)ctx->lim.max_records);
@@ -1055,6 +1215,79 @@ extern "C" int sk_allreduce_counts(sk_ctx *ctx, uint32_t slot, void *nccl_comm) 
     int rc = fn(s->counts, s->counts, (size_t)ctx->S + 2, 5, 0, nccl_comm, s->stream);
     if (rc != 0) {
         ctx->err = "ncclAllReduce failed with code " + std::to_string(rc);
+        return SK_E_CUDA;
+    }
+    return SK_OK;
+}
+// Run totals: the counters of a finished batch are added to the context's device-side totals on the slot's
+// stream (call it once the batch's outcome is final, i.e. after sk_wait and any replay); at the end of a run
+// the totals of all GPUs of the process are merged with ONE grouped ncclAllReduce (fasta_demultiplex.rs:263-264
+// needs total / identified; the dry-run table needs the per-sample counts).
+__global__ void sk_add_counts_kernel(unsigned long long *totals, const unsigned long long *counts, uint32_t n) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) totals[i] += counts[i];
+}
+extern "C" int sk_counts_accumulate(sk_ctx *ctx, uint32_t slot) {
+    Slot *s = get_slot(ctx, slot);
+    if (!s || !s->counts || !ctx->d_totals) return SK_E_INVALID;
+    const uint32_t n = ctx->S + 2;
+    sk_add_counts_kernel<<<(n + 255) / 256, 256, 0, s->stream>>>(ctx->d_totals, s->counts, n);
+    return cudaGetLastError() == cudaSuccess ? SK_OK : SK_E_CUDA;
+}
+extern "C" int sk_totals_reset(sk_ctx *ctx) {
+    if (!ctx || !ctx->d_totals) return SK_E_INVALID;
+    cudaSetDevice(ctx->device);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemset(ctx->d_totals, 0, (uint64_t)(ctx->lim.max_samples + 2) * 8));
+    return SK_OK;
+}
+extern "C" int sk_download_totals(sk_ctx *ctx, uint64_t *totals) {
+    if (!ctx || !ctx->d_totals || !totals) return SK_E_INVALID;
+    cudaSetDevice(ctx->device);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(totals, ctx->d_totals, (uint64_t)(ctx->S + 2) * 8, cudaMemcpyDeviceToHost));
+    return SK_OK;
+}
+extern "C" int sk_allreduce_totals(sk_ctx **ctxs, int n) {
+    if (!ctxs || n < 1 || !ctxs[0]) return SK_E_INVALID;
+    sk_ctx *ctx = ctxs[0];
+    for (int i = 0; i < n; i++) {
+        if (!ctxs[i] || !ctxs[i]->d_totals || ctxs[i]->S != ctx->S) return SK_E_INVALID;
+        cudaSetDevice(ctxs[i]->device);
+        CK(cudaDeviceSynchronize());
+    }
+    if (n == 1) return SK_OK;
+    typedef int (*init_all_fn)(void **, int, const int *);
+    typedef int (*group_fn)(void);
+    typedef int (*allreduce_fn)(const void *, void *, size_t, int, int, void *, cudaStream_t);
+    typedef int (*destroy_fn)(void *);
+    init_all_fn init_all = (init_all_fn)nccl_sym(ctx, "ncclCommInitAll");
+    group_fn gstart = (group_fn)nccl_sym(ctx, "ncclGroupStart"), gend = (group_fn)nccl_sym(ctx, "ncclGroupEnd");
+    allreduce_fn allreduce = (allreduce_fn)nccl_sym(ctx, "ncclAllReduce");
+    destroy_fn destroy = (destroy_fn)nccl_sym(ctx, "ncclCommDestroy");
+    if (!init_all || !gstart || !gend || !allreduce || !destroy) return SK_E_UNSUPPORTED;
+    std::vector<void *> comms((size_t)n, nullptr);
+    std::vector<int> devs((size_t)n);
+    for (int i = 0; i < n; i++) devs[(size_t)i] = ctxs[i]->device;
+    int rc = init_all(comms.data(), n, devs.data());
+    if (rc != 0) {
+        ctx->err = "ncclCommInitAll failed with code " + std::to_string(rc);
+        return SK_E_CUDA;
+    }
+    gstart();
+    for (int i = 0; i < n && rc == 0; i++) {
+        cudaSetDevice(ctxs[i]->device);
+        // ncclUint64 = 5, ncclSum = 0; the context's first slot stream carries the collective
+        rc = allreduce(ctxs[i]->d_totals, ctxs[i]->d_totals, (size_t)ctx->S + 2, 5, 0, comms[(size_t)i], ctxs[i]->slots[0].stream);
+    }
+    const int rc2 = gend();
+    for (int i = 0; i < n; i++) {
+        cudaSetDevice(ctxs[i]->device);
+        cudaStreamSynchronize(ctxs[i]->slots[0].stream);
+        destroy(comms[(size_t)i]);
+    }
+    if (rc != 0 || rc2 != 0) {
+        ctx->err = "ncclAllReduce (grouped) failed with code " + std::to_string(rc ? rc : rc2);
         return SK_E_CUDA;
     }
     return SK_OK;

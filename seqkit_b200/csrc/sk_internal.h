@@ -124,7 +124,8 @@ struct DevStats {
     unsigned int pad0;
     unsigned long long phase_cycles[16];  // -DSK_PHASE_TIMING: per-phase SM cycles summed over chunks (thread 0)
     // the two words every chunk hits with an atomic, each on a 128-byte line of its own
-    unsigned long long pad1[8];
+    unsigned long long compact_extent;  // per-sample compaction (sk_compact.cu): bytes of the compacted buffer in use
+    unsigned long long pad1[7];
     unsigned long long out_cursor;    // demux: bump allocator
     unsigned long long pad2[15];
     unsigned int ticket;              // dynamic chunk counter
@@ -163,6 +164,8 @@ struct SheetDev {
     const uint32_t *umask;   // S entries (u32) or 2*S (u64 as lo,hi): positions where the sheet has 'U'
     const uint8_t *lut;      // 256: bits 0-2 = 3-bit code (0 = matches no literal), bit 3 = [ACGTNacgtn+]
     uint32_t S, L, Umax, wide;
+    uint32_t u_uniform;            // 1: every sample has its 'U' at the same positions (the usual sheet) ...
+    unsigned long long u_mask;     // ... namely these: no per-record look-up of umask[]
     HalfIdx hidx;
     FastIdx fidx;
 };
@@ -268,5 +271,10 @@ int launch_fast_kernel(int geo, int op, const KParams &p, int sm_count, void *st
 bool warp_supported(int op, const KParams &p);
 int launch_tile_gather(const KParams &p, int sm_count, void *stream, const char **err);  // after an `unordered` launch
 int launch_warp_kernel(int op, const KParams &p, int sm_count, void *stream, const char **err);
+// Per-sample compaction of a demultiplex result (sk_compact.cu)
+uint64_t compact_work_bytes(uint32_t max_rows, uint32_t S);
+int launch_compact(const ChunkRow *rows, const Group *groups, uint32_t n_rows, uint32_t S, const uint8_t *src, uint8_t *dst,
+                   uint64_t dst_cap, void *work, unsigned long long *slices, unsigned long long *piece_dst, DevStats *st,
+                   int sm_count, void *stream, const char **err);
 
 }  // namespace sk

@@ -408,6 +408,166 @@ __device__ __forceinline__ bool plan_trim_lane16(const uint8_t *b, bool has, uin
     return lowest_k <= L2 - L1;
 }
 
+// Bytes [lo, hi) of the aligned 16-byte block at window offset a keep their value, the others become
+// `sub` (the byte whose contribution to the running total is zero); [lo, hi) = the block's part of the
+// quality string [L3, E).
+__device__ __forceinline__ uint4 blk16_keep(uint4 v, uint32_t a, uint32_t L3, uint32_t E, int sub) {
+    const uint32_t lo = a < L3 ? L3 - a : 0u;
+    const uint32_t hi = a + 16u > E ? (E > a ? E - a : 0u) : 16u;
+    const uint32_t sub4 = (uint32_t)sub * 0x01010101u;
+    auto keep = [&](uint32_t w, int q) {
+        const int l = (int)lo - 4 * q, h = (int)hi - 4 * q;
+        const uint32_t ml = l <= 0 ? 0xFFFFFFFFu : (l >= 4 ? 0u : 0xFFFFFFFFu << (8 * l));
+        const uint32_t mh = h >= 4 ? 0xFFFFFFFFu : (h <= 0 ? 0u : 0xFFFFFFFFu >> (8 * (4 - h)));
+        const uint32_t m = ml & mh;
+        return (w & m) | (sub4 & ~m);
+    };
+    return make_uint4(keep(v.x, 0), keep(v.y, 1), keep(v.z, 2), keep(v.w, 3));
+}
+// Summary of one aligned 16-byte block of a quality string, relative to an entering total of 0, in the
+// order the reference examines the bytes (highest address first, fasta_trim_by_quality.rs:33): keys
+// 16 * T + i, T = the total after the i-th byte examined.  mx / mn = the largest / smallest key of the
+// block (the smallest names the lowest total and, among equal totals, the byte examined first, :38),
+// last = the key after all sixteen bytes.  The four words are summarised on their own (four dot products
+// with constant accumulators, one min and one max of four) and then offset by the words before them.
+// 7-bit bytes; c0..c3 = -(j+1) * 16 * sub + j.
+struct Blk16 {
+    int mx, mn, last;
+};
+__device__ __forceinline__ Blk16 blk16_summary(const uint4 v, int c0, int c1, int c2, int c3) {
+#define SK_W4(w, k0, k1, k2, k3)                                 \
+    const int k0 = (int)__dp4a(w, 0x10000000u, (uint32_t)c0);    \
+    const int k1 = (int)__dp4a(w, 0x10100000u, (uint32_t)c1);    \
+    const int k2 = (int)__dp4a(w, 0x10101000u, (uint32_t)c2);    \
+    const int k3 = (int)__dp4a(w, 0x10101010u, (uint32_t)c3);
+    SK_W4(v.w, a0, a1, a2, a3)
+    SK_W4(v.z, b0, b1, b2, b3)
+    SK_W4(v.y, d0, d1, d2, d3)
+    SK_W4(v.x, e0, e1, e2, e3)
+#undef SK_W4
+    // a word's last key is 16 * sum + 3: the next word's keys start 16 * sum + 4 higher
+    const int B1 = a3 + 1, B2 = B1 + b3 + 1, B3 = B2 + d3 + 1;
+    Blk16 r;
+    r.mx = max3i(max3i(a0, a1, max(a2, a3)), max3i(b0, b1, max(b2, b3)) + B1,
+                 max(max3i(d0, d1, max(d2, d3)) + B2, max3i(e0, e1, max(e2, e3)) + B3));
+    r.mn = min3i(min3i(a0, a1, min(a2, a3)), min3i(b0, b1, min(b2, b3)) + B1,
+                 min(min3i(d0, d1, min(d2, d3)) + B2, min3i(e0, e1, min(e2, e3)) + B3));
+    r.last = B3 + e3;
+    return r;
+}
+// 0x80 in every byte position <=> none of the sixteen (7-bit) bytes is below '!'
+__device__ __forceinline__ uint32_t blk16_ge33(const uint4 v) {
+    const uint32_t A = 0x5F5F5F5Fu;
+    return (v.x + A) & (v.y + A) & (v.z + A) & (v.w + A);
+}
+
+// fasta_trim_by_quality.rs:28-48 for one record per lane with block summaries that do not depend on each
+// other: every lane goes down its quality string two aligned 16-byte blocks per step; a block's summary
+// (blk16_summary) is relative to an entering total of 0, so the sixteen running totals of a block wait
+// for nothing but the block's bytes, and the walk itself -- break (:37), minimum (:38), entering total of
+// the next block -- is a handful of instructions per block.  The warp leaves the loop when every lane has
+// met its break or the start of its string; only then does a lane that broke look into its break block,
+// whose totals before the break may still lower the minimum.  Bytes below '!' take the wrapping u8
+// subtraction (:35): a lane that saw one says so in `cold` and the caller repeats the record byte-wise.
+// Must be called by all 32 lanes (`has` = this lane carries a record).  33 + min_baseq <= 127.
+__device__ __forceinline__ bool plan_trim_blocks(const uint8_t *b, bool has, uint32_t L1, uint32_t L2, uint32_t L3, uint32_t L4,
+                                                 int minq, uint8_t &mode, uint32_t &kk, uint32_t &body_len, bool &cold) {
+    constexpr uint32_t FULL = 0xffffffffu, NONE = 0xFFFFFFFFu;
+    uint32_t k = has ? L4 - L3 : 0u;
+#pragma unroll 1
+    while (k > 0 && is_ws(b[L3 + k - 1])) k--;  // qual.trim_end().len()  (:31)
+    __syncwarp();
+    const uint32_t E = L3 + k;
+    const int sub = 33 + minq, s16 = 16 * sub;
+    const int c0 = -s16, c1 = -2 * s16 + 1, c2 = -3 * s16 + 2, c3 = -4 * s16 + 3;
+    const uint32_t a_bot = L3 & ~15u;
+    uint32_t a = k ? ((E - 1u) & ~15u) : 0u;  // block examined next (a dead lane keeps re-reading its last block)
+    int total = -50, lowest = -50;            // :28-29
+    uint32_t lowest_k = k;
+    uint32_t brk_a = NONE;
+    int brk_total = 0;
+    uint32_t ge33 = 0x80808080u;
+    bool live = k > 0;
+    // one block of the walk: `on` = the lane has reached this block
+    auto walk = [&](bool on, uint32_t at, const Blk16 &s) {
+        if (on) {
+            const int e16 = 16 * total;
+            if (e16 + s.mx > 15) {  // a total above 0 (:37) inside this block
+                brk_a = at;
+                brk_total = total;
+                live = false;
+            } else {
+                const int cand = e16 + s.mn;
+                if ((cand >> 4) < lowest) {  // strict '<': an earlier block keeps a tie
+                    lowest = cand >> 4;
+                    lowest_k = at + 15u - (uint32_t)(cand & 15) - L3;
+                }
+                total += (s.last - 15) >> 4;
+                if (at == a_bot) live = false;
+            }
+        }
+    };
+#pragma unroll 1
+    while (__any_sync(FULL, live)) {
+        const bool two = live && a != a_bot;
+        const uint32_t a2 = two ? a - 16u : a;
+        uint4 v1 = *(const uint4 *)(b + a), v2 = *(const uint4 *)(b + a2);
+        const bool edge = a + 16u > E || a2 < L3;
+        if (__any_sync(FULL, live && edge)) {  // the two ends of the string only
+            if (edge) {
+                v1 = blk16_keep(v1, a, L3, E, sub);
+                v2 = blk16_keep(v2, a2, L3, E, sub);
+            }
+        }
+        ge33 &= live ? blk16_ge33(v1) & blk16_ge33(v2) : 0xFFFFFFFFu;  // (a dead lane's block is not masked)
+        const Blk16 s1 = blk16_summary(v1, c0, c1, c2, c3), s2 = blk16_summary(v2, c0, c1, c2, c3);
+        walk(live, a, s1);
+        walk(live && two, a2, s2);
+        if (live) a = a2 - 16u;
+    }
+    if (__any_sync(FULL, brk_a != NONE)) {
+        if (brk_a != NONE) {  // the totals of the break block up to the break
+            const uint4 v = blk16_keep(*(const uint4 *)(b + brk_a), brk_a, L3, E, sub);
+            int K[16];
+            int base = 16 * brk_total;
+#define SK_KEY4(w, q)                                                                   \
+    K[4 * q + 0] = (int)__dp4a(w, 0x10000000u, (uint32_t)(base + c0 + 4 * q));          \
+    K[4 * q + 1] = (int)__dp4a(w, 0x10100000u, (uint32_t)(base + c1 + 4 * q));          \
+    K[4 * q + 2] = (int)__dp4a(w, 0x10101000u, (uint32_t)(base + c2 + 4 * q));          \
+    K[4 * q + 3] = (int)__dp4a(w, 0x10101010u, (uint32_t)(base + c3 + 4 * q));          \
+    base = K[4 * q + 3] - (4 * q + 3);
+            SK_KEY4(v.w, 0)
+            SK_KEY4(v.z, 1)
+            SK_KEY4(v.y, 2)
+            SK_KEY4(v.x, 3)
+#undef SK_KEY4
+            bool ok = true;
+            int best = 0x7FFFFFFF;
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                ok = ok && K[i] <= 15;  // totals after the break are never looked at
+                best = (ok && K[i] < best) ? K[i] : best;
+            }
+            if (best != 0x7FFFFFFF && (best >> 4) < lowest) {
+                lowest = best >> 4;
+                lowest_k = brk_a + 15u - (uint32_t)(best & 15) - L3;
+            }
+        }
+    }
+    __syncwarp();
+    cold = k > 0 && (ge33 & 0x80808080u) != 0x80808080u;
+    if (lowest_k == 0) {  // :44-45
+        mode = B_GARBAGE;
+        kk = 0;
+        body_len = 6;  // "N\n+\n!\n"
+        return true;
+    }
+    mode = B_TRIM;
+    kk = lowest_k;
+    body_len = 2 * lowest_k + 4;  // seq[..k] "\n+\n" qual[..k] "\n"  (:47)
+    return lowest_k <= L2 - L1;
+}
+
 // plan_trim_warp with two adjacent lanes per record (sub = 0 / 1): the pair walks the quality string
 // down sixteen bytes per step, lane 0 on the upper 8-byte block and lane 1 on the one below it; each
 // lane computes its block's totals relative to 0, one shuffle gives lane 1 the sum of lane 0's block

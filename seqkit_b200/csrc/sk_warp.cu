@@ -46,6 +46,15 @@ extern __shared__ __align__(128) unsigned char sk_smem[];
 #ifndef SKW_GROUP_WARPS
 #define SKW_GROUP_WARPS 8  // warps that take consecutive tiles and start them together (8 = the CTA, or 4)
 #endif
+#ifndef SKW_EMIT_RUNS
+#define SKW_EMIT_RUNS 1  // sector emit run by run (0: one piece per step, every step through the run table)
+#endif
+#ifndef SKW_EARLY_PROBE
+#define SKW_EARLY_PROBE 0  // mate 1: 1 = barcode search, hash and table probes before the quality trim (measured: no gain)
+#endif
+#ifndef SKW_TRIM_BLOCKS
+#define SKW_TRIM_BLOCKS 0  // quality trim with independent 16-byte block summaries (0: plan_trim_lane16)
+#endif
 
 namespace sk {
 
@@ -204,6 +213,33 @@ static __device__ __noinline__ uint32_t plan_trim_cold(const uint8_t *b, uint32_
     uint32_t kk = 0, body_len = 0;
     const bool fine = plan_trim_body(b, L1, L2, L3, L4, minq, mode, kk, body_len);
     return (kk & 0xFFFFu) | ((uint32_t)mode << 16) | (fine ? 1u << 24 : 0u);
+}
+
+// fasta_trim_by_quality.rs:28-48 for one record per lane (all 32 lanes call; `ok` = this lane carries a
+// record): block summaries in the usual case, the byte-wise form for a lane whose quality string holds a
+// byte below '!' (wrapping u8 subtraction, :35) and for thresholds outside the block form's range.
+__device__ __forceinline__ bool plan_trim_any(const uint8_t *win, bool ok, uint32_t L1, uint32_t L2, uint32_t L3, uint32_t L4,
+                                              int trim_q, uint8_t &mode, uint32_t &kk, uint32_t &body) {
+    bool fine = true, cold = ok;
+#if SKW_TRIM_BLOCKS
+    if (trim_q <= 94) fine = plan_trim_blocks(win, ok, L1, L2, L3, L4, trim_q, mode, kk, body, cold);
+#else
+    if (trim_q <= 222) {
+        fine = plan_trim_lane16(win, ok, L1, L2, L3, L4, trim_q, mode, kk, body);
+        cold = false;
+    }
+#endif
+    if (__any_sync(0xffffffffu, cold)) {
+        if (cold) {
+            const uint32_t pk = plan_trim_cold(win, L1, L2, L3, L4, trim_q);
+            kk = pk & 0xFFFFu;
+            mode = (uint8_t)(pk >> 16);
+            fine = (pk >> 24) != 0u;
+            body = mode == B_GARBAGE ? 6u : 2u * kk + 4u;
+        }
+        __syncwarp();
+    }
+    return fine;
 }
 
 // Look-back of the warp engine over p.tile_lines: inc[c] (u64: bit 63 | lines through tile c) and, behind
@@ -574,18 +610,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                     }
                     bool fine = true;
                     uint32_t body = 0;
-                    if (trim_q <= 222) {
-                        fine = plan_trim_lane16(win, ok, L1, L2, L3, L4, trim_q, mode, kk, body);
-                    } else {
-                        if (ok) {
-                            const uint32_t pk = plan_trim_cold(win, L1, L2, L3, L4, trim_q);
-                            kk = pk & 0xFFFFu;
-                            mode = (uint8_t)(pk >> 16);
-                            fine = (pk >> 24) != 0u;
-                            body = mode == B_GARBAGE ? 6u : 2u * kk + 4u;
-                        }
-                        __syncwarp();
-                    }
+                    fine = plan_trim_any(win, ok, L1, L2, L3, L4, trim_q, mode, kk, body);
                     if (!ok) {
                         mode = B_NONE;
                     } else if (!fine) {  // &seq[..k] would panic (:47)
@@ -626,37 +651,16 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 const uint32_t L0 = LB(j), L1 = LB(j + 1), L2 = LB(j + 2), L3 = LB(j + 3), L4 = LB(j + 4);
                 uint8_t mode = B_VERBATIM;
                 uint32_t kk = 0, body = L4 - L1;  // three lines verbatim (:209-212)
-                if (fused) {
-                    const bool ok = has && L1 > L0 && win[L1 - 1] == '\n';
-                    bool fine;
-                    mode = B_FAIL;
-                    if (trim_q <= 222) {
-                        fine = plan_trim_lane16(win, ok, L1, L2, L3, L4, trim_q, mode, kk, body);
-                    } else {
-                        fine = true;
-                        if (ok) {
-                            const uint32_t pk = plan_trim_cold(win, L1, L2, L3, L4, trim_q);
-                            kk = pk & 0xFFFFu;
-                            mode = (uint8_t)(pk >> 16);
-                            fine = (pk >> 24) != 0u;
-                            body = mode == B_GARBAGE ? 6u : 2u * kk + 4u;
-                        }
-                        __syncwarp();
-                    }
-                    if (!ok || !fine) mode = B_FAIL;
-                }
-                // trim / mask by quality: failure kind in errk, output length in slen
-                uint32_t errk = 0, slen = 0;
-                if (!IS_DEMUX) slen = stream_plan(has, L0, L1, L2, L3, L4, mode, kk, errk);
                 int sample = -1;
                 unsigned long long um = 0;  // positions where the sample's sheet barcode has 'U'
                 uint32_t alen = 0, blen = 0, cut0 = 0, cut1 = 0, taglen = 0xFFu;
-                if (!IS_DEMUX) {
-                } else if (D1) {
-                    // fasta_demultiplex.rs:117-194: validate, locate the barcode, match, decide.  Outcome:
-                    // sample >= 0 assigned; -2 ambiguous (best, last, mismatches in alen, blen, taglen);
-                    // -1 unassigned (taglen = failure kind, or 0xFF for a record that never reached the match)
-                    bool live = has;
+                // mate 1, first half (fasta_demultiplex.rs:117-150): validate, locate the barcode, hash its two
+                // halves and send the two table probes on their way -- they come back while the quality trim runs
+                bool live = D1 && has;
+                uint32_t raw[NWMAX + 1];
+                FProbe probe;
+                uint32_t bs = 0;
+                auto d1_locate = [&]() {
                     uint32_t stp = 0;
                     if (live) {
                         if (win[L0] != '@') {
@@ -671,14 +675,33 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                         }
                     }
                     __syncwarp();
-                    uint32_t raw[NWMAX + 1];
-                    FProbe probe;
-                    const uint32_t bs = stp + 4;
+                    bs = stp + 4;
                     if (live) {
                         cut0 = stp - L0;
                         cut1 = cut0 + 4 + Lb;
                         load_raw<NWMAX + 1>(win, bs, (Lb + 4u) >> 2, raw);
                         probe = fidx_issue<NWMAX + 1>(raw, p.sheet.hidx, p.sheet.fidx, hcls, 0u);  // consumed after the class check
+                    }
+                    __syncwarp();
+                };
+                if (D1 && SKW_EARLY_PROBE) d1_locate();
+                if (fused) {
+                    const bool ok = has && L1 > L0 && win[L1 - 1] == '\n';
+                    bool fine;
+                    mode = B_FAIL;
+                    fine = plan_trim_any(win, ok, L1, L2, L3, L4, trim_q, mode, kk, body);
+                    if (!ok || !fine) mode = B_FAIL;
+                }
+                // trim / mask by quality: failure kind in errk, output length in slen
+                uint32_t errk = 0, slen = 0;
+                if (!IS_DEMUX) slen = stream_plan(has, L0, L1, L2, L3, L4, mode, kk, errk);
+                if (!IS_DEMUX) {
+                } else if (D1) {
+                    // fasta_demultiplex.rs:148-194, second half: barcode length, match, decide.  Outcome:
+                    // sample >= 0 assigned; -2 ambiguous (best, last, mismatches in alen, blen, taglen);
+                    // -1 unassigned (taglen = failure kind, or 0xFF for a record that never reached the match)
+                    if (!SKW_EARLY_PROBE) d1_locate();
+                    if (live) {
                         if (!class_run_is<NWMAX + 1>(raw, sh_lut, Lb, L1 - bs)) {  // :38, :148-150
                             taglen = K_BC_LEN;
                             live = false;
@@ -702,7 +725,9 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                     }
                     __syncwarp();
                     if (sample >= 0) {
-                        um = p.sheet.wide ? ((const unsigned long long *)p.sheet.umask)[sample] : (unsigned long long)p.sheet.umask[sample];
+                        um = p.sheet.u_uniform ? p.sheet.u_mask
+                             : p.sheet.wide  ? ((const unsigned long long *)p.sheet.umask)[sample]
+                                             : (unsigned long long)p.sheet.umask[sample];
                         header_pieces(win, L0, L1, L0 + cut0, L0 + cut1, alen, blen);  // drain (:145) + trim_end (:206)
                         const uint32_t ul = sh_ulen[sample];
                         taglen = ul ? 5 + ul : 0;  // " UMI:" + umi (:207)
@@ -1109,6 +1134,73 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                     if (lane == 0) rt[96] = round_out;
                     __syncwarp();
                     uint8_t *gbase = p.out + rbase;
+#if SKW_EMIT_RUNS
+                    // The lane goes through the three runs of its record in turn.  Sectors that lie inside one
+                    // run are one unaligned 32-byte read of the window and one store (no merge, no table); the
+                    // sector that straddles the end of a run -- at most one per run -- is put together from the
+                    // tail of this run and the heads of the runs that follow (the next records' runs if need be).
+                    {
+                        uint32_t i = 3u * (uint32_t)lane;
+                        uint32_t e = rt[i], en = rt[i + 1];
+                        uint32_t o = (my_off + 31u) & ~31u;
+#pragma unroll 1
+                        for (int q = 0; q < 3; q++) {
+                            const uint32_t rb = emit ? (en & 0xFFFFu) : 0u;  // end of this run in the round's output
+                            const int delta = (int)(e >> 16) - (int)(e & 0xFFFFu);
+                            bool in = o + 32u <= rb;
+                            {   // consecutive sectors of a run share a word of the window: eight loads per sector, not nine
+                                const int so = (int)o + delta;
+                                const uint32_t *pw = (const uint32_t *)(win + (so & ~3));
+                                const uint32_t sh = ((uint32_t)so & 3u) * 8u;
+                                uint32_t lo = in ? pw[0] : 0u;
+#pragma unroll 1
+                                while (__any_sync(FULL, in)) {
+                                    if (in) {
+                                        const uint32_t w1 = pw[1], w2 = pw[2], w3 = pw[3], w4 = pw[4], w5 = pw[5], w6 = pw[6], w7 = pw[7], w8 = pw[8];
+                                        stg256(gbase + o, __funnelshift_r(lo, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                                               __funnelshift_r(w3, w4, sh), __funnelshift_r(w4, w5, sh), __funnelshift_r(w5, w6, sh),
+                                               __funnelshift_r(w6, w7, sh), __funnelshift_r(w7, w8, sh));
+                                        lo = w8;
+                                        pw += 8;
+                                        o += 32u;
+                                        in = o + 32u <= rb;
+                                    }
+                                }
+                            }
+                            bool seam = o < rb;
+                            if (__any_sync(FULL, seam)) {
+                                uint32_t si = i, se = e, sen = en, filled = 0;
+                                U256 v;
+#pragma unroll
+                                for (int k = 0; k < 8; k++) v.w[k] = 0u;
+#pragma unroll 1
+                                while (__any_sync(FULL, seam)) {
+                                    if (seam) {
+#pragma unroll 1
+                                        while ((sen & 0xFFFFu) <= o + filled && si < 95u) {  // runs that end before the next byte
+                                            si++;
+                                            se = sen;
+                                            sen = rt[si + 1];
+                                        }
+                                        const U256 ld = lds_unaligned32(win, (int)(se >> 16) + (int)o - (int)(se & 0xFFFFu));
+                                        v = merge_low32(v, ld, filled);
+                                        const uint32_t upto = (sen & 0xFFFFu) - o;  // bytes of the sector known after this run
+                                        if (upto >= 32u || (sen & 0xFFFFu) >= round_out) {
+                                            stg256(gbase + o, v.w[0], v.w[1], v.w[2], v.w[3], v.w[4], v.w[5], v.w[6], v.w[7]);
+                                            o += 32u;
+                                            seam = false;
+                                        } else {
+                                            filled = upto;
+                                        }
+                                    }
+                                }
+                            }
+                            i++;
+                            e = en;
+                            en = rt[i + 1];
+                        }
+                    }
+#else
                     // One step = one piece: read 32 bytes of the current run at the offset that puts them in
                     // place, merge them behind the bytes the sector already has, then either store the sector
                     // (full, or the round's last) or move on to the next run.  Every lane takes the same path
@@ -1145,6 +1237,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                             }
                         }
                     }
+#endif
                     if (emit) {
                         Group g;
                         g.sample = (uint16_t)sample;

@@ -39,7 +39,7 @@ def _check(ctx, rc, what):
 
 class Engine:
     def __init__(self, device: int = 0, max_stream_bytes: int = 32 << 20, max_records: int = 1 << 19,
-                 n_slots: int = 1, max_samples: int = 1024, aux_streams: bool = True):
+                 n_slots: int = 1, max_samples: int = 1024, aux_streams: bool = True, compact: bool = True):
         self.lib = L.lib()
         lim = L.Limits(max_stream_bytes, max_records, n_slots, max_samples, 1 if aux_streams else 0, 0)
         ctx = C.c_void_p()
@@ -48,6 +48,9 @@ class Engine:
             raise L.SkError("sk_ctx_create failed (%d): %s" % (rc, (self.lib.sk_last_error(None) or b"").decode()))
         self.ctx = ctx
         self.max_records = max_records
+        # per-sample output streams come from the device-side compaction (sk_demux_compact); False: from the
+        # per-record slice tables and the host helper sk_demux_gather
+        self.compact = compact
         self.S = 0
         self.L = 0
 
@@ -206,6 +209,8 @@ class Engine:
 
     def _demux_call(self, opts):
         _check(self.ctx, self.lib.sk_demultiplex(self.ctx, 0, C.byref(opts)), "sk_demultiplex")
+        if self.compact and not opts.no_output:
+            _check(self.ctx, self.lib.sk_demux_compact(self.ctx, 0), "sk_demux_compact")
         res = self.wait()
         self._refuse(res)
         return res
@@ -213,6 +218,20 @@ class Engine:
     def _gather_files(self, res, names, paired):
         files = {}
         S = self.S
+        if res.reserved & 8:  # compacted on the device: one slice per sample and mate
+            for mate in range(2 if paired else 1):
+                n = res.out_extent[mate]
+                buf = C.create_string_buffer(max(n, 1))
+                sl = (L.Slice * (S + 1))()
+                _check(self.ctx, self.lib.sk_download_compact(self.ctx, 0, mate, buf, n), "sk_download_compact")
+                _check(self.ctx, self.lib.sk_download_slices(self.ctx, 0, mate, sl), "sk_download_slices")
+                self.wait()
+                assert sl[S].offset == n and sl[S].len == res.out_bytes[mate], "slice table and outcome block disagree"
+                raw = buf.raw
+                for s, name in enumerate(names):
+                    key = (name + (b"_%d.fq.gz" % (mate + 1) if paired else b".fq.gz")).decode()
+                    files[key] = raw[sl[s].offset:sl[s].offset + sl[s].len]
+            return files
         for mate in range(2 if paired else 1):
             n = res.out_extent[mate]
             out = self.fetch_out(mate, n)
