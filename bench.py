@@ -7,9 +7,14 @@ sheet (10+10 bp, literal '+', 8 bp UMI -> 29-character barcodes), synthetic FAST
 device.  The 1 B-pair job does not fit any memory, so it is streamed: a "step" is one batch of
 `--pairs` read pairs per GPU (weak scaling: every rank processes its own contiguous pair range).
 
-  value     reads/s over all ranks with inputs resident in HBM (CUDA events on the kernels' stream)
-  e2e       the same metric through the C ABI with HOST buffers: pinned H2D upload, kernels, D2H of
-            outputs + tables, 3 slots in flight
+  value     reads/s over all ranks with inputs resident in HBM (CUDA events on the kernels' stream): the two
+            fused trim+demultiplex passes, as in round 1.  `value_with_compaction` adds the device-side
+            per-sample compaction of both mates (one contiguous output run per sample; `value_breakdown`
+            gives its cost in ms per step)
+  e2e       the same metric through the C ABI with HOST buffers: pinned H2D upload, kernels, compaction, D2H
+            of the per-sample streams (compacted buffers + slice tables), 3 slots in flight, the host thread
+            and its pinned buffers on the GPU's NUMA node
+  configs   device time, algorithmic bytes and roofline fraction of BASELINE configs[0..3] as well
   roofline  algorithmic bytes (input once + output once) / average device time of the dominant
             kernel, against MEASURED_PEAKS.json
   cpu_baseline  the CPU oracle (port of the reference; the Rust reference cannot be built here)
@@ -155,28 +160,39 @@ def synth_pair(eng, n_pairs, first_pair, seed=5):
     return n1, n2
 
 
+def host_pairs(bcs, n_pairs, first_pair=0, seed=5, threads=None):
+    """Both mates of `n_pairs` read pairs from the HOST twin of the device generator (oracle/synth_host.c):
+    the same bytes as Engine.synth for the same (seed, range), without loading the product's library."""
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import pyoracle as O
+    O.build()
+    threads = threads or max(1, min(os.cpu_count() or 1, 32))
+    per = (n_pairs + threads - 1) // threads
+    jobs = [(m, first_pair + k * per, max(0, min(per, n_pairs - k * per))) for m in (1, 2) for k in range(threads)]
+    with ThreadPoolExecutor(threads) as ex:  # (ctypes releases the GIL)
+        parts = list(ex.map(lambda j: O.synth_fastq(j[2], seed=seed, first_pair=j[1], read_len=READ_LEN, mate=j[0],
+                                                    barcodes=bcs), jobs))
+    return b"".join(parts[:threads]), b"".join(parts[threads:])
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
-    from seqkit_b200 import Engine
     bcs = make_sheet()
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 64))
     n_pairs = args.ref_pairs_per_core * procs
-    with Engine(max_stream_bytes=n_pairs * 420 + (1 << 20), max_records=n_pairs, max_samples=N_SAMPLES,
-                aux_streams=False) as eng:  # input creation only: the timed path below is pure CPU
-        eng.set_sheet(bcs)
-        n1, n2 = synth_pair(eng, n_pairs, 0)
-        r1, r2 = eng.download_in(0, n1), eng.download_in(1, n2)
+    r1, r2 = host_pairs(bcs, n_pairs)  # input creation only: no GPU, no libseqkit_b200.so in this arm
     rps, dt = time_oracle(sheet_text(bcs), r1, r2, n_pairs, procs, args.steps, max(args.warmup, 1))
     line = {
         "impl": "reference", "metric": "reads_per_s", "value": rps, "unit": "reads/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "gbases_per_s": rps * READ_LEN / 1e9,
-        "config": workload_config(n_pairs, note="CPU arm: bounded sample of the same workload per step"),
+        "config": workload_config(args.pairs),
         "cpu_baseline": {"value": rps, "unit": "reads/s", "cores": procs, "kind": "port",
-                         "sample": "%d pairs per step, %d independent shards (oracle/fasta_oracle.c, in memory, no gzip)"
+                         "sample": "%d pairs per step (bounded sample of the workload), %d independent shards "
+                                   "(oracle/fasta_oracle.c, in memory, no gzip); input from oracle/synth_host.c"
                                    % (n_pairs, procs)},
         "e2e": {"value": rps, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -217,7 +233,7 @@ def main():
     os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=8_000_000, help="read pairs per GPU per step (device-resident)")
@@ -228,6 +244,7 @@ def main():
     ap.add_argument("--cli-pairs", type=int, default=200_000,
                     help="bounded sample for the files+gzip end-to-end leg (the `fasta` binary; 0 = skip)")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-configs", action="store_true", help="no device-time legs for BASELINE configs[0..3]")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -256,18 +273,21 @@ def main():
     bcs = make_sheet()
     P = args.pairs
     steps, warm = args.steps, max(args.warmup, 3)
-    eng = Engine(device=local_rank, max_stream_bytes=P * 410 + (1 << 20), max_records=P, n_slots=1,
-                 max_samples=N_SAMPLES, aux_streams=False)
+    cfg_reads = 0 if args.skip_configs else 10_000_000  # configs[1] wants 10 M single-end reads resident
+    eng = Engine(device=local_rank, max_stream_bytes=max(P * 410, cfg_reads * 345) + (1 << 20),
+                 max_records=max(P, cfg_reads), n_slots=1, max_samples=N_SAMPLES, aux_streams=False)
     lib = eng.lib
     eng.set_sheet(bcs)
     n1, n2 = synth_pair(eng, P, rank * P)  # weak scaling: rank r owns pairs [r*P, (r+1)*P)
     opts = L.DemuxOpts(MIN_BASEQ, 0, 0, 0, 0)
     stream = torch.cuda.ExternalStream(lib.sk_slot_stream(eng.ctx, 0), device=local_rank)
 
-    def step():
+    def step(compact=True):
         rc = lib.sk_demultiplex(eng.ctx, 0, C.byref(opts))
+        if rc == 0 and compact:
+            rc = lib.sk_demux_compact(eng.ctx, 0)
         if rc != 0:
-            raise RuntimeError("sk_demultiplex failed: %s" % lib.sk_last_error(eng.ctx).decode())
+            raise RuntimeError("sk_demultiplex / sk_demux_compact failed: %s" % lib.sk_last_error(eng.ctx).decode())
 
     # the one collective of the path: per-sample counts merged over NVLink with a single NCCL all-reduce
     comm = C.c_void_p()
@@ -288,45 +308,56 @@ def main():
         assert lib.sk_allreduce_counts(eng.ctx, 0, comm) == 0, lib.sk_last_error(eng.ctx)
     res = eng.wait()
     assert res.status == 0 and res.n_records == P, (res.status, res.n_records)
-    # sk_result.reserved: bit0 = the warp / lean engine ran, bit1 = it was re-run on the general engine
-    assert res.reserved == 1, "bench workload must run on the warp engine without a re-run (got %d)" % res.reserved
+    # sk_result.reserved: bit0 = the warp / lean engine ran, bit1 = it was re-run on the general engine, bit3 = compacted
+    assert (res.reserved & 3) == 1, "bench workload must run on the warp engine without a re-run (got %d)" % res.reserved
+    assert res.reserved & 8, "the per-sample compaction must have run"
     pairs_done = res.n_records
+
+    def timed(n_steps, compact):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record(stream)
+        for _ in range(n_steps):
+            step(compact)
+        if world > 1:
+            assert lib.sk_allreduce_counts(eng.ctx, 0, comm) == 0, lib.sk_last_error(eng.ctx)
+        ev1.record(stream)
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
 
     sampler = ClockSampler(local_rank)
     sampler.start()
     time.sleep(0.3)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    for _ in range(steps):
-        step()
-    if world > 1:
-        assert lib.sk_allreduce_counts(eng.ctx, 0, comm) == 0, lib.sk_last_error(eng.ctx)
-    ev1.record(stream)
-    barrier()
-    ms_total = ev0.elapsed_time(ev1)
+    ms_total = timed(steps, False)
     res = eng.wait()
     assert res.status == 0, res.status
     launches = res.gpu_launches * steps
     counts = (C.c_uint64 * (N_SAMPLES + 2))()
     lib.sk_download_counts(eng.ctx, 0, counts)
     if world > 1:
-        t = torch.tensor([ms_total], device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
         assert counts[N_SAMPLES] == P * world, "all-reduced total_reads must cover every rank"
     clocks = sampler.finish()
     ms_step = ms_total / steps
     value = 2.0 * P * world / (ms_step * 1e-3)
+    ms_demux_only = ms_step
+    ms_with_compaction = timed(steps, True) / steps  # + the per-sample compaction of both mates
+    res_c = eng.wait()
+    assert res_c.status == 0 and res_c.reserved & 8
 
     # per-kernel device time (CUDA events around each launch, on the launching stream)
     lib.sk_set_profiling(eng.ctx, 1)
     pass_ms = [0.0, 0.0]
-    for _ in range(steps):
-        step()
+    prof_steps = min(steps, 20)
+    for _ in range(prof_steps):
+        step(False)
         r = eng.wait()
-        pass_ms[0] += r.pass_ms[0] / steps
-        pass_ms[1] += r.pass_ms[1] / steps
+        pass_ms[0] += r.pass_ms[0] / prof_steps
+        pass_ms[1] += r.pass_ms[1] / prof_steps
     lib.sk_set_profiling(eng.ctx, 0)
     bytes_pass = [n1 + res.out_bytes[0], n2 + res.out_bytes[1]]
     dom = 0 if pass_ms[0] >= pass_ms[1] else 1
@@ -337,11 +368,11 @@ def main():
         kname = lambda k: "sk_fast_kernel<%s, OP_DEMUX%d>" % (geo, k + 1)
     else:
         kname = lambda k: "sk_warp_kernel<OP_DEMUX%d>" % (k + 1)
-    # DRAM traffic of the dominant kernel from the committed ncu capture (dram__bytes_read + write, 1 M pairs
-    # per launch), scaled to this launch's pairs; null when the summary is missing
+    # DRAM traffic of the dominant kernel from this round's committed ncu capture (dram__bytes_read + write,
+    # 1 M pairs per launch), scaled to this launch's pairs; null when the summary is missing
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
             tj = json.load(f)
         traffic = tj["dram_bytes_per_launch"]["DEMUX%d" % (dom + 1)] * (P / float(tj["pairs_per_launch"]))
     except Exception:
@@ -351,11 +382,20 @@ def main():
                 "algorithmic_bytes_per_launch": bytes_pass[dom], "ms_per_launch": pass_ms[dom],
                 "other_kernel": {"kernel": kname(1 - dom), "ms_per_launch": pass_ms[1 - dom],
                                  "achieved": bytes_pass[1 - dom] / (pass_ms[1 - dom] * 1e-3) / 1e9},
-                "step_bytes": sum(bytes_pass), "step_achieved": sum(bytes_pass) / (ms_step * 1e-3) / 1e9,
+                "step_bytes": sum(bytes_pass), "step_achieved": sum(bytes_pass) / (ms_demux_only * 1e-3) / 1e9,
                 # against the nominal figure of the north star as well (~8 TB/s)
                 "frac_of_nominal_8000_gbs": achieved / 8000.0}
     identified = counts[N_SAMPLES + 1]
     out_bytes = [int(res.out_bytes[0]), int(res.out_bytes[1])]
+    compact_ms = ms_with_compaction - ms_demux_only
+    breakdown = {"demux1_ms": pass_ms[0], "demux2_ms": pass_ms[1], "compact_ms": compact_ms,
+                 "step_ms": ms_step, "step_ms_with_compaction": ms_with_compaction,
+                 "compact": {"kernels": "sk_compact_hist/cols/bases/addr/move_kernel, both mates",
+                             "algorithmic_bytes": 2 * sum(out_bytes),  # the emitted bytes once more in and out
+                             "achieved": 2 * sum(out_bytes) / (max(compact_ms, 1e-6) * 1e-3) / 1e9,
+                             "frac": 2 * sum(out_bytes) / (max(compact_ms, 1e-6) * 1e-3) / 1e9 / peak}}
+    value_with_compaction = 2.0 * P * world / (ms_with_compaction * 1e-3)
+    configs = None
     # the path's other two operators on the same resident mate-1 stream (BASELINE configs[0] / [1] shapes):
     # device time per launch and algorithmic bytes (input once + output once), for the record
     if rank == 0:
@@ -381,9 +421,24 @@ def main():
             other[name] = {"kernel": kn, "engine_bits": eng_bits,
                            "reads_per_launch": P, "ms_per_launch": ms, "algorithmic_bytes_per_launch": n1 + ob,
                            "achieved": (n1 + ob) / (ms * 1e-3) / 1e9, "frac": (n1 + ob) / (ms * 1e-3) / 1e9 / peak}
-        lib.sk_set_profiling(eng.ctx, 0)
         roofline["other_ops"] = other
+        if not args.skip_configs:
+            try:
+                configs = run_configs(eng, L, P, peak)
+                configs["configs[3] add barcode"] = run_add_barcode_leg(local_rank, peak)
+            except Exception as ex:  # reported extras: never cost the contract line
+                configs = {"error": "%s: %s" % (type(ex).__name__, ex)}
+        lib.sk_set_profiling(eng.ctx, 0)
     eng.close()
+
+    # ---- bytes, not only counts: per-sample streams are a function of the pair range, whichever GPU / batching
+    verify = None
+    try:
+        verify = verify_ranges(torch, L, bcs, local_rank, rank, world)
+    except AssertionError:
+        raise
+    except Exception as ex:
+        verify = {"error": "%s: %s" % (type(ex).__name__, ex)}
 
     # ---- e2e: host buffers through the C ABI, 3 slots in flight
     e2e = None
@@ -393,11 +448,7 @@ def main():
     # ---- CPU baseline (rank 0, N=1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
-        with Engine(device=local_rank, max_stream_bytes=args.cpu_pairs * 420 + (1 << 20), max_records=args.cpu_pairs,
-                    max_samples=N_SAMPLES, aux_streams=False) as e2:
-            e2.set_sheet(bcs)
-            m1, m2 = synth_pair(e2, args.cpu_pairs, 0)
-            r1, r2 = e2.download_in(0, m1), e2.download_in(1, m2)
+        r1, r2 = host_pairs(bcs, args.cpu_pairs)
         rps, dt = time_oracle(sheet_text(bcs), r1, r2, args.cpu_pairs, 1, 1, 0)
         cpu = {"value": rps, "unit": "reads/s", "cores": 1, "kind": "port",
                "sample": "%d pairs (same generator), oracle/fasta_oracle.c trim x2 + demultiplex in memory, %.1f s"
@@ -418,8 +469,11 @@ def main():
             "data": "synthetic", "config": workload_config(P), "gbases_per_s": value * READ_LEN / 1e9,
             "pairs_per_s": value / 2, "identified_fraction": identified / float(P * world),
             "bytes_per_step_per_gpu": {"in": [n1, n2], "out": out_bytes},
+            "value_includes": "the two fused trim+demultiplex passes (round-1 definition); value_with_compaction adds "
+                              "the device-side per-sample compaction of both mates",
+            "value_with_compaction": value_with_compaction, "value_breakdown": breakdown,
             "clocks": clocks, "gpu_launches": launches, "roofline": roofline, "e2e": e2e, "cpu_baseline": cpu,
-            "e2e_files_gzip": e2e_files,
+            "e2e_files_gzip": e2e_files, "configs": configs, "verify": verify,
         }
         emit_line(line)
     if world > 1:
@@ -442,11 +496,7 @@ def run_cli_leg(args, bcs, local_rank, with_cpu=True):
         subprocess.check_call(["make", "-s", "-C", ROOT, "seqkit_b200/fasta"])
     O.build()
     oracle_cli = os.path.join(ROOT, "oracle", "_build", "fasta_oracle")
-    with Engine(device=local_rank, max_stream_bytes=n * 420 + (1 << 20), max_records=n, max_samples=N_SAMPLES,
-                aux_streams=False) as e3:
-        e3.set_sheet(bcs)
-        m1, m2 = synth_pair(e3, n, 0, seed=11)
-        r1, r2 = e3.download_in(0, m1), e3.download_in(1, m2)
+    r1, r2 = host_pairs(bcs, n, seed=11)
     base = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
     top = tempfile.mkdtemp(prefix="skbench_", dir=base)
     try:
@@ -520,44 +570,207 @@ def run_cli_leg(args, bcs, local_rank, with_cpu=True):
         shutil.rmtree(top, ignore_errors=True)
 
 
+def make_sheet_single(n_samples=96, length=8, seed=3):
+    """configs[2]: 96 single-index 8-mers with pairwise Hamming distance >= 3 (greedy from the seed)."""
+    rng = random.Random(seed)
+    codes = []
+    while len(codes) < n_samples:
+        c = bytes(rng.choice(b"ACGT") for _ in range(length))
+        if all(sum(a != b for a, b in zip(c, d)) >= 3 for d in codes):
+            codes.append(c)
+    return codes
+
+
+def run_configs(eng, L, P, peak):
+    """Device time, algorithmic bytes (input once + output once) and fraction of the measured HBM peak for
+    BASELINE configs[0..3], on the main engine (profiling on: CUDA events around every pass)."""
+    lib = eng.lib
+    out = {}
+
+    def stream_leg(fn, n, seed, reps):
+        n_in = eng.synth(0, n, seed=seed, mate=1, with_bc=False)
+        ms, ob, launches = 0.0, 0, 0
+        for i in range(reps + 2):
+            assert fn(eng.ctx, 0, MIN_BASEQ, 0) == 0, lib.sk_last_error(eng.ctx)
+            r = eng.wait()
+            assert r.status == 0 and r.n_records == n, (r.status, r.n_records)
+            if i >= 2:
+                ms += r.pass_ms[0] / reps
+                ob, launches = int(r.out_bytes[0]), int(r.gpu_launches)
+        b = n_in + ob
+        return {"reads": n, "ms": ms, "launches": launches, "algorithmic_bytes": b, "achieved": b / (ms * 1e-3) / 1e9,
+                "frac": b / (ms * 1e-3) / 1e9 / peak, "reads_per_s": n / (ms * 1e-3)}
+
+    out["configs[0]"] = dict(stream_leg(lib.sk_trim_by_quality, 1_000_000, 1, 20),
+                             workload="fasta trim by quality, 1 M single-end 150 bp reads, Q20 (launch-latency regime: "
+                                      "trim kernel + tile sum + scan + gather)")
+    out["configs[1]"] = dict(stream_leg(lib.sk_mask_by_quality, 10_000_000, 2, 5),
+                             workload="fasta mask by quality, 10 M single-end 150 bp reads, 3'-decaying qualities, Q20")
+
+    def demux_leg(bcs, fused, reps=5):
+        eng.set_sheet(bcs)
+        m1 = eng.synth(0, P, seed=7, mate=1, with_bc=True)
+        m2 = eng.synth(1, P, seed=7, mate=2, with_bc=True)
+        opts = L.DemuxOpts(fused, 0, 0, 0, 0)
+        ms = [0.0, 0.0]
+        for i in range(reps + 1):
+            assert lib.sk_demultiplex(eng.ctx, 0, C.byref(opts)) == 0, lib.sk_last_error(eng.ctx)
+            r = eng.wait()
+            assert r.status == 0 and r.n_records == P and (r.reserved & 3) == 1, (r.status, r.n_records, r.reserved)
+            if i:
+                ms[0] += r.pass_ms[0] / reps
+                ms[1] += r.pass_ms[1] / reps
+        b = [m1 + int(r.out_bytes[0]), m2 + int(r.out_bytes[1])]
+        return {"pairs": P, "ms": ms, "algorithmic_bytes": b, "achieved": [b[k] / (ms[k] * 1e-3) / 1e9 for k in range(2)],
+                "frac": [b[k] / (ms[k] * 1e-3) / 1e9 / peak for k in range(2)], "reads_per_s": 2.0 * P / (sum(ms) * 1e-3),
+                "identified_fraction": r.identified_reads / float(P)}
+
+    out["configs[2]"] = dict(demux_leg(make_sheet_single(), -1),
+                             workload="fasta demultiplex, paired-end 2x150 bp, 96-sample 8 bp single index, <=1 mismatch "
+                                      "(50 M-pair job streamed in batches of `pairs`)")
+    out["configs[3]"] = dict(demux_leg(make_sheet(), -1),
+                             workload="fasta demultiplex (no trim), 384 samples, dual index 10+10 bp + 8 bp UMI; the "
+                                      "`fasta add barcode` step of the chain is timed separately below")
+    eng.set_sheet(make_sheet())
+    return out
+
+
+def run_add_barcode_leg(local_rank, peak, n=1_000_000):
+    """configs[3], first step of the chain (README.md:44-47): `fasta add barcode reads.fq barcodes.fq` on 1 M reads
+    (general engine: OP_SCAN over the barcode file, then OP_ADDBC over the reads)."""
+    from seqkit_b200 import Engine
+    bcs = make_sheet()
+    with Engine(device=local_rank, max_stream_bytes=n * 420 + (1 << 20), max_records=n, max_samples=N_SAMPLES,
+                aux_streams=True) as eng:
+        lib = eng.lib
+        eng.set_sheet(bcs)
+        m1 = eng.synth(0, n, seed=13, mate=1, with_bc=True)
+        r1 = eng.download_in(0, m1)
+        lines = r1.split(b"\n")
+        obs = [ln[ln.rfind(b" BC:") + 4:] for ln in lines[0::4] if ln]
+        bcfile = b"".join(b"@bc%07d\n%s\n+\n%s\n" % (i, b, b"I" * len(b)) for i, b in enumerate(obs))
+        m1 = eng.synth(0, n, seed=13, mate=1, with_bc=False)
+        eng.upload(2, bcfile)
+        lib.sk_set_profiling(eng.ctx, 1)
+        ms, reps, ob = 0.0, 5, 0
+        for i in range(reps + 1):
+            assert lib.sk_add_barcode(eng.ctx, 0, 0) == 0, lib.sk_last_error(eng.ctx)
+            r = eng.wait()
+            assert r.status == 0 and r.n_records == n, (r.status, r.n_records)
+            if i:
+                ms += (r.pass_ms[0] + r.pass_ms[2]) / reps
+                ob = int(r.out_bytes[0])
+        b = m1 + len(bcfile) + ob
+        return {"reads": n, "ms": ms, "algorithmic_bytes": b, "achieved": b / (ms * 1e-3) / 1e9,
+                "frac": b / (ms * 1e-3) / 1e9 / peak, "reads_per_s": n / (ms * 1e-3),
+                "workload": "fasta add barcode, 1 M reads + 1 M barcode records (i7+i5UMI on the sequence line)"}
+
+
+def verify_ranges(torch, L, bcs, local_rank, rank, world, n=1_000_000):
+    """Bytes, not only counts.  A CRC-32 of every per-sample output stream (compacted buffers + slices, both
+    mates) of a pair range, chained over batches in batch order, so equal CRCs mean equal concatenated bytes.
+    One GPU: the range in one batch against the same range in two half batches (the order contract of
+    fasta_demultiplex.rs:196-238 across batches).  Several GPUs: every rank also recomputes the first `n` pairs
+    of its right neighbour's range and the two ranks' CRCs are compared (outputs depend on the pair range,
+    not on the GPU that ran it)."""
+    import zlib
+    from seqkit_b200 import Engine
+    S = N_SAMPLES
+    with Engine(device=local_rank, max_stream_bytes=n * 410 + (1 << 20), max_records=n, max_samples=S,
+                aux_streams=False) as eng:
+        lib = eng.lib
+        eng.set_sheet(bcs)
+        opts = L.DemuxOpts(MIN_BASEQ, 0, 0, 0, 0)
+
+        def crcs(batches):
+            acc = [[0] * S, [0] * S]
+            for first, cnt in batches:
+                synth_pair(eng, cnt, first)
+                assert lib.sk_demultiplex(eng.ctx, 0, C.byref(opts)) == 0, lib.sk_last_error(eng.ctx)
+                assert lib.sk_demux_compact(eng.ctx, 0) == 0, lib.sk_last_error(eng.ctx)
+                r = eng.wait()
+                assert r.status == 0 and r.n_records == cnt
+                for m in range(2):
+                    ext = int(r.out_extent[m])
+                    buf = torch.empty(max(ext, 1), dtype=torch.uint8)
+                    sl = (L.Slice * (S + 1))()
+                    assert lib.sk_download_compact(eng.ctx, 0, m, buf.data_ptr(), ext) == 0
+                    assert lib.sk_download_slices(eng.ctx, 0, m, sl) == 0
+                    eng.wait()
+                    mv = memoryview(buf.numpy())
+                    for s in range(S):
+                        acc[m][s] = zlib.crc32(mv[sl[s].offset:sl[s].offset + sl[s].len], acc[m][s])
+            return acc
+
+        P0 = rank * 8_000_000  # (any range will do; ranks use distinct ones)
+        if world == 1:
+            whole = crcs([(P0, n)])
+            halves = crcs([(P0, n // 2), (P0 + n // 2, n - n // 2)])
+            assert whole == halves, "per-sample streams of two half batches differ from the single batch"
+            return {"ok": True, "pairs": n, "check": "CRC-32 of all %d per-sample streams: one batch == two half batches" % (2 * S)}
+        import torch.distributed as dist
+        mine = crcs([(P0, n)])
+        right = ((rank + 1) % world) * 8_000_000
+        theirs = crcs([(right, n)])
+        t_mine = torch.tensor(mine, dtype=torch.int64, device="cuda")
+        gathered = [torch.empty_like(t_mine) for _ in range(world)]
+        dist.all_gather(gathered, t_mine)
+        ok = gathered[(rank + 1) % world].cpu().tolist() == theirs
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        assert int(flag.item()) == 1, "a rank's per-sample streams differ from its neighbour's recomputation"
+        return {"ok": True, "pairs": n, "check": "CRC-32 of all %d per-sample streams of every rank's range == the same "
+                                                 "range recomputed on the neighbouring GPU" % (2 * S)}
+
+
 def run_e2e(args, torch, L, bcs, local_rank, rank, world, barrier):
-    """Same metric through the reference-facing call with HOST buffers: every step uploads its
-    inputs from pinned memory, runs the kernels, and reads back outputs, slice tables and counters."""
+    """Same metric through the reference-facing call with HOST buffers: every step uploads its inputs from
+    pinned memory, runs the kernels and the per-sample compaction, and reads back the per-sample streams
+    (compacted buffers + slice tables).  The host thread and its pinned buffers sit on the GPU's NUMA node."""
     from seqkit_b200 import Engine
     Pe, nslots = args.e2e_pairs, 3
     eng = Engine(device=local_rank, max_stream_bytes=Pe * 410 + (1 << 20), max_records=Pe, n_slots=nslots,
                  max_samples=N_SAMPLES, aux_streams=False)
     lib = eng.lib
+    numa = lib.sk_bind_thread_to_device(local_rank) if os.environ.get("SK_NO_NUMA", "0") in ("", "0") else -2
     eng.set_sheet(bcs)
     n1, n2 = synth_pair(eng, Pe, rank * Pe, seed=9)
-    h_in = [torch.empty(n, dtype=torch.uint8).pin_memory() for n in (n1, n2)]
-    for w, t in enumerate(h_in):
-        assert lib.sk_download_in(eng.ctx, 0, w, t.data_ptr(), t.numel()) == 0
+
+    def pinned(nbytes):  # NUMA-local, portable pinned memory from the library (a torch view over it)
+        ptr = lib.sk_pinned_alloc(eng.ctx, nbytes)
+        assert ptr, lib.sk_last_error(eng.ctx)
+        return ptr
+
+    h_in = [pinned(n) for n in (n1, n2)]
+    for w, (ptr, n) in enumerate(zip(h_in, (n1, n2))):
+        assert lib.sk_download_in(eng.ctx, 0, w, ptr, n) == 0
     cap = max(n1, n2) + Pe * 16 + (1 << 20)
-    nchunks = lib.sk_max_chunks(eng.ctx)
-    h_out = [[torch.empty(cap, dtype=torch.uint8).pin_memory() for _ in range(2)] for _ in range(nslots)]
-    h_rows = [[torch.empty(nchunks * 2, dtype=torch.int64).pin_memory() for _ in range(2)] for _ in range(nslots)]
-    h_groups = [[torch.empty(Pe, dtype=torch.int32).pin_memory() for _ in range(2)] for _ in range(nslots)]
-    h_counts = [torch.empty(N_SAMPLES + 2, dtype=torch.int64).pin_memory() for _ in range(nslots)]
+    h_out = [[pinned(cap) for _ in range(2)] for _ in range(nslots)]
+    h_slices = [[C.cast(pinned((N_SAMPLES + 1) * 16), C.POINTER(L.Slice)) for _ in range(2)] for _ in range(nslots)]
     opts = L.DemuxOpts(MIN_BASEQ, 0, 0, 0, 0)
     d2h = [0]
+    ident = [0]
 
     def submit(s):
-        assert lib.sk_upload(eng.ctx, s, 0, h_in[0].data_ptr(), n1) == 0
-        assert lib.sk_upload(eng.ctx, s, 1, h_in[1].data_ptr(), n2) == 0
+        assert lib.sk_upload(eng.ctx, s, 0, h_in[0], n1) == 0
+        assert lib.sk_upload(eng.ctx, s, 1, h_in[1], n2) == 0
         assert lib.sk_demultiplex(eng.ctx, s, C.byref(opts)) == 0
+        assert lib.sk_demux_compact(eng.ctx, s) == 0
 
     def collect(s):
         res = L.Result()
         assert lib.sk_wait(eng.ctx, s, C.byref(res)) == 0 and res.status == 0
         nb = 0
         for m in range(2):
-            assert lib.sk_download_out(eng.ctx, s, m, h_out[s][m].data_ptr(), res.out_extent[m]) == 0
-            assert lib.sk_download_demux_tables(eng.ctx, s, m, h_rows[s][m].data_ptr(), h_groups[s][m].data_ptr(),
-                                                res.n_records) == 0
-            nb += res.out_extent[m] + res.n_chunks[m] * 16 + res.n_records * 4
-        assert lib.sk_download_counts(eng.ctx, s, h_counts[s].data_ptr()) == 0  # syncs the slot
-        d2h[0] = nb + (N_SAMPLES + 2) * 8
+            assert res.out_extent[m] <= cap
+            assert lib.sk_download_compact(eng.ctx, s, m, h_out[s][m], res.out_extent[m]) == 0
+            assert lib.sk_download_slices(eng.ctx, s, m, h_slices[s][m]) == 0
+            nb += res.out_extent[m] + (N_SAMPLES + 1) * 16
+        assert lib.sk_counts_accumulate(eng.ctx, s) == 0
+        assert lib.sk_wait(eng.ctx, s, None) == 0  # the per-sample streams of this batch are in host memory now
+        assert h_slices[s][0][N_SAMPLES].len == res.out_bytes[0]
+        ident[0] = res.identified_reads
+        d2h[0] = nb
         return res
 
     def run(k):
@@ -572,7 +785,7 @@ def run_e2e(args, torch, L, bcs, local_rank, rank, world, barrier):
             collect(s)
 
     run(3)
-    steps = max(args.steps, 6)
+    steps = max(min(args.steps, 40), 6)
     barrier()
     t0 = time.perf_counter()
     run(steps)
@@ -587,7 +800,9 @@ def run_e2e(args, torch, L, bcs, local_rank, rank, world, barrier):
     return {"value": 2.0 * Pe * world * steps / dt, "unit": "reads/s", "h2d_bytes_per_step": int(n1 + n2),
             "d2h_bytes_per_step": int(d2h[0]), "pairs_per_step": Pe, "steps": steps, "slots": nslots,
             "pcie_gbs": {"h2d": (n1 + n2) * steps / dt / 1e9, "d2h": d2h[0] * steps / dt / 1e9},
-            "note": "pinned host buffers -> sk_upload -> sk_demultiplex -> sk_download_out/tables/counts; gzip excluded"}
+            "numa_node": numa,
+            "note": "pinned host buffers -> sk_upload -> sk_demultiplex -> sk_demux_compact -> sk_download_compact + "
+                    "sk_download_slices (per-sample streams in host memory) + device-side run totals; gzip excluded"}
 
 
 if __name__ == "__main__":

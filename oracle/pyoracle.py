@@ -15,7 +15,8 @@ _SO = os.path.join(_HERE, "_build", "liboracle.so")
 
 def build(force: bool = False) -> str:
     src = os.path.join(_HERE, "fasta_oracle.c")
-    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < os.path.getmtime(src):
+    src2 = os.path.join(_HERE, "synth_host.c")
+    if force or not os.path.exists(_SO) or os.path.getmtime(_SO) < max(os.path.getmtime(src), os.path.getmtime(src2)):
         subprocess.check_call(["make", "-s", "-C", _HERE, "all"])
     return _SO
 
@@ -131,3 +132,28 @@ def demultiplex(sheet: bytes, fastq_1: bytes, fastq_2: bytes | None = None, inde
                 "identified": L.orc_demux_identified(D)}
     finally:
         L.orc_demux_free(D)
+
+
+class _SynthSpec(C.Structure):
+    _fields_ = [("seed", C.c_uint64), ("first_pair", C.c_uint64), ("n_pairs", C.c_uint64), ("read_len", C.c_uint32),
+                ("mate", C.c_uint32), ("with_bc", C.c_uint32), ("qual_profile", C.c_uint32), ("p_sub_ppm", C.c_uint32),
+                ("p_n_ppm", C.c_uint32), ("p_random_ppm", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+def synth_fastq(n_pairs: int, seed: int = 1, first_pair: int = 0, read_len: int = 150, mate: int = 1,
+                barcodes: list | None = None, qual_profile: int = 0, p_sub_ppm: int = 10000, p_n_ppm: int = 5000,
+                p_random_ppm: int = 20000) -> bytes:
+    """Host twin of the device generator (synth_host.c == seqkit_b200/csrc/sk_synth.cu): the same bytes for the
+    same (seed, pair range, mate).  `barcodes` = the sheet's barcodes (observed barcodes are drawn from them)."""
+    L = lib()
+    L.orc_synth_fastq.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(_SynthSpec), C.c_char_p, C.c_uint32, C.c_uint32]
+    L.orc_synth_fastq.restype = C.c_uint64
+    S = len(barcodes) if barcodes else 0
+    Lb = len(barcodes[0]) if S else 0
+    spec = _SynthSpec(seed, first_pair, n_pairs, read_len, mate, 1 if S else 0, qual_profile, p_sub_ppm, p_n_ppm,
+                      p_random_ppm, 0)
+    cap = n_pairs * (64 + Lb + 2 * read_len) + 64
+    buf = C.create_string_buffer(cap)
+    n = L.orc_synth_fastq(buf, cap, C.byref(spec), b"".join(barcodes) if S else b"", S, Lb)
+    assert n or n_pairs == 0, "synthetic buffer too small"
+    return buf.raw[:n]

@@ -39,6 +39,7 @@ struct Slot {
     uint64_t *tile_out = nullptr;
     DevStats *stats = nullptr;    // [SK_N_INPUTS] device
     DevStats *stats_h = nullptr;  // pinned mirror
+    unsigned long long *ti_h = nullptr;  // pinned: total_reads, identified_reads of the last demultiplex
     int16_t *assign = nullptr;
     uint8_t *umi = nullptr;
     uint64_t umi_cap = 0;
@@ -95,16 +96,15 @@ struct sk_ctx {
     uint2 *d_ftab = nullptr;      // FastIdx
     uint16_t *d_fnext = nullptr;
     bool fast_sheet = false;  // the sheet's FastIdx is usable
-    int fast_geo = 1;   // lean-engine geometry: 0 = GeoS (8 KiB chunks), 1 = GeoM (16 KiB chunks, default); SK_FAST_GEO
     bool warp = true;   // warp engine (sk_warp.cu) for header-route demultiplex; SK_NO_WARP=1 disables
-    // Warp engine for the two ordered operators as well: bit 0 = trim, bit 1 = mask (SK_WARP_STREAM=0: the lean
+    // Warp engine for the two ordered operators as well: bit 0 = trim, bit 1 = mask (SK_WARP_STREAM=0: the general
     // engine for both).  Their tiles write in input order, so a tile needs the output sizes of all tiles before
     // it.  Mask knows its sizes right after the line table: second look-back on output bytes, 2.9 ms per 8 M
-    // reads of 150 bp (lean engine 5.4 ms).  Trim knows them only after its plan, and waiting for the slowest
+    // reads of 150 bp (the retired lean engine: 5.4 ms).  Trim knows them only after its plan, and waiting for the slowest
     // plan among a thousand predecessors costs more than a second pass (5.5 ms): with trim_gather (default,
     // SK_TRIM_GATHER=0 switches it off) the tiles write wherever the output cursor puts them (the spare output
     // buffer), a one-block scan turns their lengths into destinations and a gather kernel writes the stream in
-    // input order: 3.0 ms (lean engine 5.3 ms).
+    // input order: 3.0 ms (the retired lean engine: 5.3 ms).
     uint32_t warp_stream = 3;
     bool trim_gather = true;
     // mask by quality of a regular file keeps every record's length: tiles write at their input offsets, no second
@@ -113,7 +113,7 @@ struct sk_ctx {
     uint32_t tile_lanes = GeoW::TILE_LANES;  // warp-engine tile = tile_lanes x 400 B; SK_TILE_LANES
     bool tile_auto = true;   // tile_lanes follows the record size of the data (no SK_TILE_LANES override)
     double rec_est = 0.0;    // bytes per record: peeked from the first batch, then measured by every operator
-    bool fast = true;   // lean engine (sk_fast.cu) for trim / mask / header-route demultiplex; SK_NO_FAST=1 disables
+    bool fast = true;   // warp engine for trim / mask / header-route demultiplex; SK_NO_FAST=1: everything on the general engine
     int cfg = 0;  // chunk-engine geometry: 0 = CfgA (16 KiB chunks, 4 warps), 1 = CfgB (32 KiB chunks, 8 warps)
 };
 
@@ -126,12 +126,10 @@ struct sk_ctx {
         }                                                                                \
     } while (0)
 
-// engine of a pass: 0 = general (sk_kernels.cu), 1 = lean (sk_fast.cu), 2 = warp (sk_warp.cu)
-enum { ENG_GENERAL = 0, ENG_LEAN = 1, ENG_WARP = 2 };
+// engine of a pass: 0 = general (sk_kernels.cu), 2 = warp (sk_warp.cu); 1 was the lean engine (sk_fast.cu, retired in round 2)
+enum { ENG_GENERAL = 0, ENG_WARP = 2 };
 static uint32_t chunks_of(const sk_ctx *ctx, uint64_t n, int eng = ENG_GENERAL) {
-    const uint64_t ch = eng == ENG_WARP   ? (uint64_t)ctx->tile_lanes * GeoW::LANE_BYTES
-                        : eng == ENG_LEAN ? (uint64_t)fast_chunk_bytes(ctx->fast_geo)
-                                          : (uint64_t)cfg_chunk_bytes(ctx->cfg);
+    const uint64_t ch = eng == ENG_WARP ? (uint64_t)ctx->tile_lanes * GeoW::LANE_BYTES : (uint64_t)cfg_chunk_bytes(ctx->cfg);
     return (uint32_t)((n + ch - 1) / ch);
 }
 
@@ -153,6 +151,7 @@ static void free_slot(Slot &s) {
     cudaFree(s.tile_out);
     cudaFree(s.stats);
     cudaFreeHost(s.stats_h);
+    cudaFreeHost(s.ti_h);
     cudaFree(s.assign);
     cudaFree(s.umi);
     cudaFree(s.counts);
@@ -208,7 +207,6 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
     ctx->cfg = (lim->reserved & 0xFFu) == 2 ? 1 : 0;  // reserved: 0/1 = 16 KiB chunks (default), 2 = 32 KiB chunks
     if (const char *e = getenv("SK_CFG")) ctx->cfg = atoi(e) ? 1 : 0;
     if (const char *e = getenv("SK_NO_FAST")) ctx->fast = atoi(e) == 0;
-    if (const char *e = getenv("SK_FAST_GEO")) ctx->fast_geo = atoi(e) ? 1 : 0;
     if (const char *e = getenv("SK_NO_WARP")) ctx->warp = atoi(e) == 0;
     if (const char *e = getenv("SK_WARP_STREAM")) ctx->warp_stream = atoi(e) ? 3u : 0u;
     if (const char *e = getenv("SK_TRIM_GATHER")) ctx->trim_gather = atoi(e) != 0;
@@ -241,7 +239,7 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
     const uint64_t B = (lim->max_stream_bytes + 15) & ~15ull;
     const uint64_t R = lim->max_records;
     // slice-table rows: one per chunk, or GeoW::ROUNDS per tile of the warp engine (smallest tile: 8 lanes)
-    ctx->max_chunks = std::max(chunks_of(ctx, B, ENG_GENERAL), (uint32_t)((B + GeoS::CHUNK - 1) / GeoS::CHUNK)) + 1;
+    ctx->max_chunks = chunks_of(ctx, B, ENG_GENERAL) + 1;
     ctx->max_chunks = std::max(ctx->max_chunks, (uint32_t)(B / (8 * GeoW::LANE_BYTES) + 1) * GeoW::ROUNDS);
     const uint32_t Smax = lim->max_samples;
     // every chunk / round owns whole 32-byte sectors; a compacted buffer starts every sample on a 128-byte line
@@ -267,6 +265,8 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
         CKC(cudaMalloc(&s.stats, sizeof(DevStats) * SK_N_INPUTS));
         CKC(cudaMallocHost(&s.stats_h, sizeof(DevStats) * SK_N_INPUTS));
         memset(s.stats_h, 0, sizeof(DevStats) * SK_N_INPUTS);
+        CKC(cudaMallocHost(&s.ti_h, 16));
+        s.ti_h[0] = s.ti_h[1] = 0;
         CKC(cudaMalloc(&s.synth_tmp, (R + 1) * 8));
         if (Smax) {
             CKC(cudaMalloc(&s.assign, R * 2));
@@ -582,9 +582,9 @@ extern "C" int sk_set_sheet(sk_ctx *ctx, const uint8_t *barcodes, uint32_t S, ui
     }
     if (hcand.size() > 0xFFFFu) h_classes = 0;  // list offsets are 16-bit
     if (hcand.empty()) hcand.push_back(0);
-    // the same index for the lean engine (FastIdx): same slots, tag = the slot hash before mixing, first
+    // the same index in the form the warp engine probes (FastIdx): same slots, tag = the slot hash before mixing, first
     // sample in the slot, the rest chained.  Tags must be unique inside a table so that a probe can stop
-    // at the first tag match; otherwise the lean engine is not used for this sheet.
+    // at the first tag match; otherwise the warp engine is not used for this sheet.
     std::vector<uint2> ftab(htab.size(), make_uint2(0u, 0u));
     std::vector<uint16_t> fnext((size_t)std::max(h_classes, 1u) * 2 * std::max(S, 1u), (uint16_t)0xFFFFu);
     bool fast_ok = h_classes != 0;
@@ -713,9 +713,8 @@ static int run_pass(sk_ctx *ctx, Slot *s, int which, int op, const KParams &p, b
         CK(cudaMemsetAsync(p.tile_out, 0, eng == ENG_WARP ? (uint64_t)p.n_chunks * (p.unordered ? 20 : 10) + 64 : (uint64_t)p.n_chunks * 8, s->stream));
     const char *err = nullptr;
     if (ctx->profiling) CK(cudaEventRecord(s->ev[which][0], s->stream));
-    int rc = eng == ENG_WARP   ? launch_warp_kernel(op, p, ctx->sm_count, s->stream, &err)
-             : eng == ENG_LEAN ? launch_fast_kernel(ctx->fast_geo, op, p, ctx->sm_count, s->stream, &err)
-                               : launch_chunk_kernel(ctx->cfg, op, p, ctx->sm_count, s->stream, &err);
+    int rc = eng == ENG_WARP ? launch_warp_kernel(op, p, ctx->sm_count, s->stream, &err)
+                             : launch_chunk_kernel(ctx->cfg, op, p, ctx->sm_count, s->stream, &err);
     if (rc < 0) {
         ctx->err = std::string("kernel launch failed: ") + (err ? err : "?");
         return SK_E_CUDA;
@@ -736,6 +735,8 @@ static int run_pass(sk_ctx *ctx, Slot *s, int which, int op, const KParams &p, b
 
 static int end_op(sk_ctx *ctx, Slot *s) {
     CK(cudaMemcpyAsync(s->stats_h, s->stats, sizeof(DevStats) * SK_N_INPUTS, cudaMemcpyDeviceToHost, s->stream));
+    if (s->last_op == OP_DEMUX1 && s->counts)  // total / identified ride along (no blocking copy in sk_wait)
+        CK(cudaMemcpyAsync(s->ti_h, s->counts + ctx->S, 16, cudaMemcpyDeviceToHost, s->stream));
     return SK_OK;
 }
 
@@ -747,7 +748,7 @@ static int stream_op_enqueue(sk_ctx *ctx, Slot *s, int op, uint32_t min_baseq, u
     if (rc) return rc;
     KParams p;
     const bool want_warp = ctx->warp && (ctx->warp_stream & (op == OP_TRIM ? 1u : 2u)) != 0;
-    int eng = fast ? (want_warp ? ENG_WARP : ENG_LEAN) : ENG_GENERAL;
+    int eng = fast && want_warp ? ENG_WARP : ENG_GENERAL;
     auto fill = [&](int e) {
         base_params(ctx, s, SK_IN_R1, p, e);
         p.min_baseq = min_baseq;
@@ -757,10 +758,6 @@ static int stream_op_enqueue(sk_ctx *ctx, Slot *s, int op, uint32_t min_baseq, u
     };
     fill(eng);
     if (eng == ENG_WARP && !warp_supported(op, p)) {
-        eng = ENG_LEAN;
-        fill(eng);
-    }
-    if (eng == ENG_LEAN && !fast_supported(ctx->fast_geo, op, p)) {
         eng = ENG_GENERAL;
         fill(eng);
     }
@@ -905,7 +902,7 @@ static int demux_enqueue(sk_ctx *ctx, Slot *s, const sk_demux_opts *o, bool fast
     uint32_t n_index = 0;
     if (o->use_index & 1u) idx_stream[n_index++] = SK_IN_AUX1;
     if (o->use_index & 2u) idx_stream[n_index++] = SK_IN_AUX2;
-    // the lean engine does the header route on sheets its index can represent
+    // the warp engine does the header route on sheets its index can represent
     if (n_index || !ctx->h_classes || !ctx->fast_sheet || getenv("SK_NO_HIDX")) fast = false;
     s->used_fast = fast;
     {
@@ -921,7 +918,8 @@ static int demux_enqueue(sk_ctx *ctx, Slot *s, const sk_demux_opts *o, bool fast
         rc = run_pass(ctx, s, idx_stream[q], OP_SCAN, k, false);
         if (rc) return rc;
     }
-    int eng = fast ? (ctx->warp ? ENG_WARP : ENG_LEAN) : ENG_GENERAL;
+    int eng = fast && ctx->warp ? ENG_WARP : ENG_GENERAL;
+    if (eng == ENG_GENERAL) s->used_fast = false;
     auto demux_params = [&](int which, int mate, KParams &p) {
         base_params(ctx, s, which, p, eng);
         p.sheet.fidx.table = ctx->d_ftab;
@@ -965,10 +963,6 @@ static int demux_enqueue(sk_ctx *ctx, Slot *s, const sk_demux_opts *o, bool fast
     KParams p1;
     demux_params(SK_IN_R1, 0, p1);
     if (eng == ENG_WARP && !warp_supported(OP_DEMUX1, p1)) {
-        eng = ENG_LEAN;
-        demux_params(SK_IN_R1, 0, p1);
-    }
-    if (eng == ENG_LEAN && !fast_supported(ctx->fast_geo, OP_DEMUX1, p1)) {
         eng = ENG_GENERAL;
         s->used_fast = false;
         demux_params(SK_IN_R1, 0, p1);
@@ -988,6 +982,8 @@ static int demux_enqueue(sk_ctx *ctx, Slot *s, const sk_demux_opts *o, bool fast
 static int compact_enqueue(sk_ctx *ctx, Slot *s) {
     const uint32_t S = ctx->S;
     const int nm = s->paired ? 2 : 1;
+    // (a mate that is absent or empty has empty slices, not those of an earlier batch)
+    CK(cudaMemsetAsync(s->slices, 0, (uint64_t)(ctx->lim.max_samples + 1) * 16 * 2, s->stream));
     for (int m = 0; m < nm; m++) {
         const int which = m == 0 ? SK_IN_R1 : SK_IN_R2;
         const char *err = nullptr;
@@ -1037,7 +1033,7 @@ extern "C" int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res) {
     if (!s) return SK_E_INVALID;
     CK(cudaStreamSynchronize(s->stream));
     if (s->used_fast && s->last_op >= 0) {
-        // The lean engine met something outside its limits (long record, dense chunk, oversized chunk
+        // The warp engine met something outside its limits (long record, dense tile, oversized
         // output): run the operator again on the general engine.
         unsigned fl = 0;
         for (int i = 0; i < SK_N_INPUTS; i++) fl |= s->stats_h[i].flags;
@@ -1085,7 +1081,7 @@ extern "C" int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res) {
     if (h[SK_IN_R1].n_records >= 64 && h[SK_IN_R1].consumed)  // record size of this data, for the next tile choice
         ctx->rec_est = (double)h[SK_IN_R1].consumed / (double)h[SK_IN_R1].n_records;
     res->gpu_launches = s->launches;
-    res->reserved = (s->used_fast ? 1u : 0u) | (s->reran_general ? 2u : 0u) | (s->no_inplace ? 4u : 0u) | (s->compacted ? 8u : 0u);  // diagnostic: bit0 warp / lean engine, bit1 re-run on the general engine, bit2 mask re-run in its ordered form
+    res->reserved = (s->used_fast ? 1u : 0u) | (s->reran_general ? 2u : 0u) | (s->no_inplace ? 4u : 0u) | (s->compacted ? 8u : 0u);  // diagnostic: bit0 warp engine, bit1 re-run on the general engine, bit2 mask re-run in its ordered form
     if (ctx->profiling)
         for (int i = 0; i < SK_N_INPUTS; i++)
             if (s->pass_ran[i]) cudaEventElapsedTime(&res->pass_ms[i], s->ev[i][0], s->ev[i][1]);
@@ -1104,11 +1100,9 @@ extern "C" int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res) {
         if (s->paired && h[SK_IN_R2].n_records < h[SK_IN_R1].n_records) flags |= F_MATE_COUNT;
         for (int i = SK_IN_AUX1; i <= SK_IN_AUX2; i++)
             if (s->pass_ran[i] && h[i].n_records < h[SK_IN_R1].n_records) flags |= F_MATE_COUNT;
-        // counters live on the device; fetch total / identified for convenience
-        unsigned long long ti[2] = {0, 0};
-        CK(cudaMemcpy(ti, s->counts + ctx->S, 16, cudaMemcpyDeviceToHost));
-        res->total_reads = ti[0];
-        res->identified_reads = ti[1];
+        // counters live on the device; total / identified came over with the outcome block (end_op)
+        res->total_reads = s->ti_h[0];
+        res->identified_reads = s->ti_h[1];
     } else {
         res->out_bytes[0] = h[SK_IN_R1].out_bytes;
         res->out_extent[0] = h[SK_IN_R1].out_extent;

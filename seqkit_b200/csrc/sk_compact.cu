@@ -28,6 +28,12 @@
 #include "sk_internal.h"
 
 namespace sk {
+extern __shared__ __align__(128) unsigned char sk_smem[];
+}
+#include "sk_device.cuh"
+#include "sk_record.cuh"
+
+namespace sk {
 
 constexpr uint32_t CB_ROWS = 1024;  // slice-table rows per compaction block (256 tiles of the warp engine)
 
@@ -56,7 +62,7 @@ __device__ __forceinline__ void for_rows_of_block(const ChunkRow *rows, uint32_t
 
 __global__ void __launch_bounds__(256) sk_compact_hist_kernel(const ChunkRow *__restrict__ rows, const Group *__restrict__ groups,
                                                               uint32_t n_rows, uint32_t S, uint32_t *__restrict__ hist) {
-    extern __shared__ uint32_t sh_hist[];
+    uint32_t *sh_hist = (uint32_t *)sk_smem;
     for (uint32_t s = threadIdx.x; s < S; s += blockDim.x) sh_hist[s] = 0u;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -148,7 +154,7 @@ __global__ void __launch_bounds__(32) sk_compact_addr_kernel(const ChunkRow *__r
                                                              uint32_t n_rows, uint32_t S, const uint32_t *__restrict__ offs,
                                                              const unsigned long long *__restrict__ slices,
                                                              unsigned long long *__restrict__ piece_dst) {
-    extern __shared__ unsigned long long running[];
+    unsigned long long *running = (unsigned long long *)sk_smem;
     constexpr uint32_t FULL = 0xffffffffu;
     const int lane = threadIdx.x;
     const uint32_t *o = offs + (size_t)blockIdx.x * S;
@@ -220,19 +226,53 @@ __device__ __forceinline__ void warp_copy_piece(const uint8_t *__restrict__ src,
     }
 }
 
-__global__ void __launch_bounds__(256) sk_compact_move_kernel(const ChunkRow *__restrict__ rows, const Group *__restrict__ groups,
-                                                              uint32_t n_rows, uint32_t S, const unsigned long long *__restrict__ piece_dst,
-                                                              const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
-                                                              const unsigned long long *__restrict__ slices, unsigned long long dst_cap) {
+// One warp per row.  The row's pieces lie back to back in the input-order stream: the warp brings the whole
+// row into its window of shared memory with one TMA bulk copy and then every lane copies one piece from the
+// window to its destination (gcopy: whole 32-byte sectors inside the piece, small stores at its two ends,
+// which share their sectors with the neighbouring pieces of the sample's run).  Rows that do not fit the
+// window, hold more than 32 pieces or start off a 16-byte boundary take the piece-by-piece copy above.
+constexpr uint32_t MV_ROW = 12288;               // bytes of a row the window holds
+constexpr uint32_t MV_WIN = MV_ROW + 96;         // + slack: gcopy reads whole aligned words past a piece
+constexpr int MV_WARPS = 6;                      // 6 x 12.1 KB: three CTAs per SM
+__global__ void __launch_bounds__(MV_WARPS * 32) sk_compact_move_kernel(const ChunkRow *__restrict__ rows, const Group *__restrict__ groups,
+                                                                        uint32_t n_rows, uint32_t S,
+                                                                        const unsigned long long *__restrict__ piece_dst,
+                                                                        const uint8_t *__restrict__ src, uint8_t *__restrict__ dst,
+                                                                        const unsigned long long *__restrict__ slices,
+                                                                        unsigned long long dst_cap, unsigned int *ticket) {
     constexpr uint32_t FULL = 0xffffffffu;
     if (slices[2 * S] > dst_cap) return;  // reported by the bases kernel (K_OUT_OVERFLOW): nothing is written
-    const int lane = threadIdx.x & 31;
-    const uint32_t wpb = blockDim.x >> 5, gw = blockIdx.x * wpb + (threadIdx.x >> 5), nw = gridDim.x * wpb;
-    for (uint32_t rb = gw * 32u; rb < n_rows; rb += nw * 32u) {
-        const uint32_t r = rb + (uint32_t)lane;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint8_t *win = sk_smem + (uint32_t)warp * MV_WIN;
+    uint64_t *mbar = (uint64_t *)(sk_smem + MV_WARPS * MV_WIN) + warp;
+    if (lane == 0) mbar_init(mbar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncwarp();
+    uint32_t parity = 0;
+    // Rows are handed out four at a time (one tile of the warp engine) by a ticket counter, in order: the rows
+    // in flight at any moment then span a few tens of megabytes of the input-order stream, so the pieces that
+    // share a sector or a line of a sample's run are written within microseconds of each other and meet in L2
+    // (with a static split of the rows the dirty lines of a whole wave, > L2, went to DRAM half written).
+    // The next ticket's rows are fetched while the current ones are copied.
+    constexpr uint32_t RB = 4;
+    const uint32_t n_batches = (n_rows + RB - 1) / RB;
+    auto take = [&]() -> uint32_t {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(ticket, 1u);
+        return __shfl_sync(FULL, t, 0);
+    };
+    auto fetch = [&](uint32_t t) -> ChunkRow {
         ChunkRow row;
         row.base = 0, row.first_group = 0, row.n_groups = 0;
-        if (r < n_rows) row = rows[r];
+        const uint32_t r = t * RB + (uint32_t)lane;
+        if (t < n_batches && (uint32_t)lane < RB && r < n_rows) row = rows[r];
+        return row;
+    };
+    uint32_t t_cur = take();
+    ChunkRow row = fetch(t_cur);
+    while (t_cur < n_batches) {
+        const uint32_t t_next = take();
+        const ChunkRow row_next = fetch(t_next);
         uint32_t todo = __ballot_sync(FULL, row.n_groups != 0u);
         while (todo) {
             const int q = __ffs((int)todo) - 1;
@@ -256,17 +296,39 @@ __global__ void __launch_bounds__(256) sk_compact_move_kernel(const ChunkRow *__
                     const uint32_t y = __shfl_up_sync(FULL, incl, o);
                     if (lane >= o) incl += y;
                 }
-                const unsigned long long ps = run + incl - g.len;
-                const uint32_t live = __ballot_sync(FULL, g.len != 0 && g.sample < S);
-                const uint32_t n_here = min(32u, ng - k0);
-                for (uint32_t j = 0; j < n_here; j++) {
-                    const unsigned long long so = __shfl_sync(FULL, ps, (int)j), d_o = __shfl_sync(FULL, pd, (int)j);
-                    const uint32_t len = __shfl_sync(FULL, (uint32_t)g.len, (int)j);
-                    if ((live >> j) & 1u) warp_copy_piece(src, dst, so, d_o, len, lane);
+                const uint32_t total = __shfl_sync(FULL, incl, 31);
+                const bool mine = g.len != 0 && g.sample < S;
+                if (total <= MV_ROW && (run & 15ull) == 0ull) {
+                    // the row (this slice of it) through the window
+                    const uint32_t nbytes = (total + 15u) & ~15u;
+                    fence_proxy_async();  // this lane's reads of the previous window before the next TMA write
+                    __syncwarp();
+                    if (lane == 0 && nbytes) {
+                        mbar_expect_tx(mbar, nbytes);
+                        bulk_g2s(win, src + run, nbytes, mbar);
+                    }
+                    if (nbytes) {
+                        mbar_wait_parked(mbar, parity);
+                        parity ^= 1u;
+                    }
+                    __syncwarp();
+                    if (mine) gcopy(dst + pd, win, incl - g.len, g.len);
+                    __syncwarp();
+                } else {
+                    const unsigned long long ps = run + incl - g.len;
+                    const uint32_t live = __ballot_sync(FULL, mine);
+                    const uint32_t n_here = min(32u, ng - k0);
+                    for (uint32_t j = 0; j < n_here; j++) {
+                        const unsigned long long so = __shfl_sync(FULL, ps, (int)j), d_o = __shfl_sync(FULL, pd, (int)j);
+                        const uint32_t len = __shfl_sync(FULL, (uint32_t)g.len, (int)j);
+                        if ((live >> j) & 1u) warp_copy_piece(src, dst, so, d_o, len, lane);
+                    }
                 }
-                run += __shfl_sync(FULL, incl, 31);
+                run += total;
             }
         }
+        t_cur = t_next;
+        row = row_next;
     }
 }
 
@@ -277,7 +339,7 @@ __global__ void __launch_bounds__(256) sk_compact_move_kernel(const ChunkRow *__
 uint32_t compact_blocks(uint32_t n_rows) { return (n_rows + CB_ROWS - 1) / CB_ROWS; }
 uint64_t compact_work_bytes(uint32_t max_rows, uint32_t S) {
     const uint64_t nb = compact_blocks(max_rows) + 1;
-    return nb * S * 4ull * 2ull + (uint64_t)S * 8ull + 256;
+    return nb * S * 4ull * 2ull + (uint64_t)S * 8ull + 256 + 64;  // hist, offs, totals, the move kernel's ticket
 }
 int launch_compact(const ChunkRow *rows, const Group *groups, uint32_t n_rows, uint32_t S, const uint8_t *src, uint8_t *dst,
                    uint64_t dst_cap, void *work, unsigned long long *slices, unsigned long long *piece_dst, DevStats *st,
@@ -292,6 +354,7 @@ int launch_compact(const ChunkRow *rows, const Group *groups, uint32_t n_rows, u
     uint32_t *offs = hist + (size_t)(nb + 1) * S;
     unsigned long long *total = (unsigned long long *)(offs + (size_t)(nb + 1) * S);
     total = (unsigned long long *)(((uintptr_t)total + 15) & ~(uintptr_t)15);
+    unsigned int *ticket = (unsigned int *)(total + S + 2);
     if (nb == 0) {  // nothing was emitted: empty slices
         cudaMemsetAsync(slices, 0, (size_t)(S + 1) * 16, stream);
         return 0;
@@ -300,9 +363,16 @@ int launch_compact(const ChunkRow *rows, const Group *groups, uint32_t n_rows, u
     sk_compact_cols_kernel<<<(S + 127) / 128, 128, 0, stream>>>(hist, offs, nb, S, total);
     sk_compact_bases_kernel<<<1, 1024, 0, stream>>>(total, S, slices, dst_cap, st);
     sk_compact_addr_kernel<<<nb, 32, S * 8, stream>>>(rows, groups, n_rows, S, offs, slices, piece_dst);
-    const unsigned want = (n_rows + 255u) / 256u;  // 8 warps x 32 rows per CTA and pass
-    const unsigned grid = std::max(1u, std::min<unsigned>((unsigned)sm_count * 8u, want));
-    sk_compact_move_kernel<<<grid, 256, 0, stream>>>(rows, groups, n_rows, S, piece_dst, src, dst, slices, dst_cap);
+    const unsigned want = (n_rows + 4u * MV_WARPS - 1u) / (4u * MV_WARPS);  // MV_WARPS warps x 4 rows per CTA and ticket
+    const unsigned grid = std::max(1u, std::min<unsigned>((unsigned)sm_count * 3u, want));
+    const int mv_smem = (int)(MV_WARPS * MV_WIN + MV_WARPS * 8 + 16);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(sk_compact_move_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mv_smem);
+        attr_set = true;
+    }
+    cudaMemsetAsync(ticket, 0, 4, stream);
+    sk_compact_move_kernel<<<grid, MV_WARPS * 32, mv_smem, stream>>>(rows, groups, n_rows, S, piece_dst, src, dst, slices, dst_cap, ticket);
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         *err = cudaGetErrorString(e);

@@ -1,4 +1,4 @@
-// sk_device.cuh -- device-side building blocks shared by the chunk engines (sk_kernels.cu, sk_fast.cu):
+// sk_device.cuh -- device-side building blocks shared by the engines (sk_kernels.cu, sk_warp.cu):
 // PTX wrappers (mbarrier, TMA bulk copies, look-back words), SWAR byte tests and the per-record
 // restatements of the reference logic (trim scan, " BC:" search, barcode match, header surgery).
 #pragma once

@@ -44,32 +44,6 @@ struct CfgB {  // 32 KiB chunks, 8 warps
     static constexpr int STAGE = 35840;
     static constexpr int MIN_CTAS = 2;
 };
-// Geometry of the lean engine (sk_fast.cu): the chunk is a whole number of scan threads (102 x 80 B),
-// the window holds no bytes before the chunk, 8 CTAs of 4 warps per SM.
-struct GeoS {
-    static constexpr int ID = 0;
-    static constexpr int NT = 128;
-    static constexpr int PPL = 5;
-    static constexpr int WIN_MAX = NT * PPL * 16;       // 10240
-    static constexpr int CHUNK = 102 * PPL * 16;        // 8160
-    static constexpr int OVERHANG = WIN_MAX - CHUNK;    // 2080
-    static constexpr int MAXREC = NT;
-    static constexpr int MAXLINES = 4 * MAXREC + 16;
-    static constexpr int STAGE = WIN_MAX;
-    static constexpr int MIN_CTAS = 8;
-};
-struct GeoM {  // 16 KiB chunks, 8 warps, 4 CTAs per SM: half the per-chunk fixed cost per record
-    static constexpr int ID = 1;
-    static constexpr int NT = 256;
-    static constexpr int PPL = 5;
-    static constexpr int WIN_MAX = NT * PPL * 16;       // 20480
-    static constexpr int CHUNK = 204 * PPL * 16;        // 16320
-    static constexpr int OVERHANG = WIN_MAX - CHUNK;    // 4160
-    static constexpr int MAXREC = NT;
-    static constexpr int MAXLINES = 4 * MAXREC + 16;
-    static constexpr int STAGE = WIN_MAX;
-    static constexpr int MIN_CTAS = 4;
-};
 // Geometry of the warp engine (sk_warp.cu): a warp owns a tile, a lane owns a record.  Every lane scans
 // UPL 16-byte units (odd: conflict-free LDS.128); the tile is the first `tile_lanes` lanes' bytes
 // (KParams::tile_lanes, 29 unless the records are short), the remaining lanes' bytes are the overhang.
@@ -151,7 +125,7 @@ struct HalfIdx {
     const uint32_t *skeys;   // [S][nwp]: cared bytes of every sample, 0 elsewhere
 };
 constexpr int HIDX_CLS_ROWS = 7;
-// The same index in the form the lean engine probes: one 8-byte entry per slot that already names
+// The same index in the form the warp engine probes: one 8-byte entry per slot that already names
 // the first sample of the key, further samples of a key chained through `next`.
 struct FastIdx {
     const uint2 *table;     // [n_classes][2][tsize]: {tag, (first sample + 1) | more << 16}; y == 0: empty slot
@@ -263,10 +237,6 @@ inline __host__ __device__ SmemLayout smem_layout(uint32_t S, uint32_t wide, uin
 // Launchers (sk_kernels.cu)
 int launch_chunk_kernel(int cfg, int op, const KParams &p, int sm_count, void *stream, const char **err);
 int chunk_kernel_smem_bytes(int cfg, uint32_t S, uint32_t wide, uint32_t n_classes, uint32_t nwp);
-// Lean engine (sk_fast.cu)
-int fast_chunk_bytes(int geo);
-bool fast_supported(int geo, int op, const KParams &p);
-int launch_fast_kernel(int geo, int op, const KParams &p, int sm_count, void *stream, const char **err);
 // Warp engine (sk_warp.cu)
 bool warp_supported(int op, const KParams &p);
 int launch_tile_gather(const KParams &p, int sm_count, void *stream, const char **err);  // after an `unordered` launch

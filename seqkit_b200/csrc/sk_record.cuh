@@ -1,6 +1,6 @@
-// sk_lean.cuh -- device helpers shared by the lean chunk engine (sk_fast.cu) and the warp engine
-// (sk_warp.cu): newline maps, " BC:" search, class-run checks, block-wise quality trim, pigeonhole
-// barcode match, masked copy.  Include after sk_device.cuh.
+// sk_record.cuh -- per-record device helpers of the warp engine (sk_warp.cu): newline maps, " BC:" search,
+// class-run checks, block-wise quality trim, pigeonhole barcode match, masked copy.  Include after
+// sk_device.cuh.  (Round 1's lean engine, sk_fast.cu, shared them; it was retired in round 2.)
 #pragma once
 #include "sk_device.cuh"
 
@@ -24,36 +24,6 @@ __device__ __forceinline__ uint32_t bits_below(int hi) {
     return hi <= 0 ? 0u : (hi >= 32 ? 0xFFFFFFFFu : (1u << hi) - 1u);
 }
 
-// Exclusive block scan of one u32 per thread (4 or 8 warps): warp scans by shuffle, then every thread
-// sums the warp totals out of two 16-byte shared-memory reads.  `scratch` holds 2*NW words (double
-// buffered by `flip`, one barrier per call).
-template <int NT>
-__device__ __forceinline__ uint32_t block_scan_fast(uint32_t v, uint32_t *scratch, uint32_t &flip, uint32_t &total) {
-    constexpr int NW = NT / 32;
-    static_assert(NW == 4 || NW == 8, "block_scan_fast: 4 or 8 warps");
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    uint32_t x = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x += y;
-    }
-    uint32_t *s = scratch + flip * NW;
-    flip ^= 1u;
-    if (lane == 31) s[w] = x;
-    __syncthreads();
-    const uint4 a = *(const uint4 *)s;
-    uint32_t before = (w > 0 ? a.x : 0u) + (w > 1 ? a.y : 0u) + (w > 2 ? a.z : 0u) + (w > 3 ? a.w : 0u);
-    uint32_t all = a.x + a.y + a.z + a.w;
-    if (NW == 8) {
-        const uint4 b = *(const uint4 *)(s + 4);
-        before += (w > 4 ? b.x : 0u) + (w > 5 ? b.y : 0u) + (w > 6 ? b.z : 0u);
-        all += b.x + b.y + b.z + b.w;
-    }
-    total = all;
-    return before + x - v;
-}
-
 // mbarrier wait that parks the thread in hardware for up to the hinted time per attempt
 __device__ __forceinline__ void mbar_wait_parked(uint64_t *bar, uint32_t parity) {
     asm volatile(
@@ -68,19 +38,6 @@ __device__ __forceinline__ void mbar_wait_parked(uint64_t *bar, uint32_t parity)
         "r"(parity), "r"(0x989680u)
         : "memory");
 }
-#ifdef SK_PHASE_TIMING
-#define FK_T(i)                                              \
-    do {                                                     \
-        if (tid == 0) {                                      \
-            const long long t_now = clock64();               \
-            ph[i] += (unsigned long long)(t_now - t_prev);   \
-            t_prev = t_now;                                  \
-        }                                                    \
-    } while (0)
-#else
-#define FK_T(i) do { } while (0)
-#endif
-
 // Leftmost match of " BC:[class]" in [h0,h1), 16 bytes per step (see bc_find).
 __device__ __forceinline__ bool bc_find16(const uint8_t *b, const uint8_t *lut, uint32_t h0, uint32_t h1, uint32_t &st) {
     if (h1 < h0 + 5) return false;
@@ -162,126 +119,6 @@ __device__ __forceinline__ uint32_t class_run_end(const uint8_t *b, const uint8_
         break;
     }
     return e < h1 ? e : h1;
-}
-
-// Running totals of fasta_trim_by_quality.rs:33-36 over the aligned 8-byte block at window offset a,
-// in the order the reference examines the bytes: T[i] is the total after byte a+7-i, starting from
-// `total`.  Bytes outside the quality string [L3,E) contribute nothing (they are replaced by the
-// byte whose contribution is zero, sub = 33 + min_baseq <= 255).  A byte below '!' takes the wrapping
-// u8 subtraction (:35) on the byte-wise path.
-__device__ __forceinline__ void blk8_totals(const uint8_t *b, uint32_t a, uint32_t L3, uint32_t E, int sub, int minq,
-                                            int total, int (&T)[8]) {
-    uint2 v = *(const uint2 *)(b + a);
-    if (a < L3 || a + 8 > E) {
-        const uint32_t nlow = a < L3 ? L3 - a : 0u, nhigh = a + 8 > E ? a + 8 - E : 0u;
-        unsigned long long m = nlow >= 8u ? 0ull : (~0ull << (8u * nlow));
-        m = nhigh >= 8u ? 0ull : (m & (~0ull >> (8u * nhigh)));
-        const uint32_t mlo = (uint32_t)m, mhi = (uint32_t)(m >> 32), sub4 = (uint32_t)sub * 0x01010101u;
-        v.x = (v.x & mlo) | (sub4 & ~mlo);
-        v.y = (v.y & mhi) | (sub4 & ~mhi);
-    }
-    const uint32_t H = 0x80808080u, C = 0x21212121u;
-    const uint32_t bad = (~((v.x | H) - C) & ~v.x & H) | (~((v.y | H) - C) & ~v.y & H);  // bytes below '!'
-    if (!bad) {
-        T[0] = (int)__dp4a(v.y, 0x01000000u, (uint32_t)(total - sub));
-        T[1] = (int)__dp4a(v.y, 0x01010000u, (uint32_t)(total - 2 * sub));
-        T[2] = (int)__dp4a(v.y, 0x01010100u, (uint32_t)(total - 3 * sub));
-        T[3] = (int)__dp4a(v.y, 0x01010101u, (uint32_t)(total - 4 * sub));
-        T[4] = (int)__dp4a(v.x, 0x01000000u, (uint32_t)(T[3] - sub));
-        T[5] = (int)__dp4a(v.x, 0x01010000u, (uint32_t)(T[3] - 2 * sub));
-        T[6] = (int)__dp4a(v.x, 0x01010100u, (uint32_t)(T[3] - 3 * sub));
-        T[7] = (int)__dp4a(v.x, 0x01010101u, (uint32_t)(T[3] - 4 * sub));
-    } else {
-        int t = total;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const uint32_t q = ((i < 4 ? v.y : v.x) >> (8 * (3 - (i & 3)))) & 0xFFu;
-            t += q >= 33u ? (int)q - sub : (int)((q - 33u) & 0xFFu) - minq;
-            T[i] = t;
-        }
-    }
-}
-
-// fasta_trim_by_quality.rs:28-48 for one record per lane, all lanes of the warp in step: every lane
-// walks its quality string down in aligned 8-byte blocks inside one warp-synchronous loop and only
-// notes (a) the block in which the running total first exceeds 0 (:37) and (b) the block holding the
-// minimum so far (:38); the positions inside those two blocks are resolved once after the loop.
-// Must be called by all 32 lanes (`has` = this lane carries a record).  min_baseq <= 222.
-__device__ __forceinline__ bool plan_trim_warp(const uint8_t *b, bool has, uint32_t L1, uint32_t L2, uint32_t L3, uint32_t L4,
-                                               int minq, uint8_t &mode, uint32_t &kk, uint32_t &body_len) {
-    const uint32_t NONE = 0xFFFFFFFFu;
-    uint32_t k = has ? L4 - L3 : 0u;
-    while (k > 0 && is_ws(b[L3 + k - 1])) k--;  // qual.trim_end().len()  (:31)
-    __syncwarp();
-    const uint32_t E = L3 + k;
-    const int sub = 33 + minq;
-    int total = -50, lowest = -50;  // :28-29
-    uint32_t low_a = NONE, brk_a = NONE;
-    int low_total = 0, brk_total = 0;
-    uint32_t a = k ? ((E - 1u) & ~7u) : 0u;
-    bool active = k > 0;
-    while (__any_sync(0xffffffffu, active)) {
-        if (active) {
-            int T[8];
-            blk8_totals(b, a, L3, E, sub, minq, total, T);
-            const int mx = max(max(max(T[0], T[1]), max(T[2], T[3])), max(max(T[4], T[5]), max(T[6], T[7])));
-            const int mn = min(min(min(T[0], T[1]), min(T[2], T[3])), min(min(T[4], T[5]), min(T[6], T[7])));
-            if (mx > 0) {  // the break is inside this block
-                brk_a = a;
-                brk_total = total;
-                active = false;
-            } else {
-                if (mn < lowest) {  // strict '<': an earlier block keeps a tie
-                    lowest = mn;
-                    low_a = a;
-                    low_total = total;
-                }
-                total = T[7];
-                if (a <= L3) active = false;
-                else a -= 8;
-            }
-        }
-    }
-    // resolve positions: first the break block (its totals before the break may lower the minimum),
-    // then the block that holds the minimum
-    uint32_t lowest_k = k;
-    bool placed = false;
-#pragma unroll 1
-    for (int pass = 0; pass < 2; pass++) {
-        const uint32_t ra = pass == 0 ? brk_a : low_a;
-        const bool go = ra != NONE && !placed;
-        if (go) {
-            int T[8];
-            blk8_totals(b, ra, L3, E, sub, minq, pass == 0 ? brk_total : low_total, T);
-            bool ok = true;
-            int best = 0x7FFFFFFF;
-            uint32_t at = 0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                ok = ok && T[i] <= 0;           // totals after the break are never looked at
-                if (ok && T[i] < best) {        // first (highest address) of equal totals wins
-                    best = T[i];
-                    at = ra + 7u - (uint32_t)i;
-                }
-            }
-            if (pass == 0 ? best < lowest : best == lowest) {
-                lowest = best;
-                lowest_k = at - L3;
-                placed = true;
-            }
-        }
-        __syncwarp();
-    }
-    if (lowest_k == 0) {  // :44-45
-        mode = B_GARBAGE;
-        kk = 0;
-        body_len = 6;  // "N\n+\n!\n"
-        return true;
-    }
-    mode = B_TRIM;
-    kk = lowest_k;
-    body_len = 2 * lowest_k + 4;  // seq[..k] "\n+\n" qual[..k] "\n"  (:47)
-    return lowest_k <= L2 - L1;
 }
 
 // Running totals of fasta_trim_by_quality.rs:33-36 over the aligned 16-byte block at window offset a, in
@@ -568,107 +405,6 @@ __device__ __forceinline__ bool plan_trim_blocks(const uint8_t *b, bool has, uin
     return lowest_k <= L2 - L1;
 }
 
-// plan_trim_warp with two adjacent lanes per record (sub = 0 / 1): the pair walks the quality string
-// down sixteen bytes per step, lane 0 on the upper 8-byte block and lane 1 on the one below it; each
-// lane computes its block's totals relative to 0, one shuffle gives lane 1 the sum of lane 0's block
-// (its entering total), another tells the pair whether either block contains the break (:37).  Each
-// lane keeps the minimum over its own blocks; the pair's minimum is the lower of the two, the block
-// examined first winning a tie (:38).  The positions are resolved after the loop, the break block by
-// lane 0 and the minimum block by lane 1 at the same time.  Halves the length of the serial chain.
-// Must be called by all 32 lanes; both lanes of a pair pass the same arguments.  min_baseq <= 222.
-__device__ __forceinline__ bool plan_trim_pair(const uint8_t *b, bool has, uint32_t sub, uint32_t L1, uint32_t L2,
-                                               uint32_t L3, uint32_t L4, int minq, uint8_t &mode, uint32_t &kk,
-                                               uint32_t &body_len) {
-    const uint32_t FULL = 0xffffffffu;
-    const int NONE = -1;
-    uint32_t k = has ? L4 - L3 : 0u;
-    while (k > 0 && is_ws(b[L3 + k - 1])) k--;  // qual.trim_end().len()  (:31)
-    __syncwarp();
-    const uint32_t E = L3 + k;
-    const int sq = 33 + minq;
-    int tot = -50, lowest = -50;  // :28-29; tot = total entering lane 0's block of this step
-    int low_a = NONE, low_total = 0, brk_a = NONE, brk_total = 0;
-    int a = (k ? (int)((E - 1u) & ~7u) : 0) - 8 * (int)sub;
-    bool active = k > 0;
-    while (__any_sync(FULL, active)) {
-        const bool mine = active && a >= 0 && a + 8 > (int)L3;
-        int S = 0, mx = -0x40000000, mn = 0x40000000;
-        if (mine) {
-            int T[8];
-            blk8_totals(b, (uint32_t)a, L3, E, sq, minq, 0, T);
-            S = T[7];
-            mx = max(max(max(T[0], T[1]), max(T[2], T[3])), max(max(T[4], T[5]), max(T[6], T[7])));
-            mn = min(min(min(T[0], T[1]), min(T[2], T[3])), min(min(T[4], T[5]), min(T[6], T[7])));
-        }
-        const int S_o = __shfl_xor_sync(FULL, S, 1);
-        const int enter = tot + (sub ? S_o : 0);
-        const bool brk_me = mine && enter + mx > 0;
-        const bool brk_o = __shfl_xor_sync(FULL, (int)brk_me, 1) != 0;
-        const bool reached = mine && !(sub && brk_o);  // lane 0's block comes first
-        if (reached) {
-            if (brk_me) {
-                brk_a = a;
-                brk_total = enter;
-            } else if (enter + mn < lowest) {
-                lowest = enter + mn;
-                low_a = a;
-                low_total = enter;
-            }
-        }
-        tot += S + S_o;
-        const int a_first = a + 8 * (int)sub;  // lane 0's block of this step
-        active = active && !(brk_me || brk_o) && a_first - 8 > (int)L3;
-        a -= 16;
-    }
-    // the pair's break block (lane 0's if it broke, else lane 1's) and minimum block
-    {
-        const int ba_o = __shfl_xor_sync(FULL, brk_a, 1), bt_o = __shfl_xor_sync(FULL, brk_total, 1);
-        const int b0 = sub ? ba_o : brk_a, b1 = sub ? brk_a : ba_o;
-        const int t0 = sub ? bt_o : brk_total, t1 = sub ? brk_total : bt_o;
-        brk_a = b0 != NONE ? b0 : b1;
-        brk_total = b0 != NONE ? t0 : t1;
-        const int lo_o = __shfl_xor_sync(FULL, lowest, 1), la_o = __shfl_xor_sync(FULL, low_a, 1);
-        const int lt_o = __shfl_xor_sync(FULL, low_total, 1);
-        if (la_o != NONE && (lo_o < lowest || (lo_o == lowest && (low_a == NONE || la_o > low_a)))) {
-            lowest = lo_o;
-            low_a = la_o;
-            low_total = lt_o;
-        }
-    }
-    // resolve: lane 0 looks into the break block, lane 1 into the minimum block
-    const int ra = sub ? low_a : brk_a;
-    int best = 0x7FFFFFFF, at = 0;
-    if (ra != NONE) {
-        int T[8];
-        blk8_totals(b, (uint32_t)ra, L3, E, sq, minq, sub ? low_total : brk_total, T);
-        bool ok = true;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            ok = ok && T[i] <= 0;     // totals after the break are never looked at
-            if (ok && T[i] < best) {  // first (highest address) of equal totals wins
-                best = T[i];
-                at = ra + 7 - i;
-            }
-        }
-    }
-    __syncwarp();
-    const int best0 = __shfl_sync(FULL, best, (threadIdx.x & 31) & ~1), at0 = __shfl_sync(FULL, at, (threadIdx.x & 31) & ~1);
-    const int at1 = __shfl_sync(FULL, at, (threadIdx.x & 31) | 1);
-    uint32_t lowest_k = k;
-    if (brk_a != NONE && best0 < lowest) lowest_k = (uint32_t)at0 - L3;  // a lower total just before the break
-    else if (low_a != NONE) lowest_k = (uint32_t)at1 - L3;
-    if (lowest_k == 0) {  // :44-45
-        mode = B_GARBAGE;
-        kk = 0;
-        body_len = 6;  // "N\n+\n!\n"
-        return true;
-    }
-    mode = B_TRIM;
-    kk = lowest_k;
-    body_len = 2 * lowest_k + 4;  // seq[..k] "\n+\n" qual[..k] "\n"  (:47)
-    return lowest_k <= L2 - L1;
-}
-
 // Pigeonhole barcode match on the compact tables (FastIdx): both half-key probes of a class are
 // issued before either is consumed; a probe stops at the first slot whose tag matches (tags are
 // unique per table, checked when the sheet is packed).  Same contract as hidx_match.
@@ -810,6 +546,147 @@ __device__ __forceinline__ void mask_copy(uint8_t *dst, const uint8_t *seq, cons
     }
     while (len) SK_MASK_BYTE()
 #undef SK_MASK_BYTE
+}
+
+// ------------------------------------------------------------------------------------------------
+// window -> global memory copies (the emit of sk_warp.cu, the move of sk_compact.cu)
+// ------------------------------------------------------------------------------------------------
+// Up to eight bytes of the window from any byte offset, as aligned words and funnel shifts.  The window
+// is addressed as base + offset throughout, so that the compiler keeps the accesses in the shared space
+// (a pointer rebuilt from an integer turns them into generic loads).
+__device__ __forceinline__ uint32_t lds_un32(const uint8_t *win, uint32_t off) {
+    const uint32_t *w = (const uint32_t *)(win + (off & ~3u));
+    return __funnelshift_r(w[0], w[1], (off & 3u) * 8u);
+}
+__device__ __forceinline__ uint2 lds_un64(const uint8_t *win, uint32_t off) {
+    const uint32_t *w = (const uint32_t *)(win + (off & ~3u));
+    const uint32_t sh = (off & 3u) * 8u;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
+    return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
+}
+// Sixteen bytes of the window from any byte offset.
+__device__ __forceinline__ uint4 lds_unaligned16(const uint8_t *win, uint32_t off) {
+    const uint32_t *w = (const uint32_t *)(win + (off & ~3u));
+    const uint32_t sh = (off & 3u) * 8u;
+    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+    return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
+}
+// Thirty-two bytes of the window from any byte offset >= -32.
+struct U256 {
+    uint32_t w[8];
+};
+__device__ __forceinline__ U256 lds_unaligned32(const uint8_t *win, int off) {
+    const uint32_t *p = (const uint32_t *)(win + (off & ~3));
+    const uint32_t sh = ((uint32_t)off & 3u) * 8u;
+    U256 r;
+    uint32_t lo = p[0];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const uint32_t hi = p[k + 1];
+        r.w[k] = __funnelshift_r(lo, hi, sh);
+        lo = hi;
+    }
+    return r;
+}
+// bytes [0, f) of a, the others of b (0 <= f < 32)
+__device__ __forceinline__ U256 merge_low32(const U256 &a, const U256 &b, uint32_t f) {
+    // Three instructions a word: the bit position of byte f in word k, clamped below at 0 by the fused
+    // add-max and above at 32 by shl (PTX clamps the shift amount), is where b takes over from a.
+    U256 r;
+    const int t = 8 * (int)f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int s = __viaddmax_s32(t, -32 * k, 0);
+        uint32_t mb;
+        asm("shl.b32 %0, %1, %2;" : "=r"(mb) : "r"(0xFFFFFFFFu), "r"(s));
+        r.w[k] = (a.w[k] & ~mb) | (b.w[k] & mb);
+    }
+    return r;
+}
+// One 256-bit store to a 32-byte aligned global address (sm_100: STG.256).
+__device__ __forceinline__ void stg256(void *dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                       uint32_t g, uint32_t h) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e),
+                 "r"(f), "r"(g), "r"(h)
+                 : "memory");
+}
+// Lane-serial copy of `len` window bytes from offset `so` to global memory, any alignment on either side.
+// The destination is brought to a 16-byte boundary by at most one store of each size 1, 2, 4, 8 (no
+// loops: the lanes of a warp copy runs of different alignment), one of 16 to reach a 32-byte sector
+// boundary, then 32 bytes per step (8 LDS.32 + 8 funnel shifts + 1 STG.256), then at most one store of
+// each size 16, 8, 4, 2, 1.  The window is only ever read as aligned words (up to seven bytes past the run).
+__device__ __forceinline__ void gcopy(uint8_t *dst, const uint8_t *win, uint32_t so, uint32_t len) {
+    if (((uint32_t)(uintptr_t)dst & 1u) && len >= 1u) {
+        *dst = win[so];
+        dst += 1, so += 1, len -= 1;
+    }
+    if (((uint32_t)(uintptr_t)dst & 2u) && len >= 2u) {
+        *(uint16_t *)dst = (uint16_t)lds_un32(win, so);
+        dst += 2, so += 2, len -= 2;
+    }
+    if (((uint32_t)(uintptr_t)dst & 4u) && len >= 4u) {
+        *(uint32_t *)dst = lds_un32(win, so);
+        dst += 4, so += 4, len -= 4;
+    }
+    if (((uint32_t)(uintptr_t)dst & 8u) && len >= 8u) {
+        *(uint2 *)dst = lds_un64(win, so);
+        dst += 8, so += 8, len -= 8;
+    }
+    // dst is 16-byte aligned here; one 16-byte step brings it to a 32-byte sector boundary, then whole
+    // sectors go out with 256-bit stores (STG.256: half as many requests, none of them a partial sector)
+    if ((((uint32_t)(uintptr_t)dst & 16u) && len >= 16u)) {
+        *(uint4 *)dst = lds_unaligned16(win, so);
+        dst += 16, so += 16, len -= 16;
+    }
+    if (len >= 32u) {
+        const uint32_t sh = (so & 3u) * 8u;
+        const uint32_t *sw = (const uint32_t *)(win + (so & ~3u));
+        uint32_t lo = *sw;
+        const uint32_t n32 = len >> 5;
+#pragma unroll 1
+        for (uint32_t i = 0; i < n32; i++) {
+            const uint32_t w1 = sw[1], w2 = sw[2], w3 = sw[3], w4 = sw[4], w5 = sw[5], w6 = sw[6], w7 = sw[7], w8 = sw[8];
+            stg256(dst, __funnelshift_r(lo, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
+                   __funnelshift_r(w3, w4, sh), __funnelshift_r(w4, w5, sh), __funnelshift_r(w5, w6, sh),
+                   __funnelshift_r(w6, w7, sh), __funnelshift_r(w7, w8, sh));
+            lo = w8;
+            sw += 8;
+            dst += 32;
+        }
+        so += n32 * 32u, len &= 31u;
+    }
+    if (len & 16u) {
+        *(uint4 *)dst = lds_unaligned16(win, so);
+        dst += 16, so += 16;
+    }
+    if (len & 8u) {
+        if (((uint32_t)(uintptr_t)dst & 7u) == 0u) {
+            *(uint2 *)dst = lds_un64(win, so);
+        } else {  // (a run shorter than its head alignment)
+#pragma unroll 1
+            for (uint32_t i = 0; i < 8u; i++) dst[i] = win[so + i];
+        }
+        dst += 8, so += 8;
+    }
+    if (len & 4u) {
+        if (((uint32_t)(uintptr_t)dst & 3u) == 0u) {
+            *(uint32_t *)dst = lds_un32(win, so);
+        } else {
+#pragma unroll 1
+            for (uint32_t i = 0; i < 4u; i++) dst[i] = win[so + i];
+        }
+        dst += 4, so += 4;
+    }
+    if (len & 2u) {
+        if (((uint32_t)(uintptr_t)dst & 1u) == 0u) {
+            *(uint16_t *)dst = (uint16_t)lds_un32(win, so);
+        } else {
+            dst[0] = win[so];
+            dst[1] = win[so + 1];
+        }
+        dst += 2, so += 2;
+    }
+    if (len & 1u) *dst = win[so];
 }
 
 }  // namespace sk

@@ -2,10 +2,10 @@
 // quality trim), trim by quality and mask by quality, with one warp per tile and one lane per record
 // (DESIGN.md section 3.0).
 //
-// The lean engine (sk_fast.cu) spends a third of its warp time at CTA barriers: its per-record phase
-// runs one lane per record on the few warps a 16 KiB chunk fills, while the other warps of the CTA
-// wait.  Here a warp owns a whole tile of the stream from load to store (the warps of a CTA only start
-// their tiles together, for the instruction cache):
+// A CTA-per-chunk engine (round 1's lean engine, retired) spends a third of its warp time at CTA barriers:
+// its per-record phase runs one lane per record on the few warps a 16 KiB chunk fills, while the other warps
+// of the CTA wait.  Here a warp owns a whole tile of the stream from load to store (the warps of a CTA only
+// start their tiles together, for the instruction cache):
 //   * tile = 29 lanes x 400 B of input (about 31 records of 2x150 bp FASTQ) + 3 lanes of overhang,
 //     loaded by one TMA bulk copy into the warp's private window; 16 such warps per SM sit in
 //     different phases, so nobody waits at a barrier and every per-record step has its 32 lanes busy;
@@ -38,7 +38,7 @@ namespace sk {
 extern __shared__ __align__(128) unsigned char sk_smem[];
 }
 #include "sk_device.cuh"
-#include "sk_lean.cuh"
+#include "sk_record.cuh"
 
 #ifndef SKW_LOCKSTEP
 #define SKW_LOCKSTEP 1  // 0: every warp takes its own tickets
@@ -67,144 +67,6 @@ struct WLayout {
     static constexpr uint32_t dyn = lut + 256;  // hcls rows, per-sample counters, UMI lengths
 };
 static_assert(WLayout::per_warp % 16 == 0, "warp areas are 16-byte aligned");
-
-// Up to eight bytes of the window from any byte offset, as aligned words and funnel shifts.  The window
-// is addressed as base + offset throughout, so that the compiler keeps the accesses in the shared space
-// (a pointer rebuilt from an integer turns them into generic loads).
-__device__ __forceinline__ uint32_t lds_un32(const uint8_t *win, uint32_t off) {
-    const uint32_t *w = (const uint32_t *)(win + (off & ~3u));
-    return __funnelshift_r(w[0], w[1], (off & 3u) * 8u);
-}
-__device__ __forceinline__ uint2 lds_un64(const uint8_t *win, uint32_t off) {
-    const uint32_t *w = (const uint32_t *)(win + (off & ~3u));
-    const uint32_t sh = (off & 3u) * 8u;
-    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2];
-    return make_uint2(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh));
-}
-// Sixteen bytes of the window from any byte offset.
-__device__ __forceinline__ uint4 lds_unaligned16(const uint8_t *win, uint32_t off) {
-    const uint32_t *w = (const uint32_t *)(win + (off & ~3u));
-    const uint32_t sh = (off & 3u) * 8u;
-    const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
-    return make_uint4(__funnelshift_r(w0, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh), __funnelshift_r(w3, w4, sh));
-}
-// Thirty-two bytes of the window from any byte offset >= -32.
-struct U256 {
-    uint32_t w[8];
-};
-__device__ __forceinline__ U256 lds_unaligned32(const uint8_t *win, int off) {
-    const uint32_t *p = (const uint32_t *)(win + (off & ~3));
-    const uint32_t sh = ((uint32_t)off & 3u) * 8u;
-    U256 r;
-    uint32_t lo = p[0];
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const uint32_t hi = p[k + 1];
-        r.w[k] = __funnelshift_r(lo, hi, sh);
-        lo = hi;
-    }
-    return r;
-}
-// bytes [0, f) of a, the others of b (0 <= f < 32)
-__device__ __forceinline__ U256 merge_low32(const U256 &a, const U256 &b, uint32_t f) {
-    // Three instructions a word: the bit position of byte f in word k, clamped below at 0 by the fused
-    // add-max and above at 32 by shl (PTX clamps the shift amount), is where b takes over from a.
-    U256 r;
-    const int t = 8 * (int)f;
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const int s = __viaddmax_s32(t, -32 * k, 0);
-        uint32_t mb;
-        asm("shl.b32 %0, %1, %2;" : "=r"(mb) : "r"(0xFFFFFFFFu), "r"(s));
-        r.w[k] = (a.w[k] & ~mb) | (b.w[k] & mb);
-    }
-    return r;
-}
-// One 256-bit store to a 32-byte aligned global address (sm_100: STG.256).
-__device__ __forceinline__ void stg256(void *dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
-                                       uint32_t g, uint32_t h) {
-    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e),
-                 "r"(f), "r"(g), "r"(h)
-                 : "memory");
-}
-// Lane-serial copy of `len` window bytes from offset `so` to global memory, any alignment on either side.
-// The destination is brought to a 16-byte boundary by at most one store of each size 1, 2, 4, 8 (no
-// loops: the lanes of a warp copy runs of different alignment), one of 16 to reach a 32-byte sector
-// boundary, then 32 bytes per step (8 LDS.32 + 8 funnel shifts + 1 STG.256), then at most one store of
-// each size 16, 8, 4, 2, 1.  The window is only ever read as aligned words (up to seven bytes past the run).
-__device__ __forceinline__ void gcopy(uint8_t *dst, const uint8_t *win, uint32_t so, uint32_t len) {
-    if (((uint32_t)(uintptr_t)dst & 1u) && len >= 1u) {
-        *dst = win[so];
-        dst += 1, so += 1, len -= 1;
-    }
-    if (((uint32_t)(uintptr_t)dst & 2u) && len >= 2u) {
-        *(uint16_t *)dst = (uint16_t)lds_un32(win, so);
-        dst += 2, so += 2, len -= 2;
-    }
-    if (((uint32_t)(uintptr_t)dst & 4u) && len >= 4u) {
-        *(uint32_t *)dst = lds_un32(win, so);
-        dst += 4, so += 4, len -= 4;
-    }
-    if (((uint32_t)(uintptr_t)dst & 8u) && len >= 8u) {
-        *(uint2 *)dst = lds_un64(win, so);
-        dst += 8, so += 8, len -= 8;
-    }
-    // dst is 16-byte aligned here; one 16-byte step brings it to a 32-byte sector boundary, then whole
-    // sectors go out with 256-bit stores (STG.256: half as many requests, none of them a partial sector)
-    if ((((uint32_t)(uintptr_t)dst & 16u) && len >= 16u)) {
-        *(uint4 *)dst = lds_unaligned16(win, so);
-        dst += 16, so += 16, len -= 16;
-    }
-    if (len >= 32u) {
-        const uint32_t sh = (so & 3u) * 8u;
-        const uint32_t *sw = (const uint32_t *)(win + (so & ~3u));
-        uint32_t lo = *sw;
-        const uint32_t n32 = len >> 5;
-#pragma unroll 1
-        for (uint32_t i = 0; i < n32; i++) {
-            const uint32_t w1 = sw[1], w2 = sw[2], w3 = sw[3], w4 = sw[4], w5 = sw[5], w6 = sw[6], w7 = sw[7], w8 = sw[8];
-            stg256(dst, __funnelshift_r(lo, w1, sh), __funnelshift_r(w1, w2, sh), __funnelshift_r(w2, w3, sh),
-                   __funnelshift_r(w3, w4, sh), __funnelshift_r(w4, w5, sh), __funnelshift_r(w5, w6, sh),
-                   __funnelshift_r(w6, w7, sh), __funnelshift_r(w7, w8, sh));
-            lo = w8;
-            sw += 8;
-            dst += 32;
-        }
-        so += n32 * 32u, len &= 31u;
-    }
-    if (len & 16u) {
-        *(uint4 *)dst = lds_unaligned16(win, so);
-        dst += 16, so += 16;
-    }
-    if (len & 8u) {
-        if (((uint32_t)(uintptr_t)dst & 7u) == 0u) {
-            *(uint2 *)dst = lds_un64(win, so);
-        } else {  // (a run shorter than its head alignment)
-#pragma unroll 1
-            for (uint32_t i = 0; i < 8u; i++) dst[i] = win[so + i];
-        }
-        dst += 8, so += 8;
-    }
-    if (len & 4u) {
-        if (((uint32_t)(uintptr_t)dst & 3u) == 0u) {
-            *(uint32_t *)dst = lds_un32(win, so);
-        } else {
-#pragma unroll 1
-            for (uint32_t i = 0; i < 4u; i++) dst[i] = win[so + i];
-        }
-        dst += 4, so += 4;
-    }
-    if (len & 2u) {
-        if (((uint32_t)(uintptr_t)dst & 1u) == 0u) {
-            *(uint16_t *)dst = (uint16_t)lds_un32(win, so);
-        } else {
-            dst[0] = win[so];
-            dst[1] = win[so + 1];
-        }
-        dst += 2, so += 2;
-    }
-    if (len & 1u) *dst = win[so];
-}
 
 // min_baseq > 222 (never in practice): the byte-wise trim of sk_device.cuh, out of line.  Returns
 // kk | mode << 16 | fine << 24 (no reference parameters: they would pin the caller's variables to the stack).

@@ -226,7 +226,9 @@ class Engine:
                 _check(self.ctx, self.lib.sk_download_compact(self.ctx, 0, mate, buf, n), "sk_download_compact")
                 _check(self.ctx, self.lib.sk_download_slices(self.ctx, 0, mate, sl), "sk_download_slices")
                 self.wait()
-                assert sl[S].offset == n and sl[S].len == res.out_bytes[mate], "slice table and outcome block disagree"
+                assert sl[S].offset == n and sl[S].len == res.out_bytes[mate], \
+                    "slice table and outcome block disagree: mate %d extent %d / %d, payload %d / %d, reserved %d" % (
+                        mate, sl[S].offset, n, sl[S].len, res.out_bytes[mate], res.reserved)
                 raw = buf.raw
                 for s, name in enumerate(names):
                     key = (name + (b"_%d.fq.gz" % (mate + 1) if paired else b".fq.gz")).decode()

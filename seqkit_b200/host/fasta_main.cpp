@@ -11,8 +11,15 @@
 //
 // This file is the *batcher*: it reads bytes, cuts batches at record boundaries (a newline count; no
 // per-read arithmetic happens here), packs them into pinned multi-MB buffers, calls the CUDA path
-// through the ABI with two slots in flight, and streams the results to stdout / the gzip children in
-// batch order.  Every operator result comes from the GPU; there is no CPU fallback.
+// through the ABI and streams the results to stdout / the per-sample gzip sinks in batch order.  Batches are
+// dealt round-robin to every visible GPU (one context per device, two slots each: consecutive batches =
+// contiguous record ranges on different GPUs; SK_DEVICE pins one device, SK_GPUS limits the count); results
+// are consumed strictly in batch order, so output bytes do not depend on the number of GPUs.  Per-sample
+// output comes back as one contiguous slice per sample, mate and batch (sk_demux_compact); the per-sample
+// counters are summed on the devices and merged with one NCCL all-reduce at the end of the run.  gzip is
+// block-parallel deflate on host threads (independent gzip members, zlib), or one `gzip -c` / `pigz -c`
+// child per file as in the reference with SK_GZIP=child.  Every operator result comes from the GPU; there
+// is no CPU fallback.
 #include <errno.h>
 #include <fcntl.h>
 #include <signal.h>
@@ -25,8 +32,15 @@
 #include <sys/wait.h>
 #include <unistd.h>
 
+#include <time.h>
+#include <zlib.h>
+
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <map>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <unordered_map>
@@ -73,13 +87,43 @@ static const char *USAGE_DEMUX =
     "sample sheet. Each read in the pooled FASTQ file must carry a BC:xxxxxxxx\n"
     "field in its header.\n";
 
-struct GzipSink;
-static std::vector<GzipSink *> g_sinks;  // closed (children reaped) before any exit
+// SK_TIMING=1: wall-clock seconds per phase of the batcher on stderr at exit (diagnostic; off by default)
+static double now_s() {
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+static const double g_t0 = now_s();
+static double g_phase[6] = {0, 0, 0, 0, 0, 0};  // init, read+submit, wait, drain, close, -
+struct Phase {
+    int k;
+    double t;
+    explicit Phase(int k_) : k(k_), t(now_s()) {}
+    ~Phase() { g_phase[k] += now_s() - t; }
+};
+
+struct Sink;
+static std::vector<Sink *> g_sinks;  // flushed and closed (children reaped) before any exit
 static void close_all_sinks();
+static std::vector<pid_t> g_gunzip;  // `gunzip -c` children of *.gz inputs
 
 [[noreturn]] static void finish(int code) {
     fflush(stdout);
-    close_all_sinks();
+    // On an early exit a gunzip child may sit blocked on its full output pipe: it goes first, so that nothing
+    // that waits below can wait on it.
+    for (pid_t pid : g_gunzip) kill(pid, SIGKILL);
+    for (pid_t pid : g_gunzip) {
+        int st;
+        waitpid(pid, &st, 0);
+    }
+    g_gunzip.clear();
+    {
+        Phase ph(4);
+        close_all_sinks();
+    }
+    if (getenv("SK_TIMING"))
+        fprintf(stderr, "seqkit_b200 timing: total %.3f s = init %.3f + read/submit %.3f + wait %.3f + drain %.3f + close %.3f\n",
+                now_s() - g_t0, g_phase[0], g_phase[1], g_phase[2], g_phase[3], g_phase[4]);
     fflush(stderr);
     _exit(code);
 }
@@ -143,11 +187,11 @@ struct Input {
             fd = 0;
             return;
         }
-        int f = open(path.c_str(), O_RDONLY);
+        int f = open(path.c_str(), O_RDONLY | O_CLOEXEC);  // (every descriptor is close-on-exec: children inherit 0/1/2 only)
         if (f < 0) fatal("Cannot open file %s for reading.", path.c_str());
         if (path.size() >= 3 && path.compare(path.size() - 3, 3, ".gz") == 0) {
             int pp[2];
-            if (pipe(pp) != 0) fatal("Cannot start gunzip process.");
+            if (pipe2(pp, O_CLOEXEC) != 0) fatal("Cannot start gunzip process.");
             pid_t pid = fork();
             if (pid < 0) fatal("Cannot start gunzip process.");
             if (pid == 0) {
@@ -163,6 +207,7 @@ struct Input {
             close(f);
             fd = pp[0];
             child = pid;
+            g_gunzip.push_back(pid);
             fcntl(fd, F_SETPIPE_SZ, 1 << 20);
         } else {
             fd = f;
@@ -183,24 +228,27 @@ struct Input {
     }
 };
 
-// One input stream of the batcher: bytes accumulate in one of two pinned buffers (the other one may
-// still be the source of an in-flight H2D copy); complete records are found by counting newlines.
+// One input stream of the batcher: bytes accumulate in one buffer of a ring of pinned buffers; the buffers
+// behind it in the ring belong to batches that are still in flight (sources of H2D copies, and of the header
+// text quoted in messages), so a buffer is written again only after every batch cut from it has been
+// consumed.  Complete records are found by counting newlines.
 struct Stream {
     Input in;
     bool active = false;
-    uint8_t *buf[2] = {nullptr, nullptr};
+    std::vector<uint8_t *> ring;
     size_t cap = 0;
     int cur = 0;
     size_t fill = 0, scanned = 0;
     uint32_t lines_mod = 0;
     uint32_t lpr = 4;
-    std::vector<uint32_t> rec_ends;  // end offset (exclusive) of every complete record in buf[cur]
+    std::vector<uint32_t> rec_ends;  // end offset (exclusive) of every complete record in ring[cur]
     uint64_t records_done = 0;
 
+    uint8_t *buf() const { return ring[(size_t)cur]; }
     void top_up() {
         if (!active) return;
-        if (!in.eof && fill < cap) fill += in.read_some(buf[cur] + fill, cap - fill);
-        const uint8_t *b = buf[cur];
+        if (!in.eof && fill < cap) fill += in.read_some(buf() + fill, cap - fill);
+        const uint8_t *b = buf();
         while (scanned < fill) {
             const uint8_t *nl = (const uint8_t *)memchr(b + scanned, '\n', fill - scanned);
             if (!nl) {
@@ -219,11 +267,13 @@ struct Stream {
     size_t avail() const { return rec_ends.size() + ((in.eof && fill > last_end()) ? 1 : 0); }
     bool drained() const { return in.eof && fill == 0; }
     size_t bytes_for(size_t n) const { return n == 0 ? 0 : (n <= rec_ends.size() ? rec_ends[n - 1] : fill); }
-    // drops the first `bytes` (= n records) of the buffer; the tail moves to the other pinned buffer
+    // moves on to the next buffer of the ring without dropping anything (the current one stays as it is)
+    void park() { cur = (cur + 1) % (int)ring.size(); }
+    // drops the first `bytes` (= n records) of the buffer; the tail moves to the next buffer of the ring
     void consume(size_t n, size_t bytes) {
-        const int nxt = cur ^ 1;
+        const int nxt = (cur + 1) % (int)ring.size();
         const size_t tail = fill - bytes;
-        if (tail) memcpy(buf[nxt], buf[cur] + bytes, tail);
+        if (tail) memcpy(ring[(size_t)nxt], buf() + bytes, tail);
         const size_t nr = std::min(n, rec_ends.size());
         rec_ends.erase(rec_ends.begin(), rec_ends.begin() + nr);
         for (auto &e : rec_ends) e -= (uint32_t)bytes;
@@ -237,21 +287,32 @@ struct Stream {
 // ------------------------------------------------------------------------------------------------
 // GzipWriter (common.rs:49-81)
 // ------------------------------------------------------------------------------------------------
-struct GzipSink {
+// A per-sample output file.  The reference wires File::create(path) to the stdout of a `gzip -c` (or, with
+// --parallel, `pigz -c`) child and writes into the child's stdin; ChildSink does exactly that (SK_GZIP=child).
+// The default, DeflateSink, compresses in this process: the bytes of a file are cut into blocks, every block
+// becomes one gzip member (RFC 1952 allows a file to be a sequence of members; `gunzip`, `zcat` and every
+// gzip reader concatenate them) on a pool of host threads, and the members are written in order.  The
+// decompressed bytes are the same; the compressed bytes are not (nor are they with pigz).
+struct Sink {
+    virtual ~Sink() {}
+    virtual void append(const uint8_t *p, size_t n) = 0;
+    virtual void flush_last() = 0;  // no more data: hand the rest to the compressor / close the pipe
+    virtual void close_wait() = 0;  // after flush_last (and, for DeflateSink, after the pool has drained)
+};
+
+struct ChildSink : Sink {
     int fd = -1;
     pid_t child = 0;
     void open_path(const std::string &path, bool pigz) {
-        int f = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+        int f = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0666);
         if (f < 0) fatal("Cannot open file %s for writing.", path.c_str());
         int pp[2];
-        if (pipe(pp) != 0) fatal("Cannot start %s process.", pigz ? "pigz" : "gzip");
+        if (pipe2(pp, O_CLOEXEC) != 0) fatal("Cannot start %s process.", pigz ? "pigz" : "gzip");
         pid_t pid = fork();
         if (pid < 0) fatal("Cannot start %s process.", pigz ? "pigz" : "gzip");
         if (pid == 0) {
             dup2(pp[0], 0);
             dup2(f, 1);
-            // the child must not hold the write ends of the other sinks' pipes open
-            for (int k = 3; k < 4096; k++) close(k);
             execlp(pigz ? "pigz" : "gzip", pigz ? "pigz" : "gzip", "-c", (char *)nullptr);
             _exit(127);
         }
@@ -262,9 +323,13 @@ struct GzipSink {
         fcntl(fd, F_SETPIPE_SZ, 1 << 20);
         g_sinks.push_back(this);
     }
-    void close_wait() {
+    void append(const uint8_t *p, size_t n) override { write_all(fd, p, n); }
+    void flush_last() override {
         if (fd >= 0) close(fd);
         fd = -1;
+    }
+    void close_wait() override {
+        flush_last();
         if (child > 0) {
             int st;
             waitpid(child, &st, 0);
@@ -272,32 +337,177 @@ struct GzipSink {
         child = 0;
     }
 };
-static void close_all_sinks() {
-    for (auto *s : g_sinks)
-        if (s->fd >= 0) {
-            close(s->fd);
-            s->fd = -1;
+
+struct DeflateSink;
+struct DeflateJob {
+    DeflateSink *sink;
+    uint64_t seq;
+    std::vector<uint8_t> data;
+};
+// The compressor threads.  submit() blocks while more than `limit` uncompressed bytes are queued.
+struct DeflatePool {
+    std::mutex m;
+    std::condition_variable cv_job, cv_space, cv_idle;
+    std::deque<DeflateJob> q;
+    size_t queued = 0, busy = 0;
+    const size_t limit = 256u << 20;
+    bool stop = false;
+    int level = 4;
+    std::vector<std::thread> th;
+    void start() {
+        if (!th.empty()) return;
+        if (const char *e = getenv("SK_GZIP_LEVEL")) level = std::max(1, std::min(9, atoi(e)));
+        unsigned n = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+        if (const char *e = getenv("SK_GZIP_THREADS")) n = (unsigned)std::max(1, atoi(e));
+        for (unsigned i = 0; i < n; i++) th.emplace_back([this] { work(); });
+    }
+    void submit(DeflateJob &&j) {
+        start();
+        std::unique_lock<std::mutex> lk(m);
+        cv_space.wait(lk, [&] { return queued < limit; });
+        queued += j.data.size();
+        q.push_back(std::move(j));
+        cv_job.notify_one();
+    }
+    void wait_idle() {
+        std::unique_lock<std::mutex> lk(m);
+        cv_idle.wait(lk, [&] { return q.empty() && busy == 0; });
+    }
+    void shutdown() {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            stop = true;
         }
+        cv_job.notify_all();
+        for (auto &t : th) t.join();
+        th.clear();
+    }
+    void work();
+};
+static DeflatePool g_pool;
+
+struct DeflateSink : Sink {
+    static constexpr size_t BLOCK = 512u << 10;
+    int fd = -1;
+    std::vector<uint8_t> pending;
+    uint64_t next_seq = 0;
+    std::mutex wm;  // members leave in sequence order
+    uint64_t next_write = 0;
+    std::map<uint64_t, std::vector<uint8_t>> done;
+    void open_path(const std::string &path) {
+        fd = open(path.c_str(), O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0666);
+        if (fd < 0) fatal("Cannot open file %s for writing.", path.c_str());
+        g_sinks.push_back(this);
+    }
+    void cut() {
+        DeflateJob j{this, next_seq++, std::move(pending)};
+        pending = std::vector<uint8_t>();
+        g_pool.submit(std::move(j));
+    }
+    void append(const uint8_t *p, size_t n) override {
+        while (n) {
+            const size_t k = std::min(n, BLOCK - pending.size());
+            pending.insert(pending.end(), p, p + k);
+            p += k;
+            n -= k;
+            if (pending.size() >= BLOCK) cut();
+        }
+    }
+    void flush_last() override {
+        if (!pending.empty() || next_seq == 0) cut();  // an empty file is one empty member, as `gzip -c` writes it
+    }
+    void deliver(uint64_t seq, std::vector<uint8_t> &&z) {
+        std::lock_guard<std::mutex> lk(wm);
+        done.emplace(seq, std::move(z));
+        while (!done.empty() && done.begin()->first == next_write) {
+            write_all(fd, done.begin()->second.data(), done.begin()->second.size());
+            done.erase(done.begin());
+            next_write++;
+        }
+    }
+    void close_wait() override {
+        if (fd >= 0) close(fd);
+        fd = -1;
+    }
+};
+void DeflatePool::work() {
+    for (;;) {
+        DeflateJob j;
+        {
+            std::unique_lock<std::mutex> lk(m);
+            cv_job.wait(lk, [&] { return stop || !q.empty(); });
+            if (q.empty()) return;
+            j = std::move(q.front());
+            q.pop_front();
+            busy++;
+        }
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        std::vector<uint8_t> z;
+        if (deflateInit2(&zs, level, Z_DEFLATED, 15 + 16 /* gzip wrapper */, 8, Z_DEFAULT_STRATEGY) == Z_OK) {
+            z.resize(deflateBound(&zs, (uLong)j.data.size()) + 64);
+            zs.next_in = j.data.data();
+            zs.avail_in = (uInt)j.data.size();
+            zs.next_out = z.data();
+            zs.avail_out = (uInt)z.size();
+            deflate(&zs, Z_FINISH);
+            z.resize(z.size() - zs.avail_out);
+            deflateEnd(&zs);
+        }
+        j.sink->deliver(j.seq, std::move(z));
+        {
+            std::lock_guard<std::mutex> lk(m);
+            queued -= j.data.size();
+            busy--;
+        }
+        cv_space.notify_all();
+        cv_idle.notify_all();
+    }
+}
+static void close_all_sinks() {
+    for (auto *s : g_sinks) s->flush_last();
+    if (!g_pool.th.empty()) {
+        g_pool.wait_idle();
+        g_pool.shutdown();
+    }
     for (auto *s : g_sinks) s->close_wait();
     g_sinks.clear();
 }
 
 // ------------------------------------------------------------------------------------------------
-// GPU context shared by the subcommands
+// GPU contexts shared by the subcommands: one per device, batches dealt round-robin
 // ------------------------------------------------------------------------------------------------
+// A *lane* is one (device, slot) pair.  Batch i runs on lane i % lanes: device i % G, so consecutive batches
+// (contiguous record ranges) sit on different GPUs, and slot (i / G) % NSLOT of that device.
 struct Gpu {
-    sk_ctx *ctx = nullptr;
-    uint64_t batch_bytes = 0, max_records = 0, out_cap = 0;
+    std::vector<sk_ctx *> ctxs;
+    sk_ctx *ctx = nullptr;  // ctxs[0]: sheet-independent queries
+    int G = 0;
     static const int NSLOT = 2;
-    uint8_t *out_h[NSLOT][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    uint64_t batch_bytes = 0, max_records = 0, out_cap = 0;
+    std::vector<uint8_t *> out_h[2];   // per lane and mate: pinned, grown on demand (ensure_out)
+    std::vector<uint64_t> out_hcap[2];
 
+    int lanes() const { return G * NSLOT; }
+    sk_ctx *c(int lane) const { return ctxs[(size_t)(lane % G)]; }
+    uint32_t slot(int lane) const { return (uint32_t)(lane / G); }
     void create(uint32_t max_samples, bool aux, int n_out) {
-        uint64_t mb = 32;
+        // 16 MiB batches: page-locking host memory is the slowest part of start-up (a few ms per MiB), and the
+        // kernels lose nothing at this size
+        uint64_t mb = 16;
         if (const char *e = getenv("SK_BATCH_MB")) mb = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
         batch_bytes = mb << 20;
         max_records = std::max<uint64_t>(batch_bytes / 64, 1024);
-        int dev = 0;
-        if (const char *e = getenv("SK_DEVICE")) dev = atoi(e);
+        const int ndev = sk_device_count();
+        std::vector<int> devs;
+        if (const char *e = getenv("SK_DEVICE")) {
+            devs.push_back(atoi(e));
+        } else {
+            int want = ndev;
+            if (const char *g = getenv("SK_GPUS")) want = std::max(1, std::min(ndev, atoi(g)));
+            for (int d = 0; d < want; d++) devs.push_back(d);
+        }
+        if (devs.empty()) devs.push_back(0);  // no device: sk_ctx_create reports it
         sk_limits lim;
         memset(&lim, 0, sizeof lim);
         lim.max_stream_bytes = batch_bytes;
@@ -305,38 +515,66 @@ struct Gpu {
         lim.n_slots = NSLOT;
         lim.max_samples = max_samples;
         lim.aux_streams = aux ? 1 : 0;
-        int rc = sk_ctx_create(dev, &lim, &ctx);
-        if (rc != SK_OK) {
-            fprintf(stderr, "seqkit_b200: cannot initialise the GPU path: %s\n", sk_last_error(nullptr));
-            finish(3);
+        for (int d : devs) {
+            sk_ctx *x = nullptr;
+            int rc = sk_ctx_create(d, &lim, &x);
+            if (rc != SK_OK) {
+                fprintf(stderr, "seqkit_b200: cannot initialise the GPU path: %s\n", sk_last_error(nullptr));
+                finish(3);
+            }
+            ctxs.push_back(x);
         }
+        ctx = ctxs[0];
+        G = (int)ctxs.size();
         out_cap = sk_out_capacity(ctx);
-        for (int s = 0; s < NSLOT; s++)
-            for (int m = 0; m < n_out; m++) out_h[s][m] = (uint8_t *)pinned(out_cap);
+        // the device-side capacity allows for 72 more bytes per record (add barcode); what the operators here
+        // usually write is about the batch itself, so the host mirrors start there and grow when they must
+        const uint64_t first = aux ? out_cap : std::min<uint64_t>(out_cap, batch_bytes + batch_bytes / 8 + (uint64_t)max_samples * 128 + (1u << 20));
+        for (int m = 0; m < n_out; m++)
+            for (int l = 0; l < lanes(); l++) {
+                out_h[m].push_back((uint8_t *)pinned(c(l), first));
+                out_hcap[m].push_back(first);
+            }
     }
-    void *pinned(uint64_t n) {
-        void *p = sk_pinned_alloc(ctx, n);
+    uint8_t *ensure_out(int m, int lane, uint64_t n) {
+        if (n > out_cap) refuse("output larger than the slot capacity");
+        if (n > out_hcap[m][(size_t)lane]) {
+            sk_pinned_free(c(lane), out_h[m][(size_t)lane]);
+            const uint64_t want = std::min<uint64_t>(out_cap, n + n / 4);
+            out_h[m][(size_t)lane] = (uint8_t *)pinned(c(lane), want);
+            out_hcap[m][(size_t)lane] = want;
+        }
+        return out_h[m][(size_t)lane];
+    }
+    void *pinned(sk_ctx *x, uint64_t n) {
+        void *p = sk_pinned_alloc(x, n);
         if (!p) {
             fprintf(stderr, "seqkit_b200: cannot allocate %llu bytes of pinned memory\n", (unsigned long long)n);
             finish(3);
         }
         return p;
     }
+    // The ring holds one buffer per batch in flight plus the one being filled: batch i is cut from ring[i % nb],
+    // and ring[i % nb] is next written (the tail of batch i + nb - 1) when batch i + nb - 1 is submitted, which
+    // happens only after batch i + nb - 1 - lanes() = i + G - 1 >= i has been completed and consumed.  Its length
+    // is a multiple of G, so that ring[j] only ever feeds device j % G and can live on that device's NUMA node.
     void init_stream(Stream &st, const std::string &path) {
         st.active = true;
         st.cap = batch_bytes;
-        st.buf[0] = (uint8_t *)pinned(batch_bytes);
-        st.buf[1] = (uint8_t *)pinned(batch_bytes);
-        st.in.open_path(path);
+        const int nb = G * (NSLOT + 1);
+        for (int j = 0; j < nb; j++) st.ring.push_back((uint8_t *)pinned(ctxs[(size_t)(j % G)], batch_bytes));
+        if (st.in.fd < 0) st.in.open_path(path);  // (an input is opened exactly once: it may be a FIFO)
     }
-    void ck(int rc, const char *what) {
+    void ck(sk_ctx *x, int rc, const char *what) {
         if (rc != SK_OK) {
             fflush(stdout);
-            fprintf(stderr, "seqkit_b200: %s failed (%d): %s\n", what, rc, sk_last_error(ctx));
+            fprintf(stderr, "seqkit_b200: %s failed (%d): %s\n", what, rc, sk_last_error(x));
             finish(3);
         }
     }
+    void ck(int rc, const char *what) { ck(ctx, rc, what); }
 };
+
 
 static void refuse_status(const sk_result &r, uint64_t base) {
     const unsigned long long rec = (unsigned long long)(base + r.err_record);
@@ -378,24 +616,33 @@ struct Batch {
     uint64_t first_record = 0;
 };
 
-static int run_stream_op(StreamOp op, const std::string &fastq_path, const std::string &aux_path, unsigned min_baseq) {
+static int run_stream_op(StreamOp op, const Input &fastq_in, const Input &aux_in, unsigned min_baseq) {
     Gpu g;
     g.create(0, op == OP_ADDBC, 1);
     Stream rd, bc;
-    g.init_stream(rd, fastq_path);
-    if (op == OP_ADDBC) g.init_stream(bc, aux_path);
+    rd.in = fastq_in;  // opened by the dispatcher, in the reference's order of errors
+    g.init_stream(rd, "");
+    if (op == OP_ADDBC) {
+        bc.in = aux_in;
+        g.init_stream(bc, "");
+    }
     std::vector<uint8_t> last_bc;  // last barcode record: reused once the barcode file is exhausted (fasta_add_barcode.rs:20-27)
     bool first = true, bc_fastx = false;
-    Batch batches[Gpu::NSLOT];
+    const int NL = g.lanes();
+    std::vector<Batch> batches((size_t)NL);
     uint64_t bi = 0;
 
-    auto launch = [&](int slot, uint64_t rec_limit) {
-        if (op == OP_TRIM) g.ck(sk_trim_by_quality(g.ctx, slot, min_baseq, rec_limit), "sk_trim_by_quality");
-        else if (op == OP_MASK) g.ck(sk_mask_by_quality(g.ctx, slot, min_baseq, rec_limit), "sk_mask_by_quality");
-        else g.ck(sk_add_barcode(g.ctx, slot, rec_limit), "sk_add_barcode");
+    auto launch = [&](int lane, uint64_t rec_limit) {
+        sk_ctx *x = g.c(lane);
+        const uint32_t slot = g.slot(lane);
+        if (op == OP_TRIM) g.ck(x, sk_trim_by_quality(x, slot, min_baseq, rec_limit), "sk_trim_by_quality");
+        else if (op == OP_MASK) g.ck(x, sk_mask_by_quality(x, slot, min_baseq, rec_limit), "sk_mask_by_quality");
+        else g.ck(x, sk_add_barcode(x, slot, rec_limit), "sk_add_barcode");
     };
-    auto submit = [&](int slot) -> bool {
-        Batch &B = batches[slot];
+    auto submit = [&](int lane) -> bool {
+        sk_ctx *x = g.c(lane);
+        const uint32_t slot = g.slot(lane);
+        Batch &B = batches[(size_t)lane];
         B = Batch();
         rd.top_up();
         if (first) {
@@ -408,10 +655,10 @@ static int run_stream_op(StreamOp op, const std::string &fastq_path, const std::
                     x.lines_mod = 0;
                     x.top_up();
                 };
-                if (rd.fill && rd.buf[rd.cur][0] == '>') reframe(rd);
+                if (rd.fill && rd.buf()[0] == '>') reframe(rd);
                 bc.top_up();
-                bc_fastx = bc.fill && (bc.buf[bc.cur][0] == '@' || bc.buf[bc.cur][0] == '>');
-                if (bc.fill && bc.buf[bc.cur][0] == '>') reframe(bc);
+                bc_fastx = bc.fill && (bc.buf()[0] == '@' || bc.buf()[0] == '>');
+                if (bc.fill && bc.buf()[0] == '>') reframe(bc);
             }
         }
         size_t n = std::min<size_t>(rd.avail(), g.max_records);
@@ -437,49 +684,54 @@ static int run_stream_op(StreamOp op, const std::string &fastq_path, const std::
         B.n = n;
         B.first_record = rd.records_done;
         B.bytes[SK_IN_R1] = rd.bytes_for(n);
-        B.src[SK_IN_R1] = rd.buf[rd.cur];
-        g.ck(sk_upload(g.ctx, slot, SK_IN_R1, B.src[SK_IN_R1], B.bytes[SK_IN_R1]), "sk_upload");
+        B.src[SK_IN_R1] = rd.buf();
+        g.ck(x, sk_upload(x, slot, SK_IN_R1, B.src[SK_IN_R1], B.bytes[SK_IN_R1]), "sk_upload");
         if (op == OP_ADDBC) {
-            B.src[SK_IN_AUX1] = bc.buf[bc.cur];
+            B.src[SK_IN_AUX1] = bc.buf();
             if (bc_reuse) {
-                memcpy(bc.buf[bc.cur], last_bc.data(), last_bc.size());
+                memcpy(bc.buf(), last_bc.data(), last_bc.size());
                 B.bytes[SK_IN_AUX1] = last_bc.size();
-                bc.cur ^= 1;  // the copy stays untouched until this slot is reused
             } else if (nb) {
                 B.bytes[SK_IN_AUX1] = bc.bytes_for(nb);
                 const size_t s0 = nb >= 2 ? bc.bytes_for(nb - 1) : 0;
-                last_bc.assign(bc.buf[bc.cur] + s0, bc.buf[bc.cur] + B.bytes[SK_IN_AUX1]);
+                last_bc.assign(bc.buf() + s0, bc.buf() + B.bytes[SK_IN_AUX1]);
             }
-            g.ck(sk_upload(g.ctx, slot, SK_IN_AUX1, B.src[SK_IN_AUX1], B.bytes[SK_IN_AUX1]), "sk_upload");
+            g.ck(x, sk_upload(x, slot, SK_IN_AUX1, B.src[SK_IN_AUX1], B.bytes[SK_IN_AUX1]), "sk_upload");
+            // the barcode ring moves in step with the read ring: a buffer stays untouched until its batch is done
             if (nb) bc.consume(nb, B.bytes[SK_IN_AUX1]);
+            else bc.park();
         }
-        launch(slot, 0);
+        launch(lane, 0);
         rd.consume(n, B.bytes[SK_IN_R1]);
         return true;
     };
-    auto fetch_out = [&](int slot, uint64_t n) {
-        if (n > g.out_cap) refuse("output larger than the slot capacity");
-        if (n) g.ck(sk_download_out(g.ctx, slot, 0, g.out_h[slot][0], n), "sk_download_out");
-        g.ck(sk_wait(g.ctx, slot, nullptr), "sk_wait");
-        write_all(1, g.out_h[slot][0], n);
+    auto fetch_out = [&](int lane, uint64_t n) {
+        sk_ctx *x = g.c(lane);
+        const uint32_t slot = g.slot(lane);
+        uint8_t *h = g.ensure_out(0, lane, n);
+        if (n) g.ck(x, sk_download_out(x, slot, 0, h, n), "sk_download_out");
+        g.ck(x, sk_wait(x, slot, nullptr), "sk_wait");
+        write_all(1, h, n);
     };
-    auto complete = [&](int slot) {
-        Batch &B = batches[slot];
+    auto complete = [&](int lane) {
+        sk_ctx *x = g.c(lane);
+        const uint32_t slot = g.slot(lane);
+        Batch &B = batches[(size_t)lane];
         sk_result r;
-        g.ck(sk_wait(g.ctx, slot, &r), "sk_wait");
+        g.ck(x, sk_wait(x, slot, &r), "sk_wait");
         refuse_status(r, B.first_record);
         if (r.status == SK_DATA_OK) {
-            fetch_out(slot, r.out_bytes[0]);
+            fetch_out(lane, r.out_bytes[0]);
             B.live = false;
             return;
         }
         // A record the reference stops at: everything before it has already been printed (replay).
         uint64_t off = 0;
         if (r.err_record) {
-            launch(slot, r.err_record);
+            launch(lane, r.err_record);
             sk_result rep;
-            g.ck(sk_wait(g.ctx, slot, &rep), "sk_wait");
-            fetch_out(slot, rep.out_bytes[0]);
+            g.ck(x, sk_wait(x, slot, &rep), "sk_wait");
+            fetch_out(lane, rep.out_bytes[0]);
             off = rep.consumed[SK_IN_R1];
         }
         const uint8_t *d = B.src[SK_IN_R1];
@@ -521,12 +773,20 @@ static int run_stream_op(StreamOp op, const std::string &fastq_path, const std::
         }
     };
 
-    bool more = submit(0);
-    while (more) {
-        const int slot = (int)(bi & 1), nxt = slot ^ 1;
-        more = submit(nxt);
-        complete(slot);
+    // Batches are submitted up to NL ahead and completed strictly in order: batch i on lane i % NL.
+    uint64_t submitted = 0;
+    bool more = true;
+    while (more && submitted < (uint64_t)NL) {
+        more = submit((int)(submitted % (uint64_t)NL));
+        if (more) submitted++;
+    }
+    while (bi < submitted) {
+        complete((int)(bi % (uint64_t)NL));
         bi++;
+        if (more) {
+            more = submit((int)(submitted % (uint64_t)NL));
+            if (more) submitted++;
+        }
     }
     return 0;
 }
@@ -536,7 +796,7 @@ static int run_stream_op(StreamOp op, const std::string &fastq_path, const std::
 // ------------------------------------------------------------------------------------------------
 struct Sample {
     std::string name, barcode;
-    GzipSink out[2];
+    Sink *out[2] = {nullptr, nullptr};
     uint64_t total_reads = 0;
 };
 
@@ -603,7 +863,9 @@ static int run_demultiplex(int argc, char **argv) {
     }
     const bool paired = pos.size() == 3 && !pos[2].empty();
 
-    // Readers are opened before the sheet is read (:41-55), so "Cannot open file" comes first.
+    // Readers are opened before the sheet is read (:41-55), so "Cannot open file" comes first -- each input
+    // exactly once (a FIFO or process substitution cannot be opened twice); the pinned rings come with the
+    // contexts below.
     Gpu g;
     Stream st[SK_N_INPUTS];
     Input sheet_in;
@@ -613,12 +875,7 @@ static int run_demultiplex(int argc, char **argv) {
     if (paired) to_open.push_back({SK_IN_R2, pos[2]});
     if (!index1.empty()) to_open.push_back({SK_IN_AUX1, index1});
     if (!index2.empty()) to_open.push_back({SK_IN_AUX2, index2});
-    for (auto &o : to_open) {  // check readability up front; the pinned buffers come with the context below
-        if (o.second == "-") continue;
-        int f = open(o.second.c_str(), O_RDONLY);
-        if (f < 0) fatal("Cannot open file %s for reading.", o.second.c_str());
-        close(f);
-    }
+    for (auto &o : to_open) st[o.first].in.open_path(o.second);
 
     fputs("Reading sample sheet...\n", stderr);  // :58
     sheet_in.open_path(pos[0]);
@@ -632,6 +889,8 @@ static int run_demultiplex(int argc, char **argv) {
         if (c >= 0x80) refuse("non-ASCII bytes in the sample sheet");
     std::vector<Sample *> samples;
     size_t barcode_len = 0;
+    // SK_GZIP=child: one `gzip -c` (--parallel: `pigz -c`) child per output file, as the reference does it
+    const bool child_gzip = getenv("SK_GZIP") && strcmp(getenv("SK_GZIP"), "child") == 0;
     for (size_t p = 0; p < sheet.size();) {  // :63-95
         const uint8_t *nl = (const uint8_t *)memchr(sheet.data() + p, '\n', sheet.size() - p);
         const size_t end = nl ? (size_t)(nl - sheet.data()) + 1 : sheet.size();
@@ -659,11 +918,21 @@ static int run_demultiplex(int argc, char **argv) {
         s->barcode.assign((const char *)c1, bc_n);
         samples.push_back(s);
         if (dry_run == 0) {  // outputs are created while the sheet is read (:77-87)
+            auto make_sink = [&](const std::string &path) -> Sink * {
+                if (child_gzip) {
+                    ChildSink *k = new ChildSink();
+                    k->open_path(path, parallel);
+                    return k;
+                }
+                DeflateSink *k = new DeflateSink();
+                k->open_path(path);
+                return k;
+            };
             if (paired) {
-                s->out[0].open_path(name + "_1.fq.gz", parallel);
-                s->out[1].open_path(name + "_2.fq.gz", parallel);
+                s->out[0] = make_sink(name + "_1.fq.gz");
+                s->out[1] = make_sink(name + "_2.fq.gz");
             } else {
-                s->out[0].open_path(name + ".fq.gz", parallel);
+                s->out[0] = make_sink(name + ".fq.gz");
             }
         }
     }
@@ -676,6 +945,7 @@ static int run_demultiplex(int argc, char **argv) {
     const uint32_t S = (uint32_t)samples.size();
     if (S == 0) refuse("empty sample sheet");
     const bool use_aux = !index1.empty() || !index2.empty();
+    Phase *ph_init = new Phase(0);
     g.create(S, use_aux, paired ? 2 : 1);
     for (auto &o : to_open) g.init_stream(st[o.first], o.second);
     {
@@ -686,13 +956,22 @@ static int run_demultiplex(int argc, char **argv) {
         g.ck(rc, "sk_set_sheet");
     }
     const uint32_t use_index = (index1.empty() ? 0u : 1u) | (index2.empty() ? 0u : 2u);
+    const int NL = g.lanes();
+    // Per-sample output: one contiguous slice per sample, mate and batch from the device-side compaction
+    // (sk_demux_compact).  Sheets beyond its limit (4096 samples) fall back to the per-record slice tables.
+    const bool compact = S <= 4096 && !getenv("SK_NO_COMPACT");
     const uint32_t max_chunks = sk_max_chunks(g.ctx);
-    sk_chunk_row *rows_h[Gpu::NSLOT][2];
-    sk_group *groups_h[Gpu::NSLOT][2];
-    for (int s = 0; s < Gpu::NSLOT; s++)
-        for (int m = 0; m < (paired ? 2 : 1); m++) {
-            rows_h[s][m] = (sk_chunk_row *)g.pinned((uint64_t)max_chunks * sizeof(sk_chunk_row));
-            groups_h[s][m] = (sk_group *)g.pinned(g.max_records * sizeof(sk_group));
+    std::vector<sk_slice *> slices_h[2];
+    std::vector<sk_chunk_row *> rows_h[2];
+    std::vector<sk_group *> groups_h[2];
+    for (int m = 0; m < (paired ? 2 : 1); m++)
+        for (int l = 0; l < NL; l++) {
+            if (compact) {
+                slices_h[m].push_back((sk_slice *)g.pinned(g.c(l), (uint64_t)(S + 1) * sizeof(sk_slice)));
+            } else {
+                rows_h[m].push_back((sk_chunk_row *)g.pinned(g.c(l), (uint64_t)max_chunks * sizeof(sk_chunk_row)));
+                groups_h[m].push_back((sk_group *)g.pinned(g.c(l), g.max_records * sizeof(sk_group)));
+            }
         }
     std::vector<uint64_t> counts_h(S + 2);
     std::vector<sk_event> events;
@@ -700,21 +979,26 @@ static int run_demultiplex(int argc, char **argv) {
     std::unordered_map<std::string, uint64_t> extra;  // dry run: barcodes matching no sample (:190-194)
     std::vector<std::string> extra_order;
     uint64_t total_reads = 0, identified_reads = 0;
-    Batch batches[Gpu::NSLOT];
+    std::vector<Batch> batches((size_t)NL);
     uint64_t bi = 0;
     unsigned n_threads = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
 
-    auto call = [&](int slot, uint64_t rec_limit) {
+    auto call = [&](int lane, uint64_t rec_limit) {
+        sk_ctx *x = g.c(lane);
         sk_demux_opts o;
         memset(&o, 0, sizeof o);
         o.fused_trim_min_baseq = fused_trim;
         o.use_index = use_index;
         o.rec_limit = rec_limit;
         o.no_output = dry_run ? 1 : 0;
-        g.ck(sk_demultiplex(g.ctx, slot, &o), "sk_demultiplex");
+        g.ck(x, sk_demultiplex(x, g.slot(lane), &o), "sk_demultiplex");
+        if (compact && !dry_run) g.ck(x, sk_demux_compact(x, g.slot(lane)), "sk_demux_compact");
     };
-    auto submit = [&](int slot) -> bool {
-        Batch &B = batches[slot];
+    auto submit = [&](int lane) -> bool {
+        Phase ph(1);
+        sk_ctx *x = g.c(lane);
+        const uint32_t slot = g.slot(lane);
+        Batch &B = batches[(size_t)lane];
         B = Batch();
         if (dry_run && st[SK_IN_R1].records_done >= dry_run) return false;  // :248
         for (auto &o : to_open) st[o.first].top_up();
@@ -725,10 +1009,10 @@ static int run_demultiplex(int argc, char **argv) {
         }
         for (auto &o : to_open) {
             if (o.first == SK_IN_R1) continue;
-            Stream &x = st[o.first];
-            if (x.avail() < n) {
-                if (x.in.eof) refuse("mate / index files hold fewer records than <fastq_1>");
-                n = x.avail();
+            Stream &other = st[o.first];
+            if (other.avail() < n) {
+                if (other.in.eof) refuse("mate / index files hold fewer records than <fastq_1>");
+                n = other.avail();
                 if (n == 0) refuse("a record does not fit in one batch; raise SK_BATCH_MB");
             }
         }
@@ -737,13 +1021,13 @@ static int run_demultiplex(int argc, char **argv) {
         B.n = n;
         B.first_record = st[SK_IN_R1].records_done;
         for (auto &o : to_open) {
-            Stream &x = st[o.first];
-            B.bytes[o.first] = x.bytes_for(n);
-            B.src[o.first] = x.buf[x.cur];
-            g.ck(sk_upload(g.ctx, slot, o.first, B.src[o.first], B.bytes[o.first]), "sk_upload");
+            Stream &xs = st[o.first];
+            B.bytes[o.first] = xs.bytes_for(n);
+            B.src[o.first] = xs.buf();
+            g.ck(x, sk_upload(x, slot, o.first, B.src[o.first], B.bytes[o.first]), "sk_upload");
         }
-        if (!paired) g.ck(sk_set_input_len(g.ctx, slot, SK_IN_R2, 0), "sk_set_input_len");
-        call(slot, 0);
+        if (!paired) g.ck(x, sk_set_input_len(x, slot, SK_IN_R2, 0), "sk_set_input_len");
+        call(lane, 0);
         for (auto &o : to_open) st[o.first].consume(n, B.bytes[o.first]);
         return true;
     };
@@ -765,16 +1049,17 @@ static int run_demultiplex(int argc, char **argv) {
         return bc;
     };
     // processes the results of a batch that ran with `r` (possibly a replay limited to the records before an error)
-    auto drain = [&](int slot, const sk_result &r) {
-        Batch &B = batches[slot];
-        g.ck(sk_download_counts(g.ctx, slot, counts_h.data()), "sk_download_counts");
-        for (uint32_t s = 0; s < S; s++) samples[s]->total_reads += counts_h[s];
-        total_reads += counts_h[S];
-        identified_reads += counts_h[S + 1];
+    auto drain = [&](int lane, const sk_result &r) {
+        Phase ph(3);
+        sk_ctx *x = g.c(lane);
+        const uint32_t slot = g.slot(lane);
+        Batch &B = batches[(size_t)lane];
+        // counters stay on the device: added to the context's run totals, merged over the GPUs at the end (:169,177-178)
+        g.ck(x, sk_counts_accumulate(x, slot), "sk_counts_accumulate");
         // WARNING lines in record order (:184-188)
         if (r.flags & SK_FLAG_EVENTS_OVERFLOW) refuse("too many ambiguous reads in one batch");
         events.resize(std::max<uint32_t>(r.n_events, 1));
-        const int ne = sk_download_events(g.ctx, slot, events.data(), r.n_events);
+        const int ne = sk_download_events(x, slot, events.data(), r.n_events);
         for (int k = 0; k < ne; k++) {
             const sk_event &e = events[k];
             std::string bc = use_index ? index_barcode(B, e.bc_off, e.bc_off2)
@@ -788,7 +1073,7 @@ static int run_demultiplex(int argc, char **argv) {
         if (dry_run) {
             // tally the barcodes of reads whose best match is worse than one mismatch (:190-194)
             assign_h.resize(std::max<uint64_t>(r.n_records, 1));
-            g.ck(sk_download_assign(g.ctx, slot, assign_h.data(), r.n_records), "sk_download_assign");
+            g.ck(x, sk_download_assign(x, slot, assign_h.data(), r.n_records), "sk_download_assign");
             const uint8_t *d = B.src[SK_IN_R1];
             size_t p = 0;
             std::vector<size_t> ipos(2, 0);
@@ -838,17 +1123,32 @@ static int run_demultiplex(int argc, char **argv) {
             }
             return;
         }
-        // per-sample slices -> gzip children, in (batch, chunk) order; samples are spread over writer threads
+        // per-sample output -> the samples' sinks, in batch order
         const int nm = paired ? 2 : 1;
+        if (compact) {
+            // one contiguous slice per sample and mate (sk_compact.cu): S appends per mate, not one per record
+            for (int m = 0; m < nm; m++) {
+                uint8_t *h = g.ensure_out(m, lane, r.out_extent[m]);
+                if (r.out_extent[m]) g.ck(x, sk_download_compact(x, slot, (uint32_t)m, h, r.out_extent[m]), "sk_download_compact");
+                g.ck(x, sk_download_slices(x, slot, (uint32_t)m, slices_h[m][(size_t)lane]), "sk_download_slices");
+            }
+            g.ck(x, sk_wait(x, slot, nullptr), "sk_wait");
+            for (int m = 0; m < nm; m++) {
+                const sk_slice *sl = slices_h[m][(size_t)lane];
+                const uint8_t *base = g.out_h[m][(size_t)lane];
+                for (uint32_t s = 0; s < S; s++)
+                    if (sl[s].len) samples[s]->out[m]->append(base + sl[s].offset, (size_t)sl[s].len);
+            }
+            return;
+        }
         for (int m = 0; m < nm; m++) {
-            if (r.out_extent[m] > g.out_cap) refuse("output larger than the slot capacity");
-            if (r.out_extent[m]) g.ck(sk_download_out(g.ctx, slot, m, g.out_h[slot][m], r.out_extent[m]), "sk_download_out");
-            g.ck(sk_download_demux_tables(g.ctx, slot, m, rows_h[slot][m], groups_h[slot][m], r.n_records),
+            uint8_t *h = g.ensure_out(m, lane, r.out_extent[m]);
+            if (r.out_extent[m]) g.ck(x, sk_download_out(x, slot, (uint32_t)m, h, r.out_extent[m]), "sk_download_out");
+            g.ck(x, sk_download_demux_tables(x, slot, (uint32_t)m, rows_h[m][(size_t)lane], groups_h[m][(size_t)lane], r.n_records),
                  "sk_download_demux_tables");
         }
-        g.ck(sk_wait(g.ctx, slot, nullptr), "sk_wait");
-        // Bucket the groups by sample (one pass over the chunk rows), then let the writer threads append
-        // each sample's groups, in chunk order, to its gzip child.
+        g.ck(x, sk_wait(x, slot, nullptr), "sk_wait");
+        // Bucket the groups by sample (one pass over the chunk rows), then append each sample's groups in chunk order.
         struct Piece {
             uint64_t off;
             uint32_t len;
@@ -857,8 +1157,8 @@ static int run_demultiplex(int argc, char **argv) {
         std::vector<Piece> pieces;
         for (int m = 0; m < nm; m++) {
             const uint32_t nc = r.n_chunks[m];
-            const sk_chunk_row *rows = rows_h[slot][m];
-            const sk_group *groups = groups_h[slot][m];
+            const sk_chunk_row *rows = rows_h[m][(size_t)lane];
+            const sk_group *groups = groups_h[m][(size_t)lane];
             std::fill(cnt.begin(), cnt.end(), 0u);
             for (uint32_t c = 0; c < nc; c++)
                 for (uint32_t k = 0; k < rows[c].n_groups; k++) cnt[groups[rows[c].first_group + k].sample + 1]++;
@@ -881,10 +1181,10 @@ static int run_demultiplex(int argc, char **argv) {
                     if (s >= S) break;
                     tmp.clear();
                     for (uint32_t k = cnt[s]; k < cnt[s + 1]; k++) {
-                        const uint8_t *src = g.out_h[slot][m] + pieces[k].off;
+                        const uint8_t *src = g.out_h[m][(size_t)lane] + pieces[k].off;
                         tmp.insert(tmp.end(), src, src + pieces[k].len);
                     }
-                    if (!tmp.empty()) write_all(samples[s]->out[m].fd, tmp.data(), tmp.size());
+                    if (!tmp.empty()) samples[s]->out[m]->append(tmp.data(), tmp.size());
                 }
             };
             std::vector<std::thread> pool;
@@ -894,23 +1194,36 @@ static int run_demultiplex(int argc, char **argv) {
             for (auto &t : pool) t.join();
         }
     };
-    auto complete = [&](int slot) {
-        Batch &B = batches[slot];
+    // Run totals: one grouped NCCL all-reduce over the GPUs' device-side counters, then a single download.
+    auto finish_counts = [&]() {
+        g.ck(sk_allreduce_totals(g.ctxs.data(), g.G), "sk_allreduce_totals");
+        g.ck(sk_download_totals(g.ctx, counts_h.data()), "sk_download_totals");
+        for (uint32_t s = 0; s < S; s++) samples[s]->total_reads = counts_h[s];
+        total_reads = counts_h[S];
+        identified_reads = counts_h[S + 1];
+    };
+    auto complete = [&](int lane) {
+        sk_ctx *x = g.c(lane);
+        const uint32_t slot = g.slot(lane);
+        Batch &B = batches[(size_t)lane];
         sk_result r;
-        g.ck(sk_wait(g.ctx, slot, &r), "sk_wait");
+        {
+            Phase ph(2);
+            g.ck(x, sk_wait(x, slot, &r), "sk_wait");
+        }
         refuse_status(r, B.first_record);
         if (r.flags & SK_FLAG_MATE_COUNT) refuse("mate / index files hold fewer records than <fastq_1>");
         if (r.status == SK_DATA_OK) {
-            drain(slot, r);
+            drain(lane, r);
             B.live = false;
             return;
         }
         sk_result rep;
         memset(&rep, 0, sizeof rep);
         if (r.err_record) {
-            call(slot, r.err_record);
-            g.ck(sk_wait(g.ctx, slot, &rep), "sk_wait");
-            drain(slot, rep);
+            call(lane, r.err_record);
+            g.ck(x, sk_wait(x, slot, &rep), "sk_wait");
+            drain(lane, rep);
         }
         const uint8_t *d = B.src[SK_IN_R1];
         const size_t nbytes = B.bytes[SK_IN_R1];
@@ -949,13 +1262,23 @@ static int run_demultiplex(int argc, char **argv) {
         }
     };
 
-    bool more = submit(0);
-    while (more) {
-        const int slot = (int)(bi & 1), nxt = slot ^ 1;
-        more = submit(nxt);
-        complete(slot);
-        bi++;
+    delete ph_init;
+    // Batches are submitted up to NL ahead (round-robin over the GPUs) and completed strictly in order.
+    uint64_t submitted = 0;
+    bool more = true;
+    while (more && submitted < (uint64_t)NL) {
+        more = submit((int)(submitted % (uint64_t)NL));
+        if (more) submitted++;
     }
+    while (bi < submitted) {
+        complete((int)(bi % (uint64_t)NL));
+        bi++;
+        if (more) {
+            more = submit((int)(submitted % (uint64_t)NL));
+            if (more) submitted++;
+        }
+    }
+    finish_counts();
 
     if (dry_run) {  // :251-261
         fflush(stdout);
@@ -992,33 +1315,23 @@ int main(int argc, char **argv) {
     if (argc >= 4 && is(1, "trim") && is(2, "by") && is(3, "quality")) {
         if (argc != 6 || argv[4][0] == '\0') invalid_args(USAGE_TRIM);
         unsigned q;
-        Input probe;  // FileReader::new precedes the parse of <min_baseq> (fasta_trim_by_quality.rs:12-13)
-        if (strcmp(argv[4], "-") != 0) {
-            int f = open(argv[4], O_RDONLY);
-            if (f < 0) fatal("Cannot open file %s for reading.", argv[4]);
-            close(f);
-        }
+        Input in, none;  // FileReader::new precedes the parse of <min_baseq> (fasta_trim_by_quality.rs:12-13)
+        in.open_path(argv[4]);
         if (!parse_u8(argv[5], &q)) panic101("min_baseq parse");
-        rc = run_stream_op(OP_TRIM, argv[4], "", q);
+        rc = run_stream_op(OP_TRIM, in, none, q);
     } else if (argc >= 4 && is(1, "mask") && is(2, "by") && is(3, "quality")) {
         if (argc != 6) invalid_args(USAGE_MASK);
         unsigned q;
-        if (strcmp(argv[4], "-") != 0) {
-            int f = open(argv[4], O_RDONLY);
-            if (f < 0) fatal("Cannot open file %s for reading.", argv[4]);
-            close(f);
-        }
+        Input in, none;
+        in.open_path(argv[4]);
         if (!parse_u8(argv[5], &q)) panic101("min_baseq parse");
-        rc = run_stream_op(OP_MASK, argv[4], "", q);
+        rc = run_stream_op(OP_MASK, in, none, q);
     } else if (argc >= 3 && is(1, "add") && is(2, "barcode")) {
         if (argc != 5) invalid_args(USAGE_ADDBC);
-        for (int k = 3; k <= 4; k++)
-            if (strcmp(argv[k], "-") != 0) {
-                int f = open(argv[k], O_RDONLY);
-                if (f < 0) fatal("Cannot open file %s for reading.", argv[k]);
-                close(f);
-            }
-        rc = run_stream_op(OP_ADDBC, argv[3], argv[4], 0);
+        Input in, bcin;
+        in.open_path(argv[3]);
+        bcin.open_path(argv[4]);
+        rc = run_stream_op(OP_ADDBC, in, bcin, 0);
     } else if (argc >= 2 && is(1, "demultiplex")) {
         rc = run_demultiplex(argc, argv);
     } else {

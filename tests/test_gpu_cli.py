@@ -203,3 +203,67 @@ def test_fused_trim_extension_equals_shell_composition(oracle_bin, tmp_path):
     got = run(FASTA, ["demultiplex", "--trim-by-quality=20", "sheet.tsv", "r1.fq", "r2.fq"], str(e))
     same(got, want)
     assert gz_files(str(e)) == want_files
+
+
+def test_errors_in_early_and_middle_batches(oracle_bin, tmp_path):
+    """A failing record, an ambiguous read and a dry run whose interesting record is the FIRST record of a
+    middle batch of a multi-batch run (SK_BATCH_MB=1): the header text quoted in the messages and the dry-run
+    walk come from the batch's own pinned buffer, which later batches must not have touched; and a .gz input
+    that fails in its first batch must still exit (no gunzip child left blocked on a full pipe)."""
+    sheet, bcs = G.make_sheet(5, 12, 8, umi=0, min_dist=1)
+    r1, r2 = G.clean_pairs(77, 16000, bcs, p_sub=0.0, p_n=0.0, p_random=0.02, read_len=(100, 150))
+    assert len(r1) > 4 << 20
+    recs = r1.split(b"\n")
+    # byte offset of the first record that starts beyond 2 MiB: with 1 MiB batches it sits in a middle batch
+    pos, k = 0, 0
+    while pos < (2 << 20) + 1000:
+        pos += sum(len(x) + 1 for x in recs[4 * k:4 * k + 4])
+        k += 1
+    head, tail = b"\n".join(recs[:4 * k]) + b"\n", b"\n".join(recs[4 * k:])
+    env = {"SK_BATCH_MB": "1"}
+    bad = head + b"@nobc 1:N:0:1\nACGT\n+\nIIII\n" + tail
+    both(oracle_bin, tmp_path, ["demultiplex", "sheet.tsv", "r1.fq"], {"sheet.tsv": sheet, "r1.fq": bad}, env=env, ctx="no BC, middle")
+    bad = head + b"Xnot a header BC:" + bcs[0] + b"\nACGT\n+\nIIII\n" + tail
+    both(oracle_bin, tmp_path, ["demultiplex", "sheet.tsv", "r1.fq"], {"sheet.tsv": sheet, "r1.fq": bad}, env=env, ctx="bad header, middle")
+    bad = head + b"@short BC:ACG\nACGT\n+\nIIII\n" + tail
+    both(oracle_bin, tmp_path, ["demultiplex", "sheet.tsv", "r1.fq"], {"sheet.tsv": sheet, "r1.fq": bad}, env=env, ctx="barcode length, middle")
+    # ambiguous reads (two sheet rows one mismatch apart on either side of the observed barcode)
+    amb_sheet = b"A\tACGTACGT\nB\tACGTACGA\n" + sheet
+    amb = head + b"@amb 1:N:0:1 BC:ACGTACGC\nACGT\n+\nIIII\n" + tail
+    both(oracle_bin, tmp_path, ["demultiplex", "sheet.tsv", "r1.fq"], {"sheet.tsv": amb_sheet, "r1.fq": amb}, env=env, ctx="ambiguous, middle")
+    # dry run that covers three batches and a bit
+    both(oracle_bin, tmp_path, ["demultiplex", "--dry-run=%d" % (k + 50), "sheet.tsv", "r1.fq"],
+         {"sheet.tsv": G.make_sheet(4, 120, 8)[0], "r1.fq": r1}, env=env, ctx="dry run, middle")
+    # .gz input, failure in the very first batch of a multi-batch file
+    bad = b"@nobc 1:N:0:1\nACGT\n+\nIIII\n" + r1
+    both(oracle_bin, tmp_path, ["demultiplex", "sheet.tsv", "r1.fq.gz"], {"sheet.tsv": sheet, "r1.fq.gz": bad}, env=env, ctx="gz, first batch")
+    for op in ("trim", "mask"):
+        bad = G.clean_fastq(3, 10) + b"Xbroken\nACGT\n+\nIIII\n" + G.clean_fastq(11, 20000, qual_style="mix")
+        both(oracle_bin, tmp_path, [op, "by", "quality", "in.fq.gz", "20"], {"in.fq.gz": bad}, env=env, ctx=(op, "gz early"))
+
+
+def test_gzip_children_and_per_record_tables_give_the_same_files(oracle_bin, tmp_path):
+    """SK_GZIP=child (one `gzip -c` child per file, the reference's GzipWriter) and SK_NO_COMPACT=1 (per-record
+    slice tables instead of the device-side compaction) are the same drop-in: decompressed files identical."""
+    sheet, bcs = G.make_sheet(6, 24, 20, umi=8, dual=True)
+    r1, r2 = G.clean_pairs(78, 5000, bcs, p_sub=0.03, p_random=0.05)
+    files = {"sheet.tsv": sheet, "r1.fq": r1, "r2.fq": r2}
+    for env in ({"SK_GZIP": "child"}, {"SK_NO_COMPACT": "1"}, {"SK_GZIP": "child", "SK_NO_COMPACT": "1", "SK_BATCH_MB": "1"},
+                {"SK_GZIP_THREADS": "3", "SK_BATCH_MB": "1"}):
+        both(oracle_bin, tmp_path, ["demultiplex", "sheet.tsv", "r1.fq", "r2.fq"], files, env=env, ctx=env)
+
+
+def test_all_visible_gpus_give_the_single_gpu_bytes(oracle_bin, tmp_path):
+    """Batches are dealt round-robin to every visible GPU and consumed in batch order: the output does not
+    depend on the number of GPUs (one GPU visible: the same code path with one lane group)."""
+    sheet, bcs = G.make_sheet(7, 48, 20, umi=8, dual=True)
+    r1, r2 = G.clean_pairs(79, 12000, bcs, p_sub=0.03, p_random=0.05)
+    files = {"sheet.tsv": sheet, "r1.fq": r1, "r2.fq": r2}
+    res = []
+    for env in ({"SK_BATCH_MB": "1"}, {"SK_BATCH_MB": "1", "SK_GPUS": "1"}, {"SK_BATCH_MB": "1", "SK_DEVICE": "0"}):
+        res.append(both(oracle_bin, tmp_path, ["demultiplex", "--trim-by-quality=20", "sheet.tsv", "r1.fq", "r2.fq"]
+                        if False else ["demultiplex", "sheet.tsv", "r1.fq", "r2.fq"], files, env=env, ctx=env))
+    assert res[0][1] == res[1][1] == res[2][1]
+    data = G.clean_fastq(21, 30000, qual_style="mix")
+    for op in ("trim", "mask"):
+        both(oracle_bin, tmp_path, [op, "by", "quality", "in.fq", "20"], {"in.fq": data}, env={"SK_BATCH_MB": "1"}, ctx=op)

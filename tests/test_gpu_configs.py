@@ -164,3 +164,54 @@ def test_compaction_equals_the_slice_tables():
             assert not eng.last_result.reserved & 8
             assert a["files"] == b["files"] and a["counts"] == b["counts"] and a["stderr"] == b["stderr"]
         eng.compact = True
+
+
+def test_host_generator_is_the_device_generator():
+    """oracle/synth_host.c (input of `bench.py --impl reference`, which must not load the product's library)
+    yields the bytes of the device generator for the same (seed, pair range, mate, sheet)."""
+    import bench
+    from oracle import pyoracle as O
+    from seqkit_b200 import Engine
+    bcs = bench.make_sheet()
+    with Engine(max_stream_bytes=32 << 20, max_records=1 << 16, max_samples=bench.N_SAMPLES, aux_streams=False) as eng:
+        eng.set_sheet(bcs)
+        for seed, first, n, mate, with_bc, prof in ((5, 0, 3000, 1, True, 0), (5, 123456789, 2000, 2, True, 0),
+                                                    (1, 7, 2500, 1, False, 0), (9, 1 << 40, 1000, 2, True, 1)):
+            nb = eng.synth(0, n, seed=seed, first_pair=first, mate=mate, with_bc=with_bc, qual_profile=prof)
+            dev = eng.download_in(0, nb)
+            host = O.synth_fastq(n, seed=seed, first_pair=first, mate=mate, barcodes=bcs if with_bc else None, qual_profile=prof)
+            assert dev == host, (seed, first, mate, with_bc)
+    r1, r2 = bench.host_pairs(bcs, 5000, first_pair=11, seed=5, threads=3)
+    assert r1 == O.synth_fastq(5000, seed=5, first_pair=11, mate=1, barcodes=bcs)
+    assert r2 == O.synth_fastq(5000, seed=5, first_pair=11, mate=2, barcodes=bcs)
+
+
+def test_run_totals_accumulate_on_the_device():
+    """sk_counts_accumulate / sk_download_totals: the counters of finished batches add up on the device (what the
+    `fasta` binary merges over its GPUs with one grouped NCCL all-reduce; one context: nothing to merge)."""
+    import numpy as np
+    import bench
+    from seqkit_b200 import Engine, _lib as L
+    S = 96
+    sheet, bcs = G.make_sheet(3, S, 8)
+    with Engine(max_stream_bytes=32 << 20, max_records=1 << 16, max_samples=S, aux_streams=False) as eng:
+        lib = eng.lib
+        eng.set_sheet(bcs)
+        want = np.zeros(S + 2, dtype=np.uint64)
+        opts = L.DemuxOpts(-1, 0, 0, 0, 0)
+        for k in range(3):
+            eng.synth(0, 20000, seed=4, first_pair=20000 * k, mate=1, with_bc=True)
+            eng.synth(1, 20000, seed=4, first_pair=20000 * k, mate=2, with_bc=True)
+            assert lib.sk_demultiplex(eng.ctx, 0, C.byref(opts)) == 0
+            eng.wait()
+            c = np.zeros(S + 2, dtype=np.uint64)
+            assert lib.sk_download_counts(eng.ctx, 0, c.ctypes.data) == 0
+            want += c
+            assert lib.sk_counts_accumulate(eng.ctx, 0) == 0
+        ctxs = (C.c_void_p * 1)(eng.ctx)
+        assert lib.sk_allreduce_totals(ctxs, 1) == 0
+        got = np.zeros(S + 2, dtype=np.uint64)
+        assert lib.sk_download_totals(eng.ctx, got.ctypes.data) == 0
+        assert np.array_equal(got, want) and int(got[S]) == 60000
+        assert lib.sk_totals_reset(eng.ctx) == 0
+        assert lib.sk_download_totals(eng.ctx, got.ctypes.data) == 0 and int(got.sum()) == 0

@@ -254,12 +254,11 @@ def _bc_headers(data, bcs, seed):
     return b"\n".join(out)
 
 
-def test_lean_engine_is_the_default_and_reruns_beyond_its_limits(O, monkeypatch):
-    """Trim, mask and header-route demultiplex run on the lean / warp engines (sk_fast.cu, sk_warp.cu).
-    Records of ~5.5 KB are longer than their overhangs (4160 B; 1200 B with the warp engine's tile pinned
-    at 29 lanes) but inside the general engine's (6128 B): as soon as one of them starts near the end of a
-    chunk the operator is re-run on the general engine (sk_result.reserved bit 1), and the bytes stay
-    those of the oracle either way."""
+def test_warp_engine_is_the_default_and_reruns_beyond_its_limits(O, monkeypatch):
+    """Trim, mask and header-route demultiplex run on the warp engine (sk_warp.cu).  Records of ~5.5 KB are
+    longer than its overhang (1200 B with the tile pinned at 29 lanes) but inside the general engine's
+    (6128 B): as soon as one of them starts near the end of a tile the operator is re-run on the general
+    engine (sk_result.reserved bit 1), and the bytes stay those of the oracle either way."""
     from seqkit_b200 import Engine
     monkeypatch.setenv("SK_TILE_LANES", "29")
     with Engine(max_stream_bytes=48 << 20, max_records=1 << 18, max_samples=512) as eng:
@@ -276,11 +275,11 @@ def _rerun_body(eng, O):
         long_list.append(b"@long read %d\n" % i + bytes(rng.choice(b"ACGT") for _ in range(n)) + b"\n+\n" +
                          b"I" * (n // 2) + b"#" * (n - n // 2) + b"\n")
     long_recs = b"".join(long_list)
-    # the construction must really leave the lean window (chunk 16320 B + 4160 B overhang) somewhere
+    # the construction must really leave the warp engine's window (tile 11600 B + 1200 B overhang) somewhere
     pos, overruns = len(data), 0
     for rec in long_list:
-        start_in_chunk = pos - ((pos - 1) // 16320) * 16320
-        overruns += start_in_chunk + len(rec) > 20480
+        start_in_tile = pos - (pos // 11600) * 11600
+        overruns += start_in_tile + len(rec) > 12800
         pos += len(rec)
     assert overruns > 0
     for label, blob, rerun in (("normal", data, False), ("long", data + long_recs + data, True)):
@@ -292,11 +291,11 @@ def _rerun_body(eng, O):
         for fused in (None, 20):
             want_in = r1 if fused is None else O.trim_by_quality(r1, fused)[1]
             _cmp_demux(eng.demultiplex(sheet, r1, None, fused_trim=fused), O.demultiplex(sheet, want_in, None), (label, fused))
-            assert eng.last_result.reserved == (2 if rerun else 1), ("demux", label, fused, eng.last_result.reserved)
+            assert eng.last_result.reserved & 3 == (2 if rerun else 1), ("demux", label, fused, eng.last_result.reserved)
 
 
 def test_framing_guess_is_verified_against_the_line_count(eng, O):
-    """The lean engine guesses a chunk's record framing from the text ('@' line whose second successor
+    """The warp engine guesses a tile's record framing from the text ('@' line whose second successor
     starts with '+') and checks the guess against the global line count.  Here every sequence starts
     with '+' and every quality string with '@', so the guess is wrong for chunks that begin inside a
     record; the output must still be that of plain line counting (common.rs:106-112)."""
@@ -316,7 +315,7 @@ def test_framing_guess_is_verified_against_the_line_count(eng, O):
     r1 = _bc_headers(data, bcs, 11)
     _cmp_demux(eng.demultiplex(sheet, r1, r1, fused_trim=20),
                O.demultiplex(sheet, O.trim_by_quality(r1, 20)[1], O.trim_by_quality(r1, 20)[1]), "fused")
-    assert eng.last_result.reserved == 1
+    assert eng.last_result.reserved & 3 == 1  # (bit 3: compacted on the device)
 
 
 def test_properties_at_bench_batch_size():

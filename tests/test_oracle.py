@@ -208,3 +208,21 @@ def test_fuzz_c_vs_python_demux():
             a = O.demultiplex(sheet, r1, r2, dry_run=5)
             b = R.demultiplex(sheet, r1, r2, dry_run=5)
             assert a["exit_code"] == b["exit_code"] and a["counts"] == b["counts"]
+
+
+def test_host_generator_shapes():
+    """oracle/synth_host.c: deterministic, range-addressable (two half ranges concatenate to the whole), four
+    lines per record, ' BC:' fields of the sheet's length."""
+    import bench
+    from oracle import pyoracle as O
+    bcs = bench.make_sheet(24)
+    a = O.synth_fastq(500, seed=5, first_pair=100, mate=1, barcodes=bcs)
+    assert a == O.synth_fastq(500, seed=5, first_pair=100, mate=1, barcodes=bcs)
+    assert a == O.synth_fastq(200, seed=5, first_pair=100, mate=1, barcodes=bcs) + \
+        O.synth_fastq(300, seed=5, first_pair=300, mate=1, barcodes=bcs)
+    lines = a.split(b"\n")
+    assert len(lines) == 4 * 500 + 1 and all(len(x) == 150 for x in lines[1::4]) and all(x == b"+" for x in lines[2:-1:4])
+    assert all(h.startswith(b"@SIM:1:FC:") and len(h[h.rfind(b" BC:") + 4:]) == 29 for h in lines[0:-1:4])
+    b = O.synth_fastq(500, seed=5, first_pair=100, mate=2, barcodes=bcs)
+    h1, h2 = lines[0:-1:4], b.split(b"\n")[0:-1:4]
+    assert all(x.replace(b" 1:N", b" 2:N") == y for x, y in zip(h1, h2))  # mates share coordinates and barcode
