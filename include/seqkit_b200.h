@@ -45,6 +45,10 @@ extern "C" {
 #define SK_DATA_BC_LEN 5          /* demux: barcode length != sheet (fasta_demultiplex.rs:148-150) */
 #define SK_DATA_INDEX_ASSERT 6    /* demux --index: '@' / '+' assertion -> panic 101 (fasta_demultiplex.rs:130,134) */
 #define SK_DATA_BAD_FASTX_LINE 7  /* add barcode: header is neither '@' nor '>' (fasta_add_barcode.rs:41-43) */
+#define SK_DATA_NO_PLUS 8         /* check: line 2 of a FASTQ record lacks '+' (fasta_check.rs:58-61) */
+#define SK_DATA_INCONSISTENT 9    /* interleave / deinterleave / extract dual umi: the second record of a pair does not start
+                                     like the first (fasta_interleave.rs:26-29, fasta_deinterleave.rs:30-33, fasta_extract_dual_umi.rs:42-52) */
+#define SK_DATA_QUAL_SHORT 10     /* trim / extract dual umi: &qual[..] out of range -> Rust panic, status 101 (fasta_trim.rs:41) */
 /* Inputs this implementation refuses instead of guessing: */
 #define SK_DATA_NON_ASCII 32      /* a byte >= 0x80 in the batch */
 #define SK_DATA_RECORD_TOO_LONG 33
@@ -52,6 +56,7 @@ extern "C" {
 #define SK_DATA_MIXED_FORMAT 35   /* '@' and '>' records mixed in one add-barcode input */
 #define SK_DATA_OUT_OVERFLOW 36   /* output capacity of the slot exceeded */
 #define SK_DATA_TRUNCATED_FUSED 37 /* fused trim+demux on a header line without '\n' */
+#define SK_DATA_HASH_COLLISION 38  /* statistics: two different barcodes with one 64-bit hash (reported, never merged) */
 
 /* sk_result.flags */
 #define SK_FLAG_MATE_COUNT 1u      /* mate/index streams hold fewer records than stream 0 */
@@ -72,7 +77,8 @@ typedef struct sk_limits {
     uint32_t n_slots;          /* independent stream slots for H2D / kernel / D2H overlap (>= 1) */
     uint32_t max_samples;      /* largest sample sheet (0 = no demultiplexing) */
     uint32_t aux_streams;      /* 0: allocate only R1/R2; 1: also AUX1/AUX2 (index reads, barcode file) */
-    uint32_t reserved;         /* tuning: 0 default geometry, 1 = 16 KiB chunks, 2 = 32 KiB chunks */
+    uint32_t reserved;         /* low byte, tuning: 0 default geometry, 1 = 16 KiB chunks, 2 = 32 KiB chunks; bit 8 (0x100): no
+                                  buffers for sk_demux_compact; bit 9 (0x200): buffers for the line operators (sk_line_op) */
 } sk_limits;
 
 typedef struct sk_result {
@@ -171,6 +177,34 @@ int sk_add_barcode(sk_ctx *ctx, uint32_t slot, uint64_t rec_limit);
 /* fasta_demultiplex.rs:117-249: SK_IN_R1 (+SK_IN_R2, +AUX index reads) -> output streams 0/1,
  * slice tables, counters, events. */
 int sk_demultiplex(sk_ctx *ctx, uint32_t slot, const sk_demux_opts *opts);
+
+/* The line engine: a global line table (newline scan with block prefix sums) and the
+ * record-shuffling operators on top of it.  SK_IN_R1 (+ SK_IN_R2 for interleave) -> output stream 0 (+ stream 1 for
+ * deinterleave: sk_result.out_bytes[1]).  Framing follows the stream's first byte ('@': 4 lines per record, '>': 2);
+ * a record that starts with the other character is SK_DATA_MIXED_FORMAT.  On a data outcome the records before
+ * err_record are in the output (sk_result.n_records = their number), as the reference has printed them by then.
+ *   SK_LOP_TRIM          fasta trim --first=x --last=y             (fasta_trim.rs:24-47)
+ *   SK_LOP_CHECK         fasta check                               (fasta_check.rs:49-70); no output
+ *   SK_LOP_STATS         fasta statistics                          (fasta_statistics.rs:13-52); sk_download_stats
+ *   SK_LOP_INTERLEAVE    fasta interleave <R1> <R2>                (fasta_interleave.rs:14-35)
+ *   SK_LOP_DEINTERLEAVE  fasta deinterleave                        (fasta_deinterleave.rs:14-39); n_records = pairs
+ *   SK_LOP_DUAL_UMI      fasta extract dual umi --first-bases=x    (fasta_extract_dual_umi.rs:14-72); n_records = pairs
+ * Needs a context created with sk_limits.reserved bit 9. */
+#define SK_LOP_TRIM 0
+#define SK_LOP_CHECK 1
+#define SK_LOP_STATS 2
+#define SK_LOP_INTERLEAVE 3
+#define SK_LOP_DEINTERLEAVE 4
+#define SK_LOP_DUAL_UMI 5
+int sk_line_op(sk_ctx *ctx, uint32_t slot, uint32_t op, uint32_t x, uint32_t y, uint64_t rec_limit);
+typedef struct sk_stat_entry {
+    uint32_t off; /* one occurrence (the earliest) of the barcode in SK_IN_R1 */
+    uint32_t len;
+    uint64_t count;
+} sk_stat_entry;
+/* Distinct " BC:[ACGTNacgtn]+" barcodes of the last SK_LOP_STATS call, in no particular order; *n = their number
+ * (SK_E_TOO_LARGE when cap is smaller: call again with room for *n). */
+int sk_download_stats(sk_ctx *ctx, uint32_t slot, sk_stat_entry *entries, uint32_t cap, uint32_t *n);
 
 /* Blocks until the slot's stream is idle and returns the outcome of the last operator. */
 int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res);

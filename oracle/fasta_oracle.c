@@ -604,6 +604,292 @@ static void run_demux(demux_t *D, const uint8_t *sheet, size_t ns, const uint8_t
     free(extra);
 }
 
+
+/* ================================================================== SURVEY.md section 8(f): the operators next to the path */
+/* error! with a message of any length (fasta_check.rs quotes up to ten lines) */
+static void fatal_buf(proc *P, const obuf *msg) {
+    ob_puts(&P->err, "ERROR: ");
+    ob_put(&P->err, msg->p, msg->n);
+    ob_putc(&P->err, '\n');
+    P->exit_code = ORC_EXIT_ERROR;
+    longjmp(P->jb, 1);
+}
+static int char_boundary(const line_t *l, size_t k) { return k >= l->n || (l->s[k] & 0xC0) != 0x80; }
+
+/* ------------------------------------------------------------------ trim --first / --last */
+/* fasta_trim.rs:14-48 */
+static void run_trim_fixed(proc *P, const uint8_t *in, size_t n, size_t remove_first, size_t remove_last) {
+    lrd f = {in, n, 0};
+    line_t line, seq, qual;
+    while (read_line(P, &f, &line)) { /* :27 */
+        if (!starts_with(&line, '>') && !starts_with(&line, '@')) /* :28-30 */
+            fatal(P, "Invalid FASTA/FASTQ format encountered.");
+        read_line(P, &f, &seq);                          /* :32 */
+        size_t seq_len = trim_end_len(seq.s, seq.n);     /* :33 */
+        int cut = remove_first + remove_last < seq_len;  /* :34 */
+        if (cut) { /* :35 print!("{}{}\n", line, &seq[remove_first..seq_len-remove_last]) */
+            if (!char_boundary(&seq, remove_first) || !char_boundary(&seq, seq_len - remove_last))
+                rust_panic(P, "byte index is not a char boundary in seq (fasta_trim.rs:35)");
+            ob_put(&P->out, line.s, line.n);
+            ob_put(&P->out, seq.s + remove_first, seq_len - remove_last - remove_first);
+            ob_putc(&P->out, '\n');
+        } else { /* :37 */
+            ob_put(&P->out, line.s, line.n);
+            ob_putc(&P->out, '\n');
+        }
+        if (starts_with(&line, '@')) { /* :40 */
+            read_line(P, &f, &line);   /* :41 */
+            read_line(P, &f, &qual);   /* :42 */
+            if (cut) { /* :44 print!("+\n{}\n", &qual[remove_first..seq_len-remove_last]): the slice is evaluated first */
+                if (seq_len - remove_last > qual.n) rust_panic(P, "byte index out of range of qual (fasta_trim.rs:44)");
+                if (!char_boundary(&qual, remove_first) || !char_boundary(&qual, seq_len - remove_last))
+                    rust_panic(P, "byte index is not a char boundary in qual (fasta_trim.rs:44)");
+                ob_puts(&P->out, "+\n");
+                ob_put(&P->out, qual.s + remove_first, seq_len - remove_last - remove_first);
+                ob_putc(&P->out, '\n');
+            } else { /* :46 */
+                ob_puts(&P->out, "+\n\n");
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ check */
+/* fasta_check.rs:14-47: a reader that remembers the last ten lines */
+typedef struct {
+    lrd file;
+    size_t lines_read;
+    line_t prev[10];
+    int n_prev;
+} memrd;
+static int mem_read_line(proc *P, memrd *r, line_t *l) {
+    if (!read_line(P, &r->file, l)) return 0; /* :31 (the line is cleared) */
+    if (r->n_prev == 10) {                    /* :32-35 */
+        memmove(r->prev, r->prev + 1, 9 * sizeof(line_t));
+        r->n_prev = 9;
+    }
+    r->prev[r->n_prev++] = *l;
+    r->lines_read++; /* :36 */
+    return 1;
+}
+static void check_fail(proc *P, memrd *r, const char *what) { /* :40-46 history(), :59-60 / :64-65 */
+    obuf m = {0};
+    ob_printf(&m, "%s on line %zu:\n", what, r->lines_read);
+    for (int k = 0; k < r->n_prev; k++) {
+        ob_put(&m, r->prev[k].s, r->prev[k].n);
+        ob_putc(&m, '\n');
+    }
+    ob_putc(&m, '\n');
+    fatal_buf(P, &m);
+}
+/* fasta_check.rs:49-70 */
+static void run_check(proc *P, const uint8_t *in, size_t n) {
+    memrd r;
+    memset(&r, 0, sizeof r);
+    r.file.p = in;
+    r.file.n = n;
+    line_t line;
+    while (mem_read_line(P, &r, &line)) {  /* :54 */
+        if (starts_with(&line, '>')) {     /* :55-56 */
+            mem_read_line(P, &r, &line);
+        } else if (starts_with(&line, '@')) { /* :57-63 */
+            mem_read_line(P, &r, &line);
+            mem_read_line(P, &r, &line);
+            if (!starts_with(&line, '+')) check_fail(P, &r, "Missing quality header prefix '+'");
+            mem_read_line(P, &r, &line);
+        } else { /* :64-66 */
+            check_fail(P, &r, "Missing header prefix '>' or '@'");
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ statistics */
+static int stat_class(uint8_t c) { /* fasta_statistics.rs:17: [ACGTNacgtn], no '+' */
+    switch (c) {
+        case 'A': case 'C': case 'G': case 'T': case 'N': case 'a': case 'c': case 'g': case 't': case 'n': return 1;
+    }
+    return 0;
+}
+typedef struct {
+    uint8_t *s;
+    size_t n;
+    uint64_t count;
+} stat_ent;
+static int stat_cmp_key(const void *a, const void *b) {
+    const stat_ent *x = (const stat_ent *)a, *y = (const stat_ent *)b;
+    size_t m = x->n < y->n ? x->n : y->n;
+    int c = memcmp(x->s, y->s, m);
+    if (c) return c;
+    return x->n < y->n ? -1 : x->n > y->n;
+}
+static int stat_cmp_rank(const void *a, const void *b) { /* count descending; equal counts: barcode descending */
+    const stat_ent *x = (const stat_ent *)a, *y = (const stat_ent *)b;
+    if (x->count != y->count) return x->count > y->count ? -1 : 1;
+    return -stat_cmp_key(a, b);
+}
+/* fasta_statistics.rs:13-52.  The reference collects a HashMap, sorts by count (stable) and reverses: entries of
+ * equal count come out in an order that depends on the hash seed.  The restatement fixes that order (barcode
+ * descending), and so does the product; everything else is the reference's. */
+static void run_statistics(proc *P, const uint8_t *in, size_t n) {
+    lrd f = {in, n, 0};
+    line_t line;
+    uint64_t total_records = 0;
+    stat_ent *ents = NULL;
+    size_t n_ents = 0, cap = 0;
+    while (read_line(P, &f, &line)) { /* :24 */
+        /* :26-29 leftmost match of " BC:[ACGTNacgtn]+" */
+        for (size_t k = 0; k + 5 <= line.n; k++)
+            if (line.s[k] == ' ' && line.s[k + 1] == 'B' && line.s[k + 2] == 'C' && line.s[k + 3] == ':' && stat_class(line.s[k + 4])) {
+                size_t e = k + 5;
+                while (e < line.n && stat_class(line.s[e])) e++;
+                if (n_ents == cap) {
+                    cap = cap ? cap * 2 : 1024;
+                    ents = (stat_ent *)realloc(ents, cap * sizeof(stat_ent));
+                }
+                ents[n_ents].s = (uint8_t *)line.s + k + 4;
+                ents[n_ents].n = e - k - 4;
+                ents[n_ents].count = 1;
+                n_ents++;
+                break;
+            }
+        if (starts_with(&line, '@')) { /* :32-33 */
+            line_t t;
+            for (int i = 0; i < 3; i++) read_line(P, &f, &t);
+        } else if (starts_with(&line, '>')) { /* :34-35 */
+            line_t t;
+            read_line(P, &f, &t);
+        } else { /* :36-38 */
+            obuf m = {0};
+            ob_puts(&m, "Invalid FASTQ header:\n");
+            ob_put(&m, line.s, line.n);
+            fatal_buf(P, &m);
+        }
+        total_records += 1; /* :40 */
+    }
+    ob_printf(&P->out, "Total sequence records: %llu\n", (unsigned long long)total_records); /* :43 */
+    ob_puts(&P->out, "Most frequent sample barcodes:\n");                                   /* :45 */
+    /* the HashMap: merge equal barcodes */
+    qsort(ents, n_ents, sizeof(stat_ent), stat_cmp_key);
+    size_t m = 0;
+    for (size_t i = 0; i < n_ents; i++) {
+        if (m && stat_cmp_key(&ents[m - 1], &ents[i]) == 0) ents[m - 1].count++;
+        else ents[m++] = ents[i];
+    }
+    qsort(ents, m, sizeof(stat_ent), stat_cmp_rank); /* :46-49 */
+    if (m < 100) rust_panic(P, "range end index 100 out of range for slice (fasta_statistics.rs:50)");
+    for (size_t i = 0; i < 100; i++) { /* :50-52 */
+        ob_puts(&P->out, "- ");
+        ob_put(&P->out, ents[i].s, ents[i].n);
+        ob_printf(&P->out, ": %llu\n", (unsigned long long)ents[i].count);
+    }
+    free(ents);
+}
+
+/* ------------------------------------------------------------------ interleave / deinterleave */
+static void not_fastx(proc *P, const line_t *line) { /* "Line is not FASTA/FASTQ format: {}" */
+    obuf m = {0};
+    ob_puts(&m, "Line is not FASTA/FASTQ format: ");
+    ob_put(&m, line->s, line->n);
+    fatal_buf(P, &m);
+}
+/* fasta_interleave.rs:14-35 */
+static void run_interleave(proc *P, const uint8_t *a, size_t na, const uint8_t *b, size_t nb) {
+    lrd f1 = {a, na, 0}, f2 = {b, nb, 0};
+    line_t line;
+    while (read_line(P, &f1, &line)) { /* :20 */
+        int lines = starts_with(&line, '@') ? 4 : starts_with(&line, '>') ? 2 : 0; /* :21-23 */
+        if (!lines) not_fastx(P, &line);
+        ob_put(&P->out, line.s, line.n); /* :24 */
+        for (int k = 0; k < lines - 1; k++) { /* :25-27 */
+            read_line(P, &f1, &line);
+            ob_put(&P->out, line.s, line.n);
+        }
+        read_line(P, &f2, &line); /* :29 */
+        if ((lines == 4 && !starts_with(&line, '@')) || (lines == 2 && !starts_with(&line, '>'))) /* :30-33 */
+            fatal(P, "Input files do not share a consistent format.");
+        ob_put(&P->out, line.s, line.n); /* :34 */
+        for (int k = 0; k < lines - 1; k++) {
+            read_line(P, &f2, &line);
+            ob_put(&P->out, line.s, line.n);
+        }
+    }
+}
+/* fasta_deinterleave.rs:14-39; the two gzip outputs are out / out2 */
+static void run_deinterleave(proc *P, obuf *out2, const uint8_t *in, size_t n) {
+    lrd f = {in, n, 0};
+    line_t line;
+    while (read_line(P, &f, &line)) { /* :22 */
+        int lines = starts_with(&line, '@') ? 4 : starts_with(&line, '>') ? 2 : 0; /* :23-25 */
+        if (!lines) not_fastx(P, &line);
+        ob_put(&P->out, line.s, line.n); /* :26 */
+        for (int k = 0; k < lines - 1; k++) {
+            read_line(P, &f, &line);
+            ob_put(&P->out, line.s, line.n);
+        }
+        read_line(P, &f, &line); /* :31 */
+        if ((lines == 4 && !starts_with(&line, '@')) || (lines == 2 && !starts_with(&line, '>'))) /* :32-35 */
+            fatal(P, "Interleaved FASTA records are not in consistent format.");
+        ob_put(out2, line.s, line.n); /* :36 */
+        for (int k = 0; k < lines - 1; k++) {
+            read_line(P, &f, &line);
+            ob_put(out2, line.s, line.n);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ extract dual umi */
+/* fasta_extract_dual_umi.rs:14-72 */
+static void run_dual_umi(proc *P, const uint8_t *in, size_t n, size_t first_bases) {
+    lrd f = {in, n, 0};
+    line_t header_1, header_2 = {(const uint8_t *)"", 0}, seq_1 = header_2, seq_2 = header_2, qual_1 = header_2, qual_2 = header_2, line;
+    while (read_line(P, &f, &header_1)) { /* :30 */
+        int fastq_format;
+        if (starts_with(&header_1, '@')) fastq_format = 1; /* :33-35 */
+        else if (starts_with(&header_1, '>')) fastq_format = 0;
+        else {
+            obuf m = {0};
+            ob_puts(&m, "Header is not valid FASTA/FASTQ:\n");
+            ob_put(&m, header_1.s, header_1.n);
+            fatal_buf(P, &m);
+            return;
+        }
+        if (fastq_format) { /* :37-47 */
+            read_line(P, &f, &seq_1);
+            read_line(P, &f, &line);
+            read_line(P, &f, &qual_1);
+            read_line(P, &f, &header_2);
+            read_line(P, &f, &seq_2);
+            read_line(P, &f, &line);
+            read_line(P, &f, &qual_2);
+            if (!starts_with(&header_2, '@')) fatal(P, "Invalid FASTQ record found in input file.");
+        } else { /* :48-54 */
+            read_line(P, &f, &seq_1);
+            read_line(P, &f, &header_2);
+            read_line(P, &f, &seq_2);
+            if (!starts_with(&header_2, '>')) fatal(P, "Invalid FASTA record found in input file.");
+        }
+        /* :56-58 umi = seq_1[0..N] + "+" + seq_2[0..N] */
+        if (first_bases > seq_1.n || !char_boundary(&seq_1, first_bases)) rust_panic(P, "byte index out of range of seq_1 (fasta_extract_dual_umi.rs:56)");
+        if (first_bases > seq_2.n || !char_boundary(&seq_2, first_bases)) rust_panic(P, "byte index out of range of seq_2 (fasta_extract_dual_umi.rs:58)");
+        if (fastq_format && (first_bases > qual_1.n || first_bases > qual_2.n || !char_boundary(&qual_1, first_bases) || !char_boundary(&qual_2, first_bases)))
+            rust_panic(P, "byte index out of range of qual (fasta_extract_dual_umi.rs:63-65)");
+        const line_t *hs[2] = {&header_1, &header_2}, *ss[2] = {&seq_1, &seq_2}, *qs[2] = {&qual_1, &qual_2};
+        for (int m = 0; m < 2; m++) { /* :60-70, one print! per pair: all slices are taken before anything is written */
+            ob_put(&P->out, hs[m]->s, trim_end_len(hs[m]->s, hs[m]->n));
+            ob_puts(&P->out, " RX:");
+            ob_put(&P->out, seq_1.s, first_bases);
+            ob_putc(&P->out, '+');
+            ob_put(&P->out, seq_2.s, first_bases);
+            ob_putc(&P->out, '\n');
+            ob_put(&P->out, ss[m]->s + first_bases, ss[m]->n - first_bases);
+            if (fastq_format) {
+                ob_puts(&P->out, "+\n");
+                ob_put(&P->out, qs[m]->s + first_bases, qs[m]->n - first_bases);
+            }
+        }
+    }
+}
+
 /* ------------------------------------------------------------------ exported C API (ctypes) */
 typedef struct {
     int exit_code;
@@ -641,6 +927,34 @@ int orc_add_barcode(const uint8_t *fq, size_t n, const uint8_t *bc, size_t nb, o
     if (setjmp(P->jb) == 0) run_add_barcode(P, fq, n, bc, nb);
     finish(P, R);
     free(P);
+    return R->exit_code;
+}
+
+/* SURVEY.md section 8(f) operators: op 0 trim --first=x --last=y, 1 check, 2 statistics, 3 interleave (a, b), 4 deinterleave
+ * (second output in out2), 5 extract dual umi --first-bases=x */
+int orc_next(int op, const uint8_t *a, size_t na, const uint8_t *b, size_t nb, uint64_t x, uint64_t y, orc_result *R,
+             uint8_t **out2, size_t *out2_n) {
+    proc *P = (proc *)calloc(1, sizeof(proc));
+    obuf *o2 = (obuf *)calloc(1, sizeof(obuf)); /* (on the heap: it is written between setjmp and longjmp) */
+    if (setjmp(P->jb) == 0) {
+        switch (op) {
+            case 0: run_trim_fixed(P, a, na, (size_t)x, (size_t)y); break;
+            case 1: run_check(P, a, na); break;
+            case 2: run_statistics(P, a, na); break;
+            case 3: run_interleave(P, a, na, b, nb); break;
+            case 4: run_deinterleave(P, o2, a, na); break;
+            case 5: run_dual_umi(P, a, na, (size_t)x); break;
+        }
+    }
+    finish(P, R);
+    free(P);
+    if (out2) {
+        *out2 = o2->p;
+        *out2_n = o2->n;
+    } else {
+        free(o2->p);
+    }
+    free(o2);
     return R->exit_code;
 }
 
@@ -758,6 +1072,49 @@ int main(int argc, char **argv) {
         if (argc != 5) { fprintf(stderr, "ERROR: Invalid arguments.\n\nUsage:\n  fasta add barcode <fastq_file> <barcode_file>\n\n"); return 255; }
         size_t n, nb; uint8_t *fq = open_input(argv[3], &n); uint8_t *bc = open_input(argv[4], &nb);
         orc_add_barcode(fq, n, bc, nb, &R);
+    } else if (argc >= 2 && (!strcmp(argv[1], "trim") || !strcmp(argv[1], "check") || !strcmp(argv[1], "statistics") ||
+                             !strcmp(argv[1], "interleave") || !strcmp(argv[1], "deinterleave") ||
+                             (argc >= 4 && !strcmp(argv[1], "extract") && !strcmp(argv[2], "dual") && !strcmp(argv[3], "umi")))) {
+        /* fasta trim [--first=N] [--last=N] <f> | check <f> | statistics <f> | interleave <f1> <f2> |
+         * deinterleave <f> <prefix> | extract dual umi [--first-bases=N] <f> */
+        const int is_umi = !strcmp(argv[1], "extract");
+        const int op = !strcmp(argv[1], "trim") ? 0 : !strcmp(argv[1], "check") ? 1 : !strcmp(argv[1], "statistics") ? 2
+                       : !strcmp(argv[1], "interleave") ? 3 : !strcmp(argv[1], "deinterleave") ? 4 : 5;
+        const char *pos[4]; int npos = 0; const char *first = "0", *last = "0", *fb = "0";
+        for (int a = is_umi ? 4 : 2; a < argc; a++) {
+            if (op == 0 && !strncmp(argv[a], "--first=", 8)) first = argv[a] + 8;
+            else if (op == 0 && !strncmp(argv[a], "--last=", 7)) last = argv[a] + 7;
+            else if (op == 5 && !strncmp(argv[a], "--first-bases=", 14)) fb = argv[a] + 14;
+            else if (argv[a][0] == '-' && argv[a][1]) npos = 99;
+            else if (npos < 4) pos[npos++] = argv[a];
+        }
+        const int want = (op == 3 || op == 4) ? 2 : 1;
+        if (npos != want) { fprintf(stderr, "ERROR: Invalid arguments.\n"); return 255; }
+        size_t na, nb = 0; uint8_t *a = open_input(pos[0], &na), *b = NULL;
+        if (op == 3) b = open_input(pos[1], &nb);
+        uint64_t x = 0, y = 0;
+        const char *vals[2] = {op == 5 ? fb : first, last};
+        const char *names[2] = {op == 5 ? "--first-bases=N" : "--first=N", "--last=N"};
+        for (int k = 0; k < (op == 0 ? 2 : op == 5 ? 1 : 0); k++) { /* usize::from_str: optional '+', digits */
+            const char *q = vals[k]; if (*q == '+') q++;
+            char *e; unsigned long long v = strtoull(q, &e, 10);
+            if (!*q || *e || q[0] < '0' || q[0] > '9') { fprintf(stderr, "ERROR: N must be a non-negative integer in %s.\n", names[k]); return 255; }
+            if (k == 0) x = v; else y = v;
+        }
+        char p1[4096], p2[4096];
+        if (op == 4) { /* GzipWriter::with_method creates the files first (fasta_deinterleave.rs:17-20) */
+            snprintf(p1, sizeof p1, "%s_1.fq.gz", pos[1]);
+            snprintf(p2, sizeof p2, "%s_2.fq.gz", pos[1]);
+            FILE *c1 = fopen(p1, "wb"); if (!c1) { fprintf(stderr, "ERROR: Cannot open file %s for writing.\n", p1); return 255; } fclose(c1);
+            FILE *c2 = fopen(p2, "wb"); if (!c2) { fprintf(stderr, "ERROR: Cannot open file %s for writing.\n", p2); return 255; } fclose(c2);
+        }
+        uint8_t *o2 = NULL; size_t o2n = 0;
+        orc_next(op, a, na, b, nb, x, y, &R, &o2, &o2n);
+        if (op == 4) {
+            gzip_write(p1, R.out, R.out_n, 0);
+            gzip_write(p2, o2, o2n, 0);
+            R.out_n = 0;
+        }
     } else if (argc >= 2 && !strcmp(argv[1], "demultiplex")) {
         const char *i1 = NULL, *i2 = NULL, *pos[3]; int npos = 0, parallel = 0; uint64_t dry = 0;
         for (int a = 2; a < argc; a++) {

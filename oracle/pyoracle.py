@@ -157,3 +157,18 @@ def synth_fastq(n_pairs: int, seed: int = 1, first_pair: int = 0, read_len: int 
     n = L.orc_synth_fastq(buf, cap, C.byref(spec), b"".join(barcodes) if S else b"", S, Lb)
     assert n or n_pairs == 0, "synthetic buffer too small"
     return buf.raw[:n]
+
+
+def next_op(op: int, a: bytes, b: bytes | None = None, x: int = 0, y: int = 0):
+    """SURVEY.md section 8(f) operators of the oracle: 0 trim --first=x --last=y, 1 check, 2 statistics, 3 interleave(a, b),
+    4 deinterleave, 5 extract dual umi --first-bases=x.  Returns (exit_code, stdout, stderr, second_output)."""
+    L = lib()
+    L.orc_next.argtypes = [C.c_int, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t, C.c_uint64, C.c_uint64, C.POINTER(_Result),
+                           C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]
+    L.orc_next.restype = C.c_int
+    R = _Result()
+    o2, n2 = C.c_void_p(), C.c_size_t()
+    L.orc_next(op, a, len(a), b or b"", len(b or b""), x, y, C.byref(R), C.byref(o2), C.byref(n2))
+    out2 = C.string_at(o2, n2.value) if n2.value else b""
+    code, out, err = _take(R)
+    return code, out, err, out2

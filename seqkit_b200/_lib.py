@@ -12,7 +12,8 @@ IN_R1, IN_R2, IN_AUX1, IN_AUX2 = 0, 1, 2, 3
 
 # sk_result.status values
 DATA_OK, DATA_BAD_HEADER, DATA_LEN_MISMATCH, DATA_SEQ_SHORT, DATA_NO_BC, DATA_BC_LEN, DATA_INDEX_ASSERT, \
-    DATA_BAD_FASTX_LINE = range(8)
+    DATA_BAD_FASTX_LINE, DATA_NO_PLUS, DATA_INCONSISTENT, DATA_QUAL_SHORT = range(11)
+LOP_TRIM, LOP_CHECK, LOP_STATS, LOP_INTERLEAVE, LOP_DEINTERLEAVE, LOP_DUAL_UMI = range(6)
 DATA_NON_ASCII, DATA_RECORD_TOO_LONG, DATA_CHUNK_TOO_DENSE, DATA_MIXED_FORMAT, DATA_OUT_OVERFLOW, \
     DATA_TRUNCATED_FUSED = range(32, 38)
 FLAG_MATE_COUNT, FLAG_EVENTS_OVERFLOW = 1, 2
@@ -52,6 +53,10 @@ class Slice(C.Structure):
     _fields_ = [("offset", C.c_uint64), ("len", C.c_uint64)]
 
 
+class StatEntry(C.Structure):
+    _fields_ = [("off", C.c_uint32), ("len", C.c_uint32), ("count", C.c_uint64)]
+
+
 class DemuxOpts(C.Structure):
     _fields_ = [("fused_trim_min_baseq", C.c_int32), ("use_index", C.c_uint32), ("rec_limit", C.c_uint64),
                 ("no_output", C.c_uint32), ("reserved", C.c_uint32)]
@@ -88,6 +93,8 @@ SIGNATURES = {
     "sk_mask_by_quality": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint64]),
     "sk_add_barcode": (C.c_int, [_P, C.c_uint32, C.c_uint64]),
     "sk_demultiplex": (C.c_int, [_P, C.c_uint32, C.POINTER(DemuxOpts)]),
+    "sk_line_op": (C.c_int, [_P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64]),
+    "sk_download_stats": (C.c_int, [_P, C.c_uint32, C.POINTER(StatEntry), C.c_uint32, C.POINTER(C.c_uint32)]),
     "sk_wait": (C.c_int, [_P, C.c_uint32, C.POINTER(Result)]),
     "sk_out_dev": (_P, [_P, C.c_uint32, C.c_uint32]),
     "sk_download_out": (C.c_int, [_P, C.c_uint32, C.c_uint32, _P, C.c_uint64]),

@@ -55,6 +55,11 @@ struct Slot {
     unsigned long long *slices = nullptr;     // [2][(Smax + 1) * 2]
     unsigned long long *piece_dst = nullptr;  // [max_records]
     bool want_compact = false, compacted = false;
+    // line engine (sk_lineops.cu; sk_limits.reserved bit 9)
+    void *lwork = nullptr;
+    void *stats_tab = nullptr;
+    uint32_t h_cap = 0;
+    uint32_t line_op = 0;
     // description of the last operator, for sk_wait
     int last_op = -1;
     bool paired = false;
@@ -157,6 +162,8 @@ static void free_slot(Slot &s) {
     cudaFree(s.counts);
     cudaFree(s.events);
     cudaFree(s.synth_tmp);
+    cudaFree(s.lwork);
+    cudaFree(s.stats_tab);
     cudaFree(s.cbuf);
     cudaFree(s.cwork);
     cudaFree(s.slices);
@@ -285,6 +292,13 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
         }
         if (lim->aux_streams)
             for (int i = 0; i < 2; i++) CKC(cudaMalloc(&s.scan_tab[i], R * sizeof(RecRef)));
+        if (lim->reserved & 0x200u) {  // line operators
+            CKC(cudaMalloc(&s.lwork, lineops_work_bytes(B, R)));
+            uint32_t cap = 1024;
+            while ((uint64_t)cap < 2 * R && cap < (1u << 30)) cap <<= 1;
+            s.h_cap = cap;
+            CKC(cudaMalloc(&s.stats_tab, (uint64_t)cap * 36 + 64));
+        }
     }
 #undef CKC
     *out = ctx;
@@ -845,6 +859,58 @@ extern "C" int sk_add_barcode(sk_ctx *ctx, uint32_t slot, uint64_t rec_limit) {
     return end_op(ctx, s);
 }
 
+// The line engine's operators (sk_lineops.cu): SK_IN_R1 (+ SK_IN_R2 for interleave) -> output stream 0 (+ 1 for
+// deinterleave).  Framing by the stream's first byte: '@' = 4 lines per record, '>' = 2.
+extern "C" int sk_line_op(sk_ctx *ctx, uint32_t slot, uint32_t op, uint32_t x, uint32_t y, uint64_t rec_limit) {
+    Slot *s = get_slot(ctx, slot);
+    if (!s || op > 5) return SK_E_INVALID;
+    if (!s->lwork) {
+        ctx->err = "sk_line_op needs a context created with sk_limits.reserved bit 9 (0x200)";
+        return SK_E_INVALID;
+    }
+    int c = -1;
+    int rc = peek_first_byte(ctx, s, SK_IN_R1, &c);
+    if (rc) return rc;
+    rc = begin_op(ctx, s, OP_LINE);
+    if (rc) return rc;
+    s->line_op = op;
+    const uint32_t lpr = c == '>' ? 2u : 4u, head = c == '>' ? (uint32_t)'>' : (uint32_t)'@';
+    const char *err = nullptr;
+    const int n = launch_lineop((int)op, s->in[SK_IN_R1], s->in_len[SK_IN_R1], s->in[SK_IN_R2], s->in_len[SK_IN_R2], lpr, head, x, y,
+                                rec_limit, s->out[0], s->out[1], s->out_cap, s->lwork, ctx->lim.max_stream_bytes, ctx->lim.max_records,
+                                s->stats_tab, s->h_cap, s->stats + SK_IN_R1, ctx->sm_count, s->stream, &err);
+    if (n < 0) {
+        ctx->err = std::string("line operator launch failed: ") + (err ? err : "?");
+        return SK_E_CUDA;
+    }
+    s->launches += (uint32_t)n;
+    s->pass_ran[SK_IN_R1] = true;
+    return end_op(ctx, s);
+}
+// Statistics: the distinct barcodes of the last sk_line_op(SK_LOP_STATS) -- (offset, length) of one occurrence
+// (the earliest) in SK_IN_R1 and the number of records that carry it -- in no particular order.
+extern "C" int sk_download_stats(sk_ctx *ctx, uint32_t slot, sk_stat_entry *entries, uint32_t cap, uint32_t *n) {
+    Slot *s = get_slot(ctx, slot);
+    if (!s || !s->stats_tab || !n) return SK_E_INVALID;
+    CK(cudaStreamSynchronize(s->stream));
+    const uint64_t hc = s->h_cap;
+    const uint8_t *base = (const uint8_t *)s->stats_tab;
+    const unsigned long long *list = (const unsigned long long *)(base + hc * 20);
+    const uint32_t *n_list = (const uint32_t *)(base + hc * 36);
+    uint32_t cnt = 0;
+    CK(cudaMemcpy(&cnt, n_list, 4, cudaMemcpyDeviceToHost));
+    *n = cnt;
+    if (!entries || cap < cnt) return cnt ? SK_E_TOO_LARGE : SK_OK;
+    std::vector<unsigned long long> tmp((size_t)cnt * 2);
+    if (cnt) CK(cudaMemcpy(tmp.data(), list, (size_t)cnt * 16, cudaMemcpyDeviceToHost));
+    for (uint32_t k = 0; k < cnt; k++) {
+        entries[k].off = (uint32_t)(tmp[2 * (size_t)k] >> 32);
+        entries[k].len = (uint32_t)tmp[2 * (size_t)k];
+        entries[k].count = tmp[2 * (size_t)k + 1];
+    }
+    return SK_OK;
+}
+
 static int demux_enqueue(sk_ctx *ctx, Slot *s, const sk_demux_opts *o, bool fast);
 extern "C" int sk_demultiplex(sk_ctx *ctx, uint32_t slot, const sk_demux_opts *o) {
     Slot *s = get_slot(ctx, slot);
@@ -1106,6 +1172,10 @@ extern "C" int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res) {
     } else {
         res->out_bytes[0] = h[SK_IN_R1].out_bytes;
         res->out_extent[0] = h[SK_IN_R1].out_extent;
+        if (s->last_op == OP_LINE) {  // deinterleave: the second output stream
+            res->out_bytes[1] = h[SK_IN_R1].compact_extent;
+            res->out_extent[1] = h[SK_IN_R1].compact_extent;
+        }
     }
     res->flags = flags & 0xFFu;
     if (best_key != ~0ull) {

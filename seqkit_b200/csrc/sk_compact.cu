@@ -191,41 +191,6 @@ __global__ void __launch_bounds__(32) sk_compact_addr_kernel(const ChunkRow *__r
 }
 
 // ---- move ----------------------------------------------------------------------------------------
-// len bytes from src + so to dst + d_o (any alignment on either side), the whole warp: a lane takes the
-// 16-byte units of the destination, reads the two aligned 16-byte pieces of the source that hold a unit's
-// bytes and shifts them into place (the shift is the same for every unit of a piece).
-__device__ __forceinline__ void warp_copy_piece(const uint8_t *__restrict__ src, uint8_t *__restrict__ dst, unsigned long long so,
-                                                unsigned long long d_o, uint32_t len, int lane) {
-    uint8_t *d = dst + d_o;
-    const uint32_t a = (uint32_t)(uintptr_t)d & 15u;  // d - a is 16-byte aligned
-    const uint32_t units = (a + len + 15u) >> 4;
-    const long long s0 = (long long)so - (long long)a;  // source offset of the first unit's first byte (may be < 0)
-    const uint32_t sh = (uint32_t)(s0 & 15), wo = sh >> 2, bs = (sh & 3u) * 8u;
-    for (uint32_t u = (uint32_t)lane; u < units; u += 32u) {
-        const long long su = (s0 + 16ll * u) & ~15ll;  // aligned piece that holds the unit's first byte
-        uint4 A = make_uint4(0u, 0u, 0u, 0u), B = make_uint4(0u, 0u, 0u, 0u);
-        if (su >= 0) A = *(const uint4 *)(src + su);
-        if (sh && su + 16 >= 0) B = *(const uint4 *)(src + su + 16);  // (the buffers end with slack: reading past a piece is fine)
-        const uint32_t W[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
-        uint4 o4;
-        switch (wo) {  // uniform over the piece
-            case 0: o4 = make_uint4(__funnelshift_r(W[0], W[1], bs), __funnelshift_r(W[1], W[2], bs), __funnelshift_r(W[2], W[3], bs), __funnelshift_r(W[3], W[4], bs)); break;
-            case 1: o4 = make_uint4(__funnelshift_r(W[1], W[2], bs), __funnelshift_r(W[2], W[3], bs), __funnelshift_r(W[3], W[4], bs), __funnelshift_r(W[4], W[5], bs)); break;
-            case 2: o4 = make_uint4(__funnelshift_r(W[2], W[3], bs), __funnelshift_r(W[3], W[4], bs), __funnelshift_r(W[4], W[5], bs), __funnelshift_r(W[5], W[6], bs)); break;
-            default: o4 = make_uint4(__funnelshift_r(W[3], W[4], bs), __funnelshift_r(W[4], W[5], bs), __funnelshift_r(W[5], W[6], bs), __funnelshift_r(W[6], W[7], bs)); break;
-        }
-        uint8_t *du = d - a + 16u * u;
-        const uint32_t first = u == 0 ? a : 0u;  // valid bytes of the unit: [first, last)
-        const uint32_t last = 16u * u + 16u > a + len ? a + len - 16u * u : 16u;
-        if (first == 0u && last == 16u) {
-            *(uint4 *)du = o4;
-        } else {  // the piece's first and last unit are shared with its neighbours in the sample's run
-            const uint32_t ow[4] = {o4.x, o4.y, o4.z, o4.w};
-            for (uint32_t i = first; i < last; i++) du[i] = (uint8_t)(ow[i >> 2] >> (8u * (i & 3u)));
-        }
-    }
-}
-
 // One warp per row.  The row's pieces lie back to back in the input-order stream: the warp brings the whole
 // row into its window of shared memory with one TMA bulk copy and then every lane copies one piece from the
 // window to its destination (gcopy: whole 32-byte sectors inside the piece, small stores at its two ends,

@@ -12,6 +12,7 @@ enum Op : int {
     OP_ADDBC = 3,   // fasta_add_barcode.rs:11-45
     OP_DEMUX1 = 4,  // fasta_demultiplex.rs:117-212 (mate 1: extract, match, decide, emit)
     OP_DEMUX2 = 5,  // fasta_demultiplex.rs:215-238 (mate 2: emit)
+    OP_LINE = 6,    // the line engine's operators (sk_lineops.cu): trim --first/--last, check, statistics, ...
 };
 
 // Geometry of one chunk-engine configuration.  WIN_MAX = NT*PPL*16 bytes of window per CTA:
@@ -209,6 +210,7 @@ enum : unsigned {
     K_BAD_HEADER = 1, K_LEN_MISMATCH = 2, K_SEQ_SHORT = 3, K_NO_BC = 4, K_BC_LEN = 5, K_INDEX_ASSERT = 6,
     K_BAD_FASTX_LINE = 7, K_NON_ASCII = 32, K_TOO_LONG = 33, K_TOO_DENSE = 34, K_MIXED = 35, K_OUT_OVERFLOW = 36,
     K_TRUNC_FUSED = 37,
+    // line operators (sk_lineops.cu): K_NO_PLUS = 8, K_INCONSISTENT = 9, K_QUAL_SHORT = 10, K_HASH_COLLISION = 38
 };
 enum : unsigned { F_MATE_COUNT = 1u, F_EVENTS_OVERFLOW = 2u, F_NON_ASCII = 0x100u, F_NEED_GENERAL = 0x200u, F_NEED_ORDERED = 0x400u };
 
@@ -241,6 +243,11 @@ int chunk_kernel_smem_bytes(int cfg, uint32_t S, uint32_t wide, uint32_t n_class
 bool warp_supported(int op, const KParams &p);
 int launch_tile_gather(const KParams &p, int sm_count, void *stream, const char **err);  // after an `unordered` launch
 int launch_warp_kernel(int op, const KParams &p, int sm_count, void *stream, const char **err);
+// Line engine (sk_lineops.cu): trim --first/--last, check, statistics, interleave, deinterleave, extract dual umi
+uint64_t lineops_work_bytes(uint64_t max_stream_bytes, uint64_t max_records);
+int launch_lineop(int op, const uint8_t *in_a, uint64_t n_a, const uint8_t *in_b, uint64_t n_b, uint32_t lpr, uint32_t head, uint32_t x,
+                  uint32_t y, uint64_t rec_limit, uint8_t *out0, uint8_t *out1, uint64_t out_cap, void *work, uint64_t max_stream_bytes,
+                  uint64_t max_records, void *stats_tab, uint32_t h_cap, DevStats *st, int sm_count, void *stream, const char **err);
 // Per-sample compaction of a demultiplex result (sk_compact.cu)
 uint64_t compact_work_bytes(uint32_t max_rows, uint32_t S);
 int launch_compact(const ChunkRow *rows, const Group *groups, uint32_t n_rows, uint32_t S, const uint8_t *src, uint8_t *dst,

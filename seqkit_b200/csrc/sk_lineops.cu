@@ -1,0 +1,630 @@
+// sk_lineops.cu -- the line engine: record-boundary scan by global line table, and the record-shuffling
+// operators of SURVEY.md section 8(f) on top of it:
+//
+//   fasta trim --first/--last   fasta_trim.rs:24-47          LOP_TRIMFIX
+//   fasta check                 fasta_check.rs:49-70         LOP_CHECK
+//   fasta statistics            fasta_statistics.rs:13-52    LOP_STATS
+//   fasta interleave            fasta_interleave.rs:14-35    LOP_INTERLEAVE
+//   fasta deinterleave          fasta_deinterleave.rs:14-39  LOP_DEINTERLEAVE
+//   fasta extract dual umi      fasta_extract_dual_umi.rs:14-72  LOP_DUALUMI
+//
+// Every operator is a handful of bandwidth-bound kernels over the whole stream:
+//   nl_count / nl_bases / nl_fill   the north star's kernel (a): newline flags by SWAR, warp shuffles and a
+//                                   block scan give every 16 KiB block its newline count; one CTA turns the
+//                                   counts into block bases; the blocks write the line-start table.  Record
+//                                   i is lines [lpr*i, lpr*i + lpr) exactly as the reference's read_line
+//                                   calls see them (common.rs:106-112), whatever the record length.
+//   plan      one thread per record: validity, output length, failure kind (the first failing record wins)
+//   scan      exclusive prefix of the output lengths (sk_warp.cu: tile sum / scan kernels)
+//   emit      one warp per record: the record's pieces go to their place, 16 destination-aligned bytes per
+//             lane and step (warp_copy_piece), literals by lane 0
+// Framing is uniform per stream -- '@' files are 4 lines per record, '>' files 2 -- as decided by the stream's
+// first byte; a record that starts with the other character is reported as SK_DATA_MIXED_FORMAT (the
+// reference decides per record).  Streams are ASCII (F_NON_ASCII otherwise).
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <algorithm>
+
+#include "sk_internal.h"
+
+namespace sk {
+extern __shared__ __align__(128) unsigned char sk_smem[];
+}
+#include "sk_device.cuh"
+#include "sk_record.cuh"
+
+namespace sk {
+
+constexpr uint32_t NLB = 16384;  // bytes per block of the newline kernels (256 threads x 64 bytes)
+
+// ---- line table ------------------------------------------------------------------------------------
+// Newline flags of the 64 bytes of a thread: bit k <=> byte k is '\n'.  Bytes at or past n read as 0.
+__device__ __forceinline__ unsigned long long nl_bits64(const uint8_t *in, uint64_t pos, uint64_t n, uint32_t &hib) {
+    unsigned long long m = 0;
+    if (pos + 64 <= n) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const uint4 v = *(const uint4 *)(in + pos + 16 * q);
+            hib |= v.x | v.y | v.z | v.w;
+            m |= (unsigned long long)nl_map_nat(v) << (16 * q);
+        }
+    } else {
+        for (uint32_t k = 0; k < 64 && pos + k < n; k++) {
+            const uint8_t c = in[pos + k];
+            hib |= c;
+            if (c == '\n') m |= 1ull << k;
+        }
+    }
+    return m;
+}
+template <int NT>
+__device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t *scratch, uint32_t &total) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) scratch[w] = x;
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (int k = 0; k < NT / 32; k++) {
+        const uint32_t t = scratch[k];
+        if (k < w) before += t;
+        all += t;
+    }
+    total = all;
+    return before + x - v;
+}
+__global__ void __launch_bounds__(256) sk_nl_count_kernel(const uint8_t *__restrict__ in, uint64_t n, uint32_t *__restrict__ blk, DevStats *st) {
+    __shared__ uint32_t scratch[8];
+    const uint64_t pos = (uint64_t)blockIdx.x * NLB + 64ull * threadIdx.x;
+    uint32_t hib = 0;
+    const unsigned long long m = pos < n ? nl_bits64(in, pos, n, hib) : 0ull;
+    if (hib & 0x80808080u) atomicOr(&st->flags, F_NON_ASCII);
+    uint32_t total;
+    block_excl_scan_u32<256>((uint32_t)__popcll(m), scratch, total);
+    if (threadIdx.x == 0) blk[blockIdx.x] = total;
+}
+// One CTA: blk[b] -> exclusive prefix; info = {n_lines, n_rec[lpr], ...}.  n_lines = newlines + 1 when the
+// stream does not end with '\n' (the reference's last read_line returns the unterminated rest).
+struct LineInfo {
+    uint32_t n_lines, n_rec, overflow, pad;
+};
+__global__ void __launch_bounds__(1024) sk_nl_bases_kernel(uint32_t *blk, uint32_t nb, const uint8_t *__restrict__ in, uint64_t n, uint32_t lpr,
+                                                           uint32_t *starts, uint32_t cap, LineInfo *info) {
+    __shared__ uint32_t scratch[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < nb; b0 += 1024u) {
+        const uint32_t b = b0 + threadIdx.x;
+        const uint32_t v = b < nb ? blk[b] : 0u;
+        uint32_t total;
+        const uint32_t ex = block_excl_scan_u32<1024>(v, scratch, total);
+        if (b < nb) blk[b] = carry + ex;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const uint32_t newlines = carry;
+        const uint32_t n_lines = newlines + ((n > 0 && in[n - 1] != '\n') ? 1u : 0u);
+        info->n_lines = n_lines;
+        info->n_rec = (n_lines + lpr - 1) / lpr;
+        info->overflow = n_lines + 1u > cap ? 1u : 0u;
+        info->pad = 0;
+        if (cap) starts[0] = 0;
+        if (n_lines < cap) starts[n_lines] = (uint32_t)n;  // sentinel: one past the last line
+    }
+}
+__global__ void __launch_bounds__(256) sk_nl_fill_kernel(const uint8_t *__restrict__ in, uint64_t n, const uint32_t *__restrict__ blk,
+                                                         uint32_t *__restrict__ starts, uint32_t cap) {
+    __shared__ uint32_t scratch[8];
+    const uint64_t pos = (uint64_t)blockIdx.x * NLB + 64ull * threadIdx.x;
+    uint32_t hib = 0;
+    unsigned long long m = pos < n ? nl_bits64(in, pos, n, hib) : 0ull;
+    uint32_t total;
+    uint32_t idx = blk[blockIdx.x] + block_excl_scan_u32<256>((uint32_t)__popcll(m), scratch, total);
+    while (m) {  // newline number idx (0-based) at pos + k starts line idx + 1 at pos + k + 1
+        const uint32_t k = (uint32_t)__ffsll((long long)m) - 1u;
+        m &= m - 1;
+        if (idx + 1u < cap) starts[idx + 1u] = (uint32_t)(pos + k + 1u);
+        idx++;
+    }
+}
+
+// ---- per-record views --------------------------------------------------------------------------------
+struct LStream {
+    const uint8_t *in;
+    uint64_t n;
+    const uint32_t *starts;
+    const LineInfo *info;
+};
+struct LineRef {
+    uint32_t s, len;
+};
+__device__ __forceinline__ LineRef line_of(const LStream &S, uint32_t k) {
+    LineRef r;
+    const uint32_t nl = S.info->n_lines;
+    if (k >= nl) {  // past the end: read_line left the string empty
+        r.s = (uint32_t)S.n;
+        r.len = 0;
+        return r;
+    }
+    r.s = S.starts[k];
+    r.len = S.starts[k + 1] - r.s;
+    return r;
+}
+__device__ __forceinline__ uint32_t trim_end_len_dev(const uint8_t *p, uint32_t len) {
+    while (len && is_ws(p[len - 1])) len--;
+    return len;
+}
+
+struct LParams {
+    int op;
+    LStream a, b;          // b: second input of interleave
+    uint32_t lpr;          // lines per record of stream a: 4 ('@') or 2 ('>')
+    uint32_t head;         // '@' or '>'
+    uint32_t x, y;         // trim: first, last; dual umi: first_bases; deinterleave: parity of the pass
+    uint64_t rec_limit;
+    uint32_t *out_len;     // [records]
+    uint64_t *dst;         // [records] exclusive prefix of out_len
+    uint8_t *out;
+    uint64_t out_cap;
+    DevStats *st;
+    // statistics
+    unsigned long long *h_keys, *h_rep;
+    uint32_t *h_cnt;
+    uint32_t h_mask;
+    uint32_t *bc_ref;      // [records] (off << 8 | len) of the record's barcode, 0xFFFFFFFF = none
+};
+
+enum : int { LOP_TRIMFIX = 0, LOP_CHECK = 1, LOP_STATS = 2, LOP_INTERLEAVE = 3, LOP_DEINTERLEAVE = 4, LOP_DUALUMI = 5 };
+// further data outcome kinds of the line operators (== SK_DATA_* in the header)
+enum : unsigned { K_NO_PLUS = 8, K_INCONSISTENT = 9, K_QUAL_SHORT = 10, K_HASH_COLLISION = 38 };
+
+// number of output units of the operator: records, or record pairs
+__device__ __forceinline__ uint32_t units_of(const LParams &p) {
+    const uint32_t nr = p.a.info->n_rec;
+    uint32_t u = (p.op == LOP_DEINTERLEAVE || p.op == LOP_DUALUMI) ? (nr + 1u) / 2u : nr;
+    if ((uint64_t)u > p.rec_limit) u = (uint32_t)p.rec_limit;
+    return u;
+}
+// header check of a record of stream a: 0 fine, else failure kind
+__device__ __forceinline__ unsigned head_kind(const LStream &S, LineRef h, uint32_t head) {
+    const uint32_t c = h.len ? S.in[h.s] : 0u;
+    if (c == head) return 0;
+    return (c == '@' || c == '>') ? K_MIXED : K_BAD_HEADER;
+}
+// bytes of record r of a stream (its lpr lines are contiguous)
+__device__ __forceinline__ LineRef record_of(const LStream &S, uint32_t r, uint32_t lpr) {
+    const LineRef a = line_of(S, r * lpr), e = line_of(S, r * lpr + lpr);
+    LineRef o;
+    o.s = a.s;
+    o.len = e.s - a.s;
+    return o;
+}
+
+// FNV-1a over the barcode bytes; bit 0 forced so that 0 marks an empty slot
+__device__ __forceinline__ unsigned long long fnv64(const uint8_t *p, uint32_t len) {
+    unsigned long long h = 1469598103934665603ull;
+    for (uint32_t i = 0; i < len; i++) h = (h ^ p[i]) * 1099511628211ull;
+    return h | 1ull;
+}
+__device__ __forceinline__ bool stat_class(uint8_t c) {  // [ACGTNacgtn] (fasta_statistics.rs:17: no '+')
+    switch (c) {
+        case 'A': case 'C': case 'G': case 'T': case 'N': case 'a': case 'c': case 'g': case 't': case 'n': return true;
+    }
+    return false;
+}
+
+// ---- plan --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sk_line_plan_kernel(const LParams p) {
+    if (p.a.info->overflow || (p.op == LOP_INTERLEAVE && p.b.info->overflow)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) report_err(p.st, 0, K_TOO_DENSE);
+        return;
+    }
+    const uint32_t nu = units_of(p);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nu; i += gridDim.x * blockDim.x) {
+        uint32_t olen = 0;
+        unsigned kind = 0;
+        const uint8_t *in = p.a.in;
+        if (p.op == LOP_TRIMFIX) {
+            const LineRef h = line_of(p.a, i * p.lpr);
+            kind = head_kind(p.a, h, p.head);
+            if (!kind) {
+                const LineRef sq = line_of(p.a, i * p.lpr + 1);
+                const uint32_t sl = trim_end_len_dev(in + sq.s, sq.len);              // seq.trim_end().len()  (:31)
+                const bool cut = (uint64_t)p.x + p.y < sl;                            // :32
+                const uint32_t L = cut ? sl - p.x - p.y : 0u;
+                olen = h.len + L + 1u;                                                // :33 / :35
+                if (p.lpr == 4) {
+                    const LineRef ql = line_of(p.a, i * p.lpr + 3);
+                    if (cut && ql.len < sl - p.y) kind = K_QUAL_SHORT;                // &qual[..] out of range (:41): panic
+                    olen += 2u + L + 1u;                                              // "+\n" qual "\n"  (:41 / :43)
+                }
+            }
+        } else if (p.op == LOP_CHECK) {
+            const LineRef h = line_of(p.a, i * p.lpr);
+            kind = head_kind(p.a, h, p.head);
+            if (!kind && p.lpr == 4) {
+                const LineRef pl = line_of(p.a, i * p.lpr + 2);
+                if (!(pl.len && in[pl.s] == '+')) kind = K_NO_PLUS;                   // fasta_check.rs:58-61
+            }
+        } else if (p.op == LOP_STATS) {
+            const LineRef h = line_of(p.a, i * p.lpr);
+            uint32_t ref = 0xFFFFFFFFu;
+            // leftmost " BC:" followed by at least one class byte; the run extends while in class (:17,:25-28)
+            for (uint32_t k = 0; k + 5 <= h.len; k++) {
+                const uint8_t *q = in + h.s + k;
+                if (q[0] == ' ' && q[1] == 'B' && q[2] == 'C' && q[3] == ':' && stat_class(q[4])) {
+                    uint32_t e = k + 5;
+                    while (e < h.len && stat_class(in[h.s + e])) e++;
+                    const uint32_t off = h.s + k + 4, len = e - k - 4;
+                    // one slot per distinct hash; count and the earliest occurrence (the representative) by atomics
+                    const unsigned long long key = fnv64(in + off, len);
+                    uint32_t slot = (uint32_t)(key >> 17) & p.h_mask;
+                    for (;;) {
+                        const unsigned long long old = atomicCAS(&p.h_keys[slot], 0ull, key);
+                        if (old == 0ull || old == key) break;
+                        slot = (slot + 1u) & p.h_mask;
+                    }
+                    atomicAdd(&p.h_cnt[slot], 1u);
+                    atomicMin(&p.h_rep[slot], ((unsigned long long)off << 32) | len);
+                    ref = slot;
+                    break;
+                }
+            }
+            p.bc_ref[i] = ref;
+            kind = head_kind(p.a, h, p.head);  // the header is validated after the search (:31-37)
+        } else if (p.op == LOP_INTERLEAVE) {
+            const LineRef h = line_of(p.a, i * p.lpr);
+            kind = head_kind(p.a, h, p.head);
+            if (!kind) {
+                const LineRef h2 = line_of(p.b, i * p.lpr);
+                const uint32_t c2 = h2.len ? p.b.in[h2.s] : 0u;
+                if (c2 != p.head) kind = K_INCONSISTENT;                              // fasta_interleave.rs:26-29
+                olen = record_of(p.a, i, p.lpr).len + record_of(p.b, i, p.lpr).len;
+            }
+        } else if (p.op == LOP_DEINTERLEAVE) {
+            const LineRef h = line_of(p.a, 2u * i * p.lpr);
+            kind = head_kind(p.a, h, p.head);
+            if (!kind) {
+                const LineRef h2 = line_of(p.a, (2u * i + 1u) * p.lpr);
+                const uint32_t c2 = h2.len ? in[h2.s] : 0u;
+                if (c2 != p.head) kind = K_INCONSISTENT;                              // fasta_deinterleave.rs:30-33
+                olen = record_of(p.a, 2u * i + p.x, p.lpr).len;                        // pass x = 0: mate 1, 1: mate 2
+            }
+        } else {  // LOP_DUALUMI (fasta_extract_dual_umi.rs:27-70)
+            const uint32_t r1 = 2u * i, r2 = 2u * i + 1u, N = p.x;
+            const LineRef h1 = line_of(p.a, r1 * p.lpr);
+            kind = head_kind(p.a, h1, p.head);
+            if (!kind) {
+                const LineRef h2 = line_of(p.a, r2 * p.lpr);
+                const uint32_t c2 = h2.len ? in[h2.s] : 0u;
+                const LineRef s1 = line_of(p.a, r1 * p.lpr + 1), s2 = line_of(p.a, r2 * p.lpr + 1);
+                if (c2 != p.head) {
+                    kind = K_INCONSISTENT;                                            // :42-44 / :50-52
+                } else if (N > s1.len || N > s2.len) {
+                    kind = K_SEQ_SHORT;                                               // &seq_1[0..N] out of range: panic (:55,:57)
+                } else {
+                    const uint32_t t1 = trim_end_len_dev(in + h1.s, h1.len), t2 = trim_end_len_dev(in + h2.s, h2.len);
+                    const uint32_t umi = 2u * N + 1u;
+                    olen = t1 + 4u + umi + 1u + (s1.len - N) + t2 + 4u + umi + 1u + (s2.len - N);
+                    if (p.lpr == 4) {
+                        const LineRef q1 = line_of(p.a, r1 * p.lpr + 3), q2 = line_of(p.a, r2 * p.lpr + 3);
+                        if (N > q1.len || N > q2.len) kind = K_QUAL_SHORT;            // &qual_1[N..] out of range: panic (:62,:64)
+                        olen += 2u + (q1.len - N) + 2u + (q2.len - N);
+                    }
+                }
+            }
+        }
+        if (kind) {
+            report_err(p.st, i, kind);
+            olen = 0;
+        }
+        if (p.out_len) p.out_len[i] = olen;
+    }
+}
+
+// statistics, second pass: every record's bytes against the representative of its slot (a 64-bit collision
+// between different barcodes is reported, never merged)
+__global__ void __launch_bounds__(256) sk_stats_verify_kernel(const LParams p) {
+    const uint32_t nu = units_of(p);
+    const uint8_t *in = p.a.in;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nu; i += gridDim.x * blockDim.x) {
+        const uint32_t slot = p.bc_ref[i];
+        if (slot == 0xFFFFFFFFu) continue;
+        const LineRef h = line_of(p.a, i * p.lpr);
+        // locate the barcode again (cheap) and compare with the representative
+        for (uint32_t k = 0; k + 5 <= h.len; k++) {
+            const uint8_t *q = in + h.s + k;
+            if (q[0] == ' ' && q[1] == 'B' && q[2] == 'C' && q[3] == ':' && stat_class(q[4])) {
+                uint32_t e = k + 5;
+                while (e < h.len && stat_class(in[h.s + e])) e++;
+                const uint32_t off = h.s + k + 4, len = e - k - 4;
+                const unsigned long long rep = p.h_rep[slot];
+                const uint32_t roff = (uint32_t)(rep >> 32), rlen = (uint32_t)rep;
+                bool same = rlen == len;
+                for (uint32_t t = 0; same && t < len; t++) same = in[off + t] == in[roff + t];
+                if (!same) report_err(p.st, i, K_HASH_COLLISION);
+                break;
+            }
+        }
+    }
+}
+// statistics, third pass: the table's entries as a dense list {rep, count}
+__global__ void __launch_bounds__(256) sk_stats_list_kernel(const unsigned long long *keys, const unsigned long long *rep, const uint32_t *cnt,
+                                                            uint32_t cap, unsigned long long *list, uint32_t *n_list) {
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += gridDim.x * blockDim.x)
+        if (keys[s]) {
+            const uint32_t k = atomicAdd(n_list, 1u);
+            list[2 * k] = rep[s];
+            list[2 * k + 1] = cnt[s];
+        }
+}
+
+// ---- finish: records before the first failure are the output -------------------------------------------
+__global__ void sk_line_finish_kernel(const LParams p, int which_out) {
+    const uint32_t nu = units_of(p);
+    uint32_t lim = nu;
+    if (p.st->err_key) {
+        const unsigned long long k = ~p.st->err_key;
+        const unsigned long long rec = k >> 8;
+        if (rec < lim) lim = (uint32_t)rec;
+    }
+    unsigned long long bytes = 0;
+    if (lim && p.out_len) bytes = p.dst[lim - 1] + p.out_len[lim - 1];
+    p.st->n_records = lim;
+    p.st->n_lines = p.a.info->n_lines;
+    if (which_out == 0) {
+        p.st->out_bytes = bytes;
+        p.st->out_extent = bytes;
+    } else {
+        p.st->compact_extent = bytes;  // second output stream (deinterleave): length parked here
+    }
+    // bytes of stream a covered by the processed records
+    const uint32_t per = (p.op == LOP_DEINTERLEAVE || p.op == LOP_DUALUMI) ? 2u * p.lpr : p.lpr;
+    p.st->consumed = line_of(p.a, lim * per).s;
+    if (bytes > p.out_cap) report_err(p.st, 0, K_OUT_OVERFLOW);
+}
+
+// ---- emit --------------------------------------------------------------------------------------------
+__device__ __forceinline__ void put_lit(uint8_t *dst, unsigned long long at, const char *lit, uint32_t n, int lane) {
+    if ((uint32_t)lane < n) dst[at + lane] = (uint8_t)lit[lane];
+}
+__global__ void __launch_bounds__(256) sk_line_emit_kernel(const LParams p) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t wpb = blockDim.x >> 5, gw = blockIdx.x * wpb + (threadIdx.x >> 5), nw = gridDim.x * wpb;
+    uint32_t lim = units_of(p);
+    if (p.st->err_key) {
+        const unsigned long long rec = (~p.st->err_key) >> 8;
+        if (rec < lim) lim = (uint32_t)rec;
+    }
+    if (lim && p.dst[lim - 1] + p.out_len[lim - 1] > p.out_cap) return;  // K_OUT_OVERFLOW (finish kernel)
+    const uint8_t *in = p.a.in;
+    uint8_t *out = p.out;
+    for (uint32_t i = gw; i < lim; i += nw) {
+        unsigned long long d = p.dst[i];
+        if (p.op == LOP_TRIMFIX) {
+            const LineRef h = line_of(p.a, i * p.lpr), sq = line_of(p.a, i * p.lpr + 1);
+            const uint32_t sl = trim_end_len_dev(in + sq.s, sq.len);
+            const bool cut = (uint64_t)p.x + p.y < sl;
+            const uint32_t L = cut ? sl - p.x - p.y : 0u;
+            warp_copy_piece(in, out, h.s, d, h.len, lane);
+            d += h.len;
+            if (L) warp_copy_piece(in, out, sq.s + p.x, d, L, lane);
+            d += L;
+            if (p.lpr == 4) {
+                const LineRef ql = line_of(p.a, i * p.lpr + 3);
+                put_lit(out, d, "\n+\n", 3, lane);
+                d += 3;
+                if (L) warp_copy_piece(in, out, ql.s + p.x, d, L, lane);
+                d += L;
+            }
+            put_lit(out, d, "\n", 1, lane);
+        } else if (p.op == LOP_INTERLEAVE) {
+            const LineRef r1 = record_of(p.a, i, p.lpr), r2 = record_of(p.b, i, p.lpr);
+            if (r1.len) warp_copy_piece(in, out, r1.s, d, r1.len, lane);
+            if (r2.len) warp_copy_piece(p.b.in, out, r2.s, d + r1.len, r2.len, lane);
+        } else if (p.op == LOP_DEINTERLEAVE) {
+            const LineRef r = record_of(p.a, 2u * i + p.x, p.lpr);
+            if (r.len) warp_copy_piece(in, out, r.s, d, r.len, lane);
+        } else if (p.op == LOP_DUALUMI) {
+            const uint32_t N = p.x;
+            for (uint32_t m = 0; m < 2; m++) {
+                const uint32_t r = 2u * i + m;
+                const LineRef h = line_of(p.a, r * p.lpr), sq = line_of(p.a, r * p.lpr + 1);
+                const LineRef s1 = line_of(p.a, 2u * i * p.lpr + 1), s2 = line_of(p.a, (2u * i + 1u) * p.lpr + 1);
+                const uint32_t t = trim_end_len_dev(in + h.s, h.len);
+                if (t) warp_copy_piece(in, out, h.s, d, t, lane);               // header.trim_end()
+                d += t;
+                put_lit(out, d, " RX:", 4, lane);
+                d += 4;
+                if (N) warp_copy_piece(in, out, s1.s, d, N, lane);              // umi = seq_1[0..N] "+" seq_2[0..N]
+                d += N;
+                put_lit(out, d, "+", 1, lane);
+                d += 1;
+                if (N) warp_copy_piece(in, out, s2.s, d, N, lane);
+                d += N;
+                put_lit(out, d, "\n", 1, lane);
+                d += 1;
+                if (sq.len > N) warp_copy_piece(in, out, sq.s + N, d, sq.len - N, lane);   // &seq[N..] with its newline
+                d += sq.len - N;
+                if (p.lpr == 4) {
+                    const LineRef ql = line_of(p.a, r * p.lpr + 3);
+                    put_lit(out, d, "+\n", 2, lane);
+                    d += 2;
+                    if (ql.len > N) warp_copy_piece(in, out, ql.s + N, d, ql.len - N, lane);
+                    d += ql.len - N;
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side of the launch sequences (called from sk_api.cu)
+// ------------------------------------------------------------------------------------------------
+// dst[i] = sum of len[0..i): sums of blocks of 1024, one CTA over the block sums, then every block adds its base
+__global__ void __launch_bounds__(1024) sk_len_sum_kernel(const uint32_t *__restrict__ len, unsigned long long *__restrict__ bsum, uint32_t n) {
+    __shared__ uint32_t scratch[32];
+    const uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+    uint32_t total;
+    block_excl_scan_u32<1024>(i < n ? len[i] : 0u, scratch, total);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = total;
+}
+__global__ void __launch_bounds__(1024) sk_len_bases_kernel(unsigned long long *bsum, uint32_t nb) {
+    __shared__ unsigned long long ws[32];
+    __shared__ unsigned long long carry;
+    const uint32_t lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (uint32_t b0 = 0; b0 < nb; b0 += 1024u) {
+        const uint32_t b = b0 + threadIdx.x;
+        const unsigned long long v = b < nb ? bsum[b] : 0ull;
+        unsigned long long x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+            if ((int)lane >= o) x += y;
+        }
+        if (lane == 31) ws[w] = x;
+        __syncthreads();
+        unsigned long long before = carry;
+        for (uint32_t k = 0; k < w; k++) before += ws[k];
+        if (b < nb) bsum[b] = before + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + x;
+        __syncthreads();
+    }
+}
+__global__ void __launch_bounds__(1024) sk_len_apply_kernel(const uint32_t *__restrict__ len, const unsigned long long *__restrict__ bsum,
+                                                            uint64_t *__restrict__ dst, uint32_t n) {
+    __shared__ uint32_t scratch[32];
+    const uint32_t i = blockIdx.x * 1024u + threadIdx.x;
+    uint32_t total;
+    const uint32_t ex = block_excl_scan_u32<1024>(i < n ? len[i] : 0u, scratch, total);
+    if (i < n) dst[i] = bsum[blockIdx.x] + ex;
+}
+static int launch_len_scan(const uint32_t *len, uint64_t *dst, uint32_t n, unsigned long long *bsum, cudaStream_t stream) {
+    if (!n) return 0;
+    const uint32_t nb = (n + 1023u) / 1024u;
+    sk_len_sum_kernel<<<nb, 1024, 0, stream>>>(len, bsum, n);
+    sk_len_bases_kernel<<<1, 1024, 0, stream>>>(bsum, nb);
+    sk_len_apply_kernel<<<nb, 1024, 0, stream>>>(len, bsum, dst, n);
+    return 3;
+}
+
+struct LineWork {
+    uint32_t *blk[2], *starts[2];
+    LineInfo *info[2];
+    uint32_t *out_len, *bc_ref;
+    uint64_t *dst;
+    unsigned long long *bsum;
+    uint32_t cap_lines;
+};
+static LineWork carve(void *work, uint64_t max_stream_bytes, uint64_t max_records) {
+    LineWork w;
+    uint8_t *q = (uint8_t *)work;
+    auto take = [&](uint64_t bytes) {
+        uint8_t *r = q;
+        q += (bytes + 255) & ~255ull;
+        return r;
+    };
+    const uint64_t nb = (max_stream_bytes + NLB - 1) / NLB + 2;
+    w.cap_lines = (uint32_t)std::min<uint64_t>(max_records * 4 + 64, 0xFFFFFFF0ull);
+    for (int k = 0; k < 2; k++) {
+        w.blk[k] = (uint32_t *)take(nb * 4);
+        w.starts[k] = (uint32_t *)take((uint64_t)w.cap_lines * 4);
+        w.info[k] = (LineInfo *)take(64);
+    }
+    w.out_len = (uint32_t *)take(max_records * 4);
+    w.dst = (uint64_t *)take(max_records * 8);
+    w.bc_ref = (uint32_t *)take(max_records * 4);
+    w.bsum = (unsigned long long *)take((max_records / 1024 + 2) * 8);
+    return w;
+}
+uint64_t lineops_work_bytes(uint64_t max_stream_bytes, uint64_t max_records) {
+    const uint64_t nb = (max_stream_bytes + NLB - 1) / NLB + 2;
+    const uint64_t cap_lines = std::min<uint64_t>(max_records * 4 + 64, 0xFFFFFFF0ull);
+    auto r = [](uint64_t b) { return (b + 255) & ~255ull; };
+    return 2 * (r(nb * 4) + r(cap_lines * 4) + r(64)) + r(max_records * 4) + r(max_records * 8) + r(max_records * 4) +
+           r((max_records / 1024 + 2) * 8) + 256;
+}
+
+static int index_lines(const uint8_t *in, uint64_t n, uint32_t lpr, const LineWork &w, int k, DevStats *st, cudaStream_t stream) {
+    const uint32_t nb = (uint32_t)((n + NLB - 1) / NLB);
+    if (nb) sk_nl_count_kernel<<<nb, 256, 0, stream>>>(in, n, w.blk[k], st);
+    sk_nl_bases_kernel<<<1, 1024, 0, stream>>>(w.blk[k], nb, in, n, lpr, w.starts[k], w.cap_lines, w.info[k]);
+    if (nb) sk_nl_fill_kernel<<<nb, 256, 0, stream>>>(in, n, w.blk[k], w.starts[k], w.cap_lines);
+    return nb ? 3 : 1;
+}
+
+// One line operator over the slot's streams.  stats table: keys / rep / cnt of `h_cap` slots, list of 2*h_cap u64.
+int launch_lineop(int op, const uint8_t *in_a, uint64_t n_a, const uint8_t *in_b, uint64_t n_b, uint32_t lpr, uint32_t head, uint32_t x,
+                  uint32_t y, uint64_t rec_limit, uint8_t *out0, uint8_t *out1, uint64_t out_cap, void *work, uint64_t max_stream_bytes,
+                  uint64_t max_records, void *stats_tab, uint32_t h_cap, DevStats *st, int sm_count, void *stream_, const char **err) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const LineWork w = carve(work, max_stream_bytes, max_records);
+    int launches = index_lines(in_a, n_a, lpr, w, 0, st, stream);
+    if (op == LOP_INTERLEAVE) launches += index_lines(in_b, n_b, lpr, w, 1, st, stream);
+    LParams p;
+    memset(&p, 0, sizeof p);
+    p.op = op;
+    p.a.in = in_a, p.a.n = n_a, p.a.starts = w.starts[0], p.a.info = w.info[0];
+    p.b.in = in_b, p.b.n = n_b, p.b.starts = w.starts[1], p.b.info = w.info[1];
+    p.lpr = lpr, p.head = head, p.x = x, p.y = y;
+    p.rec_limit = rec_limit ? rec_limit : ~0ull;
+    p.out_len = w.out_len, p.dst = w.dst, p.out = out0, p.out_cap = out_cap, p.st = st;
+    p.bc_ref = w.bc_ref;
+    const unsigned grid = (unsigned)std::max(1, sm_count * 8);
+    const uint32_t n_scan = (uint32_t)std::min<uint64_t>(max_records, 0xFFFFFFFFull);
+    if (op == LOP_STATS) {
+        unsigned long long *keys = (unsigned long long *)stats_tab, *rep = keys + h_cap;
+        uint32_t *cnt = (uint32_t *)(rep + h_cap);
+        unsigned long long *list = (unsigned long long *)(cnt + h_cap);
+        uint32_t *n_list = (uint32_t *)(list + 2ull * h_cap);
+        cudaMemsetAsync(keys, 0, (size_t)h_cap * 8, stream);
+        cudaMemsetAsync(rep, 0xFF, (size_t)h_cap * 8, stream);
+        cudaMemsetAsync(cnt, 0, (size_t)h_cap * 4, stream);
+        cudaMemsetAsync(n_list, 0, 4, stream);
+        p.h_keys = keys, p.h_rep = rep, p.h_cnt = cnt, p.h_mask = h_cap - 1u;
+        p.out_len = nullptr;
+        sk_line_plan_kernel<<<grid, 256, 0, stream>>>(p);
+        sk_stats_verify_kernel<<<grid, 256, 0, stream>>>(p);
+        sk_line_finish_kernel<<<1, 1, 0, stream>>>(p, 0);
+        sk_stats_list_kernel<<<grid, 256, 0, stream>>>(keys, rep, cnt, h_cap, list, n_list);
+        launches += 4;
+    } else if (op == LOP_CHECK) {
+        p.out_len = nullptr;
+        sk_line_plan_kernel<<<grid, 256, 0, stream>>>(p);
+        sk_line_finish_kernel<<<1, 1, 0, stream>>>(p, 0);
+        launches += 2;
+    } else {
+        const int passes = op == LOP_DEINTERLEAVE ? 2 : 1;
+        for (int pass = 0; pass < passes; pass++) {
+            if (op == LOP_DEINTERLEAVE) {
+                p.x = (uint32_t)pass;
+                p.out = pass == 0 ? out0 : out1;
+            }
+            sk_line_plan_kernel<<<grid, 256, 0, stream>>>(p);
+            launches += 1 + launch_len_scan(w.out_len, w.dst, n_scan, w.bsum, stream);
+            sk_line_finish_kernel<<<1, 1, 0, stream>>>(p, pass);
+            sk_line_emit_kernel<<<grid, 256, 0, stream>>>(p);
+            launches += 2;
+        }
+    }
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        *err = cudaGetErrorString(e);
+        return -1;
+    }
+    return launches;
+}
+
+}  // namespace sk

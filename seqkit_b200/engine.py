@@ -39,9 +39,11 @@ def _check(ctx, rc, what):
 
 class Engine:
     def __init__(self, device: int = 0, max_stream_bytes: int = 32 << 20, max_records: int = 1 << 19,
-                 n_slots: int = 1, max_samples: int = 1024, aux_streams: bool = True, compact: bool = True):
+                 n_slots: int = 1, max_samples: int = 1024, aux_streams: bool = True, compact: bool = True,
+                 line_ops: bool = False):
         self.lib = L.lib()
-        lim = L.Limits(max_stream_bytes, max_records, n_slots, max_samples, 1 if aux_streams else 0, 0)
+        lim = L.Limits(max_stream_bytes, max_records, n_slots, max_samples, 1 if aux_streams else 0,
+                       0x200 if line_ops else 0)
         ctx = C.c_void_p()
         rc = self.lib.sk_ctx_create(device, C.byref(lim), C.byref(ctx))
         if rc != 0:
@@ -364,6 +366,29 @@ class Engine:
                    % (ident, total, pct))  # :263-264
         R["stderr"] = b"".join(err)
         return R
+
+    # ------------------------------------------------------------------ the line engine
+    def line_op(self, op: int, a: bytes, b: bytes | None = None, x: int = 0, y: int = 0):
+        """Raw call of one line operator (sk_line_op): returns (sk_result, output 0, output 1).  The reference's
+        messages for the failing outcomes are composed by the `fasta` binary (seqkit_b200/host/fasta_main.cpp);
+        tests/test_gpu_lineops.py compares that binary with the oracle's CLI."""
+        self.upload(L.IN_R1, a)
+        self.upload(L.IN_R2, b)
+        _check(self.ctx, self.lib.sk_line_op(self.ctx, 0, op, x, y, 0), "sk_line_op")
+        res = self.wait()
+        self._refuse(res)
+        out0 = self.fetch_out(0, res.out_bytes[0])
+        out1 = self.fetch_out(1, res.out_bytes[1]) if op == L.LOP_DEINTERLEAVE else b""
+        return res, out0, out1
+
+    def statistics(self, data: bytes):
+        """fasta statistics (fasta_statistics.rs:13-52): (total records, {barcode: count}) of a well-formed file."""
+        res, _, _ = self.line_op(L.LOP_STATS, data)
+        n = C.c_uint32()
+        self.lib.sk_download_stats(self.ctx, 0, None, 0, C.byref(n))
+        ents = (L.StatEntry * max(n.value, 1))()
+        _check(self.ctx, self.lib.sk_download_stats(self.ctx, 0, ents, n.value, C.byref(n)), "sk_download_stats")
+        return res, {data[e.off:e.off + e.len]: e.count for e in ents[:n.value]}
 
     # ------------------------------------------------------------------ synthetic workloads (bench / tests)
     def synth(self, which: int, n_pairs: int, seed: int = 1, first_pair: int = 0, read_len: int = 150, mate: int = 1,

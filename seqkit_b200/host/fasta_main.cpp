@@ -491,7 +491,7 @@ struct Gpu {
     int lanes() const { return G * NSLOT; }
     sk_ctx *c(int lane) const { return ctxs[(size_t)(lane % G)]; }
     uint32_t slot(int lane) const { return (uint32_t)(lane / G); }
-    void create(uint32_t max_samples, bool aux, int n_out) {
+    void create(uint32_t max_samples, bool aux, int n_out, bool line_ops = false) {
         // 16 MiB batches: page-locking host memory is the slowest part of start-up (a few ms per MiB), and the
         // kernels lose nothing at this size
         uint64_t mb = 16;
@@ -515,6 +515,7 @@ struct Gpu {
         lim.n_slots = NSLOT;
         lim.max_samples = max_samples;
         lim.aux_streams = aux ? 1 : 0;
+        lim.reserved = line_ops ? 0x200u : 0u;
         for (int d : devs) {
             sk_ctx *x = nullptr;
             int rc = sk_ctx_create(d, &lim, &x);
@@ -1305,6 +1306,281 @@ static int run_demultiplex(int argc, char **argv) {
     return 0;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// trim --first/--last, check, statistics, interleave, deinterleave, extract dual umi
+// (fasta_trim.rs, fasta_check.rs, fasta_statistics.rs, fasta_interleave.rs, fasta_deinterleave.rs,
+// fasta_extract_dual_umi.rs) on the line engine (sk_line_op)
+// ------------------------------------------------------------------------------------------------
+static const char *USAGE_TRIMFIX =
+    "\nUsage:\n  fasta trim [options] <fastq_file>\n\nOptions:\n"
+    "  --first=N          Remove first N bases of each read [default: 0].\n"
+    "  --last=N           Remove last N bases of each read [default: 0].\n";
+static const char *USAGE_CHECK =
+    "\nUsage:\n  fasta check <fasta/fastq>\n\nDescription:\nChecks that the input FASTA or FASTQ file is correctly formatted, and reports\n"
+    "the line number if any malformatted lines are found.\n";
+static const char *USAGE_STATS = "\nUsage:\n  fasta statistics <fastq_file>\n";
+static const char *USAGE_INTERLEAVE = "\nUsage:\n  fasta interleave <fastq_1> <fastq_2>\n";
+static const char *USAGE_DEINTERLEAVE = "\nUsage:\n  fasta deinterleave <interleaved_fastq> <out_prefix>\n";
+static const char *USAGE_DUALUMI =
+    "\nUsage:\n  fasta extract dual umi [options] <interleaved_fastq>\n\nOptions:\n"
+    "  --first-bases=N   First N bases of read contain UMI bases [default: 0]\n";
+
+// usize::from_str: optional '+', decimal digits
+static bool parse_usize(const char *s, uint64_t *v) {
+    if (*s == '+') s++;
+    if (!*s) return false;
+    uint64_t x = 0;
+    for (; *s; s++) {
+        if (*s < '0' || *s > '9') return false;
+        if (x > (~0ull - 9) / 10) return false;
+        x = x * 10 + (uint64_t)(*s - '0');
+    }
+    *v = x;
+    return true;
+}
+// bytes [0, e) of d that hold the next `lines` lines from offset `from` (fewer at the end of the data)
+static size_t skip_lines(const uint8_t *d, size_t n, size_t from, unsigned lines) {
+    size_t p = from;
+    for (unsigned k = 0; k < lines && p < n; k++) {
+        const uint8_t *nl = (const uint8_t *)memchr(d + p, '\n', n - p);
+        p = nl ? (size_t)(nl - d) + 1 : n;
+    }
+    return p;
+}
+
+static int run_line_op(uint32_t op, const Input &in_a, const Input &in_b, uint64_t x, uint64_t y, const std::string &out_prefix) {
+    const bool two_out = op == SK_LOP_DEINTERLEAVE, two_in = op == SK_LOP_INTERLEAVE;
+    const bool pairs = op == SK_LOP_DEINTERLEAVE || op == SK_LOP_DUAL_UMI;
+    Sink *gz[2] = {nullptr, nullptr};
+    if (two_out) {  // GzipWriter::with_method creates both files before anything is read (fasta_deinterleave.rs:17-20)
+        const bool child_gzip = getenv("SK_GZIP") && strcmp(getenv("SK_GZIP"), "child") == 0;
+        for (int m = 0; m < 2; m++) {
+            const std::string path = out_prefix + (m == 0 ? "_1.fq.gz" : "_2.fq.gz");
+            if (child_gzip) {
+                ChildSink *k = new ChildSink();
+                k->open_path(path, false);
+                gz[m] = k;
+            } else {
+                DeflateSink *k = new DeflateSink();
+                k->open_path(path);
+                gz[m] = k;
+            }
+        }
+    }
+    Gpu g;
+    g.create(0, false, two_out ? 2 : 1, true);
+    Stream sa, sb;
+    sa.in = in_a;
+    g.init_stream(sa, "");
+    if (two_in) {
+        sb.in = in_b;
+        g.init_stream(sb, "");
+    }
+    const int NL = g.lanes();
+    std::vector<Batch> batches((size_t)NL);
+    bool first = true;
+    unsigned lpr = 4;        // lines per record of the data: '@' 4, '>' 2
+    uint64_t total_records = 0;
+    std::unordered_map<std::string, uint64_t> barcodes;  // statistics
+    std::vector<sk_stat_entry> ents;
+    std::vector<std::string> tail_lines;  // check: the last ten lines before the current batch (fasta_check.rs:32-35)
+    uint64_t lines_before = 0;            // ... and their number
+
+    auto submit = [&](int lane) -> bool {
+        sk_ctx *xc = g.c(lane);
+        const uint32_t slot = g.slot(lane);
+        Batch &B = batches[(size_t)lane];
+        B = Batch();
+        sa.top_up();
+        if (first) {
+            first = false;
+            if (sa.fill && sa.buf()[0] == '>') lpr = 2;
+            const unsigned unit = pairs ? 2 * lpr : lpr;  // batches are cut at whole records (pairs)
+            for (Stream *st : {&sa, &sb}) {
+                if (!st->active) continue;
+                st->lpr = st == &sb ? lpr : unit;
+                st->rec_ends.clear();
+                st->scanned = 0;
+                st->lines_mod = 0;
+                st->top_up();
+            }
+        }
+        size_t n = std::min<size_t>(sa.avail(), g.max_records / 2);
+        if (n == 0) {
+            if (sa.drained()) return false;
+            refuse("a record does not fit in one batch (%llu bytes); raise SK_BATCH_MB", (unsigned long long)g.batch_bytes);
+        }
+        size_t nb = 0;
+        if (two_in) {  // the second file may run out early: the reference then fails at that record (:29-33)
+            sb.top_up();
+            nb = std::min(n, sb.avail());
+            if (nb < n && !sb.in.eof) n = nb;
+            if (n == 0) refuse("a record does not fit in one batch; raise SK_BATCH_MB");
+            nb = std::min(n, sb.avail());
+        }
+        B.live = true;
+        B.n = n;
+        B.first_record = sa.records_done;
+        B.bytes[SK_IN_R1] = sa.bytes_for(n);
+        B.src[SK_IN_R1] = sa.buf();
+        g.ck(xc, sk_upload(xc, slot, SK_IN_R1, B.src[SK_IN_R1], B.bytes[SK_IN_R1]), "sk_upload");
+        if (two_in) {
+            B.bytes[SK_IN_R2] = sb.bytes_for(nb);
+            B.src[SK_IN_R2] = sb.buf();
+            g.ck(xc, sk_upload(xc, slot, SK_IN_R2, B.src[SK_IN_R2], B.bytes[SK_IN_R2]), "sk_upload");
+        } else {
+            g.ck(xc, sk_set_input_len(xc, slot, SK_IN_R2, 0), "sk_set_input_len");
+        }
+        g.ck(xc, sk_line_op(xc, slot, op, (uint32_t)std::min<uint64_t>(x, 0xFFFFFFFFull), (uint32_t)std::min<uint64_t>(y, 0xFFFFFFFFull), 0),
+             "sk_line_op");
+        sa.consume(n, B.bytes[SK_IN_R1]);
+        if (two_in) {
+            if (nb) sb.consume(nb, B.bytes[SK_IN_R2]);
+            else sb.park();
+        }
+        return true;
+    };
+    auto complete = [&](int lane) {
+        sk_ctx *xc = g.c(lane);
+        const uint32_t slot = g.slot(lane);
+        Batch &B = batches[(size_t)lane];
+        sk_result r;
+        g.ck(xc, sk_wait(xc, slot, &r), "sk_wait");
+        refuse_status(r, B.first_record);
+        const uint8_t *d = B.src[SK_IN_R1];
+        const size_t nbytes = B.bytes[SK_IN_R1];
+        // output of the records before the failing one (all of them when nothing failed)
+        if (op == SK_LOP_TRIM || op == SK_LOP_INTERLEAVE || op == SK_LOP_DUAL_UMI) {
+            uint8_t *h = g.ensure_out(0, lane, r.out_bytes[0]);
+            if (r.out_bytes[0]) g.ck(xc, sk_download_out(xc, slot, 0, h, r.out_bytes[0]), "sk_download_out");
+            g.ck(xc, sk_wait(xc, slot, nullptr), "sk_wait");
+            write_all(1, h, r.out_bytes[0]);
+        } else if (op == SK_LOP_DEINTERLEAVE) {
+            for (int m = 0; m < 2; m++) {
+                uint8_t *h = g.ensure_out(m, lane, r.out_bytes[m]);
+                if (r.out_bytes[m]) g.ck(xc, sk_download_out(xc, slot, (uint32_t)m, h, r.out_bytes[m]), "sk_download_out");
+            }
+            g.ck(xc, sk_wait(xc, slot, nullptr), "sk_wait");
+            for (int m = 0; m < 2; m++) gz[m]->append(g.out_h[m][(size_t)lane], r.out_bytes[m]);
+        } else if (op == SK_LOP_STATS) {
+            uint32_t ne = 0;
+            sk_download_stats(xc, slot, nullptr, 0, &ne);
+            ents.resize(std::max<uint32_t>(ne, 1));
+            g.ck(xc, sk_download_stats(xc, slot, ents.data(), ne, &ne), "sk_download_stats");
+            for (uint32_t k = 0; k < ne; k++) barcodes[std::string((const char *)d + ents[k].off, ents[k].len)] += ents[k].count;
+        }
+        total_records += r.n_records;
+        const size_t off = (size_t)r.consumed[SK_IN_R1];  // where the failing record (pair) starts
+        const unsigned unit = pairs ? 2 * lpr : lpr;
+        if (r.status != SK_DATA_OK) {
+            const size_t hend = skip_lines(d, nbytes, off, 1);
+            const std::string hdr((const char *)d + off, hend - off);
+            switch (r.status) {
+                case SK_DATA_BAD_HEADER:
+                    if (op == SK_LOP_TRIM) fatal("Invalid FASTA/FASTQ format encountered.");                 // fasta_trim.rs:28-30
+                    if (op == SK_LOP_STATS) fatal("Invalid FASTQ header:\n%s", hdr.c_str());                 // fasta_statistics.rs:36-38
+                    if (op == SK_LOP_INTERLEAVE || op == SK_LOP_DEINTERLEAVE) fatal("Line is not FASTA/FASTQ format: %s", hdr.c_str());
+                    if (op == SK_LOP_DUAL_UMI) fatal("Header is not valid FASTA/FASTQ:\n%s", hdr.c_str());   // :33-35
+                    break;  // check: below
+                case SK_DATA_QUAL_SHORT:
+                    if (op == SK_LOP_TRIM) {  // the first print! of the record is out when &qual[..] panics (fasta_trim.rs:35,:44)
+                        const size_t s1 = skip_lines(d, nbytes, off, 2);
+                        const size_t sl = trim_end_len(d + hend, s1 - hend);
+                        write_all(1, d + off, hend - off);
+                        write_all(1, d + hend + x, sl - y - x);
+                        write_all(1, (const uint8_t *)"\n", 1);
+                    }
+                    panic101("byte index out of range of qual");
+                case SK_DATA_SEQ_SHORT: panic101("byte index out of range of seq (fasta_extract_dual_umi.rs:56-58)");
+                case SK_DATA_INCONSISTENT:
+                    if (op == SK_LOP_INTERLEAVE) {  // the record of <fastq_1> is out before <fastq_2>'s header is looked at (:24-29)
+                        write_all(1, d + off, skip_lines(d, nbytes, off, lpr) - off);
+                        fatal("Input files do not share a consistent format.");
+                    }
+                    if (op == SK_LOP_DEINTERLEAVE) {  // :26-35
+                        gz[0]->append(d + off, skip_lines(d, nbytes, off, lpr) - off);
+                        fatal("Interleaved FASTA records are not in consistent format.");
+                    }
+                    fatal(lpr == 4 ? "Invalid FASTQ record found in input file." : "Invalid FASTA record found in input file.");
+                default: break;
+            }
+            if (op == SK_LOP_CHECK) {  // fasta_check.rs:58-66: the line number and the last ten lines read
+                // lines of this batch up to and including the offending one
+                std::vector<std::string> hist = tail_lines;
+                uint64_t lines_read = lines_before;
+                const size_t upto = r.status == SK_DATA_NO_PLUS ? skip_lines(d, nbytes, off, 3) : hend;
+                for (size_t p = 0; p < upto;) {
+                    const size_t e = skip_lines(d, nbytes, p, 1);
+                    hist.push_back(std::string((const char *)d + p, e - p));
+                    if (hist.size() > 10) hist.erase(hist.begin());
+                    lines_read++;
+                    p = e;
+                }
+                std::string msg = r.status == SK_DATA_NO_PLUS ? "Missing quality header prefix '+'" : "Missing header prefix '>' or '@'";
+                msg += " on line " + std::to_string(lines_read) + ":\n";
+                for (auto &l : hist) msg += l + "\n";
+                msg += "\n";
+                fflush(stdout);
+                fputs("ERROR: ", stderr);
+                fwrite(msg.data(), 1, msg.size(), stderr);
+                fputc('\n', stderr);
+                finish(255);
+            }
+            fprintf(stderr, "seqkit_b200: unexpected data status %d\n", r.status);
+            finish(3);
+        }
+        if (op == SK_LOP_CHECK) {  // remember the batch's last ten lines
+            size_t p = nbytes, cnt = 0;
+            std::vector<std::string> last;
+            while (p > 0 && cnt < 10) {
+                size_t q = p - 1;  // start of the line that ends at p
+                while (q > 0 && d[q - 1] != '\n') q--;
+                last.insert(last.begin(), std::string((const char *)d + q, p - q));
+                p = q;
+                cnt++;
+            }
+            for (auto &l : last) {
+                tail_lines.push_back(l);
+                if (tail_lines.size() > 10) tail_lines.erase(tail_lines.begin());
+            }
+            lines_before += (uint64_t)r.n_lines[SK_IN_R1];
+        }
+        (void)unit;
+        B.live = false;
+    };
+
+    uint64_t submitted = 0, bi = 0;
+    bool more = true;
+    while (more && submitted < (uint64_t)NL) {
+        more = submit((int)(submitted % (uint64_t)NL));
+        if (more) submitted++;
+    }
+    while (bi < submitted) {
+        complete((int)(bi % (uint64_t)NL));
+        bi++;
+        if (more) {
+            more = submit((int)(submitted % (uint64_t)NL));
+            if (more) submitted++;
+        }
+    }
+    if (op == SK_LOP_STATS) {  // fasta_statistics.rs:43-52
+        printf("Total sequence records: %llu\n", (unsigned long long)total_records);
+        printf("Most frequent sample barcodes:\n");
+        fflush(stdout);
+        std::vector<std::pair<std::string, uint64_t>> entries(barcodes.begin(), barcodes.end());
+        // count descending; the reference leaves the order of equal counts to its HashMap: barcode descending here (and in the oracle)
+        std::sort(entries.begin(), entries.end(), [](const std::pair<std::string, uint64_t> &a, const std::pair<std::string, uint64_t> &b) {
+            if (a.second != b.second) return a.second > b.second;
+            return a.first > b.first;
+        });
+        if (entries.size() < 100) panic101("range end index 100 out of range for slice (fasta_statistics.rs:50)");
+        for (size_t q = 0; q < 100; q++) printf("- %s: %llu\n", entries[q].first.c_str(), (unsigned long long)entries[q].second);
+        fflush(stdout);
+    }
+    return 0;
+}
+
 // ------------------------------------------------------------------------------------------------
 // dispatcher (fasta_main.rs:42-82)
 // ------------------------------------------------------------------------------------------------
@@ -1332,6 +1608,48 @@ int main(int argc, char **argv) {
         in.open_path(argv[3]);
         bcin.open_path(argv[4]);
         rc = run_stream_op(OP_ADDBC, in, bcin, 0);
+    } else if (argc >= 2 && (is(1, "trim") || is(1, "check") || is(1, "statistics") || is(1, "interleave") || is(1, "deinterleave") ||
+                             (argc >= 4 && is(1, "extract") && is(2, "dual") && is(3, "umi")))) {
+        const bool umi = is(1, "extract");
+        const uint32_t op = is(1, "trim") ? SK_LOP_TRIM : is(1, "check") ? SK_LOP_CHECK : is(1, "statistics") ? SK_LOP_STATS
+                            : is(1, "interleave") ? SK_LOP_INTERLEAVE : is(1, "deinterleave") ? SK_LOP_DEINTERLEAVE : SK_LOP_DUAL_UMI;
+        const char *usage = op == SK_LOP_TRIM ? USAGE_TRIMFIX : op == SK_LOP_CHECK ? USAGE_CHECK : op == SK_LOP_STATS ? USAGE_STATS
+                            : op == SK_LOP_INTERLEAVE ? USAGE_INTERLEAVE : op == SK_LOP_DEINTERLEAVE ? USAGE_DEINTERLEAVE : USAGE_DUALUMI;
+        std::vector<std::string> pos;
+        std::string v_first = "0", v_last = "0", v_fb = "0";
+        for (int a = umi ? 4 : 2; a < argc; a++) {
+            const std::string s = argv[a];
+            auto opt = [&](const char *name, std::string &dst) -> bool {
+                const size_t k = strlen(name);
+                if (s.compare(0, k, name) != 0) return false;
+                if (s.size() > k && s[k] == '=') {
+                    dst = s.substr(k + 1);
+                    return true;
+                }
+                if (s.size() == k && a + 1 < argc) {
+                    dst = argv[++a];
+                    return true;
+                }
+                return false;
+            };
+            if (op == SK_LOP_TRIM && (opt("--first", v_first) || opt("--last", v_last))) continue;
+            if (op == SK_LOP_DUAL_UMI && opt("--first-bases", v_fb)) continue;
+            if (s.size() > 1 && s[0] == '-') invalid_args(usage);
+            pos.push_back(s);
+        }
+        const size_t want = (op == SK_LOP_INTERLEAVE || op == SK_LOP_DEINTERLEAVE) ? 2 : 1;
+        if (pos.size() != want) invalid_args(usage);
+        Input a, b;  // FileReader::new comes before the options are parsed (fasta_trim.rs:17-22)
+        a.open_path(pos[0]);
+        if (op == SK_LOP_INTERLEAVE) b.open_path(pos[1]);
+        uint64_t x = 0, y = 0;
+        if (op == SK_LOP_TRIM) {
+            if (!parse_usize(v_first.c_str(), &x)) fatal("N must be a non-negative integer in --first=N.");
+            if (!parse_usize(v_last.c_str(), &y)) fatal("N must be a non-negative integer in --last=N.");
+        } else if (op == SK_LOP_DUAL_UMI) {
+            if (!parse_usize(v_fb.c_str(), &x)) fatal("N must be a non-negative integer in --first-bases=N.");
+        }
+        rc = run_line_op(op, a, b, x, y, op == SK_LOP_DEINTERLEAVE ? pos[1] : std::string());
     } else if (argc >= 2 && is(1, "demultiplex")) {
         rc = run_demultiplex(argc, argv);
     } else {

@@ -226,3 +226,38 @@ def test_host_generator_shapes():
     b = O.synth_fastq(500, seed=5, first_pair=100, mate=2, barcodes=bcs)
     h1, h2 = lines[0:-1:4], b.split(b"\n")[0:-1:4]
     assert all(x.replace(b" 1:N", b" 2:N") == y for x, y in zip(h1, h2))  # mates share coordinates and barcode
+
+
+def test_next_row_operators_kats():
+    """Hand-derived expectations for the SURVEY 8(f) restatements (fasta_trim.rs, fasta_check.rs, fasta_statistics.rs,
+    fasta_interleave.rs, fasta_deinterleave.rs, fasta_extract_dual_umi.rs)."""
+    from oracle import pyoracle as O
+    fq = b"@r1 x\nACGTACGT\n+r1\nIIIIIIII\n@r2\nAC\n+\nII\n"
+    # trim: first+last < seq_len cuts both lines; otherwise both lines come out empty; '+' line normalised
+    assert O.next_op(0, fq, x=2, y=1)[:3] == (0, b"@r1 x\nGTACG\n+\nIIIII\n@r2\n\n+\n\n", b"")
+    assert O.next_op(0, b">s\nACGT\n", x=1)[:3] == (0, b">s\nCGT\n", b"")
+    assert O.next_op(0, b"x\nAC\n")[:3] == (255, b"", b"ERROR: Invalid FASTA/FASTQ format encountered.\n")
+    code, out, err, _ = O.next_op(0, b"@q\nACGTACGT\n+\nIII\n", x=1)  # &qual[1..8] on a 4-byte line: panic after the first print
+    assert code == 101 and out == b"@q\nCGTACGT\n" and err
+    # check: line number of the offending line and the (up to ten) lines read so far, each followed by a blank line
+    assert O.next_op(1, fq)[:3] == (0, b"", b"")
+    assert O.next_op(1, b"@r1\nAC\nX\nII\n")[:3] == (255, b"", b"ERROR: Missing quality header prefix '+' on line 3:\n@r1\n\nAC\n\nX\n\n\n\n")
+    assert O.next_op(1, b">s\nAC\nzz\n")[:3] == (255, b"", b"ERROR: Missing header prefix '>' or '@' on line 3:\n>s\n\nAC\n\nzz\n\n\n\n")
+    assert O.next_op(1, b"@r1\nAC\n")[2] == b"ERROR: Missing quality header prefix '+' on line 2:\n@r1\n\nAC\n\n\n\n"  # EOF: nothing more was read
+    # statistics: fewer than 100 distinct barcodes -> the two header lines, then the slice panic
+    code, out, err, _ = O.next_op(2, b"@a BC:ACGT+TT\nA\n+\nI\n>b BC:acgt\nA\n")
+    assert code == 101 and out == b"Total sequence records: 2\nMost frequent sample barcodes:\n"
+    many = b"".join(b"@r BC:%s\nA\n+\nI\n" % (bytes(b"ACGT"[(i >> s) & 3] for s in (0, 2, 4, 6))) * (1 + i % 3) for i in range(128))
+    code, out, err, _ = O.next_op(2, many)
+    lines = out.split(b"\n")
+    assert code == 0 and lines[0] == b"Total sequence records: 255" and len(lines) == 103
+    counts = [int(x.rsplit(b": ", 1)[1]) for x in lines[2:102]]
+    assert counts == sorted(counts, reverse=True) and counts[0] == 3
+    # interleave / deinterleave / extract dual umi
+    a, b = b"@a/1\nAC\n+\nII\n@b/1\nGG\n+\nII\n", b"@a/2\nTT\n+\nII\n@b/2\nCC\n+\nII\n"
+    il = O.next_op(3, a, b)
+    assert il[:3] == (0, b"@a/1\nAC\n+\nII\n@a/2\nTT\n+\nII\n@b/1\nGG\n+\nII\n@b/2\nCC\n+\nII\n", b"")
+    assert O.next_op(4, il[1]) == (0, a, b"", b)
+    assert O.next_op(3, a, b[:13])[:3] == (255, a[:13] + b[:13] + a[13:], b"ERROR: Input files do not share a consistent format.\n")
+    assert O.next_op(5, il[1], x=1)[1] == (b"@a/1 RX:A+T\nC\n+\nI\n@a/2 RX:A+T\nT\n+\nI\n@b/1 RX:G+C\nG\n+\nI\n@b/2 RX:G+C\nC\n+\nI\n")
+    assert O.next_op(5, a[:13], x=0)[:3] == (255, b"", b"ERROR: Invalid FASTQ record found in input file.\n")
