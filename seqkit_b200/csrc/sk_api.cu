@@ -70,6 +70,7 @@ struct Slot {
     // the request behind last_op, so that sk_wait can re-run it on the general engine
     bool used_fast = false;
     bool reran_general = false;
+    bool ran_line = false;  // trim / mask by quality ended up on the line engine (sk_lineops.cu)
     bool no_inplace = false;  // mask: the in-place layout was refused by the data (F_NEED_ORDERED), ordered form from now on
     uint32_t req_min_baseq = 0;
     uint64_t req_rec_limit = 0;
@@ -292,8 +293,9 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
         }
         if (lim->aux_streams)
             for (int i = 0; i < 2; i++) CKC(cudaMalloc(&s.scan_tab[i], R * sizeof(RecRef)));
-        if (lim->reserved & 0x200u) {  // line operators
-            CKC(cudaMalloc(&s.lwork, lineops_work_bytes(B, R)));
+        // the line engine's work area: the line operators (reserved bit 9), and trim / mask by quality as the last resort
+        CKC(cudaMalloc(&s.lwork, lineops_work_bytes(B, R)));
+        if (lim->reserved & 0x200u) {  // statistics table
             uint32_t cap = 1024;
             while ((uint64_t)cap < 2 * R && cap < (1u << 30)) cap <<= 1;
             s.h_cap = cap;
@@ -695,6 +697,7 @@ static int begin_op(sk_ctx *ctx, Slot *s, int op) {
     s->used_fast = false;
     s->launches = 0;
     s->want_compact = s->compacted = false;
+    s->ran_line = false;
     for (int i = 0; i < SK_N_INPUTS; i++) {
         s->pass_ran[i] = false;
         s->n_chunks[i] = 0;
@@ -864,8 +867,8 @@ extern "C" int sk_add_barcode(sk_ctx *ctx, uint32_t slot, uint64_t rec_limit) {
 extern "C" int sk_line_op(sk_ctx *ctx, uint32_t slot, uint32_t op, uint32_t x, uint32_t y, uint64_t rec_limit) {
     Slot *s = get_slot(ctx, slot);
     if (!s || op > 5) return SK_E_INVALID;
-    if (!s->lwork) {
-        ctx->err = "sk_line_op needs a context created with sk_limits.reserved bit 9 (0x200)";
+    if (op == 2 && !s->stats_tab) {
+        ctx->err = "SK_LOP_STATS needs a context created with sk_limits.reserved bit 9 (0x200)";
         return SK_E_INVALID;
     }
     int c = -1;
@@ -1131,6 +1134,37 @@ extern "C" int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res) {
             s->reran_general = true;
         }
     }
+    if ((s->last_op == OP_TRIM || s->last_op == OP_MASK) && !s->ran_line && s->lwork) {
+        // Last resort for trim / mask by quality: what neither chunk engine takes -- a record longer than the general
+        // engine's overhang, more records in a chunk than it has slots for, bytes >= 0x80 (UTF-8 in header or '+' lines
+        // is data like any other; in bases or qualities the batch is still refused) -- runs on the line engine, which
+        // frames records by a global line table and has no such limits.
+        unsigned fl = 0;
+        unsigned long long key = ~0ull;
+        for (int i = 0; i < SK_N_INPUTS; i++) {
+            fl |= s->stats_h[i].flags;
+            if (s->stats_h[i].err_key) key = std::min(key, ~s->stats_h[i].err_key);
+        }
+        const unsigned kind = key == ~0ull ? 0u : (unsigned)(key & 0xFFu);
+        if ((fl & F_NON_ASCII) || kind == K_TOO_LONG || kind == K_TOO_DENSE) {
+            const uint32_t before = s->launches;
+            CK(cudaMemsetAsync(s->stats, 0, sizeof(DevStats) * SK_N_INPUTS, s->stream));
+            const char *err = nullptr;
+            const int n = launch_lineop(s->last_op == OP_TRIM ? 6 : 7 /* LOP_TRIMQ / LOP_MASKQ */, s->in[SK_IN_R1], s->in_len[SK_IN_R1],
+                                        nullptr, 0, 4, '@', s->req_min_baseq, 0, s->req_rec_limit, s->out[0], s->out[1], s->out_cap,
+                                        s->lwork, ctx->lim.max_stream_bytes, ctx->lim.max_records, nullptr, 0, s->stats + SK_IN_R1,
+                                        ctx->sm_count, s->stream, &err);
+            if (n < 0) {
+                ctx->err = std::string("line engine launch failed: ") + (err ? err : "?");
+                return SK_E_CUDA;
+            }
+            s->launches = before + (uint32_t)n;
+            s->ran_line = true;
+            int rc = end_op(ctx, s);
+            if (rc) return rc;
+            CK(cudaStreamSynchronize(s->stream));
+        }
+    }
     if (!res) return SK_OK;
     memset(res, 0, sizeof *res);
     if (s->last_op < 0) return SK_OK;
@@ -1147,7 +1181,7 @@ extern "C" int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res) {
     if (h[SK_IN_R1].n_records >= 64 && h[SK_IN_R1].consumed)  // record size of this data, for the next tile choice
         ctx->rec_est = (double)h[SK_IN_R1].consumed / (double)h[SK_IN_R1].n_records;
     res->gpu_launches = s->launches;
-    res->reserved = (s->used_fast ? 1u : 0u) | (s->reran_general ? 2u : 0u) | (s->no_inplace ? 4u : 0u) | (s->compacted ? 8u : 0u);  // diagnostic: bit0 warp engine, bit1 re-run on the general engine, bit2 mask re-run in its ordered form
+    res->reserved = (s->used_fast ? 1u : 0u) | (s->reran_general ? 2u : 0u) | (s->no_inplace ? 4u : 0u) | (s->compacted ? 8u : 0u) | (s->ran_line ? 16u : 0u);  // diagnostic: bit0 warp engine, bit1 re-run on the general engine, bit2 mask re-run in its ordered form
     if (ctx->profiling)
         for (int i = 0; i < SK_N_INPUTS; i++)
             if (s->pass_ran[i]) cudaEventElapsedTime(&res->pass_ms[i], s->ev[i][0], s->ev[i][1]);

@@ -331,11 +331,8 @@ int launch_compact(const ChunkRow *rows, const Group *groups, uint32_t n_rows, u
     const unsigned want = (n_rows + 4u * MV_WARPS - 1u) / (4u * MV_WARPS);  // MV_WARPS warps x 4 rows per CTA and ticket
     const unsigned grid = std::max(1u, std::min<unsigned>((unsigned)sm_count * 3u, want));
     const int mv_smem = (int)(MV_WARPS * MV_WIN + MV_WARPS * 8 + 16);
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaFuncSetAttribute(sk_compact_move_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mv_smem);
-        attr_set = true;
-    }
+    // (a per-device attribute: set on every launch, the process may drive several GPUs)
+    cudaFuncSetAttribute(sk_compact_move_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mv_smem);
     cudaMemsetAsync(ticket, 0, 4, stream);
     sk_compact_move_kernel<<<grid, MV_WARPS * 32, mv_smem, stream>>>(rows, groups, n_rows, S, piece_dst, src, dst, slices, dst_cap, ticket);
     const cudaError_t e = cudaGetLastError();

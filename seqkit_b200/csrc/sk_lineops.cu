@@ -15,7 +15,7 @@
 //                                   i is lines [lpr*i, lpr*i + lpr) exactly as the reference's read_line
 //                                   calls see them (common.rs:106-112), whatever the record length.
 //   plan      one thread per record: validity, output length, failure kind (the first failing record wins)
-//   scan      exclusive prefix of the output lengths (sk_warp.cu: tile sum / scan kernels)
+//   scan      exclusive prefix of the output lengths (len_sum / len_bases / len_apply)
 //   emit      one warp per record: the record's pieces go to their place, 16 destination-aligned bytes per
 //             lane and step (warp_copy_piece), literals by lane 0
 // Framing is uniform per stream -- '@' files are 4 lines per record, '>' files 2 -- as decided by the stream's
@@ -39,6 +39,14 @@ namespace sk {
 constexpr uint32_t NLB = 16384;  // bytes per block of the newline kernels (256 threads x 64 bytes)
 
 // ---- line table ------------------------------------------------------------------------------------
+// newline map of a 16-byte piece in natural order, exact for every byte value (eq_flags; nl_map_nat is the 7-bit form)
+__device__ __forceinline__ uint32_t nl_map_exact(const uint4 v) {
+    const uint32_t zx = eq_flags(v.x, 0x0A0A0A0Au), zy = eq_flags(v.y, 0x0A0A0A0Au);
+    const uint32_t zz = eq_flags(v.z, 0x0A0A0A0Au), zw = eq_flags(v.w, 0x0A0A0A0Au);
+    const uint32_t lo = __dp4a(zx, 0x08040201u, __dp4a(zy, 0x80402010u, 0u));
+    const uint32_t hi = __dp4a(zz, 0x08040201u, __dp4a(zw, 0x80402010u, 0u));
+    return (lo >> 7) + hi * 2u;
+}
 // Newline flags of the 64 bytes of a thread: bit k <=> byte k is '\n'.  Bytes at or past n read as 0.
 __device__ __forceinline__ unsigned long long nl_bits64(const uint8_t *in, uint64_t pos, uint64_t n, uint32_t &hib) {
     unsigned long long m = 0;
@@ -47,7 +55,7 @@ __device__ __forceinline__ unsigned long long nl_bits64(const uint8_t *in, uint6
         for (int q = 0; q < 4; q++) {
             const uint4 v = *(const uint4 *)(in + pos + 16 * q);
             hib |= v.x | v.y | v.z | v.w;
-            m |= (unsigned long long)nl_map_nat(v) << (16 * q);
+            m |= (unsigned long long)nl_map_exact(v) << (16 * q);
         }
     } else {
         for (uint32_t k = 0; k < 64 && pos + k < n; k++) {
@@ -79,12 +87,18 @@ __device__ __forceinline__ uint32_t block_excl_scan_u32(uint32_t v, uint32_t *sc
     total = all;
     return before + x - v;
 }
-__global__ void __launch_bounds__(256) sk_nl_count_kernel(const uint8_t *__restrict__ in, uint64_t n, uint32_t *__restrict__ blk, DevStats *st) {
+// `high`: set when the stream holds a byte >= 0x80.  strict: that refuses the batch (F_NON_ASCII); otherwise the
+// operator's plan looks at the records one by one (UTF-8 in header and '+' lines is data like any other).
+__global__ void __launch_bounds__(256) sk_nl_count_kernel(const uint8_t *__restrict__ in, uint64_t n, uint32_t *__restrict__ blk, DevStats *st,
+                                                          uint32_t *high, int strict) {
     __shared__ uint32_t scratch[8];
     const uint64_t pos = (uint64_t)blockIdx.x * NLB + 64ull * threadIdx.x;
     uint32_t hib = 0;
     const unsigned long long m = pos < n ? nl_bits64(in, pos, n, hib) : 0ull;
-    if (hib & 0x80808080u) atomicOr(&st->flags, F_NON_ASCII);
+    if (hib & 0x80808080u) {
+        if (strict) atomicOr(&st->flags, F_NON_ASCII);
+        else *high = 1u;
+    }
     uint32_t total;
     block_excl_scan_u32<256>((uint32_t)__popcll(m), scratch, total);
     if (threadIdx.x == 0) blk[blockIdx.x] = total;
@@ -92,7 +106,7 @@ __global__ void __launch_bounds__(256) sk_nl_count_kernel(const uint8_t *__restr
 // One CTA: blk[b] -> exclusive prefix; info = {n_lines, n_rec[lpr], ...}.  n_lines = newlines + 1 when the
 // stream does not end with '\n' (the reference's last read_line returns the unterminated rest).
 struct LineInfo {
-    uint32_t n_lines, n_rec, overflow, pad;
+    uint32_t n_lines, n_rec, overflow, high;  // high: a byte >= 0x80 somewhere in the stream (non-strict operators)
 };
 __global__ void __launch_bounds__(1024) sk_nl_bases_kernel(uint32_t *blk, uint32_t nb, const uint8_t *__restrict__ in, uint64_t n, uint32_t lpr,
                                                            uint32_t *starts, uint32_t cap, LineInfo *info) {
@@ -116,7 +130,6 @@ __global__ void __launch_bounds__(1024) sk_nl_bases_kernel(uint32_t *blk, uint32
         info->n_lines = n_lines;
         info->n_rec = (n_lines + lpr - 1) / lpr;
         info->overflow = n_lines + 1u > cap ? 1u : 0u;
-        info->pad = 0;
         if (cap) starts[0] = 0;
         if (n_lines < cap) starts[n_lines] = (uint32_t)n;  // sentinel: one past the last line
     }
@@ -183,7 +196,10 @@ struct LParams {
     uint32_t *bc_ref;      // [records] (off << 8 | len) of the record's barcode, 0xFFFFFFFF = none
 };
 
-enum : int { LOP_TRIMFIX = 0, LOP_CHECK = 1, LOP_STATS = 2, LOP_INTERLEAVE = 3, LOP_DEINTERLEAVE = 4, LOP_DUALUMI = 5 };
+enum : int { LOP_TRIMFIX = 0, LOP_CHECK = 1, LOP_STATS = 2, LOP_INTERLEAVE = 3, LOP_DEINTERLEAVE = 4, LOP_DUALUMI = 5,
+             // trim / mask by quality on the line engine: the last resort behind the warp and the general engine, for
+             // records of any length and density and for UTF-8 in header and '+' lines (sk_api.cu: sk_wait)
+             LOP_TRIMQ = 6, LOP_MASKQ = 7 };
 // further data outcome kinds of the line operators (== SK_DATA_* in the header)
 enum : unsigned { K_NO_PLUS = 8, K_INCONSISTENT = 9, K_QUAL_SHORT = 10, K_HASH_COLLISION = 38 };
 
@@ -220,6 +236,37 @@ __device__ __forceinline__ bool stat_class(uint8_t c) {  // [ACGTNacgtn] (fasta_
         case 'A': case 'C': case 'G': case 'T': case 'N': case 'a': case 'c': case 'g': case 't': case 'n': return true;
     }
     return false;
+}
+
+// str::from_utf8 acceptance of a line (what BufRead::read_line enforces, common.rs:106-112)
+__device__ __forceinline__ bool utf8_ok(const uint8_t *s, uint32_t n) {
+    uint32_t i = 0;
+    while (i < n) {
+        const uint8_t c = s[i];
+        if (c < 0x80) {
+            i++;
+        } else if (c >= 0xC2 && c <= 0xDF) {
+            if (i + 1 >= n || (s[i + 1] & 0xC0) != 0x80) return false;
+            i += 2;
+        } else if (c >= 0xE0 && c <= 0xEF) {
+            if (i + 2 >= n) return false;
+            const uint8_t c1 = s[i + 1], c2 = s[i + 2];
+            if ((c1 & 0xC0) != 0x80 || (c2 & 0xC0) != 0x80) return false;
+            if (c == 0xE0 && c1 < 0xA0) return false;  // overlong
+            if (c == 0xED && c1 >= 0xA0) return false;  // surrogates
+            i += 3;
+        } else if (c >= 0xF0 && c <= 0xF4) {
+            if (i + 3 >= n) return false;
+            const uint8_t c1 = s[i + 1], c2 = s[i + 2], c3 = s[i + 3];
+            if ((c1 & 0xC0) != 0x80 || (c2 & 0xC0) != 0x80 || (c3 & 0xC0) != 0x80) return false;
+            if (c == 0xF0 && c1 < 0x90) return false;
+            if (c == 0xF4 && c1 >= 0x90) return false;
+            i += 4;
+        } else {
+            return false;
+        }
+    }
+    return true;
 }
 
 // ---- plan --------------------------------------------------------------------------------------------
@@ -298,6 +345,41 @@ __global__ void __launch_bounds__(256) sk_line_plan_kernel(const LParams p) {
                 const uint32_t c2 = h2.len ? in[h2.s] : 0u;
                 if (c2 != p.head) kind = K_INCONSISTENT;                              // fasta_deinterleave.rs:30-33
                 olen = record_of(p.a, 2u * i + p.x, p.lpr).len;                        // pass x = 0: mate 1, 1: mate 2
+            }
+        } else if (p.op == LOP_TRIMQ || p.op == LOP_MASKQ) {
+            const LineRef h = line_of(p.a, i * 4u), sq = line_of(p.a, i * 4u + 1u), pl = line_of(p.a, i * 4u + 2u), ql = line_of(p.a, i * 4u + 3u);
+            if (!(h.len && in[h.s] == '@')) kind = K_BAD_HEADER;  // fasta_trim_by_quality.rs:20-22, fasta_mask_by_quality.rs:21-23
+            if (!kind && p.a.info->high) {
+                // bytes >= 0x80: data like any other in the header and the '+' line when they are valid UTF-8 (read_line,
+                // common.rs:106-112); in the bases or qualities (char-wise zip, Unicode trim_end) the batch is refused
+                bool bad = !utf8_ok(in + h.s, h.len) || !utf8_ok(in + pl.s, pl.len);
+                for (uint32_t t = 0; t < sq.len; t++) bad = bad || in[sq.s + t] >= 0x80;
+                for (uint32_t t = 0; t < ql.len; t++) bad = bad || in[ql.s + t] >= 0x80;
+                if (bad) kind = K_NON_ASCII;
+            }
+            if (!kind && p.op == LOP_TRIMQ) {  // fasta_trim_by_quality.rs:28-48
+                const int minq = (int)p.x;
+                uint32_t k = trim_end_len_dev(in + ql.s, ql.len);  // :31
+                int total = -50, lowest = -50;                     // :28-29
+                uint32_t lowest_k = k;
+                while (k > 0) {                                    // :33-42
+                    k--;
+                    total += (int)(uint8_t)(in[ql.s + k] - 33u) - minq;  // wrapping u8 subtraction (:35)
+                    if (total > 0) break;
+                    if (total < lowest) {
+                        lowest = total;
+                        lowest_k = k;
+                    }
+                }
+                p.bc_ref[i] = lowest_k;
+                if (lowest_k == 0) olen = h.len + 6u;              // "N\n+\n!\n"  (:44-45)
+                else if (lowest_k > sq.len) kind = K_SEQ_SHORT;    // &seq[..k] panics (:47)
+                else olen = h.len + 2u * lowest_k + 4u;            // :47
+            } else if (!kind) {  // fasta_mask_by_quality.rs:32-45
+                const uint32_t sl = sq.len - ((sq.len && in[sq.s + sq.len - 1] == '\n') ? 1u : 0u);  // :32
+                const uint32_t qn = ql.len - ((ql.len && in[ql.s + ql.len - 1] == '\n') ? 1u : 0u);  // :33
+                if (sl != qn) kind = K_LEN_MISMATCH;                                                  // :35-37
+                else olen = h.len + 2u * sl + 4u;                                                     // :26,:44
             }
         } else {  // LOP_DUALUMI (fasta_extract_dual_umi.rs:27-70)
             const uint32_t r1 = 2u * i, r2 = 2u * i + 1u, N = p.x;
@@ -427,6 +509,29 @@ __global__ void __launch_bounds__(256) sk_line_emit_kernel(const LParams p) {
                 d += L;
             }
             put_lit(out, d, "\n", 1, lane);
+        } else if (p.op == LOP_TRIMQ) {
+            const LineRef h = line_of(p.a, i * 4u), sq = line_of(p.a, i * 4u + 1u), ql = line_of(p.a, i * 4u + 3u);
+            const uint32_t kk = p.bc_ref[i];
+            warp_copy_piece(in, out, h.s, d, h.len, lane);  // header verbatim (:23)
+            d += h.len;
+            if (kk == 0) {
+                put_lit(out, d, "N\n+\n!\n", 6, lane);    // :44-45
+            } else {                                         // :47
+                warp_copy_piece(in, out, sq.s, d, kk, lane);
+                put_lit(out, d + kk, "\n+\n", 3, lane);
+                warp_copy_piece(in, out, ql.s, d + kk + 3u, kk, lane);
+                put_lit(out, d + 2ull * kk + 3u, "\n", 1, lane);
+            }
+        } else if (p.op == LOP_MASKQ) {
+            const LineRef h = line_of(p.a, i * 4u), sq = line_of(p.a, i * 4u + 1u), ql = line_of(p.a, i * 4u + 3u);
+            const uint32_t sl = sq.len - ((sq.len && in[sq.s + sq.len - 1] == '\n') ? 1u : 0u);
+            warp_copy_piece(in, out, h.s, d, h.len, lane);  // :26
+            d += h.len;
+            for (uint32_t t = (uint32_t)lane; t < sl; t += 32u)  // :40-43 (wrapping u8: bytes below '!' are never masked)
+                out[d + t] = (uint8_t)(in[ql.s + t] - 33u) < (uint8_t)p.x ? (uint8_t)'N' : in[sq.s + t];
+            put_lit(out, d + sl, "\n+\n", 3, lane);       // :44
+            if (sl) warp_copy_piece(in, out, ql.s, d + sl + 3u, sl, lane);
+            put_lit(out, d + 2ull * sl + 3u, "\n", 1, lane);
         } else if (p.op == LOP_INTERLEAVE) {
             const LineRef r1 = record_of(p.a, i, p.lpr), r2 = record_of(p.b, i, p.lpr);
             if (r1.len) warp_copy_piece(in, out, r1.s, d, r1.len, lane);
@@ -557,9 +662,10 @@ uint64_t lineops_work_bytes(uint64_t max_stream_bytes, uint64_t max_records) {
            r((max_records / 1024 + 2) * 8) + 256;
 }
 
-static int index_lines(const uint8_t *in, uint64_t n, uint32_t lpr, const LineWork &w, int k, DevStats *st, cudaStream_t stream) {
+static int index_lines(const uint8_t *in, uint64_t n, uint32_t lpr, const LineWork &w, int k, DevStats *st, int strict, cudaStream_t stream) {
     const uint32_t nb = (uint32_t)((n + NLB - 1) / NLB);
-    if (nb) sk_nl_count_kernel<<<nb, 256, 0, stream>>>(in, n, w.blk[k], st);
+    cudaMemsetAsync(&w.info[k]->high, 0, 4, stream);
+    if (nb) sk_nl_count_kernel<<<nb, 256, 0, stream>>>(in, n, w.blk[k], st, &w.info[k]->high, strict);
     sk_nl_bases_kernel<<<1, 1024, 0, stream>>>(w.blk[k], nb, in, n, lpr, w.starts[k], w.cap_lines, w.info[k]);
     if (nb) sk_nl_fill_kernel<<<nb, 256, 0, stream>>>(in, n, w.blk[k], w.starts[k], w.cap_lines);
     return nb ? 3 : 1;
@@ -571,8 +677,9 @@ int launch_lineop(int op, const uint8_t *in_a, uint64_t n_a, const uint8_t *in_b
                   uint64_t max_records, void *stats_tab, uint32_t h_cap, DevStats *st, int sm_count, void *stream_, const char **err) {
     cudaStream_t stream = (cudaStream_t)stream_;
     const LineWork w = carve(work, max_stream_bytes, max_records);
-    int launches = index_lines(in_a, n_a, lpr, w, 0, st, stream);
-    if (op == LOP_INTERLEAVE) launches += index_lines(in_b, n_b, lpr, w, 1, st, stream);
+    const int strict = (op == LOP_TRIMQ || op == LOP_MASKQ) ? 0 : 1;
+    int launches = index_lines(in_a, n_a, lpr, w, 0, st, strict, stream);
+    if (op == LOP_INTERLEAVE) launches += index_lines(in_b, n_b, lpr, w, 1, st, strict, stream);
     LParams p;
     memset(&p, 0, sizeof p);
     p.op = op;

@@ -952,9 +952,11 @@ static int run_demultiplex(int argc, char **argv) {
     {
         std::string flat;
         for (auto *s : samples) flat += s->barcode;
-        int rc = sk_set_sheet(g.ctx, (const uint8_t *)flat.data(), S, (uint32_t)barcode_len);
-        if (rc == SK_E_UNSUPPORTED) refuse("%s", sk_last_error(g.ctx));
-        g.ck(rc, "sk_set_sheet");
+        for (sk_ctx *xc : g.ctxs) {  // every device holds the sheet
+            int rc = sk_set_sheet(xc, (const uint8_t *)flat.data(), S, (uint32_t)barcode_len);
+            if (rc == SK_E_UNSUPPORTED) refuse("%s", sk_last_error(xc));
+            g.ck(xc, rc, "sk_set_sheet");
+        }
     }
     const uint32_t use_index = (index1.empty() ? 0u : 1u) | (index2.empty() ? 0u : 2u);
     const int NL = g.lanes();
@@ -1197,7 +1199,23 @@ static int run_demultiplex(int argc, char **argv) {
     };
     // Run totals: one grouped NCCL all-reduce over the GPUs' device-side counters, then a single download.
     auto finish_counts = [&]() {
-        g.ck(sk_allreduce_totals(g.ctxs.data(), g.G), "sk_allreduce_totals");
+        // NCCL writes its version banner (and, with NCCL_DEBUG, its log) to stdout, which belongs to the reference's
+        // output: the descriptor points at /dev/null while the collective runs (failures come back as codes)
+        fflush(stdout);
+        const int saved = g.G > 1 ? dup(1) : -1;
+        if (saved >= 0) {
+            const int nul = open("/dev/null", O_WRONLY | O_CLOEXEC);
+            if (nul >= 0) {
+                dup2(nul, 1);
+                close(nul);
+            }
+        }
+        const int arc = sk_allreduce_totals(g.ctxs.data(), g.G);
+        if (saved >= 0) {
+            dup2(saved, 1);
+            close(saved);
+        }
+        g.ck(arc, "sk_allreduce_totals");
         g.ck(sk_download_totals(g.ctx, counts_h.data()), "sk_download_totals");
         for (uint32_t s = 0; s < S; s++) samples[s]->total_reads = counts_h[s];
         total_reads = counts_h[S];

@@ -105,15 +105,37 @@ def test_fuzz_stream_ops_vs_oracle(eng, O):
         check3(eng.add_barcode(data, bc), O.add_barcode(data, bc), ("addbc", it))
 
 
-def test_dense_or_long_records_are_refused_not_mangled(eng):
-    """Inputs outside the chunk geometry must surface as explicit statuses."""
+def test_dense_long_and_utf8_records_take_the_line_engine(eng, O):
+    """Inputs outside the chunk engines' geometry.  trim / mask by quality fall through to the
+    line engine (sk_result.reserved bit 4), which frames records by a global line table: records of any length,
+    any density, and UTF-8 in header and '+' lines give the oracle's bytes.  Non-ASCII bases or qualities and
+    invalid UTF-8 are still refused, and so are demultiplex inputs of that kind -- explicitly."""
     from seqkit_b200.engine import Unsupported
     tiny = b"@a\nAC\n+\nII\n" * 4000  # 11-byte records: > 512 per 32 KiB chunk
+    big = (b"@long\n" + b"A" * 20000 + b"\n+\n" + b"I" * 12000 + b"#" * 8000 + b"\n") * 3
+    mixed = G.clean_fastq(3, 500) + big + tiny + G.clean_fastq(4, 500)
+    utf8 = "@réad 日本 1\nACGTACGT\n+réad\nIIII##II\n".encode() * 50 + G.clean_fastq(5, 200)
+    nbsp = "@x \nACGT\n+\nIIII\n".encode()  # header ends in U+00A0: printed verbatim by trim and mask
+    for label, blob in (("tiny", tiny), ("big", big), ("mixed", mixed), ("utf8", utf8), ("nbsp", nbsp)):
+        for q in (20, 0, 41):
+            check3(eng.trim_by_quality(blob, q), O.trim_by_quality(blob, q), ("trim", label, q))
+            assert eng.last_result.reserved & 16, ("trim", label, eng.last_result.reserved)
+            check3(eng.mask_by_quality(blob, q), O.mask_by_quality(blob, q), ("mask", label, q))
+            assert eng.last_result.reserved & 16, ("mask", label, eng.last_result.reserved)
+    # failing records behind long ones: the reference's messages after the output of the records before them
+    for bad in (big + b"oops\nAC\n+\nII\n" + big, big + b"@s\nACGT\n+\nII\n", tiny + b"\n"):
+        check3(eng.trim_by_quality(bad, 20), O.trim_by_quality(bad, 20), "trim after long")
+        check3(eng.mask_by_quality(bad, 20), O.mask_by_quality(bad, 20), "mask after long")
+    for blob in ("@r\nACéT\n+\nIIIII\n".encode(), "@r\nACGT\n+\nIIé\n".encode(), b"@r\xff\nACGT\n+\nIIII\n", b"@r\nACGT\n+\xc3\nIIII\n"):
+        with pytest.raises(Unsupported):
+            eng.trim_by_quality(blob, 20)
+        with pytest.raises(Unsupported):
+            eng.mask_by_quality(blob, 20)
+    sheet, bcs = G.make_sheet(1, 4, 8)
     with pytest.raises(Unsupported):
-        eng.trim_by_quality(tiny, 20)
-    big = b"@long\n" + b"A" * 20000 + b"\n+\n" + b"I" * 20000 + b"\n"
+        eng.demultiplex(sheet, (b"@long BC:" + bcs[0] + b"\n" + b"A" * 20000 + b"\n+\n" + b"I" * 20000 + b"\n") * 3)
     with pytest.raises(Unsupported):
-        eng.mask_by_quality(big * 3, 20)
+        eng.demultiplex(sheet, "@ré BC:".encode() + bcs[0] + b"\nAC\n+\nII\n")
 
 
 def test_add_barcode_fasta_and_reuse(eng, O):

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Copies the outputs of tools/round_measure.sh (gpurun_out/) into profiles/: the bench line, the ncu launch
 list with a per-kernel summary, the per-phase / per-line summary of the full capture and the DRAM-traffic /
-issue figures of the two hot kernels (profiles/r1_traffic.json, which bench.py reads for roofline.traffic)."""
+issue / pipe figures of the hot kernels (profiles/<round>_traffic.json, which bench.py reads for roofline.traffic;
+<round> = the tag up to its first underscore).  usage: python tools/refresh_profiles.py r2_warp"""
 import collections, csv, json, os, shutil, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -48,11 +49,34 @@ d = collections.OrderedDict(source="ncu --set full --clock-control none, bench.p
 keys = {"dram_bytes_per_launch": None, "gpu_time_us_under_ncu": "gpu__time_duration.sum",
         "issue_active_pct": "smsp__issue_active.avg.pct_of_peak_sustained_active", "icc_hit_rate_pct": "sm__icc_request_hit_rate.pct",
         "gcc_instruction_requests_pct_of_peak": "gcc__cache_requests_type_instruction.sum.pct_of_peak_sustained_elapsed",
-        "warp_instructions": "smsp__inst_executed.sum"}
+        "warp_instructions": "smsp__inst_executed.sum",
+        "pipe_alu_pct": "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active",
+        "pipe_fma_pct": "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active",
+        "lsu_wavefronts_pct": "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "lanes_per_instruction": "smsp__thread_inst_executed_per_inst_executed.ratio"}
 for k in keys:
     d[k] = {}
-for nm, r in zip(("DEMUX1", "DEMUX2"), raw[2:]):
+
+
+def take(nm, r):
     for k, m in keys.items():
-        d[k][nm] = val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum") if m is None else val(r, m)
-json.dump(d, open(os.path.join(P, "r1_traffic.json"), "w"), indent=1)
+        try:
+            d[k][nm] = val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum") if m is None else val(r, m)
+        except Exception:
+            d[k][nm] = None
+
+
+for nm, r in zip(("DEMUX1", "DEMUX2"), raw[2:]):
+    take(nm, r)
+for nm, fn in (("TRIM", "prof_trim.ncu-rep"), ("MASK", "prof_mask.ncu-rep"), ("COMPACT_MOVE", "prof_move.ncu-rep")):
+    rp = os.path.join(G, fn)
+    if not os.path.exists(rp):
+        continue
+    rr = list(csv.reader(subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout.splitlines()))
+    if len(rr) > 2:
+        hdr, units = rr[0], rr[1]
+        c = hdr.index
+        take(nm, rr[2])
+d["note"] = "TRIM = the trim kernel alone (its scan and gather launches are separate kernels); *_pct = percent of the pipe's peak"
+json.dump(d, open(os.path.join(P, tag.split("_")[0] + "_traffic.json"), "w"), indent=1)
 print(json.dumps(d, indent=1))
