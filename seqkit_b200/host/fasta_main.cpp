@@ -28,6 +28,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/stat.h>
 #include <sys/types.h>
 #include <sys/wait.h>
 #include <unistd.h>
@@ -182,6 +183,12 @@ struct Input {
     int fd = -1;
     pid_t child = 0;
     bool eof = false;
+    // bytes of a plain regular file (0 for stdin, pipes and *.gz: their producers are far slower than one GPU)
+    uint64_t plain_bytes() const {
+        struct stat sb;
+        if (fd < 0 || child || fstat(fd, &sb) != 0 || !S_ISREG(sb.st_mode)) return 0;
+        return (uint64_t)sb.st_size;
+    }
     void open_path(const std::string &path) {
         if (path == "-") {
             fd = 0;
@@ -491,7 +498,11 @@ struct Gpu {
     int lanes() const { return G * NSLOT; }
     sk_ctx *c(int lane) const { return ctxs[(size_t)(lane % G)]; }
     uint32_t slot(int lane) const { return (uint32_t)(lane / G); }
-    void create(uint32_t max_samples, bool aux, int n_out, bool line_ops = false) {
+    // input_bytes: bytes of the plain input files (Input::plain_bytes).  Without SK_GPUS / SK_DEVICE the run takes one more
+    // GPU per 4 GiB of such input, all visible GPUs at most: every context costs start-up time (page-locked buffers, the
+    // NCCL communicator at the end), one GPU outruns any host-side producer of a small or compressed input, and the
+    // output bytes do not depend on the number of GPUs anyway.
+    void create(uint32_t max_samples, bool aux, int n_out, bool line_ops = false, uint64_t input_bytes = 0) {
         // 16 MiB batches: page-locking host memory is the slowest part of start-up (a few ms per MiB), and the
         // kernels lose nothing at this size
         uint64_t mb = 16;
@@ -503,7 +514,7 @@ struct Gpu {
         if (const char *e = getenv("SK_DEVICE")) {
             devs.push_back(atoi(e));
         } else {
-            int want = ndev;
+            int want = (int)std::min<uint64_t>((uint64_t)std::max(ndev, 1), 1 + (input_bytes >> 32));
             if (const char *g = getenv("SK_GPUS")) want = std::max(1, std::min(ndev, atoi(g)));
             for (int d = 0; d < want; d++) devs.push_back(d);
         }
@@ -516,26 +527,50 @@ struct Gpu {
         lim.max_samples = max_samples;
         lim.aux_streams = aux ? 1 : 0;
         lim.reserved = line_ops ? 0x200u : 0u;
-        for (int d : devs) {
-            sk_ctx *x = nullptr;
-            int rc = sk_ctx_create(d, &lim, &x);
-            if (rc != SK_OK) {
-                fprintf(stderr, "seqkit_b200: cannot initialise the GPU path: %s\n", sk_last_error(nullptr));
-                finish(3);
-            }
-            ctxs.push_back(x);
+        // One thread per device: context creation and page-locking are the slow part of start-up (seconds with
+        // eight GPUs when done one after the other), and nothing in them depends on another device.
+        G = (int)devs.size();
+        ctxs.assign((size_t)G, nullptr);
+        std::vector<std::string> errs((size_t)G);
+        out_cap = 0;
+        for (int m = 0; m < n_out; m++) {
+            out_h[m].assign((size_t)lanes(), nullptr);
+            out_hcap[m].assign((size_t)lanes(), 0);
         }
-        ctx = ctxs[0];
-        G = (int)ctxs.size();
-        out_cap = sk_out_capacity(ctx);
         // the device-side capacity allows for 72 more bytes per record (add barcode); what the operators here
         // usually write is about the batch itself, so the host mirrors start there and grow when they must
-        const uint64_t first = aux ? out_cap : std::min<uint64_t>(out_cap, batch_bytes + batch_bytes / 8 + (uint64_t)max_samples * 128 + (1u << 20));
-        for (int m = 0; m < n_out; m++)
-            for (int l = 0; l < lanes(); l++) {
-                out_h[m].push_back((uint8_t *)pinned(c(l), first));
-                out_hcap[m].push_back(first);
+        auto first_cap = [&](uint64_t cap) {
+            return aux ? cap : std::min<uint64_t>(cap, batch_bytes + batch_bytes / 8 + (uint64_t)max_samples * 128 + (1u << 20));
+        };
+        per_device([&](int k) {
+            sk_ctx *x = nullptr;
+            if (sk_ctx_create(devs[(size_t)k], &lim, &x) != SK_OK) {
+                errs[(size_t)k] = sk_last_error(nullptr);
+                return;
             }
+            ctxs[(size_t)k] = x;
+            const uint64_t cap = first_cap(sk_out_capacity(x));
+            for (int m = 0; m < n_out; m++)
+                for (int l = k; l < lanes(); l += G) {
+                    out_h[m][(size_t)l] = (uint8_t *)sk_pinned_alloc(x, cap);
+                    out_hcap[m][(size_t)l] = cap;
+                    if (!out_h[m][(size_t)l]) errs[(size_t)k] = "cannot allocate pinned memory";
+                }
+        });
+        for (int k = 0; k < G; k++)
+            if (!errs[(size_t)k].empty() || !ctxs[(size_t)k]) {
+                fprintf(stderr, "seqkit_b200: cannot initialise the GPU path: %s\n", errs[(size_t)k].c_str());
+                finish(3);
+            }
+        ctx = ctxs[0];
+        out_cap = sk_out_capacity(ctx);
+    }
+    template <class F>
+    void per_device(F f) {
+        std::vector<std::thread> th;
+        for (int k = 1; k < G; k++) th.emplace_back([&f, k] { f(k); });
+        f(0);
+        for (auto &t : th) t.join();
     }
     uint8_t *ensure_out(int m, int lane, uint64_t n) {
         if (n > out_cap) refuse("output larger than the slot capacity");
@@ -563,7 +598,15 @@ struct Gpu {
         st.active = true;
         st.cap = batch_bytes;
         const int nb = G * (NSLOT + 1);
-        for (int j = 0; j < nb; j++) st.ring.push_back((uint8_t *)pinned(ctxs[(size_t)(j % G)], batch_bytes));
+        st.ring.assign((size_t)nb, nullptr);
+        per_device([&](int k) {
+            for (int j = k; j < nb; j += G) st.ring[(size_t)j] = (uint8_t *)sk_pinned_alloc(ctxs[(size_t)k], batch_bytes);
+        });
+        for (uint8_t *b : st.ring)
+            if (!b) {
+                fprintf(stderr, "seqkit_b200: cannot allocate %llu bytes of pinned memory\n", (unsigned long long)batch_bytes);
+                finish(3);
+            }
         if (st.in.fd < 0) st.in.open_path(path);  // (an input is opened exactly once: it may be a FIFO)
     }
     void ck(sk_ctx *x, int rc, const char *what) {
@@ -619,7 +662,7 @@ struct Batch {
 
 static int run_stream_op(StreamOp op, const Input &fastq_in, const Input &aux_in, unsigned min_baseq) {
     Gpu g;
-    g.create(0, op == OP_ADDBC, 1);
+    g.create(0, op == OP_ADDBC, 1, false, fastq_in.plain_bytes());
     Stream rd, bc;
     rd.in = fastq_in;  // opened by the dispatcher, in the reference's order of errors
     g.init_stream(rd, "");
@@ -947,7 +990,9 @@ static int run_demultiplex(int argc, char **argv) {
     if (S == 0) refuse("empty sample sheet");
     const bool use_aux = !index1.empty() || !index2.empty();
     Phase *ph_init = new Phase(0);
-    g.create(S, use_aux, paired ? 2 : 1);
+    uint64_t plain = 0;
+    for (auto &o : to_open) plain += st[o.first].in.plain_bytes();
+    g.create(S, use_aux, paired ? 2 : 1, false, plain);
     for (auto &o : to_open) g.init_stream(st[o.first], o.second);
     {
         std::string flat;
@@ -1387,7 +1432,7 @@ static int run_line_op(uint32_t op, const Input &in_a, const Input &in_b, uint64
         }
     }
     Gpu g;
-    g.create(0, false, two_out ? 2 : 1, true);
+    g.create(0, false, two_out ? 2 : 1, true, in_a.plain_bytes() + (two_in ? in_b.plain_bytes() : 0));
     Stream sa, sb;
     sa.in = in_a;
     g.init_stream(sa, "");

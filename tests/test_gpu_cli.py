@@ -90,7 +90,7 @@ def test_stream_ops_multi_batch(oracle_bin, tmp_path):
     data = G.clean_fastq(11, 12000, qual_style="mix")  # ~2.5 MB -> several 1 MiB batches, two slots in flight
     assert len(data) > 2 << 20
     for op in ("trim", "mask"):
-        both(oracle_bin, tmp_path, [op, "by", "quality", "in.fq", "20"], {"in.fq": data}, env={"SK_BATCH_MB": "1"}, ctx=op)
+        both(oracle_bin, tmp_path, [op, "by", "quality", "in.fq", "20"], {"in.fq": data}, env={"SK_BATCH_MB": "1", "SK_GPUS": "8"}, ctx=op)
     bad = data + b"Xbroken\nACGT\n+\nIIII\n" + G.clean_fastq(12, 10)  # fatal in the last batch: earlier output stays
     for op in ("trim", "mask"):
         both(oracle_bin, tmp_path, [op, "by", "quality", "in.fq", "20"], {"in.fq": bad}, env={"SK_BATCH_MB": "1"}, ctx=op)
@@ -254,16 +254,17 @@ def test_gzip_children_and_per_record_tables_give_the_same_files(oracle_bin, tmp
 
 
 def test_all_visible_gpus_give_the_single_gpu_bytes(oracle_bin, tmp_path):
-    """Batches are dealt round-robin to every visible GPU and consumed in batch order: the output does not
-    depend on the number of GPUs (one GPU visible: the same code path with one lane group)."""
+    """Batches are dealt round-robin to the run's GPUs and consumed in batch order: the output does not depend on
+    the number of GPUs (SK_GPUS=8 = every visible GPU, eight at most; one GPU visible: the same code path with one
+    lane group).  Without SK_GPUS a run takes one GPU per 4 GiB of plain input."""
     sheet, bcs = G.make_sheet(7, 48, 20, umi=8, dual=True)
     r1, r2 = G.clean_pairs(79, 12000, bcs, p_sub=0.03, p_random=0.05)
     files = {"sheet.tsv": sheet, "r1.fq": r1, "r2.fq": r2}
     res = []
-    for env in ({"SK_BATCH_MB": "1"}, {"SK_BATCH_MB": "1", "SK_GPUS": "1"}, {"SK_BATCH_MB": "1", "SK_DEVICE": "0"}):
+    for env in ({"SK_BATCH_MB": "1", "SK_GPUS": "8"}, {"SK_BATCH_MB": "1", "SK_GPUS": "1"}, {"SK_BATCH_MB": "1", "SK_DEVICE": "0"}):
         res.append(both(oracle_bin, tmp_path, ["demultiplex", "--trim-by-quality=20", "sheet.tsv", "r1.fq", "r2.fq"]
                         if False else ["demultiplex", "sheet.tsv", "r1.fq", "r2.fq"], files, env=env, ctx=env))
     assert res[0][1] == res[1][1] == res[2][1]
     data = G.clean_fastq(21, 30000, qual_style="mix")
     for op in ("trim", "mask"):
-        both(oracle_bin, tmp_path, [op, "by", "quality", "in.fq", "20"], {"in.fq": data}, env={"SK_BATCH_MB": "1"}, ctx=op)
+        both(oracle_bin, tmp_path, [op, "by", "quality", "in.fq", "20"], {"in.fq": data}, env={"SK_BATCH_MB": "1", "SK_GPUS": "8"}, ctx=op)

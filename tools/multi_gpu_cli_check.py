@@ -16,7 +16,7 @@ sheet, bcs = G.make_sheet(5, 48, 20, umi=8, dual=True)
 r1, r2 = G.clean_pairs(77, 9000, bcs, p_sub=0.03, p_random=0.05)
 top = tempfile.mkdtemp(prefix="skmg_")
 outs = []
-for tag, env in (("all", {}), ("one", {"SK_GPUS": "1"})):
+for tag, env in (("all", {"SK_GPUS": "64"}), ("one", {"SK_GPUS": "1"})):
     d = os.path.join(top, tag)
     os.mkdir(d)
     for name, data in (("sheet.tsv", sheet), ("r1.fq", r1), ("r2.fq", r2)):

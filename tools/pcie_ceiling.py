@@ -23,6 +23,10 @@ sys.path.insert(0, ROOT)
 
 
 def main():
+    # libraries print banners on stdout (NCCL: its version line); the JSON object goes to the saved descriptor
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -82,7 +86,7 @@ def main():
         del h_in, h_out
         os.sched_setaffinity(0, affinity0)
     if rank == 0:
-        print(json.dumps(out))
+        os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 
