@@ -818,7 +818,20 @@ def run_e2e(args, torch, L, bcs, local_rank, rank, world, barrier):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
     eng.close()
-    return {"value": 2.0 * Pe * world * steps / dt, "unit": "reads/s", "h2d_bytes_per_step": int(n1 + n2),
+    # the box's measured copy ceiling for this many GPUs (tools/pcie_ceiling.py, committed from the pool's 8-GPU box)
+    ceiling = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_pcie_ceiling.json")) as f:
+            c = json.load(f)["ceiling_gbs"].get("N=%d" % world)
+        if c:
+            h2d_all = (n1 + n2) * steps / dt / 1e9 * world
+            d2h_all = d2h[0] * steps / dt / 1e9 * world
+            ceiling = dict(c, h2d_gbs_all_gpus=h2d_all, d2h_gbs_all_gpus=d2h_all,
+                           frac_of_both_at_once=max(h2d_all, d2h_all) / c["both_at_once_per_direction"],
+                           source="profiles/r2_pcie_ceiling.json (plain cudaMemcpyAsync, pinned, both directions at once)")
+    except Exception:
+        pass
+    return {"value": 2.0 * Pe * world * steps / dt, "unit": "reads/s", "h2d_bytes_per_step": int(n1 + n2), "copy_ceiling": ceiling,
             "d2h_bytes_per_step": int(d2h[0]), "pairs_per_step": Pe, "steps": steps, "slots": nslots,
             "pcie_gbs": {"h2d": (n1 + n2) * steps / dt / 1e9, "d2h": d2h[0] * steps / dt / 1e9},
             "numa_node": numa,

@@ -33,7 +33,7 @@ for cubin in glob.glob(os.path.join(tmp, "*.cubin")):
 src = open("seqkit_b200/csrc/sk_warp.cu").read().splitlines()
 marks = [("setup", "template <int OP, int NWMAX>"), ("load", "// ---- load the window"), ("scan", "// ---- newline scan"),
          ("count+lines", "uint32_t cnt_all = 0;"), ("framing", "// ---- framing."), ("nrec", "uint32_t nrec = 0;"),
-         ("plan:trim", "// ---- plan: one lane per record"), ("plan:header", "int sample = -1;"),
+         ("plan:trim", "// ---- plan: one lane per record"), ("plan:header", "// trim / mask by quality: failure kind in errk, output length in slen"),
          ("verify/lookback", "// ---- the guess is verified"), ("outcome", "// ---- outcome of every record"),
          ("layout", "// ---- place of the record"), ("emit:header", "// ---- emit"), ("emit:body", "// body: "),
          ("tables", "if (emit) {\n"), ("tail", "if (wrong) continue;")]
