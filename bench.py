@@ -658,7 +658,7 @@ def run_configs(eng, L, P, peak):
 
 def run_add_barcode_leg(local_rank, peak, n=1_000_000):
     """configs[3], first step of the chain (README.md:44-47): `fasta add barcode reads.fq barcodes.fq` on 1 M reads
-    (general engine: OP_SCAN over the barcode file, then OP_ADDBC over the reads)."""
+    (record table of the barcode file from its line table, then OP_ADDBC over the reads on the warp engine)."""
     from seqkit_b200 import Engine
     bcs = make_sheet()
     with Engine(device=local_rank, max_stream_bytes=n * 420 + (1 << 20), max_records=n, max_samples=N_SAMPLES,
@@ -682,7 +682,7 @@ def run_add_barcode_leg(local_rank, peak, n=1_000_000):
                 ms += (r.pass_ms[0] + r.pass_ms[2]) / reps
                 ob = int(r.out_bytes[0])
         b = m1 + len(bcfile) + ob
-        return {"reads": n, "ms": ms, "algorithmic_bytes": b, "achieved": b / (ms * 1e-3) / 1e9,
+        return {"reads": n, "ms": ms, "engine_bits": int(r.reserved), "launches": int(r.gpu_launches), "algorithmic_bytes": b, "achieved": b / (ms * 1e-3) / 1e9,
                 "frac": b / (ms * 1e-3) / 1e9 / peak, "reads_per_s": n / (ms * 1e-3),
                 "workload": "fasta add barcode, 1 M reads + 1 M barcode records (i7+i5UMI on the sequence line)"}
 

@@ -819,6 +819,74 @@ static int peek_first_byte(sk_ctx *ctx, Slot *s, int which, int *c) {
     return SK_OK;
 }
 
+// Pass 1: (seq_off, seq_len, flags) of every barcode record, from the stream's global line table (sk_lineops.cu);
+// pass 2: the reads -- on the warp engine when they are FASTQ (first with every record at its input offset plus a
+// multiple of the first barcode's length, sk_wait repeats it in the ordered form when a record does not fit that),
+// else on the general engine.
+static int addbc_enqueue(sk_ctx *ctx, Slot *s, uint64_t rec_limit, bool fast) {
+    int c_reads, c_bc;
+    int rc = peek_first_byte(ctx, s, SK_IN_R1, &c_reads);
+    if (rc) return rc;
+    rc = peek_first_byte(ctx, s, SK_IN_AUX1, &c_bc);
+    if (rc) return rc;
+    rc = (fast && ctx->warp && c_reads == '@') ? choose_tile_lanes(ctx, s) : SK_OK;
+    if (rc) return rc;
+    rc = begin_op(ctx, s, OP_ADDBC);
+    if (rc) return rc;
+    s->req_rec_limit = rec_limit;
+    // pass 1: where is the sequence line of every barcode record?
+    const bool bc_fastx = (c_bc == '@' || c_bc == '>');
+    // A barcode file whose first line is neither '@' nor '>' never yields a barcode (:20-27): every
+    // read gets an empty one.  (A later '@' line in such a file is reported as mixed format.)
+    if (s->lwork) {
+        const char *err = nullptr;
+        if (ctx->profiling) CK(cudaEventRecord(s->ev[SK_IN_AUX1][0], s->stream));
+        const int n = launch_scan_table(s->in[SK_IN_AUX1], s->in_len[SK_IN_AUX1], c_bc == '>' ? 2u : 4u, bc_fastx ? (uint32_t)c_bc : 0xFFFFu,
+                                        bc_fastx ? ~0ull : 0ull, 1u, s->scan_tab[0], ctx->lim.max_records, s->lwork, 1,
+                                        ctx->lim.max_stream_bytes, ctx->lim.max_records, s->stats + SK_IN_AUX1, ctx->sm_count, s->stream, &err);
+        if (n < 0) {
+            ctx->err = std::string("record table launch failed: ") + (err ? err : "?");
+            return SK_E_CUDA;
+        }
+        if (ctx->profiling) CK(cudaEventRecord(s->ev[SK_IN_AUX1][1], s->stream));
+        s->launches += (uint32_t)n;
+        s->pass_ran[SK_IN_AUX1] = true;
+    } else {
+        KParams q;
+        base_params(ctx, s, SK_IN_AUX1, q);
+        q.lpr = c_bc == '>' ? 2 : 4;
+        q.head_char = bc_fastx ? (uint32_t)c_bc : 0;
+        q.scan_out = s->scan_tab[0];
+        q.scan_cap = ctx->lim.max_records;
+        if (!bc_fastx) q.rec_limit = 0, q.head_char = 0xFFFF;
+        rc = run_pass(ctx, s, SK_IN_AUX1, OP_SCAN, q, false);
+        if (rc) return rc;
+    }
+    // pass 2: the reads
+    KParams p;
+    int eng = (fast && ctx->warp && c_reads == '@') ? ENG_WARP : ENG_GENERAL;
+    auto fill = [&](int e) {
+        base_params(ctx, s, SK_IN_R1, p, e);
+        p.lpr = c_reads == '>' ? 2 : 4;
+        p.head_char = c_reads == '>' ? '>' : '@';
+        p.rec_limit = rec_limit ? rec_limit : ~0ull;
+        p.out = s->out[0];
+        p.out_cap = s->out_cap;
+        p.ext_tab[0] = s->scan_tab[0];
+        p.ext_data[0] = s->in[SK_IN_AUX1];
+        p.ext_stats[0] = s->stats + SK_IN_AUX1;
+    };
+    fill(eng);
+    if (eng == ENG_WARP && !warp_supported(OP_ADDBC, p)) {
+        eng = ENG_GENERAL;
+        fill(eng);
+    }
+    if (eng == ENG_WARP && !s->no_inplace && p.rec_limit == ~0ull) p.inplace = 1;
+    s->used_fast = eng != ENG_GENERAL;
+    rc = run_pass(ctx, s, SK_IN_R1, OP_ADDBC, p, true, eng);
+    if (rc) return rc;
+    return end_op(ctx, s);
+}
 extern "C" int sk_add_barcode(sk_ctx *ctx, uint32_t slot, uint64_t rec_limit) {
     Slot *s = get_slot(ctx, slot);
     if (!s) return SK_E_INVALID;
@@ -826,40 +894,9 @@ extern "C" int sk_add_barcode(sk_ctx *ctx, uint32_t slot, uint64_t rec_limit) {
         ctx->err = "sk_add_barcode needs sk_limits.aux_streams = 1";
         return SK_E_INVALID;
     }
-    int c_reads, c_bc;
-    int rc = peek_first_byte(ctx, s, SK_IN_R1, &c_reads);
-    if (rc) return rc;
-    rc = peek_first_byte(ctx, s, SK_IN_AUX1, &c_bc);
-    if (rc) return rc;
-    rc = begin_op(ctx, s, OP_ADDBC);
-    if (rc) return rc;
-    // pass 1: where is the sequence line of every barcode record?
-    KParams q;
-    base_params(ctx, s, SK_IN_AUX1, q);
-    const bool bc_fastx = (c_bc == '@' || c_bc == '>');
-    q.lpr = c_bc == '>' ? 2 : 4;
-    q.head_char = bc_fastx ? (uint32_t)c_bc : 0;
-    q.scan_out = s->scan_tab[0];
-    q.scan_cap = ctx->lim.max_records;
-    // A barcode file whose first line is neither '@' nor '>' never yields a barcode (:20-27): every
-    // read gets an empty one.  (A later '@' line in such a file is reported as mixed format.)
-    if (!bc_fastx) q.rec_limit = 0, q.head_char = 0xFFFF;
-    rc = run_pass(ctx, s, SK_IN_AUX1, OP_SCAN, q, false);
-    if (rc) return rc;
-    // pass 2: the reads
-    KParams p;
-    base_params(ctx, s, SK_IN_R1, p);
-    p.lpr = c_reads == '>' ? 2 : 4;
-    p.head_char = c_reads == '>' ? '>' : '@';
-    p.rec_limit = rec_limit ? rec_limit : ~0ull;
-    p.out = s->out[0];
-    p.out_cap = s->out_cap;
-    p.ext_tab[0] = s->scan_tab[0];
-    p.ext_data[0] = s->in[SK_IN_AUX1];
-    p.ext_stats[0] = s->stats + SK_IN_AUX1;
-    rc = run_pass(ctx, s, SK_IN_R1, OP_ADDBC, p, true);
-    if (rc) return rc;
-    return end_op(ctx, s);
+    s->reran_general = false;
+    s->no_inplace = false;
+    return addbc_enqueue(ctx, s, rec_limit, ctx->fast);
 }
 
 // The line engine's operators (sk_lineops.cu): SK_IN_R1 (+ SK_IN_R2 for interleave) -> output stream 0 (+ 1 for
@@ -1106,11 +1143,13 @@ extern "C" int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res) {
         // output): run the operator again on the general engine.
         unsigned fl = 0;
         for (int i = 0; i < SK_N_INPUTS; i++) fl |= s->stats_h[i].flags;
-        if (!(fl & F_NEED_GENERAL) && (fl & F_NEED_ORDERED) && s->last_op == OP_MASK && !s->no_inplace) {
-            // mask met a record that changes its length (or fails): same engine, ordered output
+        if (!(fl & F_NEED_GENERAL) && (fl & F_NEED_ORDERED) && (s->last_op == OP_MASK || s->last_op == OP_ADDBC) && !s->no_inplace) {
+            // mask met a record that changes its length (or fails), add barcode one that does not grow like the
+            // first: same engine, ordered output
             const uint32_t first_launches = s->launches;
             s->no_inplace = true;
-            int rc = stream_op_enqueue(ctx, s, s->last_op, s->req_min_baseq, s->req_rec_limit, ctx->fast);
+            int rc = s->last_op == OP_ADDBC ? addbc_enqueue(ctx, s, s->req_rec_limit, ctx->fast)
+                                            : stream_op_enqueue(ctx, s, s->last_op, s->req_min_baseq, s->req_rec_limit, ctx->fast);
             if (rc) return rc;
             CK(cudaStreamSynchronize(s->stream));
             s->launches += first_launches;
@@ -1121,8 +1160,9 @@ extern "C" int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res) {
             const uint32_t fast_launches = s->launches;
             const sk_demux_opts o = s->req_opts;
             const bool again = s->want_compact;  // (begin_op clears it)
-            int rc = s->last_op == OP_DEMUX1 ? demux_enqueue(ctx, s, &o, false)
-                                             : stream_op_enqueue(ctx, s, s->last_op, s->req_min_baseq, s->req_rec_limit, false);
+            int rc = s->last_op == OP_DEMUX1  ? demux_enqueue(ctx, s, &o, false)
+                     : s->last_op == OP_ADDBC ? addbc_enqueue(ctx, s, s->req_rec_limit, false)
+                                              : stream_op_enqueue(ctx, s, s->last_op, s->req_min_baseq, s->req_rec_limit, false);
             if (rc) return rc;
             if (again) {
                 s->want_compact = true;

@@ -387,17 +387,22 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
                     // barcode of iteration i = sequence line of barcode record i; the last one is reused
                     // once the barcode file is exhausted (:20-27)
                     uint32_t bl = 0, bo = 0;
+                    bool bc_long = false;
                     const uint64_t nb = p.ext_stats[0] ? p.ext_stats[0]->n_records : 0;
                     if (nb) {
                         const uint64_t bi = rec < nb ? rec : nb - 1;
                         const RecRef rr = p.ext_tab[0][bi];
                         bl = rr.seq_len;
                         bo = rr.seq_off;
+                        bc_long = (rr.flags & RR_LONG) != 0;  // a barcode line of 64 KiB or more
                     }
                     taglen = 4 + bl;  // " BC:" + barcode
                     ext = bo;
                     cut1 = alen;
-                    if (h != (uint8_t)p.head_char) {
+                    if (bc_long) {
+                        report_err(st, rec, K_TOO_LONG);
+                        taglen = 0;
+                    } else if (h != (uint8_t)p.head_char) {
                         // the reference prints the BC'd header and then stops (:33 before :41-43); the host
                         // reproduces that line, the kernel only reports where.
                         report_err(st, rec, (h == '@' || h == '>') ? K_MIXED : K_BAD_FASTX_LINE);

@@ -671,6 +671,71 @@ static int index_lines(const uint8_t *in, uint64_t n, uint32_t lpr, const LineWo
     return nb ? 3 : 1;
 }
 
+// ---- record table of an index / barcode stream ------------------------------------------------------
+// The (seq_off, seq_len after trim_end, flags) table of OP_SCAN (sk_kernels.cu) from the global line table: no limit
+// on record length or density (a FASTQ of 8-base index reads has hundreds of records per 16 KiB).  Record counting
+// follows the chunk engines: with final_batch every record whose first line exists, otherwise only records followed
+// by the start of another line (the rest is the next batch's).
+__global__ void __launch_bounds__(256) sk_recref_kernel(const LStream a, uint32_t lpr, uint32_t head_char, uint64_t rec_limit, uint32_t final_batch,
+                                                        RecRef *out, uint64_t cap, DevStats *st) {
+    const uint32_t nl = a.info->n_lines;
+    if (a.info->overflow) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) report_err(st, 0, K_TOO_DENSE);
+        return;
+    }
+    uint32_t nrec = final_batch ? (nl + lpr - 1u) / lpr : (nl ? (nl - 1u) / lpr : 0u);
+    if ((uint64_t)nrec > rec_limit) nrec = (uint32_t)rec_limit;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->n_lines = nl;
+        st->n_records = nrec;
+        st->consumed = line_of(a, nrec * lpr).s;
+    }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nrec; i += gridDim.x * blockDim.x) {
+        const LineRef h = line_of(a, i * lpr), sq = line_of(a, i * lpr + 1u);
+        uint32_t sl = trim_end_len_dev(a.in + sq.s, sq.len);
+        const uint32_t c0 = h.len ? a.in[h.s] : 0x100u;
+        uint16_t fl = 0;
+        if (c0 == '@') fl |= RR_L0_AT;
+        if (c0 == '>') fl |= RR_L0_GT;
+        if (lpr == 4) {
+            const LineRef pl = line_of(a, i * lpr + 2u);
+            if (pl.len && a.in[pl.s] == '+') fl |= RR_L2_PLUS;
+        }
+        if (sl > 0xFFFFu) {
+            fl |= RR_LONG;
+            sl = 0xFFFFu;
+        }
+        if (head_char && c0 != head_char) report_err(st, i, K_MIXED);
+        if (i < cap) {
+            RecRef rr;
+            rr.seq_off = sq.s;
+            rr.seq_len = (uint16_t)sl;
+            rr.flags = fl;
+            out[i] = rr;
+        }
+    }
+}
+// Line table `k` (0 or 1) of the work area is used.  Returns the number of launches, < 0 on a launch error.
+int launch_scan_table(const uint8_t *in, uint64_t n, uint32_t lpr, uint32_t head_char, uint64_t rec_limit, uint32_t final_batch,
+                      RecRef *out, uint64_t cap, void *work, int k, uint64_t max_stream_bytes, uint64_t max_records, DevStats *st,
+                      int sm_count, void *stream_, const char **err) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const LineWork w = carve(work, max_stream_bytes, max_records);
+    int launches = index_lines(in, n, lpr, w, k, st, 1, stream);
+    LStream a;
+    a.in = in, a.n = n, a.starts = w.starts[k], a.info = w.info[k];
+    const uint64_t want = (n / 64 + 255) / 256 + 1;  // a thread per 64 bytes is plenty
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sm_count * 8, want));
+    sk_recref_kernel<<<grid, 256, 0, stream>>>(a, lpr, head_char, rec_limit, final_batch, out, cap, st);
+    launches++;
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        *err = cudaGetErrorString(e);
+        return -1;
+    }
+    return launches;
+}
+
 // One line operator over the slot's streams.  stats table: keys / rep / cnt of `h_cap` slots, list of 2*h_cap u64.
 int launch_lineop(int op, const uint8_t *in_a, uint64_t n_a, const uint8_t *in_b, uint64_t n_b, uint32_t lpr, uint32_t head, uint32_t x,
                   uint32_t y, uint64_t rec_limit, uint8_t *out0, uint8_t *out1, uint64_t out_cap, void *work, uint64_t max_stream_bytes,

@@ -197,8 +197,8 @@ static __device__ __noinline__ uint64_t wlb_consume(uint64_t *inc, const uint16_
 template <int OP, int NWMAX>
 __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const __grid_constant__ KParams p) {
     constexpr bool D1 = OP == OP_DEMUX1;
-    constexpr bool IS_DEMUX = OP == OP_DEMUX1 || OP == OP_DEMUX2;  // else OP_TRIM / OP_MASK: one output stream, input order
-    static_assert(IS_DEMUX || OP == OP_TRIM || OP == OP_MASK, "warp engine: demultiplex passes, trim, mask");
+    constexpr bool IS_DEMUX = OP == OP_DEMUX1 || OP == OP_DEMUX2;  // else OP_TRIM / OP_MASK / OP_ADDBC: one output stream, input order
+    static_assert(IS_DEMUX || OP == OP_TRIM || OP == OP_MASK || OP == OP_ADDBC, "warp engine: demultiplex passes, trim, mask, add barcode");
     constexpr int UPL = GeoW::UPL, LANE_BYTES = GeoW::LANE_BYTES, WIN = GeoW::WIN;
     constexpr int MAXREC = GeoW::MAXREC, MAXLINES = GeoW::MAXLINES;
     constexpr uint32_t FULL = 0xffffffffu;
@@ -253,6 +253,11 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
     const uint32_t Lb = p.sheet.L;
     uint16_t *agg16 = wlb_agg(p.tile_lines, p.n_chunks);
     const unsigned long long r1_nrec = (D1 || !IS_DEMUX) ? 0ull : p.r1_stats->n_records;  // mate 2: records of the mate-1 pass
+    // add barcode: records of the barcode stream's table, and the growth of a record when every barcode is as long
+    // as the first and no header ends in white space (" BC:" + barcode; the in-place form's assumption)
+    const unsigned long long bc_n = (OP == OP_ADDBC && p.ext_stats[0]) ? p.ext_stats[0]->n_records : 0ull;
+    const uint32_t addD = 4u + (bc_n ? (uint32_t)p.ext_tab[0][0].seq_len : 0u);
+    unsigned long long my_outmax = 0;      // lane 0, add barcode in place: end of the output of this warp's tiles
     uint32_t parity = 0;
     uint32_t my_total = 0, my_ident = 0;   // DEMUX1 counters of this lane's records
     unsigned long long my_out = 0;         // lane 0: payload bytes of this warp's tiles
@@ -293,7 +298,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
     // (the kernels are larger than that cache, and sixteen warps spread over them saturate the GPC-level
     // instruction cache).  Mask (a small kernel whose tiles wait on each other's output sizes) runs faster
     // with every warp on its own ticket, taken when the tile starts.
-    constexpr bool LS = SKW_LOCKSTEP && OP != OP_MASK;
+    constexpr bool LS = SKW_LOCKSTEP && OP != OP_MASK && OP != OP_ADDBC;
     volatile uint32_t *cta_ticket =
         (volatile uint32_t *)(sk_smem + (uint32_t)(warp - wg) * WL::per_warp + WL::misc + 8);  // two slots in the leader's misc area
     uint32_t cta_next = 0, flipk = 0;
@@ -500,6 +505,32 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 }
                 return slen;
             };
+            // add barcode for one record per lane (fasta_add_barcode.rs:20-43): the record's output length; the barcode of
+            // record `rec` is the sequence line of barcode record `rec`, the last one once that file is exhausted
+            auto addbc_plan = [&](bool has, uint64_t rec, uint32_t L0, uint32_t L1, uint32_t L4, uint32_t &alen, uint32_t &bl,
+                                  uint32_t &bo, uint32_t &errk) -> uint32_t {
+                errk = 0;
+                alen = bl = bo = 0;
+                if (!has) return 0u;
+                uint32_t e = L1;
+                while (e > L0 && is_ws(win[e - 1])) e--;  // header.trim_end()  (:33)
+                alen = e - L0;
+                if (bc_n) {
+                    const RecRef rr = p.ext_tab[0][rec < bc_n ? rec : bc_n - 1ull];
+                    bl = rr.seq_len;
+                    bo = rr.seq_off;
+                    if (rr.flags & RR_LONG) {
+                        errk = K_TOO_LONG;
+                        return 0u;
+                    }
+                }
+                const uint8_t h = win[L0];
+                if (h != '@') {  // the reference prints the BC'd header and stops (:33 before :41-43): the host reproduces that
+                    errk = h == '>' ? K_MIXED : K_BAD_FASTX_LINE;
+                    return 0u;
+                }
+                return alen + 4u + bl + 1u + (L4 - L1);
+            };
             uint64_t s_obase = 0;   // trim / mask: the tile's place in the output stream ...
             uint32_t s_done = 0;    // ... and the bytes its earlier rounds have written
             bool s_writable = false;
@@ -556,7 +587,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 }
                 // trim / mask by quality: failure kind in errk, output length in slen
                 uint32_t errk = 0, slen = 0;
-                if (!IS_DEMUX) slen = stream_plan(has, L0, L1, L2, L3, L4, mode, kk, errk);
+                if (!IS_DEMUX && OP != OP_ADDBC) slen = stream_plan(has, L0, L1, L2, L3, L4, mode, kk, errk);
                 if (!IS_DEMUX) {
                 } else if (D1) {
                     // fasta_demultiplex.rs:148-194, second half: barcode length, match, decide.  Outcome:
@@ -634,6 +665,8 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                         cta_next = atomicAdd(&st->ticket, (uint32_t)GW);
                         cta_have = true;
                     }
+                    uint32_t a_alen = 0, a_bl = 0, a_bo = 0;
+                    if (OP == OP_ADDBC) slen = addbc_plan(has, rec, L0, L1, L4, a_alen, a_bl, a_bo, errk);
                     if (has && errk) report_err(st, rec, errk);
                     uint32_t oincl = slen;
 #pragma unroll
@@ -652,8 +685,10 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                             const bool has2 = rr + (uint32_t)lane < nrec;
                             const uint32_t j2 = j0 + (has2 ? rr + (uint32_t)lane : 0u) * 4u;
                             uint8_t m2;
-                            uint32_t k2 = 0, e2 = 0;
-                            const uint32_t l2 = stream_plan(has2, LB(j2), LB(j2 + 1), LB(j2 + 2), LB(j2 + 3), LB(j2 + 4), m2, k2, e2);
+                            uint32_t k2 = 0, e2 = 0, x0, x1, x2;
+                            const uint32_t l2 = OP == OP_ADDBC
+                                                    ? addbc_plan(has2, rec0 + rr + (uint32_t)lane, LB(j2), LB(j2 + 1), LB(j2 + 4), x0, x1, x2, e2)
+                                                    : stream_plan(has2, LB(j2), LB(j2 + 1), LB(j2 + 2), LB(j2 + 3), LB(j2 + 4), m2, k2, e2);
                             tile_outb += __reduce_add_sync(FULL, l2);
                         }
                         if (lane == 0 && !p.unordered && !p.inplace) wlb_publish(oagg16, c, tile_outb);
@@ -661,7 +696,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                     // patches (and the mask itself, in place) while the predecessors' counts arrive
                     uint32_t run1 = 0, run2 = 0;
                     bool slow = false;
-                    if (slen && p.out) {
+                    if (OP != OP_ADDBC && slen && p.out) {
                         if (mode == B_MASK) {
                             if (L1 + kk + 3u <= L3) {
                                 mask_copy(win + L1, win + L1, win + L3, kk, p.min_baseq);  // :40-43, in place
@@ -718,6 +753,15 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                             if (lane == 0) report_err(st, rec0, K_OUT_OVERFLOW);
                             s_writable = false;
                         }
+                    } else if (r0 == 0 && OP == OP_ADDBC && p.inplace) {
+                        // add barcode with one barcode length: record r of the stream moves up by r * addD bytes
+                        s_obase = c0 + __shfl_sync(FULL, L0, 0) + rec0 * addD;
+                        out_done = true;
+                        s_writable = p.out != nullptr && tile_outb > 0;
+                        if (s_writable && s_obase + tile_outb > p.out_cap) {
+                            if (lane == 0) report_err(st, rec0, K_OUT_OVERFLOW);
+                            s_writable = false;
+                        }
                     } else if (r0 == 0) {
                         s_obase = wlb_consume(p.tile_out, oagg16, c, tile_outb, lane);
                         out_done = true;
@@ -764,6 +808,46 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                             const uint32_t tl = len & 15u;
                             if ((uint32_t)lane < tl) g0[16u * nv + (uint32_t)lane] = win[so + 16u * nv + (uint32_t)lane];
                         }
+                    }
+                    if (OP == OP_ADDBC) {
+                        bool wr = s_writable;
+                        if (p.inplace && __any_sync(FULL, has && slen != (L4 - L0) + addD)) {
+                            // a barcode of another length, a header that ends in white space, a failing record: the output
+                            // offsets are not the input offsets plus a multiple of addD; sk_wait runs the ordered form
+                            if (lane == 0) atomicOr(&st->flags, F_NEED_ORDERED);
+                            wr = false;
+                        }
+                        if (wr) {
+                            // the rest of the record goes out first; then " BC:" + barcode + "\n" is written behind the
+                            // trimmed header, over the head of the sequence line, and header + tag go out as one run
+                            uint8_t *gd = p.out + s_obase + my_off;
+                            const uint32_t hl = a_alen + 5u + a_bl;
+                            const bool fits = slen && hl <= L4 - L0;
+                            gcopy(gd + hl, win, L1, slen ? L4 - L1 : 0u);
+                            __syncwarp();
+                            const uint8_t *bsrc = p.ext_data[0] + a_bo;
+                            if (fits) {
+                                uint8_t *d = win + L0 + a_alen;
+                                d[0] = ' '; d[1] = 'B'; d[2] = 'C'; d[3] = ':';
+#pragma unroll 4
+                                for (uint32_t t = 0; t < a_bl; t++) d[4u + t] = bsrc[t];
+                                d[4u + a_bl] = '\n';
+                            }
+                            __syncwarp();
+                            gcopy(gd, win, L0, fits ? hl : 0u);
+                            if (slen && !fits) {  // rare: a record shorter than its new header line
+                                uint8_t *d = gd;
+#pragma unroll 1
+                                for (uint32_t i = 0; i < a_alen; i++) *d++ = win[L0 + i];
+                                d[0] = ' '; d[1] = 'B'; d[2] = 'C'; d[3] = ':';
+                                d += 4;
+#pragma unroll 1
+                                for (uint32_t t = 0; t < a_bl; t++) *d++ = bsrc[t];
+                                *d = '\n';
+                            }
+                        }
+                        __syncwarp();
+                        continue;
                     }
                     if (s_writable && !whole) {
                         uint8_t *gd = p.out + s_obase + my_off;
@@ -1206,6 +1290,10 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 my_nrec += nrec;
                 const unsigned long long upto = c0 + LB(j0 + nrec * 4u);
                 my_upto = upto > my_upto ? upto : my_upto;
+                if (OP == OP_ADDBC) {
+                    const unsigned long long oend = upto + (((g0 + j0) >> 2) + nrec) * addD;
+                    my_outmax = oend > my_outmax ? oend : my_outmax;
+                }
             }
         }
         // The next ticket is taken during the last round (or now): a tile's count must appear soon after
@@ -1230,6 +1318,10 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
         if (OP == OP_MASK && p.inplace) {  // output == input bytes of the complete records
             atomicMax(&st->out_bytes, my_upto);
             atomicMax(&st->out_extent, my_upto);
+        }
+        if (OP == OP_ADDBC && p.inplace) {
+            atomicMax(&st->out_bytes, my_outmax);
+            atomicMax(&st->out_extent, my_outmax);
         }
     }
     if (D1) {  // fasta_demultiplex.rs:108-109,169,177-178
@@ -1384,6 +1476,7 @@ static uint32_t warp_smem(uint32_t S, uint32_t n_classes, uint32_t nwp, bool d1)
 bool warp_supported(int op, const KParams &p) {
     if (p.lpr != 4 || p.tile_lanes < 8 || p.tile_lanes > 30) return false;
     if (op == OP_TRIM || op == OP_MASK) return true;
+    if (op == OP_ADDBC) return p.head_char == '@' && p.ext_tab[0] && p.ext_data[0] && p.ext_stats[0];
     if (op != OP_DEMUX1 && op != OP_DEMUX2) return false;
     if (p.n_index || !p.sheet.hidx.n_classes || !p.sheet.fidx.table) return false;
     if (p.tile_lanes < 8 || p.tile_lanes > 30) return false;
@@ -1393,7 +1486,7 @@ bool warp_supported(int op, const KParams &p) {
 template <int OP, int NWMAX>
 static int launch_warp_one(const KParams &p, int sm_count, cudaStream_t stream, const char **err) {
     auto kfn = sk_warp_kernel<OP, NWMAX>;
-    const bool stream_op = OP == OP_TRIM || OP == OP_MASK;  // no sheet tables
+    const bool stream_op = OP == OP_TRIM || OP == OP_MASK || OP == OP_ADDBC;  // no sheet tables
     const int smem = (int)warp_smem(stream_op ? 0u : p.sheet.S, stream_op ? 0u : p.sheet.hidx.n_classes, p.sheet.hidx.nwp, OP == OP_DEMUX1);
     cudaError_t e = cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e != cudaSuccess) {
@@ -1430,6 +1523,7 @@ int launch_warp_kernel(int op, const KParams &p, int sm_count, void *stream_, co
         case OP_DEMUX2: return launch_warp_one<OP_DEMUX2, 8>(p, sm_count, stream, err);
         case OP_TRIM: return launch_warp_one<OP_TRIM, 8>(p, sm_count, stream, err);
         case OP_MASK: return launch_warp_one<OP_MASK, 8>(p, sm_count, stream, err);
+        case OP_ADDBC: return launch_warp_one<OP_ADDBC, 8>(p, sm_count, stream, err);
     }
     *err = "operator not handled by the warp engine";
     return -1;

@@ -250,3 +250,49 @@ def test_mask_in_place_and_its_ordered_form(O, monkeypatch):
                     assert got[0] == want[0] and got[1] == want[1] and got[2] == want[2], (label, q, switch)
                     if bits is not None:
                         assert e.last_result.reserved == (bits if switch == "1" else 1), (label, q, switch, e.last_result.reserved)
+
+
+def test_add_barcode_on_the_warp_engine(eng, O):
+    """fasta add barcode (fasta_add_barcode.rs:19-44) on the warp engine: barcodes of one length put every record at
+    its input offset plus a multiple of that growth (first form); any other shape -- barcodes of several lengths, a
+    header that ends in white space, a barcode file that runs out or yields nothing -- repeats the pass with an
+    ordered look-back on output bytes (sk_result.reserved bit 2).  The barcode records come from the global line
+    table, so index reads far denser than a chunk engine's record slots are fine."""
+    def run(reads, bc, ctx, want=None):
+        got, exp = eng.add_barcode(reads, bc), O.add_barcode(reads, bc)
+        assert got[0] == exp[0], ctx
+        assert got[1] == exp[1], ctx
+        if exp[0] != 101:
+            assert got[2] == exp[2], ctx
+        if want is not None:
+            assert eng.last_result.reserved & 7 == want, (ctx, eng.last_result.reserved)
+
+    n = 60000
+    reads = G.clean_fastq(11, n, read_len=(100, 151))
+    uni = G.index_reads(12, n, [b"ACGTACGT", b"TTGGCCAA"], p_random=0.2, p_n=0.05)
+    run(reads, uni, "one length", want=1)
+    dual = G.index_reads(13, n, [b"ACGTACGT+TTGGCCAA"])
+    run(reads, dual, "dual index, one length", want=1)
+    run(reads, G.index_reads(14, n, [b"ACGT", b"GG+TT", b"ACGTACGTAC"]), "three lengths", want=5)
+    run(reads, G.index_reads(15, n - 1000, [b"ACGTACGT"]), "barcode file runs out: the last one is reused", want=1)
+    run(reads, G.index_reads(16, n // 2, [b"ACGT", b"ACGTAC"]), "runs out, two lengths", want=5)
+    run(reads, b"", "no barcodes at all", want=1)
+    run(reads, b"junk\nlines\n", "not a FASTA/FASTQ file: empty barcodes", want=1)
+    run(reads, uni[:-9], "last barcode record cut short", want=1)
+    fa_bc = b"".join(b">b%d\nACGTAC\n" % i for i in range(n))
+    run(reads, fa_bc, "FASTA barcode file", want=1)
+    # a header that ends in white space shrinks before the tag goes on (:33)
+    ws = reads.replace(b"\n", b" \t\n", 1)
+    run(ws, uni, "one header ends in white space", want=5)
+    # tiny barcode records: ~2000 per 32 KiB
+    tiny = b"".join(b"@\nAC\n+\nII\n" for _ in range(n))
+    run(reads, tiny, "dense barcode file", want=1)
+    # records shorter than their new header line; empty lines
+    short = (b"@" + b"h" * 89 + b"\nA\n+\nI\n@" + b"g" * 89 + b"\n\n+\n\n") * 1000 + G.clean_fastq(25, 300)
+    run(short, G.index_reads(17, 2300, [b"ACGTACGTACGTACGTACGT"]), "short records", want=1)
+    # failures: a line that is neither '@' nor '>' (message after the BC'd header), FASTA record among FASTQ
+    bad = G.clean_fastq(18, 3000) + b"oops\nAC\n+\nII\n" + G.clean_fastq(19, 100)
+    run(bad, G.index_reads(20, 4000, [b"ACGTACGT"]), "bad line")
+    # several rounds per tile (short records) and a record across tiles
+    run(G.clean_fastq(21, 20000, read_len=(5, 30)), G.index_reads(22, 20000, [b"ACGTACGT"]), "short reads", want=1)
+    run(G.clean_fastq(23, 5000, read_len=(400, 700)), G.index_reads(24, 5000, [b"ACGTACGT"]), "long reads", want=1)
