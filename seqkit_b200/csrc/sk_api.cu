@@ -48,6 +48,7 @@ struct Slot {
     unsigned long long *counts = nullptr;
     Event *events = nullptr;
     RecRef *scan_tab[2] = {nullptr, nullptr};
+    uint4 *bc_inline = nullptr;  // add barcode: 32 bytes of barcode per record (sk_lineops.cu:sk_recref_kernel)
     uint64_t *synth_tmp = nullptr;
     // per-sample compaction (sk_compact.cu): mate 1 -> cbuf, mate 2 -> out[0] (free once mate 1 is compacted)
     uint8_t *cbuf = nullptr;
@@ -153,6 +154,7 @@ static void free_slot(Slot &s) {
         cudaFree(s.groups[i]);
         cudaFree(s.rows[i]);
         cudaFree(s.scan_tab[i]);
+        if (i == 0) cudaFree(s.bc_inline);
     }
     cudaFree(s.tile_out);
     cudaFree(s.stats);
@@ -293,6 +295,7 @@ extern "C" int sk_ctx_create(int device, const sk_limits *lim, sk_ctx **out) {
         }
         if (lim->aux_streams)
             for (int i = 0; i < 2; i++) CKC(cudaMalloc(&s.scan_tab[i], R * sizeof(RecRef)));
+            CKC(cudaMalloc(&s.bc_inline, R * 32));
         // the line engine's work area: the line operators (reserved bit 9), and trim / mask by quality as the last resort
         CKC(cudaMalloc(&s.lwork, lineops_work_bytes(B, R)));
         if (lim->reserved & 0x200u) {  // statistics table
@@ -842,7 +845,7 @@ static int addbc_enqueue(sk_ctx *ctx, Slot *s, uint64_t rec_limit, bool fast) {
         const char *err = nullptr;
         if (ctx->profiling) CK(cudaEventRecord(s->ev[SK_IN_AUX1][0], s->stream));
         const int n = launch_scan_table(s->in[SK_IN_AUX1], s->in_len[SK_IN_AUX1], c_bc == '>' ? 2u : 4u, bc_fastx ? (uint32_t)c_bc : 0xFFFFu,
-                                        bc_fastx ? ~0ull : 0ull, 1u, s->scan_tab[0], ctx->lim.max_records, s->lwork, 1,
+                                        bc_fastx ? ~0ull : 0ull, 1u, s->scan_tab[0], s->bc_inline, ctx->lim.max_records, s->lwork, 1,
                                         ctx->lim.max_stream_bytes, ctx->lim.max_records, s->stats + SK_IN_AUX1, ctx->sm_count, s->stream, &err);
         if (n < 0) {
             ctx->err = std::string("record table launch failed: ") + (err ? err : "?");
@@ -875,6 +878,7 @@ static int addbc_enqueue(sk_ctx *ctx, Slot *s, uint64_t rec_limit, bool fast) {
         p.ext_tab[0] = s->scan_tab[0];
         p.ext_data[0] = s->in[SK_IN_AUX1];
         p.ext_stats[0] = s->stats + SK_IN_AUX1;
+        p.bc_inline = s->lwork ? s->bc_inline : nullptr;
     };
     fill(eng);
     if (eng == ENG_WARP && !warp_supported(OP_ADDBC, p)) {
@@ -1016,6 +1020,21 @@ static int demux_enqueue(sk_ctx *ctx, Slot *s, const sk_demux_opts *o, bool fast
         s->req_opts = keep;
     }
     for (uint32_t q = 0; q < n_index; q++) {
+        if (s->lwork) {  // from the stream's line table: index reads are short, hundreds of records per 16 KiB
+            const char *err = nullptr;
+            const int w = idx_stream[q];
+            if (ctx->profiling) CK(cudaEventRecord(s->ev[w][0], s->stream));
+            const int n = launch_scan_table(s->in[w], s->in_len[w], 4u, 0u, limit, 1u, s->scan_tab[q], nullptr, ctx->lim.max_records, s->lwork, (int)q,
+                                            ctx->lim.max_stream_bytes, ctx->lim.max_records, s->stats + w, ctx->sm_count, s->stream, &err);
+            if (n < 0) {
+                ctx->err = std::string("record table launch failed: ") + (err ? err : "?");
+                return SK_E_CUDA;
+            }
+            if (ctx->profiling) CK(cudaEventRecord(s->ev[w][1], s->stream));
+            s->launches += (uint32_t)n;
+            s->pass_ran[w] = true;
+            continue;
+        }
         KParams k;
         base_params(ctx, s, idx_stream[q], k);
         k.scan_out = s->scan_tab[q];

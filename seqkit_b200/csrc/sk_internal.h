@@ -203,6 +203,8 @@ struct KParams {
     const RecRef *ext_tab[2];
     const uint8_t *ext_data[2];
     const DevStats *ext_stats[2];  // n_records of the OP_SCAN pass that produced ext_tab[q]
+    const uint4 *bc_inline;        // add barcode: the first 32 bytes of every record's barcode, zero-padded (2 x uint4 per
+                                   // record, next to ext_tab[0]; nullptr = read the barcode where it lies)
 };
 
 // Data outcome kinds (== SK_DATA_* in include/seqkit_b200.h); the low byte of DevStats::err_key.
@@ -250,8 +252,8 @@ int launch_lineop(int op, const uint8_t *in_a, uint64_t n_a, const uint8_t *in_b
                   uint64_t max_records, void *stats_tab, uint32_t h_cap, DevStats *st, int sm_count, void *stream, const char **err);
 // OP_SCAN's record table from the global line table (sk_lineops.cu): any record length and density
 int launch_scan_table(const uint8_t *in, uint64_t n, uint32_t lpr, uint32_t head_char, uint64_t rec_limit, uint32_t final_batch,
-                      RecRef *out, uint64_t cap, void *work, int k, uint64_t max_stream_bytes, uint64_t max_records, DevStats *st,
-                      int sm_count, void *stream, const char **err);
+                      RecRef *out, uint4 *inline32, uint64_t cap, void *work, int k, uint64_t max_stream_bytes, uint64_t max_records,
+                      DevStats *st, int sm_count, void *stream, const char **err);
 // Per-sample compaction of a demultiplex result (sk_compact.cu)
 uint64_t compact_work_bytes(uint32_t max_rows, uint32_t S);
 int launch_compact(const ChunkRow *rows, const Group *groups, uint32_t n_rows, uint32_t S, const uint8_t *src, uint8_t *dst,

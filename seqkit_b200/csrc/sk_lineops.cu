@@ -677,7 +677,7 @@ static int index_lines(const uint8_t *in, uint64_t n, uint32_t lpr, const LineWo
 // follows the chunk engines: with final_batch every record whose first line exists, otherwise only records followed
 // by the start of another line (the rest is the next batch's).
 __global__ void __launch_bounds__(256) sk_recref_kernel(const LStream a, uint32_t lpr, uint32_t head_char, uint64_t rec_limit, uint32_t final_batch,
-                                                        RecRef *out, uint64_t cap, DevStats *st) {
+                                                        RecRef *out, uint4 *inline32, uint64_t cap, DevStats *st) {
     const uint32_t nl = a.info->n_lines;
     if (a.info->overflow) {
         if (blockIdx.x == 0 && threadIdx.x == 0) report_err(st, 0, K_TOO_DENSE);
@@ -712,13 +712,20 @@ __global__ void __launch_bounds__(256) sk_recref_kernel(const LStream a, uint32_
             rr.seq_len = (uint16_t)sl;
             rr.flags = fl;
             out[i] = rr;
+            if (inline32) {  // the barcode itself, for readers that want it at a predictable address (add barcode)
+                uint32_t w[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                const uint32_t m = sl < 32u ? sl : 32u;
+                for (uint32_t t = 0; t < m; t++) w[t >> 2] |= (uint32_t)a.in[sq.s + t] << (8u * (t & 3u));
+                inline32[2ull * i] = make_uint4(w[0], w[1], w[2], w[3]);
+                inline32[2ull * i + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+            }
         }
     }
 }
 // Line table `k` (0 or 1) of the work area is used.  Returns the number of launches, < 0 on a launch error.
 int launch_scan_table(const uint8_t *in, uint64_t n, uint32_t lpr, uint32_t head_char, uint64_t rec_limit, uint32_t final_batch,
-                      RecRef *out, uint64_t cap, void *work, int k, uint64_t max_stream_bytes, uint64_t max_records, DevStats *st,
-                      int sm_count, void *stream_, const char **err) {
+                      RecRef *out, uint4 *inline32, uint64_t cap, void *work, int k, uint64_t max_stream_bytes, uint64_t max_records,
+                      DevStats *st, int sm_count, void *stream_, const char **err) {
     cudaStream_t stream = (cudaStream_t)stream_;
     const LineWork w = carve(work, max_stream_bytes, max_records);
     int launches = index_lines(in, n, lpr, w, k, st, 1, stream);
@@ -726,7 +733,7 @@ int launch_scan_table(const uint8_t *in, uint64_t n, uint32_t lpr, uint32_t head
     a.in = in, a.n = n, a.starts = w.starts[k], a.info = w.info[k];
     const uint64_t want = (n / 64 + 255) / 256 + 1;  // a thread per 64 bytes is plenty
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sm_count * 8, want));
-    sk_recref_kernel<<<grid, 256, 0, stream>>>(a, lpr, head_char, rec_limit, final_batch, out, cap, st);
+    sk_recref_kernel<<<grid, 256, 0, stream>>>(a, lpr, head_char, rec_limit, final_batch, out, inline32, cap, st);
     launches++;
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -52,6 +52,15 @@ extern __shared__ __align__(128) unsigned char sk_smem[];
 #ifndef SKW_EARLY_PROBE
 #define SKW_EARLY_PROBE 0  // mate 1: 1 = barcode search, hash and table probes before the quality trim (measured: no gain)
 #endif
+#ifndef SKW_ADDBC_LS
+#define SKW_ADDBC_LS 0  // add barcode: 1 = the warps of a CTA start their tiles together
+#endif
+#ifndef SKW_ADDBC_NOLOAD
+#define SKW_ADDBC_NOLOAD 0  // timing experiment only (wrong output): add barcode without the loads of the barcode table and bytes
+#endif
+#ifndef SKW_TRIM_FREE
+#define SKW_TRIM_FREE 1  // trim by quality: 1 = every warp on its own ticket (like mask; 2.68 vs 3.03 ms per 8 M reads)
+#endif
 #ifndef SKW_TRIM_BLOCKS
 #define SKW_TRIM_BLOCKS 0  // quality trim with independent 16-byte block summaries (0: plan_trim_lane16)
 #endif
@@ -298,7 +307,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
     // (the kernels are larger than that cache, and sixteen warps spread over them saturate the GPC-level
     // instruction cache).  Mask (a small kernel whose tiles wait on each other's output sizes) runs faster
     // with every warp on its own ticket, taken when the tile starts.
-    constexpr bool LS = SKW_LOCKSTEP && OP != OP_MASK && OP != OP_ADDBC;
+    constexpr bool LS = SKW_LOCKSTEP && OP != OP_MASK && !(!SKW_ADDBC_LS && OP == OP_ADDBC) && !(SKW_TRIM_FREE && OP == OP_TRIM);
     volatile uint32_t *cta_ticket =
         (volatile uint32_t *)(sk_smem + (uint32_t)(warp - wg) * WL::per_warp + WL::misc + 8);  // two slots in the leader's misc area
     uint32_t cta_next = 0, flipk = 0;
@@ -531,6 +540,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                 }
                 return alen + 4u + bl + 1u + (L4 - L1);
             };
+            uint32_t s_l0 = 0;      // add barcode in place: window offset of the tile's first record
             uint64_t s_obase = 0;   // trim / mask: the tile's place in the output stream ...
             uint32_t s_done = 0;    // ... and the bytes its earlier rounds have written
             bool s_writable = false;
@@ -665,6 +675,86 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                         cta_next = atomicAdd(&st->ticket, (uint32_t)GW);
                         cta_have = true;
                     }
+                    if (OP == OP_ADDBC && p.inplace) {
+                        // Add barcode, first form: every barcode is taken to be as long as the first and no header to end
+                        // in white space, so record r of the stream moves up by r * addD bytes and nothing has to wait
+                        // for the barcode table: the rest of the record goes out while the table entry is on its way,
+                        // then " BC:" + barcode + "\n" is written behind the header, over the head of the sequence line
+                        // (already copied), and header + tag go out as one run.  A record that does not fit the assumption
+                        // raises F_NEED_ORDERED: sk_wait repeats the operator in the ordered form below.
+                        uint32_t e = L1;
+                        while (has && e > L0 && is_ws(win[e - 1])) e--;  // header.trim_end()  (:33)
+                        const uint32_t alen = e - L0;
+                        RecRef rr;
+                        rr.seq_off = 0, rr.seq_len = (uint16_t)(addD - 4u), rr.flags = 0;
+                        uint4 bq0 = make_uint4(0u, 0u, 0u, 0u), bq1 = bq0;
+                        const bool binl = p.bc_inline != nullptr && addD <= 36u;  // the barcode's bytes come with the table entry
+#if !SKW_ADDBC_NOLOAD
+                        if (has && bc_n) {
+                            const unsigned long long bi = rec < bc_n ? rec : bc_n - 1ull;
+                            rr = p.ext_tab[0][bi];
+                            if (binl) {
+                                bq0 = p.bc_inline[2ull * bi];
+                                if (addD > 20u) bq1 = p.bc_inline[2ull * bi + 1ull];
+                            }
+                        }
+#endif
+                        if (r0 == 0) {
+                            s_l0 = __shfl_sync(FULL, L0, 0);
+                            s_obase = c0 + s_l0 + rec0 * addD;
+                            const uint32_t tile_outb = (LB(j0 + nrec * 4u) - s_l0) + nrec * addD;
+                            out_done = true;
+                            s_writable = p.out != nullptr;
+                            if (s_writable && s_obase + tile_outb > p.out_cap) {
+                                if (lane == 0) report_err(st, rec0, K_OUT_OVERFLOW);
+                                s_writable = false;
+                            }
+                        }
+                        uint8_t *gd = p.out + s_obase + (L0 - s_l0) + r * addD;
+                        const uint32_t hl = alen + 1u + addD;
+                        const bool fits = hl <= L4 - L0;
+                        if (s_writable) gcopy(gd + hl, win, L1, has ? L4 - L1 : 0u);
+                        __syncwarp();
+                        const bool uni = !has || (win[L0] == '@' && !(rr.flags & RR_LONG) && alen + 1u == L1 - L0 && (uint32_t)rr.seq_len + 4u == addD);
+                        if (!__all_sync(FULL, uni)) {
+                            if (lane == 0) atomicOr(&st->flags, F_NEED_ORDERED);
+                        } else if (s_writable) {
+#if SKW_ADDBC_NOLOAD
+                            const uint8_t *bsrc = win + L3;
+#else
+                            const uint8_t *bsrc = p.ext_data[0] + rr.seq_off;
+#endif
+                            const uint32_t bl = addD - 4u;
+                            if (has && fits) {
+                                uint8_t *d = win + L0 + alen;
+                                d[0] = ' '; d[1] = 'B'; d[2] = 'C'; d[3] = ':';
+                                if (binl) {
+                                    const uint32_t bw[8] = {bq0.x, bq0.y, bq0.z, bq0.w, bq1.x, bq1.y, bq1.z, bq1.w};
+#pragma unroll
+                                    for (uint32_t t = 0; t < 32u; t++)
+                                        if (t < bl) d[4u + t] = (uint8_t)(bw[t >> 2] >> (8u * (t & 3u)));
+                                } else {
+#pragma unroll 4
+                                    for (uint32_t t = 0; t < bl; t++) d[4u + t] = bsrc[t];
+                                }
+                                d[4u + bl] = '\n';
+                            }
+                            __syncwarp();
+                            gcopy(gd, win, L0, has && fits ? hl : 0u);
+                            if (has && !fits) {  // rare: a record shorter than its new header line
+                                uint8_t *d = gd;
+#pragma unroll 1
+                                for (uint32_t i = 0; i < alen; i++) *d++ = win[L0 + i];
+                                d[0] = ' '; d[1] = 'B'; d[2] = 'C'; d[3] = ':';
+                                d += 4;
+#pragma unroll 1
+                                for (uint32_t t = 0; t < bl; t++) *d++ = bsrc[t];
+                                *d = '\n';
+                            }
+                        }
+                        __syncwarp();
+                        continue;
+                    }
                     uint32_t a_alen = 0, a_bl = 0, a_bo = 0;
                     if (OP == OP_ADDBC) slen = addbc_plan(has, rec, L0, L1, L4, a_alen, a_bl, a_bo, errk);
                     if (has && errk) report_err(st, rec, errk);
@@ -753,15 +843,6 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                             if (lane == 0) report_err(st, rec0, K_OUT_OVERFLOW);
                             s_writable = false;
                         }
-                    } else if (r0 == 0 && OP == OP_ADDBC && p.inplace) {
-                        // add barcode with one barcode length: record r of the stream moves up by r * addD bytes
-                        s_obase = c0 + __shfl_sync(FULL, L0, 0) + rec0 * addD;
-                        out_done = true;
-                        s_writable = p.out != nullptr && tile_outb > 0;
-                        if (s_writable && s_obase + tile_outb > p.out_cap) {
-                            if (lane == 0) report_err(st, rec0, K_OUT_OVERFLOW);
-                            s_writable = false;
-                        }
                     } else if (r0 == 0) {
                         s_obase = wlb_consume(p.tile_out, oagg16, c, tile_outb, lane);
                         out_done = true;
@@ -810,14 +891,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                         }
                     }
                     if (OP == OP_ADDBC) {
-                        bool wr = s_writable;
-                        if (p.inplace && __any_sync(FULL, has && slen != (L4 - L0) + addD)) {
-                            // a barcode of another length, a header that ends in white space, a failing record: the output
-                            // offsets are not the input offsets plus a multiple of addD; sk_wait runs the ordered form
-                            if (lane == 0) atomicOr(&st->flags, F_NEED_ORDERED);
-                            wr = false;
-                        }
-                        if (wr) {
+                        if (s_writable) {  // ordered form
                             // the rest of the record goes out first; then " BC:" + barcode + "\n" is written behind the
                             // trimmed header, over the head of the sequence line, and header + tag go out as one run
                             uint8_t *gd = p.out + s_obase + my_off;
