@@ -35,7 +35,7 @@ extern __shared__ __align__(128) unsigned char sk_smem[];
 
 namespace sk {
 
-constexpr uint32_t CB_ROWS = 1024;  // slice-table rows per compaction block (256 tiles of the warp engine)
+constexpr uint32_t CB_ROWS = 512;  // slice-table rows per compaction block (128 tiles of the warp engine)
 
 // ---- hist ----------------------------------------------------------------------------------------
 // One warp takes 32 rows at a time (one 16-byte row per lane, coalesced), then walks the non-empty ones.
@@ -79,29 +79,52 @@ __global__ void __launch_bounds__(256) sk_compact_hist_kernel(const ChunkRow *__
 }
 
 // ---- cols ----------------------------------------------------------------------------------------
-// Thread s: offs[b][s] = sum of hist[b'][s] over b' < b (eight independent loads per step), total[s].
-__global__ void __launch_bounds__(128) sk_compact_cols_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ offs,
-                                                              uint32_t nb, uint32_t S, unsigned long long *__restrict__ total) {
-    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= S) return;
-    unsigned long long run = 0;
-    uint32_t b = 0;
-    for (; b + 8u <= nb; b += 8u) {
-        uint32_t v[8];
+// offs[b][s] = sum of hist[b'][s] over b' < b, total[s].  A CTA owns 64 samples (threadIdx.x: consecutive samples,
+// coalesced rows of the table) and cuts the blocks into 16 ranges (threadIdx.y): every thread sums its range, the
+// ranges' sums are scanned through shared memory, and a second walk over the range writes the prefixes.
+constexpr uint32_t CL_S = 64, CL_R = 16;
+__global__ void __launch_bounds__(CL_S * CL_R) sk_compact_cols_kernel(const uint32_t *__restrict__ hist, uint32_t *__restrict__ offs,
+                                                                    uint32_t nb, uint32_t S, unsigned long long *__restrict__ total) {
+    __shared__ unsigned long long part[CL_R][CL_S];
+    const uint32_t s = blockIdx.x * CL_S + threadIdx.x, y = threadIdx.y;
+    const uint32_t per = (nb + CL_R - 1u) / CL_R;
+    const uint32_t b0 = min(y * per, nb), b1 = min(b0 + per, nb);
+    const bool live = s < S;
+    unsigned long long sum = 0;
+    if (live) {
+        uint32_t b = b0;
+        for (; b + 8u <= b1; b += 8u) {
+            uint32_t v[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) v[k] = hist[(size_t)(b + k) * S + s];
+            for (int k = 0; k < 8; k++) v[k] = hist[(size_t)(b + k) * S + s];
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            offs[(size_t)(b + k) * S + s] = (uint32_t)run;
-            run += v[k];
+            for (int k = 0; k < 8; k++) sum += v[k];
         }
+        for (; b < b1; b++) sum += hist[(size_t)b * S + s];
     }
-    for (; b < nb; b++) {
-        const uint32_t v = hist[(size_t)b * S + s];
-        offs[(size_t)b * S + s] = (uint32_t)run;
-        run += v;
+    part[y][threadIdx.x] = sum;
+    __syncthreads();
+    unsigned long long run = 0;
+    for (uint32_t k = 0; k < y; k++) run += part[k][threadIdx.x];
+    if (live) {
+        uint32_t b = b0;
+        for (; b + 8u <= b1; b += 8u) {
+            uint32_t v[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = hist[(size_t)(b + k) * S + s];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                offs[(size_t)(b + k) * S + s] = (uint32_t)run;
+                run += v[k];
+            }
+        }
+        for (; b < b1; b++) {
+            const uint32_t v = hist[(size_t)b * S + s];
+            offs[(size_t)b * S + s] = (uint32_t)run;
+            run += v;
+        }
+        if (y == CL_R - 1u) total[s] = run;
     }
-    total[s] = run;
 }
 
 // ---- bases ---------------------------------------------------------------------------------------
@@ -160,34 +183,70 @@ __global__ void __launch_bounds__(32) sk_compact_addr_kernel(const ChunkRow *__r
     const uint32_t *o = offs + (size_t)blockIdx.x * S;
     for (uint32_t s = (uint32_t)lane; s < S; s += 32u) running[s] = slices[2 * s] + o[s];
     __syncwarp();
-    for_rows_of_block(rows, n_rows, blockIdx.x, 0, 1, lane, [&](unsigned long long, uint32_t fg, uint32_t ng) {
-        for (uint32_t k0 = 0; k0 < ng; k0 += 32u) {
-            const uint32_t k = k0 + (uint32_t)lane;
-            Group g;
-            g.sample = 0xFFFFu, g.len = 0;
-            if (k < ng) g = groups[fg + k];
-            const bool act = g.len != 0 && g.sample < S;
-            // lanes of one sample, lowest lane = earliest piece; an idle lane is a group of its own
-            const uint32_t key = act ? (uint32_t)g.sample : 0x10000u + (uint32_t)lane;
-            const uint32_t peers = __match_any_sync(FULL, key);
-            uint32_t lower = peers & ((1u << lane) - 1u);
-            uint32_t pre = 0;
-            while (__any_sync(FULL, lower != 0u)) {  // bytes of the same sample in lower lanes (a few at most)
-                const int j = lower ? __ffs((int)lower) - 1 : lane;
-                const uint32_t v = __shfl_sync(FULL, (uint32_t)g.len, j);
-                if (lower) {
-                    pre += v;
-                    lower &= lower - 1;
-                }
-            }
-            unsigned long long base = 0;
-            if (act) base = running[g.sample];
-            __syncwarp();
-            if (act && (peers >> lane) == 1u) running[g.sample] = base + pre + g.len;  // the group's last lane
-            __syncwarp();
-            if (act) piece_dst[fg + k] = base + pre;
+    // The rows are taken 32 at a time (one per lane, coalesced) and the non-empty ones walked in order; the groups
+    // of the next non-empty row (and the next 32 rows) are fetched while the current row is worked on.
+    const uint32_t r0 = blockIdx.x * CB_ROWS, r1 = min(r0 + CB_ROWS, n_rows);
+    auto load_rows = [&](uint32_t rb) -> ChunkRow {
+        ChunkRow row;
+        row.base = 0, row.first_group = 0, row.n_groups = 0;
+        const uint32_t r = rb + (uint32_t)lane;
+        if (rb < r1 && r < r1) row = rows[r];
+        return row;
+    };
+    auto load_group = [&](uint32_t fg, uint32_t ng, uint32_t k0) -> Group {
+        Group g;
+        g.sample = 0xFFFFu, g.len = 0;
+        const uint32_t k = k0 + (uint32_t)lane;
+        if (k < ng) g = groups[fg + k];
+        return g;
+    };
+    ChunkRow row = load_rows(r0);
+    for (uint32_t rb = r0; rb < r1; rb += 32u) {
+        const ChunkRow row_next = load_rows(rb + 32u);
+        uint32_t todo = __ballot_sync(FULL, row.n_groups != 0u);
+        Group g_pre;
+        g_pre.sample = 0xFFFFu, g_pre.len = 0;
+        if (todo) {
+            const int q = __ffs((int)todo) - 1;
+            g_pre = load_group(__shfl_sync(FULL, row.first_group, q), __shfl_sync(FULL, row.n_groups, q), 0u);
         }
-    });
+        while (todo) {
+            const int q = __ffs((int)todo) - 1;
+            todo &= todo - 1;
+            const uint32_t fg = __shfl_sync(FULL, row.first_group, q);
+            const uint32_t ng = __shfl_sync(FULL, row.n_groups, q);
+            Group g = g_pre;
+            if (todo) {  // the next non-empty row's groups
+                const int qn = __ffs((int)todo) - 1;
+                g_pre = load_group(__shfl_sync(FULL, row.first_group, qn), __shfl_sync(FULL, row.n_groups, qn), 0u);
+            }
+            for (uint32_t k0 = 0; k0 < ng; k0 += 32u) {
+                const uint32_t k = k0 + (uint32_t)lane;
+                if (k0) g = load_group(fg, ng, k0);
+                const bool act = g.len != 0 && g.sample < S;
+                // lanes of one sample, lowest lane = earliest piece; an idle lane is a group of its own
+                const uint32_t key = act ? (uint32_t)g.sample : 0x10000u + (uint32_t)lane;
+                const uint32_t peers = __match_any_sync(FULL, key);
+                uint32_t lower = peers & ((1u << lane) - 1u);
+                uint32_t pre = 0;
+                while (__any_sync(FULL, lower != 0u)) {  // bytes of the same sample in lower lanes (a few at most)
+                    const int j = lower ? __ffs((int)lower) - 1 : lane;
+                    const uint32_t v = __shfl_sync(FULL, (uint32_t)g.len, j);
+                    if (lower) {
+                        pre += v;
+                        lower &= lower - 1;
+                    }
+                }
+                unsigned long long base = 0;
+                if (act) base = running[g.sample];
+                __syncwarp();
+                if (act && (peers >> lane) == 1u) running[g.sample] = base + pre + g.len;  // the group's last lane
+                __syncwarp();
+                if (act) piece_dst[fg + k] = base + pre;
+            }
+        }
+        row = row_next;
+    }
 }
 
 // ---- move ----------------------------------------------------------------------------------------
@@ -196,6 +255,9 @@ __global__ void __launch_bounds__(32) sk_compact_addr_kernel(const ChunkRow *__r
 // window to its destination (gcopy: whole 32-byte sectors inside the piece, small stores at its two ends,
 // which share their sectors with the neighbouring pieces of the sample's run).  Rows that do not fit the
 // window, hold more than 32 pieces or start off a 16-byte boundary take the piece-by-piece copy above.
+#ifndef SKC_WARP_PIECE
+#define SKC_WARP_PIECE 1  // 1: the warp copies a row's pieces one by one (contiguous stores); 0: one lane per piece (gcopy)
+#endif
 constexpr uint32_t MV_ROW = 12288;               // bytes of a row the window holds
 constexpr uint32_t MV_WIN = MV_ROW + 96;         // + slack: gcopy reads whole aligned words past a piece
 constexpr int MV_WARPS = 6;                      // 6 x 12.1 KB: three CTAs per SM
@@ -277,7 +339,50 @@ __global__ void __launch_bounds__(MV_WARPS * 32) sk_compact_move_kernel(const Ch
                         parity ^= 1u;
                     }
                     __syncwarp();
+#if SKC_WARP_PIECE
+                    {   // the warp copies the row's pieces one after the other: 16 destination-aligned bytes per lane
+                        // (two aligned 16-byte reads of the window, shifted into place), the piece's first and last
+                        // bytes -- which share their 16 bytes with the neighbouring pieces of the sample's run -- one
+                        // per lane.  A piece is a few contiguous store wavefronts, not one per lane and sector.
+                        const uint32_t live = __ballot_sync(FULL, mine);
+                        const uint32_t my_so = incl - g.len;
+                        uint32_t rest = live;
+#pragma unroll 2
+                        while (rest) {
+                            const int j = __ffs((int)rest) - 1;
+                            rest &= rest - 1;
+                            const unsigned long long d_o = __shfl_sync(FULL, pd, j);
+                            const uint32_t so = __shfl_sync(FULL, my_so, j), len = __shfl_sync(FULL, (uint32_t)g.len, j);
+                            uint8_t *d = dst + d_o;
+                            const uint32_t head = min((16u - ((uint32_t)(uintptr_t)d & 15u)) & 15u, len);
+                            const uint32_t body = (len - head) >> 4, tail = (len - head) & 15u;
+                            const uint32_t sb = so + head;                 // window offset of the first whole unit
+                            const uint32_t wo = (sb & 15u) >> 2, bs = (sb & 3u) * 8u;
+                            for (uint32_t u = (uint32_t)lane; u < body; u += 32u) {
+                                const uint8_t *sp = win + ((sb + 16u * u) & ~15u);
+                                const uint4 A = *(const uint4 *)sp, B = *(const uint4 *)(sp + 16);
+                                const uint32_t W[8] = {A.x, A.y, A.z, A.w, B.x, B.y, B.z, B.w};
+                                uint4 o4;
+                                switch (wo) {  // uniform over the piece
+                                    case 0: o4 = make_uint4(__funnelshift_r(W[0], W[1], bs), __funnelshift_r(W[1], W[2], bs), __funnelshift_r(W[2], W[3], bs), __funnelshift_r(W[3], W[4], bs)); break;
+                                    case 1: o4 = make_uint4(__funnelshift_r(W[1], W[2], bs), __funnelshift_r(W[2], W[3], bs), __funnelshift_r(W[3], W[4], bs), __funnelshift_r(W[4], W[5], bs)); break;
+                                    case 2: o4 = make_uint4(__funnelshift_r(W[2], W[3], bs), __funnelshift_r(W[3], W[4], bs), __funnelshift_r(W[4], W[5], bs), __funnelshift_r(W[5], W[6], bs)); break;
+                                    default: o4 = make_uint4(__funnelshift_r(W[3], W[4], bs), __funnelshift_r(W[4], W[5], bs), __funnelshift_r(W[5], W[6], bs), __funnelshift_r(W[6], W[7], bs)); break;
+                                }
+                                *(uint4 *)(d + head + 16u * u) = o4;
+                            }
+                            // lanes 0..15: the bytes before the first whole unit; lanes 16..31: those behind the last
+                            const uint32_t e = (uint32_t)lane & 15u;
+                            const bool hi = lane >= 16;
+                            if (e < (hi ? tail : head)) {
+                                const uint32_t o = hi ? head + 16u * body + e : e;
+                                d[o] = win[so + o];
+                            }
+                        }
+                    }
+#else
                     if (mine) gcopy(dst + pd, win, incl - g.len, g.len);
+#endif
                     __syncwarp();
                 } else {
                     const unsigned long long ps = run + incl - g.len;
@@ -325,7 +430,7 @@ int launch_compact(const ChunkRow *rows, const Group *groups, uint32_t n_rows, u
         return 0;
     }
     sk_compact_hist_kernel<<<nb, 256, S * 4, stream>>>(rows, groups, n_rows, S, hist);
-    sk_compact_cols_kernel<<<(S + 127) / 128, 128, 0, stream>>>(hist, offs, nb, S, total);
+    sk_compact_cols_kernel<<<(S + CL_S - 1) / CL_S, dim3(CL_S, CL_R), 0, stream>>>(hist, offs, nb, S, total);
     sk_compact_bases_kernel<<<1, 1024, 0, stream>>>(total, S, slices, dst_cap, st);
     sk_compact_addr_kernel<<<nb, 32, S * 8, stream>>>(rows, groups, n_rows, S, offs, slices, piece_dst);
     const unsigned want = (n_rows + 4u * MV_WARPS - 1u) / (4u * MV_WARPS);  // MV_WARPS warps x 4 rows per CTA and ticket
