@@ -50,7 +50,11 @@ struct CfgB {  // 32 KiB chunks, 8 warps
 // (KParams::tile_lanes, 29 unless the records are short), the remaining lanes' bytes are the overhang.
 struct GeoW {
     static constexpr int ID = 2;
+#ifdef SKW_WARPS
+    static constexpr int WARPS = SKW_WARPS;  // experiment: one CTA of 16 warps per SM
+#else
     static constexpr int WARPS = 8;
+#endif
     static constexpr int NT = WARPS * 32;
     static constexpr int UPL = 25;
     static constexpr int LANE_BYTES = UPL * 16;           // 400
@@ -59,7 +63,7 @@ struct GeoW {
     static constexpr int ROUNDS = 4;                      // rounds of 32 records; one slice-table row each
     static constexpr int MAXREC = 32 * ROUNDS;
     static constexpr int MAXLINES = 4 * MAXREC + 8;
-    static constexpr int MIN_CTAS = 2;
+    static constexpr int MIN_CTAS = 16 / WARPS;
 };
 constexpr int FAST_CCOUNT_MAX = 1024;  // per-sample counters live in shared memory up to this many samples
 inline int cfg_chunk_bytes(int cfg) { return cfg == CfgB::ID ? CfgB::CHUNK : CfgA::CHUNK; }

@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
         }
     }
     constexpr int GW = SKW_GROUP_WARPS;  // warps of a group; its first warp is the group's leader
-    static_assert(GW == 8 || GW == 4, "groups of 8 or 4 warps");
+    static_assert(GW == GeoW::WARPS || GW == 4, "groups of 4 warps, or the whole CTA");
     const bool g_lead = (tid % (GW * 32)) == 0;
     const int wg = warp % GW;
     if (g_lead) {  // the group's ticket slots (below): 0 is never newer than a ticket
@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
         if (LS) {
             if (g_lead) cta_ticket[flipk] = cta_have ? cta_next : atomicAdd(&st->ticket, (uint32_t)GW);
             cta_have = false;
-            if (GW == 8) __syncthreads();
+            if (GW == GeoW::WARPS) __syncthreads();
             else asm volatile("bar.sync %0, %1;" ::"r"(1 + warp / GW), "r"(GW * 32) : "memory");
             cb = cta_ticket[flipk];
             flipk ^= 1u;
@@ -1554,7 +1554,7 @@ bool warp_supported(int op, const KParams &p) {
     if (op != OP_DEMUX1 && op != OP_DEMUX2) return false;
     if (p.n_index || !p.sheet.hidx.n_classes || !p.sheet.fidx.table) return false;
     if (p.tile_lanes < 8 || p.tile_lanes > 30) return false;
-    return warp_smem(p.sheet.S, p.sheet.hidx.n_classes, p.sheet.hidx.nwp, true) <= 115200u;
+    return warp_smem(p.sheet.S, p.sheet.hidx.n_classes, p.sheet.hidx.nwp, true) <= (GeoW::WARPS == 8 ? 115200u : 231000u);
 }
 
 template <int OP, int NWMAX>

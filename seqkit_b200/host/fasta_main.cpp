@@ -1257,6 +1257,7 @@ static int run_demultiplex(int argc, char **argv) {
         }
         const int arc = sk_allreduce_totals(g.ctxs.data(), g.G);
         if (saved >= 0) {
+            fflush(stdout);  // what the library left in the stdio buffer goes to /dev/null too
             dup2(saved, 1);
             close(saved);
         }

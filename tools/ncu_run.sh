@@ -7,4 +7,6 @@ ncu --set full --clock-control none --import-source on -k regex:'sk_(chunk|warp)
 ncu --set full --clock-control none --import-source on -k regex:'sk_warp_kernel' -s 14 -c 1 -f -o gpurun_out/prof_trim $B > gpurun_out/ncu_trim.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'sk_warp_kernel' -s 20 -c 1 -f -o gpurun_out/prof_mask $B > gpurun_out/ncu_mask.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:'sk_compact_move' -s 2 -c 1 -f -o gpurun_out/prof_move $B > gpurun_out/ncu_move.log 2>&1
+# add barcode on the warp engine: tools/stream_time.py launches sk_warp_kernel 7 x for trim, 7 x for mask, then add barcode (1 M reads)
+ncu --set full --clock-control none --import-source on -k regex:'sk_warp_kernel' -s 16 -c 1 -f -o gpurun_out/prof_addbc python tools/stream_time.py 1000000 > gpurun_out/ncu_addbc.log 2>&1
 tail -3 gpurun_out/ncu_head.log | cut -c1-300

@@ -68,7 +68,8 @@ def take(nm, r):
 
 for nm, r in zip(("DEMUX1", "DEMUX2"), raw[2:]):
     take(nm, r)
-for nm, fn in (("TRIM", "prof_trim.ncu-rep"), ("MASK", "prof_mask.ncu-rep"), ("COMPACT_MOVE", "prof_move.ncu-rep")):
+for nm, fn in (("TRIM", "prof_trim.ncu-rep"), ("MASK", "prof_mask.ncu-rep"), ("COMPACT_MOVE", "prof_move.ncu-rep"),
+               ("ADDBC", "prof_addbc.ncu-rep")):
     rp = os.path.join(G, fn)
     if not os.path.exists(rp):
         continue
