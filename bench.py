@@ -482,6 +482,17 @@ def main():
         dist.destroy_process_group()
 
 
+def _nth_newline(buf, k):
+    """Offset just past the k-th newline of buf (len(buf) if it has fewer)."""
+    pos = 0
+    for _ in range(k):
+        j = buf.find(b"\n", pos)
+        if j < 0:
+            return len(buf)
+        pos = j + 1
+    return pos
+
+
 def run_cli_leg(args, bcs, local_rank, with_cpu=True):
     """Third number of SURVEY 8(d): end to end WITH files and gzip.  The drop-in `fasta` binary
     (`demultiplex --trim-by-quality=Q`, its one-pass form of the benchmark's pipeline) reads two plain FASTQ
@@ -526,6 +537,19 @@ def run_cli_leg(args, bcs, local_rank, with_cpu=True):
                 time.sleep(0.2)
             return last
 
+        # one untimed invocation on the first 2 000 pairs: the first CUDA process of a fresh box pays one-off costs
+        # (driver and library page-in) that belong to the box, not to the run; its wall time is reported beside
+        d_warm = os.path.join(top, "warm")
+        os.mkdir(d_warm)
+        cut1, cut2 = _nth_newline(r1, 8000), _nth_newline(r2, 8000)
+        for name, data in (("w1.fq", r1[:cut1]), ("w2.fq", r2[:cut2])):
+            with open(os.path.join(top, name), "wb") as f:
+                f.write(data)
+        t0 = time.perf_counter()
+        subprocess.run([fasta, "demultiplex", "--trim-by-quality=%d" % MIN_BASEQ, "../sheet.tsv", "../w1.fq", "../w2.fq"],
+                       cwd=d_warm, env=env, capture_output=True, timeout=600)
+        dt_warm = time.perf_counter() - t0
+        shutil.rmtree(d_warm, ignore_errors=True)
         d_ours = os.path.join(top, "ours")
         os.mkdir(d_ours)
         t0 = time.perf_counter()
@@ -536,6 +560,7 @@ def run_cli_leg(args, bcs, local_rank, with_cpu=True):
             raise RuntimeError("fasta demultiplex: exit %d: %s" % (p.returncode, p.stderr[-300:].decode("utf-8", "replace")))
         gz_ours = settle(d_ours)
         res = {"value": 2.0 * n / dt_ours, "unit": "reads/s", "seconds": dt_ours, "pairs": n,
+               "warmup_invocation_seconds": dt_warm,
                "gz_bytes_out": gz_ours, "summary": p.stderr.decode("utf-8", "replace").strip().splitlines()[-1][:200],
                "note": "fasta demultiplex --trim-by-quality=%d sheet r1.fq r2.fq: process start, CUDA context, file "
                        "reads, kernels, compaction, %d .fq.gz files through block-parallel deflate (zlib level 4); wall clock"

@@ -95,9 +95,10 @@ typedef struct sk_result {
     uint32_t n_chunks[2];           /* rows of the demux slice table per output stream */
     uint32_t n_events;              /* ambiguity events (fasta_demultiplex.rs:184-188) */
     uint32_t gpu_launches;          /* kernels this call enqueued */
-    uint32_t reserved;              /* diagnostic: bit0 = the warp or lean engine (sk_warp.cu, sk_fast.cu) ran, bit1 = the
+    uint32_t reserved;              /* diagnostic: bit0 = the warp engine (sk_warp.cu) ran, bit1 = the
                                        operator met something outside its limits and was re-run on the general engine, bit2 = mask by
-                                       quality met a record that changes its length (or fails) and was re-run in its ordered form, bit3 =
+                                       quality met a record that changes its length (or fails), or add barcode a record that does not
+                                       grow like the first, and the pass was re-run in its ordered form, bit3 =
                                        the demultiplex output was compacted per sample (sk_demux_compact), bit4 = trim / mask by
                                        quality ended up on the line engine (long or dense records, UTF-8 header lines) */
     float pass_ms[SK_N_INPUTS];     /* device time of the chunk-engine kernel over each input stream

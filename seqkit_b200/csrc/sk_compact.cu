@@ -184,7 +184,8 @@ __global__ void __launch_bounds__(32) sk_compact_addr_kernel(const ChunkRow *__r
     for (uint32_t s = (uint32_t)lane; s < S; s += 32u) running[s] = slices[2 * s] + o[s];
     __syncwarp();
     // The rows are taken 32 at a time (one per lane, coalesced) and the non-empty ones walked in order; the groups
-    // of the next non-empty row (and the next 32 rows) are fetched while the current row is worked on.
+    // of the batch's first eight non-empty rows are fetched at once (and the next 32 rows meanwhile), so that the walk
+    // itself waits for no load.
     const uint32_t r0 = blockIdx.x * CB_ROWS, r1 = min(r0 + CB_ROWS, n_rows);
     auto load_rows = [&](uint32_t rb) -> ChunkRow {
         ChunkRow row;
@@ -204,25 +205,37 @@ __global__ void __launch_bounds__(32) sk_compact_addr_kernel(const ChunkRow *__r
     for (uint32_t rb = r0; rb < r1; rb += 32u) {
         const ChunkRow row_next = load_rows(rb + 32u);
         uint32_t todo = __ballot_sync(FULL, row.n_groups != 0u);
-        Group g_pre;
-        g_pre.sample = 0xFFFFu, g_pre.len = 0;
-        if (todo) {
-            const int q = __ffs((int)todo) - 1;
-            g_pre = load_group(__shfl_sync(FULL, row.first_group, q), __shfl_sync(FULL, row.n_groups, q), 0u);
+        // the first groups of up to eight non-empty rows at once (a tile of the warp engine fills one row in four)
+        constexpr int PF = 8;
+        Group gq[PF];
+        {
+            uint32_t t = todo;
+#pragma unroll
+            for (int i = 0; i < PF; i++) {
+                gq[i].sample = 0xFFFFu, gq[i].len = 0;
+                if (t) {
+                    const int q = __ffs((int)t) - 1;
+                    t &= t - 1;
+                    gq[i] = load_group(__shfl_sync(FULL, row.first_group, q), __shfl_sync(FULL, row.n_groups, q), 0u);
+                }
+            }
         }
+        int qi = 0;
         while (todo) {
             const int q = __ffs((int)todo) - 1;
             todo &= todo - 1;
             const uint32_t fg = __shfl_sync(FULL, row.first_group, q);
             const uint32_t ng = __shfl_sync(FULL, row.n_groups, q);
-            Group g = g_pre;
-            if (todo) {  // the next non-empty row's groups
-                const int qn = __ffs((int)todo) - 1;
-                g_pre = load_group(__shfl_sync(FULL, row.first_group, qn), __shfl_sync(FULL, row.n_groups, qn), 0u);
-            }
+            Group g;
+            g.sample = 0xFFFFu, g.len = 0;
+            bool have = false;
+#pragma unroll
+            for (int i = 0; i < PF; i++)
+                if (i == qi) g = gq[i], have = true;
+            qi++;
             for (uint32_t k0 = 0; k0 < ng; k0 += 32u) {
                 const uint32_t k = k0 + (uint32_t)lane;
-                if (k0) g = load_group(fg, ng, k0);
+                if (k0 || !have) g = load_group(fg, ng, k0);
                 const bool act = g.len != 0 && g.sample < S;
                 // lanes of one sample, lowest lane = earliest piece; an idle lane is a group of its own
                 const uint32_t key = act ? (uint32_t)g.sample : 0x10000u + (uint32_t)lane;
