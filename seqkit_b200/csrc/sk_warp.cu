@@ -1376,6 +1376,10 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
             if (lane == 0 && !have_next) c_next = atomicAdd(&st->ticket, 1u);
             c = __shfl_sync(FULL, c_next, 0);
         } else {  // the CTA's next ticket may be known already (tickets only grow): start the next load now
+            // (An unsynchronised peek at a word only the group's leader writes -- compute-sanitizer's racecheck reports
+            // it against the two stores above.  Either the slot still holds the ticket of two tiles ago, which is not
+            // newer than this tile's and is ignored, or the leader's next ticket, which the barrier at the top of the
+            // loop hands to every warp anyway.)
             const uint32_t v = cta_ticket[flipk];
             if (v > cb && v + (uint32_t)wg < p.n_chunks) {
                 issue_load(v + (uint32_t)wg);
