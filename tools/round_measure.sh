@@ -2,7 +2,7 @@
 # and full captures of the hot kernels (1 M pairs per launch).  Outputs under gpurun_out/; tools/refresh_profiles.py r2_warp
 # then copies the summaries into profiles/.
 set -x
-timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 > gpurun_out/rm_tests.log
+timeout 900 python -m pytest tests -m gpu -x -q --durations=12 2>&1 | tail -30 > gpurun_out/rm_tests.log
 timeout 120 python __graft_entry__.py smoke > gpurun_out/rm_smoke.log 2>&1
 timeout 600 python bench.py > gpurun_out/rm_bench.json 2> gpurun_out/rm_bench.err
 timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/rm_bench_ref.json 2> gpurun_out/rm_bench_ref.err
