@@ -96,6 +96,15 @@ static void fatal(proc *P, const char *fmt, ...) {
     P->exit_code = ORC_EXIT_ERROR;
     longjmp(P->jb, 1);
 }
+/* error!("<prefix>{line}") with a line of any length */
+static void fatal_line(proc *P, const char *prefix, const uint8_t *line, size_t n) {
+    ob_puts(&P->err, "ERROR: ");
+    ob_puts(&P->err, prefix);
+    ob_put(&P->err, line, n);
+    ob_putc(&P->err, '\n');
+    P->exit_code = ORC_EXIT_ERROR;
+    longjmp(P->jb, 1);
+}
 /* Rust panic (unwrap / slice OOB / assert): message text is rustc-version dependent, so
  * only the status (101) and "stderr non-empty" are part of the contract. */
 static void rust_panic(proc *P, const char *what) {
@@ -321,9 +330,7 @@ static void run_add_barcode(proc *P, const uint8_t *fq, size_t n, const uint8_t 
             read_line(P, &fastq, &line);
             ob_put(&P->out, line.s, line.n);
         } else { /* :41-43 */
-            char msg[900];
-            snprintf(msg, sizeof msg, "Invalid FASTQ line:\n%.*s", (int)(header.n > 800 ? 800 : header.n), header.s);
-            fatal(P, "%s", msg);
+            fatal_line(P, "Invalid FASTQ line:\n", header.s, header.n);
         }
     }
 }
@@ -440,9 +447,7 @@ static void run_demux(demux_t *D, const uint8_t *sheet, size_t ns, const uint8_t
     obuf hdr = {0}, barcode = {0}, umi = {0}, l2 = {0};
     while (read_line(P, &fastq[0], &header)) { /* :117 */
         if (!starts_with(&header, '@')) {       /* :118-120 */
-            char msg[900];
-            snprintf(msg, sizeof msg, "Invalid FASTQ header line:\n%.*s", (int)(header.n > 800 ? 800 : header.n), header.s);
-            fatal(P, "%s", msg);
+            fatal_line(P, "Invalid FASTQ header line:\n", header.s, header.n);
         }
         hdr.n = 0;
         ob_put(&hdr, header.s, header.n);

@@ -1103,7 +1103,48 @@ static int demux_enqueue(sk_ctx *ctx, Slot *s, const sk_demux_opts *o, bool fast
     return end_op(ctx, s);
 }
 
+// Header-route demultiplex on the line engine (sk_lineops.cu): what neither chunk engine takes -- records longer than the
+// general engine's overhang, more records in a chunk than it has slots for, UTF-8 in header and '+' lines.  Same tables and
+// buffers as demux_enqueue leaves.
+static int line_demux_enqueue(sk_ctx *ctx, Slot *s) {
+    const sk_demux_opts o = s->req_opts;
+    const uint32_t S = ctx->S;
+    int rc = begin_op(ctx, s, OP_DEMUX1);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(s->counts, 0, (uint64_t)(S + 2) * 8, s->stream));
+    SheetDev sh;
+    memset(&sh, 0, sizeof sh);
+    sh.planes = ctx->d_planes;
+    sh.umask = ctx->d_umask;
+    sh.lut = ctx->d_lut;
+    sh.S = S;
+    sh.L = ctx->L;
+    sh.Umax = ctx->Umax;
+    sh.wide = ctx->wide;
+    const int nm = s->paired ? 2 : 1;
+    for (int mate = 0; mate < nm; mate++) {
+        const int which = mate == 0 ? SK_IN_R1 : SK_IN_R2;
+        const char *err = nullptr;
+        uint32_t n_rows = 0;
+        const int n = launch_line_demux(mate, s->in[which], s->in_len[which], o.rec_limit, o.fused_trim_min_baseq, sh, s->assign, s->umi,
+                                        s->groups[mate], s->rows[mate], ctx->max_chunks, s->counts, s->events,
+                                        (uint32_t)std::min<uint64_t>(ctx->lim.max_records, 0xFFFFFFFFull), s->stats + SK_IN_R1,
+                                        o.no_output ? nullptr : s->out[mate], s->out_cap, s->lwork, ctx->lim.max_stream_bytes,
+                                        ctx->lim.max_records, s->stats + which, ctx->sm_count, s->stream, &n_rows, &err);
+        if (n < 0) {
+            ctx->err = std::string("line engine launch failed: ") + (err ? err : "?");
+            return SK_E_CUDA;
+        }
+        s->n_chunks[which] = n_rows;
+        s->launches += (uint32_t)n;
+        s->pass_ran[which] = true;
+    }
+    s->ran_line = true;
+    return end_op(ctx, s);
+}
+
 // Per-sample compaction of the last demultiplex of the slot (sk_compact.cu), both mates, on the slot's stream.
+static int compact_enqueue(sk_ctx *ctx, Slot *s);
 static int compact_enqueue(sk_ctx *ctx, Slot *s) {
     const uint32_t S = ctx->S;
     const int nm = s->paired ? 2 : 1;
@@ -1222,6 +1263,29 @@ extern "C" int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res) {
             int rc = end_op(ctx, s);
             if (rc) return rc;
             CK(cudaStreamSynchronize(s->stream));
+        }
+    }
+    if (s->last_op == OP_DEMUX1 && !s->ran_line && s->lwork && !s->req_opts.use_index) {
+        // The same last resort for header-route demultiplex (sk_result.reserved bit 4).
+        unsigned fl = 0;
+        unsigned long long key = ~0ull;
+        for (int i = 0; i < SK_N_INPUTS; i++) {
+            fl |= s->stats_h[i].flags;
+            if (s->stats_h[i].err_key) key = std::min(key, ~s->stats_h[i].err_key);
+        }
+        const unsigned kind = key == ~0ull ? 0u : (unsigned)(key & 0xFFu);
+        if ((fl & F_NON_ASCII) || kind == K_TOO_LONG || kind == K_TOO_DENSE) {
+            const uint32_t before = s->launches;
+            const bool again = s->want_compact || s->compacted;
+            int rc = line_demux_enqueue(ctx, s);
+            if (rc) return rc;
+            if (again) {
+                s->want_compact = true;
+                rc = compact_enqueue(ctx, s);
+                if (rc) return rc;
+            }
+            CK(cudaStreamSynchronize(s->stream));
+            s->launches += before;
         }
     }
     if (!res) return SK_OK;

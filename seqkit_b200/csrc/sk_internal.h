@@ -258,6 +258,12 @@ int launch_lineop(int op, const uint8_t *in_a, uint64_t n_a, const uint8_t *in_b
 int launch_scan_table(const uint8_t *in, uint64_t n, uint32_t lpr, uint32_t head_char, uint64_t rec_limit, uint32_t final_batch,
                       RecRef *out, uint4 *inline32, uint64_t cap, void *work, int k, uint64_t max_stream_bytes, uint64_t max_records,
                       DevStats *st, int sm_count, void *stream, const char **err);
+// Header-route demultiplex of one mate on the line engine (sk_lineops.cu): records of any length and density, UTF-8 headers
+int launch_line_demux(int mate, const uint8_t *in, uint64_t n, uint64_t rec_limit, int fused_trim, const SheetDev &sheet, int16_t *assign,
+                      uint8_t *umi, Group *groups, ChunkRow *rows, uint32_t max_rows, unsigned long long *counts, Event *events,
+                      uint32_t events_cap, const DevStats *r1_stats, uint8_t *out, uint64_t out_cap, void *work,
+                      uint64_t max_stream_bytes, uint64_t max_records, DevStats *st, int sm_count, void *stream, uint32_t *n_rows,
+                      const char **err);
 // Per-sample compaction of a demultiplex result (sk_compact.cu)
 uint64_t compact_work_bytes(uint32_t max_rows, uint32_t S);
 int launch_compact(const ChunkRow *rows, const Group *groups, uint32_t n_rows, uint32_t S, const uint8_t *src, uint8_t *dst,

@@ -671,6 +671,320 @@ static int index_lines(const uint8_t *in, uint64_t n, uint32_t lpr, const LineWo
     return nb ? 3 : 1;
 }
 
+// ---- demultiplex on the line engine ------------------------------------------------------------------
+// Header-route demultiplex (fasta_demultiplex.rs:117-249) for the batches neither chunk engine takes: records longer
+// than the general engine's overhang, denser than its record slots, UTF-8 in header and '+' lines.  One thread per record
+// plans (validate, leftmost " BC:x", length, distance to every sample over the sheet's bit planes, decide, UMI, header
+// pieces, fused quality trim, output length), an exclusive scan places the records, one warp per record writes its pieces.
+// The tables the other engines leave -- assign[], umi[], counts[], events, one (sample, len) group per record and one
+// slice-table row per 32 records -- are filled in the same form, so the compaction and the host code do not know the
+// difference.  A failing record is reported (lowest record first) and the host replays the batch up to it, as with the
+// other engines.  A record's output is limited to 64 KiB - 1 by the group table (SK_DATA_RECORD_TOO_LONG beyond).
+struct DParams {
+    LStream a;             // the mate's stream
+    uint32_t mate;         // 0: mate 1 (extract, match, decide, emit), 1: mate 2 (emit)
+    uint64_t rec_limit;
+    int32_t fused_trim;    // >= 0: trim by quality with this threshold first
+    SheetDev sheet;
+    int16_t *assign;
+    uint8_t *umi;
+    Group *groups;
+    ChunkRow *rows;
+    uint32_t max_rows;
+    unsigned long long *counts;
+    Event *events;
+    uint32_t events_cap;
+    const DevStats *r1_stats;
+    uint32_t *out_len, *kk;  // [records]; kk: bases kept by the fused trim (0 = the "N" record), 0xFFFFFFFF = three lines verbatim
+    uint64_t *dst;
+    uint8_t *out;            // nullptr: dry run
+    uint64_t out_cap;
+    DevStats *st;
+};
+__device__ __forceinline__ uint32_t dm_units(const DParams &p) {
+    uint32_t u = p.a.info->n_rec;
+    if ((uint64_t)u > p.rec_limit) u = (uint32_t)p.rec_limit;
+    return u;
+}
+// str::trim_end (Unicode White_Space) of valid UTF-8: the new length
+__device__ __forceinline__ uint32_t trim_end_unicode(const uint8_t *s, uint32_t n) {
+    for (;;) {
+        if (!n) return 0;
+        const uint8_t c = s[n - 1];
+        if (c < 0x80) {
+            if (!is_ws(c)) return n;
+            n--;
+            continue;
+        }
+        if (n >= 2 && s[n - 2] == 0xC2 && (c == 0x85 || c == 0xA0)) {  // U+0085, U+00A0
+            n -= 2;
+            continue;
+        }
+        if (n >= 3) {
+            const uint8_t a = s[n - 3], b = s[n - 2];
+            const bool ws = (a == 0xE1 && b == 0x9A && c == 0x80) ||                                                   // U+1680
+                            (a == 0xE2 && b == 0x80 && ((c >= 0x80 && c <= 0x8A) || c == 0xA8 || c == 0xA9 || c == 0xAF)) ||  // U+2000-200A, 2028, 2029, 202F
+                            (a == 0xE2 && b == 0x81 && c == 0x9F) ||                                                   // U+205F
+                            (a == 0xE3 && b == 0x80 && c == 0x80);                                                     // U+3000
+            if (ws) {
+                n -= 3;
+                continue;
+            }
+        }
+        return n;
+    }
+}
+// leftmost " BC:" followed by at least one class byte, greedy class run (fasta_demultiplex.rs:38,138-141)
+__device__ __forceinline__ bool dm_find_bc(const uint8_t *h, uint32_t n, const uint8_t *lut, uint32_t &st, uint32_t &en) {
+    for (uint32_t k = 0; k + 5 <= n; k++) {
+        if (h[k] == ' ' && h[k + 1] == 'B' && h[k + 2] == 'C' && h[k + 3] == ':' && (lut[h[k + 4]] & 8u)) {
+            uint32_t e = k + 5;
+            while (e < n && (lut[h[e]] & 8u)) e++;
+            st = k;
+            en = e;
+            return true;
+        }
+    }
+    return false;
+}
+// header.drain(st..en) then trim_end (:145,:206 / :219-229): the header is its first alen bytes and blen bytes from en
+__device__ __forceinline__ void dm_pieces(const uint8_t *h, uint32_t n, bool cut, uint32_t st, uint32_t en, uint32_t &alen, uint32_t &blen) {
+    if (!cut) {
+        alen = trim_end_unicode(h, n);
+        blen = 0;
+        return;
+    }
+    blen = trim_end_unicode(h + en, n - en);
+    alen = blen ? st : trim_end_unicode(h, st);
+}
+// fasta_trim_by_quality.rs:28-48 on one record: bases kept (0: the "N" record); false: &seq[..k] would panic (:47)
+__device__ __forceinline__ bool dm_trimq(const uint8_t *in, LineRef sq, LineRef ql, int minq, uint32_t &kept) {
+    uint32_t k = trim_end_len_dev(in + ql.s, ql.len);
+    int total = -50, lowest = -50;
+    uint32_t lowest_k = k;
+    while (k > 0) {
+        k--;
+        total += (int)(uint8_t)(in[ql.s + k] - 33u) - minq;
+        if (total > 0) break;
+        if (total < lowest) {
+            lowest = total;
+            lowest_k = k;
+        }
+    }
+    kept = lowest_k;
+    return lowest_k <= sq.len;
+}
+__device__ __forceinline__ bool dm_utf8_fine(const LStream &S, LineRef h, LineRef sq, LineRef pl, LineRef ql) {
+    const uint8_t *in = S.in;
+    bool bad = !utf8_ok(in + h.s, h.len) || !utf8_ok(in + pl.s, pl.len);
+    for (uint32_t t = 0; t < sq.len; t++) bad = bad || in[sq.s + t] >= 0x80;
+    for (uint32_t t = 0; t < ql.len; t++) bad = bad || in[ql.s + t] >= 0x80;
+    return !bad;
+}
+
+__global__ void __launch_bounds__(256) sk_dm_plan_kernel(const DParams p) {
+    if (p.a.info->overflow) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) report_err(p.st, 0, K_TOO_DENSE);
+        return;
+    }
+    const uint32_t nu = dm_units(p);
+    if ((nu + 31u) / 32u > p.max_rows) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) report_err(p.st, 0, K_TOO_DENSE);
+        return;
+    }
+    const uint8_t *in = p.a.in;
+    const uint8_t *lut = p.sheet.lut;
+    const uint32_t S = p.sheet.S, Lb = p.sheet.L;
+    const bool fused = p.fused_trim >= 0;
+    const unsigned long long n1 = p.mate ? p.r1_stats->n_records : 0ull;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nu; i += gridDim.x * blockDim.x) {
+        const LineRef h = line_of(p.a, i * 4u), sq = line_of(p.a, i * 4u + 1u), pl = line_of(p.a, i * 4u + 2u), ql = line_of(p.a, i * 4u + 3u);
+        unsigned kind = 0;
+        uint32_t olen = 0, kept = 0xFFFFFFFFu;
+        int sample = -1;
+        const bool nl_ok = h.len && in[h.s + h.len - 1] == '\n';
+        if (p.mate == 0) {
+            if (!(h.len && in[h.s] == '@')) kind = K_BAD_HEADER;  // :118-120
+            if (!kind && p.a.info->high && !dm_utf8_fine(p.a, h, sq, pl, ql)) kind = K_NON_ASCII;
+            if (!kind && fused && !nl_ok) kind = K_TRUNC_FUSED;
+            uint32_t st = 0, en = 0;
+            if (!kind && !dm_find_bc(in + h.s, h.len, lut, st, en)) kind = K_NO_BC;  // :138-141
+            if (!kind && en - st - 4u != Lb) kind = K_BC_LEN;                         // :148-150
+            if (!kind) {
+                const uint8_t *ob = in + h.s + st + 4u;
+                unsigned long long o0 = 0, o1 = 0, o2 = 0;
+                for (uint32_t q = 0; q < Lb; q++) {
+                    const unsigned long long code = lut[ob[q]] & 7u;
+                    o0 |= (code & 1ull) << q;
+                    o1 |= ((code >> 1) & 1ull) << q;
+                    o2 |= ((code >> 2) & 1ull) << q;
+                }
+                uint32_t lowest = 0xFFFFFFFFu, best = 0, last = 0;  // :154-166
+                for (uint32_t s2 = 0; s2 < S; s2++) {
+                    unsigned long long p0, p1, p2, care;
+                    if (p.sheet.wide) {
+                        const unsigned long long *pw = (const unsigned long long *)p.sheet.planes + 4ull * s2;
+                        p0 = pw[0], p1 = pw[1], p2 = pw[2], care = pw[3];
+                    } else {
+                        const uint32_t *pw = p.sheet.planes + 4ull * s2;
+                        p0 = pw[0], p1 = pw[1], p2 = pw[2], care = pw[3];
+                    }
+                    const uint32_t d = (uint32_t)__popcll(((o0 ^ p0) | (o1 ^ p1) | (o2 ^ p2)) & care);
+                    if (d < lowest) {
+                        lowest = d;
+                        best = s2;
+                        last = s2;
+                    } else if (d == lowest) {
+                        last = s2;
+                    }
+                }
+                atomicAdd(&p.counts[S], 1ull);  // :169
+                if (S && lowest <= 1u) {         // :172
+                    if (best == last) {          // :173-178
+                        sample = (int)best;
+                        atomicAdd(&p.counts[S + 1], 1ull);
+                        atomicAdd(&p.counts[best], 1ull);
+                    } else {                     // :184-188
+                        const uint32_t ei = atomicAdd(&p.st->n_events, 1u);
+                        if (ei < p.events_cap) {
+                            Event ev;
+                            ev.record = i;
+                            ev.bc_off = h.s + st + 4u;
+                            ev.bc_off2 = 0xFFFFFFFFu;
+                            ev.best = (int16_t)best;
+                            ev.last = (int16_t)last;
+                            ev.mismatches = lowest;
+                            p.events[ei] = ev;
+                        } else {
+                            atomicOr(&p.st->flags, F_EVENTS_OVERFLOW);
+                        }
+                    }
+                }
+                if (sample >= 0) {
+                    // UMI = observed characters where the sheet barcode has 'U' (:200-203), parked for mate 2
+                    unsigned long long um = p.sheet.wide ? ((const unsigned long long *)p.sheet.umask)[sample]
+                                                         : (unsigned long long)p.sheet.umask[sample];
+                    uint32_t t = 0;
+                    while (um) {
+                        const uint32_t q = (uint32_t)__ffsll((long long)um) - 1u;
+                        um &= um - 1ull;
+                        p.umi[(uint64_t)i * p.sheet.Umax + t++] = ob[q];
+                    }
+                    uint32_t body = sq.len + pl.len + ql.len;  // three lines verbatim (:209-212)
+                    if (fused) {
+                        if (!dm_trimq(in, sq, ql, p.fused_trim, kept)) {
+                            kind = K_SEQ_SHORT;
+                            sample = -1;
+                        }
+                        body = kept ? 2u * kept + 4u : 6u;
+                    }
+                    if (!kind && p.out) {
+                        uint32_t alen, blen;
+                        dm_pieces(in + h.s, h.len, true, st, en, alen, blen);
+                        olen = alen + blen + (t ? 5u + t : 0u) + 1u + body;  // :206-212
+                    }
+                }
+            }
+            p.assign[i] = (int16_t)sample;
+        } else {
+            // mate 2 of an assigned pair (:215-237)
+            sample = (unsigned long long)i < n1 ? (int)p.assign[i] : -1;
+            if (sample >= 0 && p.out) {
+                if (p.a.info->high && !dm_utf8_fine(p.a, h, sq, pl, ql)) kind = K_NON_ASCII;
+                if (!kind && fused && !nl_ok) kind = K_TRUNC_FUSED;
+                if (!kind) {
+                    uint32_t st = 0, en = 0, alen, blen;
+                    const bool cut = dm_find_bc(in + h.s, h.len, lut, st, en);  // :219-227
+                    dm_pieces(in + h.s, h.len, cut, st, en, alen, blen);         // :229
+                    const uint32_t ul = p.sheet.wide ? (uint32_t)__popcll(((const unsigned long long *)p.sheet.umask)[sample])
+                                                     : (uint32_t)__popc(p.sheet.umask[sample]);
+                    uint32_t body = sq.len + pl.len + ql.len;
+                    if (fused) {
+                        if (!dm_trimq(in, sq, ql, p.fused_trim, kept)) kind = K_SEQ_SHORT;
+                        body = kept ? 2u * kept + 4u : 6u;
+                    }
+                    if (!kind) olen = alen + blen + (ul ? 5u + ul : 0u) + 1u + body;
+                }
+            }
+        }
+        if (!kind && olen > 0xFFFFu) kind = K_TOO_LONG;  // a group's length is 16 bits
+        if (kind) {
+            report_err(p.st, i, kind);
+            olen = 0;
+        }
+        p.out_len[i] = olen;
+        p.kk[i] = kept;
+    }
+}
+__global__ void sk_dm_finish_kernel(const DParams p) {
+    const uint32_t nu = p.a.info->overflow ? 0u : dm_units(p);
+    unsigned long long bytes = 0;
+    if (nu) bytes = p.dst[nu - 1] + p.out_len[nu - 1];
+    p.st->n_records = nu;
+    p.st->n_lines = p.a.info->n_lines;
+    p.st->out_bytes = bytes;
+    p.st->out_cursor = bytes;
+    p.st->consumed = line_of(p.a, nu * 4u).s;
+    if (bytes > p.out_cap) report_err(p.st, 0, K_OUT_OVERFLOW);
+}
+__global__ void __launch_bounds__(256) sk_dm_emit_kernel(const DParams p) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t wpb = blockDim.x >> 5, gw = blockIdx.x * wpb + (threadIdx.x >> 5), nw = gridDim.x * wpb;
+    if (p.st->err_key || p.a.info->overflow) return;  // the host replays the batch up to the failing record
+    const uint32_t nu = dm_units(p);
+    const uint8_t *in = p.a.in;
+    const uint8_t *lut = p.sheet.lut;
+    uint8_t *out = p.out;
+    for (uint32_t i = gw; i < nu; i += nw) {
+        const uint32_t olen = p.out_len[i];
+        const int sample = (int)p.assign[i];
+        if (lane == 0) {
+            Group g;
+            g.sample = (uint16_t)(olen ? sample : 0xFFFF);
+            g.len = (uint16_t)olen;
+            p.groups[i] = g;
+            if ((i & 31u) == 0u) {
+                ChunkRow row;
+                row.base = p.dst[i];
+                row.first_group = i;
+                row.n_groups = min(32u, nu - i);
+                p.rows[i >> 5] = row;
+            }
+        }
+        if (!olen || !out) continue;
+        const LineRef h = line_of(p.a, i * 4u), sq = line_of(p.a, i * 4u + 1u), pl = line_of(p.a, i * 4u + 2u), ql = line_of(p.a, i * 4u + 3u);
+        uint32_t st = 0, en = 0, alen, blen;
+        const bool cut = dm_find_bc(in + h.s, h.len, lut, st, en);
+        dm_pieces(in + h.s, h.len, cut, st, en, alen, blen);
+        const uint32_t ul = p.sheet.wide ? (uint32_t)__popcll(((const unsigned long long *)p.sheet.umask)[sample])
+                                         : (uint32_t)__popc(p.sheet.umask[sample]);
+        unsigned long long d = p.dst[i];
+        if (alen) warp_copy_piece(in, out, h.s, d, alen, lane);
+        d += alen;
+        if (blen) warp_copy_piece(in, out, (unsigned long long)h.s + en, d, blen, lane);
+        d += blen;
+        if (ul) {  // " UMI:" + umi (:207 / :230)
+            put_lit(out, d, " UMI:", 5, lane);
+            for (uint32_t t = (uint32_t)lane; t < ul; t += 32u) out[d + 5u + t] = p.umi[(uint64_t)i * p.sheet.Umax + t];
+            d += 5u + ul;
+        }
+        put_lit(out, d, "\n", 1, lane);
+        d += 1;
+        const uint32_t kept = p.kk[i];
+        if (kept == 0xFFFFFFFFu) {  // three lines verbatim: they are contiguous in the stream
+            const uint32_t body = sq.len + pl.len + ql.len;
+            if (body) warp_copy_piece(in, out, sq.s, d, body, lane);
+        } else if (kept == 0) {
+            put_lit(out, d, "N\n+\n!\n", 6, lane);
+        } else {
+            warp_copy_piece(in, out, sq.s, d, kept, lane);
+            put_lit(out, d + kept, "\n+\n", 3, lane);
+            warp_copy_piece(in, out, ql.s, d + kept + 3u, kept, lane);
+            put_lit(out, d + 2ull * kept + 3u, "\n", 1, lane);
+        }
+    }
+}
+
 // ---- record table of an index / barcode stream ------------------------------------------------------
 // The (seq_off, seq_len after trim_end, flags) table of OP_SCAN (sk_kernels.cu) from the global line table: no limit
 // on record length or density (a FASTQ of 8-base index reads has hundreds of records per 16 KiB).  Record counting
@@ -735,6 +1049,45 @@ int launch_scan_table(const uint8_t *in, uint64_t n, uint32_t lpr, uint32_t head
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)sm_count * 8, want));
     sk_recref_kernel<<<grid, 256, 0, stream>>>(a, lpr, head_char, rec_limit, final_batch, out, inline32, cap, st);
     launches++;
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        *err = cudaGetErrorString(e);
+        return -1;
+    }
+    return launches;
+}
+
+// Header-route demultiplex of one mate on the line engine.  mate 0 must run before mate 1 (assign[], umi[], r1_stats).
+// Line table k = mate.  Returns the number of launches, < 0 on a launch error; *n_rows = slice-table rows in use.
+int launch_line_demux(int mate, const uint8_t *in, uint64_t n, uint64_t rec_limit, int fused_trim, const SheetDev &sheet, int16_t *assign,
+                      uint8_t *umi, Group *groups, ChunkRow *rows, uint32_t max_rows, unsigned long long *counts, Event *events,
+                      uint32_t events_cap, const DevStats *r1_stats, uint8_t *out, uint64_t out_cap, void *work,
+                      uint64_t max_stream_bytes, uint64_t max_records, DevStats *st, int sm_count, void *stream_, uint32_t *n_rows,
+                      const char **err) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    const LineWork w = carve(work, max_stream_bytes, max_records);
+    int launches = index_lines(in, n, 4, w, mate, st, 0, stream);
+    DParams p;
+    memset(&p, 0, sizeof p);
+    p.a.in = in, p.a.n = n, p.a.starts = w.starts[mate], p.a.info = w.info[mate];
+    p.mate = (uint32_t)mate;
+    p.rec_limit = rec_limit ? rec_limit : ~0ull;
+    p.fused_trim = fused_trim;
+    p.sheet = sheet;
+    p.assign = assign, p.umi = umi, p.groups = groups, p.rows = rows;
+    p.max_rows = (uint32_t)std::min<uint64_t>(max_rows, (max_records + 31) / 32);
+    p.counts = counts, p.events = events, p.events_cap = events_cap, p.r1_stats = r1_stats;
+    p.out_len = w.out_len, p.kk = w.bc_ref, p.dst = w.dst;
+    p.out = out, p.out_cap = out_cap, p.st = st;
+    *n_rows = p.max_rows;
+    cudaMemsetAsync(rows, 0, (size_t)p.max_rows * sizeof(ChunkRow), stream);
+    const unsigned grid = (unsigned)std::max(1, sm_count * 8);
+    const uint32_t n_scan = (uint32_t)std::min<uint64_t>(max_records, 0xFFFFFFFFull);
+    sk_dm_plan_kernel<<<grid, 256, 0, stream>>>(p);
+    launches += 1 + launch_len_scan(w.out_len, w.dst, n_scan, w.bsum, stream);
+    sk_dm_finish_kernel<<<1, 1, 0, stream>>>(p);
+    sk_dm_emit_kernel<<<grid, 256, 0, stream>>>(p);
+    launches += 2;
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         *err = cudaGetErrorString(e);

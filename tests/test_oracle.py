@@ -58,6 +58,12 @@ def test_error_paths(impl):
     # invalid UTF-8 -> I/O error
     code, out, err = impl.trim_by_quality(b"@r\nAC\n+\n\xff\xfe\n", 20)
     assert code == 255 and err == b"ERROR: I/O error while reading from file.\n"
+    # the offending line is quoted whole, whatever its length (error! formats the String, common.rs:11-16)
+    long_line = b"x" * 5000
+    res = impl.demultiplex(b"A\tACGT\n", long_line + b"\nAC\n+\nII\n")
+    assert res["exit_code"] == 255 and res["stderr"].endswith(b"ERROR: Invalid FASTQ header line:\n" + long_line + b"\n\n")
+    code, out, err = impl.add_barcode(long_line + b"\nAC\n", b"")
+    assert code == 255 and err == b"ERROR: Invalid FASTQ line:\n" + long_line + b"\n\n"
 
 
 @pytest.mark.parametrize("impl", [O, R], ids=["c", "py"])
