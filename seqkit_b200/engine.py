@@ -98,8 +98,9 @@ class Engine:
 
     @staticmethod
     def _refuse(res):
-        names = {L.DATA_NON_ASCII: "non-ASCII input", L.DATA_RECORD_TOO_LONG: "record longer than the chunk overhang",
-                 L.DATA_CHUNK_TOO_DENSE: "more than 512 records in one 32 KiB chunk",
+        names = {L.DATA_NON_ASCII: "non-ASCII bases or qualities, or invalid UTF-8",
+                 L.DATA_RECORD_TOO_LONG: "record beyond the operator's length limit",
+                 L.DATA_CHUNK_TOO_DENSE: "more records per chunk than the operator's engine has slots for",
                  L.DATA_MIXED_FORMAT: "mixed FASTA/FASTQ records", L.DATA_OUT_OVERFLOW: "output capacity exceeded",
                  L.DATA_TRUNCATED_FUSED: "fused trim+demux on a truncated header"}
         if res.status in names:

@@ -268,3 +268,22 @@ def test_all_visible_gpus_give_the_single_gpu_bytes(oracle_bin, tmp_path):
     data = G.clean_fastq(21, 30000, qual_style="mix")
     for op in ("trim", "mask"):
         both(oracle_bin, tmp_path, [op, "by", "quality", "in.fq", "20"], {"in.fq": data}, env={"SK_BATCH_MB": "1", "SK_GPUS": "8"}, ctx=op)
+
+
+def test_demultiplex_long_and_utf8_records(oracle_bin, tmp_path):
+    """Records no chunk engine frames -- 20 kb reads, UTF-8 and Unicode white space in headers -- go through the line
+    engine inside the same `fasta demultiplex` run, batch by batch (fasta_demultiplex.rs:117-249)."""
+    rng = random.Random(5)
+    sheet, bcs = G.make_sheet(9, 12, 8, umi=4)
+    p1, p2 = G.clean_pairs(41, 4000, bcs)
+    extra1, extra2 = [], []
+    for i in range(40):
+        bc = G.observed_barcode(rng, bcs, p_sub=0.03)
+        n = rng.choice((60, 9000, 20000))
+        name = ("né%d 日" % i).encode() if i % 2 else b"long%d" % i
+        tail = rng.choice((b"", "  ".encode(), b" z:9"))
+        sq, q = G.rand_seq(rng, n), bytes(rng.choice(b"#5II") for _ in range(n))
+        extra1.append(b"@" + name + b" 1 BC:" + bc + tail + b"\n" + sq + b"\n+\n" + q + b"\n")
+        extra2.append(b"@" + name + b" 2 BC:" + bc + b"\n" + sq[::-1] + b"\n+\n" + q + b"\n")
+    files = {"sheet.tsv": sheet, "r1.fq": p1 + b"".join(extra1) + p1, "r2.fq": p2 + b"".join(extra2) + p2}
+    both(oracle_bin, tmp_path, ["demultiplex", "sheet.tsv", "r1.fq", "r2.fq"], files, env={"SK_BATCH_MB": "1"}, ctx="long+utf8")
