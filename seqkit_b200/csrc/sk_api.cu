@@ -891,6 +891,39 @@ static int addbc_enqueue(sk_ctx *ctx, Slot *s, uint64_t rec_limit, bool fast) {
     if (rc) return rc;
     return end_op(ctx, s);
 }
+// Add barcode on the line engine: reads of any length and density, UTF-8 lines ('@' and '>' reads alike).
+static int line_addbc_enqueue(sk_ctx *ctx, Slot *s) {
+    int c_reads, c_bc;
+    int rc = peek_first_byte(ctx, s, SK_IN_R1, &c_reads);
+    if (rc) return rc;
+    rc = peek_first_byte(ctx, s, SK_IN_AUX1, &c_bc);
+    if (rc) return rc;
+    const uint64_t rec_limit = s->req_rec_limit;
+    rc = begin_op(ctx, s, OP_ADDBC);
+    if (rc) return rc;
+    s->req_rec_limit = rec_limit;
+    const bool bc_fastx = (c_bc == '@' || c_bc == '>');
+    const char *err = nullptr;
+    int n = launch_scan_table(s->in[SK_IN_AUX1], s->in_len[SK_IN_AUX1], c_bc == '>' ? 2u : 4u, bc_fastx ? (uint32_t)c_bc : 0xFFFFu,
+                              bc_fastx ? ~0ull : 0ull, 1u, s->scan_tab[0], nullptr, ctx->lim.max_records, s->lwork, 1,
+                              ctx->lim.max_stream_bytes, ctx->lim.max_records, s->stats + SK_IN_AUX1, ctx->sm_count, s->stream, &err);
+    if (n >= 0) {
+        s->launches += (uint32_t)n;
+        s->pass_ran[SK_IN_AUX1] = true;
+        n = launch_lineop(8 /* LOP_ADDBC */, s->in[SK_IN_R1], s->in_len[SK_IN_R1], s->in[SK_IN_AUX1], s->in_len[SK_IN_AUX1],
+                          c_reads == '>' ? 2u : 4u, c_reads == '>' ? (uint32_t)'>' : (uint32_t)'@', 0, 0, rec_limit, s->out[0], s->out[1],
+                          s->out_cap, s->lwork, ctx->lim.max_stream_bytes, ctx->lim.max_records, nullptr, 0, s->stats + SK_IN_R1,
+                          ctx->sm_count, s->stream, &err, s->scan_tab[0], s->stats + SK_IN_AUX1);
+    }
+    if (n < 0) {
+        ctx->err = std::string("line engine launch failed: ") + (err ? err : "?");
+        return SK_E_CUDA;
+    }
+    s->launches += (uint32_t)n;
+    s->pass_ran[SK_IN_R1] = true;
+    s->ran_line = true;
+    return end_op(ctx, s);
+}
 extern "C" int sk_add_barcode(sk_ctx *ctx, uint32_t slot, uint64_t rec_limit) {
     Slot *s = get_slot(ctx, slot);
     if (!s) return SK_E_INVALID;
@@ -1263,6 +1296,22 @@ extern "C" int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res) {
             int rc = end_op(ctx, s);
             if (rc) return rc;
             CK(cudaStreamSynchronize(s->stream));
+        }
+    }
+    if (s->last_op == OP_ADDBC && !s->ran_line && s->lwork) {  // and for add barcode
+        unsigned fl = 0;
+        unsigned long long key = ~0ull;
+        for (int i = 0; i < SK_N_INPUTS; i++) {
+            fl |= s->stats_h[i].flags;
+            if (s->stats_h[i].err_key) key = std::min(key, ~s->stats_h[i].err_key);
+        }
+        const unsigned kind = key == ~0ull ? 0u : (unsigned)(key & 0xFFu);
+        if ((fl & F_NON_ASCII) || kind == K_TOO_LONG || kind == K_TOO_DENSE) {
+            const uint32_t before = s->launches;
+            int rc = line_addbc_enqueue(ctx, s);
+            if (rc) return rc;
+            CK(cudaStreamSynchronize(s->stream));
+            s->launches += before;
         }
     }
     if (s->last_op == OP_DEMUX1 && !s->ran_line && s->lwork && !s->req_opts.use_index) {

@@ -253,7 +253,8 @@ int launch_warp_kernel(int op, const KParams &p, int sm_count, void *stream, con
 uint64_t lineops_work_bytes(uint64_t max_stream_bytes, uint64_t max_records);
 int launch_lineop(int op, const uint8_t *in_a, uint64_t n_a, const uint8_t *in_b, uint64_t n_b, uint32_t lpr, uint32_t head, uint32_t x,
                   uint32_t y, uint64_t rec_limit, uint8_t *out0, uint8_t *out1, uint64_t out_cap, void *work, uint64_t max_stream_bytes,
-                  uint64_t max_records, void *stats_tab, uint32_t h_cap, DevStats *st, int sm_count, void *stream, const char **err);
+                  uint64_t max_records, void *stats_tab, uint32_t h_cap, DevStats *st, int sm_count, void *stream, const char **err,
+                  const RecRef *bc_tab = nullptr, const DevStats *bc_stats = nullptr);
 // OP_SCAN's record table from the global line table (sk_lineops.cu): any record length and density
 int launch_scan_table(const uint8_t *in, uint64_t n, uint32_t lpr, uint32_t head_char, uint64_t rec_limit, uint32_t final_batch,
                       RecRef *out, uint4 *inline32, uint64_t cap, void *work, int k, uint64_t max_stream_bytes, uint64_t max_records,

@@ -177,6 +177,35 @@ __device__ __forceinline__ uint32_t trim_end_len_dev(const uint8_t *p, uint32_t 
     return len;
 }
 
+// str::trim_end (Unicode White_Space) of valid UTF-8: the new length
+__device__ __forceinline__ uint32_t trim_end_unicode(const uint8_t *s, uint32_t n) {
+    for (;;) {
+        if (!n) return 0;
+        const uint8_t c = s[n - 1];
+        if (c < 0x80) {
+            if (!is_ws(c)) return n;
+            n--;
+            continue;
+        }
+        if (n >= 2 && s[n - 2] == 0xC2 && (c == 0x85 || c == 0xA0)) {  // U+0085, U+00A0
+            n -= 2;
+            continue;
+        }
+        if (n >= 3) {
+            const uint8_t a = s[n - 3], b = s[n - 2];
+            const bool ws = (a == 0xE1 && b == 0x9A && c == 0x80) ||                                                   // U+1680
+                            (a == 0xE2 && b == 0x80 && ((c >= 0x80 && c <= 0x8A) || c == 0xA8 || c == 0xA9 || c == 0xAF)) ||  // U+2000-200A, 2028, 2029, 202F
+                            (a == 0xE2 && b == 0x81 && c == 0x9F) ||                                                   // U+205F
+                            (a == 0xE3 && b == 0x80 && c == 0x80);                                                     // U+3000
+            if (ws) {
+                n -= 3;
+                continue;
+            }
+        }
+        return n;
+    }
+}
+
 struct LParams {
     int op;
     LStream a, b;          // b: second input of interleave
@@ -194,12 +223,17 @@ struct LParams {
     uint32_t *h_cnt;
     uint32_t h_mask;
     uint32_t *bc_ref;      // [records] (off << 8 | len) of the record's barcode, 0xFFFFFFFF = none
+    // add barcode: record table of the barcode stream (b.in holds its bytes)
+    const RecRef *bc_tab;
+    const DevStats *bc_stats;
 };
 
 enum : int { LOP_TRIMFIX = 0, LOP_CHECK = 1, LOP_STATS = 2, LOP_INTERLEAVE = 3, LOP_DEINTERLEAVE = 4, LOP_DUALUMI = 5,
              // trim / mask by quality on the line engine: the last resort behind the warp and the general engine, for
              // records of any length and density and for UTF-8 in header and '+' lines (sk_api.cu: sk_wait)
-             LOP_TRIMQ = 6, LOP_MASKQ = 7 };
+             LOP_TRIMQ = 6, LOP_MASKQ = 7,
+             // add barcode on the line engine (fasta_add_barcode.rs:19-44): the same last resort, reads of any length
+             LOP_ADDBC = 8 };
 // further data outcome kinds of the line operators (== SK_DATA_* in the header)
 enum : unsigned { K_NO_PLUS = 8, K_INCONSISTENT = 9, K_QUAL_SHORT = 10, K_HASH_COLLISION = 38 };
 
@@ -381,6 +415,23 @@ __global__ void __launch_bounds__(256) sk_line_plan_kernel(const LParams p) {
                 if (sl != qn) kind = K_LEN_MISMATCH;                                                  // :35-37
                 else olen = h.len + 2u * sl + 4u;                                                     // :26,:44
             }
+        } else if (p.op == LOP_ADDBC) {  // fasta_add_barcode.rs:29-43
+            const LineRef h = line_of(p.a, i * p.lpr);
+            const LineRef whole = record_of(p.a, i, p.lpr);
+            const uint32_t c = h.len ? in[h.s] : 0u;
+            if (c != p.head) kind = (c == '@' || c == '>') ? K_MIXED : K_BAD_FASTX_LINE;
+            // every line is data like any other as long as it is valid UTF-8 (read_line, common.rs:106-112)
+            if (!kind && p.a.info->high && !utf8_ok(in + whole.s, whole.len)) kind = K_NON_ASCII;
+            if (!kind) {
+                uint32_t bl = 0;
+                const unsigned long long nb = p.bc_stats->n_records;
+                if (nb) {  // barcode of iteration i; the last one is reused once the barcode file is exhausted (:20-27)
+                    const RecRef rr = p.bc_tab[(unsigned long long)i < nb ? i : nb - 1ull];
+                    bl = rr.seq_len;
+                    if (rr.flags & RR_LONG) kind = K_TOO_LONG;
+                }
+                olen = trim_end_unicode(in + h.s, h.len) + 4u + bl + 1u + (whole.len - h.len);  // :33 + the other lines
+            }
         } else {  // LOP_DUALUMI (fasta_extract_dual_umi.rs:27-70)
             const uint32_t r1 = 2u * i, r2 = 2u * i + 1u, N = p.x;
             const LineRef h1 = line_of(p.a, r1 * p.lpr);
@@ -532,6 +583,22 @@ __global__ void __launch_bounds__(256) sk_line_emit_kernel(const LParams p) {
             put_lit(out, d + sl, "\n+\n", 3, lane);       // :44
             if (sl) warp_copy_piece(in, out, ql.s, d + sl + 3u, sl, lane);
             put_lit(out, d + 2ull * sl + 3u, "\n", 1, lane);
+        } else if (p.op == LOP_ADDBC) {
+            const LineRef h = line_of(p.a, i * p.lpr), whole = record_of(p.a, i, p.lpr);
+            const uint32_t alen = trim_end_unicode(in + h.s, h.len);
+            if (alen) warp_copy_piece(in, out, h.s, d, alen, lane);
+            d += alen;
+            put_lit(out, d, " BC:", 4, lane);
+            d += 4;
+            const unsigned long long nb = p.bc_stats->n_records;
+            if (nb) {
+                const RecRef rr = p.bc_tab[(unsigned long long)i < nb ? i : nb - 1ull];
+                if (rr.seq_len) warp_copy_piece(p.b.in, out, rr.seq_off, d, rr.seq_len, lane);
+                d += rr.seq_len;
+            }
+            put_lit(out, d, "\n", 1, lane);
+            d += 1;
+            if (whole.len > h.len) warp_copy_piece(in, out, (unsigned long long)h.s + h.len, d, whole.len - h.len, lane);
         } else if (p.op == LOP_INTERLEAVE) {
             const LineRef r1 = record_of(p.a, i, p.lpr), r2 = record_of(p.b, i, p.lpr);
             if (r1.len) warp_copy_piece(in, out, r1.s, d, r1.len, lane);
@@ -705,34 +772,6 @@ __device__ __forceinline__ uint32_t dm_units(const DParams &p) {
     uint32_t u = p.a.info->n_rec;
     if ((uint64_t)u > p.rec_limit) u = (uint32_t)p.rec_limit;
     return u;
-}
-// str::trim_end (Unicode White_Space) of valid UTF-8: the new length
-__device__ __forceinline__ uint32_t trim_end_unicode(const uint8_t *s, uint32_t n) {
-    for (;;) {
-        if (!n) return 0;
-        const uint8_t c = s[n - 1];
-        if (c < 0x80) {
-            if (!is_ws(c)) return n;
-            n--;
-            continue;
-        }
-        if (n >= 2 && s[n - 2] == 0xC2 && (c == 0x85 || c == 0xA0)) {  // U+0085, U+00A0
-            n -= 2;
-            continue;
-        }
-        if (n >= 3) {
-            const uint8_t a = s[n - 3], b = s[n - 2];
-            const bool ws = (a == 0xE1 && b == 0x9A && c == 0x80) ||                                                   // U+1680
-                            (a == 0xE2 && b == 0x80 && ((c >= 0x80 && c <= 0x8A) || c == 0xA8 || c == 0xA9 || c == 0xAF)) ||  // U+2000-200A, 2028, 2029, 202F
-                            (a == 0xE2 && b == 0x81 && c == 0x9F) ||                                                   // U+205F
-                            (a == 0xE3 && b == 0x80 && c == 0x80);                                                     // U+3000
-            if (ws) {
-                n -= 3;
-                continue;
-            }
-        }
-        return n;
-    }
 }
 // leftmost " BC:" followed by at least one class byte, greedy class run (fasta_demultiplex.rs:38,138-141)
 __device__ __forceinline__ bool dm_find_bc(const uint8_t *h, uint32_t n, const uint8_t *lut, uint32_t &st, uint32_t &en) {
@@ -1099,10 +1138,11 @@ int launch_line_demux(int mate, const uint8_t *in, uint64_t n, uint64_t rec_limi
 // One line operator over the slot's streams.  stats table: keys / rep / cnt of `h_cap` slots, list of 2*h_cap u64.
 int launch_lineop(int op, const uint8_t *in_a, uint64_t n_a, const uint8_t *in_b, uint64_t n_b, uint32_t lpr, uint32_t head, uint32_t x,
                   uint32_t y, uint64_t rec_limit, uint8_t *out0, uint8_t *out1, uint64_t out_cap, void *work, uint64_t max_stream_bytes,
-                  uint64_t max_records, void *stats_tab, uint32_t h_cap, DevStats *st, int sm_count, void *stream_, const char **err) {
+                  uint64_t max_records, void *stats_tab, uint32_t h_cap, DevStats *st, int sm_count, void *stream_, const char **err,
+                  const RecRef *bc_tab, const DevStats *bc_stats) {
     cudaStream_t stream = (cudaStream_t)stream_;
     const LineWork w = carve(work, max_stream_bytes, max_records);
-    const int strict = (op == LOP_TRIMQ || op == LOP_MASKQ) ? 0 : 1;
+    const int strict = (op == LOP_TRIMQ || op == LOP_MASKQ || op == LOP_ADDBC) ? 0 : 1;
     int launches = index_lines(in_a, n_a, lpr, w, 0, st, strict, stream);
     if (op == LOP_INTERLEAVE) launches += index_lines(in_b, n_b, lpr, w, 1, st, strict, stream);
     LParams p;
@@ -1114,6 +1154,7 @@ int launch_lineop(int op, const uint8_t *in_a, uint64_t n_a, const uint8_t *in_b
     p.rec_limit = rec_limit ? rec_limit : ~0ull;
     p.out_len = w.out_len, p.dst = w.dst, p.out = out0, p.out_cap = out_cap, p.st = st;
     p.bc_ref = w.bc_ref;
+    p.bc_tab = bc_tab, p.bc_stats = bc_stats;
     const unsigned grid = (unsigned)std::max(1, sm_count * 8);
     const uint32_t n_scan = (uint32_t)std::min<uint64_t>(max_records, 0xFFFFFFFFull);
     if (op == LOP_STATS) {

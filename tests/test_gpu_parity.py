@@ -122,6 +122,14 @@ def test_dense_long_and_utf8_records_take_the_line_engine(eng, O):
             assert eng.last_result.reserved & 16, ("trim", label, eng.last_result.reserved)
             check3(eng.mask_by_quality(blob, q), O.mask_by_quality(blob, q), ("mask", label, q))
             assert eng.last_result.reserved & 16, ("mask", label, eng.last_result.reserved)
+    # add barcode (fasta_add_barcode.rs:19-44): header.trim_end() is Unicode-aware, every line is copied as it is
+    bcf = G.index_reads(9, 5000, [b"ACGTACGT", b"GG+TT"])
+    for label, blob in (("tiny", tiny), ("big", big), ("mixed", mixed), ("utf8", utf8), ("nbsp", nbsp)):
+        check3(eng.add_barcode(blob, bcf), O.add_barcode(blob, bcf), ("addbc", label))
+        assert eng.last_result.reserved & 16, ("addbc", label, eng.last_result.reserved)
+    fa_long = (b">s desc \n" + b"A" * 30000 + b"\n") * 5
+    check3(eng.add_barcode(fa_long, b">b\nAA\n>b\nCC\n"), O.add_barcode(fa_long, b">b\nAA\n>b\nCC\n"), "addbc long FASTA")
+    check3(eng.add_barcode(big + b"oops\nAC\n+\nII\n" + big, bcf), O.add_barcode(big + b"oops\nAC\n+\nII\n" + big, bcf), "addbc bad line")
     # failing records behind long ones: the reference's messages after the output of the records before them
     for bad in (big + b"oops\nAC\n+\nII\n" + big, big + b"@s\nACGT\n+\nII\n", tiny + b"\n"):
         check3(eng.trim_by_quality(bad, 20), O.trim_by_quality(bad, 20), "trim after long")
