@@ -100,7 +100,7 @@ typedef struct sk_result {
                                        quality met a record that changes its length (or fails), or add barcode a record that does not
                                        grow like the first, and the pass was re-run in its ordered form, bit3 =
                                        the demultiplex output was compacted per sample (sk_demux_compact), bit4 = trim / mask by
-                                       quality, add barcode or header-route demultiplex ended up on the line engine (long or dense records,
+                                       quality, add barcode or demultiplex ended up on the line engine (long or dense records,
                                        UTF-8 header lines) */
     float pass_ms[SK_N_INPUTS];     /* device time of the chunk-engine kernel over each input stream
                                        (CUDA events on the slot's stream; only with sk_set_profiling) */

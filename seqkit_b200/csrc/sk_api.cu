@@ -1154,6 +1154,30 @@ static int line_demux_enqueue(sk_ctx *ctx, Slot *s) {
     sh.L = ctx->L;
     sh.Umax = ctx->Umax;
     sh.wide = ctx->wide;
+    // --index1 / --index2: record tables of the index streams (line tables 0 and 1 are free until the mates take them)
+    int idx_stream[2];
+    uint32_t n_index = 0;
+    if (o.use_index & 1u) idx_stream[n_index++] = SK_IN_AUX1;
+    if (o.use_index & 2u) idx_stream[n_index++] = SK_IN_AUX2;
+    const RecRef *ext_tab[2] = {nullptr, nullptr};
+    const uint8_t *ext_data[2] = {nullptr, nullptr};
+    const DevStats *ext_stats[2] = {nullptr, nullptr};
+    for (uint32_t q = 0; q < n_index; q++) {
+        const int w = idx_stream[q];
+        const char *err = nullptr;
+        const int n = launch_scan_table(s->in[w], s->in_len[w], 4u, 0u, o.rec_limit ? o.rec_limit : ~0ull, 1u, s->scan_tab[q], nullptr,
+                                        ctx->lim.max_records, s->lwork, (int)q, ctx->lim.max_stream_bytes, ctx->lim.max_records,
+                                        s->stats + w, ctx->sm_count, s->stream, &err);
+        if (n < 0) {
+            ctx->err = std::string("record table launch failed: ") + (err ? err : "?");
+            return SK_E_CUDA;
+        }
+        s->launches += (uint32_t)n;
+        s->pass_ran[w] = true;
+        ext_tab[q] = s->scan_tab[q];
+        ext_data[q] = s->in[w];
+        ext_stats[q] = s->stats + w;
+    }
     const int nm = s->paired ? 2 : 1;
     for (int mate = 0; mate < nm; mate++) {
         const int which = mate == 0 ? SK_IN_R1 : SK_IN_R2;
@@ -1163,7 +1187,8 @@ static int line_demux_enqueue(sk_ctx *ctx, Slot *s) {
                                         s->groups[mate], s->rows[mate], ctx->max_chunks, s->counts, s->events,
                                         (uint32_t)std::min<uint64_t>(ctx->lim.max_records, 0xFFFFFFFFull), s->stats + SK_IN_R1,
                                         o.no_output ? nullptr : s->out[mate], s->out_cap, s->lwork, ctx->lim.max_stream_bytes,
-                                        ctx->lim.max_records, s->stats + which, ctx->sm_count, s->stream, &n_rows, &err);
+                                        ctx->lim.max_records, s->stats + which, ctx->sm_count, s->stream, &n_rows, &err, n_index,
+                                        ext_tab, ext_data, ext_stats);
         if (n < 0) {
             ctx->err = std::string("line engine launch failed: ") + (err ? err : "?");
             return SK_E_CUDA;
@@ -1314,7 +1339,7 @@ extern "C" int sk_wait(sk_ctx *ctx, uint32_t slot, sk_result *res) {
             s->launches += before;
         }
     }
-    if (s->last_op == OP_DEMUX1 && !s->ran_line && s->lwork && !s->req_opts.use_index) {
+    if (s->last_op == OP_DEMUX1 && !s->ran_line && s->lwork) {
         // The same last resort for header-route demultiplex (sk_result.reserved bit 4).
         unsigned fl = 0;
         unsigned long long key = ~0ull;

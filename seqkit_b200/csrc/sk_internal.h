@@ -264,7 +264,8 @@ int launch_line_demux(int mate, const uint8_t *in, uint64_t n, uint64_t rec_limi
                       uint8_t *umi, Group *groups, ChunkRow *rows, uint32_t max_rows, unsigned long long *counts, Event *events,
                       uint32_t events_cap, const DevStats *r1_stats, uint8_t *out, uint64_t out_cap, void *work,
                       uint64_t max_stream_bytes, uint64_t max_records, DevStats *st, int sm_count, void *stream, uint32_t *n_rows,
-                      const char **err);
+                      const char **err, uint32_t n_index = 0, const RecRef *const *ext_tab = nullptr,
+                      const uint8_t *const *ext_data = nullptr, const DevStats *const *ext_stats = nullptr);
 // Per-sample compaction of a demultiplex result (sk_compact.cu)
 uint64_t compact_work_bytes(uint32_t max_rows, uint32_t S);
 int launch_compact(const ChunkRow *rows, const Group *groups, uint32_t n_rows, uint32_t S, const uint8_t *src, uint8_t *dst,

@@ -762,6 +762,10 @@ struct DParams {
     Event *events;
     uint32_t events_cap;
     const DevStats *r1_stats;
+    uint32_t n_index;        // --index1 / --index2: the barcode is the index reads' sequence lines (:126-136), the header stays whole
+    const RecRef *ext_tab[2];
+    const uint8_t *ext_data[2];
+    const DevStats *ext_stats[2];
     uint32_t *out_len, *kk;  // [records]; kk: bases kept by the fused trim (0 = the "N" record), 0xFFFFFFFF = three lines verbatim
     uint64_t *dst;
     uint8_t *out;            // nullptr: dry run
@@ -847,13 +851,43 @@ __global__ void __launch_bounds__(256) sk_dm_plan_kernel(const DParams p) {
             if (!kind && p.a.info->high && !dm_utf8_fine(p.a, h, sq, pl, ql)) kind = K_NON_ASCII;
             if (!kind && fused && !nl_ok) kind = K_TRUNC_FUSED;
             uint32_t st = 0, en = 0;
-            if (!kind && !dm_find_bc(in + h.s, h.len, lut, st, en)) kind = K_NO_BC;  // :138-141
-            if (!kind && en - st - 4u != Lb) kind = K_BC_LEN;                         // :148-150
+            RecRef ir0{0, 0, 0}, ir1{0, 0, 0};
+            uint32_t sep = 0;
+            if (!kind && p.n_index) {  // :126-136
+                for (uint32_t q = 0; q < p.n_index && !kind; q++) {
+                    if ((unsigned long long)i >= p.ext_stats[q]->n_records) {
+                        kind = K_INDEX_ASSERT;
+                        break;
+                    }
+                    const RecRef t = p.ext_tab[q][i];
+                    if (!(t.flags & RR_L0_AT) || !(t.flags & RR_L2_PLUS)) kind = K_INDEX_ASSERT;  // :130,:134
+                    if (t.flags & RR_LONG) kind = K_TOO_LONG;
+                    if (q == 0) ir0 = t;
+                    else ir1 = t;
+                }
+                if (!kind) {
+                    uint32_t bclen = ir0.seq_len;
+                    if (p.n_index == 2) {
+                        sep = bclen ? 1u : 0u;  // '+' only behind a non-empty first part (:128)
+                        bclen += sep + ir1.seq_len;
+                    }
+                    if (bclen != Lb) kind = K_BC_LEN;  // :148-150
+                }
+            } else {
+                if (!kind && !dm_find_bc(in + h.s, h.len, lut, st, en)) kind = K_NO_BC;  // :138-141
+                if (!kind && en - st - 4u != Lb) kind = K_BC_LEN;                         // :148-150
+            }
             if (!kind) {
-                const uint8_t *ob = in + h.s + st + 4u;
+                const uint8_t *hb = in + h.s + st + 4u;
+                auto obs = [&](uint32_t q) -> uint8_t {
+                    if (!p.n_index) return hb[q];
+                    if (q < ir0.seq_len) return p.ext_data[0][(uint64_t)ir0.seq_off + q];
+                    if (q < ir0.seq_len + sep) return (uint8_t)'+';
+                    return p.ext_data[1][(uint64_t)ir1.seq_off + (q - ir0.seq_len - sep)];
+                };
                 unsigned long long o0 = 0, o1 = 0, o2 = 0;
                 for (uint32_t q = 0; q < Lb; q++) {
-                    const unsigned long long code = lut[ob[q]] & 7u;
+                    const unsigned long long code = lut[obs(q)] & 7u;
                     o0 |= (code & 1ull) << q;
                     o1 |= ((code >> 1) & 1ull) << q;
                     o2 |= ((code >> 2) & 1ull) << q;
@@ -888,8 +922,8 @@ __global__ void __launch_bounds__(256) sk_dm_plan_kernel(const DParams p) {
                         if (ei < p.events_cap) {
                             Event ev;
                             ev.record = i;
-                            ev.bc_off = h.s + st + 4u;
-                            ev.bc_off2 = 0xFFFFFFFFu;
+                            ev.bc_off = p.n_index ? ir0.seq_off : h.s + st + 4u;
+                            ev.bc_off2 = p.n_index == 2 ? ir1.seq_off : 0xFFFFFFFFu;
                             ev.best = (int16_t)best;
                             ev.last = (int16_t)last;
                             ev.mismatches = lowest;
@@ -907,7 +941,7 @@ __global__ void __launch_bounds__(256) sk_dm_plan_kernel(const DParams p) {
                     while (um) {
                         const uint32_t q = (uint32_t)__ffsll((long long)um) - 1u;
                         um &= um - 1ull;
-                        p.umi[(uint64_t)i * p.sheet.Umax + t++] = ob[q];
+                        p.umi[(uint64_t)i * p.sheet.Umax + t++] = obs(q);
                     }
                     uint32_t body = sq.len + pl.len + ql.len;  // three lines verbatim (:209-212)
                     if (fused) {
@@ -919,7 +953,7 @@ __global__ void __launch_bounds__(256) sk_dm_plan_kernel(const DParams p) {
                     }
                     if (!kind && p.out) {
                         uint32_t alen, blen;
-                        dm_pieces(in + h.s, h.len, true, st, en, alen, blen);
+                        dm_pieces(in + h.s, h.len, p.n_index == 0, st, en, alen, blen);
                         olen = alen + blen + (t ? 5u + t : 0u) + 1u + body;  // :206-212
                     }
                 }
@@ -933,8 +967,8 @@ __global__ void __launch_bounds__(256) sk_dm_plan_kernel(const DParams p) {
                 if (!kind && fused && !nl_ok) kind = K_TRUNC_FUSED;
                 if (!kind) {
                     uint32_t st = 0, en = 0, alen, blen;
-                    const bool cut = dm_find_bc(in + h.s, h.len, lut, st, en);  // :219-227
-                    dm_pieces(in + h.s, h.len, cut, st, en, alen, blen);         // :229
+                    const bool cut = p.n_index == 0 && dm_find_bc(in + h.s, h.len, lut, st, en);  // :219-227
+                    dm_pieces(in + h.s, h.len, cut, st, en, alen, blen);                           // :229
                     const uint32_t ul = p.sheet.wide ? (uint32_t)__popcll(((const unsigned long long *)p.sheet.umask)[sample])
                                                      : (uint32_t)__popc(p.sheet.umask[sample]);
                     uint32_t body = sq.len + pl.len + ql.len;
@@ -993,7 +1027,7 @@ __global__ void __launch_bounds__(256) sk_dm_emit_kernel(const DParams p) {
         if (!olen || !out) continue;
         const LineRef h = line_of(p.a, i * 4u), sq = line_of(p.a, i * 4u + 1u), pl = line_of(p.a, i * 4u + 2u), ql = line_of(p.a, i * 4u + 3u);
         uint32_t st = 0, en = 0, alen, blen;
-        const bool cut = dm_find_bc(in + h.s, h.len, lut, st, en);
+        const bool cut = p.n_index == 0 && dm_find_bc(in + h.s, h.len, lut, st, en);
         dm_pieces(in + h.s, h.len, cut, st, en, alen, blen);
         const uint32_t ul = p.sheet.wide ? (uint32_t)__popcll(((const unsigned long long *)p.sheet.umask)[sample])
                                          : (uint32_t)__popc(p.sheet.umask[sample]);
@@ -1102,7 +1136,8 @@ int launch_line_demux(int mate, const uint8_t *in, uint64_t n, uint64_t rec_limi
                       uint8_t *umi, Group *groups, ChunkRow *rows, uint32_t max_rows, unsigned long long *counts, Event *events,
                       uint32_t events_cap, const DevStats *r1_stats, uint8_t *out, uint64_t out_cap, void *work,
                       uint64_t max_stream_bytes, uint64_t max_records, DevStats *st, int sm_count, void *stream_, uint32_t *n_rows,
-                      const char **err) {
+                      const char **err, uint32_t n_index, const RecRef *const *ext_tab, const uint8_t *const *ext_data,
+                      const DevStats *const *ext_stats) {
     cudaStream_t stream = (cudaStream_t)stream_;
     const LineWork w = carve(work, max_stream_bytes, max_records);
     int launches = index_lines(in, n, 4, w, mate, st, 0, stream);
@@ -1116,6 +1151,8 @@ int launch_line_demux(int mate, const uint8_t *in, uint64_t n, uint64_t rec_limi
     p.assign = assign, p.umi = umi, p.groups = groups, p.rows = rows;
     p.max_rows = (uint32_t)std::min<uint64_t>(max_rows, (max_records + 31) / 32);
     p.counts = counts, p.events = events, p.events_cap = events_cap, p.r1_stats = r1_stats;
+    p.n_index = n_index;
+    for (uint32_t q = 0; q < n_index && q < 2; q++) p.ext_tab[q] = ext_tab[q], p.ext_data[q] = ext_data[q], p.ext_stats[q] = ext_stats[q];
     p.out_len = w.out_len, p.kk = w.bc_ref, p.dst = w.dst;
     p.out = out, p.out_cap = out_cap, p.st = st;
     *n_rows = p.max_rows;

@@ -203,6 +203,24 @@ def test_demultiplex_takes_the_line_engine_for_long_dense_and_utf8_records(eng, 
     # failures behind a long record: message and the files written so far
     bad = p1[: len(p1) // 2] + longs[0][0] + b"@nobc\nAC\n+\nII\n" + p1
     check(bad, None, "no barcode behind a long record", want_line=False)
+    # --index1 / --index2 route (:126-136): the headers stay whole, the barcode comes from the index reads
+    sheet2, bcs2 = G.make_sheet(6, 12, 16, umi=4, dual=True)
+    lit = [b.rstrip(b"U") for b in bcs2]
+    n_i = 600
+    q1, q2 = G.clean_pairs(33, n_i, bcs2, bc_in_r2=False)
+    recs1, recs2 = q1.split(b"\n@"), q2.split(b"\n@")
+    for k in (5, 300):  # two long reads, one with a UTF-8 header
+        name = ("@né%d" % k).encode() if k == 300 else b"@long%d" % k
+        big_rec = lambda m: name + b" %d\n" % m + G.rand_seq(rng, 12000) + b"\n+\n" + quals(12000)
+        recs1[k] = big_rec(1)[1:] if k else big_rec(1)
+        recs2[k] = big_rec(2)[1:] if k else big_rec(2)
+    q1, q2 = b"\n@".join(recs1), b"\n@".join(recs2)
+    i1 = G.index_reads(34, n_i, [b.split(b"+")[0] for b in lit], p_sub=0.03)
+    i2 = b"".join(b"@i\n" + r.split(b"\n")[1] + b"ACGT\n+\nIIII\n" for r in G.index_reads(35, n_i, [b.split(b"+")[1] for b in lit], p_sub=0.03).split(b"@")[1:])
+    for a2 in (q2, None):
+        _cmp_demux(eng.demultiplex(sheet2, q1, a2, index1=i1, index2=i2), O.demultiplex(sheet2, q1, a2, index1=i1, index2=i2), ("index route", a2 is None))
+        assert eng.last_result.reserved & 16
+    _cmp_demux(eng.demultiplex(sheet2, q1, q2, index1=i1[: len(i1) // 2], index2=i2), O.demultiplex(sheet2, q1, q2, index1=i1[: len(i1) // 2], index2=i2), "index file runs out")
     amb_sheet = b"P\tACGTACGT\nQ\tACGTACGA\n"
     amb = rec(b"a", b"ACGTACGC", b"A" * 9000, b"I" * 9000) * 3
     _cmp_demux(eng.demultiplex(amb_sheet, amb), O.demultiplex(amb_sheet, amb), "ambiguous long records")
