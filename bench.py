@@ -310,7 +310,7 @@ def main():
         assert lib.sk_allreduce_counts(eng.ctx, 0, comm) == 0, lib.sk_last_error(eng.ctx)
     res = eng.wait()
     assert res.status == 0 and res.n_records == P, (res.status, res.n_records)
-    # sk_result.reserved: bit0 = the warp / lean engine ran, bit1 = it was re-run on the general engine, bit3 = compacted
+    # sk_result.reserved: bit0 = the warp engine ran, bit1 = it was re-run on the general engine, bit3 = compacted
     assert (res.reserved & 3) == 1, "bench workload must run on the warp engine without a re-run (got %d)" % res.reserved
     assert res.reserved & 8, "the per-sample compaction must have run"
     pairs_done = res.n_records
@@ -365,9 +365,8 @@ def main():
     dom = 0 if pass_ms[0] >= pass_ms[1] else 1
     peak, peak_src = peaks()
     achieved = bytes_pass[dom] / (pass_ms[dom] * 1e-3) / 1e9
-    if os.environ.get("SK_NO_WARP", "0") not in ("", "0"):  # the lean engine instead of the warp engine
-        geo = "GeoS" if os.environ.get("SK_FAST_GEO") == "0" else "GeoM"
-        kname = lambda k: "sk_fast_kernel<%s, OP_DEMUX%d>" % (geo, k + 1)
+    if os.environ.get("SK_NO_WARP", "0") not in ("", "0"):  # the general engine instead of the warp engine
+        kname = lambda k: "sk_chunk_kernel<OP_DEMUX%d>" % (k + 1)
     else:
         kname = lambda k: "sk_warp_kernel<OP_DEMUX%d>" % (k + 1)
     # DRAM traffic of the dominant kernel from this round's committed ncu capture (dram__bytes_read + write,
@@ -413,11 +412,11 @@ def main():
                 if i:
                     ms += r.pass_ms[0] / reps
                     ob = int(r.out_bytes[0])
-                    eng_bits = int(r.reserved)  # 1: lean (or warp) engine, 2: re-run on the general engine
+                    eng_bits = int(r.reserved)  # 1: warp engine, 2: re-run on the general engine
             opn = "TRIM" if name.startswith("trim") else "MASK"
             ws = os.environ.get("SK_WARP_STREAM")  # default: both on the warp engine (trim: + scan + gather kernels)
             on_warp = os.environ.get("SK_NO_WARP", "0") in ("", "0") and ws not in ("", "0")
-            kn = ("sk_warp_kernel<OP_%s>" if on_warp else "sk_fast_kernel<GeoM, OP_%s>") % opn
+            kn = ("sk_warp_kernel<OP_%s>" if on_warp else "sk_chunk_kernel<OP_%s>") % opn
             if on_warp and opn == "TRIM" and os.environ.get("SK_TRIM_GATHER") not in ("", "0"):
                 kn += " + sk_tile_sum_kernel + sk_tile_scan_kernel + sk_tile_gather_kernel"
             other[name] = {"kernel": kn, "engine_bits": eng_bits,

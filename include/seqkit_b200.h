@@ -222,8 +222,8 @@ int sk_download_out(sk_ctx *ctx, uint32_t slot, uint32_t which, void *host, uint
 
 /* Demultiplex side tables (valid after sk_wait).  The kernels write the emitted records of a chunk back
  * to back as a sequence of *groups* -- runs of bytes that belong to one sample, in input order inside a
- * sample (the warp and lean engines emit one group per record in input order -- the warp engine one row
- * per round of 32 records, four rows per tile, unused ones empty; the general engine groups a chunk's
+ * sample (the warp engine emits one group per record in input order, one row per round of 32 records, four
+ * rows per tile, unused ones empty; the line engine one row per 32 records; the general engine groups a chunk's
  * records by sample).  For output stream m, row c describes chunk (or round) c: its groups are
  * groups[first_group .. first_group+n_groups), laid out back to back from byte `base` of output
  * stream m.  Appending, for every sample, its groups over c = 0..n_chunks-1 gives that sample's file

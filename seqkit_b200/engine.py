@@ -75,7 +75,7 @@ class Engine:
     def wait(self, slot: int = 0) -> L.Result:
         res = L.Result()
         _check(self.ctx, self.lib.sk_wait(self.ctx, slot, C.byref(res)), "sk_wait")
-        self.last_result = res  # .reserved: bit0 = lean engine ran, bit1 = re-run on the general engine
+        self.last_result = res  # .reserved: bit0 = warp engine ran, bit1 = re-run on the general engine, bit4 = line engine
         return res
 
     def fetch_out(self, which: int, n: int, slot: int = 0) -> bytes:

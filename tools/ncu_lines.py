@@ -62,13 +62,6 @@ for r in rows:
 
 def demangle_match(kname, funcs):
     # match by template arguments: Cfg name and OP number
-    m = re.search(r"sk_fast_kernel<sk::(\w+), \(int\)(\d+), \(int\)(\d+)>", kname)
-    if m:
-        geo, op, nw = m.group(1), m.group(2), m.group(3)
-        for f in funcs:
-            if "sk_fast_kernel" in f and ("%d%s" % (len(geo), geo)) in f and ("Li%sELi%sE" % (op, nw)) in f:
-                return f
-        return None
     m = re.search(r"sk_warp_kernel<\(int\)(\d+), \(int\)(\d+)>", kname)
     if m:
         for f in funcs:
