@@ -57,6 +57,9 @@ extern "C" {
 #define SK_DATA_OUT_OVERFLOW 36   /* output capacity of the slot exceeded */
 #define SK_DATA_TRUNCATED_FUSED 37 /* fused trim+demux on a header line without '\n' */
 #define SK_DATA_HASH_COLLISION 38  /* statistics: two different barcodes with one 64-bit hash (reported, never merged) */
+#define SK_DATA_TOO_MANY_RECORDS 39 /* the batch holds more records than sk_limits.max_records (err_record = max_records): nothing of it
+                                      is valid; re-issue the call with rec_limit = err_record (sk_result.consumed[] then tells where
+                                      the next batch starts) or create the context with a larger limit */
 
 /* sk_result.flags */
 #define SK_FLAG_MATE_COUNT 1u      /* mate/index streams hold fewer records than stream 0 */

@@ -16,6 +16,7 @@ DATA_OK, DATA_BAD_HEADER, DATA_LEN_MISMATCH, DATA_SEQ_SHORT, DATA_NO_BC, DATA_BC
 LOP_TRIM, LOP_CHECK, LOP_STATS, LOP_INTERLEAVE, LOP_DEINTERLEAVE, LOP_DUAL_UMI = range(6)
 DATA_NON_ASCII, DATA_RECORD_TOO_LONG, DATA_CHUNK_TOO_DENSE, DATA_MIXED_FORMAT, DATA_OUT_OVERFLOW, \
     DATA_TRUNCATED_FUSED = range(32, 38)
+DATA_TOO_MANY_RECORDS = 39
 FLAG_MATE_COUNT, FLAG_EVENTS_OVERFLOW = 1, 2
 
 

@@ -716,6 +716,7 @@ static void base_params(sk_ctx *ctx, Slot *s, int which, KParams &p, int eng = E
     p.n_chunks = chunks_of(ctx, p.n, eng);
     p.tile_lanes = ctx->tile_lanes;
     p.lpr = 4;
+    p.max_records = ctx->lim.max_records;
     p.rec_limit = ~0ull;
     p.final_batch = 1;
     p.fused_trim = -1;

@@ -172,6 +172,8 @@ struct KParams {
     uint64_t n;
     uint32_t n_chunks;
     uint32_t lpr;         // lines per record: 4 (FASTQ) or 2 (FASTA)
+    uint64_t max_records; // sk_limits.max_records: size of the per-record tables (assign, umi, groups, record tables); a batch
+                          // with more records is refused (K_TOO_MANY) before anything is written past them
     uint64_t rec_limit;   // process records with index < rec_limit
     uint32_t final_batch; // 1: end of buffer is end of file (EOF semantics); 0: trailing partial record is left
     uint32_t min_baseq;
@@ -215,7 +217,7 @@ struct KParams {
 enum : unsigned {
     K_BAD_HEADER = 1, K_LEN_MISMATCH = 2, K_SEQ_SHORT = 3, K_NO_BC = 4, K_BC_LEN = 5, K_INDEX_ASSERT = 6,
     K_BAD_FASTX_LINE = 7, K_NON_ASCII = 32, K_TOO_LONG = 33, K_TOO_DENSE = 34, K_MIXED = 35, K_OUT_OVERFLOW = 36,
-    K_TRUNC_FUSED = 37,
+    K_TRUNC_FUSED = 37, K_TOO_MANY = 39,
     // line operators (sk_lineops.cu): K_NO_PLUS = 8, K_INCONSISTENT = 9, K_QUAL_SHORT = 10, K_HASH_COLLISION = 38
 };
 enum : unsigned { F_MATE_COUNT = 1u, F_EVENTS_OVERFLOW = 2u, F_NON_ASCII = 0x100u, F_NEED_GENERAL = 0x200u, F_NEED_ORDERED = 0x400u };

@@ -285,7 +285,19 @@ __global__ void __launch_bounds__(Cfg::NT, Cfg::MIN_CTAS) sk_chunk_kernel(const 
                 const uint32_t need = jend < nls ? jend : nls - 1;
                 if (need >= (uint32_t)MAXLINES || (OP != OP_SCAN && nrec > (uint32_t)MAXREC)) chunk_err = K_TOO_DENSE;
             }
-            if (chunk_err) {
+            // per-record tables hold sk_limits.max_records entries (OP_SCAN guards its own table, trim / mask have none)
+            bool too_many = false;
+            if (!chunk_err && nrec) {
+                if (IS_DEMUX) too_many = rec0 + nrec > p.max_records;
+                if (OP == OP_ADDBC && p.ext_stats[0] && p.ext_stats[0]->n_records) {
+                    const unsigned long long nb = p.ext_stats[0]->n_records, hi = rec0 + nrec - 1u;
+                    too_many = (hi < nb ? hi : nb - 1ull) >= p.max_records;
+                }
+            }
+            if (too_many) {
+                if (tid == 0) report_err(st, p.max_records, K_TOO_MANY);
+                nrec = 0;
+            } else if (chunk_err) {
                 if (tid == 0) report_err(st, rec0, chunk_err);
                 nrec = 0;
             }

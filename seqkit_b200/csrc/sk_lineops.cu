@@ -213,6 +213,7 @@ struct LParams {
     uint32_t head;         // '@' or '>'
     uint32_t x, y;         // trim: first, last; dual umi: first_bases; deinterleave: parity of the pass
     uint64_t rec_limit;
+    uint64_t max_records;  // entries of the per-record arrays below (sk_limits.max_records)
     uint32_t *out_len;     // [records]
     uint64_t *dst;         // [records] exclusive prefix of out_len
     uint8_t *out;
@@ -243,6 +244,10 @@ __device__ __forceinline__ uint32_t units_of(const LParams &p) {
     uint32_t u = (p.op == LOP_DEINTERLEAVE || p.op == LOP_DUALUMI) ? (nr + 1u) / 2u : nr;
     if ((uint64_t)u > p.rec_limit) u = (uint32_t)p.rec_limit;
     return u;
+}
+// more lines than the line table holds, or more records than the per-record arrays: the batch is refused (K_TOO_MANY)
+__device__ __forceinline__ bool line_refused(const LParams &p) {
+    return p.a.info->overflow || (p.op == LOP_INTERLEAVE && p.b.info->overflow) || (uint64_t)units_of(p) > p.max_records;
 }
 // header check of a record of stream a: 0 fine, else failure kind
 __device__ __forceinline__ unsigned head_kind(const LStream &S, LineRef h, uint32_t head) {
@@ -305,8 +310,8 @@ __device__ __forceinline__ bool utf8_ok(const uint8_t *s, uint32_t n) {
 
 // ---- plan --------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sk_line_plan_kernel(const LParams p) {
-    if (p.a.info->overflow || (p.op == LOP_INTERLEAVE && p.b.info->overflow)) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) report_err(p.st, 0, K_TOO_DENSE);
+    if (line_refused(p)) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) report_err(p.st, p.max_records, K_TOO_MANY);
         return;
     }
     const uint32_t nu = units_of(p);
@@ -426,7 +431,7 @@ __global__ void __launch_bounds__(256) sk_line_plan_kernel(const LParams p) {
                 uint32_t bl = 0;
                 const unsigned long long nb = p.bc_stats->n_records;
                 if (nb) {  // barcode of iteration i; the last one is reused once the barcode file is exhausted (:20-27)
-                    const RecRef rr = p.bc_tab[(unsigned long long)i < nb ? i : nb - 1ull];
+                    const RecRef rr = p.bc_tab[(unsigned long long)i < nb ? i : nb - 1ull];  // (i < units <= max_records = the table's size)
                     bl = rr.seq_len;
                     if (rr.flags & RR_LONG) kind = K_TOO_LONG;
                 }
@@ -467,6 +472,7 @@ __global__ void __launch_bounds__(256) sk_line_plan_kernel(const LParams p) {
 // statistics, second pass: every record's bytes against the representative of its slot (a 64-bit collision
 // between different barcodes is reported, never merged)
 __global__ void __launch_bounds__(256) sk_stats_verify_kernel(const LParams p) {
+    if (line_refused(p)) return;
     const uint32_t nu = units_of(p);
     const uint8_t *in = p.a.in;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nu; i += gridDim.x * blockDim.x) {
@@ -503,7 +509,7 @@ __global__ void __launch_bounds__(256) sk_stats_list_kernel(const unsigned long 
 
 // ---- finish: records before the first failure are the output -------------------------------------------
 __global__ void sk_line_finish_kernel(const LParams p, int which_out) {
-    const uint32_t nu = units_of(p);
+    const uint32_t nu = line_refused(p) ? 0u : units_of(p);
     uint32_t lim = nu;
     if (p.st->err_key) {
         const unsigned long long k = ~p.st->err_key;
@@ -533,6 +539,7 @@ __device__ __forceinline__ void put_lit(uint8_t *dst, unsigned long long at, con
 __global__ void __launch_bounds__(256) sk_line_emit_kernel(const LParams p) {
     const int lane = threadIdx.x & 31;
     const uint32_t wpb = blockDim.x >> 5, gw = blockIdx.x * wpb + (threadIdx.x >> 5), nw = gridDim.x * wpb;
+    if (line_refused(p)) return;
     uint32_t lim = units_of(p);
     if (p.st->err_key) {
         const unsigned long long rec = (~p.st->err_key) >> 8;
@@ -751,6 +758,7 @@ struct DParams {
     LStream a;             // the mate's stream
     uint32_t mate;         // 0: mate 1 (extract, match, decide, emit), 1: mate 2 (emit)
     uint64_t rec_limit;
+    uint64_t max_records;  // entries of assign[], groups[], out_len[] ... (sk_limits.max_records)
     int32_t fused_trim;    // >= 0: trim by quality with this threshold first
     SheetDev sheet;
     int16_t *assign;
@@ -826,8 +834,8 @@ __device__ __forceinline__ bool dm_utf8_fine(const LStream &S, LineRef h, LineRe
 }
 
 __global__ void __launch_bounds__(256) sk_dm_plan_kernel(const DParams p) {
-    if (p.a.info->overflow) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) report_err(p.st, 0, K_TOO_DENSE);
+    if (p.a.info->overflow || (uint64_t)dm_units(p) > p.max_records) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) report_err(p.st, p.max_records, K_TOO_MANY);
         return;
     }
     const uint32_t nu = dm_units(p);
@@ -990,7 +998,7 @@ __global__ void __launch_bounds__(256) sk_dm_plan_kernel(const DParams p) {
     }
 }
 __global__ void sk_dm_finish_kernel(const DParams p) {
-    const uint32_t nu = p.a.info->overflow ? 0u : dm_units(p);
+    const uint32_t nu = (p.a.info->overflow || (uint64_t)dm_units(p) > p.max_records) ? 0u : dm_units(p);
     unsigned long long bytes = 0;
     if (nu) bytes = p.dst[nu - 1] + p.out_len[nu - 1];
     p.st->n_records = nu;
@@ -1003,7 +1011,7 @@ __global__ void sk_dm_finish_kernel(const DParams p) {
 __global__ void __launch_bounds__(256) sk_dm_emit_kernel(const DParams p) {
     const int lane = threadIdx.x & 31;
     const uint32_t wpb = blockDim.x >> 5, gw = blockIdx.x * wpb + (threadIdx.x >> 5), nw = gridDim.x * wpb;
-    if (p.st->err_key || p.a.info->overflow) return;  // the host replays the batch up to the failing record
+    if (p.st->err_key || p.a.info->overflow) return;  // the host replays the batch up to the failing record (K_TOO_MANY included)
     const uint32_t nu = dm_units(p);
     const uint8_t *in = p.a.in;
     const uint8_t *lut = p.sheet.lut;
@@ -1066,8 +1074,8 @@ __global__ void __launch_bounds__(256) sk_dm_emit_kernel(const DParams p) {
 __global__ void __launch_bounds__(256) sk_recref_kernel(const LStream a, uint32_t lpr, uint32_t head_char, uint64_t rec_limit, uint32_t final_batch,
                                                         RecRef *out, uint4 *inline32, uint64_t cap, DevStats *st) {
     const uint32_t nl = a.info->n_lines;
-    if (a.info->overflow) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) report_err(st, 0, K_TOO_DENSE);
+    if (a.info->overflow) {  // more lines than the line table holds: more records than sk_limits.max_records
+        if (blockIdx.x == 0 && threadIdx.x == 0) report_err(st, cap, K_TOO_MANY);
         return;
     }
     uint32_t nrec = final_batch ? (nl + lpr - 1u) / lpr : (nl ? (nl - 1u) / lpr : 0u);
@@ -1146,6 +1154,7 @@ int launch_line_demux(int mate, const uint8_t *in, uint64_t n, uint64_t rec_limi
     p.a.in = in, p.a.n = n, p.a.starts = w.starts[mate], p.a.info = w.info[mate];
     p.mate = (uint32_t)mate;
     p.rec_limit = rec_limit ? rec_limit : ~0ull;
+    p.max_records = max_records;
     p.fused_trim = fused_trim;
     p.sheet = sheet;
     p.assign = assign, p.umi = umi, p.groups = groups, p.rows = rows;
@@ -1189,6 +1198,7 @@ int launch_lineop(int op, const uint8_t *in_a, uint64_t n_a, const uint8_t *in_b
     p.b.in = in_b, p.b.n = n_b, p.b.starts = w.starts[1], p.b.info = w.info[1];
     p.lpr = lpr, p.head = head, p.x = x, p.y = y;
     p.rec_limit = rec_limit ? rec_limit : ~0ull;
+    p.max_records = max_records;
     p.out_len = w.out_len, p.dst = w.dst, p.out = out0, p.out_cap = out_cap, p.st = st;
     p.bc_ref = w.bc_ref;
     p.bc_tab = bc_tab, p.bc_stats = bc_stats;

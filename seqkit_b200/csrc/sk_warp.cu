@@ -664,6 +664,13 @@ __global__ void __launch_bounds__(GeoW::NT, GeoW::MIN_CTAS) sk_warp_kernel(const
                     }
                 }
                 rec0 = (g0 + j0) >> 2;
+                // the per-record tables (assign, umi, groups; the barcode stream's record table) hold sk_limits.max_records
+                // entries: a batch with more records is refused before anything is written or read past them
+                if ((IS_DEMUX && rec0 + nrec > p.max_records) ||
+                    (OP == OP_ADDBC && bc_n && (rec0 + nrec - 1u < bc_n ? rec0 + nrec - 1u : bc_n - 1ull) >= p.max_records)) {
+                    if (lane == 0) report_err(st, p.max_records, K_TOO_MANY);
+                    break;
+                }
                 const uint64_t rec = rec0 + r;
                 if (!IS_DEMUX) {
                     // ---- trim / mask: one output stream in input order.  The tile's output bytes go through a

@@ -102,7 +102,8 @@ class Engine:
                  L.DATA_RECORD_TOO_LONG: "record beyond the operator's length limit",
                  L.DATA_CHUNK_TOO_DENSE: "more records per chunk than the operator's engine has slots for",
                  L.DATA_MIXED_FORMAT: "mixed FASTA/FASTQ records", L.DATA_OUT_OVERFLOW: "output capacity exceeded",
-                 L.DATA_TRUNCATED_FUSED: "fused trim+demux on a truncated header"}
+                 L.DATA_TRUNCATED_FUSED: "fused trim+demux on a truncated header",
+                 L.DATA_TOO_MANY_RECORDS: "more records in the batch than the context's max_records"}
         if res.status in names:
             raise Unsupported("%s (record %d)" % (names[res.status], res.err_record))
 

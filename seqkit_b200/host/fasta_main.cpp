@@ -629,6 +629,7 @@ static void refuse_status(const sk_result &r, uint64_t base) {
         case SK_DATA_MIXED_FORMAT: refuse("mixed FASTA/FASTQ records (record %llu)", rec);
         case SK_DATA_OUT_OVERFLOW: refuse("output capacity exceeded near record %llu", rec);
         case SK_DATA_TRUNCATED_FUSED: refuse("fused trim+demultiplex on a truncated header (record %llu)", rec);
+        case SK_DATA_TOO_MANY_RECORDS: refuse("more than %llu records in one batch", rec);  // (the batcher counts records: not reached)
         default: break;
     }
 }

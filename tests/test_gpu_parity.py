@@ -1,6 +1,7 @@
 """Parity tests proper (-m gpu): every operator goes through the C ABI (libseqkit_b200.so) and is
 compared byte for byte with the CPU oracle on the same seeded inputs, with the committed golden
 fixtures, and -- at sizes the oracle cannot reach -- through size-independent properties."""
+import os
 import random
 
 import pytest
@@ -483,3 +484,40 @@ def test_properties_at_bench_batch_size():
         c_hi, a_hi, _, _ = run(half, n - half, True)
         assert np.array_equal(c_lo + c_hi, c_fused)
         assert np.array_equal(np.concatenate([a_lo, a_hi]), a_fused)
+
+
+def test_more_records_than_the_context_was_sized_for(O):
+    """sk_limits.max_records sizes the per-record tables (assign, umi, groups, record tables, the line engine's arrays).
+    A batch with more records is refused with SK_DATA_TOO_MANY_RECORDS before anything is written past them -- on every
+    engine -- and the context stays usable; operators without per-record tables (trim / mask by quality on the chunk
+    engines) are not affected."""
+    from seqkit_b200 import Engine
+    from seqkit_b200.engine import Unsupported
+    sheet, bcs = G.make_sheet(3, 8, 8, umi=4)
+    r1, r2 = G.clean_pairs(5, 6000, bcs)
+    small1, small2 = G.clean_pairs(6, 900, bcs)
+    idx = G.index_reads(7, 6000, [b"ACGTACGT"])
+    with Engine(max_stream_bytes=8 << 20, max_records=1000, max_samples=16, line_ops=True) as eng:
+        for env_general in (False, True):
+            if env_general:
+                os.environ["SK_NO_WARP"] = "1"
+            try:
+                with Engine(max_stream_bytes=8 << 20, max_records=1000, max_samples=16, line_ops=True) as e2:
+                    for call in (lambda: e2.demultiplex(sheet, r1, r2), lambda: e2.demultiplex(sheet, r1, r2, fused_trim=20),
+                                 lambda: e2.add_barcode(r1, idx), lambda: e2.statistics(r1)):
+                        with pytest.raises(Unsupported, match="max_records"):
+                            call()
+                    _cmp_demux(e2.demultiplex(sheet, small1, small2), O.demultiplex(sheet, small1, small2), "after a refusal")
+                    check3(e2.trim_by_quality(r1, 20), O.trim_by_quality(r1, 20), "trim has no per-record table")
+                    idx1k = G.index_reads(8, 1000, [b"ACGTACGT"])
+                    check3(e2.add_barcode(small1, idx1k), O.add_barcode(small1, idx1k), "barcode file longer than the reads")
+                    with pytest.raises(Unsupported, match="max_records"):  # the limit holds for every stream of a batch
+                        e2.add_barcode(small1, idx)
+            finally:
+                os.environ.pop("SK_NO_WARP", None)
+        # the line engine's own arrays: dense records take it there
+        tiny = b"".join(b"@t BC:" + bcs[0][:8] + b"ACGT\n\n+\n\n" for _ in range(3000))
+        with pytest.raises(Unsupported, match="max_records"):
+            eng.demultiplex(sheet, tiny)
+        with pytest.raises(Unsupported, match="max_records"):
+            eng.add_barcode(tiny, idx)
