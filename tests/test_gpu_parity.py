@@ -515,6 +515,21 @@ def test_more_records_than_the_context_was_sized_for(O):
                         e2.add_barcode(small1, idx)
             finally:
                 os.environ.pop("SK_NO_WARP", None)
+        # what INTEGRATION.md tells a byte-filling batcher to do: the same batch again with rec_limit = err_record
+        import ctypes as C
+        from seqkit_b200 import _lib as L
+        eng.set_sheet(bcs)
+        eng.upload(L.IN_R1, r1)
+        eng.upload(L.IN_R2, r2)
+        opts = L.DemuxOpts(-1, 0, 0, 0, 0)
+        assert eng.lib.sk_demultiplex(eng.ctx, 0, C.byref(opts)) == 0
+        res = eng.wait()
+        assert res.status == L.DATA_TOO_MANY_RECORDS and res.err_record == 1000
+        opts.rec_limit = res.err_record
+        assert eng.lib.sk_demultiplex(eng.ctx, 0, C.byref(opts)) == 0
+        res = eng.wait()
+        lines1 = r1.split(b"\n")
+        assert res.status == 0 and res.n_records == 1000 and res.consumed[0] == len(b"\n".join(lines1[:4000])) + 1
         # the line engine's own arrays: dense records take it there
         tiny = b"".join(b"@t BC:" + bcs[0][:8] + b"ACGT\n\n+\n\n" for _ in range(3000))
         with pytest.raises(Unsupported, match="max_records"):
