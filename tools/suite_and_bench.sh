@@ -12,7 +12,7 @@ except Exception as e:
     print("no bench line:", e); raise SystemExit
 r = d["roofline"]
 print("value %.3g reads/s (with compaction %.3g)  step %.3f ms  D1 %.3f ms D2 %.3f ms compact %.3f ms  frac %.3f" % (
-    d["value"], d["value_with_compaction"], d["ms_per_step"], r["ms_per_launch"], r["other_kernel"]["ms_per_launch"],
+    d["value"], d["value_demux_passes_only"], d["ms_per_step"], r["ms_per_launch"], r["other_kernel"]["ms_per_launch"],
     d["value_breakdown"]["compact_ms"], r["frac"]))
 print("e2e", json.dumps(d["e2e"])[:400])
 print("files", json.dumps(d["e2e_files_gzip"])[:600])
