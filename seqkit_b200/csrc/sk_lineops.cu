@@ -856,7 +856,11 @@ __global__ void __launch_bounds__(256) sk_dm_plan_kernel(const DParams p) {
         const bool nl_ok = h.len && in[h.s + h.len - 1] == '\n';
         if (p.mate == 0) {
             if (!(h.len && in[h.s] == '@')) kind = K_BAD_HEADER;  // :118-120
-            if (!kind && p.a.info->high && !dm_utf8_fine(p.a, h, sq, pl, ql)) kind = K_NON_ASCII;
+            // bytes >= 0x80: plain demultiplex copies the three lines as they are, so valid UTF-8 is data like any other; the
+            // fused quality trim works char by char on bases and qualities, which therefore stay ASCII
+            if (!kind && p.a.info->high &&
+                !(fused ? dm_utf8_fine(p.a, h, sq, pl, ql) : utf8_ok(in + h.s, h.len + sq.len + pl.len + ql.len)))
+                kind = K_NON_ASCII;
             if (!kind && fused && !nl_ok) kind = K_TRUNC_FUSED;
             uint32_t st = 0, en = 0;
             RecRef ir0{0, 0, 0}, ir1{0, 0, 0};
@@ -971,7 +975,9 @@ __global__ void __launch_bounds__(256) sk_dm_plan_kernel(const DParams p) {
             // mate 2 of an assigned pair (:215-237)
             sample = (unsigned long long)i < n1 ? (int)p.assign[i] : -1;
             if (sample >= 0 && p.out) {
-                if (p.a.info->high && !dm_utf8_fine(p.a, h, sq, pl, ql)) kind = K_NON_ASCII;
+                if (p.a.info->high &&
+                    !(fused ? dm_utf8_fine(p.a, h, sq, pl, ql) : utf8_ok(in + h.s, h.len + sq.len + pl.len + ql.len)))
+                    kind = K_NON_ASCII;
                 if (!kind && fused && !nl_ok) kind = K_TRUNC_FUSED;
                 if (!kind) {
                     uint32_t st = 0, en = 0, alen, blen;

@@ -143,8 +143,12 @@ def test_dense_long_and_utf8_records_take_the_line_engine(eng, O):
     sheet, bcs = G.make_sheet(1, 4, 8)
     with pytest.raises(Unsupported):  # a record whose output does not fit a 16-bit group length
         eng.demultiplex(sheet, (b"@long BC:" + bcs[0] + b"\n" + b"A" * 40000 + b"\n+\n" + b"I" * 40000 + b"\n") * 3)
-    with pytest.raises(Unsupported):  # non-ASCII bases
-        eng.demultiplex(sheet, "@r BC:".encode() + bcs[0] + "\nACé\n+\nIIII\n".encode())
+    utf8_seq = "@r BC:".encode() + bcs[0] + "\nACé\n+\nIIII\n".encode()
+    _cmp_demux(eng.demultiplex(sheet, utf8_seq), O.demultiplex(sheet, utf8_seq), "plain demultiplex copies lines: UTF-8 anywhere")
+    with pytest.raises(Unsupported):  # the fused quality trim wants ASCII bases and qualities
+        eng.demultiplex(sheet, utf8_seq, fused_trim=20)
+    with pytest.raises(Unsupported):  # invalid UTF-8 (the reference: I/O error while reading from file)
+        eng.demultiplex(sheet, b"@r BC:" + bcs[0] + b"\nAC\xff\n+\nIII\n")
 
 
 def test_demultiplex_takes_the_line_engine_for_long_dense_and_utf8_records(eng, O):
