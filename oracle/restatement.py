@@ -356,3 +356,253 @@ def demultiplex(sheet: bytes, fastq_1: bytes, fastq_2: bytes | None = None, inde
         "total": total_reads,
         "identified": identified_reads,
     }
+
+
+# ---------------------------------------------------------------------------------------------------------
+# SURVEY.md section 8(f) operators (the rows around the hot path).  Same return shape as pyoracle.next_op:
+# (exit_code, stdout, stderr, second_output).
+# ---------------------------------------------------------------------------------------------------------
+def _slice(proc, s: str, a: int, b: int | None, what: str) -> str:
+    """&s[a..b] (b None: &s[a..]) with BYTE indices: panics when out of range or off a char boundary."""
+    raw = s.encode("utf-8")
+    if b is None:
+        b = len(raw)
+        if a > b:
+            proc.panic("byte index out of range " + what)
+    if a > b or b > len(raw):
+        proc.panic("byte index out of range " + what)
+    for k in (a, b):
+        if k < len(raw) and (raw[k] & 0xC0) == 0x80:
+            proc.panic("byte index is not a char boundary " + what)
+    return raw[a:b].decode("utf-8")
+
+
+def trim_fixed(data: bytes, remove_first: int, remove_last: int):
+    """fasta_trim.rs:24-47."""
+    P = _Proc()
+    f = _Reader(P, data)
+    try:
+        while True:
+            ok, line = f.read_line()  # :27
+            if not ok:
+                break
+            if not line.startswith(">") and not line.startswith("@"):  # :28-30
+                P.error("Invalid FASTA/FASTQ format encountered.")
+            _, seq = f.read_line()  # :32
+            seq_len = len(_trim_end(seq).encode("utf-8"))  # :33 (a byte length)
+            cut = remove_first + remove_last < seq_len
+            if cut:  # :34-38
+                P.out.append(line + _slice(P, seq, remove_first, seq_len - remove_last, "of seq (fasta_trim.rs:35)") + "\n")
+            else:
+                P.out.append(line + "\n")
+            if line.startswith("@"):  # :40-47
+                f.read_line()
+                _, qual = f.read_line()
+                if cut:
+                    P.out.append("+\n" + _slice(P, qual, remove_first, seq_len - remove_last, "of qual (fasta_trim.rs:44)") + "\n")
+                else:
+                    P.out.append("+\n\n")
+    except _Exit as e:
+        return e.code, _enc(P.out), _enc(P.err), b""
+    return 0, _enc(P.out), _enc(P.err), b""
+
+
+def check(data: bytes):
+    """fasta_check.rs:14-70."""
+    P = _Proc()
+    f = _Reader(P, data)
+    prev, lines_read = [], 0
+
+    def read():  # ReaderWithMemory::read_line (:30-38)
+        nonlocal lines_read
+        ok, line = f.read_line()
+        if not ok:
+            return False, line
+        prev.append(line)
+        if len(prev) > 10:
+            prev.pop(0)
+        lines_read += 1
+        return True, line
+
+    def history():  # :40-46
+        return "".join(l + "\n" for l in prev)
+
+    try:
+        while True:
+            ok, line = read()
+            if not ok:
+                break
+            if line.startswith(">"):
+                read()
+            elif line.startswith("@"):
+                read()
+                _, line = read()
+                if not line.startswith("+"):  # :58-61
+                    P.error("Missing quality header prefix '+' on line %d:\n%s\n" % (lines_read, history()))
+                read()
+            else:  # :64-67
+                P.error("Missing header prefix '>' or '@' on line %d:\n%s\n" % (lines_read, history()))
+    except _Exit as e:
+        return e.code, _enc(P.out), _enc(P.err), b""
+    return 0, _enc(P.out), _enc(P.err), b""
+
+
+_STAT_RE = re.compile(r" BC:[ACGTNacgtn]+")  # fasta_statistics.rs:17 (no '+')
+
+
+def statistics(data: bytes):
+    """fasta_statistics.rs:13-52.  Barcodes of equal count: barcode descending (the reference prints its HashMap's
+    order there; the C oracle and the product fix the same order)."""
+    P = _Proc()
+    f = _Reader(P, data)
+    total, seen = 0, {}
+    try:
+        while True:
+            ok, line = f.read_line()
+            if not ok:
+                break
+            m = _STAT_RE.search(line)  # :25-28
+            if m:
+                bc = line[m.start() + 4:m.end()]
+                seen[bc] = seen.get(bc, 0) + 1
+            if line.startswith("@"):  # :31-37
+                for _ in range(3):
+                    f.read_line()
+            elif line.startswith(">"):
+                f.read_line()
+            else:
+                P.error("Invalid FASTQ header:\n" + line)
+            total += 1
+        P.out.append("Total sequence records: %d\n" % total)  # :42
+        P.out.append("Most frequent sample barcodes:\n")      # :44
+        entries = sorted(seen.items(), key=lambda kv: (kv[1], kv[0].encode("utf-8")), reverse=True)
+        if len(entries) < 100:  # &entries[0..100] (:50)
+            P.panic("range end index 100 out of range for slice (fasta_statistics.rs:50)")
+        for bc, n in entries[:100]:
+            P.out.append("- %s: %d\n" % (bc, n))
+    except _Exit as e:
+        return e.code, _enc(P.out), _enc(P.err), b""
+    return 0, _enc(P.out), _enc(P.err), b""
+
+
+def interleave(a: bytes, b: bytes):
+    """fasta_interleave.rs:14-35."""
+    P = _Proc()
+    f1, f2 = _Reader(P, a), _Reader(P, b)
+    try:
+        while True:
+            ok, line = f1.read_line()
+            if not ok:
+                break
+            if line.startswith("@"):
+                lines = 4
+            elif line.startswith(">"):
+                lines = 2
+            else:
+                P.error("Line is not FASTA/FASTQ format: " + line)  # :19
+            P.out.append(line)
+            for _ in range(lines - 1):
+                P.out.append(f1.read_line()[1])
+            _, line = f2.read_line()
+            if (lines == 4 and not line.startswith("@")) or (lines == 2 and not line.startswith(">")):  # :26-29
+                P.error("Input files do not share a consistent format.")
+            P.out.append(line)
+            for _ in range(lines - 1):
+                P.out.append(f2.read_line()[1])
+    except _Exit as e:
+        return e.code, _enc(P.out), _enc(P.err), b""
+    return 0, _enc(P.out), _enc(P.err), b""
+
+
+def deinterleave(data: bytes):
+    """fasta_deinterleave.rs:14-39: stdout stays empty, the two outputs are <prefix>_1.fq.gz (first of the return's
+    outputs, in the stdout slot) and <prefix>_2.fq.gz (second output)."""
+    P = _Proc()
+    f = _Reader(P, data)
+    out2 = []
+    try:
+        while True:
+            ok, line = f.read_line()
+            if not ok:
+                break
+            if line.startswith("@"):
+                lines = 4
+            elif line.startswith(">"):
+                lines = 2
+            else:
+                P.error("Line is not FASTA/FASTQ format: " + line)  # :23
+            P.out.append(line)
+            for _ in range(lines - 1):
+                P.out.append(f.read_line()[1])
+            _, line = f.read_line()
+            if (lines == 4 and not line.startswith("@")) or (lines == 2 and not line.startswith(">")):  # :30-33
+                P.error("Interleaved FASTA records are not in consistent format.")
+            out2.append(line)
+            for _ in range(lines - 1):
+                out2.append(f.read_line()[1])
+    except _Exit as e:
+        return e.code, _enc(P.out), _enc(P.err), _enc(out2)
+    return 0, _enc(P.out), _enc(P.err), _enc(out2)
+
+
+def extract_dual_umi(data: bytes, first_bases: int):
+    """fasta_extract_dual_umi.rs:14-72."""
+    P = _Proc()
+    f = _Reader(P, data)
+    try:
+        while True:
+            ok, h1 = f.read_line()
+            if not ok:
+                break
+            if h1.startswith("@"):
+                fq = True
+            elif h1.startswith(">"):
+                fq = False
+            else:
+                P.error("Header is not valid FASTA/FASTQ:\n" + h1)  # :33
+            q1 = q2 = ""
+            if fq:  # :35-45
+                s1 = f.read_line()[1]
+                f.read_line()
+                q1 = f.read_line()[1]
+                h2 = f.read_line()[1]
+                s2 = f.read_line()[1]
+                f.read_line()
+                q2 = f.read_line()[1]
+                if not h2.startswith("@"):
+                    P.error("Invalid FASTQ record found in input file.")
+            else:  # :46-52
+                s1 = f.read_line()[1]
+                h2 = f.read_line()[1]
+                s2 = f.read_line()[1]
+                if not h2.startswith(">"):
+                    P.error("Invalid FASTA record found in input file.")
+            umi = _slice(P, s1, 0, first_bases, "of seq_1 (fasta_extract_dual_umi.rs:55)") + "+" + \
+                _slice(P, s2, 0, first_bases, "of seq_2 (fasta_extract_dual_umi.rs:57)")
+            if fq:  # :59-64
+                P.out.append("%s RX:%s\n%s+\n%s%s RX:%s\n%s+\n%s" % (
+                    _trim_end(h1), umi, _slice(P, s1, first_bases, None, "of seq_1"), _slice(P, q1, first_bases, None, "of qual_1"),
+                    _trim_end(h2), umi, _slice(P, s2, first_bases, None, "of seq_2"), _slice(P, q2, first_bases, None, "of qual_2")))
+            else:  # :65-69
+                P.out.append("%s RX:%s\n%s%s RX:%s\n%s" % (
+                    _trim_end(h1), umi, _slice(P, s1, first_bases, None, "of seq_1"),
+                    _trim_end(h2), umi, _slice(P, s2, first_bases, None, "of seq_2")))
+    except _Exit as e:
+        return e.code, _enc(P.out), _enc(P.err), b""
+    return 0, _enc(P.out), _enc(P.err), b""
+
+
+def next_op(op: int, a: bytes, b: bytes | None = None, x: int = 0, y: int = 0):
+    """Same numbering as pyoracle.next_op: 0 trim --first=x --last=y, 1 check, 2 statistics, 3 interleave(a, b),
+    4 deinterleave, 5 extract dual umi --first-bases=x."""
+    if op == 0:
+        return trim_fixed(a, x, y)
+    if op == 1:
+        return check(a)
+    if op == 2:
+        return statistics(a)
+    if op == 3:
+        return interleave(a, b or b"")
+    if op == 4:
+        return deinterleave(a)
+    return extract_dual_umi(a, x)

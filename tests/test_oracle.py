@@ -267,3 +267,41 @@ def test_next_row_operators_kats():
     assert O.next_op(3, a, b[:13])[:3] == (255, a[:13] + b[:13] + a[13:], b"ERROR: Input files do not share a consistent format.\n")
     assert O.next_op(5, il[1], x=1)[1] == (b"@a/1 RX:A+T\nC\n+\nI\n@a/2 RX:A+T\nT\n+\nI\n@b/1 RX:G+C\nG\n+\nI\n@b/2 RX:G+C\nC\n+\nI\n")
     assert O.next_op(5, a[:13], x=0)[:3] == (255, b"", b"ERROR: Invalid FASTQ record found in input file.\n")
+
+
+def test_fuzz_c_vs_python_next_rows():
+    """The SURVEY 8(f) operators -- trim --first/--last, check, statistics, interleave, deinterleave, extract dual umi -- in
+    the two independent restatements (C: fasta_oracle.c, Python: restatement.py) on clean, FASTA, interleaved, UTF-8 and
+    malformed inputs: same exit code, stdout, second output, and stderr unless the reference would panic."""
+    rng = random.Random(99)
+
+    def same(op, a, b=None, x=0, y=0, ctx=None):
+        c, p = O.next_op(op, a, b, x, y), R.next_op(op, a, b, x, y)
+        assert c[0] == p[0], (ctx, op, c[0], p[0], c[2][-200:], p[2][-200:])
+        assert c[1] == p[1] and c[3] == p[3], (ctx, op)
+        if c[0] != 101:
+            assert c[2] == p[2], (ctx, op, c[2][-200:], p[2][-200:])
+        return c
+
+    def fasta(seed, n):
+        r = random.Random(seed)
+        return b"".join(b">s%d d\n" % i + G.rand_seq(r, r.randrange(0, 60)) + b"\n" for i in range(n))
+
+    sheet, bcs = G.make_sheet(3, 150, 8)
+    for it in range(60):
+        n = rng.choice((0, 1, 2, 7, 60, 400))
+        p1, p2 = G.clean_pairs(rng.randrange(1 << 30), n, bcs)
+        inter = same(3, p1, p2, ctx="interleave")[1]
+        variants = [p1, G.nasty_fastq(rng.randrange(1 << 30), n), fasta(it, n), inter,
+                    "@ré 日\nACGTé\n+\nIIIIII\n".encode() * 3, p1 + b"oops\n" + p2, p1[: len(p1) // 2], b"\n", b"@a", b">x\nAC"]
+        for data in variants:
+            same(0, data, None, rng.randrange(0, 9), rng.randrange(0, 9), ctx="trim fixed")
+            same(1, data, ctx="check")
+            same(2, data, ctx="statistics")
+            same(3, data, rng.choice(variants), ctx="interleave")
+            same(4, data, ctx="deinterleave")
+            same(5, data, None, rng.randrange(0, 7), ctx="dual umi")
+    # statistics with at least 100 distinct barcodes, ties included (tie order: barcode descending, section 2 of DESIGN.md)
+    p1, _ = G.clean_pairs(5, 3000, bcs, p_sub=0.2)
+    code, out, err, _ = same(2, p1, ctx="statistics table")
+    assert code == 0 and out.count(b"\n") == 102
