@@ -176,3 +176,34 @@ def test_cli_interleave_deinterleave_dual_umi(oracle_bin, tmp_path):
     for args in (["interleave", "r1.fq"], ["deinterleave", "x"], ["check"], ["statistics"], ["extract", "dual", "umi"]):
         r = run(FASTA, args, str(tmp_path))
         assert r[0] == 255 and r[2].startswith(b"ERROR: Invalid arguments.\n"), args
+
+
+def test_golden_next_rows_through_the_binary(tmp_path):
+    """The committed fixtures of the SURVEY 8(f) operators (tests/golden/golden_next.json, from the Python restatement):
+    the `fasta` binary reproduces exit status, stdout, stderr and -- for deinterleave -- the two output files."""
+    import golden_util as GU
+    argv = {0: lambda c: ["trim", "--first=%d" % c["x"], "--last=%d" % c["y"], "a.fq"], 1: lambda c: ["check", "a.fq"],
+            2: lambda c: ["statistics", "a.fq"], 3: lambda c: ["interleave", "a.fq", "b.fq"],
+            4: lambda c: ["deinterleave", "a.fq", "out"], 5: lambda c: ["extract", "dual", "umi", "--first-bases=%d" % c["x"], "a.fq"]}
+    d = tmp_path / "g"
+    d.mkdir()
+    n = 0
+    for c in GU.next_cases():
+        for f in os.listdir(d):
+            os.remove(os.path.join(d, f))
+        (d / "a.fq").write_bytes(GU.next_blob(c["a"]))
+        if c["b"] is not None:
+            (d / "b.fq").write_bytes(GU.next_blob(c["b"]))
+        code, out, err = run(FASTA, argv[c["op"]](c), str(d))
+        ctx = (c["op"], c["tag"])
+        assert code == c["exit_code"], (ctx, code, err[-300:])
+        if c["op"] == 4:  # the restatement returns the two files in the stdout / second-output slots
+            got1 = gzip.decompress((d / "out_1.fq.gz").read_bytes())
+            got2 = gzip.decompress((d / "out_2.fq.gz").read_bytes())
+            assert out == b"" and got1 == GU.next_blob(c["stdout"]) and got2 == GU.next_blob(c["out2"]), ctx
+        else:
+            assert out == GU.next_blob(c["stdout"]), ctx
+        if code != 101:
+            assert err == GU.next_blob(c["stderr"]), (ctx, err[-300:])
+        n += 1
+    assert n > 90

@@ -305,3 +305,17 @@ def test_fuzz_c_vs_python_next_rows():
     p1, _ = G.clean_pairs(5, 3000, bcs, p_sub=0.2)
     code, out, err, _ = same(2, p1, ctx="statistics table")
     assert code == 0 and out.count(b"\n") == 102
+
+
+@pytest.mark.parametrize("impl", [O, R], ids=["c", "py"])
+def test_golden_next_rows(impl):
+    """Both restatements reproduce the committed fixtures of the SURVEY 8(f) operators (tests/golden/golden_next.json)."""
+    n = 0
+    for c in GU.next_cases():
+        got = impl.next_op(c["op"], GU.next_blob(c["a"]), GU.next_blob(c["b"]), c["x"], c["y"])
+        assert got[0] == c["exit_code"], c["tag"]
+        assert got[1] == GU.next_blob(c["stdout"]) and got[3] == GU.next_blob(c["out2"]), (c["op"], c["tag"])
+        if got[0] != 101:
+            assert got[2] == GU.next_blob(c["stderr"]), (c["op"], c["tag"])
+        n += 1
+    assert n > 90
